@@ -1,0 +1,469 @@
+// Device context, launch logic and the device-facing part of the C ABI.
+//
+// Replaces the orchestration inside one iteration of the reference's hot loops
+// (run.rs:122-143 SE, run.rs:249-274 PE): "batch of records in -> ordered batch of rewritten
+// records out".  Everything per-read happens in extract_kernel (bk_kernels.cuh); there is no CPU
+// implementation of it here.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+
+#include "../../include/barkit_b200.h"
+#include "bk_internal.h"
+#include "bk_kernels.cuh"
+
+namespace {
+
+constexpr int kSlots = 2;
+constexpr size_t kMaxDynSmem = 200 * 1024;    // leave room for >= 1 CTA/SM with static smem
+constexpr size_t kTargetDynSmem = 54 * 1024;  // aim for >= 4 resident tiles per SM
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct Scratch {  // [tile counter | DevResult | desc stream 0 | desc stream 1]
+  DevBuf buf;
+  uint32_t ntiles_cap = 0;
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf text[2], off[2], out[2];
+  Scratch scratch;
+  bk::DevResult* h_res = nullptr;  // pinned
+  uint32_t n = 0;
+  uint64_t out_cap[2] = {0, 0};
+  bool busy = false;
+  uint32_t launches = 0;
+};
+
+}  // namespace
+
+struct bk_ctx {
+  int device = 0;
+  uint32_t flags = 0;
+  bool paired = false;
+  bk_devprog prog[2];
+  int sm_count = 0;
+  Slot slot[kSlots];
+  std::string last_error;
+};
+
+namespace {
+
+bool cuda_ok(bk_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  ctx->last_error = std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e);
+  return false;
+}
+#define CK(call)                                  \
+  do {                                            \
+    if (!cuda_ok(ctx, (call), #call)) return BK_E_CUDA; \
+  } while (0)
+
+int ensure(bk_ctx* ctx, DevBuf* b, size_t bytes) {
+  if (b->cap >= bytes && b->p) return BK_OK;
+  if (b->p) CK(cudaFree(b->p));
+  b->p = nullptr;
+  b->cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMalloc(&b->p, want));
+  b->cap = want;
+  return BK_OK;
+}
+
+struct LaunchPlan {
+  uint32_t tile_recs;
+  uint32_t ntiles;
+  uint32_t in_cap[2], out_cap[2];
+  size_t smem;
+  int grid;
+};
+
+size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_t in_cap[2],
+                uint32_t out_cap[2]) {
+  size_t total = 0;
+  int nm = ctx->paired ? 2 : 1;
+  for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
+  for (int m = 0; m < nm; ++m) {
+    uint32_t growth = ctx->prog[m].present ? ctx->prog[m].hdr_growth : 0;
+    in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
+    out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
+    total += in_cap[m] + out_cap[m];
+  }
+  return total;
+}
+
+template <bool PAIRED>
+int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
+  uint32_t R = bk::kTileRecs;
+  // prefer several resident tiles per SM; never go below 8 records unless a tile would not fit
+  while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > kTargetDynSmem) --R;
+  while (R > 0 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > kMaxDynSmem) --R;
+  if (R == 0) {
+    ctx->last_error = "record too long for the on-chip staging buffer";
+    return BK_E_CAPACITY;
+  }
+  lp->tile_recs = R;
+  lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap);
+  lp->ntiles = (n + R - 1) / R;
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)lp->smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, 32, lp->smem));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)per_sm * ctx->sm_count;
+  if (grid > (long long)lp->ntiles) grid = lp->ntiles;
+  lp->grid = (int)std::max<long long>(grid, 1);
+  return BK_OK;
+}
+
+size_t scratch_bytes(uint32_t ntiles) { return 256 + (size_t)ntiles * 16; }
+
+// enqueue: scratch reset + extract kernel.  All pointers are device pointers.
+int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
+                    const bk_mate_in* in2, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
+                    int32_t* match1, int32_t* match2, uint32_t* launches) {
+  if (ctx->paired && !in2) { ctx->last_error = "paired context needs two mates"; return BK_E_ARG; }
+  if (!ctx->paired && in2) { ctx->last_error = "single-end context got two mates"; return BK_E_ARG; }
+  const bk_mate_in* in[2] = {in1, in2};
+  uint32_t maxrec[2] = {0, 0};
+  for (int m = 0; m < (ctx->paired ? 2 : 1); ++m) {
+    if (!in[m] || !in[m]->text || !in[m]->rec_off) { ctx->last_error = "null batch pointer"; return BK_E_ARG; }
+    if (in[m]->text_len >= (1ull << 32)) { ctx->last_error = "batch text must be < 4 GiB per mate"; return BK_E_CAPACITY; }
+    if (((uintptr_t)in[m]->text & 15) != 0) { ctx->last_error = "batch text must be 16-byte aligned"; return BK_E_ARG; }
+    if (in[m]->max_rec_bytes == 0) { ctx->last_error = "max_rec_bytes must be set"; return BK_E_ARG; }
+    maxrec[m] = in[m]->max_rec_bytes;
+  }
+  LaunchPlan lp;
+  int rc = ctx->paired ? plan_launch<true>(ctx, n, maxrec, &lp) : plan_launch<false>(ctx, n, maxrec, &lp);
+  if (rc != BK_OK) return rc;
+  rc = ensure(ctx, &s->scratch.buf, scratch_bytes(lp.ntiles));
+  if (rc != BK_OK) return rc;
+  uint8_t* sc = (uint8_t*)s->scratch.buf.p;
+  CK(cudaMemsetAsync(sc, 0, scratch_bytes(lp.ntiles), stream));
+
+  bk::KParams P;
+  memset(&P, 0, sizeof P);
+  P.prog[0] = ctx->prog[0];
+  P.prog[1] = ctx->prog[1];
+  for (int m = 0; m < (ctx->paired ? 2 : 1); ++m) {
+    P.text[m] = in[m]->text;
+    P.off[m] = in[m]->rec_off;
+    P.in_cap[m] = lp.in_cap[m];
+    P.out_cap[m] = lp.out_cap[m];
+  }
+  P.out[0] = out1; P.out[1] = out2;
+  P.cap[0] = cap1; P.cap[1] = cap2;
+  P.match[0] = match1; P.match[1] = match2;
+  P.tile_counter = (unsigned int*)sc;
+  P.result = (bk::DevResult*)(sc + 64);
+  P.desc[0] = (unsigned long long*)(sc + 256);
+  P.desc[1] = P.desc[0] + lp.ntiles;
+  P.n = n;
+  P.ntiles = lp.ntiles;
+  P.tile_recs = lp.tile_recs;
+  P.flags = ctx->flags;
+  if (n > 0) {
+    if (ctx->paired)
+      bk::extract_kernel<true><<<lp.grid, 32, lp.smem, stream>>>(P);
+    else
+      bk::extract_kernel<false><<<lp.grid, 32, lp.smem, stream>>>(P);
+    CK(cudaGetLastError());
+    if (launches) *launches += 1;
+  }
+  return BK_OK;
+}
+
+int check_dev_result(bk_ctx* ctx, const bk::DevResult& r) {
+  if (r.error & 2u) { ctx->last_error = "a record is longer than max_rec_bytes"; return BK_E_ARG; }
+  if (r.error & 1u) { ctx->last_error = "output buffer too small"; return BK_E_CAPACITY; }
+  return BK_OK;
+}
+
+void fill_result(bk_result* res, const bk::DevResult& r, uint32_t n, float ms, uint32_t launches) {
+  if (!res) return;
+  res->out1_len = r.out_len[0];
+  res->out2_len = r.out_len[1];
+  res->n_in = n;
+  res->n_out = r.n_out;
+  res->n_match1 = r.n_match[0];
+  res->n_match2 = r.n_match[1];
+  res->kernel_ms = ms;
+  res->launches = launches;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, uint32_t flags, int* status,
+                      char* err, size_t errcap) {
+  auto fail = [&](int st, const std::string& m) -> bk_ctx* {
+    if (status) *status = st;
+    if (err && errcap) {
+      size_t k = std::min(m.size(), errcap - 1);
+      memcpy(err, m.data(), k);
+      err[k] = 0;
+    }
+    return nullptr;
+  };
+  if (!p1 && !p2) return fail(BK_E_ARG, "at least one pattern is required");
+  if (!(flags & BK_FLAG_PAIRED) && (p2 || !p1))
+    return fail(BK_E_ARG, "single-end mode takes pattern1 only (run.rs:43)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(BK_E_CUDA, std::string("no CUDA device available (") +
+                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                               "); this library has no CPU path");
+  if (device < 0 || device >= ndev) return fail(BK_E_ARG, "device index out of range");
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(BK_E_CUDA, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(BK_E_CUDA, cudaGetErrorString(e));
+  if (prop.major < 10) return fail(BK_E_CUDA, "device is not sm_100 (Blackwell B200) class");
+  bk_ctx* ctx = new (std::nothrow) bk_ctx();
+  if (!ctx) return fail(BK_E_CAPACITY, "out of memory");
+  ctx->device = device;
+  ctx->flags = flags;
+  ctx->paired = (flags & BK_FLAG_PAIRED) != 0;
+  ctx->sm_count = prop.multiProcessorCount;
+  memset(ctx->prog, 0, sizeof ctx->prog);
+  if (p1) ctx->prog[0] = p1->prog.dev;
+  if (p2) ctx->prog[1] = p2->prog.dev;
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& s = ctx->slot[i];
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&s.ev0) != cudaSuccess || cudaEventCreate(&s.ev1) != cudaSuccess ||
+        cudaHostAlloc((void**)&s.h_res, sizeof(bk::DevResult), cudaHostAllocDefault) != cudaSuccess) {
+      std::string m = std::string("CUDA resource creation failed: ") + cudaGetErrorString(cudaGetLastError());
+      bk_ctx_destroy(ctx);
+      return fail(BK_E_CUDA, m);
+    }
+  }
+  if (status) *status = BK_OK;
+  if (err && errcap) err[0] = 0;
+  return ctx;
+}
+
+void bk_ctx_destroy(bk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& s = ctx->slot[i];
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    for (int m = 0; m < 2; ++m) {
+      if (s.text[m].p) cudaFree(s.text[m].p);
+      if (s.off[m].p) cudaFree(s.off[m].p);
+      if (s.out[m].p) cudaFree(s.out[m].p);
+    }
+    if (s.scratch.buf.p) cudaFree(s.scratch.buf.p);
+    if (s.h_res) cudaFreeHost(s.h_res);
+    if (s.ev0) cudaEventDestroy(s.ev0);
+    if (s.ev1) cudaEventDestroy(s.ev1);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  delete ctx;
+}
+
+const char* bk_last_error(const bk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+void* bk_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void bk_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int bk_ctx_nslots(const bk_ctx* ctx) { return ctx ? kSlots : 0; }
+
+uint64_t bk_out_bound(const bk_ctx* ctx, int mate, uint32_t n, uint64_t text_len) {
+  if (!ctx || mate < 1 || mate > 2) return 0;
+  const bk_devprog& pg = ctx->prog[mate - 1];
+  // out record <= in record + 1 (a final record without EOL gains one) + header growth
+  return text_len + (uint64_t)n * ((pg.present ? pg.hdr_growth : 0) + 1) + 16;
+}
+
+int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2) {
+  if (!ctx || slot < 0 || slot >= kSlots || !in1) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[slot];
+  if (s.busy) { ctx->last_error = "slot is busy: call bk_wait first"; return BK_E_ARG; }
+  const bk_mate_in* in[2] = {in1, in2};
+  const int nm = ctx->paired ? 2 : 1;
+  if (ctx->paired != (in2 != nullptr)) { ctx->last_error = "mate count does not match the context mode"; return BK_E_ARG; }
+  bk_mate_in dev[2];
+  for (int m = 0; m < nm; ++m) {
+    if (!in[m]->text || !in[m]->rec_off) { ctx->last_error = "null batch pointer"; return BK_E_ARG; }
+    if (in[m]->text_len >= (1ull << 32)) { ctx->last_error = "batch text must be < 4 GiB per mate"; return BK_E_CAPACITY; }
+    int rc;
+    if ((rc = ensure(ctx, &s.text[m], in[m]->text_len + 64)) != BK_OK) return rc;
+    if ((rc = ensure(ctx, &s.off[m], ((size_t)n + 1) * 4)) != BK_OK) return rc;
+    uint64_t ob = bk_out_bound(ctx, m + 1, n, in[m]->text_len);
+    if ((rc = ensure(ctx, &s.out[m], ob)) != BK_OK) return rc;
+    s.out_cap[m] = ob;
+    CK(cudaMemcpyAsync(s.text[m].p, in[m]->text, in[m]->text_len, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.off[m].p, in[m]->rec_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    dev[m] = *in[m];
+    dev[m].text = (const uint8_t*)s.text[m].p;
+    dev[m].rec_off = (const uint32_t*)s.off[m].p;
+  }
+  s.launches = 0;
+  CK(cudaEventRecord(s.ev0, s.stream));
+  int rc = enqueue_extract(ctx, &s, s.stream, n, &dev[0], ctx->paired ? &dev[1] : nullptr,
+                           (uint8_t*)s.out[0].p, s.out_cap[0], (uint8_t*)s.out[1].p, s.out_cap[1], nullptr,
+                           nullptr, &s.launches);
+  if (rc != BK_OK) return rc;
+  CK(cudaEventRecord(s.ev1, s.stream));
+  CK(cudaMemcpyAsync(s.h_res, (uint8_t*)s.scratch.buf.p + 64, sizeof(bk::DevResult), cudaMemcpyDeviceToHost,
+                     s.stream));
+  s.n = n;
+  s.busy = true;
+  return BK_OK;
+}
+
+int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2, bk_result* res) {
+  if (!ctx || slot < 0 || slot >= kSlots) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[slot];
+  if (!s.busy) { ctx->last_error = "slot has no batch in flight"; return BK_E_ARG; }
+  s.busy = false;
+  CK(cudaStreamSynchronize(s.stream));
+  bk::DevResult r = *s.h_res;
+  int rc = check_dev_result(ctx, r);
+  if (rc != BK_OK) return rc;
+  if (r.out_len[0] > cap1 || (ctx->paired && r.out_len[1] > cap2)) {
+    ctx->last_error = "output buffer too small";
+    return BK_E_CAPACITY;
+  }
+  if (r.out_len[0]) CK(cudaMemcpyAsync(out1, s.out[0].p, r.out_len[0], cudaMemcpyDeviceToHost, s.stream));
+  if (ctx->paired && r.out_len[1]) {
+    if (!out2) { ctx->last_error = "out2 is required in paired mode"; return BK_E_ARG; }
+    CK(cudaMemcpyAsync(out2, s.out[1].p, r.out_len[1], cudaMemcpyDeviceToHost, s.stream));
+  }
+  CK(cudaStreamSynchronize(s.stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+  fill_result(res, r, s.n, ms, s.launches);
+  return BK_OK;
+}
+
+int bk_extract_host(bk_ctx* ctx, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2, uint8_t* out1,
+                    uint64_t cap1, uint8_t* out2, uint64_t cap2, bk_result* res) {
+  int rc = bk_submit(ctx, 0, n, in1, in2);
+  if (rc != BK_OK) return rc;
+  return bk_wait(ctx, 0, out1, cap1, out2, cap2, res);
+}
+
+int bk_dev_alloc(bk_ctx* ctx, uint64_t bytes, void** dptr) {
+  if (!ctx || !dptr) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMalloc(dptr, bytes ? bytes : 16));
+  return BK_OK;
+}
+int bk_dev_free(bk_ctx* ctx, void* dptr) {
+  if (!ctx) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaFree(dptr));
+  return BK_OK;
+}
+int bk_memcpy_h2d(bk_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return BK_OK;
+}
+int bk_memcpy_d2h(bk_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return BK_OK;
+}
+
+int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk_mate_in* d_in2, uint8_t* d_out1,
+                      uint64_t cap1, uint8_t* d_out2, uint64_t cap2, int32_t* d_match1, int32_t* d_match2,
+                      int iters, bk_result* res) {
+  if (!ctx || !d_in1 || iters < 1) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[0];
+  if (s.busy) { ctx->last_error = "slot 0 is busy"; return BK_E_ARG; }
+  uint32_t launches = 0;
+  CK(cudaEventRecord(s.ev0, s.stream));
+  for (int it = 0; it < iters; ++it) {
+    int rc = enqueue_extract(ctx, &s, s.stream, n, d_in1, d_in2, d_out1, cap1, d_out2, cap2, d_match1, d_match2,
+                             &launches);
+    if (rc != BK_OK) return rc;
+  }
+  CK(cudaEventRecord(s.ev1, s.stream));
+  CK(cudaMemcpyAsync(s.h_res, (uint8_t*)s.scratch.buf.p + 64, sizeof(bk::DevResult), cudaMemcpyDeviceToHost,
+                     s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+  bk::DevResult r = *s.h_res;
+  fill_result(res, r, n, ms / iters, launches);
+  return check_dev_result(ctx, r);
+}
+
+int bk_reverse_complement(bk_ctx* ctx, const uint8_t* seq, size_t n, uint8_t* out) {
+  if (!ctx || (n && (!seq || !out))) return BK_E_ARG;
+  if (n == 0) return BK_OK;
+  if (n >= (1ull << 32)) return BK_E_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[0];
+  int rc;
+  if ((rc = ensure(ctx, &s.text[0], n + 64)) != BK_OK) return rc;
+  if ((rc = ensure(ctx, &s.out[0], n + 64)) != BK_OK) return rc;
+  CK(cudaMemcpyAsync(s.text[0].p, seq, n, cudaMemcpyHostToDevice, s.stream));
+  int blocks = (int)std::min<size_t>((n + 255) / 256, 1184);
+  bk::rc_kernel<<<blocks, 256, 0, s.stream>>>((const uint8_t*)s.text[0].p, (uint8_t*)s.out[0].p, (uint32_t)n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, s.out[0].p, n, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  return BK_OK;
+}
+
+int bk_generate_device(bk_ctx* ctx, const bk_syn_config* cfg, int mate, uint64_t seed, uint64_t first_idx,
+                       uint32_t n, uint8_t* d_text, uint32_t* d_rec_off) {
+  if (!ctx || !cfg || mate < 1 || mate > 2 || !d_text || !d_rec_off) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t rl = 23 + 2ull * cfg->read_len + 6;
+  if (rl * n >= (1ull << 32)) { ctx->last_error = "batch text must be < 4 GiB per mate"; return BK_E_CAPACITY; }
+  if (cfg->plant_len[mate - 1] > 32) { ctx->last_error = "planted literal longer than 32"; return BK_E_ARG; }
+  bk::GenParams G;
+  memset(&G, 0, sizeof G);
+  G.seed = seed;
+  G.first_idx = first_idx;
+  G.n = n;
+  G.read_len = cfg->read_len;
+  G.mate = (uint32_t)mate;
+  G.plant_len = cfg->plant_len[mate - 1];
+  G.plant_off = cfg->plant_off[mate - 1];
+  G.plant_jitter = cfg->plant_jitter[mate - 1];
+  memcpy(G.plant_lit, cfg->plant_lit[mate - 1], 32);
+  Slot& s = ctx->slot[0];
+  int threads = 128;
+  int blocks = (int)((n + threads - 1) / threads);
+  if (blocks < 1) blocks = 1;
+  bk::gen_kernel<<<blocks, threads, 0, s.stream>>>(G, d_text, d_rec_off);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s.stream));
+  return BK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// Internal C++ declarations shared by the host sources (not part of the ABI).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "bk_program.h"
+
+namespace bk {
+
+struct Span { size_t begin, end; };
+
+struct FuzzySpan {   // a `( alt | alt | ... )` group produced by the expansion, in expanded text
+  size_t begin, end;
+  std::string lit;   // upper-cased literal
+  size_t k;          // min(max_error, len)
+};
+
+struct Program {
+  bk_devprog dev;
+  std::string expanded;  // what the reference would pass to Regex::new (pattern.rs:182)
+};
+
+std::vector<Span> find_fuzzy_runs(const std::string& pattern);
+int sequence_with_errors(const std::string& seq, size_t k, std::vector<std::string>* out,
+                         std::string* err);
+int expand(const std::string& pattern, size_t k, std::string* out, std::vector<FuzzySpan>* spans,
+           std::string* err);
+int compile(const std::string& pattern, size_t max_error, Program* prog, std::string* err);
+
+}  // namespace bk
+
+struct bk_program {
+  bk::Program prog;
+};

@@ -1,0 +1,587 @@
+// Device code of the extract hot path (sm_100a).
+//
+// One launch = one batch = parse_se_reads / parse_pe_reads (run.rs:63-80, :163-195) + the writer's
+// framing (fastq.rs:259-263) for every record of the batch, single pass over HBM:
+//
+//   tile  = 32 consecutive records (pairs); one warp (= one CTA) owns a tile, lane i owns record i
+//   load  : the tile's contiguous FASTQ text range, one 1-D TMA bulk copy per mate -> shared memory
+//   parse : lane finds its record's four lines (SWAR newline scan in shared memory)
+//   match : lane evaluates the lowered program (bk_program.h) at ascending starts -> leftmost match
+//           (pattern.rs:225-230), optional reverse-complement retry (parse.rs:58-68)
+//   size  : output bytes per record, warp scan, decoupled look-back across tiles -> exact global
+//           output offset (ordered, gap-free: run.rs:79,194 + fastq.rs:265-271)
+//   emit  : lane assembles `@head NAME:seq:qual...\nseq'\n+\nqual'\n` (parse.rs:92-171) in a shared
+//           output tile laid out with the global offset's 16-byte phase
+//   store : aligned middle by TMA bulk store, ragged head/tail bytes by the lanes
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bk_program.h"
+
+namespace bk {
+
+constexpr int kTileRecs = 32;  // records per tile = lanes per warp
+
+struct DevResult {
+  unsigned long long out_len[2];
+  unsigned long long n_out;
+  unsigned long long n_match[2];
+  unsigned int error;  // bit0: output capacity exceeded, bit1: tile larger than staging buffer
+  unsigned int pad;
+};
+
+struct KParams {
+  bk_devprog prog[2];
+  const uint8_t* text[2];
+  const uint32_t* off[2];
+  uint8_t* out[2];
+  unsigned long long cap[2];
+  int32_t* match[2];
+  unsigned long long* desc[2];  // look-back descriptors, one per tile and output stream
+  unsigned int* tile_counter;
+  DevResult* result;
+  uint32_t n;
+  uint32_t ntiles;
+  uint32_t tile_recs;  // <= 32 (smaller when records are too long for the staging buffer)
+  uint32_t in_cap[2];  // shared-memory bytes for the staged input / assembled output per mate
+  uint32_t out_cap[2];
+  uint32_t flags;
+};
+
+constexpr unsigned long long kFlagAgg = 1ull << 62;
+constexpr unsigned long long kFlagPrefix = 2ull << 62;
+constexpr unsigned long long kValueMask = (1ull << 62) - 1;
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D TMA: global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// 1-D TMA: shared -> global
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- record parsing --------------------------------------------------------------------------------
+
+// First '\n' at or after `from` (shared-memory byte offsets), or `end` when there is none.
+__device__ __forceinline__ uint32_t find_nl(const uint8_t* s, uint32_t from, uint32_t end) {
+  uint32_t p = from & ~3u;
+  uint32_t w = *reinterpret_cast<const uint32_t*>(s + p) ^ 0x0A0A0A0Au;
+  uint32_t m = (w - 0x01010101u) & ~w & 0x80808080u;
+  m &= 0xFFFFFFFFu << ((from & 3u) * 8u);
+  while (m == 0) {
+    p += 4;
+    if (p >= end) return end;
+    w = *reinterpret_cast<const uint32_t*>(s + p) ^ 0x0A0A0A0Au;
+    m = (w - 0x01010101u) & ~w & 0x80808080u;
+  }
+  uint32_t pos = p + ((__ffs(m) - 1) >> 3);
+  return pos < end ? pos : end;
+}
+
+struct RecView {    // seq_io field definitions: lines without EOL and without a trailing CR
+  uint32_t head;    // first byte after '@'
+  uint32_t head_len;
+  uint32_t seq;
+  uint32_t seq_len;
+  uint32_t qual;
+  uint32_t qual_len;
+};
+
+__device__ __forceinline__ uint32_t strip_cr(const uint8_t* s, uint32_t b, uint32_t e) {
+  return (e > b && s[e - 1] == '\r') ? e - 1 : e;
+}
+
+__device__ __forceinline__ RecView parse_record(const uint8_t* s, uint32_t b, uint32_t e) {
+  RecView r;
+  uint32_t nl1 = find_nl(s, b, e);
+  r.head = b + 1;
+  r.head_len = strip_cr(s, b + 1, nl1 > b ? nl1 : b + 1) - (b + 1);
+  uint32_t sb = nl1 + 1 < e ? nl1 + 1 : e;
+  uint32_t nl2 = find_nl(s, sb, e);
+  r.seq = sb;
+  r.seq_len = strip_cr(s, sb, nl2) - sb;
+  uint32_t pb = nl2 + 1 < e ? nl2 + 1 : e;
+  uint32_t nl3 = find_nl(s, pb, e);
+  uint32_t qb = nl3 + 1 < e ? nl3 + 1 : e;
+  uint32_t nl4 = find_nl(s, qb, e);
+  r.qual = qb;
+  r.qual_len = strip_cr(s, qb, nl4) - qb;
+  return r;
+}
+
+// ---- matching --------------------------------------------------------------------------------------
+
+// parse.rs:12-32 TRANSLATION_TABLE
+__device__ __forceinline__ uint8_t complement(uint8_t c) {
+  switch (c) {
+    case 'A': return 'T';
+    case 'T': return 'A';
+    case 'G': return 'C';
+    case 'C': return 'G';
+    case 'R': case 'Y': case 'S': case 'W': case 'K': case 'M':
+    case 'B': case 'D': case 'H': case 'V': case 'N':
+      return c;
+    default: return 'A';
+  }
+}
+
+template <bool RC>
+__device__ __forceinline__ uint8_t fetch(const uint8_t* seq, uint32_t L, uint32_t j) {
+  if (RC) return complement(seq[L - 1 - j]);
+  return seq[j];
+}
+
+// all compare runs of the program at start s
+template <bool RC>
+__device__ __forceinline__ bool match_at(const bk_devprog& pg, const uint8_t* seq, uint32_t L, uint32_t s) {
+  for (uint32_t o = 0; o < pg.nops; ++o) {
+    const bk_op op = pg.ops[o];
+    uint32_t base = s + op.off;
+    if (op.kind == BK_OP_LIT) {
+      uint32_t mism = 0;
+      for (uint32_t i = 0; i < op.len; ++i) {
+        uint8_t c = fetch<RC>(seq, L, base + i);
+        if (c != pg.lit[op.idx + i]) {
+          // a wildcard slot is the regex `.`: any ASCII byte except '\n' (pattern.rs:10,71)
+          if (c >= 0x80 || c == '\n') return false;
+          if (++mism > op.k) return false;
+        }
+      }
+    } else {
+      const uint32_t w0 = pg.cls[op.idx][0], w1 = pg.cls[op.idx][1], w2 = pg.cls[op.idx][2],
+                     w3 = pg.cls[op.idx][3];
+      for (uint32_t i = 0; i < op.len; ++i) {
+        uint8_t c = fetch<RC>(seq, L, base + i);
+        uint32_t w = (c & 0x40) ? ((c & 0x20) ? w3 : w2) : ((c & 0x20) ? w1 : w0);
+        if (c >= 0x80 || !((w >> (c & 31)) & 1u)) return false;
+      }
+    }
+  }
+  return true;
+}
+
+// leftmost match start or -1
+template <bool RC>
+__device__ __forceinline__ int match_read(const bk_devprog& pg, const uint8_t* seq, uint32_t L) {
+  const uint32_t T = pg.total_len;
+  if (L < T) return -1;
+  uint32_t lo = 0, hi = L - T;
+  if (pg.anchor_start) hi = 0;
+  if (pg.anchor_end) {
+    if (pg.anchor_start && L != T) return -1;
+    lo = L - T;
+    hi = L - T;
+  }
+  for (uint32_t s = lo; s <= hi; ++s)
+    if (match_at<RC>(pg, seq, L, s)) return (int)s;
+  return -1;
+}
+
+// ---- emit ----------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t copy_run(uint8_t* dst, uint32_t d, const uint8_t* src, uint32_t s,
+                                             uint32_t len) {
+#pragma unroll 4
+  for (uint32_t i = 0; i < len; ++i) dst[d + i] = src[s + i];
+  return d + len;
+}
+
+// output bytes of a kept record
+__device__ __forceinline__ uint32_t out_bytes(const bk_devprog& pg, const RecView& r, int ms, bool trim) {
+  uint32_t sl = r.seq_len, ql = r.qual_len, g = 0;
+  if (ms >= 0) {
+    g = pg.hdr_growth;
+    if (trim) {
+      uint32_t T = pg.total_len;
+      sl -= T;  // match lies inside seq
+      uint32_t qs = (uint32_t)ms < ql ? (uint32_t)ms : ql;
+      uint32_t qe = (uint32_t)ms + T < ql ? (uint32_t)ms + T : ql;
+      ql -= (qe - qs);
+    }
+  }
+  return 1 + r.head_len + g + 1 + sl + 3 + ql + 1;
+}
+
+__device__ __forceinline__ void emit_record(const bk_devprog& pg, const uint8_t* in, const RecView& r,
+                                            int ms, bool trim, uint8_t* out, uint32_t d) {
+  out[d++] = '@';
+  d = copy_run(out, d, in, r.head, r.head_len);
+  if (ms >= 0) {
+    for (uint32_t c = 0; c < pg.ncaps; ++c) {  // pattern order (parse.rs:101)
+      const bk_cap cap = pg.caps[c];
+      out[d++] = ' ';
+      for (uint32_t i = 0; i < cap.name_len; ++i) out[d++] = cap.name[i];
+      out[d++] = ':';
+      d = copy_run(out, d, in, r.seq + ms + cap.off, cap.len);
+      out[d++] = ':';
+      // qual shorter than seq cannot come out of bk_tokenize; clamp keeps the kernel memory-safe
+      uint32_t qs = ms + cap.off < r.qual_len ? ms + cap.off : r.qual_len;
+      uint32_t qe = ms + cap.off + cap.len < r.qual_len ? ms + cap.off + cap.len : r.qual_len;
+      d = copy_run(out, d, in, r.qual + qs, qe - qs);
+      for (uint32_t i = qe - qs; i < cap.len; ++i) out[d++] = '!';
+    }
+  }
+  out[d++] = '\n';
+  if (ms >= 0 && trim) {  // parse.rs:138-148: cut [start0, end0) out of seq and qual
+    uint32_t T = pg.total_len;
+    d = copy_run(out, d, in, r.seq, ms);
+    d = copy_run(out, d, in, r.seq + ms + T, r.seq_len - ms - T);
+    out[d++] = '\n'; out[d++] = '+'; out[d++] = '\n';
+    uint32_t qs = (uint32_t)ms < r.qual_len ? (uint32_t)ms : r.qual_len;
+    uint32_t qe = (uint32_t)ms + T < r.qual_len ? (uint32_t)ms + T : r.qual_len;
+    d = copy_run(out, d, in, r.qual, qs);
+    d = copy_run(out, d, in, r.qual + qe, r.qual_len - qe);
+  } else {
+    d = copy_run(out, d, in, r.seq, r.seq_len);
+    out[d++] = '\n'; out[d++] = '+'; out[d++] = '\n';
+    d = copy_run(out, d, in, r.qual, r.qual_len);
+  }
+  out[d++] = '\n';
+}
+
+// ---- ordered compaction: decoupled look-back over tiles (one warp) -------------------------------------
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// exclusive prefix of this tile's aggregate over all earlier tiles; publishes aggregate and prefix
+__device__ __forceinline__ unsigned long long lookback(unsigned long long* desc, uint32_t tile,
+                                                       unsigned long long agg, int lane) {
+  if (tile == 0) {
+    if (lane == 0) st_relaxed_u64(desc, kFlagPrefix | agg);
+    return 0;
+  }
+  if (lane == 0) st_relaxed_u64(desc + tile, kFlagAgg | agg);
+  unsigned long long excl = 0;
+  int look = (int)tile - 1;
+  for (;;) {
+    int idx = look - lane;
+    unsigned long long d = kFlagPrefix;  // virtual tiles before 0: prefix 0
+    if (idx >= 0) {
+      do {
+        d = ld_relaxed_u64(desc + idx);
+      } while ((d >> 62) == 0);
+    }
+    unsigned pm = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+    unsigned long long v = d & kValueMask;
+    if (pm) {
+      int first = __ffs(pm) - 1;  // nearest predecessor holding an inclusive prefix
+      excl += warp_sum_u64(lane <= first ? v : 0ull);
+      break;
+    }
+    excl += warp_sum_u64(v);
+    look -= 32;
+  }
+  if (lane == 0) st_relaxed_u64(desc + tile, kFlagPrefix | (excl + agg));
+  return excl;
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+
+template <bool PAIRED>
+__global__ void __launch_bounds__(32) extract_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  constexpr int NM = PAIRED ? 2 : 1;
+  const int lane = threadIdx.x;
+  const bool trim = !(P.flags & 2u);
+  const bool rc = (P.flags & 4u) != 0;
+
+  uint8_t* in_s[2];
+  uint8_t* out_s[2];
+  in_s[0] = smem;
+  in_s[1] = in_s[0] + (PAIRED ? P.in_cap[0] : 0);
+  out_s[0] = in_s[1] + (PAIRED ? P.in_cap[1] : P.in_cap[0]);
+  out_s[1] = out_s[0] + P.out_cap[0];
+
+  if (lane == 0) mbar_init(&bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  uint32_t parity = 0;
+
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= P.ntiles) break;
+    const uint32_t r0 = tile * P.tile_recs;
+    const uint32_t nrec = min(P.tile_recs, P.n - r0);
+    const bool active = lane < (int)nrec;
+
+    // ---- load: one contiguous text range per mate -----------------------------------------------
+    uint32_t rb[2], re[2], gbase[2];
+    bool too_big = false;
+    uint32_t bytes[2];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      uint32_t o = active ? P.off[m][r0 + lane] : 0;
+      uint32_t oe = P.off[m][r0 + nrec];
+      uint32_t onext = __shfl_down_sync(0xffffffffu, o, 1);
+      if (lane == (int)nrec - 1) onext = oe;
+      uint32_t first = __shfl_sync(0xffffffffu, o, 0);
+      gbase[m] = first & ~15u;
+      uint32_t gend = (oe + 15u) & ~15u;
+      bytes[m] = gend - gbase[m];
+      if (bytes[m] > P.in_cap[m]) too_big = true;
+      rb[m] = o - gbase[m];
+      re[m] = onext - gbase[m];
+    }
+    if (too_big) {  // host sized the staging buffer from max_rec_bytes; a longer record is a caller bug
+      if (lane == 0) atomicOr(&P.result->error, 2u);
+#pragma unroll
+      for (int m = 0; m < NM; ++m) lookback(P.desc[m], tile, 0, lane);
+      continue;
+    }
+    if (lane == 0) {
+      uint32_t total = bytes[0] + (PAIRED ? bytes[1] : 0);
+      mbar_arrive_expect_tx(&bar, total);
+#pragma unroll
+      for (int m = 0; m < NM; ++m)
+        if (bytes[m]) bulk_g2s(in_s[m], P.text[m] + gbase[m], bytes[m], &bar);
+    }
+    mbar_wait(&bar, parity);
+    parity ^= 1;
+
+    // ---- parse + match (lane per record) --------------------------------------------------------
+    RecView rv[2];
+    int ms[2] = {-1, -1};
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      if (active) {
+        rv[m] = parse_record(in_s[m], rb[m], re[m]);
+        if (P.prog[m].present) {
+          const uint8_t* sq = in_s[m] + rv[m].seq;
+          ms[m] = match_read<false>(P.prog[m], sq, rv[m].seq_len);
+          if (ms[m] < 0 && rc) ms[m] = match_read<true>(P.prog[m], sq, rv[m].seq_len);  // parse.rs:61-66
+        }
+        if (P.match[m]) P.match[m][r0 + lane] = ms[m];
+      }
+    }
+    // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
+    const bool keep = active && (ms[0] >= 0 || (PAIRED && ms[1] >= 0));
+
+    // ---- size + scan + look-back ----------------------------------------------------------------
+    uint32_t olen[2], ooff[2];
+    unsigned long long gout[2];
+    uint32_t total[2];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      olen[m] = keep ? out_bytes(P.prog[m], rv[m], ms[m], trim) : 0;
+      uint32_t incl = olen[m];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      ooff[m] = incl - olen[m];
+      total[m] = __shfl_sync(0xffffffffu, incl, 31);
+    }
+#pragma unroll
+    for (int m = 0; m < NM; ++m) gout[m] = lookback(P.desc[m], tile, total[m], lane);
+
+    {  // statistics
+      unsigned kb = __ballot_sync(0xffffffffu, keep);
+      unsigned m1 = __ballot_sync(0xffffffffu, active && ms[0] >= 0);
+      unsigned m2 = __ballot_sync(0xffffffffu, active && ms[1] >= 0);
+      if (lane == 0) {
+        if (kb) atomicAdd(&P.result->n_out, (unsigned long long)__popc(kb));
+        if (m1) atomicAdd(&P.result->n_match[0], (unsigned long long)__popc(m1));
+        if (PAIRED && m2) atomicAdd(&P.result->n_match[1], (unsigned long long)__popc(m2));
+        if (tile == P.ntiles - 1) {
+          P.result->out_len[0] = gout[0] + total[0];
+          if (PAIRED) P.result->out_len[1] = gout[1] + total[1];
+        }
+      }
+    }
+
+    // ---- emit into the shared output tile (same 16-byte phase as the global destination) ---------
+    bool overflow = false;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      if (gout[m] + total[m] > P.cap[m]) overflow = true;
+    }
+    if (overflow) {
+      if (lane == 0) atomicOr(&P.result->error, 1u);
+      continue;
+    }
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      uint32_t phase = (uint32_t)(gout[m] & 15ull);
+      if (keep) emit_record(P.prog[m], in_s[m], rv[m], ms[m], trim, out_s[m], phase + ooff[m]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+
+    // ---- store ------------------------------------------------------------------------------------
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      if (total[m] == 0) continue;
+      const unsigned long long g0 = gout[m], g1 = gout[m] + total[m];
+      const uint32_t phase = (uint32_t)(g0 & 15ull);
+      unsigned long long a0 = (g0 + 15ull) & ~15ull;  // first aligned byte
+      unsigned long long a1 = g1 & ~15ull;            // end of aligned middle
+      uint8_t* gdst = P.out[m];
+      if (a0 >= a1) {  // no aligned middle: all bytes ragged
+        for (unsigned long long x = g0 + lane; x < g1; x += 32) gdst[x] = out_s[m][phase + (uint32_t)(x - g0)];
+      } else {
+        if (lane == 0) bulk_s2g(gdst + a0, out_s[m] + phase + (uint32_t)(a0 - g0), (uint32_t)(a1 - a0));
+        unsigned long long x = g0 + lane;
+        if (x < a0) gdst[x] = out_s[m][phase + (uint32_t)(x - g0)];
+        x = a1 + lane;
+        if (x < g1) gdst[x] = out_s[m][phase + (uint32_t)(x - g0)];
+      }
+    }
+    if (lane == 0) {
+      bulk_commit();
+      bulk_wait_read0();  // shared tile may be overwritten once the bulk engine has read it
+    }
+    __syncwarp();
+  }
+}
+
+// parse::get_reverse_complement as a stand-alone op (API parity; the extract kernel never materialises it)
+__global__ void rc_kernel(const uint8_t* in, uint8_t* out, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = complement(in[n - 1 - i]);
+}
+
+// ---- bksyn-v1 generator (bench / tests; oracle/bksyn.py is the normative statement) -------------------------
+
+struct GenParams {
+  uint64_t seed;
+  uint64_t first_idx;
+  uint32_t n;
+  uint32_t read_len;
+  uint32_t mate;
+  uint32_t plant_len;
+  uint32_t plant_off;
+  uint32_t plant_jitter;
+  char plant_lit[32];
+};
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ int acgt_index(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; }
+
+// one thread per record; records are fixed-size so offsets are arithmetic
+__global__ void gen_kernel(const __grid_constant__ GenParams G, uint8_t* text, uint32_t* rec_off) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t L = G.read_len;
+  const uint32_t rl = 23 + 2 * L + 6;
+  if (r == 0) rec_off[G.n] = G.n * rl;
+  if (r >= G.n) return;
+  rec_off[r] = r * rl;
+  uint8_t* p = text + (size_t)r * rl;
+  const uint64_t idx = G.first_idx + r;
+  const uint64_t ctr = 8 * idx + 4 * (G.mate - 1);
+  const uint64_t k0 = splitmix64(G.seed ^ splitmix64(ctr + 0));
+  const uint64_t k1 = splitmix64(G.seed ^ splitmix64(ctr + 1));
+  const uint64_t k2 = splitmix64(G.seed ^ splitmix64(ctr + 2));
+  const uint64_t k3 = splitmix64(G.seed ^ splitmix64(ctr + 3));
+  // head "bk.%012d %d:N:0:1"
+  *p++ = '@'; *p++ = 'b'; *p++ = 'k'; *p++ = '.';
+  {
+    uint64_t v = idx;
+    for (int d = 11; d >= 0; --d) { p[d] = (uint8_t)('0' + v % 10); v /= 10; }
+    p += 12;
+  }
+  *p++ = ' '; *p++ = (uint8_t)('0' + G.mate);
+  *p++ = ':'; *p++ = 'N'; *p++ = ':'; *p++ = '0'; *p++ = ':'; *p++ = '1';
+  *p++ = '\n';
+  uint8_t* bases = p;
+  uint64_t wb = 0, wn = 0, wq = 0;
+  for (uint32_t i = 0; i < L; ++i) {
+    if ((i & 31) == 0) wb = splitmix64(k0 + (i >> 5));
+    if ((i & 7) == 0) wn = splitmix64(k2 + (i >> 3));
+    uint8_t b = "ACGT"[(wb >> (2 * (i & 31))) & 3];
+    if (((wn >> (8 * (i & 7))) & 0xFF) == 0) b = 'N';
+    bases[i] = b;
+  }
+  if (G.plant_len) {
+    const uint32_t u = (uint32_t)(splitmix64(k3 + 0) & 0xFF);
+    if (u < 250) {
+      const uint32_t nsub = u < 205 ? 0 : u < 230 ? 1 : u < 243 ? 2 : 3;
+      const uint32_t pos0 = G.plant_off + (uint32_t)(splitmix64(k3 + 5) % (G.plant_jitter + 1));
+      const uint32_t ll = G.plant_len;
+      if (pos0 + ll <= L) {
+        for (uint32_t i = 0; i < ll; ++i) bases[pos0 + i] = (uint8_t)G.plant_lit[i];
+        uint32_t used[3];
+        for (uint32_t t = 0; t < nsub; ++t) {
+          const uint64_t w = splitmix64(k3 + 1 + t);
+          uint32_t q = (uint32_t)(w % ll);
+          for (bool again = true; again;) {
+            again = false;
+            for (uint32_t v = 0; v < t; ++v)
+              if (used[v] == q) { q = (q + 1) % ll; again = true; }
+          }
+          used[t] = q;
+          const int orig = acgt_index(G.plant_lit[q]);
+          bases[pos0 + q] = "ACGT"[(orig + 1 + (int)((w >> 8) % 3)) % 4];
+        }
+      }
+    }
+  }
+  p += L;
+  *p++ = '\n'; *p++ = '+'; *p++ = '\n';
+  for (uint32_t i = 0; i < L; ++i) {
+    if ((i & 7) == 0) wq = splitmix64(k1 + (i >> 3));
+    p[i] = (uint8_t)(33 + ((wq >> (8 * (i & 7))) & 0xFF) % 41);
+  }
+  p[L] = '\n';
+}
+
+}  // namespace bk

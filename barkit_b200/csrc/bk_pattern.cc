@@ -1,0 +1,606 @@
+// Pattern front end: the host-side replacement of barkit-extract/src/pattern.rs.
+//
+//   find_fuzzy_runs      <- ADAPTER_PATTERN_REGEX            pattern.rs:11  (fancy-regex find_iter :97)
+//   sequence_with_errors <- get_sequence_with_errors        pattern.rs:40-79
+//   expand               <- get_pattern_with_errors         pattern.rs:93-109
+//   compile              <- BarcodeRegex::new               pattern.rs:179-188 (+ :191-205, :137-144)
+//
+// The reference hands the expanded text to `regex::bytes::Regex`.  We instead lower it to a
+// fixed-offset matching program (bk_program.h).  The lowering accepts the subset of the regex
+// syntax whose matches have one possible length; everything else is refused with
+// BK_E_UNSUPPORTED instead of being approximated.
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/barkit_b200.h"
+#include "bk_internal.h"
+
+namespace bk {
+
+static inline bool is_word(unsigned char c) {
+  return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+}
+static inline bool in_fuzzy_alphabet(unsigned char c) {
+  // pattern.rs:11  [atgcryswkmbdhvn]
+  switch (c) {
+    case 'a': case 't': case 'g': case 'c': case 'r': case 'y': case 's': case 'w':
+    case 'k': case 'm': case 'b': case 'd': case 'h': case 'v': case 'n':
+      return true;
+    default:
+      return false;
+  }
+}
+static inline char ascii_upper(char c) { return (c >= 'a' && c <= 'z') ? char(c - 32) : c; }
+
+// (?<!\[)\b[atgcryswkmbdhvn]+\b(?!\])  -- non-overlapping leftmost matches.
+// A candidate start i needs: s[i] in the alphabet, s[i-1] not a word character (\b) and not '['.
+// The run is greedy; any shorter end lands between two word characters, where \b cannot hold, so
+// the only end that can succeed is the end of the maximal run, and it needs a non-word character
+// (or the end of the pattern) that is not ']'.  After a failed start the rest of the run cannot
+// start a match either (its left neighbour is a word character).
+std::vector<Span> find_fuzzy_runs(const std::string& s) {
+  std::vector<Span> out;
+  size_t n = s.size(), i = 0;
+  while (i < n) {
+    unsigned char c = s[i];
+    if (!in_fuzzy_alphabet(c)) { ++i; continue; }
+    size_t j = i;
+    while (j < n && in_fuzzy_alphabet((unsigned char)s[j])) ++j;
+    bool left_ok = (i == 0) || (!is_word((unsigned char)s[i - 1]) && s[i - 1] != '[');
+    bool right_ok = (j == n) || (!is_word((unsigned char)s[j]) && s[j] != ']');
+    if (left_ok && right_ok) out.push_back({i, j});
+    // skip the rest of this word: no position inside it has a \b on its left
+    while (j < n && is_word((unsigned char)s[j])) ++j;
+    i = j;
+  }
+  return out;
+}
+
+static const size_t kMaxExpandBytes = size_t(256) << 20;
+
+int sequence_with_errors(const std::string& seq, size_t k, std::vector<std::string>* out,
+                         std::string* err) {
+  out->clear();
+  size_t n = seq.size();
+  std::string upper(seq);
+  for (auto& ch : upper) ch = ascii_upper(ch);
+  if (k == 0) { out->push_back(upper); return BK_OK; }          // pattern.rs:41-43
+  if (n == 0) return BK_OK;                                      // pattern.rs:45-47
+  if (k >= n) { out->push_back(std::string(n, '.')); return BK_OK; }  // pattern.rs:49-51
+  if (n > 64) {  // pattern.rs:56-58: the shift amount underflows, checked_shr -> None
+    *err = "Failed to choose permutation mask";
+    return BK_E_PATTERN;
+  }
+  // pattern.rs:64-77 keeps masks with popcount n-k in ascending order; bit i set = char i kept.
+  // Count first so that absurd sizes are refused instead of exhausting memory.
+  long double count = 1;
+  for (size_t i = 0; i < k; ++i) count = count * (long double)(n - i) / (long double)(i + 1);
+  if (count * (long double)(n + 1) > (long double)kMaxExpandBytes) {
+    *err = "fuzzy expansion too large";
+    return BK_E_CAPACITY;
+  }
+  size_t keep = n - k;
+  unsigned __int128 mask = (((unsigned __int128)1) << keep) - 1;
+  unsigned __int128 limit = ((unsigned __int128)1) << n;
+  while (mask < limit) {
+    std::string s(n, '.');
+    for (size_t i = 0; i < n; ++i)
+      if ((mask >> i) & 1) s[i] = upper[i];
+    out->push_back(s);
+    unsigned __int128 c = mask & (~mask + 1);  // Gosper: next mask with the same popcount
+    unsigned __int128 r = mask + c;
+    mask = (((r ^ mask) >> 2) / c) | r;
+  }
+  return BK_OK;
+}
+
+int expand(const std::string& pattern, size_t k, std::string* out, std::vector<FuzzySpan>* spans,
+           std::string* err) {
+  for (unsigned char c : pattern)
+    if (c >= 0x80) {
+      *err = "non-ASCII pattern characters are not supported";
+      return BK_E_UNSUPPORTED;
+    }
+  out->clear();
+  if (spans) spans->clear();
+  size_t last = 0;
+  for (const Span& m : find_fuzzy_runs(pattern)) {
+    out->append(pattern, last, m.begin - last);
+    std::vector<std::string> alts;
+    std::string lit = pattern.substr(m.begin, m.end - m.begin);
+    int rc = sequence_with_errors(lit, k, &alts, err);
+    if (rc != BK_OK) return rc;
+    size_t b = out->size();
+    out->push_back('(');
+    for (size_t i = 0; i < alts.size(); ++i) {
+      if (i) out->push_back('|');
+      out->append(alts[i]);
+    }
+    out->push_back(')');
+    if (spans) {
+      FuzzySpan fs;
+      fs.begin = b;
+      fs.end = out->size();
+      fs.lit = lit;
+      for (auto& ch : fs.lit) ch = ascii_upper(ch);
+      fs.k = k < lit.size() ? k : lit.size();
+      spans->push_back(fs);
+    }
+    last = m.end;
+  }
+  out->append(pattern, last, std::string::npos);
+  return BK_OK;
+}
+
+// ---- lowering ---------------------------------------------------------------------------------
+
+namespace {
+
+struct Pos {          // one byte position of a match
+  uint8_t kind;       // 0 class, 1 literal
+  uint8_t byte;       // literal byte
+  int cls;            // class index
+  int group;          // fuzzy group id (-1: strict)
+};
+
+struct Class128 {
+  uint32_t w[4];
+  bool operator==(const Class128& o) const { return !memcmp(w, o.w, sizeof w); }
+};
+
+struct Lowering {
+  const std::string& s;                  // expanded pattern
+  const std::vector<FuzzySpan>& spans;
+  std::vector<Pos> pos;
+  std::vector<Class128> classes;
+  std::vector<size_t> group_k;           // per fuzzy group
+  struct CapRec { std::string name; size_t off, len; };
+  std::vector<CapRec> caps;
+  std::string err;
+  int status = BK_OK;
+
+  Lowering(const std::string& s_, const std::vector<FuzzySpan>& sp) : s(s_), spans(sp) {}
+
+  bool fail(int st, const std::string& m) {
+    if (status == BK_OK) { status = st; err = m; }
+    return false;
+  }
+  bool unsupported(const std::string& what) {
+    return fail(BK_E_UNSUPPORTED,
+                "unsupported pattern construct (" + what + "): this build lowers only fixed-length "
+                "patterns: ^ $ literals [classes] . {n} (groups) (?P<UMI|CB|SB>...) and lowercase "
+                "fuzzy runs");
+  }
+  bool regex_error(const std::string& m) { return fail(BK_E_PATTERN, "Regex error: " + m); }
+
+  const FuzzySpan* span_at(size_t i) const {
+    for (const auto& f : spans)
+      if (f.begin == i) return &f;
+    return nullptr;
+  }
+  bool inside_span(size_t i) const {
+    for (const auto& f : spans)
+      if (i > f.begin && i < f.end) return true;
+    return false;
+  }
+
+  int class_index(const Class128& c) {
+    for (size_t i = 0; i < classes.size(); ++i)
+      if (classes[i] == c) return (int)i;
+    classes.push_back(c);
+    return (int)classes.size() - 1;
+  }
+
+  // Parses `{n}` at s[i] if present.  Returns false on error.  *rep = -1 when there is no
+  // repetition operator at i.
+  bool parse_repeat(size_t& i, long* rep) {
+    *rep = -1;
+    if (i >= s.size()) return true;
+    char c = s[i];
+    if (c == '?' || c == '*' || c == '+') return unsupported(std::string("repetition operator ") + c);
+    if (c != '{') return true;
+    size_t j = i + 1;
+    long v = 0;
+    size_t digits = 0;
+    while (j < s.size() && s[j] >= '0' && s[j] <= '9') {
+      v = v * 10 + (s[j] - '0');
+      if (v > BK_MAX_TOTAL_LEN) return unsupported("repetition count too large");
+      ++j; ++digits;
+    }
+    if (digits == 0) return regex_error("repetition quantifier expects a valid decimal");
+    if (j < s.size() && s[j] == ',') return unsupported("{m,n} variable repetition");
+    if (j >= s.size() || s[j] != '}') return regex_error("unclosed counted repetition");
+    i = j + 1;
+    if (i < s.size() && (s[i] == '?' || s[i] == '*' || s[i] == '+' || s[i] == '{'))
+      return unsupported("stacked repetition / lazy quantifier");
+    *rep = v;
+    return true;
+  }
+
+  bool parse_class(size_t& i, Class128* out) {
+    // s[i] == '['
+    size_t j = i + 1;
+    bool neg = false;
+    if (j < s.size() && s[j] == '^') { neg = true; ++j; }
+    Class128 c{{0, 0, 0, 0}};
+    auto set = [&](unsigned char b) { c.w[b >> 5] |= 1u << (b & 31); };
+    bool first = true;
+    for (;;) {
+      if (j >= s.size()) return regex_error("unclosed character class");
+      if (inside_span(j) || span_at(j)) return unsupported("lowercase run inside a character class");
+      unsigned char ch = s[j];
+      if (ch == ']' && !first) { ++j; break; }
+      if (ch == '\\') return unsupported("escape in character class");
+      if (ch == '[') return unsupported("nested / POSIX character class");
+      if (ch == '&' && j + 1 < s.size() && s[j + 1] == '&') return unsupported("class set operation");
+      if (ch == '~' && j + 1 < s.size() && s[j + 1] == '~') return unsupported("class set operation");
+      if (ch == '-' && j + 1 < s.size() && s[j + 1] == '-') return unsupported("class set operation");
+      if (ch == ']' && first) { /* literal ']' as first member */ }
+      first = false;
+      if (j + 2 < s.size() && s[j + 1] == '-' && s[j + 2] != ']') {
+        unsigned char hi = s[j + 2];
+        if (hi == '\\' || hi == '[') return unsupported("escape in character class range");
+        if (hi < ch) return regex_error("invalid character class range");
+        for (unsigned v = ch; v <= hi; ++v) set((unsigned char)v);
+        j += 3;
+      } else {
+        set(ch);
+        ++j;
+      }
+    }
+    if (neg)
+      for (int w = 0; w < 4; ++w) c.w[w] = ~c.w[w];
+    *out = c;
+    i = j;
+    return true;
+  }
+
+  // Parses a sequence until ')' (when depth > 0) or end of pattern; appends positions.
+  // has_named is set when a named capture was opened inside.
+  bool parse_seq(size_t& i, int depth, bool* has_named) {
+    while (i < s.size()) {
+      char c = s[i];
+      if (c == ')') {
+        if (depth == 0) return regex_error("unopened group");
+        return true;
+      }
+      size_t item_begin = pos.size();
+      bool item_named = false;
+      if (const FuzzySpan* f = span_at(i)) {
+        int g = (int)group_k.size();
+        group_k.push_back(f->k);
+        for (unsigned char b : f->lit) pos.push_back(Pos{1, b, -1, g});
+        i = f->end;
+      } else if (c == '(') {
+        ++i;
+        std::string name;
+        bool named = false;
+        if (i < s.size() && s[i] == '?') {
+          if (inside_span(i + 1) || span_at(i + 1)) return unsupported("lowercase run inside group flags");
+          if (s.compare(i, 3, "?P<") == 0) { named = true; i += 3; }
+          else if (s.compare(i, 2, "?<") == 0 && i + 2 < s.size() && s[i + 2] != '=' && s[i + 2] != '!') { named = true; i += 2; }
+          else if (s.compare(i, 2, "?:") == 0) { i += 2; }
+          else return unsupported("group flags / look-around");
+          if (named) {
+            size_t e = i;
+            while (e < s.size() && s[e] != '>') {
+              if (inside_span(e) || span_at(e)) return regex_error("invalid capture group character");
+              unsigned char ch = s[e];
+              if (!(is_word(ch) || ch == '.' || ch == '[' || ch == ']')) return regex_error("invalid capture group character");
+              ++e;
+            }
+            if (e >= s.size()) return regex_error("unclosed capture group name");
+            name = s.substr(i, e - i);
+            if (name.empty()) return regex_error("empty capture group name");
+            if (name[0] >= '0' && name[0] <= '9') return regex_error("invalid capture group character");
+            for (auto& cr : caps)
+              if (cr.name == name) return regex_error("duplicate capture group name");
+            i = e + 1;
+          }
+        }
+        size_t cap_slot = 0;
+        if (named) {
+          cap_slot = caps.size();
+          caps.push_back({name, pos.size(), 0});  // pattern order = order of opening parens
+          item_named = true;
+        }
+        bool inner_named = false;
+        if (!parse_seq(i, depth + 1, &inner_named)) return false;
+        if (i >= s.size() || s[i] != ')') return regex_error("unclosed group");
+        ++i;
+        if (named) caps[cap_slot].len = pos.size() - caps[cap_slot].off;
+        item_named = item_named || inner_named;
+      } else if (c == '[') {
+        Class128 cl;
+        if (!parse_class(i, &cl)) return false;
+        pos.push_back(Pos{0, 0, class_index(cl), -1});
+      } else if (c == '.') {
+        Class128 cl{{~0u, ~0u, ~0u, ~0u}};
+        cl.w[0] &= ~(1u << '\n');  // `.` = any character except \n (non-`s` mode)
+        pos.push_back(Pos{0, 0, class_index(cl), -1});
+        ++i;
+      } else if (c == '\\') {
+        return unsupported("escape sequence");
+      } else if (c == '|') {
+        return unsupported("alternation");
+      } else if (c == '^' || c == '$') {
+        return unsupported("anchor inside the pattern");
+      } else if (c == '?' || c == '*' || c == '+') {
+        return regex_error("repetition operator missing expression");
+      } else if (c == '{') {
+        return regex_error("repetition operator missing expression");
+      } else if (c == ']' || c == '}') {
+        return unsupported(std::string("unbalanced ") + c);
+      } else {
+        pos.push_back(Pos{1, (uint8_t)c, -1, -1});
+        ++i;
+      }
+      if (item_named && has_named) *has_named = true;
+      long rep;
+      if (!parse_repeat(i, &rep)) return false;
+      if (rep >= 0 && rep != 1) {
+        if (item_named) return unsupported("repetition of a named capture group");
+        std::vector<Pos> item(pos.begin() + item_begin, pos.end());
+        pos.resize(item_begin);
+        // every copy of a fuzzy group gets its own mismatch budget (the group is re-entered)
+        for (long r = 0; r < rep; ++r) {
+          std::vector<int> remap;
+          for (Pos p : item) {
+            if (p.group >= 0) {
+              int g = p.group;
+              if (r > 0) {
+                bool found = false;
+                for (size_t q = 0; q + 1 < remap.size(); q += 2)
+                  if (remap[q] == g) { g = remap[q + 1]; found = true; break; }
+                if (!found) {
+                  remap.push_back(p.group);
+                  group_k.push_back(group_k[p.group]);
+                  g = (int)group_k.size() - 1;
+                  remap.push_back(g);
+                }
+              }
+              p.group = g;
+            }
+            pos.push_back(p);
+            if (pos.size() > BK_MAX_TOTAL_LEN) return unsupported("pattern longer than 4096 bytes");
+          }
+        }
+      }
+      if (pos.size() > BK_MAX_TOTAL_LEN) return unsupported("pattern longer than 4096 bytes");
+    }
+    if (depth > 0) return regex_error("unclosed group");
+    return true;
+  }
+};
+
+}  // namespace
+
+int compile(const std::string& pattern, size_t max_error, Program* prog, std::string* err) {
+  std::vector<FuzzySpan> spans;
+  std::string expanded;
+  int rc = expand(pattern, max_error, &expanded, &spans, err);
+  if (rc != BK_OK) return rc;
+  prog->expanded = expanded;
+
+  // anchors: only as the very first / very last character
+  size_t b = 0, e = expanded.size();
+  bool a_start = false, a_end = false;
+  if (b < e && expanded[b] == '^') { a_start = true; ++b; }
+  if (e > b && expanded[e - 1] == '$') { a_end = true; --e; }
+  std::string body = expanded.substr(b, e - b);
+  for (auto& f : spans) {
+    if (f.begin < b || f.end > e) { *err = "internal: fuzzy span outside body"; return BK_E_PATTERN; }
+    f.begin -= b;
+    f.end -= b;
+  }
+
+  Lowering lw(body, spans);
+  size_t i = 0;
+  bool named = false;
+  if (!lw.parse_seq(i, 0, &named)) {
+    *err = lw.err;
+    return lw.status;
+  }
+  // pattern.rs:191-205: names are validated in group order, then emptiness is an error
+  for (auto& c : lw.caps) {
+    if (c.name != "UMI" && c.name != "CB" && c.name != "SB") {
+      *err = "Provided unexpected barcode capture group " + c.name;  // error.rs:13-14
+      return BK_E_PATTERN;
+    }
+  }
+  if (lw.caps.empty()) {
+    *err = expanded + " capture group not found in your pattern";  // error.rs:11-12, pattern.rs:202
+    return BK_E_PATTERN;
+  }
+  if (lw.classes.size() > BK_MAX_CLASSES) {
+    *err = "unsupported pattern: more than 8 distinct character classes";
+    return BK_E_UNSUPPORTED;
+  }
+
+  bk_devprog& d = prog->dev;
+  memset(&d, 0, sizeof d);
+  d.present = 1;
+  d.anchor_start = a_start;
+  d.anchor_end = a_end;
+  d.total_len = (uint32_t)lw.pos.size();
+  for (size_t c = 0; c < lw.classes.size(); ++c) memcpy(d.cls[c], lw.classes[c].w, 16);
+
+  // runs: literals first (most selective), then classes; each in pattern order
+  std::vector<bk_op> lits, clss;
+  size_t nlit = 0;
+  for (size_t p = 0; p < lw.pos.size();) {
+    size_t q = p + 1;
+    const Pos& a = lw.pos[p];
+    while (q < lw.pos.size() && lw.pos[q].kind == a.kind && lw.pos[q].group == a.group &&
+           (a.kind == 1 || lw.pos[q].cls == a.cls))
+      ++q;
+    bk_op op;
+    op.off = (uint16_t)p;
+    op.len = (uint16_t)(q - p);
+    op.kind = a.kind == 1 ? BK_OP_LIT : BK_OP_CLASS;
+    op.k = 0;
+    op.idx = 0;
+    if (a.kind == 1) {
+      if (nlit + (q - p) > BK_MAX_LIT) { *err = "unsupported pattern: literal bytes exceed 512"; return BK_E_UNSUPPORTED; }
+      op.idx = (uint16_t)nlit;
+      for (size_t t = p; t < q; ++t) d.lit[nlit++] = lw.pos[t].byte;
+      if (a.group >= 0) {
+        size_t k = lw.group_k[a.group];
+        op.k = (uint8_t)(k > 255 ? 255 : k);
+        if (k > (q - p)) op.k = (uint8_t)((q - p) > 255 ? 255 : (q - p));
+      }
+      lits.push_back(op);
+    } else {
+      op.idx = (uint16_t)a.cls;
+      clss.push_back(op);
+    }
+    p = q;
+  }
+  if (lits.size() + clss.size() > BK_MAX_OPS) {
+    *err = "unsupported pattern: more than 48 compare runs";
+    return BK_E_UNSUPPORTED;
+  }
+  for (auto& o : lits) d.ops[d.nops++] = o;
+  for (auto& o : clss) d.ops[d.nops++] = o;
+
+  d.ncaps = (uint32_t)lw.caps.size();  // <= 3: names are unique and drawn from {UMI, CB, SB}
+  d.hdr_growth = 0;
+  for (size_t c = 0; c < lw.caps.size(); ++c) {
+    d.caps[c].off = (uint16_t)lw.caps[c].off;
+    d.caps[c].len = (uint16_t)lw.caps[c].len;
+    d.caps[c].name_len = (uint8_t)lw.caps[c].name.size();
+    memcpy(d.caps[c].name, lw.caps[c].name.data(), lw.caps[c].name.size());
+    d.hdr_growth += 3 + d.caps[c].name_len + 2 * d.caps[c].len;
+  }
+  return BK_OK;
+}
+
+}  // namespace bk
+
+// ---- C ABI ---------------------------------------------------------------------------------------
+
+static void copy_err(const std::string& m, char* err, size_t cap) {
+  if (!err || cap == 0) return;
+  size_t n = m.size() < cap - 1 ? m.size() : cap - 1;
+  memcpy(err, m.data(), n);
+  err[n] = 0;
+}
+
+extern "C" {
+
+int bk_sequence_with_errors(const char* sequence, size_t max_error, char* out, size_t cap,
+                            size_t* n_alternatives) {
+  if (!sequence || !out || cap == 0) return BK_E_ARG;
+  std::vector<std::string> alts;
+  std::string err;
+  int rc = bk::sequence_with_errors(sequence, max_error, &alts, &err);
+  if (rc != BK_OK) { copy_err(err, out, cap); return rc; }
+  std::string joined;
+  for (size_t i = 0; i < alts.size(); ++i) {
+    if (i) joined.push_back('\n');
+    joined += alts[i];
+  }
+  if (n_alternatives) *n_alternatives = alts.size();
+  if (joined.size() + 1 > cap) return BK_E_CAPACITY;
+  memcpy(out, joined.c_str(), joined.size() + 1);
+  return BK_OK;
+}
+
+int bk_expand(const char* pattern, size_t max_error, char* out, size_t cap) {
+  if (!pattern || !out || cap == 0) return BK_E_ARG;
+  std::string expanded, err;
+  int rc = bk::expand(pattern, max_error, &expanded, nullptr, &err);
+  if (rc != BK_OK) { copy_err(err, out, cap); return rc; }
+  if (expanded.size() + 1 > cap) return BK_E_CAPACITY;
+  memcpy(out, expanded.c_str(), expanded.size() + 1);
+  return BK_OK;
+}
+
+bk_program* bk_compile(const char* pattern, size_t max_error, int* status, char* err, size_t errcap) {
+  if (!pattern) {
+    if (status) *status = BK_E_ARG;
+    copy_err("null pattern", err, errcap);
+    return nullptr;
+  }
+  bk_program* p = new (std::nothrow) bk_program();
+  if (!p) { if (status) *status = BK_E_CAPACITY; return nullptr; }
+  std::string e;
+  int rc = bk::compile(pattern, max_error, &p->prog, &e);
+  if (status) *status = rc;
+  if (rc != BK_OK) {
+    copy_err(e, err, errcap);
+    delete p;
+    return nullptr;
+  }
+  if (err && errcap) err[0] = 0;
+  return p;
+}
+
+void bk_program_destroy(bk_program* p) { delete p; }
+
+int bk_program_ncaps(const bk_program* p) { return p ? (int)p->prog.dev.ncaps : 0; }
+
+const char* bk_program_cap_name(const bk_program* p, int i) {
+  if (!p || i < 0 || i >= (int)p->prog.dev.ncaps) return nullptr;
+  const bk_cap& c = p->prog.dev.caps[i];
+  if (c.name_len == 3) return "UMI";
+  return c.name[0] == 'C' ? "CB" : "SB";
+}
+
+int bk_program_get_info(const bk_program* p, bk_program_info* info) {
+  if (!p || !info) return BK_E_ARG;
+  const bk_devprog& d = p->prog.dev;
+  memset(info, 0, sizeof *info);
+  info->total_len = d.total_len;
+  info->anchor_start = d.anchor_start;
+  info->anchor_end = d.anchor_end;
+  info->nops = d.nops;
+  info->ncaps = d.ncaps;
+  info->hdr_growth = d.hdr_growth;
+  for (uint32_t c = 0; c < d.ncaps; ++c) {
+    info->cap_off[c] = d.caps[c].off;
+    info->cap_len[c] = d.caps[c].len;
+  }
+  return BK_OK;
+}
+
+int bk_program_dump(const bk_program* p, char* out, size_t cap) {
+  if (!p || !out || cap == 0) return BK_E_ARG;
+  const bk_devprog& d = p->prog.dev;
+  std::string s;
+  char line[128];
+  snprintf(line, sizeof line, "anchor %u %u\ntotal %u\n", d.anchor_start, d.anchor_end, d.total_len);
+  s += line;
+  for (uint32_t o = 0; o < d.nops; ++o) {
+    const bk_op& op = d.ops[o];
+    if (op.kind == BK_OP_LIT) {
+      snprintf(line, sizeof line, "lit %u %u %u ", op.off, op.len, op.k);
+      s += line;
+      for (uint32_t i = 0; i < op.len; ++i) {
+        snprintf(line, sizeof line, "%02x", d.lit[op.idx + i]);
+        s += line;
+      }
+    } else {
+      snprintf(line, sizeof line, "class %u %u ", op.off, op.len);
+      s += line;
+      for (int b = 0; b < 16; ++b) {
+        snprintf(line, sizeof line, "%02x", (d.cls[op.idx][b >> 2] >> (8 * (b & 3))) & 0xFF);
+        s += line;
+      }
+    }
+    s += "\n";
+  }
+  for (uint32_t c = 0; c < d.ncaps; ++c) {
+    snprintf(line, sizeof line, "cap %.*s %u %u\n", (int)d.caps[c].name_len, d.caps[c].name, d.caps[c].off,
+             d.caps[c].len);
+    s += line;
+  }
+  if (s.size() + 1 > cap) return BK_E_CAPACITY;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return BK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// Lowered matching program shared by the host compiler (bk_pattern.cc) and the kernels
+// (bk_extract.cu).  POD only: it is copied verbatim into __constant__ memory.
+//
+// A program is what `regex::bytes::Regex` is to the reference (pattern.rs:161-167), restricted to
+// the grammar whose matches have a fixed length: every element sits at a fixed offset from the
+// match start, so "leftmost-first" (pattern.rs:226) reduces to "smallest start at which every
+// compare run passes".
+#pragma once
+#include <stdint.h>
+
+#define BK_MAX_OPS 48
+#define BK_MAX_CLASSES 8
+#define BK_MAX_LIT 512
+#define BK_MAX_CAPS 3
+#define BK_MAX_TOTAL_LEN 4096
+
+enum : uint8_t {
+  BK_OP_CLASS = 0,  // every byte of the run must be in class `idx`
+  BK_OP_LIT = 1,    // Hamming(run, lit[idx..idx+len)) <= k, mismatching bytes must be valid for `.`
+};
+
+struct bk_op {
+  uint16_t off;  // offset from match start
+  uint16_t len;
+  uint8_t kind;
+  uint8_t k;     // allowed mismatches (already min(k, len)); 0 for exact literals
+  uint16_t idx;  // class index or offset into lit[]
+};
+
+struct bk_cap {
+  uint16_t off;
+  uint16_t len;
+  uint8_t name_len;  // 2 or 3
+  char name[3];      // "UMI" | "CB" | "SB"
+};
+
+struct bk_devprog {
+  uint32_t present;  // 0: this mate has no pattern (run.rs:233-245 `None`)
+  uint32_t anchor_start;
+  uint32_t anchor_end;
+  uint32_t total_len;
+  uint32_t nops;
+  uint32_t ncaps;
+  uint32_t hdr_growth;  // sum over caps of 3 + name_len + 2*len  (parse.rs:161-168)
+  uint32_t pad;
+  bk_op ops[BK_MAX_OPS];
+  uint32_t cls[BK_MAX_CLASSES][4];  // 128-bit ASCII membership bitmaps (bytes >= 0x80 never match)
+  uint8_t lit[BK_MAX_LIT];
+  bk_cap caps[BK_MAX_CAPS];
+};

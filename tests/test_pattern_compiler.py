@@ -1,0 +1,215 @@
+"""Host pattern front end (C ABI) against the reference's known-answer vectors and the oracle.
+
+CPU-only: these tests make no compute calls on a device.  The lowered program is checked by
+interpreting its text dump in Python and comparing match spans with the oracle's regex
+(pattern.rs:225-230 semantics) on random reads.
+"""
+import random
+import re
+
+import pytest
+
+from barkit_b200 import _lib
+from oracle import barkit_oracle as bo
+
+# ---- the reference's own vectors, through the C ABI ------------------------------------------
+
+
+@pytest.mark.parametrize("expected,text,max_error", [   # pattern.rs:244-249, :35-38
+    (["."], "a", 1), (["A"], "a", 0), ([], "", 1),
+    (["AAA.", "AA.A", "A.AA", ".AAA"], "AAAA", 1), (["..."], "AAA", 3), (["..."], "AAA", 4),
+    (["ATG.", "AT.C", "A.GC", ".TGC"], "ATGC", 1),
+])
+def test_generate_sequences_with_pcr_errors(expected, text, max_error):
+    assert _lib.sequence_with_errors(text, max_error) == expected
+
+
+@pytest.mark.parametrize("expected,pattern,max_error", [   # pattern.rs:263-272, :88-91
+    ("^(AA.|A.A|.AA)(?P<UMI>[ATGCN]{3})", "^aaa(?P<UMI>[ATGCN]{3})", 1),
+    ("^(...)(?P<UMI>[ATGCN]{3})", "^aaa(?P<UMI>[ATGCN]{3})", 3),
+    ("^(...)(?P<UMI>[ATGCN]{3})", "^aaa(?P<UMI>[ATGCN]{3})", 4),
+    ("^((...))(?P<UMI>[ATGCN]{3})", "^(aaa)(?P<UMI>[ATGCN]{3})", 4),
+    ("^(AA.|A.A|.AA)(?P<UMI>[ATGCN]{3})CCC", "^aaa(?P<UMI>[ATGCN]{3})CCC", 1),
+    ("^(?P<UMI>[ATGCN]{3})", "^(?P<UMI>[ATGCN]{3})", 1),
+    ("^(ATG.|AT.C|A.GC|.TGC)(?<UMI>[ATGCN]{12})", "^atgc(?<UMI>[ATGCN]{12})", 1),
+])
+def test_create_fuzzy(expected, pattern, max_error):
+    assert _lib.expand(pattern, max_error) == expected
+
+
+def test_barcode_types_in_pattern_order():   # pattern.rs:191-205, parse.rs:101
+    p = _lib.Program("(?P<SB>[ATGC]{4})gattaca(?P<UMI>[ATGCN]{6})(?<CB>[ACGT]{2})", 1)
+    assert p.barcode_types() == ["SB", "UMI", "CB"]
+
+
+def test_error_messages_follow_error_rs():
+    with pytest.raises(_lib.BarkitError) as e:     # error.rs:13-14
+        _lib.Program("^(?P<XX>[ATGC]{4})", 1)
+    assert e.value.status == _lib.BK_E_PATTERN
+    assert str(e.value) == "Provided unexpected barcode capture group XX"
+    with pytest.raises(_lib.BarkitError) as e:     # error.rs:11-12, pattern.rs:201-203
+        _lib.Program("^atgc", 1)
+    assert str(e.value) == "^(ATG.|AT.C|A.GC|.TGC) capture group not found in your pattern"
+    assert str(e.value) == str(pytest.raises(bo.BarcodeCaptureGroupNotFound, bo.BarcodeRegex, "^atgc", 1).value)
+    with pytest.raises(_lib.BarkitError) as e:     # duplicate names are a regex error (pattern.rs:182)
+        _lib.Program("(?P<UMI>A)(?P<UMI>C)", 1)
+    assert str(e.value).startswith("Regex error: ")
+    with pytest.raises(_lib.BarkitError) as e:     # pattern.rs:56-58
+        _lib.Program("^" + "a" * 65 + "(?P<UMI>[ATGC]{4})", 1)
+    assert str(e.value) == "Failed to choose permutation mask"
+
+
+@pytest.mark.parametrize("pattern", [
+    "^(?P<UMI>[ATGCN]+)", "^(?P<UMI>[ATGCN]{2,4})", "^(?P<UMI>[ATGCN]*)", "^(?P<UMI>A|C)",
+    r"^(?P<UMI>\w{4})", "(?i)(?P<UMI>[ATGCN]{4})", "^(?P<UMI>[ATGCN]{4})?", "(?P<UMI>[ATGCN]{4})^",
+    "(?=A)(?P<UMI>[ATGCN]{4})", "((?P<UMI>[ATGCN]{4})){2}", "(?P<UMI>[[:alpha:]]{4})",
+    "^(?P<UMI>[^atg-z]{4})", "é(?P<UMI>A)",
+])
+def test_unsupported_constructs_are_refused(pattern):
+    with pytest.raises(_lib.BarkitError) as e:
+        _lib.Program(pattern, 1)
+    assert e.value.status in (_lib.BK_E_UNSUPPORTED, _lib.BK_E_PATTERN)
+
+
+# ---- expansion text == oracle on generated patterns ---------------------------------------------
+
+_PIECES = ["^", "$", "atgc", "n", "gattaca", "ATGC", "N", "[ATGCN]", "[atgc]", "{3}", "{12}", "(", ")",
+           "(?P<UMI>", "(?<CB>", "(?P<SB>", ".", " ", "_", "x", "[", "]", "\\", "d", "-", "|", "acgt]",
+           "[^acg", "9", "rysw", "kmbdhvn"]
+
+
+def test_expand_matches_oracle_on_random_pattern_soup():
+    rnd = random.Random(7)
+    for _ in range(1500):
+        pat = "".join(rnd.choice(_PIECES) for _ in range(rnd.randint(1, 8)))
+        for k in (0, 1, 2, 9):
+            assert _lib.expand(pat, k) == bo.BarcodePattern(pat, k).get_pattern_with_errors(), (pat, k)
+
+
+# ---- lowered program == oracle regex on random reads -----------------------------------------------
+
+
+class DumpedProgram:
+    def __init__(self, text):
+        self.ops, self.caps = [], []
+        for line in text.strip().split("\n"):
+            f = line.split()
+            if f[0] == "anchor":
+                self.a_start, self.a_end = int(f[1]), int(f[2])
+            elif f[0] == "total":
+                self.total = int(f[1])
+            elif f[0] == "lit":
+                self.ops.append(("lit", int(f[1]), int(f[2]), int(f[3]), bytes.fromhex(f[4]) if len(f) > 4 else b""))
+            elif f[0] == "class":
+                bm = int.from_bytes(bytes.fromhex(f[3]), "little")
+                self.ops.append(("class", int(f[1]), int(f[2]), bm))
+            elif f[0] == "cap":
+                self.caps.append((f[1], int(f[2]), int(f[3])))
+
+    def match_at(self, seq, s):
+        for op in self.ops:
+            if op[0] == "lit":
+                _, off, ln, k, lit = op
+                mism = 0
+                for i in range(ln):
+                    c = seq[s + off + i]
+                    if c != lit[i]:
+                        if c >= 0x80 or c == 10:
+                            return False
+                        mism += 1
+                        if mism > k:
+                            return False
+            else:
+                _, off, ln, bm = op
+                for i in range(ln):
+                    c = seq[s + off + i]
+                    if c >= 0x80 or not (bm >> c) & 1:
+                        return False
+        return True
+
+    def search(self, seq):
+        L, T = len(seq), self.total
+        if L < T:
+            return -1
+        lo, hi = 0, L - T
+        if self.a_start:
+            hi = 0
+        if self.a_end:
+            if self.a_start and L != T:
+                return -1
+            lo = hi = L - T
+        for s in range(lo, hi + 1):
+            if self.match_at(seq, s):
+                return s
+        return -1
+
+
+SUPPORTED = [
+    ("^(?P<UMI>[ATGCN]{12})", [0, 1]),
+    ("^(?P<CB>[ATGCN]{16})atgccat", [0, 1, 2, 7, 9]),
+    ("^(?P<CB>[ATGCN]{16})atgccat(?P<UMI>[ATGCN]{12})", [0, 1, 2]),
+    ("^(?P<SB>[ATGCN]{8})gtcagtac(?P<UMI>[ATGCN]{12})", [0, 1, 2]),
+    ("(?P<CB>[ATGCN]{16})atgccat", [0, 1, 2]),
+    ("(?P<SB>[ATGC]{4})gattaca(?P<UMI>[ATGCN]{6})", [0, 1, 2]),
+    ("(?P<UMI>[ATGCN]{6})acgt$", [0, 1]),
+    ("^(?P<UMI>[ATGCN]{6})acgt$", [1]),
+    ("^n{3}(?P<UMI>[ATGCN]{4})", [0, 1]),
+    ("^(atg){2}(?P<UMI>[ACGT]{3})TT", [0, 1]),
+    ("(?P<CB>atgc)(?:N|)".replace("(?:N|)", "") + "[^N]{2}(?P<UMI>.{3})", [0, 1]),
+    ("ATGCatgc(?P<UMI>[ACGT]{2})", [1]),
+    ("(?P<UMI>[A-C]{3}[G-T])acg", [1]),
+    ("^(?P<UMI>)ACG", [0]),
+    ("^(?P<UMI>[ATGCN]{0})", [1]),
+    ("(?<CB>[ATGC]{3}) (?P<UMI>[ATGC]{2})", [1]),
+]
+
+
+@pytest.mark.parametrize("pattern,ks", SUPPORTED)
+def test_lowered_program_equals_regex(pattern, ks):
+    rnd = random.Random(hash(pattern) & 0xFFFF)
+    for k in ks:
+        prog = _lib.Program(pattern, k)
+        dp = DumpedProgram(prog.dump())
+        rx = bo.BarcodeRegex(pattern, k)
+        assert prog.barcode_types() == rx.get_barcode_types()
+        lits = re.findall(r"[atgcn]{3,}", pattern)
+        for _ in range(400):
+            L = rnd.choice([0, 3, 8, 17, 23, 35, 36, 60])
+            seq = bytearray(rnd.choice(b"ACGTACGTACGTN") for _ in range(L))
+            if lits and L > 30 and rnd.random() < 0.7:          # plant a (mutated) adapter
+                lit = bytearray(rnd.choice(lits).upper().encode())
+                for _m in range(rnd.choice([0, 0, 1, 1, 2, 3])):
+                    lit[rnd.randrange(len(lit))] = rnd.choice(b"ACGTN a\r")
+                p = rnd.randrange(0, L - len(lit))
+                seq[p:p + len(lit)] = lit
+            seq = bytes(seq)
+            m = rx.regex.search(seq)
+            s = dp.search(seq)
+            assert s == (m.start(0) if m else -1), (pattern, k, seq)
+            if m:
+                assert m.end(0) - m.start(0) == dp.total
+                for name, off, ln in dp.caps:
+                    assert (m.start(name), m.end(name)) == (s + off, s + off + ln)
+
+
+def test_every_declared_symbol_is_exported(repo_root):
+    import os
+    hdr = open(os.path.join(repo_root, "include", "barkit_b200.h")).read()
+    declared = set(re.findall(r"\b(bk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(_lib.lib, name)
+
+
+def test_tokenize_host():
+    fq = b"@a x\nACGT\n+\nIIII\n@b\r\nAC\r\n+b\r\nII\r\n@c\nA\n+\nI"
+    off, consumed, maxrec = _lib.tokenize(fq)
+    assert list(off) == [0, 17, 33, len(fq)]
+    assert consumed == len(fq) and maxrec == 17
+    off, consumed, _ = _lib.tokenize(fq, final=False)          # incomplete tail is left for the next chunk
+    assert list(off) == [0, 17, 33] and consumed == 33
+    for bad in (b"a\nACGT\n+\nIIII\n", b"@a\nACGT\n-\nIIII\n", b"@a\nACGT\n+\nIII\n", b"@a\nACGT\n+\n"):
+        with pytest.raises(_lib.BarkitError):
+            _lib.tokenize(bad)
+    assert [len(r.seq) for r in bo.read_fastq(fq)] == [4, 2, 1]
