@@ -184,6 +184,8 @@ class Program:
 
 def tokenize(text, final: bool = True, cap_records: int | None = None):
     """-> (rec_off uint32[n+1], consumed, max_rec_bytes)"""
+    if len(text) == 0:
+        return np.zeros(1, dtype=np.uint32), 0, 0
     arr = np.frombuffer(text, dtype=np.uint8)
     if cap_records is None:
         cap_records = int(np.count_nonzero(arr == 10)) // 4 + 2

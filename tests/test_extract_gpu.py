@@ -1,0 +1,306 @@
+"""Parity of the CUDA extract path (through the C ABI) with the oracle.  Needs a B200.
+
+Integer / byte work: the bar is bit-exact output (BASELINE.json north_star).
+"""
+import ctypes as C
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from barkit_b200 import _lib
+from oracle import barkit_oracle as bo
+from oracle import bksyn
+from tests.util import CONFIG_PATTERNS, lib_syn_config, ragged_fastq
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ctx(p1, p2=None, k=1, paired=False, skip=False, rc=False):
+    P1 = _lib.Program(p1, k) if p1 is not None else None
+    P2 = _lib.Program(p2, k) if p2 is not None else None
+    return _lib.Context(P1, P2, paired=paired, skip_trimming=skip, rc_barcodes=rc)
+
+
+def run_se(fq, pattern, k=1, skip=False, rc=False):
+    ctx = make_ctx(pattern, k=k, skip=skip, rc=rc)
+    out, res = ctx.extract_text(fq)
+    ctx.close()
+    return out, res
+
+
+def run_pe(fq1, fq2, p1, p2, k=1, skip=False, rc=False):
+    ctx = make_ctx(p1, p2, k=k, paired=True, skip=skip, rc=rc)
+    o1, o2, res = ctx.extract_text(fq1, fq2)
+    ctx.close()
+    return o1, o2, res
+
+
+def _qual(n, start=33):
+    return bytes(range(start, start + n))
+
+
+# ---- reference known-answer vectors on the device --------------------------------------------------
+
+@pytest.mark.parametrize("seq,rc", [   # parse.rs:188-193
+    (b"", b""), (b"GGGCCCAAATTT", b"AAATTTGGGCCC"), (b"ATGCN", b"NGCAT"),
+    (b"AAP", b"ATT"), (b"CCX", b"AGG"), (b"PPP", b"AAA"),
+])
+def test_get_reverse_complement(seq, rc):
+    ctx = make_ctx("^(?P<UMI>[ATGCN]{4})")
+    src = np.frombuffer(seq, dtype=np.uint8).copy() if seq else np.zeros(1, np.uint8)
+    dst = np.zeros(max(len(seq), 1), dtype=np.uint8)
+    assert _lib.lib.bk_reverse_complement(ctx.handle, src.ctypes.data, len(seq), dst.ctypes.data) == 0
+    assert dst[:len(seq)].tobytes() == rc
+    ctx.close()
+
+
+def test_get_captures_doctest():   # pattern.rs:211-224
+    out, res = run_se(b"@r\nATGCNNNNNNCCC\n+\n" + _qual(13) + b"\n", "^atgc(?<UMI>[ATGCN]{6})", 1, skip=True)
+    assert out == b"@r UMI:NNNNNN:" + _qual(13)[4:10] + b"\nATGCNNNNNNCCC\n+\n" + _qual(13) + b"\n"
+    assert res.n_out == 1 and res.n_match1 == 1
+
+
+# ---- derived worked examples ---------------------------------------------------------
+
+def test_derived_examples():
+    pat = "^(?P<CB>[ATGCN]{16})atgccat"
+    seq = b"ACGTACGTACGTACGT" + b"ATGACAT" + b"GGGGGTTTTT"
+    fq = b"@r1 2:N:0:1\n" + seq + b"\n+\n" + _qual(len(seq)) + b"\n"
+    out, _ = run_se(fq, pat, 1)
+    assert out == bo.extract_se(fq, pat, 1)
+    assert out == (b"@r1 2:N:0:1 CB:ACGTACGTACGTACGT:" + _qual(16) + b"\nGGGGGTTTTT\n+\n"
+                   + _qual(10, 33 + 23) + b"\n")
+    seq2 = b"ACGTACGTACGTACGT" + b"ATGAAAT" + b"GGGGGTTTTT"
+    fq2 = b"@r1\n" + seq2 + b"\n+\n" + _qual(len(seq2)) + b"\n"
+    assert run_se(fq2, pat, 1)[0] == b""
+    assert run_se(fq2, pat, 2)[0] == bo.extract_se(fq2, pat, 2) != b""
+    seq3 = b"ACGTACGTACGTACGT" + b"ATGCAT" + b"GGGGGTTTTTT"     # deletion: Hamming only
+    fq3 = b"@r1\n" + seq3 + b"\n+\n" + _qual(len(seq3)) + b"\n"
+    assert run_se(fq3, pat, 1)[0] == b""
+    # B: unanchored, two barcodes, hole cut from the middle
+    patb = "(?P<SB>[ATGC]{4})gattaca(?P<UMI>[ATGCN]{6})"
+    seqb = b"NNACGTGATTACAAAAAAACCCCGATTACATTTTTTGG"
+    fqb = b"@id desc\n" + seqb + b"\n+\n" + _qual(len(seqb)) + b"\n"
+    assert run_se(fqb, patb, 1)[0] == bo.extract_se(fqb, patb, 1)
+    # C: reverse-complement quirk
+    fqc = b"@q\nTTAAGGGACGT\n+\nABCDEFGHIJK\n"
+    assert run_se(fqc, "^(?P<UMI>[ATGCN]{4})ccc", 0, rc=True)[0] == b"@q UMI:TTAA:ABCD\nACGT\n+\nHIJK\n"
+
+
+def test_pe_policy():   # run.rs:149-160
+    fq1 = b"@a 1\nACGTTTTT\n+\nIIIIHHHH\n@b 1\nNNNNNNNN\n+x\n12345678\n@c 1\nNAAAAAAA\n+\nabcdefgh\n"
+    fq2 = b"@a 2\nGGGGCCCC\n+\nJJJJKKKK\n@b 2\nGGGGAAAA\n+\n87654321\n@c 2\nTTTTTTTT\n+\nhgfedcba\n"
+    o1, o2, res = run_pe(fq1, fq2, "^(?P<UMI>[ACGT]{4})", "^(?P<CB>GGGG)", 1)
+    assert o1 == b"@a 1 UMI:ACGT:IIII\nTTTT\n+\nHHHH\n@b 1\nNNNNNNNN\n+\n12345678\n"
+    assert o2 == b"@a 2 CB:GGGG:JJJJ\nCCCC\n+\nKKKK\n@b 2 CB:GGGG:8765\nAAAA\n+\n4321\n"
+    assert (res.n_in, res.n_out, res.n_match1, res.n_match2) == (3, 2, 1, 2)
+
+
+# ---- BASELINE configs on bksyn-v1 text ------------------------------------------------------------------
+
+@pytest.mark.parametrize("name,k,skip,rc", [
+    ("C1", 1, False, False), ("C2", 1, False, False), ("C3", 1, False, False),
+    ("C4", 0, False, False), ("C4", 1, False, False), ("C4", 2, False, False),
+    ("C3", 1, True, False), ("C3", 0, False, True), ("C2", 2, True, True), ("C1", 1, False, True),
+])
+def test_baseline_configs_small(name, k, skip, rc):
+    p1, p2, paired = CONFIG_PATTERNS[name]
+    cfg = bksyn.CONFIGS[name]
+    n = 6000 + 37
+    if paired:
+        fq1, fq2 = bksyn.generate_pair(cfg, 1000, n)
+        o1, o2, res = run_pe(fq1, fq2, p1, p2, k, skip, rc)
+        e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, k, rc, skip)
+        assert o1 == e1
+        assert o2 == e2
+        assert res.n_out == e1.count(b"\n") // 4
+    else:
+        fq = bksyn.generate(cfg, 1, 1000, n)
+        out, res = run_se(fq, p1, k, skip, rc)
+        exp = bo.extract_se(fq, p1, k, rc, skip)
+        assert out == exp
+        assert res.n_out == exp.count(b"\n") // 4
+
+
+def test_c3_match_rate_is_about_090():
+    p1, p2, _ = CONFIG_PATTERNS["C3"]
+    fq1, fq2 = bksyn.generate_pair(bksyn.CONFIGS["C3"], 0, 20000)
+    _, _, res = run_pe(fq1, fq2, p1, p2, 1)
+    assert 0.88 < res.n_out / res.n_in < 0.92
+
+
+# ---- ragged / edge inputs ----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("seed", range(6))
+def test_ragged_single_end(seed):
+    rnd = random.Random(seed)
+    pats = [("^(?P<UMI>[ATGCN]{12})", 1), ("(?P<SB>[ATGC]{4})gattaca(?P<UMI>[ATGCN]{6})", seed % 3),
+            ("(?P<UMI>[ATGCN]{6})acgt$", 1), ("^(?P<CB>[ATGCN]{16})atgccat(?P<UMI>[ATGCN]{12})", 1),
+            ("(?P<CB>.{3})[^N]{2}ttagg(?P<UMI>[A-C]{2})", 2), ("^(?P<UMI>[ATGCN]{0})", 1)]
+    pat, k = pats[seed % len(pats)]
+    fq = ragged_fastq(rnd, 3000 + seed, plant=[b"GATTACA", b"ATGCCAT", b"ACGT", b"TTAGG"],
+                      crlf=(seed == 2), plus_comment=(seed % 2 == 1), final_newline=(seed != 3))
+    for skip, rc in ((False, False), (True, False), (False, True)):
+        out, _ = run_se(fq, pat, k, skip, rc)
+        assert out == bo.extract_se(fq, pat, k, rc, skip), (pat, k, skip, rc)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_ragged_paired_end(seed):
+    rnd = random.Random(100 + seed)
+    n = 2500 + seed
+    heads = [rnd.choice([3, 23, 60]) for _ in range(n)]
+    fq1 = ragged_fastq(rnd, n, 1, plant=[b"GTCAGTAC"], head_lens=heads, min_len=(0 if seed else 30))
+    fq2 = ragged_fastq(rnd, n, 2, plant=[b"ATGCCAT"], head_lens=heads, plus_comment=True)
+    combos = [("^(?P<SB>[ATGCN]{8})gtcagtac(?P<UMI>[ATGCN]{12})", "(?P<CB>[ATGCN]{16})atgccat"),
+              (None, "(?P<CB>[ATGCN]{16})atgccat"), ("^(?P<UMI>[ATGCN]{12})", None),
+              ("(?P<UMI>[ACGT]{5})gtcagtac", "^(?P<CB>[ATGCN]{16})(?P<SB>[ACGT]{3})")]
+    p1, p2 = combos[seed]
+    for k in (0, 1, 2):
+        o1, o2, _ = run_pe(fq1, fq2, p1, p2, k, skip=(k == 2), rc=(k == 1))
+        e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, k, rc_barcodes=(k == 1), skip_trimming=(k == 2))
+        assert o1 == e1 and o2 == e2, (p1, p2, k)
+
+
+def test_empty_and_tiny_inputs():
+    ctx = make_ctx("^(?P<UMI>[ATGCN]{4})")
+    out, res = ctx.extract_text(b"")
+    assert out == b"" and res.n_in == 0 and res.n_out == 0
+    out, res = ctx.extract_text(b"@x\n\n+\n\n")          # empty read
+    assert out == b""
+    out, res = ctx.extract_text(b"@x\nACGT\n+\nIIII")     # exactly the pattern, no trailing newline
+    assert out == b"@x UMI:ACGT:IIII\n\n+\n\n"
+    ctx.close()
+
+
+def test_long_records_shrink_the_tile():
+    rnd = random.Random(5)
+    fq = ragged_fastq(rnd, 300, plant=[b"GATTACA"], min_len=1500, max_len=4000)
+    pat = "(?P<SB>[ATGC]{4})gattaca(?P<UMI>[ATGCN]{6})"
+    out, _ = run_se(fq, pat, 1)
+    assert out == bo.extract_se(fq, pat, 1)
+
+
+def test_output_capacity_error_is_reported():
+    ctx = make_ctx("^(?P<UMI>[ATGCN]{12})")
+    fq = bksyn.generate(bksyn.CONFIGS["C1"], 1, 0, 1000)
+    off, _, maxrec = _lib.tokenize(fq)
+    arr = np.zeros(len(fq) + 64, np.uint8)
+    arr[:len(fq)] = np.frombuffer(fq, np.uint8)
+    m = ctx._mate(arr, off, maxrec)
+    out = np.zeros(1000, np.uint8)
+    res = _lib.Result()
+    rc = _lib.lib.bk_extract_host(ctx.handle, len(off) - 1, C.byref(m), None, out.ctypes.data, out.size,
+                                  None, 0, C.byref(res))
+    assert rc == _lib.BK_E_CAPACITY
+    ctx.close()
+
+
+# ---- device generator == normative Python generator -----------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4"])
+def test_device_generator_matches_bksyn(name):
+    ctx = make_ctx("^(?P<UMI>[ATGCN]{12})")
+    cfg = bksyn.CONFIGS[name]
+    n, first = 3000, 12345678901
+    rl = bksyn.record_len(cfg.read_len)
+    d_text = ctx.dev_alloc(n * rl + 64)
+    d_off = ctx.dev_alloc((n + 1) * 4)
+    for mate in (1, 2):
+        ctx.generate_device(lib_syn_config(name), mate, bksyn.DEFAULT_SEED, first, n, d_text, d_off)
+        text = ctx.d2h(d_text, n * rl).tobytes()
+        off = ctx.d2h(d_off, (n + 1) * 4, np.uint32)
+        assert text == bksyn.generate(cfg, mate, first, n)
+        assert (off == np.arange(n + 1, dtype=np.uint64) * rl).all()
+    ctx.dev_free(d_text)
+    ctx.dev_free(d_off)
+    ctx.close()
+
+
+# ---- device-resident path, match table, full-size properties --------------------------------------------------
+
+def _device_batch(ctx, name, first, n):
+    cfg = bksyn.CONFIGS[name]
+    rl = bksyn.record_len(cfg.read_len)
+    mates = []
+    for mate in (1, 2):
+        d_text = ctx.dev_alloc(n * rl + 64)
+        d_off = ctx.dev_alloc((n + 1) * 4)
+        ctx.generate_device(lib_syn_config(name), mate, bksyn.DEFAULT_SEED, first, n, d_text, d_off)
+        m = _lib.MateIn()
+        m.text, m.rec_off, m.text_len, m.max_rec_bytes = d_text, d_off, n * rl, rl
+        mates.append(m)
+    return mates, rl
+
+
+def test_device_resident_matches_oracle_and_match_table():
+    name, n, first = "C4", 5000, 777
+    p1, p2, _ = CONFIG_PATTERNS[name]
+    ctx = make_ctx(p1, p2, k=2, paired=True)
+    mates, rl = _device_batch(ctx, name, first, n)
+    cap = n * (rl + 120)
+    d_o1, d_o2 = ctx.dev_alloc(cap), ctx.dev_alloc(cap)
+    d_m1, d_m2 = ctx.dev_alloc(n * 4), ctx.dev_alloc(n * 4)
+    res = ctx.extract_device(n, mates[0], mates[1], d_o1, cap, d_o2, cap, d_m1, d_m2, iters=2)
+    fq1, fq2 = bksyn.generate_pair(bksyn.CONFIGS[name], first, n)
+    e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, 2)
+    assert ctx.d2h(d_o1, res.out1_len).tobytes() == e1
+    assert ctx.d2h(d_o2, res.out2_len).tobytes() == e2
+    m1 = ctx.d2h(d_m1, n * 4, np.int32)
+    m2 = ctx.d2h(d_m2, n * 4, np.int32)
+    r1, r2 = bo.BarcodeRegex(p1, 2), bo.BarcodeRegex(p2, 2)
+    for i, (a, b) in enumerate(zip(bo.read_fastq(fq1), bo.read_fastq(fq2))):
+        ma, mb = r1.regex.search(a.seq), r2.regex.search(b.seq)
+        assert m1[i] == (ma.start() if ma else -1)
+        assert m2[i] == (mb.start() if mb else -1)
+    assert res.launches == 2 and res.kernel_ms > 0
+    ctx.close()
+
+
+def test_full_size_properties_c3():
+    """2 M pairs (device-generated): size-independent properties instead of a byte diff.
+    (1) out lengths follow the closed form from n_match; (2) kept mate-2 records are byte-identical
+    to the input records, in order; (3) running the batch in two halves concatenates to the same
+    bytes (ordered compaction is tile-size independent)."""
+    name, n, first = "C3", 2_000_000, 5_000_000
+    p1, p2, _ = CONFIG_PATTERNS[name]
+    ctx = make_ctx(p1, p2, k=1, paired=True)
+    mates, rl = _device_batch(ctx, name, first, n)
+    cap = n * (rl + 70)
+    d_o1, d_o2, d_m1 = ctx.dev_alloc(cap), ctx.dev_alloc(cap), ctx.dev_alloc(n * 4)
+    res = ctx.extract_device(n, mates[0], mates[1], d_o1, cap, d_o2, cap, d_m1, 0)
+    assert res.n_out == res.n_match1 and res.n_match2 == 0
+    assert 0.88 < res.n_out / n < 0.92
+    assert res.out1_len == res.n_out * (rl + 67 - 2 * 35)       # +header text, -35 from seq and qual
+    assert res.out2_len == res.n_out * rl
+    m1 = ctx.d2h(d_m1, n * 4, np.int32)
+    keep = m1 >= 0
+    assert set(np.unique(m1)) <= {-1, 0}
+    assert int(keep.sum()) == res.n_out
+    in2 = ctx.d2h(mates[1].text, n * rl).reshape(n, rl)
+    out2 = ctx.d2h(d_o2, res.out2_len).reshape(-1, rl)
+    assert (out2 == in2[keep]).all()
+    whole1 = zlib.crc32(ctx.d2h(d_o1, res.out1_len).tobytes())
+    # halves
+    h = n // 2 + 13
+    crc, total = 0, 0
+    for a, b in ((0, h), (h, n)):
+        ma, mb = _lib.MateIn(), _lib.MateIn()
+        for src, dst in ((mates[0], ma), (mates[1], mb)):
+            dst.text = src.text + a * rl
+            dst.rec_off = ctx.dev_alloc((b - a + 1) * 4)
+            ctx.h2d(dst.rec_off, (np.arange(b - a + 1, dtype=np.uint64) * rl).astype(np.uint32))
+            dst.text_len, dst.max_rec_bytes = (b - a) * rl, rl
+        # text pointers must stay 16-byte aligned: rl*h is not in general, so realign through a copy
+        if (a * rl) % 16:
+            for dst in (ma, mb):
+                tmp = ctx.dev_alloc((b - a) * rl + 64)
+                ctx.h2d(tmp, ctx.d2h(dst.text, (b - a) * rl))
+                dst.text = tmp
+        r = ctx.extract_device(b - a, ma, mb, d_o1, cap, d_o2, cap)
+        crc = zlib.crc32(ctx.d2h(d_o1, r.out1_len).tobytes(), crc)
+        total += r.out1_len
+    assert total == res.out1_len and crc == whole1
+    ctx.close()
