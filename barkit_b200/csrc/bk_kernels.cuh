@@ -124,6 +124,9 @@ __device__ __forceinline__ uint32_t find_nl(const uint8_t* s, uint32_t from, uin
 }
 
 struct RecView {    // seq_io field definitions: lines without EOL and without a trailing CR
+  uint32_t beg;     // '@'
+  uint32_t end;     // one past the record's last byte
+  uint32_t fast;    // layout is exactly `@head LF seq LF + LF qual LF` (the writer's own framing)
   uint32_t head;    // first byte after '@'
   uint32_t head_len;
   uint32_t seq;
@@ -139,9 +142,31 @@ __device__ __forceinline__ uint32_t strip_cr(const uint8_t* s, uint32_t b, uint3
 __device__ __forceinline__ RecView parse_record(const uint8_t* s, uint32_t b, uint32_t e) {
   RecView r;
   uint32_t nl1 = find_nl(s, b, e);
+  r.beg = b;
+  r.end = e;
+  r.fast = 0;
   r.head = b + 1;
   r.head_len = strip_cr(s, b + 1, nl1 > b ? nl1 : b + 1) - (b + 1);
   uint32_t sb = nl1 + 1 < e ? nl1 + 1 : e;
+  // Fast path for the common layout `seq LF + LF qual LF`: then e - sb = 2L + 4.  A record of any
+  // other shape (CR line ends, text after '+', missing final LF) cannot pass the three probes
+  // with the L this formula gives (newlines only exist at the three line ends), so it falls
+  // through to the scanning path.
+  {
+    const uint32_t rem = e - sb;
+    if (rem >= 4 && !(rem & 1u)) {
+      const uint32_t L = (rem - 4) >> 1;
+      if (s[sb + L] == '\n' && s[sb + L + 1] == '+' && s[sb + L + 2] == '\n' && s[e - 1] == '\n' &&
+          (L == 0 || (s[sb + L - 1] != '\r' && s[e - 2] != '\r'))) {
+        r.seq = sb;
+        r.seq_len = L;
+        r.qual = sb + L + 3;
+        r.qual_len = L;
+        r.fast = (b + 1 + r.head_len == nl1);  // and no CR on the header line
+        return r;
+      }
+    }
+  }
   uint32_t nl2 = find_nl(s, sb, e);
   r.seq = sb;
   r.seq_len = strip_cr(s, sb, nl2) - sb;
@@ -176,59 +201,95 @@ __device__ __forceinline__ uint8_t fetch(const uint8_t* seq, uint32_t L, uint32_
   return seq[j];
 }
 
-// all compare runs of the program at start s
-template <bool RC>
-__device__ __forceinline__ bool match_at(const bk_devprog& pg, const uint8_t* seq, uint32_t L, uint32_t s) {
+// All compare runs of the program at start s.  Branch-free inside a run so that the lanes of a warp
+// (one read each) stay in lock step: a data-dependent early exit would split the warp and replay
+// the remaining runs once per split.  `tab[c]` = bit k set iff class k contains byte c (0 for
+// c >= 0x80).  EARLY_OUT (unanchored search, lanes already diverge on s) stops at the first
+// failed run.
+template <bool RC, bool EARLY_OUT>
+__device__ __forceinline__ bool match_at(const bk_devprog& pg, const uint8_t* tab, const uint8_t* seq,
+                                         uint32_t L, uint32_t s) {
+  bool ok = true;
   for (uint32_t o = 0; o < pg.nops; ++o) {
     const bk_op op = pg.ops[o];
-    uint32_t base = s + op.off;
+    const uint32_t base = s + op.off;
     if (op.kind == BK_OP_LIT) {
-      uint32_t mism = 0;
+      uint32_t mism = 0, bad = 0;
       for (uint32_t i = 0; i < op.len; ++i) {
-        uint8_t c = fetch<RC>(seq, L, base + i);
-        if (c != pg.lit[op.idx + i]) {
-          // a wildcard slot is the regex `.`: any ASCII byte except '\n' (pattern.rs:10,71)
-          if (c >= 0x80 || c == '\n') return false;
-          if (++mism > op.k) return false;
-        }
+        const uint32_t c = fetch<RC>(seq, L, base + i);
+        const uint32_t ne = (c != pg.lit[op.idx + i]);
+        mism += ne;
+        // a wildcard slot is the regex `.`: any ASCII byte except '\n' (pattern.rs:10,71)
+        bad |= ne & (uint32_t)((c >= 0x80u) | (c == '\n'));
       }
+      ok = ok && (mism <= op.k) && !bad;
     } else {
-      const uint32_t w0 = pg.cls[op.idx][0], w1 = pg.cls[op.idx][1], w2 = pg.cls[op.idx][2],
-                     w3 = pg.cls[op.idx][3];
-      for (uint32_t i = 0; i < op.len; ++i) {
-        uint8_t c = fetch<RC>(seq, L, base + i);
-        uint32_t w = (c & 0x40) ? ((c & 0x20) ? w3 : w2) : ((c & 0x20) ? w1 : w0);
-        if (c >= 0x80 || !((w >> (c & 31)) & 1u)) return false;
-      }
+      uint32_t acc = 0xFFu;
+      for (uint32_t i = 0; i < op.len; ++i) acc &= tab[fetch<RC>(seq, L, base + i)];
+      ok = ok && ((acc >> op.idx) & 1u);
     }
+    if (EARLY_OUT && !ok) return false;
   }
-  return true;
+  return ok;
 }
 
 // leftmost match start or -1
 template <bool RC>
-__device__ __forceinline__ int match_read(const bk_devprog& pg, const uint8_t* seq, uint32_t L) {
+__device__ __forceinline__ int match_read(const bk_devprog& pg, const uint8_t* tab, const uint8_t* seq,
+                                          uint32_t L) {
   const uint32_t T = pg.total_len;
   if (L < T) return -1;
-  uint32_t lo = 0, hi = L - T;
-  if (pg.anchor_start) hi = 0;
-  if (pg.anchor_end) {
-    if (pg.anchor_start && L != T) return -1;
-    lo = L - T;
-    hi = L - T;
+  if (pg.anchor_start || pg.anchor_end) {  // exactly one candidate start
+    if (pg.anchor_start && pg.anchor_end && L != T) return -1;
+    const uint32_t s = pg.anchor_end ? L - T : 0;
+    return match_at<RC, false>(pg, tab, seq, L, s) ? (int)s : -1;
   }
-  for (uint32_t s = lo; s <= hi; ++s)
-    if (match_at<RC>(pg, seq, L, s)) return (int)s;
+  for (uint32_t s = 0; s <= L - T; ++s)
+    if (match_at<RC, true>(pg, tab, seq, L, s)) return (int)s;
   return -1;
 }
 
 // ---- emit ----------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t copy_run(uint8_t* dst, uint32_t d, const uint8_t* src, uint32_t s,
-                                             uint32_t len) {
-#pragma unroll 4
-  for (uint32_t i = 0; i < len; ++i) dst[d + i] = src[s + i];
-  return d + len;
+// Byte-granular shared->shared copy by ONE lane: ragged head until the destination is word aligned,
+// then aligned destination words funnel-shifted out of aligned source words (4 independent loads
+// in flight per step), then a ragged tail.  Reads at most 7 bytes past the source run, which stays
+// inside the staged tile (+ slack).  `dst` and `src` never alias (input tile vs output tile).
+__device__ __forceinline__ uint32_t copy_run(uint8_t* __restrict__ dst, uint32_t d,
+                                             const uint8_t* __restrict__ src, uint32_t s, uint32_t len) {
+  const uint32_t end = d + len;
+  uint32_t h = (4u - (d & 3u)) & 3u;
+  h = h < len ? h : len;
+  for (uint32_t i = 0; i < h; ++i) dst[d + i] = src[s + i];
+  d += h;
+  s += h;
+  len -= h;
+  const uint32_t nw = len >> 2;
+  if (nw) {
+    const uint32_t* __restrict__ sp = reinterpret_cast<const uint32_t*>(src + (s & ~3u));
+    uint32_t* __restrict__ dp = reinterpret_cast<uint32_t*>(dst + d);
+    const uint32_t sh = (s & 3u) * 8u;
+    uint32_t lo = sp[0];
+    uint32_t i = 0;
+    for (; i + 4 <= nw; i += 4) {
+      const uint32_t w1 = sp[i + 1], w2 = sp[i + 2], w3 = sp[i + 3], w4 = sp[i + 4];
+      dp[i] = __funnelshift_r(lo, w1, sh);
+      dp[i + 1] = __funnelshift_r(w1, w2, sh);
+      dp[i + 2] = __funnelshift_r(w2, w3, sh);
+      dp[i + 3] = __funnelshift_r(w3, w4, sh);
+      lo = w4;
+    }
+    for (; i < nw; ++i) {
+      const uint32_t hi = sp[i + 1];
+      dp[i] = __funnelshift_r(lo, hi, sh);
+      lo = hi;
+    }
+  }
+  d += nw * 4;
+  s += nw * 4;
+  const uint32_t t = len & 3u;
+  for (uint32_t i = 0; i < t; ++i) dst[d + i] = src[s + i];
+  return end;
 }
 
 // output bytes of a kept record
@@ -247,10 +308,16 @@ __device__ __forceinline__ uint32_t out_bytes(const bk_devprog& pg, const RecVie
   return 1 + r.head_len + g + 1 + sl + 3 + ql + 1;
 }
 
-__device__ __forceinline__ void emit_record(const bk_devprog& pg, const uint8_t* in, const RecView& r,
-                                            int ms, bool trim, uint8_t* out, uint32_t d) {
-  out[d++] = '@';
-  d = copy_run(out, d, in, r.head, r.head_len);
+__device__ __forceinline__ void emit_record(const bk_devprog& pg, const uint8_t* __restrict__ in,
+                                            const RecView& r, int ms, bool trim,
+                                            uint8_t* __restrict__ out, uint32_t d) {
+  // `fast` records already carry the writer's framing, so neighbouring fields travel with their
+  // separators as one run ("\n+\n" after seq, "\n" after qual) and an unchanged record is one run.
+  if (ms < 0 && r.fast) {
+    copy_run(out, d, in, r.beg, r.end - r.beg);
+    return;
+  }
+  d = copy_run(out, d, in, r.beg, 1 + r.head_len);  // '@' + head
   if (ms >= 0) {
     for (uint32_t c = 0; c < pg.ncaps; ++c) {  // pattern order (parse.rs:101)
       const bk_cap cap = pg.caps[c];
@@ -267,21 +334,24 @@ __device__ __forceinline__ void emit_record(const bk_devprog& pg, const uint8_t*
     }
   }
   out[d++] = '\n';
+  const uint32_t sep = r.fast ? 3u : 0u, eol = r.fast ? 1u : 0u;  // separators copied with the run
   if (ms >= 0 && trim) {  // parse.rs:138-148: cut [start0, end0) out of seq and qual
-    uint32_t T = pg.total_len;
+    const uint32_t T = pg.total_len;
     d = copy_run(out, d, in, r.seq, ms);
-    d = copy_run(out, d, in, r.seq + ms + T, r.seq_len - ms - T);
-    out[d++] = '\n'; out[d++] = '+'; out[d++] = '\n';
-    uint32_t qs = (uint32_t)ms < r.qual_len ? (uint32_t)ms : r.qual_len;
-    uint32_t qe = (uint32_t)ms + T < r.qual_len ? (uint32_t)ms + T : r.qual_len;
+    d = copy_run(out, d, in, r.seq + ms + T, r.seq_len - ms - T + sep);
+    if (!r.fast) { out[d++] = '\n'; out[d++] = '+'; out[d++] = '\n'; }
+    const uint32_t qs = (uint32_t)ms < r.qual_len ? (uint32_t)ms : r.qual_len;
+    const uint32_t qe = (uint32_t)ms + T < r.qual_len ? (uint32_t)ms + T : r.qual_len;
     d = copy_run(out, d, in, r.qual, qs);
-    d = copy_run(out, d, in, r.qual + qe, r.qual_len - qe);
+    d = copy_run(out, d, in, r.qual + qe, r.qual_len - qe + eol);
+  } else if (r.fast) {
+    d = copy_run(out, d, in, r.seq, r.end - r.seq);  // seq LF + LF qual LF
   } else {
     d = copy_run(out, d, in, r.seq, r.seq_len);
     out[d++] = '\n'; out[d++] = '+'; out[d++] = '\n';
     d = copy_run(out, d, in, r.qual, r.qual_len);
   }
-  out[d++] = '\n';
+  if (!r.fast) out[d++] = '\n';
 }
 
 // ---- ordered compaction: decoupled look-back over tiles (one warp) -------------------------------------
@@ -330,6 +400,7 @@ template <bool PAIRED>
 __global__ void __launch_bounds__(32) extract_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ uint8_t cls_tab[2][256];
   constexpr int NM = PAIRED ? 2 : 1;
   const int lane = threadIdx.x;
   const bool trim = !(P.flags & 2u);
@@ -342,6 +413,15 @@ __global__ void __launch_bounds__(32) extract_kernel(const __grid_constant__ KPa
   out_s[0] = in_s[1] + (PAIRED ? P.in_cap[1] : P.in_cap[0]);
   out_s[1] = out_s[0] + P.out_cap[0];
 
+  // byte -> "which classes contain it" table, so a class test is one shared-memory lookup
+#pragma unroll
+  for (int m = 0; m < NM; ++m)
+    for (int c = lane; c < 256; c += 32) {
+      uint32_t mask = 0;
+      if (c < 128)
+        for (int k = 0; k < BK_MAX_CLASSES; ++k) mask |= ((P.prog[m].cls[k][c >> 5] >> (c & 31)) & 1u) << k;
+      cls_tab[m][c] = (uint8_t)mask;
+    }
   if (lane == 0) mbar_init(&bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
@@ -399,8 +479,8 @@ __global__ void __launch_bounds__(32) extract_kernel(const __grid_constant__ KPa
         rv[m] = parse_record(in_s[m], rb[m], re[m]);
         if (P.prog[m].present) {
           const uint8_t* sq = in_s[m] + rv[m].seq;
-          ms[m] = match_read<false>(P.prog[m], sq, rv[m].seq_len);
-          if (ms[m] < 0 && rc) ms[m] = match_read<true>(P.prog[m], sq, rv[m].seq_len);  // parse.rs:61-66
+          ms[m] = match_read<false>(P.prog[m], cls_tab[m], sq, rv[m].seq_len);
+          if (ms[m] < 0 && rc) ms[m] = match_read<true>(P.prog[m], cls_tab[m], sq, rv[m].seq_len);  // parse.rs:61-66
         }
         if (P.match[m]) P.match[m][r0 + lane] = ms[m];
       }
