@@ -14,7 +14,7 @@
 
 #include "../../include/barkit_b200.h"
 #include "bk_internal.h"
-#include "bk_kernels.cuh"
+#include "bk_extract.cuh"
 
 namespace {
 
@@ -116,8 +116,10 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   lp->ntiles = (n + R - 1) / R;
   CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)lp->smem));
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, 32, lp->smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, PAIRED ? 64 : 32, lp->smem));
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
@@ -173,7 +175,7 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.flags = ctx->flags;
   if (n > 0) {
     if (ctx->paired)
-      bk::extract_kernel<true><<<lp.grid, 32, lp.smem, stream>>>(P);
+      bk::extract_kernel<true><<<lp.grid, 64, lp.smem, stream>>>(P);
     else
       bk::extract_kernel<false><<<lp.grid, 32, lp.smem, stream>>>(P);
     CK(cudaGetLastError());

@@ -3,7 +3,7 @@
 // One launch = one batch = parse_se_reads / parse_pe_reads (run.rs:63-80, :163-195) + the writer's
 // framing (fastq.rs:259-263) for every record of the batch, single pass over HBM:
 //
-//   tile  = 32 consecutive records (pairs); one warp (= one CTA) owns a tile, lane i owns record i
+//   tile  = 32 consecutive records (pairs); one CTA owns a tile, one warp per mate, lane i owns record i
 //   load  : the tile's contiguous FASTQ text range, one 1-D TMA bulk copy per mate -> shared memory
 //   parse : lane finds its record's four lines (SWAR newline scan in shared memory)
 //   match : lane evaluates the lowered program (bk_program.h) at ascending starts -> leftmost match
@@ -13,6 +13,7 @@
 //   emit  : lane assembles `@head NAME:seq:qual...\nseq'\n+\nqual'\n` (parse.rs:92-171) in a shared
 //           output tile laid out with the global offset's 16-byte phase
 //   store : aligned middle by TMA bulk store, ragged head/tail bytes by the lanes
+// This header holds the device building blocks; the kernel itself is in bk_extract.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -352,219 +353,6 @@ __device__ __forceinline__ void emit_record(const bk_devprog& pg, const uint8_t*
     d = copy_run(out, d, in, r.qual, r.qual_len);
   }
   if (!r.fast) out[d++] = '\n';
-}
-
-// ---- ordered compaction: decoupled look-back over tiles (one warp) -------------------------------------
-
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// exclusive prefix of this tile's aggregate over all earlier tiles; publishes aggregate and prefix
-__device__ __forceinline__ unsigned long long lookback(unsigned long long* desc, uint32_t tile,
-                                                       unsigned long long agg, int lane) {
-  if (tile == 0) {
-    if (lane == 0) st_relaxed_u64(desc, kFlagPrefix | agg);
-    return 0;
-  }
-  if (lane == 0) st_relaxed_u64(desc + tile, kFlagAgg | agg);
-  unsigned long long excl = 0;
-  int look = (int)tile - 1;
-  for (;;) {
-    int idx = look - lane;
-    unsigned long long d = kFlagPrefix;  // virtual tiles before 0: prefix 0
-    if (idx >= 0) {
-      do {
-        d = ld_relaxed_u64(desc + idx);
-      } while ((d >> 62) == 0);
-    }
-    unsigned pm = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-    unsigned long long v = d & kValueMask;
-    if (pm) {
-      int first = __ffs(pm) - 1;  // nearest predecessor holding an inclusive prefix
-      excl += warp_sum_u64(lane <= first ? v : 0ull);
-      break;
-    }
-    excl += warp_sum_u64(v);
-    look -= 32;
-  }
-  if (lane == 0) st_relaxed_u64(desc + tile, kFlagPrefix | (excl + agg));
-  return excl;
-}
-
-// ---- the kernel ----------------------------------------------------------------------------------------
-
-template <bool PAIRED>
-__global__ void __launch_bounds__(32) extract_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint8_t cls_tab[2][256];
-  constexpr int NM = PAIRED ? 2 : 1;
-  const int lane = threadIdx.x;
-  const bool trim = !(P.flags & 2u);
-  const bool rc = (P.flags & 4u) != 0;
-
-  uint8_t* in_s[2];
-  uint8_t* out_s[2];
-  in_s[0] = smem;
-  in_s[1] = in_s[0] + (PAIRED ? P.in_cap[0] : 0);
-  out_s[0] = in_s[1] + (PAIRED ? P.in_cap[1] : P.in_cap[0]);
-  out_s[1] = out_s[0] + P.out_cap[0];
-
-  // byte -> "which classes contain it" table, so a class test is one shared-memory lookup
-#pragma unroll
-  for (int m = 0; m < NM; ++m)
-    for (int c = lane; c < 256; c += 32) {
-      uint32_t mask = 0;
-      if (c < 128)
-        for (int k = 0; k < BK_MAX_CLASSES; ++k) mask |= ((P.prog[m].cls[k][c >> 5] >> (c & 31)) & 1u) << k;
-      cls_tab[m][c] = (uint8_t)mask;
-    }
-  if (lane == 0) mbar_init(&bar, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncwarp();
-  uint32_t parity = 0;
-
-  for (;;) {
-    uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= P.ntiles) break;
-    const uint32_t r0 = tile * P.tile_recs;
-    const uint32_t nrec = min(P.tile_recs, P.n - r0);
-    const bool active = lane < (int)nrec;
-
-    // ---- load: one contiguous text range per mate -----------------------------------------------
-    uint32_t rb[2], re[2], gbase[2];
-    bool too_big = false;
-    uint32_t bytes[2];
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-      uint32_t o = active ? P.off[m][r0 + lane] : 0;
-      uint32_t oe = P.off[m][r0 + nrec];
-      uint32_t onext = __shfl_down_sync(0xffffffffu, o, 1);
-      if (lane == (int)nrec - 1) onext = oe;
-      uint32_t first = __shfl_sync(0xffffffffu, o, 0);
-      gbase[m] = first & ~15u;
-      uint32_t gend = (oe + 15u) & ~15u;
-      bytes[m] = gend - gbase[m];
-      if (bytes[m] > P.in_cap[m]) too_big = true;
-      rb[m] = o - gbase[m];
-      re[m] = onext - gbase[m];
-    }
-    if (too_big) {  // host sized the staging buffer from max_rec_bytes; a longer record is a caller bug
-      if (lane == 0) atomicOr(&P.result->error, 2u);
-#pragma unroll
-      for (int m = 0; m < NM; ++m) lookback(P.desc[m], tile, 0, lane);
-      continue;
-    }
-    if (lane == 0) {
-      uint32_t total = bytes[0] + (PAIRED ? bytes[1] : 0);
-      mbar_arrive_expect_tx(&bar, total);
-#pragma unroll
-      for (int m = 0; m < NM; ++m)
-        if (bytes[m]) bulk_g2s(in_s[m], P.text[m] + gbase[m], bytes[m], &bar);
-    }
-    mbar_wait(&bar, parity);
-    parity ^= 1;
-
-    // ---- parse + match (lane per record) --------------------------------------------------------
-    RecView rv[2];
-    int ms[2] = {-1, -1};
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-      if (active) {
-        rv[m] = parse_record(in_s[m], rb[m], re[m]);
-        if (P.prog[m].present) {
-          const uint8_t* sq = in_s[m] + rv[m].seq;
-          ms[m] = match_read<false>(P.prog[m], cls_tab[m], sq, rv[m].seq_len);
-          if (ms[m] < 0 && rc) ms[m] = match_read<true>(P.prog[m], cls_tab[m], sq, rv[m].seq_len);  // parse.rs:61-66
-        }
-        if (P.match[m]) P.match[m][r0 + lane] = ms[m];
-      }
-    }
-    // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
-    const bool keep = active && (ms[0] >= 0 || (PAIRED && ms[1] >= 0));
-
-    // ---- size + scan + look-back ----------------------------------------------------------------
-    uint32_t olen[2], ooff[2];
-    unsigned long long gout[2];
-    uint32_t total[2];
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-      olen[m] = keep ? out_bytes(P.prog[m], rv[m], ms[m], trim) : 0;
-      uint32_t incl = olen[m];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      ooff[m] = incl - olen[m];
-      total[m] = __shfl_sync(0xffffffffu, incl, 31);
-    }
-#pragma unroll
-    for (int m = 0; m < NM; ++m) gout[m] = lookback(P.desc[m], tile, total[m], lane);
-
-    {  // statistics
-      unsigned kb = __ballot_sync(0xffffffffu, keep);
-      unsigned m1 = __ballot_sync(0xffffffffu, active && ms[0] >= 0);
-      unsigned m2 = __ballot_sync(0xffffffffu, active && ms[1] >= 0);
-      if (lane == 0) {
-        if (kb) atomicAdd(&P.result->n_out, (unsigned long long)__popc(kb));
-        if (m1) atomicAdd(&P.result->n_match[0], (unsigned long long)__popc(m1));
-        if (PAIRED && m2) atomicAdd(&P.result->n_match[1], (unsigned long long)__popc(m2));
-        if (tile == P.ntiles - 1) {
-          P.result->out_len[0] = gout[0] + total[0];
-          if (PAIRED) P.result->out_len[1] = gout[1] + total[1];
-        }
-      }
-    }
-
-    // ---- emit into the shared output tile (same 16-byte phase as the global destination) ---------
-    bool overflow = false;
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-      if (gout[m] + total[m] > P.cap[m]) overflow = true;
-    }
-    if (overflow) {
-      if (lane == 0) atomicOr(&P.result->error, 1u);
-      continue;
-    }
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-      uint32_t phase = (uint32_t)(gout[m] & 15ull);
-      if (keep) emit_record(P.prog[m], in_s[m], rv[m], ms[m], trim, out_s[m], phase + ooff[m]);
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-
-    // ---- store ------------------------------------------------------------------------------------
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-      if (total[m] == 0) continue;
-      const unsigned long long g0 = gout[m], g1 = gout[m] + total[m];
-      const uint32_t phase = (uint32_t)(g0 & 15ull);
-      unsigned long long a0 = (g0 + 15ull) & ~15ull;  // first aligned byte
-      unsigned long long a1 = g1 & ~15ull;            // end of aligned middle
-      uint8_t* gdst = P.out[m];
-      if (a0 >= a1) {  // no aligned middle: all bytes ragged
-        for (unsigned long long x = g0 + lane; x < g1; x += 32) gdst[x] = out_s[m][phase + (uint32_t)(x - g0)];
-      } else {
-        if (lane == 0) bulk_s2g(gdst + a0, out_s[m] + phase + (uint32_t)(a0 - g0), (uint32_t)(a1 - a0));
-        unsigned long long x = g0 + lane;
-        if (x < a0) gdst[x] = out_s[m][phase + (uint32_t)(x - g0)];
-        x = a1 + lane;
-        if (x < g1) gdst[x] = out_s[m][phase + (uint32_t)(x - g0)];
-      }
-    }
-    if (lane == 0) {
-      bulk_commit();
-      bulk_wait_read0();  // shared tile may be overwritten once the bulk engine has read it
-    }
-    __syncwarp();
-  }
 }
 
 // parse::get_reverse_complement as a stand-alone op (API parity; the extract kernel never materialises it)
