@@ -20,7 +20,7 @@ namespace {
 
 constexpr int kSlots = 2;
 constexpr size_t kMaxDynSmem = 200 * 1024;    // leave room for >= 1 CTA/SM with static smem
-constexpr size_t kTargetDynSmem = 54 * 1024;  // aim for >= 4 resident tiles per SM
+constexpr size_t kTargetDynSmem = 70 * 1024;  // aim for >= 3 resident CTAs (input ring + output tile) per SM
 
 struct DevBuf {
   void* p = nullptr;
@@ -96,7 +96,7 @@ size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_
     uint32_t growth = ctx->prog[m].present ? ctx->prog[m].hdr_growth : 0;
     in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
     out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
-    total += in_cap[m] + out_cap[m];
+    total += bk::kStages * (size_t)in_cap[m] + out_cap[m];
   }
   return total;
 }
@@ -119,7 +119,7 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, PAIRED ? 64 : 32, lp->smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, PAIRED ? 128 : 64, lp->smem));
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
@@ -175,9 +175,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.flags = ctx->flags;
   if (n > 0) {
     if (ctx->paired)
-      bk::extract_kernel<true><<<lp.grid, 64, lp.smem, stream>>>(P);
+      bk::extract_kernel<true><<<lp.grid, 128, lp.smem, stream>>>(P);
     else
-      bk::extract_kernel<false><<<lp.grid, 32, lp.smem, stream>>>(P);
+      bk::extract_kernel<false><<<lp.grid, 64, lp.smem, stream>>>(P);
     CK(cudaGetLastError());
     if (launches) *launches += 1;
   }

@@ -1,11 +1,13 @@
-// The extract kernel: ordered compaction (decoupled look-back) + per-tile pipeline.
+// The extract kernel: warp-specialised tile pipeline with ordered compaction (decoupled look-back).
 // Building blocks (parse / match / emit / PTX wrappers) are in bk_kernels.cuh.
 #pragma once
 #include "bk_kernels.cuh"
 
 namespace bk {
 
-// ---- ordered compaction: decoupled look-back over tiles (one warp per output stream) -----------------
+constexpr int kStages = 2;  // input ring depth per mate (front warp runs at most this far ahead)
+
+// ---- ordered compaction: decoupled look-back over tiles ------------------------------------------------
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
@@ -15,44 +17,40 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 
 constexpr int kLookWindows = 4;  // 32-descriptor windows fetched per round (independent loads in flight)
 
-// Exclusive prefix of this tile's aggregate over all earlier tiles; publishes aggregate, then prefix.
-// Several hundred tiles are in flight chip-wide, so the nearest tile that already holds an inclusive
-// prefix is typically a few windows back: fetch kLookWindows windows per round trip instead of one.
+// Exclusive prefix of tile `tile` over all earlier tiles.  The tile's own aggregate has already been
+// published (by the front warp); this publishes the inclusive prefix once it is known.
 __device__ __forceinline__ unsigned long long lookback(unsigned long long* desc, uint32_t tile,
                                                        unsigned long long agg, int lane) {
-  if (tile == 0) {
-    if (lane == 0) st_relaxed_u64(desc, kFlagPrefix | agg);
-    return 0;
-  }
-  if (lane == 0) st_relaxed_u64(desc + tile, kFlagAgg | agg);
   unsigned long long excl = 0;
-  int look = (int)tile - 1;
-  bool done = false;
-  while (!done) {
-    unsigned long long d[kLookWindows];
+  if (tile != 0) {
+    int look = (int)tile - 1;
+    bool done = false;
+    while (!done) {
+      unsigned long long d[kLookWindows];
 #pragma unroll
-    for (int j = 0; j < kLookWindows; ++j) {
-      const int idx = look - 32 * j - lane;
-      d[j] = idx >= 0 ? ld_relaxed_u64(desc + idx) : kFlagPrefix;  // virtual tiles before 0: prefix 0
-    }
+      for (int j = 0; j < kLookWindows; ++j) {
+        const int idx = look - 32 * j - lane;
+        d[j] = idx >= 0 ? ld_relaxed_u64(desc + idx) : kFlagPrefix;  // virtual tiles before 0: prefix 0
+      }
 #pragma unroll
-    for (int j = 0; j < kLookWindows; ++j) {
-      if (done) break;
-      const int idx = look - 32 * j - lane;
-      while (__any_sync(0xffffffffu, (d[j] >> 62) == 0)) {
-        if ((d[j] >> 62) == 0) d[j] = ld_relaxed_u64(desc + idx);
+      for (int j = 0; j < kLookWindows; ++j) {
+        if (done) break;
+        const int idx = look - 32 * j - lane;
+        while (__any_sync(0xffffffffu, (d[j] >> 62) == 0)) {
+          if ((d[j] >> 62) == 0) d[j] = ld_relaxed_u64(desc + idx);
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, (d[j] >> 62) == 2);
+        const unsigned long long v = d[j] & kValueMask;
+        if (pm) {
+          const int first = __ffs(pm) - 1;  // nearest predecessor holding an inclusive prefix
+          excl += warp_sum_u64(lane <= first ? v : 0ull);
+          done = true;
+        } else {
+          excl += warp_sum_u64(v);
+        }
       }
-      const unsigned pm = __ballot_sync(0xffffffffu, (d[j] >> 62) == 2);
-      const unsigned long long v = d[j] & kValueMask;
-      if (pm) {
-        const int first = __ffs(pm) - 1;  // nearest predecessor holding an inclusive prefix
-        excl += warp_sum_u64(lane <= first ? v : 0ull);
-        done = true;
-      } else {
-        excl += warp_sum_u64(v);
-      }
+      look -= 32 * kLookWindows;
     }
-    look -= 32 * kLookWindows;
   }
   if (lane == 0) st_relaxed_u64(desc + tile, kFlagPrefix | (excl + agg));
   return excl;
@@ -60,164 +58,243 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* desc,
 
 // ---- the kernel ----------------------------------------------------------------------------------------
 //
-// CTA = one warp per mate (2 warps paired-end, 1 warp single-end); warp m owns mate m's records of the
-// tile and output stream m (-o / -O).  The two warps meet once per tile (match exchange: the PE keep
-// rule needs both mates' decisions, run.rs:149-160); everything else -- TMA load, parse, match, scan,
-// look-back, emit, TMA store -- is private to the warp.  Tiles are claimed from a global counter, in
-// order, so every predecessor a look-back waits on belongs to a running CTA that has nothing to wait
-// for before publishing its aggregate.
+// Per mate m (one for single-end, two for paired-end) a FRONT warp and a BACK warp share a ring of
+// kStages staged input tiles:
+//
+//   front F_m : wait ring slot free -> claim tile (global counter, in order) -> TMA load -> parse ->
+//               match -> exchange match decisions with the other mate's front warp (PE keep rule,
+//               run.rs:149-160) -> sizes + warp scan -> PUBLISH the tile aggregate -> hand the slot over
+//   back  B_m : take slot -> look-back (predecessors' aggregates were published long ago, so this
+//               rarely spins) -> emit into the shared output tile -> release slot -> TMA store
+//
+// The front warp never waits on another tile's result, so a claimed tile's aggregate is published
+// after a short, bounded delay; that is what keeps every other tile's look-back from stalling (a
+// warp that both publishes and waits delays its own next aggregate by its wait, and the delay
+// compounds down the chain).  Lane i of a warp owns record i of the tile.
 
 constexpr int kSkipTile = -2147483647 - 1;
+constexpr uint32_t kEndTile = 0xFFFFFFFFu;
+constexpr uint32_t kNotKept = 0xFFFFFFFFu;
+
+struct TileMeta {  // front -> back hand-over, one per (mate, stage); SoA so lanes do not conflict
+  uint32_t beg[32], end[32], head_len[32], seq[32], seq_len[32], qual[32], qual_len_fast[32];
+  int32_t ms[32];
+  uint32_t ooff[32];  // record's offset inside the tile's output, kNotKept if dropped
+  uint32_t tile;      // kEndTile terminates the back warp
+  uint32_t total;     // output bytes of the tile on this stream
+};
 
 template <bool PAIRED>
-__global__ void __launch_bounds__(PAIRED ? 64 : 32) extract_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar[2];
+  constexpr int NM = PAIRED ? 2 : 1;
+  __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_ready[2][kStages], bar_empty[2][kStages];
   __shared__ uint8_t cls_tab[2][256];
-  __shared__ int s_ms[2][2][32];   // [iteration parity][mate][lane]
-  __shared__ uint32_t s_next[2];   // [iteration parity]
+  __shared__ int s_ms[2][2][32];  // [tile parity][mate][lane]
+  __shared__ uint32_t s_tile[2];  // [tile parity]
+  __shared__ TileMeta meta[NM][kStages];
+
   const int lane = threadIdx.x & 31;
-  const int m = PAIRED ? (int)(threadIdx.x >> 5) : 0;  // this warp's mate = its output stream
+  const int warp = threadIdx.x >> 5;
+  const bool is_front = warp < NM;
+  const int m = is_front ? warp : warp - NM;  // mate = output stream
   const bk_devprog& pg = P.prog[m];
   const bool trim = !(P.flags & 2u);
   const bool rc = (P.flags & 4u) != 0;
   const uint32_t R = P.tile_recs;
 
-  uint8_t* const in_s = smem + (m ? P.in_cap[0] : 0);
-  uint8_t* const out_s = smem + P.in_cap[0] + (PAIRED ? P.in_cap[1] : 0) + (m ? P.out_cap[0] : 0);
-  const uint8_t* const text = P.text[m];
-  const uint32_t* const off = P.off[m];
-  uint8_t* const gdst = P.out[m];
-  unsigned long long* const desc = P.desc[m];
+  // dynamic shared memory: [mate0 ring][mate1 ring][out0][out1]
+  uint8_t* const in_ring = smem + (m ? kStages * P.in_cap[0] : 0);
+  const uint32_t in_stride = P.in_cap[m];
+  uint8_t* const out_s = smem + kStages * (P.in_cap[0] + (PAIRED ? P.in_cap[1] : 0)) + (m ? P.out_cap[0] : 0);
 
-  // byte -> "which classes contain it" table, so a class test is one shared-memory lookup
-  for (int c = lane; c < 256; c += 32) {
-    uint32_t mask = 0;
-    if (c < 128)
-      for (int k = 0; k < BK_MAX_CLASSES; ++k) mask |= ((pg.cls[k][c >> 5] >> (c & 31)) & 1u) << k;
-    cls_tab[m][c] = (uint8_t)mask;
+  if (is_front) {
+    // byte -> "which classes contain it" table, so a class test is one shared-memory lookup
+    for (int c = lane; c < 256; c += 32) {
+      uint32_t mask = 0;
+      if (c < 128)
+        for (int k = 0; k < BK_MAX_CLASSES; ++k) mask |= ((pg.cls[k][c >> 5] >> (c & 31)) & 1u) << k;
+      cls_tab[m][c] = (uint8_t)mask;
+    }
+    if (lane == 0)
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&bar_full[m][s], 1);
+        mbar_init(&bar_ready[m][s], 1);
+        mbar_init(&bar_empty[m][s], 1);
+      }
   }
-  if (lane == 0) mbar_init(&bar[m], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  if (threadIdx.x == 0) s_next[1] = atomicAdd(P.tile_counter, 1u);
   __syncthreads();
-  uint32_t tile = s_next[1];
-  uint32_t parity = 0, it = 0;
 
-  // record offsets of the next tile are fetched one tile ahead (registers only)
-  uint32_t o_pre = 0, oe_pre = 0;
-  if (tile < P.ntiles) {
-    const uint32_t r0 = tile * R, nrec = min(R, P.n - r0);
-    o_pre = lane < (int)nrec ? off[r0 + lane] : 0;
-    oe_pre = off[r0 + nrec];
-  }
+  if (is_front) {
+    // =============================== FRONT ======================================================
+    const uint8_t* const text = P.text[m];
+    const uint32_t* const off = P.off[m];
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
+      TileMeta& tm = meta[m][s];
+      mbar_wait(&bar_empty[m][s], ph ^ 1u);  // slot free (passes immediately for the first kStages tiles)
 
-  while (tile < P.ntiles) {
-    const uint32_t r0 = tile * R;
-    const uint32_t nrec = min(R, P.n - r0);
-    const bool active = lane < (int)nrec;
-
-    // ---- load: this mate's contiguous text range of the tile ------------------------------------
-    const uint32_t o = o_pre, oe = oe_pre;
-    uint32_t onext = __shfl_down_sync(0xffffffffu, o, 1);
-    if (lane == (int)nrec - 1) onext = oe;
-    const uint32_t gbase = __shfl_sync(0xffffffffu, o, 0) & ~15u;
-    const uint32_t bytes = ((oe + 15u) & ~15u) - gbase;
-    const bool too_big = bytes > P.in_cap[m];  // host sized the staging buffer from max_rec_bytes
-    const uint32_t rb = o - gbase, re = onext - gbase;
-    RecView rv;
-    int ms = -1;
-    if (!too_big) {
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&bar[m], bytes);
-        bulk_g2s(in_s, text + gbase, bytes, &bar[m]);
-      }
-      mbar_wait(&bar[m], parity);
-      parity ^= 1;
-      // ---- parse + match (lane per record) -----------------------------------------------------
-      if (active) {
-        rv = parse_record(in_s, rb, re);
-        if (pg.present) {
-          const uint8_t* sq = in_s + rv.seq;
-          ms = match_read<false>(pg, cls_tab[m], sq, rv.seq_len);
-          if (ms < 0 && rc) ms = match_read<true>(pg, cls_tab[m], sq, rv.seq_len);  // parse.rs:61-66
-        }
-        if (P.match[m]) P.match[m][r0 + lane] = ms;
-      }
-    } else if (lane == 0) {
-      atomicOr(&P.result->error, 2u);
-    }
-
-    // ---- exchange with the other mate's warp ----------------------------------------------------------
-    s_ms[it & 1][m][lane] = too_big ? kSkipTile : ms;
-    __syncthreads();
-    int ms_other = -1;
-    bool skip = too_big;
-    if (PAIRED) {
-      ms_other = s_ms[it & 1][m ^ 1][lane];
-      skip = skip || (s_ms[it & 1][m ^ 1][0] == kSkipTile);
-    }
-    // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
-    const bool keep = !skip && active && (ms >= 0 || ms_other >= 0);
-
-    // ---- size + scan + look-back ------------------------------------------------------------------------
-    const uint32_t olen = keep ? out_bytes(pg, rv, ms, trim) : 0;
-    uint32_t incl = olen;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
-    }
-    const uint32_t ooff = incl - olen;
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    const unsigned long long gout = lookback(desc, tile, total, lane);
-
-    {  // statistics
-      const unsigned kb = __ballot_sync(0xffffffffu, keep);
-      const unsigned mb = __ballot_sync(0xffffffffu, active && ms >= 0);
-      if (lane == 0) {
-        if (m == 0 && kb) atomicAdd(&P.result->n_out, (unsigned long long)__popc(kb));
-        if (mb) atomicAdd(&P.result->n_match[m], (unsigned long long)__popc(mb));
-        if (tile == P.ntiles - 1) P.result->out_len[m] = gout + total;
-      }
-    }
-
-    if (gout + total > P.cap[m]) {
-      if (lane == 0) atomicOr(&P.result->error, 1u);
-    } else if (total) {
-      // ---- emit into the shared output tile (same 16-byte phase as the global destination) -----------
-      const uint32_t phase = (uint32_t)(gout & 15ull);
-      if (keep) emit_record(pg, in_s, rv, ms, trim, out_s, phase + ooff);
-      fence_proxy_async_smem();
-      __syncwarp();
-      // ---- store: aligned middle by TMA, ragged edges by the lanes -------------------------------------
-      const unsigned long long g0 = gout, g1 = gout + total;
-      const unsigned long long a0 = (g0 + 15ull) & ~15ull, a1 = g1 & ~15ull;
-      if (a0 >= a1) {
-        for (unsigned long long x = g0 + lane; x < g1; x += 32) gdst[x] = out_s[phase + (uint32_t)(x - g0)];
+      // claim the next tile only now, with the slot in hand: the aggregate follows within one load
+      uint32_t tile;
+      if (PAIRED) {
+        if (threadIdx.x == 0) s_tile[k & 1] = atomicAdd(P.tile_counter, 1u);
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        tile = s_tile[k & 1];
       } else {
+        tile = 0;
+        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+      }
+      if (tile >= P.ntiles) {
         if (lane == 0) {
-          bulk_s2g(gdst + a0, out_s + phase + (uint32_t)(a0 - g0), (uint32_t)(a1 - a0));
-          bulk_commit();
+          tm.tile = kEndTile;
+          mbar_arrive(&bar_ready[m][s]);
         }
-        unsigned long long x = g0 + lane;
-        if (x < a0) gdst[x] = out_s[phase + (uint32_t)(x - g0)];
-        x = a1 + lane;
-        if (x < g1) gdst[x] = out_s[phase + (uint32_t)(x - g0)];
-        if (lane == 0) bulk_wait_read0();  // the tile may be overwritten once the bulk engine has read it
+        break;
+      }
+      const uint32_t r0 = tile * R;
+      const uint32_t nrec = min(R, P.n - r0);
+      const bool active = lane < (int)nrec;
+
+      // ---- load: this mate's contiguous text range of the tile --------------------------------
+      const uint32_t o = active ? off[r0 + lane] : 0;
+      const uint32_t oe = off[r0 + nrec];
+      uint32_t onext = __shfl_down_sync(0xffffffffu, o, 1);
+      if (lane == (int)nrec - 1) onext = oe;
+      const uint32_t gbase = __shfl_sync(0xffffffffu, o, 0) & ~15u;
+      const uint32_t bytes = ((oe + 15u) & ~15u) - gbase;
+      const bool too_big = bytes > in_stride;  // host sized the ring from max_rec_bytes
+      const uint32_t rb = o - gbase, re = onext - gbase;
+      uint8_t* const in_s = in_ring + s * in_stride;
+      RecView rv;
+      rv.beg = rv.end = rv.fast = rv.head = rv.head_len = rv.seq = rv.seq_len = rv.qual = rv.qual_len = 0;
+      int ms = -1;
+      if (!too_big) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&bar_full[m][s], bytes);
+          bulk_g2s(in_s, text + gbase, bytes, &bar_full[m][s]);
+        }
+        mbar_wait(&bar_full[m][s], ph);
+        // ---- parse + match (lane per record) ---------------------------------------------------
+        if (active) {
+          rv = parse_record(in_s, rb, re);
+          if (pg.present) {
+            const uint8_t* sq = in_s + rv.seq;
+            ms = match_read<false>(pg, cls_tab[m], sq, rv.seq_len);
+            if (ms < 0 && rc) ms = match_read<true>(pg, cls_tab[m], sq, rv.seq_len);  // parse.rs:61-66
+          }
+          if (P.match[m]) P.match[m][r0 + lane] = ms;
+        }
+      } else if (lane == 0) {
+        atomicOr(&P.result->error, 2u);
+      }
+
+      // ---- exchange match decisions with the other mate's front warp -----------------------------
+      int ms_other = -1;
+      bool skip = too_big;
+      if (PAIRED) {
+        s_ms[k & 1][m][lane] = too_big ? kSkipTile : ms;
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        ms_other = s_ms[k & 1][m ^ 1][lane];
+        skip = skip || (s_ms[k & 1][m ^ 1][0] == kSkipTile);
+      }
+      // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
+      const bool keep = !skip && active && (ms >= 0 || ms_other >= 0);
+
+      // ---- size + scan, publish the aggregate -------------------------------------------------------
+      const uint32_t olen = keep ? out_bytes(pg, rv, ms, trim) : 0;
+      uint32_t incl = olen;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      if (lane == 0) st_relaxed_u64(P.desc[m] + tile, kFlagAgg | (unsigned long long)total);
+
+      {  // statistics
+        const unsigned kb = __ballot_sync(0xffffffffu, keep);
+        const unsigned mb = __ballot_sync(0xffffffffu, active && ms >= 0);
+        if (lane == 0) {
+          if (m == 0 && kb) atomicAdd(&P.result->n_out, (unsigned long long)__popc(kb));
+          if (mb) atomicAdd(&P.result->n_match[m], (unsigned long long)__popc(mb));
+        }
+      }
+
+      // ---- hand the slot to the back warp -------------------------------------------------------------
+      tm.beg[lane] = rv.beg;
+      tm.end[lane] = rv.end;
+      tm.head_len[lane] = rv.head_len;
+      tm.seq[lane] = rv.seq;
+      tm.seq_len[lane] = rv.seq_len;
+      tm.qual[lane] = rv.qual;
+      tm.qual_len_fast[lane] = (rv.qual_len << 1) | rv.fast;
+      tm.ms[lane] = ms;
+      tm.ooff[lane] = keep ? incl - olen : kNotKept;
+      if (lane == 0) {
+        tm.tile = tile;
+        tm.total = total;
       }
       __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ready[m][s]);
     }
-    // Claim the next tile only now: a tile claimed early would sit unpublished while this warp
-    // works (and waits in its own look-back), and every later tile's look-back would wait on it.
-    if (threadIdx.x == 0) s_next[it & 1] = atomicAdd(P.tile_counter, 1u);
-    __syncthreads();
-    tile = s_next[it & 1];
-    ++it;
-    if (tile < P.ntiles) {
-      const uint32_t q0 = tile * R, qn = min(R, P.n - q0);
-      o_pre = lane < (int)qn ? off[q0 + lane] : 0;
-      oe_pre = off[q0 + qn];
+  } else {
+    // =============================== BACK =======================================================
+    uint8_t* const gdst = P.out[m];
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
+      const TileMeta& tm = meta[m][s];
+      mbar_wait(&bar_ready[m][s], ph);
+      const uint32_t tile = tm.tile;
+      if (tile == kEndTile) break;
+      const uint32_t total = tm.total;
+      const unsigned long long gout = lookback(P.desc[m], tile, total, lane);
+      if (lane == 0 && tile == P.ntiles - 1) P.result->out_len[m] = gout + total;
+      const bool fits = gout + total <= P.cap[m];
+      if (!fits && lane == 0) atomicOr(&P.result->error, 1u);
+      const uint32_t phase = (uint32_t)(gout & 15ull);
+      if (fits && total) {
+        // ---- emit into the shared output tile (same 16-byte phase as the global destination) --------
+        const uint32_t ooff = tm.ooff[lane];
+        if (ooff != kNotKept) {
+          RecView rv;
+          rv.beg = tm.beg[lane];
+          rv.end = tm.end[lane];
+          rv.head = rv.beg + 1;
+          rv.head_len = tm.head_len[lane];
+          rv.seq = tm.seq[lane];
+          rv.seq_len = tm.seq_len[lane];
+          rv.qual = tm.qual[lane];
+          const uint32_t qf = tm.qual_len_fast[lane];
+          rv.qual_len = qf >> 1;
+          rv.fast = qf & 1u;
+          emit_record(pg, in_ring + s * in_stride, rv, tm.ms[lane], trim, out_s, phase + ooff);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_empty[m][s]);  // ring slot (input tile + meta) is free again
+      if (fits && total) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        // ---- store: aligned middle by TMA, ragged edges by the lanes ---------------------------------
+        const unsigned long long g0 = gout, g1 = gout + total;
+        const unsigned long long a0 = (g0 + 15ull) & ~15ull, a1 = g1 & ~15ull;
+        if (a0 >= a1) {
+          for (unsigned long long x = g0 + lane; x < g1; x += 32) gdst[x] = out_s[phase + (uint32_t)(x - g0)];
+        } else {
+          if (lane == 0) {
+            bulk_s2g(gdst + a0, out_s + phase + (uint32_t)(a0 - g0), (uint32_t)(a1 - a0));
+            bulk_commit();
+          }
+          unsigned long long x = g0 + lane;
+          if (x < a0) gdst[x] = out_s[phase + (uint32_t)(x - g0)];
+          x = a1 + lane;
+          if (x < g1) gdst[x] = out_s[phase + (uint32_t)(x - g0)];
+          if (lane == 0) bulk_wait_read0();  // the output tile may be overwritten once the engine has read it
+        }
+        __syncwarp();
+      }
     }
   }
 }
