@@ -38,6 +38,8 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in LIB_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if force or _stale(LIB, srcs):
         cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-lpthread"]
+        if os.environ.get("BK_PROFILE_PHASES"):
+            cmd.insert(1, "-DBK_PROFILE_PHASES")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)

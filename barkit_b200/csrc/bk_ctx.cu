@@ -119,7 +119,7 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, PAIRED ? 128 : 64, lp->smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, PAIRED ? 192 : 96, lp->smem));
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
@@ -127,7 +127,7 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   return BK_OK;
 }
 
-size_t scratch_bytes(uint32_t ntiles) { return 256 + (size_t)ntiles * 16; }
+size_t scratch_bytes(uint32_t ntiles) { return 512 + (size_t)ntiles * 16; }
 
 // enqueue: scratch reset + extract kernel.  All pointers are device pointers.
 int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
@@ -167,7 +167,8 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.match[0] = match1; P.match[1] = match2;
   P.tile_counter = (unsigned int*)sc;
   P.result = (bk::DevResult*)(sc + 64);
-  P.desc[0] = (unsigned long long*)(sc + 256);
+  P.prof = (unsigned long long*)(sc + 256);
+  P.desc[0] = (unsigned long long*)(sc + 512);
   P.desc[1] = P.desc[0] + lp.ntiles;
   P.n = n;
   P.ntiles = lp.ntiles;
@@ -175,9 +176,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.flags = ctx->flags;
   if (n > 0) {
     if (ctx->paired)
-      bk::extract_kernel<true><<<lp.grid, 128, lp.smem, stream>>>(P);
+      bk::extract_kernel<true><<<lp.grid, 192, lp.smem, stream>>>(P);
     else
-      bk::extract_kernel<false><<<lp.grid, 64, lp.smem, stream>>>(P);
+      bk::extract_kernel<false><<<lp.grid, 96, lp.smem, stream>>>(P);
     CK(cudaGetLastError());
     if (launches) *launches += 1;
   }
@@ -420,6 +421,16 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
   bk::DevResult r = *s.h_res;
   fill_result(res, r, n, ms / iters, launches);
   return check_dev_result(ctx, r);
+}
+
+int bk_debug_phases(bk_ctx* ctx, uint64_t* out24) {
+  if (!ctx || !out24) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[0];
+  if (!s.scratch.buf.p) return BK_E_ARG;
+  CK(cudaStreamSynchronize(s.stream));
+  CK(cudaMemcpy(out24, (uint8_t*)s.scratch.buf.p + 256, 24 * 8, cudaMemcpyDeviceToHost));
+  return BK_OK;
 }
 
 int bk_reverse_complement(bk_ctx* ctx, const uint8_t* seq, size_t n, uint8_t* out) {

@@ -63,14 +63,29 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* desc,
 //
 //   front F_m : wait ring slot free -> claim tile (global counter, in order) -> TMA load -> parse ->
 //               match -> exchange match decisions with the other mate's front warp (PE keep rule,
-//               run.rs:149-160) -> sizes + warp scan -> PUBLISH the tile aggregate -> hand the slot over
-//   back  B_m : take slot -> look-back (predecessors' aggregates were published long ago, so this
-//               rarely spins) -> emit into the shared output tile -> release slot -> TMA store
+//               run.rs:149-160) -> sizes + warp scan -> PUBLISH the tile aggregate -> hand the slot on
+//   scan  S_m : take slot -> look-back over earlier tiles -> publish the inclusive prefix -> pass the
+//               tile's global output offset to the back warp
+//   back  B_m : take slot -> emit into the shared output tile -> release slot -> TMA store
 //
 // The front warp never waits on another tile's result, so a claimed tile's aggregate is published
 // after a short, bounded delay; that is what keeps every other tile's look-back from stalling (a
 // warp that both publishes and waits delays its own next aggregate by its wait, and the delay
-// compounds down the chain).  Lane i of a warp owns record i of the tile.
+// compounds down the chain).  The scan warp resolves prefixes as soon as aggregates exist, so
+// look-backs stay short, and its spinning costs nobody's critical path.  Lane i of a front/back
+// warp owns record i of the tile.
+
+// Optional phase timers (compile with -DBK_PROFILE_PHASES): per-role cycle sums, lane 0 only.
+#ifdef BK_PROFILE_PHASES
+#define PROF_INIT long long p_t = clock64(); long long p_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF(i) { const long long p_n = clock64(); p_acc[i] += p_n - p_t; p_t = p_n; }
+#define PROF_FLUSH(base) \
+  if (lane == 0 && m == 0) for (int p_i = 0; p_i < 8; ++p_i) atomicAdd(&P.prof[(base) + p_i], (unsigned long long)p_acc[p_i]);
+#else
+#define PROF_INIT
+#define PROF(i)
+#define PROF_FLUSH(base)
+#endif
 
 constexpr int kSkipTile = -2147483647 - 1;
 constexpr uint32_t kEndTile = 0xFFFFFFFFu;
@@ -82,13 +97,15 @@ struct TileMeta {  // front -> back hand-over, one per (mate, stage); SoA so lan
   uint32_t ooff[32];  // record's offset inside the tile's output, kNotKept if dropped
   uint32_t tile;      // kEndTile terminates the back warp
   uint32_t total;     // output bytes of the tile on this stream
+  unsigned long long gout;  // global output offset of the tile on this stream
 };
 
 template <bool PAIRED>
-__global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
-  __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_ready[2][kStages], bar_empty[2][kStages];
+  __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_pub[2][kStages], bar_ready[2][kStages],
+      bar_empty[2][kStages];
   __shared__ uint8_t cls_tab[2][256];
   __shared__ int s_ms[2][2][32];  // [tile parity][mate][lane]
   __shared__ uint32_t s_tile[2];  // [tile parity]
@@ -97,7 +114,8 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const bool is_front = warp < NM;
-  const int m = is_front ? warp : warp - NM;  // mate = output stream
+  const bool is_scan = !is_front && warp < 2 * NM;
+  const int m = warp % NM;  // mate = output stream
   const bk_devprog& pg = P.prog[m];
   const bool trim = !(P.flags & 2u);
   const bool rc = (P.flags & 4u) != 0;
@@ -119,6 +137,7 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
     if (lane == 0)
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&bar_full[m][s], 1);
+        mbar_init(&bar_pub[m][s], 1);
         mbar_init(&bar_ready[m][s], 1);
         mbar_init(&bar_empty[m][s], 1);
       }
@@ -130,10 +149,12 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
     // =============================== FRONT ======================================================
     const uint8_t* const text = P.text[m];
     const uint32_t* const off = P.off[m];
+    PROF_INIT
     for (uint32_t k = 0;; ++k) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
       TileMeta& tm = meta[m][s];
       mbar_wait(&bar_empty[m][s], ph ^ 1u);  // slot free (passes immediately for the first kStages tiles)
+      PROF(0)
 
       // claim the next tile only now, with the slot in hand: the aggregate follows within one load
       uint32_t tile;
@@ -146,10 +167,11 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
         if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
       }
+      PROF(1)
       if (tile >= P.ntiles) {
         if (lane == 0) {
           tm.tile = kEndTile;
-          mbar_arrive(&bar_ready[m][s]);
+          mbar_arrive(&bar_pub[m][s]);
         }
         break;
       }
@@ -165,6 +187,7 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
       const uint32_t gbase = __shfl_sync(0xffffffffu, o, 0) & ~15u;
       const uint32_t bytes = ((oe + 15u) & ~15u) - gbase;
       const bool too_big = bytes > in_stride;  // host sized the ring from max_rec_bytes
+      PROF(2)
       const uint32_t rb = o - gbase, re = onext - gbase;
       uint8_t* const in_s = in_ring + s * in_stride;
       RecView rv;
@@ -176,6 +199,7 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
           bulk_g2s(in_s, text + gbase, bytes, &bar_full[m][s]);
         }
         mbar_wait(&bar_full[m][s], ph);
+        PROF(3)
         // ---- parse + match (lane per record) ---------------------------------------------------
         if (active) {
           rv = parse_record(in_s, rb, re);
@@ -190,6 +214,7 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
         atomicOr(&P.result->error, 2u);
       }
 
+      PROF(4)
       // ---- exchange match decisions with the other mate's front warp -----------------------------
       int ms_other = -1;
       bool skip = too_big;
@@ -199,6 +224,7 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
         ms_other = s_ms[k & 1][m ^ 1][lane];
         skip = skip || (s_ms[k & 1][m ^ 1][0] == kSkipTile);
       }
+      PROF(5)
       // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
       const bool keep = !skip && active && (ms >= 0 || ms_other >= 0);
 
@@ -237,19 +263,42 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
         tm.total = total;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_ready[m][s]);
+      if (lane == 0) mbar_arrive(&bar_pub[m][s]);
+      PROF(6)
     }
+    PROF_FLUSH(0)
+  } else if (is_scan) {
+    // =============================== SCAN =======================================================
+    PROF_INIT
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
+      TileMeta& tm = meta[m][s];
+      mbar_wait(&bar_pub[m][s], ph);
+      PROF(0)
+      const uint32_t tile = tm.tile;
+      if (tile != kEndTile) {
+        const unsigned long long gout = lookback(P.desc[m], tile, tm.total, lane);
+        if (lane == 0) tm.gout = gout;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ready[m][s]);
+      PROF(1)
+      if (tile == kEndTile) break;
+    }
+    PROF_FLUSH(8)
   } else {
     // =============================== BACK =======================================================
     uint8_t* const gdst = P.out[m];
+    PROF_INIT
     for (uint32_t k = 0;; ++k) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
       const TileMeta& tm = meta[m][s];
       mbar_wait(&bar_ready[m][s], ph);
+      PROF(0)
       const uint32_t tile = tm.tile;
       if (tile == kEndTile) break;
       const uint32_t total = tm.total;
-      const unsigned long long gout = lookback(P.desc[m], tile, total, lane);
+      const unsigned long long gout = tm.gout;
       if (lane == 0 && tile == P.ntiles - 1) P.result->out_len[m] = gout + total;
       const bool fits = gout + total <= P.cap[m];
       if (!fits && lane == 0) atomicOr(&P.result->error, 1u);
@@ -273,6 +322,7 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
         }
       }
       __syncwarp();
+      PROF(1)
       if (lane == 0) mbar_arrive(&bar_empty[m][s]);  // ring slot (input tile + meta) is free again
       if (fits && total) {
         fence_proxy_async_smem();
@@ -295,7 +345,9 @@ __global__ void __launch_bounds__(PAIRED ? 128 : 64) extract_kernel(const __grid
         }
         __syncwarp();
       }
+      PROF(2)
     }
+    PROF_FLUSH(16)
   }
 }
 

@@ -42,6 +42,7 @@ struct KParams {
   unsigned long long* desc[2];  // look-back descriptors, one per tile and output stream
   unsigned int* tile_counter;
   DevResult* result;
+  unsigned long long* prof;  // 24 phase-cycle sums (only written when built with BK_PROFILE_PHASES)
   uint32_t n;
   uint32_t ntiles;
   uint32_t tile_recs;  // <= 32 (smaller when records are too long for the staging buffer)
