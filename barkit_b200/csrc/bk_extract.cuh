@@ -122,9 +122,12 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
   const uint32_t R = P.tile_recs;
 
   // dynamic shared memory: [mate0 ring][mate1 ring][out0][out1]
-  uint8_t* const in_ring = smem + (m ? kStages * P.in_cap[0] : 0);
+  // (32-bit shared-space addresses; see the note at the top of bk_kernels.cuh)
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t in_ring = smem_base + (m ? kStages * P.in_cap[0] : 0);
   const uint32_t in_stride = P.in_cap[m];
-  uint8_t* const out_s = smem + kStages * (P.in_cap[0] + (PAIRED ? P.in_cap[1] : 0)) + (m ? P.out_cap[0] : 0);
+  const uint32_t out_s = smem_base + kStages * (P.in_cap[0] + (PAIRED ? P.in_cap[1] : 0)) + (m ? P.out_cap[0] : 0);
+  const uint32_t tab = smem_u32(&cls_tab[m][0]);
 
   if (is_front) {
     // byte -> "which classes contain it" table, so a class test is one shared-memory lookup
@@ -189,9 +192,9 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
       const bool too_big = bytes > in_stride;  // host sized the ring from max_rec_bytes
       PROF(2)
       const uint32_t rb = o - gbase, re = onext - gbase;
-      uint8_t* const in_s = in_ring + s * in_stride;
+      const uint32_t in_s = in_ring + s * in_stride;
       RecView rv;
-      rv.beg = rv.end = rv.fast = rv.head = rv.head_len = rv.seq = rv.seq_len = rv.qual = rv.qual_len = 0;
+      rv.beg = rv.end = rv.fast = rv.head_len = rv.seq = rv.seq_len = rv.qual = rv.qual_len = 0;
       int ms = -1;
       if (!too_big) {
         if (lane == 0) {
@@ -202,11 +205,10 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
         PROF(3)
         // ---- parse + match (lane per record) ---------------------------------------------------
         if (active) {
-          rv = parse_record(in_s, rb, re);
+          rv = parse_record(in_s + rb, in_s + re);
           if (pg.present) {
-            const uint8_t* sq = in_s + rv.seq;
-            ms = match_read<false>(pg, cls_tab[m], sq, rv.seq_len);
-            if (ms < 0 && rc) ms = match_read<true>(pg, cls_tab[m], sq, rv.seq_len);  // parse.rs:61-66
+            ms = match_read<false>(pg, tab, rv.seq, rv.seq_len);
+            if (ms < 0 && rc) ms = match_read<true>(pg, tab, rv.seq, rv.seq_len);  // parse.rs:61-66
           }
           if (P.match[m]) P.match[m][r0 + lane] = ms;
         }
@@ -310,7 +312,6 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
           RecView rv;
           rv.beg = tm.beg[lane];
           rv.end = tm.end[lane];
-          rv.head = rv.beg + 1;
           rv.head_len = tm.head_len[lane];
           rv.seq = tm.seq[lane];
           rv.seq_len = tm.seq_len[lane];
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
           const uint32_t qf = tm.qual_len_fast[lane];
           rv.qual_len = qf >> 1;
           rv.fast = qf & 1u;
-          emit_record(pg, in_ring + s * in_stride, rv, tm.ms[lane], trim, out_s, phase + ooff);
+          emit_record(pg, rv, tm.ms[lane], trim, out_s + phase + ooff);
         }
       }
       __syncwarp();
@@ -331,16 +332,17 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
         const unsigned long long g0 = gout, g1 = gout + total;
         const unsigned long long a0 = (g0 + 15ull) & ~15ull, a1 = g1 & ~15ull;
         if (a0 >= a1) {
-          for (unsigned long long x = g0 + lane; x < g1; x += 32) gdst[x] = out_s[phase + (uint32_t)(x - g0)];
+          for (unsigned long long x = g0 + lane; x < g1; x += 32)
+            gdst[x] = (uint8_t)lds8(out_s + phase + (uint32_t)(x - g0));
         } else {
           if (lane == 0) {
             bulk_s2g(gdst + a0, out_s + phase + (uint32_t)(a0 - g0), (uint32_t)(a1 - a0));
             bulk_commit();
           }
           unsigned long long x = g0 + lane;
-          if (x < a0) gdst[x] = out_s[phase + (uint32_t)(x - g0)];
+          if (x < a0) gdst[x] = (uint8_t)lds8(out_s + phase + (uint32_t)(x - g0));
           x = a1 + lane;
-          if (x < g1) gdst[x] = out_s[phase + (uint32_t)(x - g0)];
+          if (x < g1) gdst[x] = (uint8_t)lds8(out_s + phase + (uint32_t)(x - g0));
           if (lane == 0) bulk_wait_read0();  // the output tile may be overwritten once the engine has read it
         }
         __syncwarp();
