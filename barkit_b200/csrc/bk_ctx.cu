@@ -6,6 +6,7 @@
 // implementation of it here.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -119,11 +120,14 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, PAIRED ? 192 : 96, lp->smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, (PAIRED ? 2 : 1) * (2 + bk::kBackWarps) * 32, lp->smem));
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
   lp->grid = (int)std::max<long long>(grid, 1);
+  if (getenv("BK_DEBUG"))
+    fprintf(stderr, "[bk] tile_recs %u smem %zu B ctas/sm %d grid %d ntiles %u\n", lp->tile_recs, lp->smem, per_sm,
+            lp->grid, lp->ntiles);
   return BK_OK;
 }
 
@@ -176,9 +180,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.flags = ctx->flags;
   if (n > 0) {
     if (ctx->paired)
-      bk::extract_kernel<true><<<lp.grid, 192, lp.smem, stream>>>(P);
+      bk::extract_kernel<true><<<lp.grid, 2 * (2 + bk::kBackWarps) * 32, lp.smem, stream>>>(P);
     else
-      bk::extract_kernel<false><<<lp.grid, 96, lp.smem, stream>>>(P);
+      bk::extract_kernel<false><<<lp.grid, (2 + bk::kBackWarps) * 32, lp.smem, stream>>>(P);
     CK(cudaGetLastError());
     if (launches) *launches += 1;
   }
@@ -430,6 +434,19 @@ int bk_debug_phases(bk_ctx* ctx, uint64_t* out24) {
   if (!s.scratch.buf.p) return BK_E_ARG;
   CK(cudaStreamSynchronize(s.stream));
   CK(cudaMemcpy(out24, (uint8_t*)s.scratch.buf.p + 256, 24 * 8, cudaMemcpyDeviceToHost));
+#ifdef BK_PROFILE_PHASES
+  {  // look-back statistics ride in the unused scan slots [10..12]
+    unsigned long long v[3] = {0, 0, 0};
+    cudaMemcpyFromSymbol(&v[0], bk::g_look_rounds, 8);
+    cudaMemcpyFromSymbol(&v[1], bk::g_look_windows, 8);
+    cudaMemcpyFromSymbol(&v[2], bk::g_look_spins, 8);
+    out24[10] = v[0]; out24[11] = v[1]; out24[12] = v[2];
+    unsigned long long z = 0;
+    cudaMemcpyToSymbol(bk::g_look_rounds, &z, 8);
+    cudaMemcpyToSymbol(bk::g_look_windows, &z, 8);
+    cudaMemcpyToSymbol(bk::g_look_spins, &z, 8);
+  }
+#endif
   return BK_OK;
 }
 

@@ -6,10 +6,11 @@
 namespace bk {
 
 constexpr int kStages = 2;  // input ring depth per mate (front warp runs at most this far ahead)
+constexpr int kBackWarps = kEmitParts;  // back warps per mate: warp j writes part j of every record (emit_part)
 
 // ---- ordered compaction: decoupled look-back over tiles ------------------------------------------------
 
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -19,13 +20,19 @@ constexpr int kLookWindows = 4;  // 32-descriptor windows fetched per round (ind
 
 // Exclusive prefix of tile `tile` over all earlier tiles.  The tile's own aggregate has already been
 // published (by the front warp); this publishes the inclusive prefix once it is known.
-__device__ __forceinline__ unsigned long long lookback(unsigned long long* desc, uint32_t tile,
+#ifdef BK_PROFILE_PHASES
+__device__ unsigned long long g_look_rounds, g_look_spins, g_look_windows;
+#endif
+__device__ __noinline__ unsigned long long lookback(unsigned long long* desc, uint32_t tile,
                                                        unsigned long long agg, int lane) {
   unsigned long long excl = 0;
   if (tile != 0) {
     int look = (int)tile - 1;
     bool done = false;
     while (!done) {
+#ifdef BK_PROFILE_PHASES
+      if (lane == 0) atomicAdd(&g_look_rounds, 1ull);
+#endif
       unsigned long long d[kLookWindows];
 #pragma unroll
       for (int j = 0; j < kLookWindows; ++j) {
@@ -36,17 +43,23 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* desc,
       for (int j = 0; j < kLookWindows; ++j) {
         if (done) break;
         const int idx = look - 32 * j - lane;
+#ifdef BK_PROFILE_PHASES
+        if (lane == 0) atomicAdd(&g_look_windows, 1ull);
+#endif
         while (__any_sync(0xffffffffu, (d[j] >> 62) == 0)) {
+#ifdef BK_PROFILE_PHASES
+          if (lane == 0) atomicAdd(&g_look_spins, 1ull);
+#endif
           if ((d[j] >> 62) == 0) d[j] = ld_relaxed_u64(desc + idx);
         }
         const unsigned pm = __ballot_sync(0xffffffffu, (d[j] >> 62) == 2);
+        // aggregates are one tile's bytes (32 bits is plenty); only the prefix itself is 64-bit
         const unsigned long long v = d[j] & kValueMask;
+        const int first = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor holding an inclusive prefix
+        excl += warp_sum_u32(lane < first ? (uint32_t)v : 0u);
         if (pm) {
-          const int first = __ffs(pm) - 1;  // nearest predecessor holding an inclusive prefix
-          excl += warp_sum_u64(lane <= first ? v : 0ull);
+          excl += __shfl_sync(0xffffffffu, v, first);
           done = true;
-        } else {
-          excl += warp_sum_u64(v);
         }
       }
       look -= 32 * kLookWindows;
@@ -66,7 +79,8 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* desc,
 //               run.rs:149-160) -> sizes + warp scan -> PUBLISH the tile aggregate -> hand the slot on
 //   scan  S_m : take slot -> look-back over earlier tiles -> publish the inclusive prefix -> pass the
 //               tile's global output offset to the back warp
-//   back  B_m : take slot -> emit into the shared output tile -> release slot -> TMA store
+//   back  B_m : (kBackWarps warps) take slot -> each warp emits its word-aligned share of every
+//               record into the shared output tile -> release slot -> one of them issues the TMA store
 //
 // The front warp never waits on another tile's result, so a claimed tile's aggregate is published
 // after a short, bounded delay; that is what keeps every other tile's look-back from stalling (a
@@ -87,6 +101,14 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* desc,
 #define PROF_FLUSH(base)
 #endif
 
+// named barrier of one mate's back warps (ids 2 and 3; 0 is __syncthreads, 1 the front warps')
+__device__ __forceinline__ void back_sync(int m) {
+  if (m == 0)
+    asm volatile("bar.sync 2, %0;" ::"n"(kBackWarps * 32) : "memory");
+  else
+    asm volatile("bar.sync 3, %0;" ::"n"(kBackWarps * 32) : "memory");
+}
+
 constexpr int kSkipTile = -2147483647 - 1;
 constexpr uint32_t kEndTile = 0xFFFFFFFFu;
 constexpr uint32_t kNotKept = 0xFFFFFFFFu;
@@ -95,27 +117,32 @@ struct TileMeta {  // front -> back hand-over, one per (mate, stage); SoA so lan
   uint32_t beg[32], end[32], head_len[32], seq[32], seq_len[32], qual[32], qual_len_fast[32];
   int32_t ms[32];
   uint32_t ooff[32];  // record's offset inside the tile's output, kNotKept if dropped
+  uint32_t olen[32];  // record's output bytes
   uint32_t tile;      // kEndTile terminates the back warp
   uint32_t total;     // output bytes of the tile on this stream
   unsigned long long gout;  // global output offset of the tile on this stream
 };
 
 template <bool PAIRED>
-__global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 3) extract_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
   __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_pub[2][kStages], bar_ready[2][kStages],
       bar_empty[2][kStages];
-  __shared__ uint8_t cls_tab[2][256];
+  __shared__ uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, then the complement table
   __shared__ int s_ms[2][2][32];  // [tile parity][mate][lane]
   __shared__ uint32_t s_tile[2];  // [tile parity]
   __shared__ TileMeta meta[NM][kStages];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const bool is_front = warp < NM;
-  const bool is_scan = !is_front && warp < 2 * NM;
+  // Warp roles, lowest warp ids first: back, scan, front.  The scheduler favours higher warp ids, and
+  // the front warps' claim -> publish latency is what every other tile's look-back waits on.
+  constexpr int NB = NM * kBackWarps;
+  const bool is_front = warp >= NB + NM;
+  const bool is_scan = !is_front && warp >= NB;
   const int m = warp % NM;  // mate = output stream
+  const int bj = warp < NB ? warp / NM : 0;  // back warp index within the mate
   const bk_devprog& pg = P.prog[m];
   const bool trim = !(P.flags & 2u);
   const bool rc = (P.flags & 4u) != 0;
@@ -136,13 +163,14 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
       if (c < 128)
         for (int k = 0; k < BK_MAX_CLASSES; ++k) mask |= ((pg.cls[k][c >> 5] >> (c & 31)) & 1u) << k;
       cls_tab[m][c] = (uint8_t)mask;
+      cls_tab[m][kTabComp + c] = (uint8_t)complement((uint32_t)c);
     }
     if (lane == 0)
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&bar_full[m][s], 1);
         mbar_init(&bar_pub[m][s], 1);
         mbar_init(&bar_ready[m][s], 1);
-        mbar_init(&bar_empty[m][s], 1);
+        mbar_init(&bar_empty[m][s], kBackWarps);
       }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -162,7 +190,7 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
       // claim the next tile only now, with the slot in hand: the aggregate follows within one load
       uint32_t tile;
       if (PAIRED) {
-        if (threadIdx.x == 0) s_tile[k & 1] = atomicAdd(P.tile_counter, 1u);
+        if (m == 0 && lane == 0) s_tile[k & 1] = atomicAdd(P.tile_counter, 1u);
         asm volatile("bar.sync 1, 64;" ::: "memory");
         tile = s_tile[k & 1];
       } else {
@@ -206,7 +234,7 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
         // ---- parse + match (lane per record) ---------------------------------------------------
         if (active) {
           rv = parse_record(in_s + rb, in_s + re);
-          if (pg.present) {
+          if (pg.present && rv.qual_len == rv.seq_len) {  // unequal lengths never leave bk_tokenize
             ms = match_read<false>(pg, tab, rv.seq, rv.seq_len);
             if (ms < 0 && rc) ms = match_read<true>(pg, tab, rv.seq, rv.seq_len);  // parse.rs:61-66
           }
@@ -260,6 +288,7 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
       tm.qual_len_fast[lane] = (rv.qual_len << 1) | rv.fast;
       tm.ms[lane] = ms;
       tm.ooff[lane] = keep ? incl - olen : kNotKept;
+      tm.olen[lane] = olen;
       if (lane == 0) {
         tm.tile = tile;
         tm.total = total;
@@ -319,15 +348,16 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
           const uint32_t qf = tm.qual_len_fast[lane];
           rv.qual_len = qf >> 1;
           rv.fast = qf & 1u;
-          emit_record(pg, rv, tm.ms[lane], trim, out_s + phase + ooff);
+          emit_part(pg, rv, tm.ms[lane], trim, out_s + phase + ooff, bj);
         }
       }
       __syncwarp();
       PROF(1)
       if (lane == 0) mbar_arrive(&bar_empty[m][s]);  // ring slot (input tile + meta) is free again
-      if (fits && total) {
-        fence_proxy_async_smem();
-        __syncwarp();
+      if (fits && total) fence_proxy_async_smem();
+      // all shares written -> one warp stores; nobody overwrites the tile until the store has read it
+      back_sync(m);
+      if (fits && total && bj == 0) {
         // ---- store: aligned middle by TMA, ragged edges by the lanes ---------------------------------
         const unsigned long long g0 = gout, g1 = gout + total;
         const unsigned long long a0 = (g0 + 15ull) & ~15ull, a1 = g1 & ~15ull;
@@ -347,9 +377,10 @@ __global__ void __launch_bounds__(PAIRED ? 192 : 96) extract_kernel(const __grid
         }
         __syncwarp();
       }
+      back_sync(m);
       PROF(2)
     }
-    PROF_FLUSH(16)
+    if (bj == 0) { PROF_FLUSH(16) }
   }
 }
 

@@ -162,7 +162,7 @@ __device__ __forceinline__ uint32_t strip_cr(uint32_t b, uint32_t e) {
   return (e > b && lds8(e - 1) == '\r') ? e - 1 : e;
 }
 
-__device__ __forceinline__ RecView parse_record(uint32_t b, uint32_t e) {
+__device__ __noinline__ RecView parse_record(uint32_t b, uint32_t e) {
   RecView r;
   const uint32_t nl1 = find_nl(b, e);
   r.beg = b;
@@ -217,9 +217,13 @@ __device__ __forceinline__ uint32_t complement(uint32_t c) {
   }
 }
 
+// `tab` is this mate's 512-byte lookup block in shared memory: [0,256) class-membership bits per
+// byte, [256,512) the complement table (a switch here was a quarter of the kernel's code).
+constexpr uint32_t kTabComp = 256, kTabBytes = 512;
+
 template <bool RC>
-__device__ __forceinline__ uint32_t fetch(uint32_t seq, uint32_t L, uint32_t j) {
-  if (RC) return complement(lds8(seq + L - 1 - j));
+__device__ __forceinline__ uint32_t fetch(uint32_t tab, uint32_t seq, uint32_t L, uint32_t j) {
+  if (RC) return lds8(tab + kTabComp + lds8(seq + L - 1 - j));
   return lds8(seq + j);
 }
 
@@ -238,7 +242,7 @@ __device__ __forceinline__ bool match_at(const bk_devprog& pg, uint32_t tab, uin
       uint32_t mism = 0, bad = 0;
 #pragma unroll 4
       for (uint32_t i = 0; i < op.len; ++i) {
-        const uint32_t c = fetch<RC>(seq, L, base + i);
+        const uint32_t c = fetch<RC>(tab, seq, L, base + i);
         const uint32_t ne = (c != pg.lit[op.idx + i]);
         mism += ne;
         // a wildcard slot is the regex `.`: any ASCII byte except '\n' (pattern.rs:10,71)
@@ -249,11 +253,11 @@ __device__ __forceinline__ bool match_at(const bk_devprog& pg, uint32_t tab, uin
       uint32_t acc = 0xFFu;
       uint32_t i = 0;
       for (; i + 4 <= op.len; i += 4) {  // 4 independent byte loads, then 4 independent table loads
-        const uint32_t c0 = fetch<RC>(seq, L, base + i), c1 = fetch<RC>(seq, L, base + i + 1);
-        const uint32_t c2 = fetch<RC>(seq, L, base + i + 2), c3 = fetch<RC>(seq, L, base + i + 3);
+        const uint32_t c0 = fetch<RC>(tab, seq, L, base + i), c1 = fetch<RC>(tab, seq, L, base + i + 1);
+        const uint32_t c2 = fetch<RC>(tab, seq, L, base + i + 2), c3 = fetch<RC>(tab, seq, L, base + i + 3);
         acc &= lds8(tab + c0) & lds8(tab + c1) & lds8(tab + c2) & lds8(tab + c3);
       }
-      for (; i < op.len; ++i) acc &= lds8(tab + fetch<RC>(seq, L, base + i));
+      for (; i < op.len; ++i) acc &= lds8(tab + fetch<RC>(tab, seq, L, base + i));
       ok = ok && ((acc >> op.idx) & 1u);
     }
     if (EARLY_OUT && !ok) return false;
@@ -263,7 +267,7 @@ __device__ __forceinline__ bool match_at(const bk_devprog& pg, uint32_t tab, uin
 
 // leftmost match start or -1
 template <bool RC>
-__device__ __forceinline__ int match_read(const bk_devprog& pg, uint32_t tab, uint32_t seq, uint32_t L) {
+__device__ __noinline__ int match_read(const bk_devprog& pg, uint32_t tab, uint32_t seq, uint32_t L) {
   const uint32_t T = pg.total_len;
   if (L < T) return -1;
   if (pg.anchor_start || pg.anchor_end) {  // exactly one candidate start
@@ -278,68 +282,110 @@ __device__ __forceinline__ int match_read(const bk_devprog& pg, uint32_t tab, ui
 
 // ---- emit ----------------------------------------------------------------------------------------------
 
-// output bytes of a kept record
+// output bytes of a kept record (qual_len == seq_len whenever ms >= 0, see emit_part)
 __device__ __forceinline__ uint32_t out_bytes(const bk_devprog& pg, const RecView& r, int ms, bool trim) {
   uint32_t sl = r.seq_len, ql = r.qual_len, g = 0;
   if (ms >= 0) {
-    g = pg.hdr_growth;
+    g = pg.hdr_growth;  // sum of " NAME:" seq ":" qual   (parse.rs:161-168)
     if (trim) {
-      const uint32_t T = pg.total_len;
-      sl -= T;  // match lies inside seq
-      const uint32_t qs = (uint32_t)ms < ql ? (uint32_t)ms : ql;
-      const uint32_t qe = (uint32_t)ms + T < ql ? (uint32_t)ms + T : ql;
-      ql -= (qe - qs);
+      sl -= pg.total_len;  // the match lies inside seq
+      ql -= pg.total_len;
     }
   }
   return 1 + r.head_len + g + 1 + sl + 3 + ql + 1;
 }
 
-// Per-lane output stream into the shared output tile.  A record's bytes are produced strictly in
-// order, so the lane keeps the (up to 3) bytes that do not yet fill a word in a register and only
-// ever stores whole aligned words; the caller writes the bytes in front of the first word boundary
-// itself (they share a word with the previous record, which the neighbouring lane writes) and
-// os_end writes the last partial word bytewise for the same reason.  Inside a run the pending-byte
-// count is constant, so a run's inner loop is one load, one funnel shift and one store per word,
-// with all loads independent of the stores.  No data-dependent branches: lanes stay converged.
+// Per-lane output stream into the shared output tile.  Bytes are produced strictly in order; the
+// lane keeps the (up to 3) bytes that do not yet fill a word in a register and stores whole aligned
+// words.  Words shared with another writer are written bytewise: the first `ragged` bytes (up to
+// the first word boundary) and whatever is pending at os_end.  Inside a run the pending-byte count
+// is constant, so the inner loop is one load, one funnel shift and one store per word, with all
+// loads independent of the stores.
 struct OutStream {
-  uint32_t wpos;  // shared address (multiple of 4) of the next word to store
-  uint32_t lo;    // pending bytes: low `nb` bytes valid, the rest zero
-  uint32_t nb;    // 0..3
+  uint32_t wpos;    // shared address of the next byte (while ragged) / word to write
+  uint32_t lo;      // pending bytes: low `nb` bytes valid, the rest zero
+  uint32_t nb;      // 0..3
+  uint32_t ragged;  // bytes still to write bytewise before wpos is word aligned
 };
 
-// append the n (0..4) low bytes of v; bytes of v above n must be zero
-__device__ __forceinline__ void os_put(OutStream& o, uint32_t v, uint32_t n) {
-  const uint32_t sh = o.nb * 8u;
-  const uint32_t word = o.lo | (v << sh);
-  const uint32_t tot = o.nb + n;
-  const bool full = tot >= 4u;
-  if (full) sts32(o.wpos, word);                       // predicated store, not a branch
-  o.wpos += full ? 4u : 0u;
-  o.lo = full ? __funnelshift_l(v, 0u, sh) : word;     // v >> (32 - sh); 0 when sh == 0
-  o.nb = tot & 3u;
+__device__ __forceinline__ void os_begin(OutStream& o, uint32_t d) {
+  o.wpos = d;
+  o.ragged = (4u - (d & 3u)) & 3u;
+  o.lo = 0;
+  o.nb = 0;
 }
 
-// append [s, s+len) of shared memory (any alignment)
-__device__ __forceinline__ void os_run(OutStream& o, uint32_t s, uint32_t len) {
-  uint32_t sp = s & ~3u;
-  const uint32_t a = s & 3u;
-  uint32_t n0 = 4u - a;
-  n0 = n0 < len ? n0 : len;
-  // first (partial) source word; the load is harmless when len == 0
-  uint32_t w = lds32(sp) >> (8u * a);
-  w = n0 < 4u ? (w & ((1u << (8u * n0)) - 1u)) : w;
-  os_put(o, w, n0);
-  len -= n0;
-  sp += 4;
-  const uint32_t nw = len >> 2;
-  if (nw) {
+// Append n (1..32) bytes starting at shared address s (any alignment) to a word-aligned stream.
+// One batch of independent loads, then register work, then stores: a single shared-memory round
+// trip per chunk, which is what bounds a lane copying many short runs.  The 9 aligned words read
+// cover [s, s+32) at any alignment (bytes past the run are read but never used); source
+// misalignment a and the stream's pending bytes nb fold into one funnel shift.
+__device__ __forceinline__ void os_chunk(OutStream& o, uint32_t s, uint32_t n) {
+  const uint32_t sp = s & ~3u, a = s & 3u;
+  uint32_t w0 = lds32(sp), w1 = lds32(sp + 4), w2 = lds32(sp + 8), w3 = lds32(sp + 12), w4 = lds32(sp + 16);
+  uint32_t w5 = lds32(sp + 20), w6 = lds32(sp + 24), w7 = lds32(sp + 28), w8 = lds32(sp + 32), w9 = 0;
+  // output word q holds stream bytes [4q, 4q+4); stream byte j >= nb is source byte (a - nb + j) of w[]
+  int delta = (int)a - (int)o.nb;
+  if (delta < 0) {  // shift the window by one word so that the funnel amount is non-negative
+    w9 = w8; w8 = w7; w7 = w6; w6 = w5; w5 = w4; w4 = w3; w3 = w2; w2 = w1; w1 = w0; w0 = 0;
+    delta += 4;
+  }
+  const uint32_t sh = 8u * (uint32_t)delta;
+  uint32_t v0 = __funnelshift_r(w0, w1, sh);
+  const uint32_t v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+  const uint32_t v3 = __funnelshift_r(w3, w4, sh), v4 = __funnelshift_r(w4, w5, sh);
+  const uint32_t v5 = __funnelshift_r(w5, w6, sh), v6 = __funnelshift_r(w6, w7, sh);
+  const uint32_t v7 = __funnelshift_r(w7, w8, sh), v8 = __funnelshift_r(w8, w9, sh);
+  const uint32_t keep = (1u << (8u * o.nb)) - 1u;  // nb <= 3
+  v0 = (v0 & ~keep) | o.lo;
+  const uint32_t tot = o.nb + n, nfull = tot >> 2, rem = tot & 3u;  // nfull <= 8
+  const uint32_t d = o.wpos;
+  if (nfull > 0) sts32(d, v0);
+  if (nfull > 1) sts32(d + 4, v1);
+  if (nfull > 2) sts32(d + 8, v2);
+  if (nfull > 3) sts32(d + 12, v3);
+  if (nfull > 4) sts32(d + 16, v4);
+  if (nfull > 5) sts32(d + 20, v5);
+  if (nfull > 6) sts32(d + 24, v6);
+  if (nfull > 7) sts32(d + 28, v7);
+  uint32_t last = v8;
+  last = nfull == 7 ? v7 : last;
+  last = nfull == 6 ? v6 : last;
+  last = nfull == 5 ? v5 : last;
+  last = nfull == 4 ? v4 : last;
+  last = nfull == 3 ? v3 : last;
+  last = nfull == 2 ? v2 : last;
+  last = nfull == 1 ? v1 : last;
+  last = nfull == 0 ? v0 : last;
+  o.wpos = d + 4u * nfull;
+  o.lo = last & ((1u << (8u * rem)) - 1u);
+  o.nb = rem;
+}
+
+// append [s, s+len) of shared memory (any alignment), len > 0.  Deliberately a real call (the
+// stream state travels in registers): inlined at every use it made the kernel ~160 KB of code,
+// several times the instruction cache the three warp roles share, and instruction-fetch stalls
+// dominated the profile.
+__device__ __noinline__ OutStream os_run_f(OutStream o, uint32_t s, uint32_t len) {
+  while (o.ragged && len) {  // at most 3 bytes per stream
+    sts8(o.wpos, lds8(s));
+    ++o.wpos; ++s; --len; --o.ragged;
+  }
+  if (len == 0) return o;
+  {  // first chunk: up to the source's next 32-byte-window boundary, which word-aligns the source
+    uint32_t n = 32u - (s & 3u);
+    n = n < len ? n : len;
+    os_chunk(o, s, n);
+    s += n;
+    len -= n;
+  }
+  if (len >= 32u) {  // long run: source is word aligned and the pending-byte count stays constant
     const uint32_t sh = o.nb * 8u;
     uint32_t prev = sh ? (o.lo << (32u - sh)) : 0u;  // so that funnelshift_l(prev, w, sh) = lo | w << sh
     uint32_t dp = o.wpos;
-    uint32_t i = 0;
-    for (; i + 8 <= nw; i += 8) {
-      const uint32_t w0 = lds32(sp), w1 = lds32(sp + 4), w2 = lds32(sp + 8), w3 = lds32(sp + 12);
-      const uint32_t w4 = lds32(sp + 16), w5 = lds32(sp + 20), w6 = lds32(sp + 24), w7 = lds32(sp + 28);
+    do {
+      const uint32_t w0 = lds32(s), w1 = lds32(s + 4), w2 = lds32(s + 8), w3 = lds32(s + 12);
+      const uint32_t w4 = lds32(s + 16), w5 = lds32(s + 20), w6 = lds32(s + 24), w7 = lds32(s + 28);
       sts32(dp, __funnelshift_l(prev, w0, sh));
       sts32(dp + 4, __funnelshift_l(w0, w1, sh));
       sts32(dp + 8, __funnelshift_l(w1, w2, sh));
@@ -349,22 +395,17 @@ __device__ __forceinline__ void os_run(OutStream& o, uint32_t s, uint32_t len) {
       sts32(dp + 24, __funnelshift_l(w5, w6, sh));
       sts32(dp + 28, __funnelshift_l(w6, w7, sh));
       prev = w7;
-      sp += 32;
+      s += 32;
       dp += 32;
-    }
-    for (; i < nw; ++i) {
-      const uint32_t wi = lds32(sp);
-      sts32(dp, __funnelshift_l(prev, wi, sh));
-      prev = wi;
-      sp += 4;
-      dp += 4;
-    }
+      len -= 32;
+    } while (len >= 32u);
     o.lo = __funnelshift_l(prev, 0u, sh);
     o.wpos = dp;
   }
-  const uint32_t r = len & 3u;
-  if (r) os_put(o, lds32(sp) & ((1u << (8u * r)) - 1u), r);
+  if (len) os_chunk(o, s, len);
+  return o;
 }
+__device__ __forceinline__ void os_run(OutStream& o, uint32_t s, uint32_t len) { o = os_run_f(o, s, len); }
 
 __device__ __forceinline__ void os_end(const OutStream& o) {
   if (o.nb > 0) sts8(o.wpos, o.lo);
@@ -372,100 +413,105 @@ __device__ __forceinline__ void os_end(const OutStream& o) {
   if (o.nb > 2) sts8(o.wpos + 2, o.lo >> 16);
 }
 
-// One record of output at shared address `d` (any alignment).  `in`-side positions in r are shared
-// addresses too.
-__device__ __forceinline__ void emit_record(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d) {
-  // The first k0 <= 3 output bytes sit in a word shared with the previous record: write them
-  // bytewise, then stream from the word boundary.  They are the first bytes of '@'+head, or of the
-  // whole record when it is copied unchanged; a header too short to cover them (< 2 bytes) takes
-  // the plain bytewise path below.
-  const bool unchanged = ms < 0 && r.fast;
-  const uint32_t k0 = (4u - (d & 3u)) & 3u;
-  OutStream o;
-  uint32_t first_len = unchanged ? r.end - r.beg : 1u + r.head_len;
-  uint32_t src = r.beg;
-  if (first_len >= 3u) {
-    if (k0 > 0) sts8(d, lds8(src));
-    if (k0 > 1) sts8(d + 1, lds8(src + 1));
-    if (k0 > 2) sts8(d + 2, lds8(src + 2));
-    o.wpos = d + k0;
-    o.lo = 0;
-    o.nb = 0;
-    src += k0;
-    first_len -= k0;
-  } else {
-    // degenerate header (rare): plain bytewise path
-    uint32_t pos = d;
-    auto put_byte = [&](uint32_t c) { sts8(pos++, c); };
-    put_byte('@');
-    for (uint32_t i = 0; i < r.head_len; ++i) put_byte(lds8(r.beg + 1 + i));
-    if (ms >= 0) {
-      for (uint32_t c = 0; c < pg.ncaps; ++c) {
-        const bk_cap cap = pg.caps[c];
-        put_byte(' ');
-        for (uint32_t i = 0; i < cap.name_len; ++i) put_byte((uint8_t)cap.name[i]);
-        put_byte(':');
-        for (uint32_t i = 0; i < cap.len; ++i) put_byte(lds8(r.seq + ms + cap.off + i));
-        put_byte(':');
-        for (uint32_t i = 0; i < cap.len; ++i)
-          put_byte(ms + cap.off + i < r.qual_len ? lds8(r.qual + ms + cap.off + i) : (uint32_t)'!');
-      }
-    }
-    put_byte('\n');
-    const uint32_t T = (ms >= 0 && trim) ? pg.total_len : 0u;
-    const uint32_t cut = (ms >= 0 && trim) ? (uint32_t)ms : 0u;
-    for (uint32_t i = 0; i < r.seq_len; ++i)
-      if (i < cut || i >= cut + T) put_byte(lds8(r.seq + i));
-    put_byte('\n'); put_byte('+'); put_byte('\n');
-    for (uint32_t i = 0; i < r.qual_len; ++i)
-      if (i < cut || i >= cut + T) put_byte(lds8(r.qual + i));
-    put_byte('\n');
-    return;
+// append the n (0..4) low bytes of register value v (bytes of v above n must be zero)
+__device__ __noinline__ OutStream os_put_f(OutStream o, uint32_t v, uint32_t n) {
+  while (o.ragged && n) {  // stream not word aligned yet: bytewise
+    sts8(o.wpos, v);
+    ++o.wpos; v >>= 8; --n; --o.ragged;
   }
-  // `fast` records already carry the writer's framing, so neighbouring fields travel with their
-  // separators as one run ("\n+\n" after seq, "\n" after qual) and an unchanged record is one run.
-  os_run(o, src, first_len);
-  if (unchanged) {
+  const uint32_t sh = o.nb * 8u;
+  const uint32_t word = o.lo | (v << sh);
+  const uint32_t tot = o.nb + n;
+  const bool full = tot >= 4u;
+  if (full) sts32(o.wpos, word);                    // predicated store, not a branch
+  o.wpos += full ? 4u : 0u;
+  o.lo = full ? __funnelshift_l(v, 0u, sh) : word;  // v >> (32 - sh); 0 when sh == 0
+  o.nb = tot & 3u;
+  return o;
+}
+__device__ __forceinline__ void os_put(OutStream& o, uint32_t v, uint32_t n) { o = os_put_f(o, v, n); }
+
+constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is written by warp j
+
+// Part `part` (0..3) of one record's output at shared address d.  The record is
+//   '@' head { " NAME:" seq[cap] ":" qual[cap] }* "\n" seq[..s0) seq[e0..] "\n+\n" qual[..s0) qual[e0..] "\n"
+// (parse.rs:101-113,138-148,161-168; fastq.rs:261) and every field's destination offset is a closed
+// form of head_len, seq_len and the program's constants, so the four parts
+//   0: '@' head + first half of the captures     1: remaining captures + "\n"
+//   2: trimmed seq + "\n+\n"                       3: trimmed qual + "\n"
+// can be produced by four warps independently.  Parts meet at arbitrary byte positions; the words
+// they share are written bytewise by both sides (ragged head / os_end), never as whole words.
+// A record that is copied unchanged and already has the writer's framing (`fast`) is one run, cut
+// into four byte ranges.  Requires qual_len == seq_len for matched records (the front warp treats
+// anything else as unmatched; bk_tokenize never produces it).
+__device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
+                                          int part) {
+  OutStream o;
+  if (ms < 0 && r.fast) {
+    const uint32_t len = r.end - r.beg;
+    const uint32_t lo = len * part / kEmitParts, hi = len * (part + 1) / kEmitParts;
+    if (lo >= hi) return;
+    os_begin(o, d + lo);
+    os_run(o, r.beg + lo, hi - lo);
     os_end(o);
     return;
   }
-  if (ms >= 0) {
-    for (uint32_t c = 0; c < pg.ncaps; ++c) {  // pattern order (parse.rs:101)
+  const uint32_t ncaps = ms >= 0 ? pg.ncaps : 0u;
+  const uint32_t csplit = (ncaps + 1u) >> 1;
+  const uint32_t H = r.head_len, L = r.seq_len;
+  if (part < 2) {
+    // header line: captures [c0, c1) of it belong to this part
+    const uint32_t c0 = part == 0 ? 0u : csplit, c1 = part == 0 ? csplit : ncaps;
+    uint32_t off = 1u + H;
+#pragma unroll 1
+    for (uint32_t c = 0; c < c0; ++c) off += 3u + pg.caps[c].name_len + 2u * pg.caps[c].len;
+    if (part == 0) {
+      os_begin(o, d);
+      os_run(o, r.beg, 1u + H);  // '@' + head
+    } else {
+      os_begin(o, d + off);
+    }
+#pragma unroll 1
+    for (uint32_t c = c0; c < c1; ++c) {  // pattern order (parse.rs:101)
       const bk_cap cap = pg.caps[c];
-      // " NAME:"  (parse.rs:166): names are 2 or 3 bytes
       const uint32_t b3 = cap.name_len == 3 ? (uint32_t)(uint8_t)cap.name[2] : (uint32_t)':';
       os_put(o, (uint32_t)' ' | ((uint32_t)(uint8_t)cap.name[0] << 8) | ((uint32_t)(uint8_t)cap.name[1] << 16) |
-                    (b3 << 24), 4u);
-      os_put(o, cap.name_len == 3 ? (uint32_t)':' : 0u, cap.name_len == 3 ? 1u : 0u);
-      os_run(o, r.seq + ms + cap.off, cap.len);
+                    (b3 << 24), 4u);  // " NAME:"  (parse.rs:166); names are 2 or 3 bytes
+      if (cap.name_len == 3) os_put(o, (uint32_t)':', 1u);
+      if (cap.len) os_run(o, r.seq + ms + cap.off, cap.len);
       os_put(o, (uint32_t)':', 1u);
-      // qual shorter than seq cannot come out of bk_tokenize; clamp keeps the kernel memory-safe
-      const uint32_t qs = ms + cap.off < r.qual_len ? ms + cap.off : r.qual_len;
-      const uint32_t qe = ms + cap.off + cap.len < r.qual_len ? ms + cap.off + cap.len : r.qual_len;
-      os_run(o, r.qual + qs, qe - qs);
-      for (uint32_t i = qe - qs; i < cap.len; ++i) os_put(o, (uint32_t)'!', 1u);
+      if (cap.len) os_run(o, r.qual + ms + cap.off, cap.len);
+    }
+    if (part == 1) os_put(o, (uint32_t)'\n', 1u);
+    os_end(o);
+    return;
+  }
+  const uint32_t G = ms >= 0 ? pg.hdr_growth : 0u;
+  const bool cut = ms >= 0 && trim;  // parse.rs:138-148: cut [s0, e0) out of seq and qual
+  const uint32_t cs = cut ? (uint32_t)ms : 0u, ce = cut ? (uint32_t)ms + pg.total_len : 0u;
+  const uint32_t kept = L - (ce - cs);
+  const uint32_t kSep = (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16);
+  if (part == 2) {
+    os_begin(o, d + 2u + H + G);
+    if (cs) os_run(o, r.seq, cs);
+    if (r.fast) {
+      os_run(o, r.seq + ce, L - ce + 3u);  // the "\n+\n" after seq travels with the run
+    } else {
+      if (L > ce) os_run(o, r.seq + ce, L - ce);
+      os_put(o, kSep, 3u);
+    }
+  } else {
+    os_begin(o, d + 2u + H + G + kept + 3u);
+    const uint32_t ql = r.qual_len;  // == L for matched records; an unmatched one is not cut
+    const uint32_t qs = cs < ql ? cs : ql, qe = ce < ql ? ce : ql;
+    if (qs) os_run(o, r.qual, qs);
+    if (r.fast) {
+      os_run(o, r.qual + qe, ql - qe + 1u);  // with its "\n"
+    } else {
+      if (ql > qe) os_run(o, r.qual + qe, ql - qe);
+      os_put(o, (uint32_t)'\n', 1u);
     }
   }
-  os_put(o, (uint32_t)'\n', 1u);
-  const uint32_t sep = r.fast ? 3u : 0u, eol = r.fast ? 1u : 0u;  // separators copied with the run
-  const uint32_t kSep = (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16);
-  if (ms >= 0 && trim) {  // parse.rs:138-148: cut [start0, end0) out of seq and qual
-    const uint32_t T = pg.total_len;
-    os_run(o, r.seq, ms);
-    os_run(o, r.seq + ms + T, r.seq_len - ms - T + sep);
-    os_put(o, r.fast ? 0u : kSep, r.fast ? 0u : 3u);
-    const uint32_t qs = (uint32_t)ms < r.qual_len ? (uint32_t)ms : r.qual_len;
-    const uint32_t qe = (uint32_t)ms + T < r.qual_len ? (uint32_t)ms + T : r.qual_len;
-    os_run(o, r.qual, qs);
-    os_run(o, r.qual + qe, r.qual_len - qe + eol);
-  } else if (r.fast) {
-    os_run(o, r.seq, r.end - r.seq);  // seq LF + LF qual LF
-  } else {
-    os_run(o, r.seq, r.seq_len);
-    os_put(o, kSep, 3u);
-    os_run(o, r.qual, r.qual_len);
-  }
-  os_put(o, r.fast ? 0u : (uint32_t)'\n', r.fast ? 0u : 1u);
   os_end(o);
 }
 

@@ -15,6 +15,7 @@ struct BP {
   int matched;   // 1: R1-style matched+trim record, 0: unchanged record (one run)
   int rec_bytes; // record length in the input tile
   int warps;
+  int parts, part;
 };
 
 __global__ void emit_bench(const __grid_constant__ BP P, const uint8_t* tile, uint32_t tile_bytes,
@@ -39,7 +40,11 @@ __global__ void emit_bench(const __grid_constant__ BP P, const uint8_t* tile, ui
   __syncwarp();
   long long t0 = clock64();
   for (int it = 0; it < P.iters; ++it) {
-    emit_record(P.pg, rv, ms, true, out_a + (it & 15) + ooff);
+    {
+      const uint32_t d = out_a + (it & 15) + ooff;
+      if (P.parts > 1) emit_part(P.pg, rv, ms, true, d, P.part);
+      else for (int q = 0; q < 4; ++q) emit_part(P.pg, rv, ms, true, d, q);
+    }
     __syncwarp();
   }
   long long t1 = clock64();
@@ -78,6 +83,8 @@ int main(int argc, char** argv) {
   P.matched = matched;
   P.rec_bytes = rl;
   P.warps = warps;
+  P.parts = argc > 5 ? atoi(argv[5]) : 1;
+  P.part = argc > 6 ? atoi(argv[6]) : 0;
   uint8_t* d_tile;
   unsigned long long* d_cyc;
   uint32_t* d_sink;
@@ -95,7 +102,7 @@ int main(int argc, char** argv) {
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
   unsigned long long cyc;
   cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
-  printf("ctas/sm %d warps/cta %d matched %d: %.0f cycles per tile-emit per warp\n", ctas_per_sm, warps, matched,
+  printf("ctas/sm %d warps/cta %d matched %d part %d/%d: %.0f cycles per tile-emit per warp\n", ctas_per_sm, warps, matched, P.part, P.parts,
          (double)cyc / ((double)grid * warps * P.iters));
   return 0;
 }
