@@ -210,18 +210,14 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from barkit_b200 import multigpu
+    dev = "cuda:%d" % local_rank if dist is not None else None
+
     def barrier():
-        if dist is not None:
-            t = torch.zeros(1, device="cuda")
-            dist.all_reduce(t)
-            torch.cuda.synchronize()
+        multigpu.barrier(dist, dev)
 
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return multigpu.max_over_ranks(x, dist, dev)
 
     if _lib.device_count() <= local_rank:
         raise SystemExit("bench.py: no CUDA device %d; the extract path has no CPU fallback" % local_rank)
@@ -244,7 +240,7 @@ def main():
         return mates
 
     # distinct batches per rank and per step slot: rank r owns records [r*2^36 + b*P, ...)
-    batches = [make_batch((rank << 36) + b * P, P) for b in range(nbatch)]
+    batches = [make_batch(multigpu.rank_first_index(rank, b, P), P) for b in range(nbatch)]
     cap1 = ctx.out_bound(1, P, P * rl)
     cap2 = ctx.out_bound(2, P, P * rl)
     d_o1, d_o2 = ctx.dev_alloc(cap1), ctx.dev_alloc(cap2)
