@@ -5,7 +5,7 @@
 
 namespace bk {
 
-constexpr int kStages = 2;  // input ring depth per mate (front warp runs at most this far ahead)
+constexpr int kStages = 3;  // input ring depth per mate (front warp runs at most this far ahead)
 constexpr int kBackWarps = kEmitParts;  // back warps per mate: warp j writes part j of every record (emit_part)
 
 // ---- ordered compaction: decoupled look-back over tiles ------------------------------------------------
@@ -112,6 +112,7 @@ __device__ __forceinline__ void back_sync(int m) {
 constexpr int kSkipTile = -2147483647 - 1;
 constexpr uint32_t kEndTile = 0xFFFFFFFFu;
 constexpr uint32_t kNotKept = 0xFFFFFFFFu;
+constexpr uint32_t kNoPrefetch = 0xFFFFFFFEu;
 
 struct TileMeta {  // front -> back hand-over, one per (mate, stage); SoA so lanes do not conflict
   uint32_t beg[32], end[32], head_len[32], seq[32], seq_len[32], qual[32], qual_len_fast[32];
@@ -124,7 +125,7 @@ struct TileMeta {  // front -> back hand-over, one per (mate, stage); SoA so lan
 };
 
 template <bool PAIRED>
-__global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 3) extract_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) extract_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
   __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_pub[2][kStages], bar_ready[2][kStages],
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 3) e
   __shared__ uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, then the complement table
   __shared__ int s_ms[2][2][32];  // [tile parity][mate][lane]
   __shared__ uint32_t s_tile[2];  // [tile parity]
+  __shared__ uint32_t s_pref[2];  // [tile parity] tile claimed ahead by front warp 0, or kNoPrefetch
   __shared__ TileMeta meta[NM][kStages];
 
   const int lane = threadIdx.x & 31;
@@ -180,25 +182,55 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 3) e
     // =============================== FRONT ======================================================
     const uint8_t* const text = P.text[m];
     const uint32_t* const off = P.off[m];
+    // Start the load of `tile` into ring slot `slot`: record offsets, then one 1-D TMA copy of the
+    // tile's contiguous text range.  Returns this lane's record bounds inside the staged tile.
+    struct Staged { uint32_t rb, re, nrec; bool too_big; };
+    auto stage_tile = [&](uint32_t tile, uint32_t slot) -> Staged {
+      Staged st;
+      const uint32_t r0 = tile * R;
+      st.nrec = min(R, P.n - r0);
+      const uint32_t o = lane < (int)st.nrec ? off[r0 + lane] : 0;
+      const uint32_t oe = off[r0 + st.nrec];
+      uint32_t onext = __shfl_down_sync(0xffffffffu, o, 1);
+      if (lane == (int)st.nrec - 1) onext = oe;
+      const uint32_t gbase = __shfl_sync(0xffffffffu, o, 0) & ~15u;
+      const uint32_t bytes = ((oe + 15u) & ~15u) - gbase;
+      st.too_big = bytes > in_stride;  // host sized the ring from max_rec_bytes
+      st.rb = o - gbase;
+      st.re = onext - gbase;
+      if (!st.too_big && lane == 0) {
+        mbar_arrive_expect_tx(&bar_full[m][slot], bytes);
+        bulk_g2s(in_ring + slot * in_stride, text + gbase, bytes, &bar_full[m][slot]);
+      }
+      return st;
+    };
     PROF_INIT
+    bool have = false;  // tile of this iteration already claimed and its load in flight
+    uint32_t tile = 0;
+    Staged cur = {0, 0, 0, false};
     for (uint32_t k = 0;; ++k) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
       TileMeta& tm = meta[m][s];
-      mbar_wait(&bar_empty[m][s], ph ^ 1u);  // slot free (passes immediately for the first kStages tiles)
-      PROF(0)
-
-      // claim the next tile only now, with the slot in hand: the aggregate follows within one load
-      uint32_t tile;
-      if (PAIRED) {
-        if (m == 0 && lane == 0) s_tile[k & 1] = atomicAdd(P.tile_counter, 1u);
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        tile = s_tile[k & 1];
-      } else {
-        tile = 0;
-        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (!have) {
+        // slot free -- on BOTH mates before anyone claims: a tile claimed while the other mate's front
+        // warp still waits for its slot would sit unpublished behind that wait
+        mbar_wait(&bar_empty[m][s], ph ^ 1u);
+        if (PAIRED) mbar_wait(&bar_empty[m ^ 1][s], ph ^ 1u);
+        PROF(0)
+        // claim with the slot in hand: the aggregate follows within one load + parse
+        if (PAIRED) {
+          if (m == 0 && lane == 0) s_tile[k & 1] = atomicAdd(P.tile_counter, 1u);
+          asm volatile("bar.sync 1, 64;" ::: "memory");
+          tile = s_tile[k & 1];
+        } else {
+          tile = 0;
+          if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+          tile = __shfl_sync(0xffffffffu, tile, 0);
+        }
+        PROF(1)
+        if (tile < P.ntiles) cur = stage_tile(tile, s);
+        PROF(2)
       }
-      PROF(1)
       if (tile >= P.ntiles) {
         if (lane == 0) {
           tm.tile = kEndTile;
@@ -206,34 +238,43 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 3) e
         }
         break;
       }
-      const uint32_t r0 = tile * R;
-      const uint32_t nrec = min(R, P.n - r0);
-      const bool active = lane < (int)nrec;
+      // ---- prefetch: if the next ring slot is already free (both mates), claim tile k+1 now and
+      // put its load in flight behind this tile's parse + match.  Holding a claimed tile through a
+      // bounded amount of own work is fine; what must never happen is waiting on OTHER tiles with
+      // an unpublished claim in hand, hence "only if the slot is free right now".
+      const uint32_t s1 = (k + 1) % kStages, ph1 = ((k + 1) / kStages) & 1u;
+      uint32_t nxt = kNoPrefetch;
+      if (PAIRED) {
+        if (m == 0 && lane == 0) {
+          const bool ok = mbar_test(&bar_empty[0][s1], ph1 ^ 1u) && mbar_test(&bar_empty[1][s1], ph1 ^ 1u);
+          s_pref[(k + 1) & 1] = ok ? atomicAdd(P.tile_counter, 1u) : kNoPrefetch;
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        nxt = s_pref[(k + 1) & 1];
+      } else {
+        if (lane == 0 && mbar_test(&bar_empty[0][s1], ph1 ^ 1u)) nxt = atomicAdd(P.tile_counter, 1u);
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+      }
+      Staged nst = {0, 0, 0, false};
+      if (nxt != kNoPrefetch && nxt < P.ntiles) {
+        mbar_wait(&bar_empty[m][s1], ph1 ^ 1u);  // already complete; acquires the slot for this warp
+        nst = stage_tile(nxt, s1);
+      }
 
-      // ---- load: this mate's contiguous text range of the tile --------------------------------
-      const uint32_t o = active ? off[r0 + lane] : 0;
-      const uint32_t oe = off[r0 + nrec];
-      uint32_t onext = __shfl_down_sync(0xffffffffu, o, 1);
-      if (lane == (int)nrec - 1) onext = oe;
-      const uint32_t gbase = __shfl_sync(0xffffffffu, o, 0) & ~15u;
-      const uint32_t bytes = ((oe + 15u) & ~15u) - gbase;
-      const bool too_big = bytes > in_stride;  // host sized the ring from max_rec_bytes
-      PROF(2)
-      const uint32_t rb = o - gbase, re = onext - gbase;
+      const uint32_t r0 = tile * R;
+      const uint32_t nrec = cur.nrec;
+      const bool active = lane < (int)nrec;
+      const bool too_big = cur.too_big;
       const uint32_t in_s = in_ring + s * in_stride;
       RecView rv;
       rv.beg = rv.end = rv.fast = rv.head_len = rv.seq = rv.seq_len = rv.qual = rv.qual_len = 0;
       int ms = -1;
       if (!too_big) {
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&bar_full[m][s], bytes);
-          bulk_g2s(in_s, text + gbase, bytes, &bar_full[m][s]);
-        }
         mbar_wait(&bar_full[m][s], ph);
         PROF(3)
         // ---- parse + match (lane per record) ---------------------------------------------------
         if (active) {
-          rv = parse_record(in_s + rb, in_s + re);
+          rv = parse_record(in_s + cur.rb, in_s + cur.re);
           if (pg.present && rv.qual_len == rv.seq_len) {  // unequal lengths never leave bk_tokenize
             ms = match_read<false>(pg, tab, rv.seq, rv.seq_len);
             if (ms < 0 && rc) ms = match_read<true>(pg, tab, rv.seq, rv.seq_len);  // parse.rs:61-66
@@ -296,6 +337,11 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 3) e
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_pub[m][s]);
       PROF(6)
+      have = nxt != kNoPrefetch;
+      if (have) {
+        tile = nxt;
+        cur = nst;
+      }
     }
     PROF_FLUSH(0)
   } else if (is_scan) {
