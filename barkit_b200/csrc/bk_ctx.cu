@@ -120,7 +120,7 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, (PAIRED ? 2 : 1) * (2 + bk::kBackWarps) * 32, lp->smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, bk::cta_warps(PAIRED) * 32, lp->smem));
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
@@ -173,16 +173,16 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.result = (bk::DevResult*)(sc + 64);
   P.prof = (unsigned long long*)(sc + 256);
   P.desc[0] = (unsigned long long*)(sc + 512);
-  P.desc[1] = P.desc[0] + lp.ntiles;
+  P.desc[1] = nullptr;  // one 16-byte descriptor per tile: {stream 0, stream 1}
   P.n = n;
   P.ntiles = lp.ntiles;
   P.tile_recs = lp.tile_recs;
   P.flags = ctx->flags;
   if (n > 0) {
     if (ctx->paired)
-      bk::extract_kernel<true><<<lp.grid, 2 * (2 + bk::kBackWarps) * 32, lp.smem, stream>>>(P);
+      bk::extract_kernel<true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
     else
-      bk::extract_kernel<false><<<lp.grid, (2 + bk::kBackWarps) * 32, lp.smem, stream>>>(P);
+      bk::extract_kernel<false><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
     CK(cudaGetLastError());
     if (launches) *launches += 1;
   }

@@ -5,89 +5,97 @@
 
 namespace bk {
 
-constexpr int kStages = 3;  // input ring depth per mate (front warp runs at most this far ahead)
+constexpr int kStages = 3;  // input ring depth per mate (the loader runs at most this far ahead)
 constexpr int kBackWarps = kEmitParts;  // back warps per mate: warp j writes part j of every record (emit_part)
 
 // ---- ordered compaction: decoupled look-back over tiles ------------------------------------------------
+//
+// One 16-byte descriptor per tile: {stream 0, stream 1}, each a 62-bit value tagged kFlagAgg (the
+// tile's own output bytes on that stream) or kFlagPrefix (inclusive prefix over all tiles up to and
+// including this one).  The two front warps publish their halves independently; one scan warp
+// resolves both streams with a single pass over the predecessors.
 
-__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+constexpr int kLookWindows = 8;  // 32-descriptor windows fetched per round (independent loads in flight)
+
+__device__ __forceinline__ ulonglong2 ld_desc(const unsigned long long* p) {
+  ulonglong2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
+// usable once both halves carry the same tag (a half-updated descriptor is simply read again)
+__device__ __forceinline__ bool desc_ready(const ulonglong2& d, bool two) {
+  const unsigned f0 = (unsigned)(d.x >> 62), f1 = (unsigned)(d.y >> 62);
+  return f0 != 0 && (!two || f1 == f0);
+}
 
-constexpr int kLookWindows = 4;  // 32-descriptor windows fetched per round (independent loads in flight)
-
-// Exclusive prefix of tile `tile` over all earlier tiles.  The tile's own aggregate has already been
-// published (by the front warp); this publishes the inclusive prefix once it is known.
 #ifdef BK_PROFILE_PHASES
 __device__ unsigned long long g_look_rounds, g_look_spins, g_look_windows;
 #endif
-__device__ __noinline__ unsigned long long lookback(unsigned long long* desc, uint32_t tile,
-                                                       unsigned long long agg, int lane) {
-  unsigned long long excl = 0;
+// Exclusive prefixes of tile `tile` on both streams.  The tile's own aggregates have already been
+// published (by the front warps); this publishes the inclusive prefixes once they are known.
+__device__ __noinline__ ulonglong2 lookback(unsigned long long* desc, uint32_t tile, uint32_t agg0, uint32_t agg1,
+                                            bool two, int lane) {
+  unsigned long long e0 = 0, e1 = 0;
   if (tile != 0) {
     int look = (int)tile - 1;
     bool done = false;
     while (!done) {
-#ifdef BK_PROFILE_PHASES
-      if (lane == 0) atomicAdd(&g_look_rounds, 1ull);
-#endif
-      unsigned long long d[kLookWindows];
+      ulonglong2 d[kLookWindows];
 #pragma unroll
       for (int j = 0; j < kLookWindows; ++j) {
         const int idx = look - 32 * j - lane;
-        d[j] = idx >= 0 ? ld_relaxed_u64(desc + idx) : kFlagPrefix;  // virtual tiles before 0: prefix 0
+        d[j] = idx >= 0 ? ld_desc(desc + 2 * (size_t)idx) : make_ulonglong2(kFlagPrefix, kFlagPrefix);  // before tile 0: prefix 0
       }
 #pragma unroll
       for (int j = 0; j < kLookWindows; ++j) {
         if (done) break;
         const int idx = look - 32 * j - lane;
-#ifdef BK_PROFILE_PHASES
-        if (lane == 0) atomicAdd(&g_look_windows, 1ull);
-#endif
-        while (__any_sync(0xffffffffu, (d[j] >> 62) == 0)) {
-#ifdef BK_PROFILE_PHASES
-          if (lane == 0) atomicAdd(&g_look_spins, 1ull);
-#endif
-          if ((d[j] >> 62) == 0) d[j] = ld_relaxed_u64(desc + idx);
+        while (__any_sync(0xffffffffu, !desc_ready(d[j], two))) {
+          if (!desc_ready(d[j], two)) d[j] = ld_desc(desc + 2 * (size_t)idx);
         }
-        const unsigned pm = __ballot_sync(0xffffffffu, (d[j] >> 62) == 2);
-        // aggregates are one tile's bytes (32 bits is plenty); only the prefix itself is 64-bit
-        const unsigned long long v = d[j] & kValueMask;
-        const int first = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor holding an inclusive prefix
-        excl += warp_sum_u32(lane < first ? (uint32_t)v : 0u);
+        const unsigned pm = __ballot_sync(0xffffffffu, (d[j].x >> 62) == 2);
+        const int first = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor holding inclusive prefixes
+        // aggregates are one tile's bytes (32 bits is plenty); only the prefixes themselves are 64-bit
+        e0 += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)d[j].x : 0u);
+        if (two) e1 += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)d[j].y : 0u);
         if (pm) {
-          excl += __shfl_sync(0xffffffffu, v, first);
+          e0 += __shfl_sync(0xffffffffu, d[j].x & kValueMask, first);
+          if (two) e1 += __shfl_sync(0xffffffffu, d[j].y & kValueMask, first);
           done = true;
         }
       }
       look -= 32 * kLookWindows;
     }
   }
-  if (lane == 0) st_relaxed_u64(desc + tile, kFlagPrefix | (excl + agg));
-  return excl;
+  if (lane == 0) {
+    unsigned long long* p = desc + 2 * (size_t)tile;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(kFlagPrefix | (e0 + agg0)),
+                 "l"(kFlagPrefix | (e1 + agg1))
+                 : "memory");
+  }
+  return make_ulonglong2(e0, e1);
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------
 //
-// Per mate m (one for single-end, two for paired-end) a FRONT warp and a BACK warp share a ring of
-// kStages staged input tiles:
+// One LOADER warp per CTA feeds a ring of kStages staged input tiles per mate (one mate for
+// single-end, two for paired-end); per mate a FRONT warp, a SCAN warp and kBackWarps BACK warps
+// drain it:
 //
-//   front F_m : wait ring slot free -> claim tile (global counter, in order) -> TMA load -> parse ->
-//               match -> exchange match decisions with the other mate's front warp (PE keep rule,
-//               run.rs:149-160) -> sizes + warp scan -> PUBLISH the tile aggregate -> hand the slot on
+//   loader L  : wait ring slot free (both mates) -> claim tile (global counter, in order) -> record
+//               offsets -> one 1-D TMA load per mate of the tile's contiguous text range
+//   front F_m : wait tile landed -> parse -> match -> exchange match decisions with the other mate's
+//               front warp (PE keep rule, run.rs:149-160) -> sizes + warp scan -> PUBLISH the tile
+//               aggregate -> hand the slot on
 //   scan  S_m : take slot -> look-back over earlier tiles -> publish the inclusive prefix -> pass the
-//               tile's global output offset to the back warp
-//   back  B_m : (kBackWarps warps) take slot -> each warp emits its word-aligned share of every
-//               record into the shared output tile -> release slot -> one of them issues the TMA store
+//               tile's global output offset to the back warps
+//   back  B_m : take slot -> assemble the tile's output in shared memory (header lines lane per
+//               record, long runs warp-cooperatively) -> release slot -> one warp issues the TMA store
 //
-// The front warp never waits on another tile's result, so a claimed tile's aggregate is published
-// after a short, bounded delay; that is what keeps every other tile's look-back from stalling (a
-// warp that both publishes and waits delays its own next aggregate by its wait, and the delay
-// compounds down the chain).  The scan warp resolves prefixes as soon as aggregates exist, so
-// look-backs stay short, and its spinning costs nobody's critical path.  Lane i of a front/back
-// warp owns record i of the tile.
+// Claim, offset fetch and load latency sit in the loader, off the front warp's critical path, and
+// every role only ever waits on its own ring slot, so a claimed tile's aggregate is published
+// after a bounded delay; that is what keeps every other tile's look-back from stalling.  Lane i of
+// a front/back warp owns record i of the tile.
 
 // Optional phase timers (compile with -DBK_PROFILE_PHASES): per-role cycle sums, lane 0 only.
 #ifdef BK_PROFILE_PHASES
@@ -109,42 +117,53 @@ __device__ __forceinline__ void back_sync(int m) {
     asm volatile("bar.sync 3, %0;" ::"n"(kBackWarps * 32) : "memory");
 }
 
-constexpr int kSkipTile = -2147483647 - 1;
-constexpr uint32_t kEndTile = 0xFFFFFFFFu;
-constexpr uint32_t kNotKept = 0xFFFFFFFFu;
-constexpr uint32_t kNoPrefetch = 0xFFFFFFFEu;
+// Named barriers (16 per CTA): 0 __syncthreads, 1 the front warps' exchange, 2-3 back_sync, then one
+// per ring slot for fronts -> scan ("aggregates published") and scan -> backs ("offsets known").
+// A slot's barrier is reused only after the slot went round the ring, i.e. after every consumer
+// has left it.
+static_assert(kStages <= 6, "barrier ids 4..15 hold two barriers per ring slot");
+__device__ __forceinline__ uint32_t pub_id(uint32_t s) { return 4u + s; }
+__device__ __forceinline__ uint32_t ready_id(uint32_t s) { return 4u + kStages + s; }
+constexpr int kScanWarps = 2;  // scan warp j resolves the tiles of ring rounds k with k % 2 == j
 
-struct TileMeta {  // front -> back hand-over, one per (mate, stage); SoA so lanes do not conflict
-  uint32_t beg[32], end[32], head_len[32], seq[32], seq_len[32], qual[32], qual_len_fast[32];
+constexpr int kSkipTile = -2147483647 - 1;
+constexpr uint32_t kEndTile = 0xFFFFFFFFu, kEndTile2 = 0xFFFFFFFEu;
+constexpr uint32_t kNotKept = 0xFFFFFFFFu;
+
+struct TileMeta {  // hand-over between the roles, one per (mate, stage); SoA so lanes do not conflict
+  uint32_t beg[32], end[32];  // record bounds, shared-memory addresses (loader)
+  uint32_t head_len[32], seq[32], seq_len[32], qual[32], qual_len_fast[32];  // (front)
   int32_t ms[32];
   uint32_t ooff[32];  // record's offset inside the tile's output, kNotKept if dropped
-  uint32_t olen[32];  // record's output bytes
-  uint32_t tile;      // kEndTile terminates the back warp
-  uint32_t total;     // output bytes of the tile on this stream
-  unsigned long long gout;  // global output offset of the tile on this stream
+  uint32_t tile;      // kEndTile terminates the consumers (loader)
+  uint32_t nrec;      // records in the tile (loader)
+  uint32_t too_big;   // tile does not fit the staging buffer: nothing was loaded (loader)
+  uint32_t total;     // output bytes of the tile on this stream (front)
+  unsigned long long gout;  // global output offset of the tile on this stream (scan)
 };
 
+constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (1 + kBackWarps) + kScanWarps + 1; }
+
 template <bool PAIRED>
-__global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) extract_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
-  __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_pub[2][kStages], bar_ready[2][kStages],
-      bar_empty[2][kStages];
+  __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_empty[2][kStages];
   __shared__ uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, then the complement table
   __shared__ int s_ms[2][2][32];  // [tile parity][mate][lane]
-  __shared__ uint32_t s_tile[2];  // [tile parity]
-  __shared__ uint32_t s_pref[2];  // [tile parity] tile claimed ahead by front warp 0, or kNoPrefetch
   __shared__ TileMeta meta[NM][kStages];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  // Warp roles, lowest warp ids first: back, scan, front.  The scheduler favours higher warp ids, and
-  // the front warps' claim -> publish latency is what every other tile's look-back waits on.
+  // Warp roles, lowest warp ids first: back, scan, front, loader.
   constexpr int NB = NM * kBackWarps;
-  const bool is_front = warp >= NB + NM;
-  const bool is_scan = !is_front && warp >= NB;
-  const int m = warp % NM;  // mate = output stream
-  const int bj = warp < NB ? warp / NM : 0;  // back warp index within the mate
+  const bool is_back = warp < NB;
+  const bool is_scan = !is_back && warp < NB + kScanWarps;
+  const bool is_front = !is_back && !is_scan && warp < NB + kScanWarps + NM;
+  const bool is_loader = warp == NB + kScanWarps + NM;
+  const int m = is_back ? warp % NM : is_front ? warp - NB - kScanWarps : 0;  // mate = output stream
+  const int bj = is_back ? warp / NM : 0;  // back warp index within the mate
+  constexpr uint32_t kPubCount = 32 * (NM + 1), kReadyCount = 32 * (1 + NB);
   const bk_devprog& pg = P.prog[m];
   const bool trim = !(P.flags & 2u);
   const bool rc = (P.flags & 4u) != 0;
@@ -153,8 +172,6 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) e
   // dynamic shared memory: [mate0 ring][mate1 ring][out0][out1]
   // (32-bit shared-space addresses; see the note at the top of bk_kernels.cuh)
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t in_ring = smem_base + (m ? kStages * P.in_cap[0] : 0);
-  const uint32_t in_stride = P.in_cap[m];
   const uint32_t out_s = smem_base + kStages * (P.in_cap[0] + (PAIRED ? P.in_cap[1] : 0)) + (m ? P.out_cap[0] : 0);
   const uint32_t tab = smem_u32(&cls_tab[m][0]);
 
@@ -170,111 +187,106 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) e
     if (lane == 0)
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&bar_full[m][s], 1);
-        mbar_init(&bar_pub[m][s], 1);
-        mbar_init(&bar_ready[m][s], 1);
         mbar_init(&bar_empty[m][s], kBackWarps);
       }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  if (is_front) {
-    // =============================== FRONT ======================================================
-    const uint8_t* const text = P.text[m];
-    const uint32_t* const off = P.off[m];
-    // Start the load of `tile` into ring slot `slot`: record offsets, then one 1-D TMA copy of the
-    // tile's contiguous text range.  Returns this lane's record bounds inside the staged tile.
-    struct Staged { uint32_t rb, re, nrec; bool too_big; };
-    auto stage_tile = [&](uint32_t tile, uint32_t slot) -> Staged {
-      Staged st;
-      const uint32_t r0 = tile * R;
-      st.nrec = min(R, P.n - r0);
-      const uint32_t o = lane < (int)st.nrec ? off[r0 + lane] : 0;
-      const uint32_t oe = off[r0 + st.nrec];
-      uint32_t onext = __shfl_down_sync(0xffffffffu, o, 1);
-      if (lane == (int)st.nrec - 1) onext = oe;
-      const uint32_t gbase = __shfl_sync(0xffffffffu, o, 0) & ~15u;
-      const uint32_t bytes = ((oe + 15u) & ~15u) - gbase;
-      st.too_big = bytes > in_stride;  // host sized the ring from max_rec_bytes
-      st.rb = o - gbase;
-      st.re = onext - gbase;
-      if (!st.too_big && lane == 0) {
-        mbar_arrive_expect_tx(&bar_full[m][slot], bytes);
-        bulk_g2s(in_ring + slot * in_stride, text + gbase, bytes, &bar_full[m][slot]);
-      }
-      return st;
-    };
+  if (is_loader) {
+    // =============================== LOADER =====================================================
     PROF_INIT
-    bool have = false;  // tile of this iteration already claimed and its load in flight
-    uint32_t tile = 0;
-    Staged cur = {0, 0, 0, false};
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
+      // slot free on every mate (passes immediately for the first kStages tiles)
+#pragma unroll
+      for (int mm = 0; mm < NM; ++mm) mbar_wait(&bar_empty[mm][s], ph ^ 1u);
+      PROF(0)
+      // claim with the slot in hand: the load starts at once and the aggregate follows a bounded
+      // time later
+      uint32_t tile = 0;
+      if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      PROF(1)
+      if (tile >= P.ntiles) {
+        // two end markers in consecutive slots: one per scan warp (they take alternate rounds); the
+        // first one also stops the back warps
+        const uint32_t s2 = (k + 1) % kStages, ph2 = ((k + 1) / kStages) & 1u;
+#pragma unroll
+        for (int mm = 0; mm < NM; ++mm) mbar_wait(&bar_empty[mm][s2], ph2 ^ 1u);
+        if (lane == 0)
+          for (int mm = 0; mm < NM; ++mm) {
+            meta[mm][s].tile = kEndTile;
+            mbar_arrive(&bar_full[mm][s]);
+            meta[mm][s2].tile = kEndTile2;
+            mbar_arrive(&bar_full[mm][s2]);
+          }
+        break;
+      }
+      const uint32_t r0 = tile * R;
+      const uint32_t nrec = min(R, P.n - r0);
+      uint32_t o[NM], oe[NM];
+#pragma unroll
+      for (int mm = 0; mm < NM; ++mm) {  // both mates' offsets in flight together
+        o[mm] = lane < (int)nrec ? P.off[mm][r0 + lane] : 0;
+        oe[mm] = P.off[mm][r0 + nrec];
+      }
+#pragma unroll
+      for (int mm = 0; mm < NM; ++mm) {
+        TileMeta& tm = meta[mm][s];
+        uint32_t onext = __shfl_down_sync(0xffffffffu, o[mm], 1);
+        if (lane == (int)nrec - 1) onext = oe[mm];
+        const uint32_t gbase = __shfl_sync(0xffffffffu, o[mm], 0) & ~15u;
+        const uint32_t bytes = ((oe[mm] + 15u) & ~15u) - gbase;
+        const bool too_big = bytes > P.in_cap[mm];  // host sized the ring from max_rec_bytes
+        const uint32_t in_s = smem_base + (mm ? kStages * P.in_cap[0] : 0) + s * P.in_cap[mm];
+        tm.beg[lane] = in_s + (o[mm] - gbase);
+        tm.end[lane] = in_s + (onext - gbase);
+        if (lane == 0) {
+          tm.tile = tile;
+          tm.nrec = nrec;
+          tm.too_big = too_big;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (too_big) {
+            mbar_arrive(&bar_full[mm][s]);
+          } else {
+            mbar_arrive_expect_tx(&bar_full[mm][s], bytes);
+            bulk_g2s(in_s, P.text[mm] + gbase, bytes, &bar_full[mm][s]);
+          }
+        }
+      }
+      PROF(2)
+    }
+    PROF_FLUSH(0)
+  } else if (is_front) {
+    // =============================== FRONT ======================================================
+    PROF_INIT
     for (uint32_t k = 0;; ++k) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
       TileMeta& tm = meta[m][s];
-      if (!have) {
-        // slot free -- on BOTH mates before anyone claims: a tile claimed while the other mate's front
-        // warp still waits for its slot would sit unpublished behind that wait
-        mbar_wait(&bar_empty[m][s], ph ^ 1u);
-        if (PAIRED) mbar_wait(&bar_empty[m ^ 1][s], ph ^ 1u);
-        PROF(0)
-        // claim with the slot in hand: the aggregate follows within one load + parse
-        if (PAIRED) {
-          if (m == 0 && lane == 0) s_tile[k & 1] = atomicAdd(P.tile_counter, 1u);
-          asm volatile("bar.sync 1, 64;" ::: "memory");
-          tile = s_tile[k & 1];
-        } else {
-          tile = 0;
-          if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
-          tile = __shfl_sync(0xffffffffu, tile, 0);
-        }
-        PROF(1)
-        if (tile < P.ntiles) cur = stage_tile(tile, s);
-        PROF(2)
+      mbar_wait(&bar_full[m][s], ph);  // offsets written, text landed
+      PROF(0)
+      const uint32_t tile = tm.tile;
+      if (tile == kEndTile || tile == kEndTile2) {
+        nbar_arrive(pub_id(s), kPubCount);
+        if (tile == kEndTile2) break;
+        continue;
       }
-      if (tile >= P.ntiles) {
-        if (lane == 0) {
-          tm.tile = kEndTile;
-          mbar_arrive(&bar_pub[m][s]);
-        }
-        break;
-      }
-      // ---- prefetch: if the next ring slot is already free (both mates), claim tile k+1 now and
-      // put its load in flight behind this tile's parse + match.  Holding a claimed tile through a
-      // bounded amount of own work is fine; what must never happen is waiting on OTHER tiles with
-      // an unpublished claim in hand, hence "only if the slot is free right now".
-      const uint32_t s1 = (k + 1) % kStages, ph1 = ((k + 1) / kStages) & 1u;
-      uint32_t nxt = kNoPrefetch;
-      if (PAIRED) {
-        if (m == 0 && lane == 0) {
-          const bool ok = mbar_test(&bar_empty[0][s1], ph1 ^ 1u) && mbar_test(&bar_empty[1][s1], ph1 ^ 1u);
-          s_pref[(k + 1) & 1] = ok ? atomicAdd(P.tile_counter, 1u) : kNoPrefetch;
-        }
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        nxt = s_pref[(k + 1) & 1];
-      } else {
-        if (lane == 0 && mbar_test(&bar_empty[0][s1], ph1 ^ 1u)) nxt = atomicAdd(P.tile_counter, 1u);
-        nxt = __shfl_sync(0xffffffffu, nxt, 0);
-      }
-      Staged nst = {0, 0, 0, false};
-      if (nxt != kNoPrefetch && nxt < P.ntiles) {
-        mbar_wait(&bar_empty[m][s1], ph1 ^ 1u);  // already complete; acquires the slot for this warp
-        nst = stage_tile(nxt, s1);
-      }
-
       const uint32_t r0 = tile * R;
-      const uint32_t nrec = cur.nrec;
+      const uint32_t nrec = tm.nrec;
       const bool active = lane < (int)nrec;
-      const bool too_big = cur.too_big;
-      const uint32_t in_s = in_ring + s * in_stride;
+      const bool too_big = tm.too_big != 0;
       RecView rv;
       rv.beg = rv.end = rv.fast = rv.head_len = rv.seq = rv.seq_len = rv.qual = rv.qual_len = 0;
       int ms = -1;
       if (!too_big) {
-        mbar_wait(&bar_full[m][s], ph);
-        PROF(3)
         // ---- parse + match (lane per record) ---------------------------------------------------
+        if (active) rv = parse_record(tm.beg[lane], tm.end[lane]);
+        __syncwarp();
+        PROF(1)
         if (active) {
-          rv = parse_record(in_s + cur.rb, in_s + cur.re);
           if (pg.present && rv.qual_len == rv.seq_len) {  // unequal lengths never leave bk_tokenize
             ms = match_read<false>(pg, tab, rv.seq, rv.seq_len);
             if (ms < 0 && rc) ms = match_read<true>(pg, tab, rv.seq, rv.seq_len);  // parse.rs:61-66
@@ -284,8 +296,8 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) e
       } else if (lane == 0) {
         atomicOr(&P.result->error, 2u);
       }
-
-      PROF(4)
+      __syncwarp();
+      PROF(2)
       // ---- exchange match decisions with the other mate's front warp -----------------------------
       int ms_other = -1;
       bool skip = too_big;
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) e
         ms_other = s_ms[k & 1][m ^ 1][lane];
         skip = skip || (s_ms[k & 1][m ^ 1][0] == kSkipTile);
       }
-      PROF(5)
+      PROF(3)
       // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
       const bool keep = !skip && active && (ms >= 0 || ms_other >= 0);
 
@@ -308,7 +320,7 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) e
         if (lane >= d) incl += t;
       }
       const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      if (lane == 0) st_relaxed_u64(P.desc[m] + tile, kFlagAgg | (unsigned long long)total);
+      if (lane == 0) st_relaxed_u64(P.desc[0] + 2 * (size_t)tile + m, kFlagAgg | (unsigned long long)total);
 
       {  // statistics
         const unsigned kb = __ballot_sync(0xffffffffu, keep);
@@ -319,9 +331,7 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) e
         }
       }
 
-      // ---- hand the slot to the back warp -------------------------------------------------------------
-      tm.beg[lane] = rv.beg;
-      tm.end[lane] = rv.end;
+      // ---- hand the slot to the scan and back warps ---------------------------------------------------
       tm.head_len[lane] = rv.head_len;
       tm.seq[lane] = rv.seq;
       tm.seq_len[lane] = rv.seq_len;
@@ -329,76 +339,166 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) e
       tm.qual_len_fast[lane] = (rv.qual_len << 1) | rv.fast;
       tm.ms[lane] = ms;
       tm.ooff[lane] = keep ? incl - olen : kNotKept;
-      tm.olen[lane] = olen;
-      if (lane == 0) {
-        tm.tile = tile;
-        tm.total = total;
-      }
+      if (lane == 0) tm.total = total;
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_pub[m][s]);
-      PROF(6)
-      have = nxt != kNoPrefetch;
-      if (have) {
-        tile = nxt;
-        cur = nst;
-      }
+      nbar_arrive(pub_id(s), kPubCount);
+      PROF(4)
     }
-    PROF_FLUSH(0)
+    PROF_FLUSH(8)
   } else if (is_scan) {
     // =============================== SCAN =======================================================
+    const int sj = warp - NB;
     PROF_INIT
-    for (uint32_t k = 0;; ++k) {
-      const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
-      TileMeta& tm = meta[m][s];
-      mbar_wait(&bar_pub[m][s], ph);
+    for (uint32_t k = sj;; k += kScanWarps) {
+      const uint32_t s = k % kStages;
+      nbar_sync(pub_id(s), kPubCount);
       PROF(0)
-      const uint32_t tile = tm.tile;
+      const uint32_t tile = meta[0][s].tile;
+      if (tile == kEndTile2) break;
       if (tile != kEndTile) {
-        const unsigned long long gout = lookback(P.desc[m], tile, tm.total, lane);
-        if (lane == 0) tm.gout = gout;
+        const ulonglong2 g = lookback(P.desc[0], tile, meta[0][s].total, PAIRED ? meta[NM - 1][s].total : 0u, PAIRED, lane);
+        if (lane == 0) {
+          meta[0][s].gout = g.x;
+          if (PAIRED) meta[NM - 1][s].gout = g.y;
+        }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_ready[m][s]);
+      nbar_arrive(ready_id(s), kReadyCount);
       PROF(1)
       if (tile == kEndTile) break;
     }
-    PROF_FLUSH(8)
+    if (sj == 0) { PROF_FLUSH(4) }
   } else {
     // =============================== BACK =======================================================
     uint8_t* const gdst = P.out[m];
+    const bool header_work = pg.present != 0;
     PROF_INIT
     for (uint32_t k = 0;; ++k) {
-      const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
+      const uint32_t s = k % kStages;
       const TileMeta& tm = meta[m][s];
-      mbar_wait(&bar_ready[m][s], ph);
+      nbar_sync(ready_id(s), kReadyCount);
       PROF(0)
       const uint32_t tile = tm.tile;
       if (tile == kEndTile) break;
       const uint32_t total = tm.total;
       const unsigned long long gout = tm.gout;
-      if (lane == 0 && tile == P.ntiles - 1) P.result->out_len[m] = gout + total;
+      if (lane == 0 && bj == 0 && tile == P.ntiles - 1) P.result->out_len[m] = gout + total;
       const bool fits = gout + total <= P.cap[m];
       if (!fits && lane == 0) atomicOr(&P.result->error, 1u);
       const uint32_t phase = (uint32_t)(gout & 15ull);
       if (fits && total) {
-        // ---- emit into the shared output tile (same 16-byte phase as the global destination) --------
+        // ---- assemble the tile's output in shared memory (same 16-byte phase as the global destination)
         const uint32_t ooff = tm.ooff[lane];
-        if (ooff != kNotKept) {
-          RecView rv;
-          rv.beg = tm.beg[lane];
-          rv.end = tm.end[lane];
-          rv.head_len = tm.head_len[lane];
-          rv.seq = tm.seq[lane];
-          rv.seq_len = tm.seq_len[lane];
-          rv.qual = tm.qual[lane];
-          const uint32_t qf = tm.qual_len_fast[lane];
-          rv.qual_len = qf >> 1;
-          rv.fast = qf & 1u;
-          emit_part(pg, rv, tm.ms[lane], trim, out_s + phase + ooff, bj);
+        const bool kept = ooff != kNotKept;
+        RecView rv;
+        rv.beg = tm.beg[lane];
+        rv.end = tm.end[lane];
+        rv.head_len = tm.head_len[lane];
+        rv.seq = tm.seq[lane];
+        rv.seq_len = tm.seq_len[lane];
+        rv.qual = tm.qual[lane];
+        const uint32_t qf = tm.qual_len_fast[lane];
+        rv.qual_len = qf >> 1;
+        rv.fast = qf & 1u;
+        const int ms = tm.ms[lane];
+        const uint32_t dst = out_s + phase + ooff;
+        const bool mat = kept && rv.fast && ms >= 0;  // rewritten, bulk-copied body
+        const bool unc = kept && rv.fast && ms < 0;   // unchanged, part of a bulk-copied run
+        const unsigned mm = __ballot_sync(0xffffffffu, mat);
+        const unsigned um = __ballot_sync(0xffffffffu, unc);
+
+        // (a) lane per record, through the stream writer: header lines of rewritten records (warps
+        //     0 and 1), the junctions of the bulk copies (warps 1..3), and every part of a record
+        //     whose framing is not the writer's own (rare: CR line ends, text after '+')
+        Body body;
+        Junctions jn;
+        body.dst = 0;
+        jn.hi[0] = 0;
+        if (mat) {
+          body = body_of(pg, rv, ms, trim, dst);
+          jn = body_junctions(body);
         }
+        if ((kept && !rv.fast) || (mat && bj < 2)) emit_part(pg, rv, ms, trim, dst, bj, mat, body, jn.hi[0]);
+        if (mat && bj >= 2) {
+#pragma unroll
+          for (int k = 1; k <= 4; ++k) {
+            if ((k == 4) != (bj == 3)) continue;  // warp 2: piece boundaries, warp 3: ragged tail
+            if (jn.lo[k] < jn.hi[k]) {
+              OutStream o;
+              os_begin(o, body.dst + jn.lo[k]);
+              body_range(o, body, jn.lo[k], jn.hi[k]);
+              os_end(o);
+            }
+          }
+        }
+        // runs of unchanged records: lane i learns its run [i0, i1]
+        uint32_t run_s = 0, run_d = 0, run_n = 0;
+        if (um) {
+          const unsigned below = ~um & ((1u << lane) - 1u);
+          const int i0 = unc ? (below ? 32 - __clz(below) : 0) : lane;
+          const unsigned above = ~(um >> lane);  // first zero at or above this lane ends the run
+          const int i1 = unc ? (above ? lane + __ffs(above) - 2 : 31) : lane;
+          run_s = __shfl_sync(0xffffffffu, rv.beg, i0);
+          run_d = __shfl_sync(0xffffffffu, dst, i0);
+          run_n = __shfl_sync(0xffffffffu, rv.end, i1) - run_s;
+          if (unc && bj >= 2) {
+            uint32_t pad = (16u - (run_d & 15u)) & 15u;
+            pad = pad < run_n ? pad : run_n;
+            const uint32_t t0 = ((run_d + run_n) & ~15u) - run_d;
+            const uint32_t tlo = (int32_t)t0 > (int32_t)pad ? t0 : pad;
+            if (bj == 2 && i0 == lane && pad) {  // ragged head of the run
+              OutStream o;
+              os_begin(o, run_d);
+              os_run(o, run_s, pad);
+              os_end(o);
+            }
+            if (bj == 3 && i1 == lane && tlo < run_n) {  // ragged tail
+              OutStream o;
+              os_begin(o, run_d + tlo);
+              os_run(o, run_s + tlo, run_n - tlo);
+              os_end(o);
+            }
+          }
+        }
+        __syncwarp();
+        PROF(1)
+        // (b) bulk, half a warp per piece: the trimmed seq and qual lines of rewritten records.
+        //     Warps 0 and 1 carry the header lines, so they take fewer records.
+        {
+          const unsigned share = !header_work ? (0x11111111u << bj)
+                                 : bj == 0 ? 0x01010101u : bj == 1 ? 0x02020202u : bj == 2 ? 0x1C1C1C1Cu : 0xE0E0E0E0u;
+          for (unsigned w = mm & share; w; w &= w - 1u) {
+            const int i = __ffs(w) - 1;
+            const uint32_t bd = __shfl_sync(0xffffffffu, body.dst, i);
+            const uint32_t n0 = __shfl_sync(0xffffffffu, body.n[0], i), n1 = __shfl_sync(0xffffffffu, body.n[1], i);
+            const uint32_t n3 = __shfl_sync(0xffffffffu, body.n[3], i);
+            const uint32_t s1 = __shfl_sync(0xffffffffu, body.src[1], i), s3 = __shfl_sync(0xffffffffu, body.src[3], i);
+            bulk8x2(s1, bd + n0, n1, s3, bd + n0 + n1 + n0, n3, lane);
+            if (n0 >= 8u) {  // the match does not start the read: the pieces in front of it
+              const uint32_t s0 = __shfl_sync(0xffffffffu, body.src[0], i), s2 = __shfl_sync(0xffffffffu, body.src[2], i);
+              bulk8x2(s0, bd, n0, s2, bd + n0 + n1, n0, lane);
+            }
+          }
+        }
+        PROF(2)
+        // (c) bulk, a warp per pass: maximal runs of consecutive unchanged records are contiguous in
+        //     the input tile and in the output
+        uint32_t t = 0;  // passes so far over all runs: pass t belongs to warp t % kBackWarps
+        for (unsigned w = um; w;) {
+          const int i0 = __ffs(w) - 1;
+          const uint32_t sb = __shfl_sync(0xffffffffu, run_s, i0), d0 = __shfl_sync(0xffffffffu, run_d, i0);
+          const uint32_t len = __shfl_sync(0xffffffffu, run_n, i0);
+          const uint32_t c0 = (d0 + 15u) & ~15u, c1 = (d0 + len) & ~15u;
+          const uint32_t npass = c1 > c0 ? (c1 - c0 + 511u) >> 9 : 0u;
+          bulk16(sb, d0, len, lane, (uint32_t)(bj - (int)t) & (kBackWarps - 1), kBackWarps);
+          t += npass;
+          const unsigned rest = ~(w >> i0);  // first zero above i0 ends the run
+          const int i1 = i0 + (rest ? __ffs(rest) - 1 : 32 - i0);  // one past the run
+          w = i1 >= 32 ? 0u : (w & (0xFFFFFFFFu << i1));
+        }
+        PROF(3)
       }
       __syncwarp();
-      PROF(1)
       if (lane == 0) mbar_arrive(&bar_empty[m][s]);  // ring slot (input tile + meta) is free again
       if (fits && total) fence_proxy_async_smem();
       // all shares written -> one warp stores; nobody overwrites the tile until the store has read it
@@ -424,7 +524,7 @@ __global__ void __launch_bounds__((PAIRED ? 2 : 1) * (2 + kBackWarps) * 32, 2) e
         __syncwarp();
       }
       back_sync(m);
-      PROF(2)
+      PROF(4)
     }
     if (bj == 0) { PROF_FLUSH(16) }
   }

@@ -79,6 +79,22 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v));
 }
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y));
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w));
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -98,15 +114,29 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // 
       : "memory");
   return done != 0;
 }
+// Blocking wait with back-off.  A bare try_wait loop issues continuously, and so does the
+// suspend-time-hint form (NANOSLEEP.SYNCS wakes on every transaction-count update of the CTA):
+// either way the pollers took a third of the SM's issue slots from the warps doing the work.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
+  const uint32_t a = smem_u32(bar);
+  while (true) {
+    uint32_t done;
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(a), "r"(parity)
         : "memory");
-  } while (!done);
+    if (done) break;
+    __nanosleep(64);
+  }
+}
+// Named barriers as one-way hand-overs between warps: the producer arrives and runs on, the
+// consumers block in hardware (no polling, no issue slots) until the count is reached.
+__device__ __forceinline__ void nbar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void nbar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // 1-D TMA: global -> shared, completion counted in bytes on the mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -171,9 +201,28 @@ __device__ __forceinline__ uint32_t strip_cr(uint32_t b, uint32_t e) {
   return (e > b && lds8(e - 1) == '\r') ? e - 1 : e;
 }
 
+// find_nl for the header line: the first eight words are fetched in one batch (independent loads, one
+// shared-memory round trip) because a lane walking its header word by word pays the full load
+// latency per word; headers longer than that fall through to the loop.
+__device__ __forceinline__ uint32_t find_nl_head(uint32_t from, uint32_t end) {
+  const uint32_t p = from & ~3u;
+  uint32_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t w = lds32(p + 4u * i) ^ 0x0A0A0A0Au;
+    m[i] = (w - 0x01010101u) & ~w & 0x80808080u;  // lowest set bit is exact; higher ones may be borrows
+  }
+  m[0] &= 0xFFFFFFFFu << ((from & 3u) * 8u);
+  uint32_t pos = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 7; i >= 0; --i) pos = m[i] ? p + 4u * i + ((__ffs(m[i]) - 1) >> 3) : pos;
+  if (pos == 0xFFFFFFFFu) return p + 32u < end ? find_nl(p + 32u, end) : end;
+  return pos < end ? pos : end;
+}
+
 __device__ __noinline__ RecView parse_record(uint32_t b, uint32_t e) {
   RecView r;
-  const uint32_t nl1 = find_nl(b, e);
+  const uint32_t nl1 = find_nl_head(b, e);
   r.beg = b;
   r.end = e;
   r.fast = 0;
@@ -241,8 +290,58 @@ __device__ __forceinline__ uint32_t fetch(uint32_t tab, uint32_t seq, uint32_t L
 // the remaining runs once per split.  `tab[c]` = bit k set iff class k contains byte c (0 for
 // c >= 0x80).  EARLY_OUT (unanchored search, lanes already diverge on s) stops at the first
 // failed run.
+// Forward strand, four bytes at a time: the run is read as unaligned words (two aligned loads and
+// a funnel shift each; the loads do not depend on data, so they pipeline), a literal run is XORed
+// with the program's word-packed literal and the non-zero bytes counted (= Hamming distance,
+// pattern.rs:40-79), a class run looks its bytes up in `tab`.  A mismatching byte sits in a
+// wildcard slot of one of the alternatives, i.e. under the regex `.`, which must be ASCII here
+// ('\n' cannot occur inside a line).
+template <bool EARLY_OUT>
+__device__ __forceinline__ bool match_at_fwd(const bk_devprog& pg, uint32_t tab, uint32_t seq, uint32_t s) {
+  bool ok = true;
+  const uint32_t* const lit32 = reinterpret_cast<const uint32_t*>(pg.lit);
+  for (uint32_t o = 0; o < pg.nops; ++o) {
+    const bk_op op = pg.ops[o];
+    const uint32_t base = seq + s + op.off;
+    const uint32_t p = base & ~3u, sh = (base & 3u) * 8u;
+    const uint32_t nw = (op.len + 3u) >> 2;
+    const uint32_t tail = op.len & 3u;  // valid bytes of the last word (0 = all four)
+    uint32_t prev = lds32(p);
+    if (op.kind == BK_OP_LIT) {
+      uint32_t mism = 0, bad = 0;
+#pragma unroll 4
+      for (uint32_t i = 0; i < nw; ++i) {
+        const uint32_t nxt = lds32(p + 4u * i + 4u);
+        const uint32_t v = __funnelshift_r(prev, nxt, sh);
+        prev = nxt;
+        uint32_t x = v ^ lit32[(op.idx >> 2) + i];
+        if (i + 1 == nw && tail) x &= (1u << (8u * tail)) - 1u;
+        const uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;  // 0x80 per differing byte
+        mism += __popc(nz);
+        bad |= nz & v;  // differing byte >= 0x80
+      }
+      ok = ok && (mism <= op.k) && !bad;
+    } else {
+      uint32_t acc = 0xFFu;
+#pragma unroll 4
+      for (uint32_t i = 0; i < nw; ++i) {
+        const uint32_t nxt = lds32(p + 4u * i + 4u);
+        uint32_t v = __funnelshift_r(prev, nxt, sh);
+        prev = nxt;
+        if (i + 1 == nw && tail) v = __byte_perm(v, 0, tail == 1 ? 0x0000 : tail == 2 ? 0x0010 : 0x0210);  // repeat byte 0
+        acc &= lds8(tab + (v & 0xFFu)) & lds8(tab + ((v >> 8) & 0xFFu)) & lds8(tab + ((v >> 16) & 0xFFu)) &
+               lds8(tab + (v >> 24));
+      }
+      ok = ok && ((acc >> op.idx) & 1u);
+    }
+    if (EARLY_OUT && !ok) return false;
+  }
+  return ok;
+}
+
 template <bool RC, bool EARLY_OUT>
 __device__ __forceinline__ bool match_at(const bk_devprog& pg, uint32_t tab, uint32_t seq, uint32_t L, uint32_t s) {
+  if (!RC) return match_at_fwd<EARLY_OUT>(pg, tab, seq, s);
   bool ok = true;
   for (uint32_t o = 0; o < pg.nops; ++o) {
     const bk_op op = pg.ops[o];
@@ -440,6 +539,126 @@ __device__ __noinline__ OutStream os_put_f(OutStream o, uint32_t v, uint32_t n) 
 }
 __device__ __forceinline__ void os_put(OutStream& o, uint32_t v, uint32_t n) { o = os_put_f(o, v, n); }
 
+// ---- bulk copies (warp-cooperative) + junctions (lane per record) -----------------------------------
+//
+// Long runs of output bytes that are verbatim input bytes (the trimmed seq / qual lines of a
+// rewritten record, whole runs of unchanged records) are copied by all lanes of a warp together:
+// consecutive lanes own consecutive aligned destination chunks, read the aligned source chunks
+// under them and funnel-shift by the run's relative misalignment, so every access of a pass covers
+// consecutive words (no bank conflicts) and the passes are independent of each other.  A bulk copy
+// writes only destination chunks that lie completely inside its run; the ragged chunks where runs
+// meet ("junctions") are written by the lane that owns the record, through the byte-exact stream
+// writer above, 32 records per instruction.  Every output byte therefore has exactly one writer
+// per word and the two kinds of writers never share a word.
+
+// Two runs at once, one per half warp, 8-byte chunks: run h (h = lane / 16) is source sX[h],
+// destination dX[h], nX[h] bytes.  Only chunks inside [ceil8(d), floor8(d + n)) are written.
+__device__ __forceinline__ void bulk8x2(uint32_t s0, uint32_t d0, uint32_t n0, uint32_t s1, uint32_t d1, uint32_t n1,
+                                        int lane) {
+  const bool hi = lane >= 16;
+  const uint32_t s = hi ? s1 : s0, d = hi ? d1 : d0, n = hi ? n1 : n0;
+  const uint32_t dend = (d + n) & ~7u;
+  const uint32_t delta = s - d;
+  const uint32_t off = delta & ~7u, sh = (delta & 3u) * 8u;
+  const bool up = (delta & 4u) != 0;
+  for (uint32_t D = ((d + 7u) & ~7u) + 8u * ((uint32_t)lane & 15u); D < dend; D += 128u) {
+    const uint2 x = lds64(D + off), y = lds64(D + off + 8u);
+    const uint32_t a = up ? x.y : x.x, b = up ? y.x : x.y, c = up ? y.y : y.x;
+    sts64(D, __funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh));
+  }
+}
+
+// One long run, 16-byte chunks, all arguments warp-uniform: the warp does passes t0, t0 + tstep, ...
+// of 32 chunks each.  Only chunks inside [ceil16(d), floor16(d + n)) are written.
+__device__ __forceinline__ void bulk16(uint32_t s, uint32_t d, uint32_t n, int lane, uint32_t t0, uint32_t tstep) {
+  const uint32_t dend = (d + n) & ~15u;
+  const uint32_t delta = s - d;
+  const uint32_t off = delta & ~15u, sh = (delta & 3u) * 8u, q = (delta >> 2) & 3u;
+  for (uint32_t D = ((d + 15u) & ~15u) + 16u * (32u * t0 + (uint32_t)lane); D < dend; D += 512u * tstep) {
+    const uint4 x = lds128(D + off), y = lds128(D + off + 16u);
+    uint32_t o0, o1, o2, o3;
+    if (q == 0) {  // warp-uniform
+      o0 = __funnelshift_r(x.x, x.y, sh); o1 = __funnelshift_r(x.y, x.z, sh);
+      o2 = __funnelshift_r(x.z, x.w, sh); o3 = __funnelshift_r(x.w, y.x, sh);
+    } else if (q == 1) {
+      o0 = __funnelshift_r(x.y, x.z, sh); o1 = __funnelshift_r(x.z, x.w, sh);
+      o2 = __funnelshift_r(x.w, y.x, sh); o3 = __funnelshift_r(y.x, y.y, sh);
+    } else if (q == 2) {
+      o0 = __funnelshift_r(x.z, x.w, sh); o1 = __funnelshift_r(x.w, y.x, sh);
+      o2 = __funnelshift_r(y.x, y.y, sh); o3 = __funnelshift_r(y.y, y.z, sh);
+    } else {
+      o0 = __funnelshift_r(x.w, y.x, sh); o1 = __funnelshift_r(y.x, y.y, sh);
+      o2 = __funnelshift_r(y.y, y.z, sh); o3 = __funnelshift_r(y.z, y.w, sh);
+    }
+    sts128(D, o0, o1, o2, o3);
+  }
+}
+
+// The part of a rewritten record's output after its header line ("body"), as up to four verbatim
+// pieces (parse.rs:138-148 with the writer's framing, fastq.rs:261):
+//   seq[..cs)   seq[ce..] "\n+\n"   qual[..cs)   qual[ce..] "\n"
+// valid for records in the writer's own framing (RecView::fast), where the separators follow the
+// lines in the input as well.  Pieces 0 and 2 are empty when the match starts the read.
+struct Body {
+  uint32_t dst;     // shared address of the body's first output byte
+  uint32_t src[4];  // shared address of each piece's first input byte
+  uint32_t n[4];    // piece lengths
+};
+
+__device__ __forceinline__ Body body_of(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d) {
+  Body b;
+  const uint32_t cs = trim ? (uint32_t)ms : 0u, ce = trim ? (uint32_t)ms + pg.total_len : 0u;
+  b.dst = d + 2u + r.head_len + pg.hdr_growth;
+  b.src[0] = r.seq;       b.n[0] = cs;
+  b.src[1] = r.seq + ce;  b.n[1] = r.seq_len - ce + 3u;
+  b.src[2] = r.qual;      b.n[2] = cs;
+  b.src[3] = r.qual + ce; b.n[3] = r.seq_len - ce + 1u;
+  return b;
+}
+
+// append body bytes [lo, hi) (body-relative) to the stream
+__device__ __forceinline__ void body_range(OutStream& o, const Body& b, uint32_t lo, uint32_t hi) {
+  uint32_t ps = 0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const uint32_t a = lo > ps ? lo : ps, e = hi < ps + b.n[p] ? hi : ps + b.n[p];
+    if (a < e) os_run(o, b.src[p] + (a - ps), e - a);
+    ps += b.n[p];
+  }
+}
+
+// Junction ranges of a body for 8-byte bulk chunks, body-relative: j[0] = [0, lo0) is the ragged
+// head (continues the header line's stream), j[1..3] the chunks that contain a piece boundary,
+// j[4] the ragged tail.  Ranges are disjoint and ascending; an empty one has lo >= hi.
+struct Junctions { uint32_t lo[5], hi[5]; };
+
+__device__ __forceinline__ Junctions body_junctions(const Body& b) {
+  Junctions j;
+  const uint32_t len = b.n[0] + b.n[1] + b.n[2] + b.n[3];
+  uint32_t pad = (8u - (b.dst & 7u)) & 7u;
+  pad = pad < len ? pad : len;
+  j.lo[0] = 0; j.hi[0] = pad;
+  uint32_t prev = pad, bd = 0;
+#pragma unroll
+  for (int k = 1; k <= 3; ++k) {
+    bd += b.n[k - 1];  // boundary between pieces k-1 and k
+    const uint32_t abs = b.dst + bd;
+    const uint32_t c0 = (abs & ~7u) - b.dst;  // chunk start, body-relative (may wrap below zero)
+    uint32_t lo = (int32_t)c0 > (int32_t)prev ? c0 : prev;
+    uint32_t hi = c0 + 8u < len ? c0 + 8u : len;
+    if ((int32_t)(c0 + 8u) < 0) hi = 0;
+    const bool valid = (abs & 7u) != 0 && bd > 0 && bd < len && lo < hi;
+    j.lo[k] = valid ? lo : 0; j.hi[k] = valid ? hi : 0;
+    prev = valid ? hi : prev;
+  }
+  const uint32_t aend = b.dst + len;
+  const uint32_t t0 = (aend & ~7u) - b.dst;
+  const uint32_t lo = (int32_t)t0 > (int32_t)prev ? t0 : prev;
+  const bool valid = (aend & 7u) != 0 && lo < len;
+  j.lo[4] = valid ? lo : 0; j.hi[4] = valid ? len : 0;
+  return j;
+}
+
 constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is written by warp j
 
 // Part `part` (0..3) of one record's output at shared address d.  The record is
@@ -453,8 +672,10 @@ constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is
 // A record that is copied unchanged and already has the writer's framing (`fast`) is one run, cut
 // into four byte ranges.  Requires qual_len == seq_len for matched records (the front warp treats
 // anything else as unmatched; bk_tokenize never produces it).
+// `cont`: the record's body is copied in bulk; part 1 then runs on past the header line's "\n" to
+// the body's first chunk boundary (body bytes [0, cont_hi)), so that the bulk copy starts aligned.
 __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
-                                          int part) {
+                                          int part, bool cont, const Body& body, uint32_t cont_hi) {
   OutStream o;
   if (ms < 0 && r.fast) {
     const uint32_t len = r.end - r.beg;
@@ -491,7 +712,10 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
       os_put(o, (uint32_t)':', 1u);
       if (cap.len) os_run(o, r.qual + ms + cap.off, cap.len);
     }
-    if (part == 1) os_put(o, (uint32_t)'\n', 1u);
+    if (part == 1) {
+      os_put(o, (uint32_t)'\n', 1u);
+      if (cont) body_range(o, body, 0, cont_hi);
+    }
     os_end(o);
     return;
   }

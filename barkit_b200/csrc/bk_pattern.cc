@@ -444,6 +444,7 @@ int compile(const std::string& pattern, size_t max_error, Program* prog, std::st
     op.k = 0;
     op.idx = 0;
     if (a.kind == 1) {
+      nlit = (nlit + 3) & ~size_t(3);  // every literal starts on a word: the kernel compares 4 bytes at a time
       if (nlit + (q - p) > BK_MAX_LIT) { *err = "unsupported pattern: literal bytes exceed 512"; return BK_E_UNSUPPORTED; }
       op.idx = (uint16_t)nlit;
       for (size_t t = p; t < q; ++t) d.lit[nlit++] = lw.pos[t].byte;

@@ -24,7 +24,7 @@ struct bk_op {
   uint16_t len;
   uint8_t kind;
   uint8_t k;     // allowed mismatches (already min(k, len)); 0 for exact literals
-  uint16_t idx;  // class index or offset into lit[]
+  uint16_t idx;  // class index or offset into lit[] (a multiple of 4)
 };
 
 struct bk_cap {
@@ -45,6 +45,6 @@ struct bk_devprog {
   uint32_t pad;
   bk_op ops[BK_MAX_OPS];
   uint32_t cls[BK_MAX_CLASSES][4];  // 128-bit ASCII membership bitmaps (bytes >= 0x80 never match)
-  uint8_t lit[BK_MAX_LIT];
+  alignas(4) uint8_t lit[BK_MAX_LIT];  // literals, each starting on a 4-byte boundary, zero padded
   bk_cap caps[BK_MAX_CAPS];
 };

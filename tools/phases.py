@@ -18,7 +18,8 @@ out=np.zeros(24,np.uint64)
 _lib.lib.bk_debug_phases(ctx.handle,out.ctypes.data)
 ntiles=(P+31)//32
 print("kernel_ms",r.kernel_ms,"Mpairs/s",P/r.kernel_ms/1e3,"tiles",ntiles)
-names={0:"F wait_empty",1:"F claim+bar",2:"F offsets",3:"F tma wait",4:"F parse+match",5:"F exchange",6:"F size/scan/pub/meta",
- 8:"S wait_pub",9:"S lookback",16:"B wait_ready",17:"B emit",18:"B release+store"}
+names={0:"L wait_empty",1:"L claim",2:"L offsets+issue",
+ 4:"S wait_pub",5:"S lookback",
+ 8:"F wait_full",9:"F parse",10:"F match",11:"F exchange",12:"F size/scan/pub/meta",
+ 16:"B wait_ready",17:"B headers (lane/rec)",18:"B matched runs",19:"B unchanged runs",20:"B release+store"}
 for i,n in names.items(): print("%-24s %8.0f cyc/tile"%(n,out[i]/ntiles))
-print("lookback per tile-stream (cumulative over the 3 timed launches): rounds %.2f windows %.2f spin-iters %.2f" % (out[10]/(6.0*ntiles), out[11]/(6.0*ntiles), out[12]/(6.0*ntiles)))
