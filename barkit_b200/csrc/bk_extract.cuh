@@ -15,7 +15,7 @@ constexpr int kBackWarps = kEmitParts;  // back warps per mate: warp j writes pa
 // including this one).  The two front warps publish their halves independently; one scan warp
 // resolves both streams with a single pass over the predecessors.
 
-constexpr int kLookWindows = 8;  // 32-descriptor windows fetched per round (independent loads in flight)
+constexpr int kLookPerLane = 4;  // consecutive descriptors per lane and round: 128 tiles per round
 
 __device__ __forceinline__ ulonglong2 ld_desc(const unsigned long long* p) {
   ulonglong2 v;
@@ -28,43 +28,48 @@ __device__ __forceinline__ bool desc_ready(const ulonglong2& d, bool two) {
   return f0 != 0 && (!two || f1 == f0);
 }
 
-#ifdef BK_PROFILE_PHASES
-__device__ unsigned long long g_look_rounds, g_look_spins, g_look_windows;
-#endif
 // Exclusive prefixes of tile `tile` on both streams.  The tile's own aggregates have already been
 // published (by the front warps); this publishes the inclusive prefixes once they are known.
+// Per round every lane fetches kLookPerLane consecutive predecessors (independent loads, one L2
+// round trip for 128 tiles), folds them locally -- aggregates up to and including its nearest
+// prefix -- and one warp-level step combines the lanes.  Deliberately compact: the kernel's hot
+// code has to fit the SM's 32 KB instruction cache, and an unrolled window-per-
+// iteration form of this function alone was 10 KB.
 __device__ __noinline__ ulonglong2 lookback(unsigned long long* desc, uint32_t tile, uint32_t agg0, uint32_t agg1,
                                             bool two, int lane) {
   unsigned long long e0 = 0, e1 = 0;
-  if (tile != 0) {
-    int look = (int)tile - 1;
-    bool done = false;
-    while (!done) {
-      ulonglong2 d[kLookWindows];
+  for (int look = (int)tile - 1; look >= 0; look -= 32 * kLookPerLane) {
+    const int base = look - kLookPerLane * lane;  // this lane's nearest predecessor
+    ulonglong2 d[kLookPerLane];
+    bool ready;
+    do {
+      ready = true;
 #pragma unroll
-      for (int j = 0; j < kLookWindows; ++j) {
-        const int idx = look - 32 * j - lane;
-        d[j] = idx >= 0 ? ld_desc(desc + 2 * (size_t)idx) : make_ulonglong2(kFlagPrefix, kFlagPrefix);  // before tile 0: prefix 0
+      for (int j = 0; j < kLookPerLane; ++j) {
+        // tiles before 0 read as "prefix 0"
+        d[j] = base - j >= 0 ? ld_desc(desc + 2 * (size_t)(base - j)) : make_ulonglong2(kFlagPrefix, kFlagPrefix);
+        ready = ready && desc_ready(d[j], two);
       }
+    } while (__any_sync(0xffffffffu, !ready));
+    // aggregates are one tile's bytes (32 bits is plenty); only the prefixes themselves are 64-bit
+    uint32_t a0 = 0, a1 = 0;
+    unsigned long long p0 = 0, p1 = 0;
+    bool found = false;
 #pragma unroll
-      for (int j = 0; j < kLookWindows; ++j) {
-        if (done) break;
-        const int idx = look - 32 * j - lane;
-        while (__any_sync(0xffffffffu, !desc_ready(d[j], two))) {
-          if (!desc_ready(d[j], two)) d[j] = ld_desc(desc + 2 * (size_t)idx);
-        }
-        const unsigned pm = __ballot_sync(0xffffffffu, (d[j].x >> 62) == 2);
-        const int first = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor holding inclusive prefixes
-        // aggregates are one tile's bytes (32 bits is plenty); only the prefixes themselves are 64-bit
-        e0 += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)d[j].x : 0u);
-        if (two) e1 += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)d[j].y : 0u);
-        if (pm) {
-          e0 += __shfl_sync(0xffffffffu, d[j].x & kValueMask, first);
-          if (two) e1 += __shfl_sync(0xffffffffu, d[j].y & kValueMask, first);
-          done = true;
-        }
-      }
-      look -= 32 * kLookWindows;
+    for (int j = 0; j < kLookPerLane; ++j) {
+      const bool pre = (d[j].x >> 62) == 2;
+      if (!found && !pre) { a0 += (uint32_t)d[j].x; a1 += (uint32_t)d[j].y; }
+      if (!found && pre) { p0 = d[j].x & kValueMask; p1 = d[j].y & kValueMask; }
+      found = found || pre;
+    }
+    const unsigned pm = __ballot_sync(0xffffffffu, found);
+    const int first = pm ? __ffs(pm) - 1 : 31;  // nearest lane holding inclusive prefixes
+    e0 += __reduce_add_sync(0xffffffffu, lane <= first ? a0 : 0u);
+    if (two) e1 += __reduce_add_sync(0xffffffffu, lane <= first ? a1 : 0u);
+    if (pm) {
+      e0 += __shfl_sync(0xffffffffu, p0, first);
+      if (two) e1 += __shfl_sync(0xffffffffu, p1, first);
+      break;
     }
   }
   if (lane == 0) {
@@ -152,6 +157,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
   __shared__ uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, then the complement table
   __shared__ int s_ms[2][2][32];  // [tile parity][mate][lane]
   __shared__ TileMeta meta[NM][kStages];
+  __shared__ uint4 body_desc[NM][32][4];  // bulk-copy descriptors of a record's four body pieces (1, 3, 0, 2)
+  __shared__ uint4 run_desc[NM][32];      // bulk-copy descriptors of the tile's runs of unchanged records
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -372,6 +379,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
     // =============================== BACK =======================================================
     uint8_t* const gdst = P.out[m];
     const bool header_work = pg.present != 0;
+    // a match that need not start the read leaves a piece of seq / qual in front of the cut
+    const bool has_prefix = trim && !pg.anchor_start;
     PROF_INIT
     for (uint32_t k = 0;; ++k) {
       const uint32_t s = k % kStages;
@@ -416,85 +425,96 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         jn.hi[0] = 0;
         if (mat) {
           body = body_of(pg, rv, ms, trim, dst);
-          jn = body_junctions(body);
+          jn = has_prefix ? body_junctions<true>(body) : body_junctions<false>(body);
         }
-        if ((kept && !rv.fast) || (mat && bj < 2)) emit_part(pg, rv, ms, trim, dst, bj, mat, body, jn.hi[0]);
+        if ((kept && !rv.fast) || (mat && bj < 2))
+          emit_part(pg, rv, ms, trim, dst, bj, mat, body, jn.hi[0], has_prefix);
         if (mat && bj >= 2) {
 #pragma unroll
           for (int k = 1; k <= 4; ++k) {
             if ((k == 4) != (bj == 3)) continue;  // warp 2: piece boundaries, warp 3: ragged tail
+            if (!has_prefix && (k == 1 || k == 3)) continue;
             if (jn.lo[k] < jn.hi[k]) {
               OutStream o;
               os_begin(o, body.dst + jn.lo[k]);
-              body_range(o, body, jn.lo[k], jn.hi[k]);
+              if (has_prefix) body_range<true>(o, body, jn.lo[k], jn.hi[k]);
+              else body_range<false>(o, body, jn.lo[k], jn.hi[k]);
               os_end(o);
             }
           }
         }
-        // runs of unchanged records: lane i learns its run [i0, i1]
-        uint32_t run_s = 0, run_d = 0, run_n = 0;
+        // runs of unchanged records: lane i learns its run [i0, i1]; the first lane of a run files
+        // its bulk-copy descriptor (all four back warps write the same list)
+        uint32_t nruns = 0;
         if (um) {
           const unsigned below = ~um & ((1u << lane) - 1u);
           const int i0 = unc ? (below ? 32 - __clz(below) : 0) : lane;
           const unsigned above = ~(um >> lane);  // first zero at or above this lane ends the run
           const int i1 = unc ? (above ? lane + __ffs(above) - 2 : 31) : lane;
-          run_s = __shfl_sync(0xffffffffu, rv.beg, i0);
-          run_d = __shfl_sync(0xffffffffu, dst, i0);
-          run_n = __shfl_sync(0xffffffffu, rv.end, i1) - run_s;
+          const uint32_t run_s = __shfl_sync(0xffffffffu, rv.beg, i0);
+          const uint32_t run_d = __shfl_sync(0xffffffffu, dst, i0);
+          const uint32_t run_n = __shfl_sync(0xffffffffu, rv.end, i1) - run_s;
+          const bool first = unc && i0 == lane;
+          const unsigned starts = __ballot_sync(0xffffffffu, first);
+          nruns = __popc(starts);
+          uint4 rd = bulk_desc(run_s, run_d, run_n, 16u, 0u);
+          const uint32_t npass = (first && rd.y > rd.x) ? (rd.y - rd.x + 511u) >> 9 : 0u;
+          uint32_t incl = npass;  // passes before this run, over all runs: pass t belongs to warp t % kBackWarps
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+          }
+          rd.w = incl - npass;
+          if (first) run_desc[m][__popc(starts & ((1u << lane) - 1u))] = rd;
           if (unc && bj >= 2) {
             uint32_t pad = (16u - (run_d & 15u)) & 15u;
             pad = pad < run_n ? pad : run_n;
             const uint32_t t0 = ((run_d + run_n) & ~15u) - run_d;
             const uint32_t tlo = (int32_t)t0 > (int32_t)pad ? t0 : pad;
-            if (bj == 2 && i0 == lane && pad) {  // ragged head of the run
+            if (bj == 2 && first && pad) {  // ragged head of the run
               OutStream o;
               os_begin(o, run_d);
-              os_run(o, run_s, pad);
+              os_short(o, run_s, pad);
               os_end(o);
             }
             if (bj == 3 && i1 == lane && tlo < run_n) {  // ragged tail
               OutStream o;
               os_begin(o, run_d + tlo);
-              os_run(o, run_s + tlo, run_n - tlo);
+              os_short(o, run_s + tlo, run_n - tlo);
               os_end(o);
             }
           }
         }
+        // bulk-copy descriptors of the rewritten records this warp will copy.  Warps 0 and 1 carry
+        // the header lines, so they take fewer records.
+        const unsigned share = mm & (!header_work ? (0x11111111u << bj)
+                                     : bj == 0 ? 0x01010101u : bj == 1 ? 0x02020202u : bj == 2 ? 0x1C1C1C1Cu : 0xE0E0E0E0u);
+        const bool mine = (share >> lane) & 1u;
+        const unsigned pre = has_prefix ? __ballot_sync(0xffffffffu, mine && body.n[0] >= 8u) : 0u;
+        if (mine) {
+          const uint32_t d1 = body.dst + body.n[0], d2 = d1 + body.n[1], d3 = d2 + body.n[2];
+          body_desc[m][lane][0] = bulk_desc(body.src[1], d1, body.n[1], 8u, 0u);
+          body_desc[m][lane][1] = bulk_desc(body.src[3], d3, body.n[3], 8u, 0u);
+          if (pre) {
+            body_desc[m][lane][2] = bulk_desc(body.src[0], body.dst, body.n[0], 8u, 0u);
+            body_desc[m][lane][3] = bulk_desc(body.src[2], d2, body.n[2], 8u, 0u);
+          }
+        }
         __syncwarp();
         PROF(1)
-        // (b) bulk, half a warp per piece: the trimmed seq and qual lines of rewritten records.
-        //     Warps 0 and 1 carry the header lines, so they take fewer records.
-        {
-          const unsigned share = !header_work ? (0x11111111u << bj)
-                                 : bj == 0 ? 0x01010101u : bj == 1 ? 0x02020202u : bj == 2 ? 0x1C1C1C1Cu : 0xE0E0E0E0u;
-          for (unsigned w = mm & share; w; w &= w - 1u) {
-            const int i = __ffs(w) - 1;
-            const uint32_t bd = __shfl_sync(0xffffffffu, body.dst, i);
-            const uint32_t n0 = __shfl_sync(0xffffffffu, body.n[0], i), n1 = __shfl_sync(0xffffffffu, body.n[1], i);
-            const uint32_t n3 = __shfl_sync(0xffffffffu, body.n[3], i);
-            const uint32_t s1 = __shfl_sync(0xffffffffu, body.src[1], i), s3 = __shfl_sync(0xffffffffu, body.src[3], i);
-            bulk8x2(s1, bd + n0, n1, s3, bd + n0 + n1 + n0, n3, lane);
-            if (n0 >= 8u) {  // the match does not start the read: the pieces in front of it
-              const uint32_t s0 = __shfl_sync(0xffffffffu, body.src[0], i), s2 = __shfl_sync(0xffffffffu, body.src[2], i);
-              bulk8x2(s0, bd, n0, s2, bd + n0 + n1, n0, lane);
-            }
-          }
+        // (b) bulk, half a warp per piece: the trimmed seq and qual lines of rewritten records
+        for (unsigned w = share; w; w &= w - 1u) {
+          const int i = __ffs(w) - 1;
+          bulk8(body_desc[m][i][lane >> 4], lane);
+          if ((pre >> i) & 1u) bulk8(body_desc[m][i][2 + (lane >> 4)], lane);  // the pieces in front of the match
         }
         PROF(2)
         // (c) bulk, a warp per pass: maximal runs of consecutive unchanged records are contiguous in
         //     the input tile and in the output
-        uint32_t t = 0;  // passes so far over all runs: pass t belongs to warp t % kBackWarps
-        for (unsigned w = um; w;) {
-          const int i0 = __ffs(w) - 1;
-          const uint32_t sb = __shfl_sync(0xffffffffu, run_s, i0), d0 = __shfl_sync(0xffffffffu, run_d, i0);
-          const uint32_t len = __shfl_sync(0xffffffffu, run_n, i0);
-          const uint32_t c0 = (d0 + 15u) & ~15u, c1 = (d0 + len) & ~15u;
-          const uint32_t npass = c1 > c0 ? (c1 - c0 + 511u) >> 9 : 0u;
-          bulk16(sb, d0, len, lane, (uint32_t)(bj - (int)t) & (kBackWarps - 1), kBackWarps);
-          t += npass;
-          const unsigned rest = ~(w >> i0);  // first zero above i0 ends the run
-          const int i1 = i0 + (rest ? __ffs(rest) - 1 : 32 - i0);  // one past the run
-          w = i1 >= 32 ? 0u : (w & (0xFFFFFFFFu << i1));
+        for (uint32_t r = 0; r < nruns; ++r) {
+          const uint4 rd = run_desc[m][r];
+          bulk16(rd, lane, (uint32_t)(bj - (int)rd.w) & (kBackWarps - 1), kBackWarps);
         }
         PROF(3)
       }

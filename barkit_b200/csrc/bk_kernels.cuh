@@ -127,7 +127,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(64);
+    __nanosleep(128);
   }
 }
 // Named barriers as one-way hand-overs between warps: the producer arrives and runs on, the
@@ -309,7 +309,7 @@ __device__ __forceinline__ bool match_at_fwd(const bk_devprog& pg, uint32_t tab,
     uint32_t prev = lds32(p);
     if (op.kind == BK_OP_LIT) {
       uint32_t mism = 0, bad = 0;
-#pragma unroll 4
+#pragma unroll 1
       for (uint32_t i = 0; i < nw; ++i) {
         const uint32_t nxt = lds32(p + 4u * i + 4u);
         const uint32_t v = __funnelshift_r(prev, nxt, sh);
@@ -323,7 +323,7 @@ __device__ __forceinline__ bool match_at_fwd(const bk_devprog& pg, uint32_t tab,
       ok = ok && (mism <= op.k) && !bad;
     } else {
       uint32_t acc = 0xFFu;
-#pragma unroll 4
+#pragma unroll 1
       for (uint32_t i = 0; i < nw; ++i) {
         const uint32_t nxt = lds32(p + 4u * i + 4u);
         uint32_t v = __funnelshift_r(prev, nxt, sh);
@@ -405,133 +405,106 @@ __device__ __forceinline__ uint32_t out_bytes(const bk_devprog& pg, const RecVie
 
 // Per-lane output stream into the shared output tile.  Bytes are produced strictly in order; the
 // lane keeps the (up to 3) bytes that do not yet fill a word in a register and stores whole aligned
-// words.  Words shared with another writer are written bytewise: the first `ragged` bytes (up to
-// the first word boundary) and whatever is pending at os_end.  Inside a run the pending-byte count
-// is constant, so the inner loop is one load, one funnel shift and one store per word, with all
-// loads independent of the stores.
+// words.  A stream may start and end anywhere inside a word; those two words are shared with other
+// writers, so only the stream's own bytes of them are stored (bytewise).  Everything is predicated
+// rather than branched: the lanes of a warp (one record each) are at different alignments.
 struct OutStream {
-  uint32_t wpos;    // shared address of the next byte (while ragged) / word to write
-  uint32_t lo;      // pending bytes: low `nb` bytes valid, the rest zero
-  uint32_t nb;      // 0..3
-  uint32_t ragged;  // bytes still to write bytewise before wpos is word aligned
+  uint32_t wpos;  // shared address of the word being filled (4-byte aligned)
+  uint32_t lo;    // its bytes so far: low `nb` bytes meaningful (the first `skip` are placeholders), rest zero
+  uint32_t nb;    // 0..3
+  uint32_t skip;  // leading bytes of the word at wpos that belong to another writer (first word only)
 };
 
 __device__ __forceinline__ void os_begin(OutStream& o, uint32_t d) {
-  o.wpos = d;
-  o.ragged = (4u - (d & 3u)) & 3u;
+  o.wpos = d & ~3u;
+  o.nb = o.skip = d & 3u;
   o.lo = 0;
-  o.nb = 0;
 }
 
-// Append n (1..32) bytes starting at shared address s (any alignment) to a word-aligned stream.
+// store the completed word v at o.wpos if `en`; the stream's first word is stored without its skipped bytes
+__device__ __forceinline__ void os_store_first(OutStream& o, uint32_t v, bool en) {
+  const uint32_t sk = o.skip;
+  if (en && sk == 0) sts32(o.wpos, v);
+  if (en && sk == 1) sts8(o.wpos + 1, v >> 8);
+  if (en && (sk == 1 || sk == 2)) sts8(o.wpos + 2, v >> 16);
+  if (en && sk != 0) sts8(o.wpos + 3, v >> 24);
+  o.skip = en ? 0u : sk;
+}
+
+// Append n (1..4*NW-4) bytes starting at shared address s (any alignment) to the stream, NW = 9 or 5.
 // One batch of independent loads, then register work, then stores: a single shared-memory round
-// trip per chunk, which is what bounds a lane copying many short runs.  The 9 aligned words read
-// cover [s, s+32) at any alignment (bytes past the run are read but never used); source
+// trip per chunk, which is what bounds a lane copying many short runs.  The NW aligned words read
+// cover [s, s+4*NW-4) at any alignment (bytes past the run are read but never used); source
 // misalignment a and the stream's pending bytes nb fold into one funnel shift.
+template <int NW>
 __device__ __forceinline__ void os_chunk(OutStream& o, uint32_t s, uint32_t n) {
   const uint32_t sp = s & ~3u, a = s & 3u;
-  uint32_t w0 = lds32(sp), w1 = lds32(sp + 4), w2 = lds32(sp + 8), w3 = lds32(sp + 12), w4 = lds32(sp + 16);
-  uint32_t w5 = lds32(sp + 20), w6 = lds32(sp + 24), w7 = lds32(sp + 28), w8 = lds32(sp + 32), w9 = 0;
+  uint32_t w[NW + 1];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) w[i] = lds32(sp + 4u * i);
+  w[NW] = 0;
   // output word q holds stream bytes [4q, 4q+4); stream byte j >= nb is source byte (a - nb + j) of w[]
   int delta = (int)a - (int)o.nb;
   if (delta < 0) {  // shift the window by one word so that the funnel amount is non-negative
-    w9 = w8; w8 = w7; w7 = w6; w6 = w5; w5 = w4; w4 = w3; w3 = w2; w2 = w1; w1 = w0; w0 = 0;
+#pragma unroll
+    for (int i = NW; i > 0; --i) w[i] = w[i - 1];
+    w[0] = 0;
     delta += 4;
   }
   const uint32_t sh = 8u * (uint32_t)delta;
-  uint32_t v0 = __funnelshift_r(w0, w1, sh);
-  const uint32_t v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
-  const uint32_t v3 = __funnelshift_r(w3, w4, sh), v4 = __funnelshift_r(w4, w5, sh);
-  const uint32_t v5 = __funnelshift_r(w5, w6, sh), v6 = __funnelshift_r(w6, w7, sh);
-  const uint32_t v7 = __funnelshift_r(w7, w8, sh), v8 = __funnelshift_r(w8, w9, sh);
+  uint32_t v[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
   const uint32_t keep = (1u << (8u * o.nb)) - 1u;  // nb <= 3
-  v0 = (v0 & ~keep) | o.lo;
-  const uint32_t tot = o.nb + n, nfull = tot >> 2, rem = tot & 3u;  // nfull <= 8
+  v[0] = (v[0] & ~keep) | o.lo;
+  const uint32_t tot = o.nb + n, nfull = tot >> 2, rem = tot & 3u;  // nfull <= NW - 1
   const uint32_t d = o.wpos;
-  if (nfull > 0) sts32(d, v0);
-  if (nfull > 1) sts32(d + 4, v1);
-  if (nfull > 2) sts32(d + 8, v2);
-  if (nfull > 3) sts32(d + 12, v3);
-  if (nfull > 4) sts32(d + 16, v4);
-  if (nfull > 5) sts32(d + 20, v5);
-  if (nfull > 6) sts32(d + 24, v6);
-  if (nfull > 7) sts32(d + 28, v7);
-  uint32_t last = v8;
-  last = nfull == 7 ? v7 : last;
-  last = nfull == 6 ? v6 : last;
-  last = nfull == 5 ? v5 : last;
-  last = nfull == 4 ? v4 : last;
-  last = nfull == 3 ? v3 : last;
-  last = nfull == 2 ? v2 : last;
-  last = nfull == 1 ? v1 : last;
-  last = nfull == 0 ? v0 : last;
+  os_store_first(o, v[0], nfull > 0);
+#pragma unroll
+  for (int i = 1; i < NW - 1; ++i)
+    if (nfull > (uint32_t)i) sts32(d + 4u * i, v[i]);
+  uint32_t last = v[NW - 1];
+#pragma unroll
+  for (int i = NW - 2; i >= 0; --i) last = nfull == (uint32_t)i ? v[i] : last;
   o.wpos = d + 4u * nfull;
   o.lo = last & ((1u << (8u * rem)) - 1u);
   o.nb = rem;
 }
 
-// append [s, s+len) of shared memory (any alignment), len > 0.  Deliberately a real call (the
-// stream state travels in registers): inlined at every use it made the kernel ~160 KB of code,
-// several times the instruction cache the three warp roles share, and instruction-fetch stalls
-// dominated the profile.
-__device__ __noinline__ OutStream os_run_f(OutStream o, uint32_t s, uint32_t len) {
-  while (o.ragged && len) {  // at most 3 bytes per stream
-    sts8(o.wpos, lds8(s));
-    ++o.wpos; ++s; --len; --o.ragged;
-  }
-  if (len == 0) return o;
-  {  // first chunk: up to the source's next 32-byte-window boundary, which word-aligns the source
-    uint32_t n = 32u - (s & 3u);
-    n = n < len ? n : len;
-    os_chunk(o, s, n);
+// append [s, s+len) of shared memory (any alignment), 1 <= len <= 16 (a barcode, a junction between
+// bulk copies).  Deliberately a real call (the stream state travels in registers), and deliberately
+// the only copy primitive: the kernel's hot code has to fit the SM's 32 KB instruction cache, and
+// an unrolled 32-byte variant plus a long-run loop cost 4 KB of it.
+__device__ __noinline__ OutStream os_short_f(OutStream o, uint32_t s, uint32_t len) {
+  os_chunk<5>(o, s, len);
+  return o;
+}
+__device__ __forceinline__ void os_short(OutStream& o, uint32_t s, uint32_t len) { o = os_short_f(o, s, len); }
+// any length > 0, 16 bytes at a time
+__device__ __forceinline__ void os_run(OutStream& o, uint32_t s, uint32_t len) {
+#pragma unroll 1
+  while (len) {
+    const uint32_t n = len < 16u ? len : 16u;
+    os_short(o, s, n);
     s += n;
     len -= n;
   }
-  if (len >= 32u) {  // long run: source is word aligned and the pending-byte count stays constant
-    const uint32_t sh = o.nb * 8u;
-    uint32_t prev = sh ? (o.lo << (32u - sh)) : 0u;  // so that funnelshift_l(prev, w, sh) = lo | w << sh
-    uint32_t dp = o.wpos;
-    do {
-      const uint32_t w0 = lds32(s), w1 = lds32(s + 4), w2 = lds32(s + 8), w3 = lds32(s + 12);
-      const uint32_t w4 = lds32(s + 16), w5 = lds32(s + 20), w6 = lds32(s + 24), w7 = lds32(s + 28);
-      sts32(dp, __funnelshift_l(prev, w0, sh));
-      sts32(dp + 4, __funnelshift_l(w0, w1, sh));
-      sts32(dp + 8, __funnelshift_l(w1, w2, sh));
-      sts32(dp + 12, __funnelshift_l(w2, w3, sh));
-      sts32(dp + 16, __funnelshift_l(w3, w4, sh));
-      sts32(dp + 20, __funnelshift_l(w4, w5, sh));
-      sts32(dp + 24, __funnelshift_l(w5, w6, sh));
-      sts32(dp + 28, __funnelshift_l(w6, w7, sh));
-      prev = w7;
-      s += 32;
-      dp += 32;
-      len -= 32;
-    } while (len >= 32u);
-    o.lo = __funnelshift_l(prev, 0u, sh);
-    o.wpos = dp;
-  }
-  if (len) os_chunk(o, s, len);
-  return o;
 }
-__device__ __forceinline__ void os_run(OutStream& o, uint32_t s, uint32_t len) { o = os_run_f(o, s, len); }
+__device__ __forceinline__ void os_copy(OutStream& o, uint32_t s, uint32_t len) { os_run(o, s, len); }
 
 __device__ __forceinline__ void os_end(const OutStream& o) {
-  if (o.nb > 0) sts8(o.wpos, o.lo);
-  if (o.nb > 1) sts8(o.wpos + 1, o.lo >> 8);
-  if (o.nb > 2) sts8(o.wpos + 2, o.lo >> 16);
+#pragma unroll
+  for (uint32_t b = 0; b < 3; ++b)
+    if (b >= o.skip && b < o.nb) sts8(o.wpos + b, o.lo >> (8u * b));
 }
 
 // append the n (0..4) low bytes of register value v (bytes of v above n must be zero)
 __device__ __noinline__ OutStream os_put_f(OutStream o, uint32_t v, uint32_t n) {
-  while (o.ragged && n) {  // stream not word aligned yet: bytewise
-    sts8(o.wpos, v);
-    ++o.wpos; v >>= 8; --n; --o.ragged;
-  }
   const uint32_t sh = o.nb * 8u;
   const uint32_t word = o.lo | (v << sh);
   const uint32_t tot = o.nb + n;
   const bool full = tot >= 4u;
-  if (full) sts32(o.wpos, word);                    // predicated store, not a branch
+  os_store_first(o, word, full);
   o.wpos += full ? 4u : 0u;
   o.lo = full ? __funnelshift_l(v, 0u, sh) : word;  // v >> (32 - sh); 0 when sh == 0
   o.nb = tot & 3u;
@@ -551,30 +524,34 @@ __device__ __forceinline__ void os_put(OutStream& o, uint32_t v, uint32_t n) { o
 // writer above, 32 records per instruction.  Every output byte therefore has exactly one writer
 // per word and the two kinds of writers never share a word.
 
-// Two runs at once, one per half warp, 8-byte chunks: run h (h = lane / 16) is source sX[h],
-// destination dX[h], nX[h] bytes.  Only chunks inside [ceil8(d), floor8(d + n)) are written.
-__device__ __forceinline__ void bulk8x2(uint32_t s0, uint32_t d0, uint32_t n0, uint32_t s1, uint32_t d1, uint32_t n1,
-                                        int lane) {
-  const bool hi = lane >= 16;
-  const uint32_t s = hi ? s1 : s0, d = hi ? d1 : d0, n = hi ? n1 : n0;
-  const uint32_t dend = (d + n) & ~7u;
-  const uint32_t delta = s - d;
+// Bulk-copy descriptor, built once per run by the lane that owns the record (32 records per
+// instruction) and read back warp-uniformly, so that the per-run cost in the copy loops is one
+// 16-byte load instead of a dozen shuffles and address computations.
+//   x: first destination chunk (aligned up)   y: end of the last full chunk (aligned down)
+//   z: source - destination                   w: free (pass prefix for the 16-byte form)
+__device__ __forceinline__ uint4 bulk_desc(uint32_t s, uint32_t d, uint32_t n, uint32_t chunk, uint32_t w) {
+  return make_uint4((d + chunk - 1u) & ~(chunk - 1u), (d + n) & ~(chunk - 1u), s - d, w);
+}
+
+// Two runs at once, one per half warp, 8-byte chunks: lanes 0-15 copy the run of q0, lanes 16-31
+// that of q1 (each lane passes the descriptor of its half).
+__device__ __forceinline__ void bulk8(const uint4 q, int lane) {
+  const uint32_t delta = q.z;
   const uint32_t off = delta & ~7u, sh = (delta & 3u) * 8u;
   const bool up = (delta & 4u) != 0;
-  for (uint32_t D = ((d + 7u) & ~7u) + 8u * ((uint32_t)lane & 15u); D < dend; D += 128u) {
+  for (uint32_t D = q.x + 8u * ((uint32_t)lane & 15u); D < q.y; D += 128u) {
     const uint2 x = lds64(D + off), y = lds64(D + off + 8u);
     const uint32_t a = up ? x.y : x.x, b = up ? y.x : x.y, c = up ? y.y : y.x;
     sts64(D, __funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh));
   }
 }
 
-// One long run, 16-byte chunks, all arguments warp-uniform: the warp does passes t0, t0 + tstep, ...
-// of 32 chunks each.  Only chunks inside [ceil16(d), floor16(d + n)) are written.
-__device__ __forceinline__ void bulk16(uint32_t s, uint32_t d, uint32_t n, int lane, uint32_t t0, uint32_t tstep) {
-  const uint32_t dend = (d + n) & ~15u;
-  const uint32_t delta = s - d;
+// One long run, 16-byte chunks, descriptor warp-uniform: the warp does passes t0, t0 + tstep, ...
+// of 32 chunks each.
+__device__ __forceinline__ void bulk16(const uint4 r, int lane, uint32_t t0, uint32_t tstep) {
+  const uint32_t delta = r.z;
   const uint32_t off = delta & ~15u, sh = (delta & 3u) * 8u, q = (delta >> 2) & 3u;
-  for (uint32_t D = ((d + 15u) & ~15u) + 16u * (32u * t0 + (uint32_t)lane); D < dend; D += 512u * tstep) {
+  for (uint32_t D = r.x + 16u * (32u * t0 + (uint32_t)lane); D < r.y; D += 512u * tstep) {
     const uint4 x = lds128(D + off), y = lds128(D + off + 16u);
     uint32_t o0, o1, o2, o3;
     if (q == 0) {  // warp-uniform
@@ -616,22 +593,26 @@ __device__ __forceinline__ Body body_of(const bk_devprog& pg, const RecView& r, 
   return b;
 }
 
-// append body bytes [lo, hi) (body-relative) to the stream
+// append body bytes [lo, hi) (body-relative) to the stream.  PREFIX = false: pieces 0 and 2 are known
+// to be empty (the pattern is anchored at the read's start, or nothing is trimmed) -- a program-wide
+// fact, so that the common case runs, and keeps in the instruction cache, half the code.
+template <bool PREFIX>
 __device__ __forceinline__ void body_range(OutStream& o, const Body& b, uint32_t lo, uint32_t hi) {
   uint32_t ps = 0;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
+  for (int p = PREFIX ? 0 : 1; p < 4; p += PREFIX ? 1 : 2) {
     const uint32_t a = lo > ps ? lo : ps, e = hi < ps + b.n[p] ? hi : ps + b.n[p];
-    if (a < e) os_run(o, b.src[p] + (a - ps), e - a);
+    if (a < e) os_short(o, b.src[p] + (a - ps), e - a);  // junctions are at most 15 bytes
     ps += b.n[p];
   }
 }
 
-// Junction ranges of a body for 8-byte bulk chunks, body-relative: j[0] = [0, lo0) is the ragged
+// Junction ranges of a body for 8-byte bulk chunks, body-relative: j[0] = [0, hi0) is the ragged
 // head (continues the header line's stream), j[1..3] the chunks that contain a piece boundary,
 // j[4] the ragged tail.  Ranges are disjoint and ascending; an empty one has lo >= hi.
 struct Junctions { uint32_t lo[5], hi[5]; };
 
+template <bool PREFIX>
 __device__ __forceinline__ Junctions body_junctions(const Body& b) {
   Junctions j;
   const uint32_t len = b.n[0] + b.n[1] + b.n[2] + b.n[3];
@@ -642,11 +623,14 @@ __device__ __forceinline__ Junctions body_junctions(const Body& b) {
 #pragma unroll
   for (int k = 1; k <= 3; ++k) {
     bd += b.n[k - 1];  // boundary between pieces k-1 and k
+    if (!PREFIX && k != 2) {  // coincides with the body's start (k = 1) or with boundary 2 (k = 3)
+      j.lo[k] = j.hi[k] = 0;
+      continue;
+    }
     const uint32_t abs = b.dst + bd;
     const uint32_t c0 = (abs & ~7u) - b.dst;  // chunk start, body-relative (may wrap below zero)
-    uint32_t lo = (int32_t)c0 > (int32_t)prev ? c0 : prev;
-    uint32_t hi = c0 + 8u < len ? c0 + 8u : len;
-    if ((int32_t)(c0 + 8u) < 0) hi = 0;
+    const uint32_t lo = (int32_t)c0 > (int32_t)prev ? c0 : prev;
+    const uint32_t hi = c0 + 8u < len ? c0 + 8u : len;
     const bool valid = (abs & 7u) != 0 && bd > 0 && bd < len && lo < hi;
     j.lo[k] = valid ? lo : 0; j.hi[k] = valid ? hi : 0;
     prev = valid ? hi : prev;
@@ -675,7 +659,7 @@ constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is
 // `cont`: the record's body is copied in bulk; part 1 then runs on past the header line's "\n" to
 // the body's first chunk boundary (body bytes [0, cont_hi)), so that the bulk copy starts aligned.
 __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
-                                          int part, bool cont, const Body& body, uint32_t cont_hi) {
+                                          int part, bool cont, const Body& body, uint32_t cont_hi, bool prefix) {
   OutStream o;
   if (ms < 0 && r.fast) {
     const uint32_t len = r.end - r.beg;
@@ -708,13 +692,15 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
       os_put(o, (uint32_t)' ' | ((uint32_t)(uint8_t)cap.name[0] << 8) | ((uint32_t)(uint8_t)cap.name[1] << 16) |
                     (b3 << 24), 4u);  // " NAME:"  (parse.rs:166); names are 2 or 3 bytes
       if (cap.name_len == 3) os_put(o, (uint32_t)':', 1u);
-      if (cap.len) os_run(o, r.seq + ms + cap.off, cap.len);
+      if (cap.len) os_copy(o, r.seq + ms + cap.off, cap.len);
       os_put(o, (uint32_t)':', 1u);
-      if (cap.len) os_run(o, r.qual + ms + cap.off, cap.len);
+      if (cap.len) os_copy(o, r.qual + ms + cap.off, cap.len);
     }
     if (part == 1) {
       os_put(o, (uint32_t)'\n', 1u);
-      if (cont) body_range(o, body, 0, cont_hi);
+      if (cont) {
+        if (prefix) body_range<true>(o, body, 0, cont_hi); else body_range<false>(o, body, 0, cont_hi);
+      }
     }
     os_end(o);
     return;

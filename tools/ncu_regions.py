@@ -14,6 +14,7 @@ for r in rows:
     elif len(r) > 7 and r[2].startswith('0x'):
         try: s = int(r[6]); x = int(r[7])
         except Exception: continue
+        if cur is None: cur = ("?", 0); src[cur] = "(no line info)"
         agg[cur] += x; samp[cur] += s
 tot = sum(agg.values()) or 1; ts = sum(samp.values()) or 1
 print("total samples", ts, "total warp instr", tot)

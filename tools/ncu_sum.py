@@ -13,6 +13,7 @@ for r in rows:
     elif len(r) > 7 and r[2].startswith('0x'):
         try: s = int(r[6]); x = int(r[7])
         except Exception: continue
+        if cur is None: cur = ("?", 0)
         agg[cur] += x; samp[cur] += s
 tot = sum(agg.values()); ts = sum(samp.values())
 print("total warp instr per tile-pair %.0f" % (tot / ntp))
