@@ -434,19 +434,6 @@ int bk_debug_phases(bk_ctx* ctx, uint64_t* out24) {
   if (!s.scratch.buf.p) return BK_E_ARG;
   CK(cudaStreamSynchronize(s.stream));
   CK(cudaMemcpy(out24, (uint8_t*)s.scratch.buf.p + 256, 24 * 8, cudaMemcpyDeviceToHost));
-#ifdef BK_PROFILE_PHASES
-  {  // look-back statistics ride in the unused scan slots [10..12]
-    unsigned long long v[3] = {0, 0, 0};
-    cudaMemcpyFromSymbol(&v[0], bk::g_look_rounds, 8);
-    cudaMemcpyFromSymbol(&v[1], bk::g_look_windows, 8);
-    cudaMemcpyFromSymbol(&v[2], bk::g_look_spins, 8);
-    out24[10] = v[0]; out24[11] = v[1]; out24[12] = v[2];
-    unsigned long long z = 0;
-    cudaMemcpyToSymbol(bk::g_look_rounds, &z, 8);
-    cudaMemcpyToSymbol(bk::g_look_windows, &z, 8);
-    cudaMemcpyToSymbol(bk::g_look_spins, &z, 8);
-  }
-#endif
   return BK_OK;
 }
 

@@ -154,11 +154,9 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
   __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_empty[2][kStages];
-  __shared__ uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, then the complement table
+  __shared__ __align__(16) uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, complement table, program
   __shared__ int s_ms[2][2][32];  // [tile parity][mate][lane]
   __shared__ TileMeta meta[NM][kStages];
-  __shared__ uint4 body_desc[NM][32][4];  // bulk-copy descriptors of a record's four body pieces (1, 3, 0, 2)
-  __shared__ uint4 run_desc[NM][32];      // bulk-copy descriptors of the tile's runs of unchanged records
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -191,6 +189,16 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
       cls_tab[m][c] = (uint8_t)mask;
       cls_tab[m][kTabComp + c] = (uint8_t)complement((uint32_t)c);
     }
+    // ... and the program behind them (layout: kTabHdr, kTabOps, kTabLit)
+    uint32_t* const tw = reinterpret_cast<uint32_t*>(&cls_tab[m][0]);
+    if (lane == 0) {
+      tw[kTabHdr / 4 + 0] = pg.nops;
+      tw[kTabHdr / 4 + 1] = pg.total_len;
+      tw[kTabHdr / 4 + 2] = pg.anchor_start;
+      tw[kTabHdr / 4 + 3] = pg.anchor_end;
+    }
+    for (int i = lane; i < 2 * BK_MAX_OPS; i += 32) tw[kTabOps / 4 + i] = reinterpret_cast<const uint32_t*>(pg.ops)[i];
+    for (int i = lane; i < BK_MAX_LIT / 4; i += 32) tw[kTabLit / 4 + i] = reinterpret_cast<const uint32_t*>(pg.lit)[i];
     if (lane == 0)
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&bar_full[m][s], 1);
@@ -295,8 +303,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         PROF(1)
         if (active) {
           if (pg.present && rv.qual_len == rv.seq_len) {  // unequal lengths never leave bk_tokenize
-            ms = match_read<false>(pg, tab, rv.seq, rv.seq_len);
-            if (ms < 0 && rc) ms = match_read<true>(pg, tab, rv.seq, rv.seq_len);  // parse.rs:61-66
+            ms = match_read<false>(tab, rv.seq, rv.seq_len);
+            if (ms < 0 && rc) ms = match_read<true>(tab, rv.seq, rv.seq_len);  // parse.rs:61-66
           }
           if (P.match[m]) P.match[m][r0 + lane] = ms;
         }
@@ -378,9 +386,6 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
   } else {
     // =============================== BACK =======================================================
     uint8_t* const gdst = P.out[m];
-    const bool header_work = pg.present != 0;
-    // a match that need not start the read leaves a piece of seq / qual in front of the cut
-    const bool has_prefix = trim && !pg.anchor_start;
     PROF_INIT
     for (uint32_t k = 0;; ++k) {
       const uint32_t s = k % kStages;
@@ -411,112 +416,9 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         rv.fast = qf & 1u;
         const int ms = tm.ms[lane];
         const uint32_t dst = out_s + phase + ooff;
-        const bool mat = kept && rv.fast && ms >= 0;  // rewritten, bulk-copied body
-        const bool unc = kept && rv.fast && ms < 0;   // unchanged, part of a bulk-copied run
-        const unsigned mm = __ballot_sync(0xffffffffu, mat);
-        const unsigned um = __ballot_sync(0xffffffffu, unc);
-
-        // (a) lane per record, through the stream writer: header lines of rewritten records (warps
-        //     0 and 1), the junctions of the bulk copies (warps 1..3), and every part of a record
-        //     whose framing is not the writer's own (rare: CR line ends, text after '+')
-        Body body;
-        Junctions jn;
-        body.dst = 0;
-        jn.hi[0] = 0;
-        if (mat) {
-          body = body_of(pg, rv, ms, trim, dst);
-          jn = has_prefix ? body_junctions<true>(body) : body_junctions<false>(body);
-        }
-        if ((kept && !rv.fast) || (mat && bj < 2))
-          emit_part(pg, rv, ms, trim, dst, bj, mat, body, jn.hi[0], has_prefix);
-        if (mat && bj >= 2) {
-#pragma unroll
-          for (int k = 1; k <= 4; ++k) {
-            if ((k == 4) != (bj == 3)) continue;  // warp 2: piece boundaries, warp 3: ragged tail
-            if (!has_prefix && (k == 1 || k == 3)) continue;
-            if (jn.lo[k] < jn.hi[k]) {
-              OutStream o;
-              os_begin(o, body.dst + jn.lo[k]);
-              if (has_prefix) body_range<true>(o, body, jn.lo[k], jn.hi[k]);
-              else body_range<false>(o, body, jn.lo[k], jn.hi[k]);
-              os_end(o);
-            }
-          }
-        }
-        // runs of unchanged records: lane i learns its run [i0, i1]; the first lane of a run files
-        // its bulk-copy descriptor (all four back warps write the same list)
-        uint32_t nruns = 0;
-        if (um) {
-          const unsigned below = ~um & ((1u << lane) - 1u);
-          const int i0 = unc ? (below ? 32 - __clz(below) : 0) : lane;
-          const unsigned above = ~(um >> lane);  // first zero at or above this lane ends the run
-          const int i1 = unc ? (above ? lane + __ffs(above) - 2 : 31) : lane;
-          const uint32_t run_s = __shfl_sync(0xffffffffu, rv.beg, i0);
-          const uint32_t run_d = __shfl_sync(0xffffffffu, dst, i0);
-          const uint32_t run_n = __shfl_sync(0xffffffffu, rv.end, i1) - run_s;
-          const bool first = unc && i0 == lane;
-          const unsigned starts = __ballot_sync(0xffffffffu, first);
-          nruns = __popc(starts);
-          uint4 rd = bulk_desc(run_s, run_d, run_n, 16u, 0u);
-          const uint32_t npass = (first && rd.y > rd.x) ? (rd.y - rd.x + 511u) >> 9 : 0u;
-          uint32_t incl = npass;  // passes before this run, over all runs: pass t belongs to warp t % kBackWarps
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-          }
-          rd.w = incl - npass;
-          if (first) run_desc[m][__popc(starts & ((1u << lane) - 1u))] = rd;
-          if (unc && bj >= 2) {
-            uint32_t pad = (16u - (run_d & 15u)) & 15u;
-            pad = pad < run_n ? pad : run_n;
-            const uint32_t t0 = ((run_d + run_n) & ~15u) - run_d;
-            const uint32_t tlo = (int32_t)t0 > (int32_t)pad ? t0 : pad;
-            if (bj == 2 && first && pad) {  // ragged head of the run
-              OutStream o;
-              os_begin(o, run_d);
-              os_short(o, run_s, pad);
-              os_end(o);
-            }
-            if (bj == 3 && i1 == lane && tlo < run_n) {  // ragged tail
-              OutStream o;
-              os_begin(o, run_d + tlo);
-              os_short(o, run_s + tlo, run_n - tlo);
-              os_end(o);
-            }
-          }
-        }
-        // bulk-copy descriptors of the rewritten records this warp will copy.  Warps 0 and 1 carry
-        // the header lines, so they take fewer records.
-        const unsigned share = mm & (!header_work ? (0x11111111u << bj)
-                                     : bj == 0 ? 0x01010101u : bj == 1 ? 0x02020202u : bj == 2 ? 0x1C1C1C1Cu : 0xE0E0E0E0u);
-        const bool mine = (share >> lane) & 1u;
-        const unsigned pre = has_prefix ? __ballot_sync(0xffffffffu, mine && body.n[0] >= 8u) : 0u;
-        if (mine) {
-          const uint32_t d1 = body.dst + body.n[0], d2 = d1 + body.n[1], d3 = d2 + body.n[2];
-          body_desc[m][lane][0] = bulk_desc(body.src[1], d1, body.n[1], 8u, 0u);
-          body_desc[m][lane][1] = bulk_desc(body.src[3], d3, body.n[3], 8u, 0u);
-          if (pre) {
-            body_desc[m][lane][2] = bulk_desc(body.src[0], body.dst, body.n[0], 8u, 0u);
-            body_desc[m][lane][3] = bulk_desc(body.src[2], d2, body.n[2], 8u, 0u);
-          }
-        }
-        __syncwarp();
+        // lane per record, warp per part: part bj of every kept record through the stream writer
+        if (kept) emit_part(pg, rv, ms, trim, dst, bj);
         PROF(1)
-        // (b) bulk, half a warp per piece: the trimmed seq and qual lines of rewritten records
-        for (unsigned w = share; w; w &= w - 1u) {
-          const int i = __ffs(w) - 1;
-          bulk8(body_desc[m][i][lane >> 4], lane);
-          if ((pre >> i) & 1u) bulk8(body_desc[m][i][2 + (lane >> 4)], lane);  // the pieces in front of the match
-        }
-        PROF(2)
-        // (c) bulk, a warp per pass: maximal runs of consecutive unchanged records are contiguous in
-        //     the input tile and in the output
-        for (uint32_t r = 0; r < nruns; ++r) {
-          const uint4 rd = run_desc[m][r];
-          bulk16(rd, lane, (uint32_t)(bj - (int)rd.w) & (kBackWarps - 1), kBackWarps);
-        }
-        PROF(3)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[m][s]);  // ring slot (input tile + meta) is free again

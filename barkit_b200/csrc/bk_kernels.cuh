@@ -277,7 +277,19 @@ __device__ __forceinline__ uint32_t complement(uint32_t c) {
 
 // `tab` is this mate's 512-byte lookup block in shared memory: [0,256) class-membership bits per
 // byte, [256,512) the complement table (a switch here was a quarter of the kernel's code).
-constexpr uint32_t kTabComp = 256, kTabBytes = 512;
+// Behind the two byte tables sits a copy of the matching program itself: read through a reference
+// into the kernel's parameter space from a non-inlined function, every field access was a
+// generic-address load with global-memory latency.
+constexpr uint32_t kTabComp = 256, kTabHdr = 512, kTabOps = 528, kTabLit = kTabOps + 8u * BK_MAX_OPS;
+constexpr uint32_t kTabBytes = kTabLit + BK_MAX_LIT;
+struct MOp { uint32_t off, len, kind, k, idx; };
+__device__ __forceinline__ MOp tab_op(uint32_t tab, uint32_t o) {  // bk_op, little endian
+  const uint2 v = lds64(tab + kTabOps + 8u * o);
+  MOp op;
+  op.off = v.x & 0xFFFFu; op.len = v.x >> 16;
+  op.kind = v.y & 0xFFu; op.k = (v.y >> 8) & 0xFFu; op.idx = v.y >> 16;
+  return op;
+}
 
 template <bool RC>
 __device__ __forceinline__ uint32_t fetch(uint32_t tab, uint32_t seq, uint32_t L, uint32_t j) {
@@ -297,11 +309,11 @@ __device__ __forceinline__ uint32_t fetch(uint32_t tab, uint32_t seq, uint32_t L
 // wildcard slot of one of the alternatives, i.e. under the regex `.`, which must be ASCII here
 // ('\n' cannot occur inside a line).
 template <bool EARLY_OUT>
-__device__ __forceinline__ bool match_at_fwd(const bk_devprog& pg, uint32_t tab, uint32_t seq, uint32_t s) {
+__device__ __forceinline__ bool match_at_fwd(uint32_t tab, uint32_t seq, uint32_t s) {
   bool ok = true;
-  const uint32_t* const lit32 = reinterpret_cast<const uint32_t*>(pg.lit);
-  for (uint32_t o = 0; o < pg.nops; ++o) {
-    const bk_op op = pg.ops[o];
+  const uint32_t nops = lds32(tab + kTabHdr);
+  for (uint32_t o = 0; o < nops; ++o) {
+    const MOp op = tab_op(tab, o);
     const uint32_t base = seq + s + op.off;
     const uint32_t p = base & ~3u, sh = (base & 3u) * 8u;
     const uint32_t nw = (op.len + 3u) >> 2;
@@ -309,12 +321,13 @@ __device__ __forceinline__ bool match_at_fwd(const bk_devprog& pg, uint32_t tab,
     uint32_t prev = lds32(p);
     if (op.kind == BK_OP_LIT) {
       uint32_t mism = 0, bad = 0;
+      const uint32_t lit = tab + kTabLit + op.idx;  // literals start on words (bk_pattern.cc)
 #pragma unroll 1
       for (uint32_t i = 0; i < nw; ++i) {
         const uint32_t nxt = lds32(p + 4u * i + 4u);
         const uint32_t v = __funnelshift_r(prev, nxt, sh);
         prev = nxt;
-        uint32_t x = v ^ lit32[(op.idx >> 2) + i];
+        uint32_t x = v ^ lds32(lit + 4u * i);
         if (i + 1 == nw && tail) x &= (1u << (8u * tail)) - 1u;
         const uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;  // 0x80 per differing byte
         mism += __popc(nz);
@@ -340,18 +353,19 @@ __device__ __forceinline__ bool match_at_fwd(const bk_devprog& pg, uint32_t tab,
 }
 
 template <bool RC, bool EARLY_OUT>
-__device__ __forceinline__ bool match_at(const bk_devprog& pg, uint32_t tab, uint32_t seq, uint32_t L, uint32_t s) {
-  if (!RC) return match_at_fwd<EARLY_OUT>(pg, tab, seq, s);
+__device__ __forceinline__ bool match_at(uint32_t tab, uint32_t seq, uint32_t L, uint32_t s) {
+  if (!RC) return match_at_fwd<EARLY_OUT>(tab, seq, s);
   bool ok = true;
-  for (uint32_t o = 0; o < pg.nops; ++o) {
-    const bk_op op = pg.ops[o];
+  const uint32_t nops = lds32(tab + kTabHdr);
+  for (uint32_t o = 0; o < nops; ++o) {
+    const MOp op = tab_op(tab, o);
     const uint32_t base = s + op.off;
     if (op.kind == BK_OP_LIT) {
       uint32_t mism = 0, bad = 0;
-#pragma unroll 4
+#pragma unroll 1
       for (uint32_t i = 0; i < op.len; ++i) {
         const uint32_t c = fetch<RC>(tab, seq, L, base + i);
-        const uint32_t ne = (c != pg.lit[op.idx + i]);
+        const uint32_t ne = (c != lds8(tab + kTabLit + op.idx + i));
         mism += ne;
         // a wildcard slot is the regex `.`: any ASCII byte except '\n' (pattern.rs:10,71)
         bad |= ne & (uint32_t)((c >= 0x80u) | (c == '\n'));
@@ -359,13 +373,8 @@ __device__ __forceinline__ bool match_at(const bk_devprog& pg, uint32_t tab, uin
       ok = ok && (mism <= op.k) && !bad;
     } else {
       uint32_t acc = 0xFFu;
-      uint32_t i = 0;
-      for (; i + 4 <= op.len; i += 4) {  // 4 independent byte loads, then 4 independent table loads
-        const uint32_t c0 = fetch<RC>(tab, seq, L, base + i), c1 = fetch<RC>(tab, seq, L, base + i + 1);
-        const uint32_t c2 = fetch<RC>(tab, seq, L, base + i + 2), c3 = fetch<RC>(tab, seq, L, base + i + 3);
-        acc &= lds8(tab + c0) & lds8(tab + c1) & lds8(tab + c2) & lds8(tab + c3);
-      }
-      for (; i < op.len; ++i) acc &= lds8(tab + fetch<RC>(tab, seq, L, base + i));
+#pragma unroll 1
+      for (uint32_t i = 0; i < op.len; ++i) acc &= lds8(tab + fetch<RC>(tab, seq, L, base + i));
       ok = ok && ((acc >> op.idx) & 1u);
     }
     if (EARLY_OUT && !ok) return false;
@@ -375,16 +384,17 @@ __device__ __forceinline__ bool match_at(const bk_devprog& pg, uint32_t tab, uin
 
 // leftmost match start or -1
 template <bool RC>
-__device__ __noinline__ int match_read(const bk_devprog& pg, uint32_t tab, uint32_t seq, uint32_t L) {
-  const uint32_t T = pg.total_len;
+__device__ __noinline__ int match_read(uint32_t tab, uint32_t seq, uint32_t L) {
+  const uint4 h = lds128(tab + kTabHdr);  // nops, total_len, anchor_start, anchor_end
+  const uint32_t T = h.y;
   if (L < T) return -1;
-  if (pg.anchor_start || pg.anchor_end) {  // exactly one candidate start
-    if (pg.anchor_start && pg.anchor_end && L != T) return -1;
-    const uint32_t s = pg.anchor_end ? L - T : 0;
-    return match_at<RC, false>(pg, tab, seq, L, s) ? (int)s : -1;
+  if (h.z || h.w) {  // exactly one candidate start
+    if (h.z && h.w && L != T) return -1;
+    const uint32_t s = h.w ? L - T : 0;
+    return match_at<RC, false>(tab, seq, L, s) ? (int)s : -1;
   }
   for (uint32_t s = 0; s <= L - T; ++s)
-    if (match_at<RC, true>(pg, tab, seq, L, s)) return (int)s;
+    if (match_at<RC, true>(tab, seq, L, s)) return (int)s;
   return -1;
 }
 
@@ -471,25 +481,48 @@ __device__ __forceinline__ void os_chunk(OutStream& o, uint32_t s, uint32_t n) {
   o.nb = rem;
 }
 
-// append [s, s+len) of shared memory (any alignment), 1 <= len <= 16 (a barcode, a junction between
-// bulk copies).  Deliberately a real call (the stream state travels in registers), and deliberately
-// the only copy primitive: the kernel's hot code has to fit the SM's 32 KB instruction cache, and
-// an unrolled 32-byte variant plus a long-run loop cost 4 KB of it.
-__device__ __noinline__ OutStream os_short_f(OutStream o, uint32_t s, uint32_t len) {
-  os_chunk<5>(o, s, len);
+// append [s, s+len) of shared memory (any alignment), len > 0.  Deliberately real calls (the
+// stream state travels in registers) and a single copy of the chunk code: the kernel's hot code
+// has to fit the SM's 32 KB instruction cache.
+__device__ __noinline__ OutStream os_chunk9_f(OutStream o, uint32_t s, uint32_t n) {
+  os_chunk<9>(o, s, n);
   return o;
 }
-__device__ __forceinline__ void os_short(OutStream& o, uint32_t s, uint32_t len) { o = os_short_f(o, s, len); }
-// any length > 0, 16 bytes at a time
-__device__ __forceinline__ void os_run(OutStream& o, uint32_t s, uint32_t len) {
-#pragma unroll 1
-  while (len) {
-    const uint32_t n = len < 16u ? len : 16u;
-    os_short(o, s, n);
+__device__ __noinline__ OutStream os_run_f(OutStream o, uint32_t s, uint32_t len) {
+  {  // first chunk: up to the source's next 32-byte-window boundary, which word-aligns the source
+    uint32_t n = 32u - (s & 3u);
+    n = n < len ? n : len;
+    o = os_chunk9_f(o, s, n);
     s += n;
     len -= n;
   }
+  if (len >= 32u) {  // long run: source is word aligned and the pending-byte count stays constant
+    const uint32_t sh = o.nb * 8u;  // (the first chunk was >= 29 bytes, so the stream's first word is out)
+    uint32_t prev = sh ? (o.lo << (32u - sh)) : 0u;  // so that funnelshift_l(prev, w, sh) = lo | w << sh
+    uint32_t dp = o.wpos;
+    do {
+      const uint32_t w0 = lds32(s), w1 = lds32(s + 4), w2 = lds32(s + 8), w3 = lds32(s + 12);
+      const uint32_t w4 = lds32(s + 16), w5 = lds32(s + 20), w6 = lds32(s + 24), w7 = lds32(s + 28);
+      sts32(dp, __funnelshift_l(prev, w0, sh));
+      sts32(dp + 4, __funnelshift_l(w0, w1, sh));
+      sts32(dp + 8, __funnelshift_l(w1, w2, sh));
+      sts32(dp + 12, __funnelshift_l(w2, w3, sh));
+      sts32(dp + 16, __funnelshift_l(w3, w4, sh));
+      sts32(dp + 20, __funnelshift_l(w4, w5, sh));
+      sts32(dp + 24, __funnelshift_l(w5, w6, sh));
+      sts32(dp + 28, __funnelshift_l(w6, w7, sh));
+      prev = w7;
+      s += 32;
+      dp += 32;
+      len -= 32;
+    } while (len >= 32u);
+    o.lo = __funnelshift_l(prev, 0u, sh);
+    o.wpos = dp;
+  }
+  if (len) o = os_chunk9_f(o, s, len);
+  return o;
 }
+__device__ __forceinline__ void os_run(OutStream& o, uint32_t s, uint32_t len) { o = os_run_f(o, s, len); }
 __device__ __forceinline__ void os_copy(OutStream& o, uint32_t s, uint32_t len) { os_run(o, s, len); }
 
 __device__ __forceinline__ void os_end(const OutStream& o) {
@@ -512,137 +545,6 @@ __device__ __noinline__ OutStream os_put_f(OutStream o, uint32_t v, uint32_t n) 
 }
 __device__ __forceinline__ void os_put(OutStream& o, uint32_t v, uint32_t n) { o = os_put_f(o, v, n); }
 
-// ---- bulk copies (warp-cooperative) + junctions (lane per record) -----------------------------------
-//
-// Long runs of output bytes that are verbatim input bytes (the trimmed seq / qual lines of a
-// rewritten record, whole runs of unchanged records) are copied by all lanes of a warp together:
-// consecutive lanes own consecutive aligned destination chunks, read the aligned source chunks
-// under them and funnel-shift by the run's relative misalignment, so every access of a pass covers
-// consecutive words (no bank conflicts) and the passes are independent of each other.  A bulk copy
-// writes only destination chunks that lie completely inside its run; the ragged chunks where runs
-// meet ("junctions") are written by the lane that owns the record, through the byte-exact stream
-// writer above, 32 records per instruction.  Every output byte therefore has exactly one writer
-// per word and the two kinds of writers never share a word.
-
-// Bulk-copy descriptor, built once per run by the lane that owns the record (32 records per
-// instruction) and read back warp-uniformly, so that the per-run cost in the copy loops is one
-// 16-byte load instead of a dozen shuffles and address computations.
-//   x: first destination chunk (aligned up)   y: end of the last full chunk (aligned down)
-//   z: source - destination                   w: free (pass prefix for the 16-byte form)
-__device__ __forceinline__ uint4 bulk_desc(uint32_t s, uint32_t d, uint32_t n, uint32_t chunk, uint32_t w) {
-  return make_uint4((d + chunk - 1u) & ~(chunk - 1u), (d + n) & ~(chunk - 1u), s - d, w);
-}
-
-// Two runs at once, one per half warp, 8-byte chunks: lanes 0-15 copy the run of q0, lanes 16-31
-// that of q1 (each lane passes the descriptor of its half).
-__device__ __forceinline__ void bulk8(const uint4 q, int lane) {
-  const uint32_t delta = q.z;
-  const uint32_t off = delta & ~7u, sh = (delta & 3u) * 8u;
-  const bool up = (delta & 4u) != 0;
-  for (uint32_t D = q.x + 8u * ((uint32_t)lane & 15u); D < q.y; D += 128u) {
-    const uint2 x = lds64(D + off), y = lds64(D + off + 8u);
-    const uint32_t a = up ? x.y : x.x, b = up ? y.x : x.y, c = up ? y.y : y.x;
-    sts64(D, __funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh));
-  }
-}
-
-// One long run, 16-byte chunks, descriptor warp-uniform: the warp does passes t0, t0 + tstep, ...
-// of 32 chunks each.
-__device__ __forceinline__ void bulk16(const uint4 r, int lane, uint32_t t0, uint32_t tstep) {
-  const uint32_t delta = r.z;
-  const uint32_t off = delta & ~15u, sh = (delta & 3u) * 8u, q = (delta >> 2) & 3u;
-  for (uint32_t D = r.x + 16u * (32u * t0 + (uint32_t)lane); D < r.y; D += 512u * tstep) {
-    const uint4 x = lds128(D + off), y = lds128(D + off + 16u);
-    uint32_t o0, o1, o2, o3;
-    if (q == 0) {  // warp-uniform
-      o0 = __funnelshift_r(x.x, x.y, sh); o1 = __funnelshift_r(x.y, x.z, sh);
-      o2 = __funnelshift_r(x.z, x.w, sh); o3 = __funnelshift_r(x.w, y.x, sh);
-    } else if (q == 1) {
-      o0 = __funnelshift_r(x.y, x.z, sh); o1 = __funnelshift_r(x.z, x.w, sh);
-      o2 = __funnelshift_r(x.w, y.x, sh); o3 = __funnelshift_r(y.x, y.y, sh);
-    } else if (q == 2) {
-      o0 = __funnelshift_r(x.z, x.w, sh); o1 = __funnelshift_r(x.w, y.x, sh);
-      o2 = __funnelshift_r(y.x, y.y, sh); o3 = __funnelshift_r(y.y, y.z, sh);
-    } else {
-      o0 = __funnelshift_r(x.w, y.x, sh); o1 = __funnelshift_r(y.x, y.y, sh);
-      o2 = __funnelshift_r(y.y, y.z, sh); o3 = __funnelshift_r(y.z, y.w, sh);
-    }
-    sts128(D, o0, o1, o2, o3);
-  }
-}
-
-// The part of a rewritten record's output after its header line ("body"), as up to four verbatim
-// pieces (parse.rs:138-148 with the writer's framing, fastq.rs:261):
-//   seq[..cs)   seq[ce..] "\n+\n"   qual[..cs)   qual[ce..] "\n"
-// valid for records in the writer's own framing (RecView::fast), where the separators follow the
-// lines in the input as well.  Pieces 0 and 2 are empty when the match starts the read.
-struct Body {
-  uint32_t dst;     // shared address of the body's first output byte
-  uint32_t src[4];  // shared address of each piece's first input byte
-  uint32_t n[4];    // piece lengths
-};
-
-__device__ __forceinline__ Body body_of(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d) {
-  Body b;
-  const uint32_t cs = trim ? (uint32_t)ms : 0u, ce = trim ? (uint32_t)ms + pg.total_len : 0u;
-  b.dst = d + 2u + r.head_len + pg.hdr_growth;
-  b.src[0] = r.seq;       b.n[0] = cs;
-  b.src[1] = r.seq + ce;  b.n[1] = r.seq_len - ce + 3u;
-  b.src[2] = r.qual;      b.n[2] = cs;
-  b.src[3] = r.qual + ce; b.n[3] = r.seq_len - ce + 1u;
-  return b;
-}
-
-// append body bytes [lo, hi) (body-relative) to the stream.  PREFIX = false: pieces 0 and 2 are known
-// to be empty (the pattern is anchored at the read's start, or nothing is trimmed) -- a program-wide
-// fact, so that the common case runs, and keeps in the instruction cache, half the code.
-template <bool PREFIX>
-__device__ __forceinline__ void body_range(OutStream& o, const Body& b, uint32_t lo, uint32_t hi) {
-  uint32_t ps = 0;
-#pragma unroll
-  for (int p = PREFIX ? 0 : 1; p < 4; p += PREFIX ? 1 : 2) {
-    const uint32_t a = lo > ps ? lo : ps, e = hi < ps + b.n[p] ? hi : ps + b.n[p];
-    if (a < e) os_short(o, b.src[p] + (a - ps), e - a);  // junctions are at most 15 bytes
-    ps += b.n[p];
-  }
-}
-
-// Junction ranges of a body for 8-byte bulk chunks, body-relative: j[0] = [0, hi0) is the ragged
-// head (continues the header line's stream), j[1..3] the chunks that contain a piece boundary,
-// j[4] the ragged tail.  Ranges are disjoint and ascending; an empty one has lo >= hi.
-struct Junctions { uint32_t lo[5], hi[5]; };
-
-template <bool PREFIX>
-__device__ __forceinline__ Junctions body_junctions(const Body& b) {
-  Junctions j;
-  const uint32_t len = b.n[0] + b.n[1] + b.n[2] + b.n[3];
-  uint32_t pad = (8u - (b.dst & 7u)) & 7u;
-  pad = pad < len ? pad : len;
-  j.lo[0] = 0; j.hi[0] = pad;
-  uint32_t prev = pad, bd = 0;
-#pragma unroll
-  for (int k = 1; k <= 3; ++k) {
-    bd += b.n[k - 1];  // boundary between pieces k-1 and k
-    if (!PREFIX && k != 2) {  // coincides with the body's start (k = 1) or with boundary 2 (k = 3)
-      j.lo[k] = j.hi[k] = 0;
-      continue;
-    }
-    const uint32_t abs = b.dst + bd;
-    const uint32_t c0 = (abs & ~7u) - b.dst;  // chunk start, body-relative (may wrap below zero)
-    const uint32_t lo = (int32_t)c0 > (int32_t)prev ? c0 : prev;
-    const uint32_t hi = c0 + 8u < len ? c0 + 8u : len;
-    const bool valid = (abs & 7u) != 0 && bd > 0 && bd < len && lo < hi;
-    j.lo[k] = valid ? lo : 0; j.hi[k] = valid ? hi : 0;
-    prev = valid ? hi : prev;
-  }
-  const uint32_t aend = b.dst + len;
-  const uint32_t t0 = (aend & ~7u) - b.dst;
-  const uint32_t lo = (int32_t)t0 > (int32_t)prev ? t0 : prev;
-  const bool valid = (aend & 7u) != 0 && lo < len;
-  j.lo[4] = valid ? lo : 0; j.hi[4] = valid ? len : 0;
-  return j;
-}
-
 constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is written by warp j
 
 // Part `part` (0..3) of one record's output at shared address d.  The record is
@@ -656,10 +558,8 @@ constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is
 // A record that is copied unchanged and already has the writer's framing (`fast`) is one run, cut
 // into four byte ranges.  Requires qual_len == seq_len for matched records (the front warp treats
 // anything else as unmatched; bk_tokenize never produces it).
-// `cont`: the record's body is copied in bulk; part 1 then runs on past the header line's "\n" to
-// the body's first chunk boundary (body bytes [0, cont_hi)), so that the bulk copy starts aligned.
 __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
-                                          int part, bool cont, const Body& body, uint32_t cont_hi, bool prefix) {
+                                          int part) {
   OutStream o;
   if (ms < 0 && r.fast) {
     const uint32_t len = r.end - r.beg;
@@ -696,12 +596,7 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
       os_put(o, (uint32_t)':', 1u);
       if (cap.len) os_copy(o, r.qual + ms + cap.off, cap.len);
     }
-    if (part == 1) {
-      os_put(o, (uint32_t)'\n', 1u);
-      if (cont) {
-        if (prefix) body_range<true>(o, body, 0, cont_hi); else body_range<false>(o, body, 0, cont_hi);
-      }
-    }
+    if (part == 1) os_put(o, (uint32_t)'\n', 1u);
     os_end(o);
     return;
   }

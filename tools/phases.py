@@ -19,7 +19,7 @@ _lib.lib.bk_debug_phases(ctx.handle,out.ctypes.data)
 ntiles=(P+31)//32
 print("kernel_ms",r.kernel_ms,"Mpairs/s",P/r.kernel_ms/1e3,"tiles",ntiles)
 names={0:"L wait_empty",1:"L claim",2:"L offsets+issue",
- 4:"S wait_pub",5:"S lookback",
+ 4:"S wait_pub",5:"S lookback (per tile of this scan warp x0.5)",
  8:"F wait_full",9:"F parse",10:"F match",11:"F exchange",12:"F size/scan/pub/meta",
- 16:"B wait_ready",17:"B headers (lane/rec)",18:"B matched runs",19:"B unchanged runs",20:"B release+store"}
+ 16:"B emit m0 part0",17:"B emit m0 part1",18:"B emit m0 part2",19:"B emit m0 part3",20:"B emit m1 q0",21:"B emit m1 q1",22:"B emit m1 q2",23:"B emit m1 q3"}
 for i,n in names.items(): print("%-24s %8.0f cyc/tile"%(n,out[i]/ntiles))
