@@ -8,76 +8,75 @@ namespace bk {
 constexpr int kStages = 3;  // input ring depth per mate (the loader runs at most this far ahead)
 constexpr int kBackWarps = kEmitParts;  // back warps per mate: warp j writes part j of every record (emit_part)
 
-// ---- ordered compaction: decoupled look-back over tiles ------------------------------------------------
+// ---- ordered compaction: two-level decoupled look-back ---------------------------------------------------
 //
-// One 16-byte descriptor per tile: {stream 0, stream 1}, each a 62-bit value tagged kFlagAgg (the
-// tile's own output bytes on that stream) or kFlagPrefix (inclusive prefix over all tiles up to and
-// including this one).  The two front warps publish their halves independently; one scan warp
-// resolves both streams with a single pass over the predecessors.
+// Tile descriptors (8 bytes): the tile's own output bytes on stream 0 | stream 1, each half tagged
+// with kTileReady; the two front warps publish their halves independently.
+// Block descriptors (16 bytes, one per 32 consecutive tiles): {stream 0, stream 1}, each a 62-bit
+// value tagged kFlagAgg (the block's own output bytes) or kFlagPrefix (inclusive prefix through the
+// block's last tile).  They are published by the scan warp of the block's last tile.
+//
+// A tile's exclusive prefix = the aggregates of the earlier tiles of its own block (one window of
+// tile descriptors) + a look-back over whole blocks.  With kStages tiles per CTA in flight, several
+// hundred claimed tiles are unresolved at any time; a flat look-back walks all of them, 128 per L2
+// round trip, and its latency in turn keeps more tiles unresolved.  Over blocks the same distance is
+// one window, and both windows' loads are issued together: two round trips become one.
 
-constexpr int kLookPerLane = 4;  // consecutive descriptors per lane and round: 128 tiles per round
+constexpr uint32_t kTileReady = 0x80000000u;
 
 __device__ __forceinline__ ulonglong2 ld_desc(const unsigned long long* p) {
   ulonglong2 v;
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long long x, unsigned long long y) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
+}
 // usable once both halves carry the same tag (a half-updated descriptor is simply read again)
 __device__ __forceinline__ bool desc_ready(const ulonglong2& d, bool two) {
   const unsigned f0 = (unsigned)(d.x >> 62), f1 = (unsigned)(d.y >> 62);
   return f0 != 0 && (!two || f1 == f0);
 }
+__device__ __forceinline__ bool tile_ready(unsigned long long t, bool two) {
+  return ((uint32_t)t & kTileReady) && (!two || ((uint32_t)(t >> 32) & kTileReady));
+}
 
-// Exclusive prefixes of tile `tile` on both streams.  The tile's own aggregates have already been
-// published (by the front warps); this publishes the inclusive prefixes once they are known.
-// Per round every lane fetches kLookPerLane consecutive predecessors (independent loads, one L2
-// round trip for 128 tiles), folds them locally -- aggregates up to and including its nearest
-// prefix -- and one warp-level step combines the lanes.  Deliberately compact: the kernel's hot
-// code has to fit the SM's 32 KB instruction cache, and an unrolled window-per-
-// iteration form of this function alone was 10 KB.
-__device__ __noinline__ ulonglong2 lookback(unsigned long long* desc, uint32_t tile, uint32_t agg0, uint32_t agg1,
-                                            bool two, int lane) {
-  unsigned long long e0 = 0, e1 = 0;
-  for (int look = (int)tile - 1; look >= 0; look -= 32 * kLookPerLane) {
-    const int base = look - kLookPerLane * lane;  // this lane's nearest predecessor
-    ulonglong2 d[kLookPerLane];
-    bool ready;
-    do {
-      ready = true;
-#pragma unroll
-      for (int j = 0; j < kLookPerLane; ++j) {
-        // tiles before 0 read as "prefix 0"
-        d[j] = base - j >= 0 ? ld_desc(desc + 2 * (size_t)(base - j)) : make_ulonglong2(kFlagPrefix, kFlagPrefix);
-        ready = ready && desc_ready(d[j], two);
-      }
-    } while (__any_sync(0xffffffffu, !ready));
-    // aggregates are one tile's bytes (32 bits is plenty); only the prefixes themselves are 64-bit
-    uint32_t a0 = 0, a1 = 0;
-    unsigned long long p0 = 0, p1 = 0;
-    bool found = false;
-#pragma unroll
-    for (int j = 0; j < kLookPerLane; ++j) {
-      const bool pre = (d[j].x >> 62) == 2;
-      if (!found && !pre) { a0 += (uint32_t)d[j].x; a1 += (uint32_t)d[j].y; }
-      if (!found && pre) { p0 = d[j].x & kValueMask; p1 = d[j].y & kValueMask; }
-      found = found || pre;
-    }
-    const unsigned pm = __ballot_sync(0xffffffffu, found);
-    const int first = pm ? __ffs(pm) - 1 : 31;  // nearest lane holding inclusive prefixes
-    e0 += __reduce_add_sync(0xffffffffu, lane <= first ? a0 : 0u);
-    if (two) e1 += __reduce_add_sync(0xffffffffu, lane <= first ? a1 : 0u);
+// Exclusive prefixes of tile `tile` on both streams.  The tile's own aggregates (agg0, agg1) have
+// already been published by the front warps.
+__device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned long long* bdesc, uint32_t tile,
+                                            uint32_t agg0, uint32_t agg1, bool two, int lane) {
+  const uint32_t blk = tile >> 5, j = tile & 31u;
+  // window 1: the earlier tiles of this block; window 2: the 32 blocks before it (lane 0 = nearest)
+  const bool in_blk = (uint32_t)lane < j;
+  const unsigned long long* tp = tdesc + (size_t)(blk << 5) + lane;
+  int look = (int)blk - 1;
+  unsigned long long t = in_blk ? ld_relaxed_u64(tp) : 0ull;
+  ulonglong2 d = look - lane >= 0 ? ld_desc(bdesc + 2 * (size_t)(look - lane)) : make_ulonglong2(kFlagPrefix, kFlagPrefix);
+  while (__any_sync(0xffffffffu, in_blk && !tile_ready(t, two)))
+    if (in_blk && !tile_ready(t, two)) t = ld_relaxed_u64(tp);
+  const uint32_t s0 = __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)t & ~kTileReady : 0u);
+  const uint32_t s1 = two ? __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)(t >> 32) & ~kTileReady : 0u) : 0u;
+  const bool last = j == 31u;  // this tile completes its block
+  if (last && lane == 0) st_desc(bdesc + 2 * (size_t)blk, kFlagAgg | (unsigned long long)(s0 + agg0),
+                                 kFlagAgg | (unsigned long long)(s1 + agg1));
+  unsigned long long e0 = s0, e1 = s1;
+  while (true) {  // blocks before 0 read as "prefix 0", so this ends at the latest there
+    while (__any_sync(0xffffffffu, !desc_ready(d, two)))
+      if (!desc_ready(d, two)) d = ld_desc(bdesc + 2 * (size_t)(look - lane));
+    const unsigned pm = __ballot_sync(0xffffffffu, (d.x >> 62) == 2);
+    const int first = pm ? __ffs(pm) - 1 : 32;  // nearest block holding inclusive prefixes
+    // a block's aggregate is at most 32 tiles' bytes (32 bits is plenty); only prefixes are 64-bit
+    e0 += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)d.x : 0u);
+    if (two) e1 += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)d.y : 0u);
     if (pm) {
-      e0 += __shfl_sync(0xffffffffu, p0, first);
-      if (two) e1 += __shfl_sync(0xffffffffu, p1, first);
+      e0 += __shfl_sync(0xffffffffu, d.x & kValueMask, first);
+      if (two) e1 += __shfl_sync(0xffffffffu, d.y & kValueMask, first);
       break;
     }
+    look -= 32;
+    d = look - lane >= 0 ? ld_desc(bdesc + 2 * (size_t)(look - lane)) : make_ulonglong2(kFlagPrefix, kFlagPrefix);
   }
-  if (lane == 0) {
-    unsigned long long* p = desc + 2 * (size_t)tile;
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(kFlagPrefix | (e0 + agg0)),
-                 "l"(kFlagPrefix | (e1 + agg1))
-                 : "memory");
-  }
+  if (last && lane == 0) st_desc(bdesc + 2 * (size_t)blk, kFlagPrefix | (e0 + agg0), kFlagPrefix | (e1 + agg1));
   return make_ulonglong2(e0, e1);
 }
 
@@ -335,7 +334,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         if (lane >= d) incl += t;
       }
       const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      if (lane == 0) st_relaxed_u64(P.desc[0] + 2 * (size_t)tile + m, kFlagAgg | (unsigned long long)total);
+      if (lane == 0)
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(P.desc[0] + tile) + m),
+                     "r"(total | kTileReady)
+                     : "memory");
 
       {  // statistics
         const unsigned kb = __ballot_sync(0xffffffffu, keep);
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
       const uint32_t tile = meta[0][s].tile;
       if (tile == kEndTile2) break;
       if (tile != kEndTile) {
-        const ulonglong2 g = lookback(P.desc[0], tile, meta[0][s].total, PAIRED ? meta[NM - 1][s].total : 0u, PAIRED, lane);
+        const ulonglong2 g = lookback(P.desc[0], P.desc[1], tile, meta[0][s].total, PAIRED ? meta[NM - 1][s].total : 0u, PAIRED, lane);
         if (lane == 0) {
           meta[0][s].gout = g.x;
           if (PAIRED) meta[NM - 1][s].gout = g.y;
