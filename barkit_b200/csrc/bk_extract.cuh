@@ -5,7 +5,7 @@
 
 namespace bk {
 
-constexpr int kStages = 3;  // input ring depth per mate (the loader runs at most this far ahead)
+constexpr int kStages = 4;  // input ring depth per mate (the loader runs at most this far ahead)
 constexpr int kBackWarps = kEmitParts;  // back warps per mate: warp j writes part j of every record (emit_part)
 
 // ---- ordered compaction: two-level decoupled look-back ---------------------------------------------------
