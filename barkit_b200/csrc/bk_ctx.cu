@@ -131,9 +131,10 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   return BK_OK;
 }
 
-// [512 B header | tile descriptors, 8 B each | block descriptors (one per 32 tiles), 16 B each]
+// [512 B header | tile descriptors, 8 B each | block descriptors (one per 32 tiles), 16 B each | block accumulators, 16 B each]
 size_t block_desc_offset(uint32_t ntiles) { return 512 + (((size_t)ntiles * 8 + 15) & ~size_t(15)); }
-size_t scratch_bytes(uint32_t ntiles) { return block_desc_offset(ntiles) + ((size_t)ntiles / 32 + 1) * 16; }
+size_t block_acc_offset(uint32_t ntiles) { return block_desc_offset(ntiles) + ((size_t)ntiles / 32 + 1) * 16; }
+size_t scratch_bytes(uint32_t ntiles) { return block_acc_offset(ntiles) + ((size_t)ntiles / 32 + 1) * 16; }
 
 // enqueue: scratch reset + extract kernel.  All pointers are device pointers.
 int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
@@ -176,6 +177,7 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.prof = (unsigned long long*)(sc + 256);
   P.desc[0] = (unsigned long long*)(sc + 512);
   P.desc[1] = (unsigned long long*)(sc + block_desc_offset(lp.ntiles));
+  P.desc[2] = (unsigned long long*)(sc + block_acc_offset(lp.ntiles));
   P.n = n;
   P.ntiles = lp.ntiles;
   P.tile_recs = lp.tile_recs;

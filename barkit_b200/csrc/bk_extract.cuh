@@ -14,7 +14,9 @@ constexpr int kBackWarps = kEmitParts;  // back warps per mate: warp j writes pa
 // with kTileReady; the two front warps publish their halves independently.
 // Block descriptors (16 bytes, one per 32 consecutive tiles): {stream 0, stream 1}, each a 62-bit
 // value tagged kFlagAgg (the block's own output bytes) or kFlagPrefix (inclusive prefix through the
-// block's last tile).  They are published by the scan warp of the block's last tile.
+// block's last tile).  The aggregate is published by whichever front warp adds the block's last
+// tile to the block's accumulator (so it depends on no scan warp's progress), the prefix by the
+// scan warp of the block's last tile.
 //
 // A tile's exclusive prefix = the aggregates of the earlier tiles of its own block (one window of
 // tile descriptors) + a look-back over whole blocks.  With kStages tiles per CTA in flight, several
@@ -32,10 +34,14 @@ __device__ __forceinline__ ulonglong2 ld_desc(const unsigned long long* p) {
 __device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long long x, unsigned long long y) {
   asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
 }
-// usable once both halves carry the same tag (a half-updated descriptor is simply read again)
+// usable once both halves are there and of the same kind (a half-updated descriptor is simply read again)
 __device__ __forceinline__ bool desc_ready(const ulonglong2& d, bool two) {
   const unsigned f0 = (unsigned)(d.x >> 62), f1 = (unsigned)(d.y >> 62);
-  return f0 != 0 && (!two || f1 == f0);
+  return f0 != 0 && (!two || (f1 != 0 && (f0 == 2) == (f1 == 2)));
+}
+// descriptors only ever move up: nothing -> aggregate -> prefix (the tags order that way)
+__device__ __forceinline__ void desc_raise(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ bool tile_ready(unsigned long long t, bool two) {
   return ((uint32_t)t & kTileReady) && (!two || ((uint32_t)(t >> 32) & kTileReady));
@@ -57,8 +63,6 @@ __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned 
   const uint32_t s0 = __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)t & ~kTileReady : 0u);
   const uint32_t s1 = two ? __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)(t >> 32) & ~kTileReady : 0u) : 0u;
   const bool last = j == 31u;  // this tile completes its block
-  if (last && lane == 0) st_desc(bdesc + 2 * (size_t)blk, kFlagAgg | (unsigned long long)(s0 + agg0),
-                                 kFlagAgg | (unsigned long long)(s1 + agg1));
   unsigned long long e0 = s0, e1 = s1;
   while (true) {  // blocks before 0 read as "prefix 0", so this ends at the latest there
     while (__any_sync(0xffffffffu, !desc_ready(d, two)))
@@ -76,7 +80,10 @@ __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned 
     look -= 32;
     d = look - lane >= 0 ? ld_desc(bdesc + 2 * (size_t)(look - lane)) : make_ulonglong2(kFlagPrefix, kFlagPrefix);
   }
-  if (last && lane == 0) st_desc(bdesc + 2 * (size_t)blk, kFlagPrefix | (e0 + agg0), kFlagPrefix | (e1 + agg1));
+  if (last && lane == 0) {
+    desc_raise(bdesc + 2 * (size_t)blk, kFlagPrefix | (e0 + agg0));
+    desc_raise(bdesc + 2 * (size_t)blk + 1, kFlagPrefix | (e1 + agg1));
+  }
   return make_ulonglong2(e0, e1);
 }
 
@@ -334,10 +341,13 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         if (lane >= d) incl += t;
       }
       const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      if (lane == 0)
+      unsigned long long blk_old = 0;  // the block's accumulator before this tile: tiles << 48 | bytes
+      if (lane == 0) {
         asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(P.desc[0] + tile) + m),
                      "r"(total | kTileReady)
                      : "memory");
+        blk_old = atomicAdd(P.desc[2] + 2 * (size_t)(tile >> 5) + m, (1ull << 48) | (unsigned long long)total);
+      }
 
       {  // statistics
         const unsigned kb = __ballot_sync(0xffffffffu, keep);
@@ -359,6 +369,13 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
       if (lane == 0) tm.total = total;
       __syncwarp();
       nbar_arrive(pub_id(s), kPubCount);
+      // whoever completes a block publishes its aggregate (the answer of the atomic is needed only now)
+      if (lane == 0) {
+        const uint32_t blk = tile >> 5;
+        const uint32_t in_blk = min(32u, P.ntiles - (blk << 5));
+        if ((uint32_t)(blk_old >> 48) + 1u == in_blk)
+          desc_raise(P.desc[1] + 2 * (size_t)blk + m, kFlagAgg | ((blk_old & ((1ull << 48) - 1)) + total));
+      }
       PROF(4)
     }
     PROF_FLUSH(8)

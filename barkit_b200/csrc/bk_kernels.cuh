@@ -42,7 +42,7 @@ struct KParams {
   uint8_t* out[2];
   unsigned long long cap[2];
   int32_t* match[2];
-  unsigned long long* desc[2];  // look-back descriptors, one per tile and output stream
+  unsigned long long* desc[3];  // look-back state: tile descriptors, block descriptors, block accumulators
   unsigned int* tile_counter;
   DevResult* result;
   unsigned long long* prof;  // 24 phase-cycle sums (only written when built with BK_PROFILE_PHASES)
