@@ -58,15 +58,19 @@ __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned 
   int look = (int)blk - 1;
   unsigned long long t = in_blk ? ld_relaxed_u64(tp) : 0ull;
   ulonglong2 d = look - lane >= 0 ? ld_desc(bdesc + 2 * (size_t)(look - lane)) : make_ulonglong2(kFlagPrefix, kFlagPrefix);
-  while (__any_sync(0xffffffffu, in_blk && !tile_ready(t, two)))
+  while (__any_sync(0xffffffffu, in_blk && !tile_ready(t, two))) {
+    __nanosleep(64);  // a predecessor is still being parsed: do not burn issue slots and L2 bandwidth on it
     if (in_blk && !tile_ready(t, two)) t = ld_relaxed_u64(tp);
+  }
   const uint32_t s0 = __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)t & ~kTileReady : 0u);
   const uint32_t s1 = two ? __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)(t >> 32) & ~kTileReady : 0u) : 0u;
   const bool last = j == 31u;  // this tile completes its block
   unsigned long long e0 = s0, e1 = s1;
   while (true) {  // blocks before 0 read as "prefix 0", so this ends at the latest there
-    while (__any_sync(0xffffffffu, !desc_ready(d, two)))
+    while (__any_sync(0xffffffffu, !desc_ready(d, two))) {
+      __nanosleep(64);
       if (!desc_ready(d, two)) d = ld_desc(bdesc + 2 * (size_t)(look - lane));
+    }
     const unsigned pm = __ballot_sync(0xffffffffu, (d.x >> 62) == 2);
     const int first = pm ? __ffs(pm) - 1 : 32;  // nearest block holding inclusive prefixes
     // a block's aggregate is at most 32 tiles' bytes (32 bits is plenty); only prefixes are 64-bit
@@ -132,7 +136,7 @@ __device__ __forceinline__ void back_sync(int m) {
 // per ring slot for fronts -> scan ("aggregates published") and scan -> backs ("offsets known").
 // A slot's barrier is reused only after the slot went round the ring, i.e. after every consumer
 // has left it.
-static_assert(kStages <= 6, "barrier ids 4..15 hold two barriers per ring slot");
+static_assert(kStages <= 5, "barrier ids 4..15: two per ring slot, then the second front pair's exchange");
 __device__ __forceinline__ uint32_t pub_id(uint32_t s) { return 4u + s; }
 __device__ __forceinline__ uint32_t ready_id(uint32_t s) { return 4u + kStages + s; }
 constexpr int kScanWarps = 2;  // scan warp j resolves the tiles of ring rounds k with k % 2 == j
@@ -153,7 +157,8 @@ struct TileMeta {  // hand-over between the roles, one per (mate, stage); SoA so
   unsigned long long gout;  // global output offset of the tile on this stream (scan)
 };
 
-constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (1 + kBackWarps) + kScanWarps + 1; }
+constexpr int kFrontPairs = 2;  // front warps per mate: warp p takes the ring rounds k with k % 2 == p
+constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + kBackWarps) + kScanWarps + 1; }
 
 template <bool PAIRED>
 __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(const __grid_constant__ KParams P) {
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
   constexpr int NM = PAIRED ? 2 : 1;
   __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_empty[2][kStages];
   __shared__ __align__(16) uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, complement table, program
-  __shared__ int s_ms[2][2][32];  // [tile parity][mate][lane]
+  __shared__ int s_ms[kFrontPairs][2][2][32];  // [front pair][round parity][mate][lane]
   __shared__ TileMeta meta[NM][kStages];
 
   const int lane = threadIdx.x & 31;
@@ -170,9 +175,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
   constexpr int NB = NM * kBackWarps;
   const bool is_back = warp < NB;
   const bool is_scan = !is_back && warp < NB + kScanWarps;
-  const bool is_front = !is_back && !is_scan && warp < NB + kScanWarps + NM;
-  const bool is_loader = warp == NB + kScanWarps + NM;
-  const int m = is_back ? warp % NM : is_front ? warp - NB - kScanWarps : 0;  // mate = output stream
+  const bool is_front = !is_back && !is_scan && warp < NB + kScanWarps + NM * kFrontPairs;
+  const bool is_loader = warp == NB + kScanWarps + NM * kFrontPairs;
+  const int fw = warp - NB - kScanWarps;  // front warp index
+  const int m = is_back ? warp % NM : is_front ? fw % NM : 0;  // mate = output stream
+  const int fp = is_front ? fw / NM : 0;  // front pair: which ring rounds this front warp takes
   const int bj = is_back ? warp / NM : 0;  // back warp index within the mate
   constexpr uint32_t kPubCount = 32 * (NM + 1), kReadyCount = 32 * (1 + NB);
   const bk_devprog& pg = P.prog[m];
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
   const uint32_t out_s = smem_base + kStages * (P.in_cap[0] + (PAIRED ? P.in_cap[1] : 0)) + (m ? P.out_cap[0] : 0);
   const uint32_t tab = smem_u32(&cls_tab[m][0]);
 
-  if (is_front) {
+  if (is_front && fp == 0) {
     // byte -> "which classes contain it" table, so a class test is one shared-memory lookup
     for (int c = lane; c < 256; c += 32) {
       uint32_t mask = 0;
@@ -283,17 +290,20 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
     PROF_FLUSH(0)
   } else if (is_front) {
     // =============================== FRONT ======================================================
+    // Two front warps per mate take alternate ring rounds: at one warp per mate the front was 80 % busy,
+    // tiles queued behind one another between claim and publication, and every later tile's look-back
+    // waited for the slowest of them.
     PROF_INIT
-    for (uint32_t k = 0;; ++k) {
+    for (uint32_t k = fp;; k += kFrontPairs) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
+      const uint32_t xb = (k / kFrontPairs) & 1u;  // exchange buffer of this pair's round
       TileMeta& tm = meta[m][s];
       mbar_wait(&bar_full[m][s], ph);  // offsets written, text landed
       PROF(0)
       const uint32_t tile = tm.tile;
-      if (tile == kEndTile || tile == kEndTile2) {
+      if (tile == kEndTile || tile == kEndTile2) {  // one end marker per front pair (and per scan warp)
         nbar_arrive(pub_id(s), kPubCount);
-        if (tile == kEndTile2) break;
-        continue;
+        break;
       }
       const uint32_t r0 = tile * R;
       const uint32_t nrec = tm.nrec;
@@ -323,10 +333,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
       int ms_other = -1;
       bool skip = too_big;
       if (PAIRED) {
-        s_ms[k & 1][m][lane] = too_big ? kSkipTile : ms;
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        ms_other = s_ms[k & 1][m ^ 1][lane];
-        skip = skip || (s_ms[k & 1][m ^ 1][0] == kSkipTile);
+        s_ms[fp][xb][m][lane] = too_big ? kSkipTile : ms;
+        nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);  // the two mates' front warps of this pair
+        ms_other = s_ms[fp][xb][m ^ 1][lane];
+        skip = skip || (s_ms[fp][xb][m ^ 1][0] == kSkipTile);
       }
       PROF(3)
       // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
