@@ -441,7 +441,7 @@ __device__ __forceinline__ void os_store_first(OutStream& o, uint32_t v, bool en
   o.skip = en ? 0u : sk;
 }
 
-// Append n (1..4*NW-4) bytes starting at shared address s (any alignment) to the stream, NW = 9 or 5.
+// Append n (1..4*NW-4) bytes starting at shared address s (any alignment) to the stream (NW = 5: up to 16).
 // One batch of independent loads, then register work, then stores: a single shared-memory round
 // trip per chunk, which is what bounds a lane copying many short runs.  The NW aligned words read
 // cover [s, s+4*NW-4) at any alignment (bytes past the run are read but never used); source
@@ -481,45 +481,42 @@ __device__ __forceinline__ void os_chunk(OutStream& o, uint32_t s, uint32_t n) {
   o.nb = rem;
 }
 
-// append [s, s+len) of shared memory (any alignment), len > 0.  Deliberately real calls (the
-// stream state travels in registers) and a single copy of the chunk code: the kernel's hot code
+// append [s, s+len) of shared memory (any alignment), len > 0.  Deliberately a real call (the
+// stream state travels in registers) around a single copy of the chunk code: the kernel's hot code
 // has to fit the SM's 32 KB instruction cache.
-__device__ __noinline__ OutStream os_chunk9_f(OutStream o, uint32_t s, uint32_t n) {
-  os_chunk<9>(o, s, n);
-  return o;
-}
+//   len <= 16 : one chunk
+//   longer    : a first chunk of 13..16 bytes that word-aligns the source and puts the stream's
+//               first (possibly shared) word out, then 16 bytes per step -- four independent loads,
+//               one funnel shift and one whole-word store each, the pending-byte count constant --
+//               and a last chunk of fewer than 16 bytes.
 __device__ __noinline__ OutStream os_run_f(OutStream o, uint32_t s, uint32_t len) {
-  {  // first chunk: up to the source's next 32-byte-window boundary, which word-aligns the source
-    uint32_t n = 32u - (s & 3u);
-    n = n < len ? n : len;
-    o = os_chunk9_f(o, s, n);
+  uint32_t n = len > 16u ? 16u - (s & 3u) : len;
+#pragma unroll 1
+  while (true) {  // at most two turns; a loop so that the chunk code exists once
+    os_chunk<5>(o, s, n);
     s += n;
     len -= n;
+    if (len >= 16u) {
+      const uint32_t sh = o.nb * 8u;
+      uint32_t prev = sh ? (o.lo << (32u - sh)) : 0u;  // so that funnelshift_l(prev, w, sh) = lo | w << sh
+      uint32_t dp = o.wpos;
+      do {
+        const uint32_t w0 = lds32(s), w1 = lds32(s + 4), w2 = lds32(s + 8), w3 = lds32(s + 12);
+        sts32(dp, __funnelshift_l(prev, w0, sh));
+        sts32(dp + 4, __funnelshift_l(w0, w1, sh));
+        sts32(dp + 8, __funnelshift_l(w1, w2, sh));
+        sts32(dp + 12, __funnelshift_l(w2, w3, sh));
+        prev = w3;
+        s += 16;
+        dp += 16;
+        len -= 16;
+      } while (len >= 16u);
+      o.lo = __funnelshift_l(prev, 0u, sh);
+      o.wpos = dp;
+    }
+    if (len == 0) break;
+    n = len;
   }
-  if (len >= 32u) {  // long run: source is word aligned and the pending-byte count stays constant
-    const uint32_t sh = o.nb * 8u;  // (the first chunk was >= 29 bytes, so the stream's first word is out)
-    uint32_t prev = sh ? (o.lo << (32u - sh)) : 0u;  // so that funnelshift_l(prev, w, sh) = lo | w << sh
-    uint32_t dp = o.wpos;
-    do {
-      const uint32_t w0 = lds32(s), w1 = lds32(s + 4), w2 = lds32(s + 8), w3 = lds32(s + 12);
-      const uint32_t w4 = lds32(s + 16), w5 = lds32(s + 20), w6 = lds32(s + 24), w7 = lds32(s + 28);
-      sts32(dp, __funnelshift_l(prev, w0, sh));
-      sts32(dp + 4, __funnelshift_l(w0, w1, sh));
-      sts32(dp + 8, __funnelshift_l(w1, w2, sh));
-      sts32(dp + 12, __funnelshift_l(w2, w3, sh));
-      sts32(dp + 16, __funnelshift_l(w3, w4, sh));
-      sts32(dp + 20, __funnelshift_l(w4, w5, sh));
-      sts32(dp + 24, __funnelshift_l(w5, w6, sh));
-      sts32(dp + 28, __funnelshift_l(w6, w7, sh));
-      prev = w7;
-      s += 32;
-      dp += 32;
-      len -= 32;
-    } while (len >= 32u);
-    o.lo = __funnelshift_l(prev, 0u, sh);
-    o.wpos = dp;
-  }
-  if (len) o = os_chunk9_f(o, s, len);
   return o;
 }
 __device__ __forceinline__ void os_run(OutStream& o, uint32_t s, uint32_t len) { o = os_run_f(o, s, len); }
