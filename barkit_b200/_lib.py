@@ -94,7 +94,7 @@ SYMBOLS = {
     "bk_extract_device": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(MateIn), C.POINTER(MateIn),
                                     C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.c_void_p, C.c_int, C.POINTER(Result)]),
-    "bk_debug_phases": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bk_debug_events": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bk_reverse_complement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "bk_generate_device": (C.c_int, [C.c_void_p, C.POINTER(SynConfig), C.c_int, C.c_uint64, C.c_uint64,
                                      C.c_uint32, C.c_void_p, C.c_void_p]),

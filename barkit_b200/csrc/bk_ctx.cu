@@ -134,7 +134,12 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
 // [512 B header | tile descriptors, 8 B each | block descriptors (one per 32 tiles), 16 B each | block accumulators, 16 B each]
 size_t block_desc_offset(uint32_t ntiles) { return 512 + (((size_t)ntiles * 8 + 15) & ~size_t(15)); }
 size_t block_acc_offset(uint32_t ntiles) { return block_desc_offset(ntiles) + ((size_t)ntiles / 32 + 1) * 16; }
-size_t scratch_bytes(uint32_t ntiles) { return block_acc_offset(ntiles) + ((size_t)ntiles / 32 + 1) * 16; }
+size_t events_offset(uint32_t ntiles) { return block_acc_offset(ntiles) + ((size_t)ntiles / 32 + 1) * 16; }
+#ifdef BK_PROFILE_PHASES
+size_t scratch_bytes(uint32_t ntiles) { return events_offset(ntiles) + (size_t)ntiles * 128; }  // + event trace
+#else
+size_t scratch_bytes(uint32_t ntiles) { return events_offset(ntiles); }
+#endif
 
 // enqueue: scratch reset + extract kernel.  All pointers are device pointers.
 int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
@@ -174,7 +179,7 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.match[0] = match1; P.match[1] = match2;
   P.tile_counter = (unsigned int*)sc;
   P.result = (bk::DevResult*)(sc + 64);
-  P.prof = (unsigned long long*)(sc + 256);
+  P.prof = (unsigned long long*)(sc + events_offset(lp.ntiles));  // only written by a BK_PROFILE_PHASES build
   P.desc[0] = (unsigned long long*)(sc + 512);
   P.desc[1] = (unsigned long long*)(sc + block_desc_offset(lp.ntiles));
   P.desc[2] = (unsigned long long*)(sc + block_acc_offset(lp.ntiles));
@@ -431,14 +436,20 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
   return check_dev_result(ctx, r);
 }
 
-int bk_debug_phases(bk_ctx* ctx, uint64_t* out24) {
-  if (!ctx || !out24) return BK_E_ARG;
+int bk_debug_events(bk_ctx* ctx, uint32_t ntiles, uint32_t first_tile, uint32_t count, uint64_t* out) {
+  if (!ctx || !out) return BK_E_ARG;
+#ifdef BK_PROFILE_PHASES
   CK(cudaSetDevice(ctx->device));
   Slot& s = ctx->slot[0];
-  if (!s.scratch.buf.p) return BK_E_ARG;
+  if (!s.scratch.buf.p || first_tile + count > ntiles) return BK_E_ARG;
   CK(cudaStreamSynchronize(s.stream));
-  CK(cudaMemcpy(out24, (uint8_t*)s.scratch.buf.p + 256, 24 * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, (uint8_t*)s.scratch.buf.p + events_offset(ntiles) + (size_t)first_tile * 128, (size_t)count * 128,
+                cudaMemcpyDeviceToHost));
   return BK_OK;
+#else
+  ctx->last_error = "library was not built with -DBK_PROFILE_PHASES";
+  return BK_E_ARG;
+#endif
 }
 
 int bk_reverse_complement(bk_ctx* ctx, const uint8_t* seq, size_t n, uint8_t* out) {

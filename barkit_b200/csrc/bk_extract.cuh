@@ -112,16 +112,12 @@ __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned 
 // after a bounded delay; that is what keeps every other tile's look-back from stalling.  Lane i of
 // a front/back warp owns record i of the tile.
 
-// Optional phase timers (compile with -DBK_PROFILE_PHASES): per-role cycle sums, lane 0 only.
+// Optional event trace (compile with -DBK_PROFILE_PHASES; tools/phases.py): one clock64() stamp per
+// tile and pipeline event, all taken on the tile's own SM, so differences between them are valid.
 #ifdef BK_PROFILE_PHASES
-#define PROF_INIT long long p_t = clock64(); long long p_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define PROF(i) { const long long p_n = clock64(); p_acc[i] += p_n - p_t; p_t = p_n; }
-#define PROF_FLUSH(base) \
-  if (lane == 0 && m == 0) for (int p_i = 0; p_i < 8; ++p_i) atomicAdd(&P.prof[(base) + p_i], (unsigned long long)p_acc[p_i]);
+#define EVT(tile, idx) { if (lane == 0) P.prof[(size_t)(tile) * 16 + (idx)] = (unsigned long long)clock64(); }
 #else
-#define PROF_INIT
-#define PROF(i)
-#define PROF_FLUSH(base)
+#define EVT(tile, idx)
 #endif
 
 // named barrier of one mate's back warps (ids 2 and 3; 0 is __syncthreads, 1 the front warps')
@@ -223,19 +219,19 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
 
   if (is_loader) {
     // =============================== LOADER =====================================================
-    PROF_INIT
     for (uint32_t k = 0;; ++k) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
       // slot free on every mate (passes immediately for the first kStages tiles)
 #pragma unroll
       for (int mm = 0; mm < NM; ++mm) mbar_wait(&bar_empty[mm][s], ph ^ 1u);
-      PROF(0)
+#ifdef BK_PROFILE_PHASES
+      const long long t_free = clock64();
+#endif
       // claim with the slot in hand: the load starts at once and the aggregate follows a bounded
       // time later
       uint32_t tile = 0;
       if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
       tile = __shfl_sync(0xffffffffu, tile, 0);
-      PROF(1)
       if (tile >= P.ntiles) {
         // two end markers in consecutive slots: one per scan warp (they take alternate rounds); the
         // first one also stops the back warps
@@ -251,6 +247,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
           }
         break;
       }
+#ifdef BK_PROFILE_PHASES
+      if (lane == 0) P.prof[(size_t)tile * 16 + 0] = (unsigned long long)t_free;
+#endif
+      EVT(tile, 1)
       const uint32_t r0 = tile * R;
       const uint32_t nrec = min(R, P.n - r0);
       uint32_t o[NM], oe[NM];
@@ -285,26 +285,24 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
           }
         }
       }
-      PROF(2)
+      EVT(tile, 2)
     }
-    PROF_FLUSH(0)
   } else if (is_front) {
     // =============================== FRONT ======================================================
     // Two front warps per mate take alternate ring rounds: at one warp per mate the front was 80 % busy,
     // tiles queued behind one another between claim and publication, and every later tile's look-back
     // waited for the slowest of them.
-    PROF_INIT
     for (uint32_t k = fp;; k += kFrontPairs) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
       const uint32_t xb = (k / kFrontPairs) & 1u;  // exchange buffer of this pair's round
       TileMeta& tm = meta[m][s];
       mbar_wait(&bar_full[m][s], ph);  // offsets written, text landed
-      PROF(0)
       const uint32_t tile = tm.tile;
       if (tile == kEndTile || tile == kEndTile2) {  // one end marker per front pair (and per scan warp)
         nbar_arrive(pub_id(s), kPubCount);
         break;
       }
+      if (m == 0) { EVT(tile, 3) }
       const uint32_t r0 = tile * R;
       const uint32_t nrec = tm.nrec;
       const bool active = lane < (int)nrec;
@@ -316,7 +314,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         // ---- parse + match (lane per record) ---------------------------------------------------
         if (active) rv = parse_record(tm.beg[lane], tm.end[lane]);
         __syncwarp();
-        PROF(1)
+        if (m == 0) { EVT(tile, 4) }
         if (active) {
           if (pg.present && rv.qual_len == rv.seq_len) {  // unequal lengths never leave bk_tokenize
             ms = match_read<false>(tab, rv.seq, rv.seq_len);
@@ -328,7 +326,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         atomicOr(&P.result->error, 2u);
       }
       __syncwarp();
-      PROF(2)
+      if (m == 0) { EVT(tile, 5) }
       // ---- exchange match decisions with the other mate's front warp -----------------------------
       int ms_other = -1;
       bool skip = too_big;
@@ -338,7 +336,6 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         ms_other = s_ms[fp][xb][m ^ 1][lane];
         skip = skip || (s_ms[fp][xb][m ^ 1][0] == kSkipTile);
       }
-      PROF(3)
       // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
       const bool keep = !skip && active && (ms >= 0 || ms_other >= 0);
 
@@ -358,6 +355,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
                      : "memory");
         blk_old = atomicAdd(P.desc[2] + 2 * (size_t)(tile >> 5) + m, (1ull << 48) | (unsigned long long)total);
       }
+      EVT(tile, m == 0 ? 6 : 14)
 
       {  // statistics
         const unsigned kb = __ballot_sync(0xffffffffu, keep);
@@ -379,6 +377,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
       if (lane == 0) tm.total = total;
       __syncwarp();
       nbar_arrive(pub_id(s), kPubCount);
+      if (m == 0) { EVT(tile, 7) }
       // whoever completes a block publishes its aggregate (the answer of the atomic is needed only now)
       if (lane == 0) {
         const uint32_t blk = tile >> 5;
@@ -386,43 +385,38 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         if ((uint32_t)(blk_old >> 48) + 1u == in_blk)
           desc_raise(P.desc[1] + 2 * (size_t)blk + m, kFlagAgg | ((blk_old & ((1ull << 48) - 1)) + total));
       }
-      PROF(4)
     }
-    PROF_FLUSH(8)
   } else if (is_scan) {
     // =============================== SCAN =======================================================
     const int sj = warp - NB;
-    PROF_INIT
     for (uint32_t k = sj;; k += kScanWarps) {
       const uint32_t s = k % kStages;
       nbar_sync(pub_id(s), kPubCount);
-      PROF(0)
       const uint32_t tile = meta[0][s].tile;
       if (tile == kEndTile2) break;
       if (tile != kEndTile) {
+        EVT(tile, 8)
         const ulonglong2 g = lookback(P.desc[0], P.desc[1], tile, meta[0][s].total, PAIRED ? meta[NM - 1][s].total : 0u, PAIRED, lane);
         if (lane == 0) {
           meta[0][s].gout = g.x;
           if (PAIRED) meta[NM - 1][s].gout = g.y;
         }
+        EVT(tile, 9)
       }
       __syncwarp();
       nbar_arrive(ready_id(s), kReadyCount);
-      PROF(1)
       if (tile == kEndTile) break;
     }
-    if (sj == 0) { PROF_FLUSH(4) }
   } else {
     // =============================== BACK =======================================================
     uint8_t* const gdst = P.out[m];
-    PROF_INIT
     for (uint32_t k = 0;; ++k) {
       const uint32_t s = k % kStages;
       const TileMeta& tm = meta[m][s];
       nbar_sync(ready_id(s), kReadyCount);
-      PROF(0)
       const uint32_t tile = tm.tile;
       if (tile == kEndTile) break;
+      if (m == 0 && bj == 0) { EVT(tile, 10) }
       const uint32_t total = tm.total;
       const unsigned long long gout = tm.gout;
       if (lane == 0 && bj == 0 && tile == P.ntiles - 1) P.result->out_len[m] = gout + total;
@@ -447,13 +441,16 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         const uint32_t dst = out_s + phase + ooff;
         // lane per record, warp per part: part bj of every kept record through the stream writer
         if (kept) emit_part(pg, rv, ms, trim, dst, bj);
-        PROF(1)
       }
+      __syncwarp();
+      if (m == 0 && bj == 0) { EVT(tile, 11) }
+      if (m == 0 && bj == 3) { EVT(tile, 15) }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[m][s]);  // ring slot (input tile + meta) is free again
       if (fits && total) fence_proxy_async_smem();
       // all shares written -> one warp stores; nobody overwrites the tile until the store has read it
       back_sync(m);
+      if (m == 0 && bj == 0) { EVT(tile, 12) }
       if (fits && total && bj == 0) {
         // ---- store: aligned middle by TMA, ragged edges by the lanes ---------------------------------
         const unsigned long long g0 = gout, g1 = gout + total;
@@ -475,9 +472,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         __syncwarp();
       }
       back_sync(m);
-      PROF(4)
+      if (m == 0 && bj == 0) { EVT(tile, 13) }
     }
-    if (bj == 0) { PROF_FLUSH(16) }
   }
 }
 

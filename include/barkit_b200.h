@@ -157,9 +157,10 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
                       uint8_t* d_out1, uint64_t cap1, uint8_t* d_out2, uint64_t cap2,
                       int32_t* d_match1, int32_t* d_match2, int iters, bk_result* res);
 
-/* Debug: cycle sums per pipeline phase of the last device launch on slot 0 (24 values: front[0..8),
- * scan[8..16), back[16..24)); all zero unless the library was built with -DBK_PROFILE_PHASES. */
-int bk_debug_phases(bk_ctx* ctx, uint64_t* out24);
+/* Debug: the pipeline event trace of the last device launch on slot 0 -- 16 clock64() stamps per tile
+ * (tools/phases.py names them) for tiles [first_tile, first_tile + count) of a launch that had `ntiles`
+ * tiles.  Fails unless the library was built with -DBK_PROFILE_PHASES. */
+int bk_debug_events(bk_ctx* ctx, uint32_t ntiles, uint32_t first_tile, uint32_t count, uint64_t* out);
 
 /* parse::get_reverse_complement (parse.rs:173-179, table parse.rs:12-32) for one sequence, computed on
  * the device with the same complement function the kernel's -r retry uses.  Host buffers. */
