@@ -171,6 +171,7 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   for (int m = 0; m < (ctx->paired ? 2 : 1); ++m) {
     P.text[m] = in[m]->text;
     P.off[m] = in[m]->rec_off;
+    P.text_len[m] = (uint32_t)in[m]->text_len;
     P.in_cap[m] = lp.in_cap[m];
     P.out_cap[m] = lp.out_cap[m];
   }

@@ -283,6 +283,17 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
             mbar_arrive_expect_tx(&bar_full[mm][s], bytes);
             bulk_g2s(in_s, P.text[mm] + gbase, bytes, &bar_full[mm][s]);
           }
+          // Warm L2 for the tile this CTA will most likely claim next (every CTA claims about one tile
+          // per ring round): its record offsets, and its text where that would start if its records are
+          // as long as this tile's.  Claim -> offsets -> load is a chain of three DRAM round trips
+          // that every later tile's look-back waits on; two of them become L2 hits.
+          const uint32_t nt = tile + gridDim.x;
+          if (nt < P.ntiles) {
+            prefetch_l2(P.off[mm] + (size_t)nt * R);
+            prefetch_l2(P.off[mm] + (size_t)nt * R + R);
+            const unsigned long long est = (unsigned long long)gbase + (unsigned long long)gridDim.x * (oe[mm] - o[mm]);
+            if (est + bytes + 256u <= P.text_len[mm]) bulk_prefetch_l2(P.text[mm] + (est & ~15ull), bytes + 256u);
+          }
         }
       }
       EVT(tile, 2)

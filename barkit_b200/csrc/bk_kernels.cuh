@@ -49,6 +49,7 @@ struct KParams {
   uint32_t n;
   uint32_t ntiles;
   uint32_t tile_recs;  // <= 32 (smaller when records are too long for the staging buffer)
+  uint32_t text_len[2];  // bytes of FASTQ text per mate
   uint32_t in_cap[2];  // shared-memory bytes for the staged input / assembled output per mate
   uint32_t out_cap[2];
   uint32_t flags;
@@ -145,6 +146,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, ui
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// L2 prefetch of a byte range (16-byte aligned address and size) / of one line
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 1-D TMA: shared -> global
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_saddr, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_saddr),
