@@ -289,8 +289,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
           // that every later tile's look-back waits on; two of them become L2 hits.
           const uint32_t nt = tile + gridDim.x;
           if (nt < P.ntiles) {
-            prefetch_l2(P.off[mm] + (size_t)nt * R);
-            prefetch_l2(P.off[mm] + (size_t)nt * R + R);
+            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(P.off[mm]) + (((size_t)nt * R * 4u) & ~size_t(15)), ((4u * R + 15u) & ~15u) + 16u);
             const unsigned long long est = (unsigned long long)gbase + (unsigned long long)gridDim.x * (oe[mm] - o[mm]);
             if (est + bytes + 256u <= P.text_len[mm]) bulk_prefetch_l2(P.text[mm] + (est & ~15ull), bytes + 256u);
           }
