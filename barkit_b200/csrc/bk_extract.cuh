@@ -121,12 +121,7 @@ __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned 
 #endif
 
 // named barrier of one mate's back warps (ids 2 and 3; 0 is __syncthreads, 1 the front warps')
-__device__ __forceinline__ void back_sync(int m) {
-  if (m == 0)
-    asm volatile("bar.sync 2, %0;" ::"n"(kBackWarps * 32) : "memory");
-  else
-    asm volatile("bar.sync 3, %0;" ::"n"(kBackWarps * 32) : "memory");
-}
+__device__ __forceinline__ void back_sync(int m, uint32_t nwarps) { nbar_sync(2u + (uint32_t)m, 32u * nwarps); }
 
 // Named barriers (16 per CTA): 0 __syncthreads, 1 the front warps' exchange, 2-3 back_sync, then one
 // per ring slot for fronts -> scan ("aggregates published") and scan -> backs ("offsets known").
@@ -174,9 +169,15 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
   const bool is_front = !is_back && !is_scan && warp < NB + kScanWarps + NM * kFrontPairs;
   const bool is_loader = warp == NB + kScanWarps + NM * kFrontPairs;
   const int fw = warp - NB - kScanWarps;  // front warp index
-  const int m = is_back ? warp % NM : is_front ? fw % NM : 0;  // mate = output stream
+  // Back warps per mate: four each, or five and three when only one mate's reads are rewritten (its
+  // records cost more to assemble than the other mate's verbatim copies).
+  const uint32_t nb0 = !PAIRED ? kBackWarps
+                       : (P.prog[0].present && !P.prog[1].present) ? kBackWarps + 1
+                       : (!P.prog[0].present && P.prog[1].present) ? kBackWarps - 1 : kBackWarps;
+  const int m = is_back ? (warp < (int)nb0 ? 0 : 1) : is_front ? fw % NM : 0;  // mate = output stream
   const int fp = is_front ? fw / NM : 0;  // front pair: which ring rounds this front warp takes
-  const int bj = is_back ? warp / NM : 0;  // back warp index within the mate
+  const int bj = is_back ? (m ? warp - (int)nb0 : warp) : 0;  // back warp index within the mate
+  const uint32_t nparts = m ? NB - nb0 : nb0;                 // back warps of this mate
   constexpr uint32_t kPubCount = 32 * (NM + 1), kReadyCount = 32 * (1 + NB);
   const bk_devprog& pg = P.prog[m];
   const bool trim = !(P.flags & 2u);
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
     if (lane == 0)
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&bar_full[m][s], 1);
-        mbar_init(&bar_empty[m][s], kBackWarps);
+        mbar_init(&bar_empty[m][s], m ? NB - nb0 : nb0);
       }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         const int ms = tm.ms[lane];
         const uint32_t dst = out_s + phase + ooff;
         // lane per record, warp per part: part bj of every kept record through the stream writer
-        if (kept) emit_part(pg, rv, ms, trim, dst, bj);
+        if (kept) emit_part(pg, rv, ms, trim, dst, (uint32_t)bj, nparts);
       }
       __syncwarp();
       if (m == 0 && bj == 0) { EVT(tile, 11) }
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
       if (lane == 0) mbar_arrive(&bar_empty[m][s]);  // ring slot (input tile + meta) is free again
       if (fits && total) fence_proxy_async_smem();
       // all shares written -> one warp stores; nobody overwrites the tile until the store has read it
-      back_sync(m);
+      back_sync(m, nparts);
       if (m == 0 && bj == 0) { EVT(tile, 12) }
       if (fits && total && bj == 0) {
         // ---- store: aligned middle by TMA, ragged edges by the lanes ---------------------------------
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         }
         __syncwarp();
       }
-      back_sync(m);
+      back_sync(m, nparts);
       if (m == 0 && bj == 0) { EVT(tile, 13) }
     }
   }

@@ -550,39 +550,47 @@ __device__ __forceinline__ void os_put(OutStream& o, uint32_t v, uint32_t n) { o
 
 constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is written by warp j
 
-// Part `part` (0..3) of one record's output at shared address d.  The record is
+// Part `part` of `nparts` (3, 4 or 5) of one record's output at shared address d.  The record is
 //   '@' head { " NAME:" seq[cap] ":" qual[cap] }* "\n" seq[..s0) seq[e0..] "\n+\n" qual[..s0) qual[e0..] "\n"
 // (parse.rs:101-113,138-148,161-168; fastq.rs:261) and every field's destination offset is a closed
-// form of head_len, seq_len and the program's constants, so the four parts
-//   0: '@' head + first half of the captures     1: remaining captures + "\n"
-//   2: trimmed seq + "\n+\n"                       3: trimmed qual + "\n"
-// can be produced by four warps independently.  Parts meet at arbitrary byte positions; the words
-// they share are written bytewise by both sides (ragged head / os_end), never as whole words.
-// A record that is copied unchanged and already has the writer's framing (`fast`) is one run, cut
-// into four byte ranges.  Requires qual_len == seq_len for matched records (the front warp treats
-// anything else as unmatched; bk_tokenize never produces it).
+// form of head_len, seq_len and the program's constants, so its five jobs
+//   A: '@' head     B: first half of the captures     C: remaining captures + "\n"
+//   D: trimmed seq + "\n+\n"                           E: trimmed qual + "\n"
+// can be produced by different warps independently: one job each with five parts (the mate whose
+// reads are rewritten, when the other mate has no pattern and lends a warp), A+B | C | D | E with
+// four, A+C | D | E with three (a mate without a pattern: nothing is captured).  Parts meet at
+// arbitrary byte positions; the words they share are written bytewise by both sides, never as
+// whole words.  A record that is copied unchanged and already has the writer's framing (`fast`) is
+// one run, cut into `nparts` byte ranges.  Requires qual_len == seq_len for matched records (the
+// front warp treats anything else as unmatched; bk_tokenize never produces it).
 __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
-                                          int part) {
+                                          uint32_t part, uint32_t nparts) {
   OutStream o;
   if (ms < 0 && r.fast) {
     const uint32_t len = r.end - r.beg;
-    const uint32_t lo = len * part / kEmitParts, hi = len * (part + 1) / kEmitParts;
+    const uint32_t inv = nparts == 4 ? 1024u : nparts == 5 ? 820u : 1366u;  // ceil(4096 / nparts): any monotone cut will do
+    const uint32_t lo = (len * part * inv) >> 12;
+    const uint32_t hi = part + 1u == nparts ? len : (len * (part + 1u) * inv) >> 12;
     if (lo >= hi) return;
     os_begin(o, d + lo);
     os_run(o, r.beg + lo, hi - lo);
     os_end(o);
     return;
   }
+  // jobs of this part, bit 0 = A ... bit 4 = E
+  const uint32_t jobs = nparts == 5 ? 1u << part : nparts == 4 ? (part == 0 ? 3u : 2u << part) : (part == 0 ? 5u : 4u << part);
   const uint32_t ncaps = ms >= 0 ? pg.ncaps : 0u;
   const uint32_t csplit = (ncaps + 1u) >> 1;
   const uint32_t H = r.head_len, L = r.seq_len;
-  if (part < 2) {
+  if (jobs & 7u) {
     // header line: captures [c0, c1) of it belong to this part
-    const uint32_t c0 = part == 0 ? 0u : csplit, c1 = part == 0 ? csplit : ncaps;
+    const uint32_t c0 = (jobs & 2u) ? 0u : csplit, c1 = (jobs & 4u) ? ncaps : (jobs & 2u) ? csplit : c0;
     uint32_t off = 1u + H;
+    if (!(jobs & 3u)) {
 #pragma unroll 1
-    for (uint32_t c = 0; c < c0; ++c) off += 3u + pg.caps[c].name_len + 2u * pg.caps[c].len;
-    if (part == 0) {
+      for (uint32_t c = 0; c < c0; ++c) off += 3u + pg.caps[c].name_len + 2u * pg.caps[c].len;
+    }
+    if (jobs & 1u) {
       os_begin(o, d);
       os_run(o, r.beg, 1u + H);  // '@' + head
     } else {
@@ -599,7 +607,7 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
       os_put(o, (uint32_t)':', 1u);
       if (cap.len) os_copy(o, r.qual + ms + cap.off, cap.len);
     }
-    if (part == 1) os_put(o, (uint32_t)'\n', 1u);
+    if (jobs & 4u) os_put(o, (uint32_t)'\n', 1u);
     os_end(o);
     return;
   }
@@ -608,7 +616,7 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
   const uint32_t cs = cut ? (uint32_t)ms : 0u, ce = cut ? (uint32_t)ms + pg.total_len : 0u;
   const uint32_t kept = L - (ce - cs);
   const uint32_t kSep = (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16);
-  if (part == 2) {
+  if (jobs & 8u) {
     os_begin(o, d + 2u + H + G);
     if (cs) os_run(o, r.seq, cs);
     if (r.fast) {
