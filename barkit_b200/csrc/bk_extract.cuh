@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         o[mm] = lane < (int)nrec ? P.off[mm][r0 + lane] : 0;
         oe[mm] = P.off[mm][r0 + nrec];
       }
-#pragma unroll
+      // (rolled: the loader is not worth 1 KB of the instruction cache)
+#pragma unroll 1
       for (int mm = 0; mm < NM; ++mm) {
         TileMeta& tm = meta[mm][s];
         uint32_t onext = __shfl_down_sync(0xffffffffu, o[mm], 1);

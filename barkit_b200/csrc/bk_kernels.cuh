@@ -226,33 +226,15 @@ __device__ __forceinline__ uint32_t find_nl_head(uint32_t from, uint32_t end) {
   return pos < end ? pos : end;
 }
 
-__device__ __noinline__ RecView parse_record(uint32_t b, uint32_t e) {
+// the general case: any line ends, text after '+', a last line without EOL (rare; kept out of line so that
+// the common path below stays small in the instruction cache)
+__device__ __noinline__ RecView parse_record_slow(uint32_t b, uint32_t e, uint32_t nl1) {
   RecView r;
-  const uint32_t nl1 = find_nl_head(b, e);
   r.beg = b;
   r.end = e;
   r.fast = 0;
   r.head_len = strip_cr(b + 1, nl1 > b ? nl1 : b + 1) - (b + 1);
   const uint32_t sb = nl1 + 1 < e ? nl1 + 1 : e;
-  // Fast path for the common layout `seq LF + LF qual LF`: then e - sb = 2L + 4.  A record of any
-  // other shape (CR line ends, text after '+', missing final LF) cannot pass the three probes
-  // with the L this formula gives (newlines only exist at the three line ends), so it falls
-  // through to the scanning path.
-  {
-    const uint32_t rem = e - sb;
-    if (rem >= 4 && !(rem & 1u)) {
-      const uint32_t L = (rem - 4) >> 1;
-      if (lds8(sb + L) == '\n' && lds8(sb + L + 1) == '+' && lds8(sb + L + 2) == '\n' && lds8(e - 1) == '\n' &&
-          (L == 0 || (lds8(sb + L - 1) != '\r' && lds8(e - 2) != '\r'))) {
-        r.seq = sb;
-        r.seq_len = L;
-        r.qual = sb + L + 3;
-        r.qual_len = L;
-        r.fast = (b + 1 + r.head_len == nl1);  // and no CR on the header line
-        return r;
-      }
-    }
-  }
   const uint32_t nl2 = find_nl(sb, e);
   r.seq = sb;
   r.seq_len = strip_cr(sb, nl2) - sb;
@@ -263,6 +245,37 @@ __device__ __noinline__ RecView parse_record(uint32_t b, uint32_t e) {
   r.qual = qb;
   r.qual_len = strip_cr(qb, nl4) - qb;
   return r;
+}
+
+__device__ __noinline__ RecView parse_record(uint32_t b, uint32_t e) {
+  const uint32_t nl1 = find_nl_head(b, e);
+  const uint32_t sb = nl1 + 1 < e ? nl1 + 1 : e;
+  // Fast path for the writer's own framing `@h LF seq LF + LF qual LF`: then e - sb = 2L + 4.  A record
+  // of any other shape (CR line ends, text after '+', missing final LF) cannot pass the probes with
+  // the L this formula gives (newlines only exist at the line ends), so it takes the scanning path.
+  // All probes are fetched together: one shared-memory round trip, not one per condition.
+  const uint32_t rem = e - sb;
+  const uint32_t L = (rem - 4u) >> 1;
+  if (rem >= 4u && !(rem & 1u) && nl1 > b) {
+    const uint32_t c0 = lds8(sb + L), c1 = lds8(sb + L + 1u), c2 = lds8(sb + L + 2u), c3 = lds8(e - 1u);
+    const uint32_t c4 = lds8(sb + L - 1u), c5 = lds8(e - 2u), c6 = lds8(nl1 - 1u);  // (c4 is the header's LF when L == 0)
+    const bool framed = (c0 == '\n') & (c1 == '+') & (c2 == '\n') & (c3 == '\n');
+    const bool cr = (c4 == '\r') | (c5 == '\r');
+    if (framed && (L == 0 || !cr)) {
+      RecView r;
+      r.beg = b;
+      r.end = e;
+      const bool hcr = nl1 > b + 1u && c6 == '\r';  // CR on the header line: stripped, but then not the writer's framing
+      r.head_len = nl1 - (b + 1u) - (hcr ? 1u : 0u);
+      r.seq = sb;
+      r.seq_len = L;
+      r.qual = sb + L + 3u;
+      r.qual_len = L;
+      r.fast = !hcr;
+      return r;
+    }
+  }
+  return parse_record_slow(b, e, nl1);
 }
 
 // ---- matching --------------------------------------------------------------------------------------
