@@ -260,8 +260,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         o[mm] = lane < (int)nrec ? P.off[mm][r0 + lane] : 0;
         oe[mm] = P.off[mm][r0 + nrec];
       }
-      // (rolled: the loader is not worth 1 KB of the instruction cache)
-#pragma unroll 1
+#pragma unroll
       for (int mm = 0; mm < NM; ++mm) {
         TileMeta& tm = meta[mm][s];
         uint32_t onext = __shfl_down_sync(0xffffffffu, o[mm], 1);
