@@ -58,9 +58,11 @@ __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned 
   int look = (int)blk - 1;
   unsigned long long t = in_blk ? ld_relaxed_u64(tp) : 0ull;
   ulonglong2 d = look - lane >= 0 ? ld_desc(bdesc + 2 * (size_t)(look - lane)) : make_ulonglong2(kFlagPrefix, kFlagPrefix);
-  while (__any_sync(0xffffffffu, in_blk && !tile_ready(t, two))) {
-    __nanosleep(64);  // a predecessor is still being parsed: do not burn issue slots and L2 bandwidth on it
+  // both windows are polled together: whichever is late, the other's round trip is not added to it
+  while (__any_sync(0xffffffffu, (in_blk && !tile_ready(t, two)) || !desc_ready(d, two))) {
+    __nanosleep(32);  // a predecessor is still being parsed: do not burn issue slots and L2 bandwidth on it
     if (in_blk && !tile_ready(t, two)) t = ld_relaxed_u64(tp);
+    if (!desc_ready(d, two)) d = ld_desc(bdesc + 2 * (size_t)(look - lane));
   }
   const uint32_t s0 = __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)t & ~kTileReady : 0u);
   const uint32_t s1 = two ? __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)(t >> 32) & ~kTileReady : 0u) : 0u;
