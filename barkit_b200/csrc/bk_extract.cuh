@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
   __shared__ __align__(16) uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, complement table, program
   __shared__ int s_ms[kFrontPairs][2][2][32];  // [front pair][round parity][mate][lane]
   __shared__ TileMeta meta[NM][kStages];
+  __shared__ uint4 run_desc[NM][32];  // copy descriptors of the tile's runs of unchanged records
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         o[mm] = lane < (int)nrec ? P.off[mm][r0 + lane] : 0;
         oe[mm] = P.off[mm][r0 + nrec];
       }
-#pragma unroll
+#pragma unroll 1  // (rolled: costs ~0.9 k cycles between claim and load, saves 1 KB of the instruction cache)
       for (int mm = 0; mm < NM; ++mm) {
         TileMeta& tm = meta[mm][s];
         uint32_t onext = __shfl_down_sync(0xffffffffu, o[mm], 1);
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
     // Two front warps per mate take alternate ring rounds: at one warp per mate the front was 80 % busy,
     // tiles queued behind one another between claim and publication, and every later tile's look-back
     // waited for the slowest of them.
+    uint32_t n_kept = 0, n_matched = 0;
     for (uint32_t k = fp;; k += kFrontPairs) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
       const uint32_t xb = (k / kFrontPairs) & 1u;  // exchange buffer of this pair's round
@@ -370,14 +372,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
       }
       EVT(tile, m == 0 ? 6 : 14)
 
-      {  // statistics
-        const unsigned kb = __ballot_sync(0xffffffffu, keep);
-        const unsigned mb = __ballot_sync(0xffffffffu, active && ms >= 0);
-        if (lane == 0) {
-          if (m == 0 && kb) atomicAdd(&P.result->n_out, (unsigned long long)__popc(kb));
-          if (mb) atomicAdd(&P.result->n_match[m], (unsigned long long)__popc(mb));
-        }
-      }
+      n_kept += keep;  // statistics: per lane, summed once at the end
+      n_matched += active && ms >= 0;
 
       // ---- hand the slot to the scan and back warps ---------------------------------------------------
       tm.head_len[lane] = rv.head_len;
@@ -397,6 +393,13 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         const uint32_t in_blk = min(32u, P.ntiles - (blk << 5));
         if ((uint32_t)(blk_old >> 48) + 1u == in_blk)
           desc_raise(P.desc[1] + 2 * (size_t)blk + m, kFlagAgg | ((blk_old & ((1ull << 48) - 1)) + total));
+      }
+    }
+    {  // statistics of this warp's tiles
+      const uint32_t nk = __reduce_add_sync(0xffffffffu, n_kept), nm = __reduce_add_sync(0xffffffffu, n_matched);
+      if (lane == 0) {
+        if (m == 0 && nk) atomicAdd(&P.result->n_out, (unsigned long long)nk);
+        if (nm) atomicAdd(&P.result->n_match[m], (unsigned long long)nm);
       }
     }
   } else if (is_scan) {
@@ -452,8 +455,46 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         rv.fast = qf & 1u;
         const int ms = tm.ms[lane];
         const uint32_t dst = out_s + phase + ooff;
-        // lane per record, warp per part: part bj of every kept record through the stream writer
-        if (kept) emit_part(pg, rv, ms, trim, dst, (uint32_t)bj, nparts);
+        // lane per record, warp per part: part bj of every rewritten record (and of a record in foreign
+        // framing: CR line ends, text after '+') through the stream writer
+        const bool unc = kept && rv.fast && ms < 0;
+        if (kept && !unc) emit_part(pg, rv, ms, trim, dst, (uint32_t)bj, nparts);
+        // warp per pass: maximal runs of consecutive unchanged records
+        const unsigned um = __ballot_sync(0xffffffffu, unc);
+        if (um) {
+          // lane i learns its run [i0, i1]; the run's first lane files the copy descriptor (every back
+          // warp of the mate writes the same list) and the runs' ragged ends go to warps 0 and 1
+          const unsigned below = ~um & ((1u << lane) - 1u);
+          const int i0 = unc ? (below ? 32 - __clz(below) : 0) : lane;
+          const unsigned above = ~(um >> lane);  // first zero at or above this lane ends the run
+          const int i1 = unc ? (above ? lane + __ffs(above) - 2 : 31) : lane;
+          const uint32_t run_s = __shfl_sync(0xffffffffu, rv.beg, i0);
+          const uint32_t run_d = __shfl_sync(0xffffffffu, dst, i0);
+          const uint32_t run_n = __shfl_sync(0xffffffffu, rv.end, i1) - run_s;
+          const bool first = unc && i0 == lane;
+          const unsigned starts = __ballot_sync(0xffffffffu, first);
+          if (first) run_desc[m][__popc(starts & ((1u << lane) - 1u))] = bulk_desc(run_s, run_d, run_n, 0u);
+          if (unc && bj < 2) {
+            uint32_t pad = (16u - (run_d & 15u)) & 15u;
+            pad = pad < run_n ? pad : run_n;
+            const uint32_t t0 = ((run_d + run_n) & ~15u) - run_d;
+            const uint32_t tlo = (int32_t)t0 > (int32_t)pad ? t0 : pad;
+            const bool head = bj == 0 && first && pad, tail = bj == 1 && i1 == lane && tlo < run_n;
+            if (head || tail) {
+              OutStream o;
+              os_begin(o, head ? run_d : run_d + tlo);
+              os_run(o, head ? run_s : run_s + tlo, head ? pad : run_n - tlo);
+              os_end(o);
+            }
+          }
+          __syncwarp();
+          const uint32_t nruns = __popc(starts);
+          uint32_t t0 = (uint32_t)bj;  // our first pass of the run; rotates from run to run so that short runs spread
+          for (uint32_t r = 0; r < nruns; ++r) {
+            bulk16(run_desc[m][r], lane, t0, nparts);
+            t0 = t0 == 0 ? nparts - 1u : t0 - 1u;
+          }
+        }
       }
       __syncwarp();
       if (m == 0 && bj == 0) { EVT(tile, 11) }

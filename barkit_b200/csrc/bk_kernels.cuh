@@ -207,23 +207,28 @@ __device__ __forceinline__ uint32_t strip_cr(uint32_t b, uint32_t e) {
   return (e > b && lds8(e - 1) == '\r') ? e - 1 : e;
 }
 
-// find_nl for the header line: the first eight words are fetched in one batch (independent loads, one
-// shared-memory round trip) because a lane walking its header word by word pays the full load
-// latency per word; headers longer than that fall through to the loop.
+// find_nl for the header line, four words per turn (independent loads: one shared-memory round trip
+// per 16 bytes instead of one per word)
 __device__ __forceinline__ uint32_t find_nl_head(uint32_t from, uint32_t end) {
-  const uint32_t p = from & ~3u;
-  uint32_t m[8];
+  uint32_t p = from & ~3u;
+  uint32_t keep = 0xFFFFFFFFu << ((from & 3u) * 8u);
+#pragma unroll 1
+  while (p < end) {
+    uint32_t m[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t w = lds32(p + 4u * i) ^ 0x0A0A0A0Au;
-    m[i] = (w - 0x01010101u) & ~w & 0x80808080u;  // lowest set bit is exact; higher ones may be borrows
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t w = lds32(p + 4u * i) ^ 0x0A0A0A0Au;
+      m[i] = (w - 0x01010101u) & ~w & 0x80808080u;  // lowest set bit is exact; higher ones may be borrows
+    }
+    m[0] &= keep;
+    keep = 0xFFFFFFFFu;
+    uint32_t pos = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 3; i >= 0; --i) pos = m[i] ? p + 4u * i + ((__ffs(m[i]) - 1) >> 3) : pos;
+    if (pos != 0xFFFFFFFFu) return pos < end ? pos : end;
+    p += 16u;
   }
-  m[0] &= 0xFFFFFFFFu << ((from & 3u) * 8u);
-  uint32_t pos = 0xFFFFFFFFu;
-#pragma unroll
-  for (int i = 7; i >= 0; --i) pos = m[i] ? p + 4u * i + ((__ffs(m[i]) - 1) >> 3) : pos;
-  if (pos == 0xFFFFFFFFu) return p + 32u < end ? find_nl(p + 32u, end) : end;
-  return pos < end ? pos : end;
+  return end;
 }
 
 // the general case: any line ends, text after '+', a last line without EOL (rare; kept out of line so that
@@ -561,6 +566,35 @@ __device__ __noinline__ OutStream os_put_f(OutStream o, uint32_t v, uint32_t n) 
 }
 __device__ __forceinline__ void os_put(OutStream& o, uint32_t v, uint32_t n) { o = os_put_f(o, v, n); }
 
+// ---- runs of unchanged records: warp-cooperative copy ------------------------------------------------
+//
+// Consecutive kept records that are copied verbatim (already in the writer's framing) are one
+// contiguous run in the input tile and in the output.  All lanes of a warp copy it together:
+// consecutive lanes own consecutive 16-byte aligned destination chunks, read the two aligned
+// source chunks under them and funnel-shift by the run's relative misalignment, so every access of
+// a pass covers 512 consecutive bytes -- no bank conflicts, a third of the shared-memory wavefronts
+// that lane-per-record copying costs at a 329-byte record stride.  Only chunks completely inside
+// the run are written; its ragged ends (< 16 bytes each) go through the stream writer.
+//   x: first destination chunk (aligned up)   y: end of the last full chunk (aligned down)
+//   z: source - destination                   w: passes of earlier runs of the tile
+__device__ __forceinline__ uint4 bulk_desc(uint32_t s, uint32_t d, uint32_t n, uint32_t w) {
+  return make_uint4((d + 15u) & ~15u, (d + n) & ~15u, s - d, w);
+}
+// descriptor warp-uniform; the warp does passes t0, t0 + tstep, ... of 32 chunks each
+__device__ __forceinline__ void bulk16(const uint4 r, int lane, uint32_t t0, uint32_t tstep) {
+  const uint32_t delta = r.z;
+  const uint32_t off = delta & ~15u, sh = (delta & 3u) * 8u;
+  const bool q1 = (delta & 4u) != 0, q2 = (delta & 8u) != 0;  // word part of the misalignment, warp-uniform
+  for (uint32_t D = r.x + 16u * (32u * t0 + (uint32_t)lane); D < r.y; D += 512u * tstep) {
+    const uint4 x = lds128(D + off), y = lds128(D + off + 16u);
+    const uint32_t a0 = q2 ? x.z : x.x, a1 = q2 ? x.w : x.y, a2 = q2 ? y.x : x.z, a3 = q2 ? y.y : x.w;
+    const uint32_t a4 = q2 ? y.z : y.x, a5 = q2 ? y.w : y.y;
+    const uint32_t b0 = q1 ? a1 : a0, b1 = q1 ? a2 : a1, b2 = q1 ? a3 : a2, b3 = q1 ? a4 : a3, b4 = q1 ? a5 : a4;
+    sts128(D, __funnelshift_r(b0, b1, sh), __funnelshift_r(b1, b2, sh), __funnelshift_r(b2, b3, sh),
+           __funnelshift_r(b3, b4, sh));
+  }
+}
+
 constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is written by warp j
 
 // Part `part` of `nparts` (3, 4 or 5) of one record's output at shared address d.  The record is
@@ -573,23 +607,12 @@ constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is
 // reads are rewritten, when the other mate has no pattern and lends a warp), A+B | C | D | E with
 // four, A+C | D | E with three (a mate without a pattern: nothing is captured).  Parts meet at
 // arbitrary byte positions; the words they share are written bytewise by both sides, never as
-// whole words.  A record that is copied unchanged and already has the writer's framing (`fast`) is
-// one run, cut into `nparts` byte ranges.  Requires qual_len == seq_len for matched records (the
-// front warp treats anything else as unmatched; bk_tokenize never produces it).
+// whole words.  (A record that is copied unchanged and already has the writer's framing is not
+// written here but as part of a run, see bulk16.)  Requires qual_len == seq_len for matched records
+// (the front warp treats anything else as unmatched; bk_tokenize never produces it).
 __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
                                           uint32_t part, uint32_t nparts) {
   OutStream o;
-  if (ms < 0 && r.fast) {
-    const uint32_t len = r.end - r.beg;
-    const uint32_t inv = nparts == 4 ? 1024u : nparts == 5 ? 820u : 1366u;  // ceil(4096 / nparts): any monotone cut will do
-    const uint32_t lo = (len * part * inv) >> 12;
-    const uint32_t hi = part + 1u == nparts ? len : (len * (part + 1u) * inv) >> 12;
-    if (lo >= hi) return;
-    os_begin(o, d + lo);
-    os_run(o, r.beg + lo, hi - lo);
-    os_end(o);
-    return;
-  }
   // jobs of this part, bit 0 = A ... bit 4 = E
   const uint32_t jobs = nparts == 5 ? 1u << part : nparts == 4 ? (part == 0 ? 3u : 2u << part) : (part == 0 ? 5u : 4u << part);
   const uint32_t ncaps = ms >= 0 ? pg.ncaps : 0u;
