@@ -35,7 +35,8 @@ __device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long lon
   asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
 }
 // usable once both halves are there and of the same kind (a half-updated descriptor is simply read again)
-__device__ __forceinline__ bool desc_ready(const ulonglong2& d, bool two) {
+template <bool two>
+__device__ __forceinline__ bool desc_ready(const ulonglong2& d) {
   const unsigned f0 = (unsigned)(d.x >> 62), f1 = (unsigned)(d.y >> 62);
   return f0 != 0 && (!two || (f1 != 0 && (f0 == 2) == (f1 == 2)));
 }
@@ -43,14 +44,16 @@ __device__ __forceinline__ bool desc_ready(const ulonglong2& d, bool two) {
 __device__ __forceinline__ void desc_raise(unsigned long long* p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ bool tile_ready(unsigned long long t, bool two) {
+template <bool two>
+__device__ __forceinline__ bool tile_ready(unsigned long long t) {
   return ((uint32_t)t & kTileReady) && (!two || ((uint32_t)(t >> 32) & kTileReady));
 }
 
 // Exclusive prefixes of tile `tile` on both streams.  The tile's own aggregates (agg0, agg1) have
 // already been published by the front warps.
+template <bool two>
 __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned long long* bdesc, uint32_t tile,
-                                            uint32_t agg0, uint32_t agg1, bool two, int lane) {
+                                            uint32_t agg0, uint32_t agg1, int lane) {
   const uint32_t blk = tile >> 5, j = tile & 31u;
   // window 1: the earlier tiles of this block; window 2: the 32 blocks before it (lane 0 = nearest)
   const bool in_blk = (uint32_t)lane < j;
@@ -59,19 +62,19 @@ __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned 
   unsigned long long t = in_blk ? ld_relaxed_u64(tp) : 0ull;
   ulonglong2 d = look - lane >= 0 ? ld_desc(bdesc + 2 * (size_t)(look - lane)) : make_ulonglong2(kFlagPrefix, kFlagPrefix);
   // both windows are polled together: whichever is late, the other's round trip is not added to it
-  while (__any_sync(0xffffffffu, (in_blk && !tile_ready(t, two)) || !desc_ready(d, two))) {
+  while (__any_sync(0xffffffffu, (in_blk && !tile_ready<two>(t)) || !desc_ready<two>(d))) {
     __nanosleep(32);  // a predecessor is still being parsed: do not burn issue slots and L2 bandwidth on it
-    if (in_blk && !tile_ready(t, two)) t = ld_relaxed_u64(tp);
-    if (!desc_ready(d, two)) d = ld_desc(bdesc + 2 * (size_t)(look - lane));
+    if (in_blk && !tile_ready<two>(t)) t = ld_relaxed_u64(tp);
+    if (!desc_ready<two>(d)) d = ld_desc(bdesc + 2 * (size_t)(look - lane));
   }
   const uint32_t s0 = __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)t & ~kTileReady : 0u);
   const uint32_t s1 = two ? __reduce_add_sync(0xffffffffu, in_blk ? (uint32_t)(t >> 32) & ~kTileReady : 0u) : 0u;
   const bool last = j == 31u;  // this tile completes its block
   unsigned long long e0 = s0, e1 = s1;
   while (true) {  // blocks before 0 read as "prefix 0", so this ends at the latest there
-    while (__any_sync(0xffffffffu, !desc_ready(d, two))) {
+    while (__any_sync(0xffffffffu, !desc_ready<two>(d))) {
       __nanosleep(64);
-      if (!desc_ready(d, two)) d = ld_desc(bdesc + 2 * (size_t)(look - lane));
+      if (!desc_ready<two>(d)) d = ld_desc(bdesc + 2 * (size_t)(look - lane));
     }
     const unsigned pm = __ballot_sync(0xffffffffu, (d.x >> 62) == 2);
     const int first = pm ? __ffs(pm) - 1 : 32;  // nearest block holding inclusive prefixes
@@ -266,13 +269,14 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
 #pragma unroll 1  // (rolled: costs ~0.9 k cycles between claim and load, saves 1 KB of the instruction cache)
       for (int mm = 0; mm < NM; ++mm) {
         TileMeta& tm = meta[mm][s];
-        uint32_t onext = __shfl_down_sync(0xffffffffu, o[mm], 1);
-        if (lane == (int)nrec - 1) onext = oe[mm];
-        const uint32_t gbase = __shfl_sync(0xffffffffu, o[mm], 0) & ~15u;
-        const uint32_t bytes = ((oe[mm] + 15u) & ~15u) - gbase;
+        const uint32_t om = mm ? o[NM - 1] : o[0], oem = mm ? oe[NM - 1] : oe[0];
+        uint32_t onext = __shfl_down_sync(0xffffffffu, om, 1);
+        if (lane == (int)nrec - 1) onext = oem;
+        const uint32_t gbase = __shfl_sync(0xffffffffu, om, 0) & ~15u;
+        const uint32_t bytes = ((oem + 15u) & ~15u) - gbase;
         const bool too_big = bytes > P.in_cap[mm];  // host sized the ring from max_rec_bytes
         const uint32_t in_s = smem_base + (mm ? kStages * P.in_cap[0] : 0) + s * P.in_cap[mm];
-        tm.beg[lane] = in_s + (o[mm] - gbase);
+        tm.beg[lane] = in_s + (om - gbase);
         tm.end[lane] = in_s + (onext - gbase);
         if (lane == 0) {
           tm.tile = tile;
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
           const uint32_t nt = tile + gridDim.x;
           if (nt < P.ntiles) {
             bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(P.off[mm]) + (((size_t)nt * R * 4u) & ~size_t(15)), ((4u * R + 15u) & ~15u) + 16u);
-            const unsigned long long est = (unsigned long long)gbase + (unsigned long long)gridDim.x * (oe[mm] - o[mm]);
+            const unsigned long long est = (unsigned long long)gbase + (unsigned long long)gridDim.x * (oem - om);  // (lane 0: om is the tile's first offset)
             if (est + bytes + 256u <= P.text_len[mm]) bulk_prefetch_l2(P.text[mm] + (est & ~15ull), bytes + 256u);
           }
         }
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
       if (tile == kEndTile2) break;
       if (tile != kEndTile) {
         EVT(tile, 8)
-        const ulonglong2 g = lookback(P.desc[0], P.desc[1], tile, meta[0][s].total, PAIRED ? meta[NM - 1][s].total : 0u, PAIRED, lane);
+        const ulonglong2 g = lookback<PAIRED>(P.desc[0], P.desc[1], tile, meta[0][s].total, PAIRED ? meta[NM - 1][s].total : 0u, lane);
         if (lane == 0) {
           meta[0][s].gout = g.x;
           if (PAIRED) meta[NM - 1][s].gout = g.y;

@@ -647,31 +647,23 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
     os_end(o);
     return;
   }
+  // D and E are the same job on the seq and on the qual line (parse.rs:138-148: cut [s0, e0) out of both)
   const uint32_t G = ms >= 0 ? pg.hdr_growth : 0u;
-  const bool cut = ms >= 0 && trim;  // parse.rs:138-148: cut [s0, e0) out of seq and qual
+  const bool cut = ms >= 0 && trim;
   const uint32_t cs = cut ? (uint32_t)ms : 0u, ce = cut ? (uint32_t)ms + pg.total_len : 0u;
-  const uint32_t kept = L - (ce - cs);
-  const uint32_t kSep = (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16);
-  if (jobs & 8u) {
-    os_begin(o, d + 2u + H + G);
-    if (cs) os_run(o, r.seq, cs);
-    if (r.fast) {
-      os_run(o, r.seq + ce, L - ce + 3u);  // the "\n+\n" after seq travels with the run
-    } else {
-      if (L > ce) os_run(o, r.seq + ce, L - ce);
-      os_put(o, kSep, 3u);
-    }
+  const bool isD = (jobs & 8u) != 0;
+  const uint32_t ll = isD ? L : r.qual_len;  // == L for matched records; an unmatched one is not cut
+  const uint32_t src = isD ? r.seq : r.qual;
+  const uint32_t ps = cs < ll ? cs : ll, pe = ce < ll ? ce : ll;
+  const uint32_t sep = isD ? (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16) : (uint32_t)'\n';
+  const uint32_t nsep = isD ? 3u : 1u;
+  os_begin(o, d + 2u + H + G + (isD ? 0u : L - (ce - cs) + 3u));
+  if (ps) os_run(o, src, ps);
+  if (r.fast) {
+    os_run(o, src + pe, ll - pe + nsep);  // the line end ("\n+\n" after seq, "\n" after qual) travels with the run
   } else {
-    os_begin(o, d + 2u + H + G + kept + 3u);
-    const uint32_t ql = r.qual_len;  // == L for matched records; an unmatched one is not cut
-    const uint32_t qs = cs < ql ? cs : ql, qe = ce < ql ? ce : ql;
-    if (qs) os_run(o, r.qual, qs);
-    if (r.fast) {
-      os_run(o, r.qual + qe, ql - qe + 1u);  // with its "\n"
-    } else {
-      if (ql > qe) os_run(o, r.qual + qe, ql - qe);
-      os_put(o, (uint32_t)'\n', 1u);
-    }
+    if (ll > pe) os_run(o, src + pe, ll - pe);
+    os_put(o, sep, nsep);
   }
   os_end(o);
 }
