@@ -102,7 +102,15 @@ size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_
   return total;
 }
 
-template <bool PAIRED>
+// extract_kernel<PAIRED, GENERAL>: GENERAL iff a pattern needs a search (not anchored) or -r is set
+bool needs_general(const bk_ctx* ctx) {
+  if (ctx->flags & BK_FLAG_RC) return true;
+  for (int m = 0; m < 2; ++m)
+    if (ctx->prog[m].present && !ctx->prog[m].anchor_start && !ctx->prog[m].anchor_end) return true;
+  return false;
+}
+
+template <bool PAIRED, bool GENERAL>
 int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
   uint32_t R = bk::kTileRecs;
   // prefer several resident tiles per SM; never go below 8 records unless a tile would not fit
@@ -115,12 +123,12 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   lp->tile_recs = R;
   lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap);
   lp->ntiles = (n + R - 1) / R;
-  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)lp->smem));
-  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED>, bk::cta_warps(PAIRED) * 32, lp->smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL>, bk::cta_warps(PAIRED) * 32, lp->smem));
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
@@ -157,7 +165,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     maxrec[m] = in[m]->max_rec_bytes;
   }
   LaunchPlan lp;
-  int rc = ctx->paired ? plan_launch<true>(ctx, n, maxrec, &lp) : plan_launch<false>(ctx, n, maxrec, &lp);
+  const bool general = needs_general(ctx);
+  int rc = ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))
+                       : (general ? plan_launch<false, true>(ctx, n, maxrec, &lp) : plan_launch<false, false>(ctx, n, maxrec, &lp));
   if (rc != BK_OK) return rc;
   rc = ensure(ctx, &s->scratch.buf, scratch_bytes(lp.ntiles));
   if (rc != BK_OK) return rc;
@@ -189,10 +199,14 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.tile_recs = lp.tile_recs;
   P.flags = ctx->flags;
   if (n > 0) {
-    if (ctx->paired)
-      bk::extract_kernel<true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
+    if (ctx->paired && general)
+      bk::extract_kernel<true, true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
+    else if (ctx->paired)
+      bk::extract_kernel<true, false><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
+    else if (general)
+      bk::extract_kernel<false, true><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
     else
-      bk::extract_kernel<false><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
+      bk::extract_kernel<false, false><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
     CK(cudaGetLastError());
     if (launches) *launches += 1;
   }

@@ -156,7 +156,10 @@ struct TileMeta {  // hand-over between the roles, one per (mate, stage); SoA so
 constexpr int kFrontPairs = 2;  // front warps per mate: warp p takes the ring rounds k with k % 2 == p
 constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + kBackWarps) + kScanWarps + 1; }
 
-template <bool PAIRED>
+// GENERAL = false: every pattern is anchored and there is no reverse-complement retry -- the common
+// case, compiled without the search code, because every kilobyte of this kernel competes for the
+// SM's instruction cache.
+template <bool PAIRED, bool GENERAL>
 __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
@@ -334,13 +337,14 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         if (active) rv = parse_record(tm.beg[lane], tm.end[lane]);
         __syncwarp();
         if (m == 0) { EVT(tile, 4) }
-        if (active) {
-          if (pg.present && rv.qual_len == rv.seq_len) {  // unequal lengths never leave bk_tokenize
-            ms = match_read<false>(tab, rv.seq, rv.seq_len);
-            if (ms < 0 && rc) ms = match_read<true>(tab, rv.seq, rv.seq_len);  // parse.rs:61-66
-          }
-          if (P.match[m]) P.match[m][r0 + lane] = ms;
+        const bool can = active && pg.present && rv.qual_len == rv.seq_len;  // unequal lengths never leave bk_tokenize
+        if (GENERAL && pg.present && !pg.anchor_start && !pg.anchor_end) {
+          ms = match_unanchored(tab, rv.seq, rv.seq_len, can, lane);  // warp per read
+        } else if (can) {
+          ms = match_read<false>(tab, rv.seq, rv.seq_len);  // lane per read
         }
+        if (GENERAL && can && ms < 0 && rc) ms = match_read<true>(tab, rv.seq, rv.seq_len);  // parse.rs:61-66
+        if (active && P.match[m]) P.match[m][r0 + lane] = ms;
       } else if (lane == 0) {
         atomicOr(&P.result->error, 2u);
       }

@@ -406,7 +406,8 @@ __device__ __forceinline__ bool match_at(uint32_t tab, uint32_t seq, uint32_t L,
   return ok;
 }
 
-// leftmost match start or -1
+// leftmost match start or -1, one lane per read.  Forward strand:
+// anchored patterns only (one candidate start); the unanchored forward search is match_unanchored.
 template <bool RC>
 __device__ __noinline__ int match_read(uint32_t tab, uint32_t seq, uint32_t L) {
   const uint4 h = lds128(tab + kTabHdr);  // nops, total_len, anchor_start, anchor_end
@@ -417,9 +418,73 @@ __device__ __noinline__ int match_read(uint32_t tab, uint32_t seq, uint32_t L) {
     const uint32_t s = h.w ? L - T : 0;
     return match_at<RC, false>(tab, seq, L, s) ? (int)s : -1;
   }
-  for (uint32_t s = 0; s <= L - T; ++s)
-    if (match_at<RC, true>(tab, seq, L, s)) return (int)s;
+  if (RC) {  // (reverse-complement retry of an unanchored pattern: rare, one lane per read)
+    for (uint32_t s = 0; s <= L - T; ++s)
+      if (match_at<RC, true>(tab, seq, L, s)) return (int)s;
+  }
   return -1;
+}
+
+// Unanchored forward search, one warp per read: the 32 lanes test 32 consecutive candidate starts
+// at once and a ballot + find-first-set picks the smallest start at which every run passes, which
+// is the regex crate's leftmost-first match (pattern.rs:225-230).  Lane-per-read scanning made the
+// whole warp wait for its unluckiest read (a read without a match walks all its starts).  Called by
+// all lanes together; `can` = this lane's read takes part; returns this lane's read's result.
+__device__ __noinline__ int match_unanchored(uint32_t tab, uint32_t seq, uint32_t L, bool can, int lane) {
+  const uint32_t T = lds32(tab + kTabHdr + 4u);
+  // The program's first run is its most selective one (bk_pattern.cc puts literals first).  When it
+  // is a literal of up to 8 bytes it is kept in registers and the warp-per-read sweep tests only
+  // it -- three loads and a dozen ALU operations per candidate start.  The candidates found (one per
+  // read) are then verified against the whole program one lane per read, all reads at once; a
+  // read whose candidate fails resumes its sweep behind it.
+  const MOp op0 = tab_op(tab, 0);
+  const bool filt = op0.kind == BK_OP_LIT && op0.len <= 8u;
+  const uint32_t lit0 = lds32(tab + kTabLit + op0.idx), lit1 = lds32(tab + kTabLit + op0.idx + 4u);
+  const uint32_t m0 = op0.len >= 4u ? 0xFFFFFFFFu : (1u << (8u * op0.len)) - 1u;
+  const uint32_t m1 = op0.len <= 4u ? 0u : op0.len >= 8u ? 0xFFFFFFFFu : (1u << (8u * (op0.len - 4u))) - 1u;
+  int ms = -1;
+  uint32_t from = 0;
+  bool pend = can && L >= T;
+  for (unsigned todo = __ballot_sync(0xffffffffu, pend); todo; todo = __ballot_sync(0xffffffffu, pend)) {
+    int cand = -1;
+    for (; todo; todo &= todo - 1u) {
+      const int r = __ffs(todo) - 1;
+      const uint32_t rseq = __shfl_sync(0xffffffffu, seq, r), last = __shfl_sync(0xffffffffu, L, r) - T;
+      int found = -1;
+      for (uint32_t s0 = __shfl_sync(0xffffffffu, from, r); s0 <= last; s0 += 32u) {
+        const uint32_t s = s0 + (uint32_t)lane;
+        bool ok = s <= last;
+        if (filt) {
+          const uint32_t base = rseq + s + op0.off, p = base & ~3u, sh = (base & 3u) * 8u;
+          const uint32_t w0 = lds32(p), w1 = lds32(p + 4u), w2 = lds32(p + 8u);
+          const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+          const uint32_t x0 = (v0 ^ lit0) & m0, x1 = (v1 ^ lit1) & m1;
+          const uint32_t z0 = (((x0 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x0) & 0x80808080u;  // 0x80 per differing byte
+          const uint32_t z1 = (((x1 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x1) & 0x80808080u;
+          ok = ok && (uint32_t)(__popc(z0) + __popc(z1)) <= op0.k && !((z0 & v0) | (z1 & v1));
+        } else if (ok) {
+          ok = match_at<false, true>(tab, rseq, 0u, s);
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, ok);
+        if (hit) {
+          found = (int)s0 + __ffs(hit) - 1;
+          break;
+        }
+      }
+      if (lane == r) cand = found;
+    }
+    if (pend) {
+      if (cand < 0) {
+        pend = false;
+      } else if (!filt || match_at<false, false>(tab, seq, 0u, (uint32_t)cand)) {
+        ms = cand;
+        pend = false;
+      } else {
+        from = (uint32_t)cand + 1u;
+      }
+    }
+  }
+  return ms;
 }
 
 // ---- emit ----------------------------------------------------------------------------------------------

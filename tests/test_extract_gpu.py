@@ -164,6 +164,33 @@ def test_ragged_paired_end(seed):
         assert o1 == e1 and o2 == e2, (p1, p2, k)
 
 
+@pytest.mark.parametrize("period", [1, 2, 3, 5, 31, 32, 33, 1000])
+def test_runs_of_unchanged_records(period):
+    """Mate 2 is copied verbatim in runs of consecutive kept pairs (warp-cooperative copy); which pairs
+    are kept is decided by mate 1.  Every run length / position inside a tile, tiles with no run at all,
+    and record lengths that move the runs' ragged ends over all 16 alignments."""
+    rnd = random.Random(period)
+    recs1, recs2 = [], []
+    for i in range(700):
+        hit = (i % period) != (period // 2) if period > 1 else True
+        if period == 1000:
+            hit = i in (0, 31, 32, 63, 699)
+        L = rnd.randint(20, 60)
+        seq1 = (b"ACGTAC" if hit else b"TTTTTT") + bytes(rnd.choice(b"ACGT") for _ in range(L))
+        seq2 = bytes(rnd.choice(b"ACGTN") for _ in range(rnd.randint(1, 70)))
+        h = b"r%d" % i
+        recs1.append(b"@" + h + b" 1\n" + seq1 + b"\n+\n" + _qual(len(seq1)) + b"\n")
+        recs2.append(b"@" + h + b" 2\n" + seq2 + b"\n+\n" + _qual(len(seq2)) + b"\n")
+    fq1, fq2 = b"".join(recs1), b"".join(recs2)
+    p1 = "^(?P<UMI>ACGTAC)"
+    o1, o2, res = run_pe(fq1, fq2, p1, None, 0)
+    e1, e2 = bo.extract_pe(fq1, fq2, p1, None, 0)
+    assert o1 == e1 and o2 == e2
+    # and with the roles of the mates swapped (pattern on mate 2: five back warps there, three here)
+    o2, o1, res = run_pe(fq2, fq1, None, p1, 0)
+    assert o1 == e1 and o2 == e2
+
+
 def test_empty_and_tiny_inputs():
     ctx = make_ctx("^(?P<UMI>[ATGCN]{4})")
     out, res = ctx.extract_text(b"")

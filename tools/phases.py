@@ -8,9 +8,13 @@ from barkit_b200 import _lib
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 4000000
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 30          # records per tile the launch plan picks (BK_DEBUG=1 prints it)
-prog = _lib.Program("^(?P<CB>[ATGCN]{16})atgccat(?P<UMI>[ATGCN]{12})", 1)
-ctx = _lib.Context(prog, None, paired=True)
-cfg = _lib.syn_config(150, plant1=(b"ATGCCAT", 16, 0)); rl = 329
+NAME = sys.argv[3] if len(sys.argv) > 3 else "C3"          # BASELINE.json config
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+from tests.util import CONFIG_PATTERNS, lib_syn_config
+p1, p2, _paired = CONFIG_PATTERNS[NAME]
+assert _paired, "the trace is wired for paired-end launches"
+ctx = _lib.Context(_lib.Program(p1, K) if p1 else None, _lib.Program(p2, K) if p2 else None, paired=True)
+cfg = lib_syn_config(NAME); rl = 329
 ms = []
 for mate in (1, 2):
     dt = ctx.dev_alloc(P * rl + 64); do = ctx.dev_alloc((P + 1) * 4)
