@@ -94,6 +94,8 @@ SYMBOLS = {
     "bk_extract_device": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(MateIn), C.POINTER(MateIn),
                                     C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.c_void_p, C.c_int, C.POINTER(Result)]),
+    "bk_tokenize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, u32p,
+                                     C.POINTER(C.c_uint64), u32p]),
     "bk_debug_events": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bk_reverse_complement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "bk_generate_device": (C.c_int, [C.c_void_p, C.POINTER(SynConfig), C.c_int, C.c_uint64, C.c_uint64,
@@ -289,6 +291,23 @@ class Context:
         if nbytes:
             self._check(lib.bk_memcpy_d2h(self.handle, out.ctypes.data, dptr, nbytes))
         return out
+
+    def tokenize_device(self, text: bytes, final: bool = True, cap_records: int | None = None):
+        """bk_tokenize_device on a host string (uploaded first): -> (rc, rec_off uint32[n+1], consumed, max_rec_bytes)"""
+        arr = np.zeros(len(text) + 64, np.uint8)
+        arr[:len(text)] = np.frombuffer(text, np.uint8)
+        if cap_records is None:
+            cap_records = int(np.count_nonzero(arr == 10)) // 4 + 2
+        d_text = self.dev_alloc(arr.size)
+        d_off = self.dev_alloc((cap_records + 1) * 4)
+        self.h2d(d_text, arr)
+        n, consumed, maxrec = C.c_uint32(0), C.c_uint64(0), C.c_uint32(0)
+        rc = lib.bk_tokenize_device(self.handle, d_text, len(text), 1 if final else 0, d_off, cap_records,
+                                    C.byref(n), C.byref(consumed), C.byref(maxrec))
+        off = self.d2h(d_off, (n.value + 1) * 4, np.uint32)
+        self.dev_free(d_text)
+        self.dev_free(d_off)
+        return rc, off, consumed.value, maxrec.value
 
     def generate_device(self, cfg: SynConfig, mate: int, seed: int, first_idx: int, n: int,
                         d_text: int, d_off: int):

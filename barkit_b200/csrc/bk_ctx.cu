@@ -16,6 +16,7 @@
 #include "../../include/barkit_b200.h"
 #include "bk_internal.h"
 #include "bk_extract.cuh"
+#include "bk_tokenize.cuh"
 
 namespace {
 
@@ -54,6 +55,7 @@ struct bk_ctx {
   bk_devprog prog[2];
   int sm_count = 0;
   Slot slot[kSlots];
+  DevBuf tok;  // bk_tokenize_device scratch: block counts + TokResult
   std::string last_error;
 };
 
@@ -307,6 +309,7 @@ void bk_ctx_destroy(bk_ctx* ctx) {
     if (s.ev1) cudaEventDestroy(s.ev1);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  if (ctx->tok.p) cudaFree(ctx->tok.p);
   delete ctx;
 }
 
@@ -465,6 +468,95 @@ int bk_debug_events(bk_ctx* ctx, uint32_t ntiles, uint32_t first_tile, uint32_t 
   ctx->last_error = "library was not built with -DBK_PROFILE_PHASES";
   return BK_E_ARG;
 #endif
+}
+
+int bk_tokenize_device(bk_ctx* ctx, const uint8_t* d_text, uint64_t len, int final_chunk, uint32_t* d_rec_off,
+                       uint32_t cap_records, uint32_t* n_out, uint64_t* consumed, uint32_t* max_rec_bytes) {
+  if (!ctx || !d_rec_off || !n_out || (len && !d_text)) return BK_E_ARG;
+  if (((uintptr_t)d_text & 15) != 0) { ctx->last_error = "batch text must be 16-byte aligned"; return BK_E_ARG; }
+  if (len >= (1ull << 32) - 1) { ctx->last_error = "batch text must be < 4 GiB"; return BK_E_CAPACITY; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->slot[0].stream;
+  *n_out = 0;
+  if (consumed) *consumed = 0;
+  if (max_rec_bytes) *max_rec_bytes = 0;
+  CK(cudaMemsetAsync(d_rec_off, 0, 4, st));
+  // Blank lines after the last record of the input are accepted and dropped (as bk_tokenize does): the
+  // scan ends behind the first newline of the text's trailing run of line ends.
+  uint64_t eff = len;
+  if (final_chunk && len) {
+    uint8_t tail[4096];
+    const uint64_t tn = len < sizeof tail ? len : sizeof tail;
+    CK(cudaMemcpyAsync(tail, d_text + (len - tn), tn, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t k = tn;
+    while (k > 0 && (tail[k - 1] == '\n' || tail[k - 1] == '\r')) --k;
+    if (k == 0 && tn == len) {  // nothing but line ends
+      if (consumed) *consumed = len;
+      return BK_OK;
+    }
+    if (k > 0) {  // (a longer run than the window: leave it to the format check)
+      uint64_t j = k;
+      while (j < tn && tail[j] != '\n') ++j;
+      eff = len - tn + (j < tn ? j + 1 : tn);
+    }
+  }
+  if (eff == 0) return BK_OK;
+  const uint32_t nblocks = (uint32_t)((eff + bk::kTokChunk - 1) / bk::kTokChunk);
+  int rc = ensure(ctx, &ctx->tok, (size_t)nblocks * 4 + 64);
+  if (rc != BK_OK) return rc;
+  uint32_t* counts = (uint32_t*)((uint8_t*)ctx->tok.p + 64);
+  bk::TokResult* d_res = (bk::TokResult*)ctx->tok.p;
+  bk::tok_count_kernel<<<nblocks, bk::kTokThreads, 0, st>>>(d_text, eff, counts);
+  bk::tok_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, d_res);
+  bk::tok_emit_kernel<<<nblocks, bk::kTokThreads, 0, st>>>(d_text, eff, counts, d_rec_off, cap_records);
+  CK(cudaGetLastError());
+  bk::TokResult r;
+  CK(cudaMemcpyAsync(&r, d_res, sizeof r, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  uint64_t n = r.newlines / 4;
+  bool truncated = false;  // bytes behind the last complete record that do not make up a record
+  uint32_t last_end = 0;
+  bool have_last_end = false;
+  if (n < cap_records) {
+    uint32_t after = 0;  // end of the last record that ends with a newline
+    CK(cudaMemcpyAsync(&after, d_rec_off + n, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (after < eff) {
+      if (final_chunk && r.newlines % 4 == 3) {  // the final record's quality line has no EOL
+        ++n;
+        last_end = (uint32_t)eff;
+        have_last_end = true;
+        CK(cudaMemcpyAsync(d_rec_off + n, &last_end, 4, cudaMemcpyHostToDevice, st));
+      } else if (final_chunk) {
+        truncated = true;
+      }
+    }
+  } else {
+    n = cap_records;
+  }
+  if (!have_last_end) {
+    CK(cudaMemcpyAsync(&last_end, d_rec_off + n, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  if (n) {
+    bk::tok_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_text, d_rec_off, (uint32_t)n, last_end, d_res);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&r, d_res, sizeof r, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  rc = truncated ? BK_E_FORMAT : BK_OK;
+  if (n && r.first_bad < n) {  // records before the first malformed one stand, as with bk_tokenize
+    n = r.first_bad;
+    CK(cudaMemcpyAsync(&last_end, d_rec_off + n, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    rc = BK_E_FORMAT;
+  }
+  if (rc == BK_E_FORMAT) ctx->last_error = "malformed FASTQ text";
+  *n_out = (uint32_t)n;
+  if (consumed) *consumed = (rc == BK_OK && final_chunk && eff != len && last_end == eff) ? len : last_end;
+  if (max_rec_bytes) *max_rec_bytes = n ? r.max_rec_bytes : 0;
+  return rc;
 }
 
 int bk_reverse_complement(bk_ctx* ctx, const uint8_t* seq, size_t n, uint8_t* out) {

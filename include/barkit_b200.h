@@ -162,6 +162,14 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
  * tiles.  Fails unless the library was built with -DBK_PROFILE_PHASES. */
 int bk_debug_events(bk_ctx* ctx, uint32_t ntiles, uint32_t first_tile, uint32_t count, uint64_t* out);
 
+/* bk_tokenize on the device: the same contract for text that is already in
+ * device memory (16-byte aligned, >= 16 bytes of slack behind `len`, < 4 GiB), rec_off in device
+ * memory with cap_records + 1 entries.  Lets a caller ship raw FASTQ text and skip the host scan.
+ * Differences from bk_tokenize, all in error cases only: after BK_E_FORMAT, max_rec_bytes covers the
+ * whole scan, not just the records before the malformed one. */
+int bk_tokenize_device(bk_ctx* ctx, const uint8_t* d_text, uint64_t len, int final_chunk, uint32_t* d_rec_off,
+                       uint32_t cap_records, uint32_t* n_out, uint64_t* consumed, uint32_t* max_rec_bytes);
+
 /* parse::get_reverse_complement (parse.rs:173-179, table parse.rs:12-32) for one sequence, computed on
  * the device with the same complement function the kernel's -r retry uses.  Host buffers. */
 int bk_reverse_complement(bk_ctx* ctx, const uint8_t* seq, size_t n, uint8_t* out);
