@@ -373,7 +373,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_step": alg_bytes / args.steps,
-                         "kernel": "bk::extract_kernel<true> (1 launch per step)"},
+                         "kernel": "bk::extract_kernel<PAIRED=true, GENERAL=false> (1 launch per step)"},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches,

@@ -43,8 +43,8 @@ with open(os.path.join(prof, tag + "_summary.md"), "w") as f:
     for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
         f.write("- `%s`: %d launches, mean %.3f ms, share of captured GPU time %.1f%%\n" % (k, len(v), sum(v) / len(v), 100 * sum(v) / tot))
     f.write("\nThe bksyn-v1 generator launches are bench set-up (outside the timed region); inside the timed region the only kernel is "
-            "`extract_kernel<true>` (one launch per step, plus one cudaMemsetAsync of the look-back scratch).\n\n")
-    f.write("Full capture of one `extract_kernel<true>` launch (%d pairs, `ncu --set full --clock-control none`; file %s_extract_kernel_full_raw.csv):\n\n" % (pairs, tag))
+            "`extract_kernel<true, false>` (paired, anchored patterns) (one launch per step, plus one cudaMemsetAsync of the look-back scratch).\n\n")
+    f.write("Full capture of one `extract_kernel<true, false>` (paired, anchored patterns) launch (%d pairs, `ncu --set full --clock-control none`; file %s_extract_kernel_full_raw.csv):\n\n" % (pairs, tag))
     for k in keys:
         if k in m: f.write("- %s = %s %s\n" % (k, m[k][0], m[k][1]))
     f.write("\nDRAM traffic per launch = %.3f GB read + %.3f GB written = %.3f GB (%.1f B/pair).\n" % (rd / 1e9, wr / 1e9, (rd + wr) / 1e9, (rd + wr) / pairs))
