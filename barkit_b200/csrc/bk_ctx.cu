@@ -166,6 +166,10 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     if (in[m]->max_rec_bytes == 0) { ctx->last_error = "max_rec_bytes must be set"; return BK_E_ARG; }
     maxrec[m] = in[m]->max_rec_bytes;
   }
+  if (((uintptr_t)out1 & 15) != 0 || ((uintptr_t)out2 & 15) != 0) {  // the tile stores are 16-byte bulk copies
+    ctx->last_error = "output buffers must be 16-byte aligned";
+    return BK_E_ARG;
+  }
   LaunchPlan lp;
   const bool general = needs_general(ctx);
   int rc = ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))

@@ -152,7 +152,8 @@ int bk_memcpy_d2h(bk_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 /* Same map as bk_extract_host on device pointers (bk_mate_in fields are device pointers).
  * `d_match1/2` (nullable, n int32 each) receive the match start of every read or -1: the
  * BarcodeRegex::get_captures decision (pattern.rs:225-230) made visible for tests.
- * `iters` >= 1 repeats the launch; res->kernel_ms is the mean over iters. */
+ * `iters` >= 1 repeats the launch; res->kernel_ms is the mean over iters.  Text and output pointers
+ * must be 16-byte aligned (the tiles move as 16-byte bulk copies); anything from bk_dev_alloc is. */
 int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk_mate_in* d_in2,
                       uint8_t* d_out1, uint64_t cap1, uint8_t* d_out2, uint64_t cap2,
                       int32_t* d_match1, int32_t* d_match2, int iters, bk_result* res);
