@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbarkit_b200.so")
+LIB_PATH = os.environ.get("BK_LIB") or os.path.join(_HERE, "libbarkit_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

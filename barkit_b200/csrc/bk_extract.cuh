@@ -154,6 +154,10 @@ struct TileMeta {  // hand-over between the roles, one per (mate, stage); SoA so
 };
 
 constexpr int kFrontPairs = 2;  // front warps per mate: warp p takes the ring rounds k with k % 2 == p
+// A ring slot's barriers must always meet the same scan warp and front pair.  With an odd ring depth
+// round k and round k + kStages share their barrier ids but belong to different scan warps, and the
+// one running ahead completes the other's barrier generation (observed: a 3-deep ring hangs).
+static_assert(kStages % kScanWarps == 0 && kStages % kFrontPairs == 0, "ring depth must be a multiple of the scan / front warp counts");
 constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + kBackWarps) + kScanWarps + 1; }
 
 // GENERAL = false: every pattern is anchored and there is no reverse-complement retry -- the common
