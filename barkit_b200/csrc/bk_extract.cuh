@@ -470,7 +470,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         // lane per record, warp per part: part bj of every rewritten record (and of a record in foreign
         // framing: CR line ends, text after '+') through the stream writer
         const bool unc = kept && rv.fast && ms < 0;
-        if (kept && !unc) emit_part(pg, rv, ms, trim, dst, (uint32_t)bj, nparts);
+        // (staggered long runs when the output records of the tile sit a multiple of 32 bytes apart)
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, ooff, 1);
+        const bool even = kept && lane < 31 && nxt != kNotKept && ((nxt - ooff) & 31u) == 0;
+        const uint32_t rot = __popc(__ballot_sync(0xffffffffu, even)) >= 8 ? ((uint32_t)lane & 7u) + 1u : 0u;
+        if (kept && !unc) emit_part(pg, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
         // warp per pass: maximal runs of consecutive unchanged records
         const unsigned um = __ballot_sync(0xffffffffu, unc);
         if (um) {

@@ -512,12 +512,14 @@ struct OutStream {
   uint32_t lo;    // its bytes so far: low `nb` bytes meaningful (the first `skip` are placeholders), rest zero
   uint32_t nb;    // 0..3
   uint32_t skip;  // leading bytes of the word at wpos that belong to another writer (first word only)
+  uint32_t rot;   // 0, or 1 + the 16-byte step at which this lane starts a long run (see os_run_f)
 };
 
 __device__ __forceinline__ void os_begin(OutStream& o, uint32_t d) {
   o.wpos = d & ~3u;
   o.nb = o.skip = d & 3u;
   o.lo = 0;
+  o.rot = 0;
 }
 
 // store the completed word v at o.wpos if `en`; the stream's first word is stored without its skipped bytes
@@ -585,7 +587,7 @@ __device__ __noinline__ OutStream os_run_f(OutStream o, uint32_t s, uint32_t len
     os_chunk<5>(o, s, n);
     s += n;
     len -= n;
-    if (len >= 16u) {
+    if (len >= 16u && o.rot == 0) {
       const uint32_t sh = o.nb * 8u;
       uint32_t prev = sh ? (o.lo << (32u - sh)) : 0u;  // so that funnelshift_l(prev, w, sh) = lo | w << sh
       uint32_t dp = o.wpos;
@@ -602,6 +604,28 @@ __device__ __noinline__ OutStream os_run_f(OutStream o, uint32_t s, uint32_t len
       } while (len >= 16u);
       o.lo = __funnelshift_l(prev, 0u, sh);
       o.wpos = dp;
+    } else if (len >= 16u) {
+      // The same steps, each reading the source word before it instead of carrying it over, so that
+      // they can be taken in any order -- and every lane starts at a different one.  When all
+      // records of a tile have the same length and that length is a multiple of 32 bytes, lanes
+      // working at the same step hit the same shared-memory bank 8 to 32 ways (BASELINE config C2
+      // on fixed-length reads); staggered starts spread them over the banks.
+      const uint32_t nsteps = len >> 4, sh = o.nb * 8u, dp = o.wpos;
+      uint32_t q = o.rot - 1u < nsteps ? o.rot - 1u : 0u;
+#pragma unroll 1
+      for (uint32_t it = 0; it < nsteps; ++it) {
+        const uint32_t a = s + 16u * q, b = dp + 16u * q;
+        const uint32_t wm = lds32(a - 4), w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8), w3 = lds32(a + 12);
+        sts32(b, __funnelshift_l(wm, w0, sh));
+        sts32(b + 4, __funnelshift_l(w0, w1, sh));
+        sts32(b + 8, __funnelshift_l(w1, w2, sh));
+        sts32(b + 12, __funnelshift_l(w2, w3, sh));
+        q = q + 1u == nsteps ? 0u : q + 1u;
+      }
+      s += 16u * nsteps;
+      len -= 16u * nsteps;
+      o.wpos = dp + 16u * nsteps;
+      o.lo = __funnelshift_l(lds32(s - 4), 0u, sh);
     }
     if (len == 0) break;
     n = len;
@@ -676,7 +700,7 @@ constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is
 // written here but as part of a run, see bulk16.)  Requires qual_len == seq_len for matched records
 // (the front warp treats anything else as unmatched; bk_tokenize never produces it).
 __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
-                                          uint32_t part, uint32_t nparts) {
+                                          uint32_t part, uint32_t nparts, uint32_t rot) {
   OutStream o;
   // jobs of this part, bit 0 = A ... bit 4 = E
   const uint32_t jobs = nparts == 5 ? 1u << part : nparts == 4 ? (part == 0 ? 3u : 2u << part) : (part == 0 ? 5u : 4u << part);
@@ -723,6 +747,7 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
   const uint32_t sep = isD ? (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16) : (uint32_t)'\n';
   const uint32_t nsep = isD ? 3u : 1u;
   os_begin(o, d + 2u + H + G + (isD ? 0u : L - (ce - cs) + 3u));
+  o.rot = rot;
   if (ps) os_run(o, src, ps);
   if (r.fast) {
     os_run(o, src + pe, ll - pe + nsep);  // the line end ("\n+\n" after seq, "\n" after qual) travels with the run
