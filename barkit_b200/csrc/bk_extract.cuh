@@ -451,6 +451,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
       const bool fits = gout + total <= P.cap[m];
       if (!fits && lane == 0) atomicOr(&P.result->error, 1u);
       const uint32_t phase = (uint32_t)(gout & 15ull);
+      // The output tile may be overwritten once the engine has read the previous tile out of it.  That
+      // wait sits here, behind the wait for this tile's offset, rather than behind the store itself.
+      if (bj == 0 && lane == 0) bulk_wait_read0();
+      back_sync(m, nparts);
       if (fits && total) {
         // ---- assemble the tile's output in shared memory (same 16-byte phase as the global destination)
         const uint32_t ooff = tm.ooff[lane];
@@ -537,13 +541,12 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
           if (x < a0) gdst[x] = (uint8_t)lds8(out_s + phase + (uint32_t)(x - g0));
           x = a1 + lane;
           if (x < g1) gdst[x] = (uint8_t)lds8(out_s + phase + (uint32_t)(x - g0));
-          if (lane == 0) bulk_wait_read0();  // the output tile may be overwritten once the engine has read it
         }
         __syncwarp();
       }
-      back_sync(m, nparts);
       if (m == 0 && bj == 0) { EVT(tile, 13) }
     }
+    if (bj == 0 && lane == 0) bulk_wait_read0();  // the last store must have left shared memory before the CTA does
   }
 }
 
