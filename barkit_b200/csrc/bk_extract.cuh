@@ -170,6 +170,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
   __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_empty[2][kStages];
   __shared__ __align__(16) uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, complement table, program
   __shared__ int s_ms[kFrontPairs][2][2][32];  // [front pair][round parity][mate][lane]
+  // search sharing (GENERAL, paired, exactly one mate unanchored): the searching mate's reads {seq, len, can}
+  // for the other mate's front warp, and that warp's results for the upper half of the tile
+  __shared__ uint32_t s_share[GENERAL && PAIRED ? kFrontPairs : 1][2][3][32];
+  __shared__ int s_help[GENERAL && PAIRED ? kFrontPairs : 1][2][32];
   __shared__ TileMeta meta[NM][kStages];
   __shared__ uint4 run_desc[NM][32];  // copy descriptors of the tile's runs of unchanged records
 
@@ -318,6 +322,14 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
     // tiles queued behind one another between claim and publication, and every later tile's look-back
     // waited for the slowest of them.
     uint32_t n_kept = 0, n_matched = 0;
+    // An unanchored search costs ten times an anchored test.  When exactly one mate needs one, the
+    // other mate's front warp of the pair -- otherwise idle until the exchange -- searches the upper
+    // half of the tile's reads for it.
+    const bool un_me = pg.present && !pg.anchor_start && !pg.anchor_end;
+    const bk_devprog& pgo = P.prog[PAIRED ? m ^ 1 : m];
+    const bool un_other = PAIRED && pgo.present && !pgo.anchor_start && !pgo.anchor_end;
+    const bool split = GENERAL && PAIRED && !rc && un_me != un_other;
+    const uint32_t tab_other = smem_u32(&cls_tab[PAIRED ? m ^ 1 : m][0]);
     for (uint32_t k = fp;; k += kFrontPairs) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
       const uint32_t xb = (k / kFrontPairs) & 1u;  // exchange buffer of this pair's round
@@ -342,15 +354,30 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         __syncwarp();
         if (m == 0) { EVT(tile, 4) }
         const bool can = active && pg.present && rv.qual_len == rv.seq_len;  // unequal lengths never leave bk_tokenize
-        if (GENERAL && pg.present && !pg.anchor_start && !pg.anchor_end) {
-          ms = match_unanchored(tab, rv.seq, rv.seq_len, can, lane);  // warp per read
+        if (GENERAL && un_me) {
+          if (split) {  // lower half here, upper half on the other mate's front warp
+            s_share[fp][xb][0][lane] = rv.seq;
+            s_share[fp][xb][1][lane] = rv.seq_len;
+            s_share[fp][xb][2][lane] = can;
+            nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);
+          }
+          ms = match_unanchored(tab, rv.seq, rv.seq_len, can && !(split && lane >= 16), lane);  // warp per read
         } else if (can) {
           ms = match_read<false>(tab, rv.seq, rv.seq_len);  // lane per read
         }
         if (GENERAL && can && ms < 0 && rc) ms = match_read<true>(tab, rv.seq, rv.seq_len);  // parse.rs:61-66
-        if (active && P.match[m]) P.match[m][r0 + lane] = ms;
-      } else if (lane == 0) {
-        atomicOr(&P.result->error, 2u);
+      } else {
+        if (lane == 0) atomicOr(&P.result->error, 2u);
+        if (GENERAL && split && un_me) {  // keep the pair's barriers in step: nothing to search
+          s_share[fp][xb][2][lane] = 0;
+          nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);
+        }
+      }
+      if (GENERAL && split && !un_me) {  // the other mate searches: take the upper half of its reads
+        nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);
+        const int h = match_unanchored(tab_other, s_share[fp][xb][0][lane], s_share[fp][xb][1][lane],
+                                       s_share[fp][xb][2][lane] != 0 && lane >= 16, lane);
+        s_help[fp][xb][lane] = h;
       }
       __syncwarp();
       if (m == 0) { EVT(tile, 5) }
@@ -362,7 +389,12 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);  // the two mates' front warps of this pair
         ms_other = s_ms[fp][xb][m ^ 1][lane];
         skip = skip || (s_ms[fp][xb][m ^ 1][0] == kSkipTile);
+        if (GENERAL && split && lane >= 16) {  // the upper half's search results come from the helper
+          const int h = s_help[fp][xb][lane];
+          if (un_me) { if (!too_big) ms = h; } else if (ms_other != kSkipTile) ms_other = h;
+        }
       }
+      if (!too_big && active && P.match[m]) P.match[m][r0 + lane] = ms;
       // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
       const bool keep = !skip && active && (ms >= 0 || ms_other >= 0);
 
