@@ -48,7 +48,10 @@ def measured_peak():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons, sampled every 10 ms from before the warm-up on; only the samples
+    whose time stamp falls inside the timed region count (widened to the warm-up steps -- the same load -- when
+    the region is too short to catch two)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -56,48 +59,67 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.path = None
+        self.t_start = self.t_begin = self.t_end = None
 
     def start(self):
+        import datetime
+        self.t_start = datetime.datetime.now()
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "10"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.3)   # nvidia-smi needs a moment before its first sample
         except Exception:
             self.proc = None
 
+    def begin(self):
+        import datetime
+        self.t_begin = datetime.datetime.now()
+
+    def end(self):
+        import datetime
+        self.t_end = datetime.datetime.now()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": "timed region"}
         if not self.proc:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                    rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                   f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
+        lo, hi = self.t_begin or self.t_start, self.t_end or datetime.datetime.now()
+        sel = [r for r in rows if lo <= r[0] <= hi]
+        if len(sel) < 2:   # a 30 ms region at a 10 ms period: take the warm-up steps (same kernel, same inputs) too
+            sel = [r for r in rows if self.t_start + datetime.timedelta(seconds=0.3) <= r[0] <= hi]
+            out["window"] = "warm-up + timed region"
+        sm = sorted(r[1] for r in sel)
+        reasons = set()
+        for r in sel:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in sel), reasons=sorted(reasons), samples=len(sm))
         return out
 
 
@@ -249,11 +271,12 @@ def main():
         m = batches[i % nbatch]
         return ctx.extract_device(P, m[0], m[1], d_o1, cap1, d_o2, cap2)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     t_wall0 = time.perf_counter()
     dev_ms, launches, alg_bytes, kept = 0.0, 0, 0, 0
     for i in range(args.steps):
@@ -264,6 +287,7 @@ def main():
         kept += r.n_out
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    sampler.end()
     clocks = sampler.stop()
     dev_ms_max = max_over_ranks(dev_ms)
     value = world * args.steps * P / (dev_ms_max / 1e3)
