@@ -96,6 +96,7 @@ SYMBOLS = {
                                     C.c_void_p, C.c_int, C.POINTER(Result)]),
     "bk_tokenize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, u32p,
                                      C.POINTER(C.c_uint64), u32p]),
+    "bk_kernel_variant": (C.c_int, [C.c_void_p]),
     "bk_debug_events": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bk_reverse_complement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "bk_generate_device": (C.c_int, [C.c_void_p, C.POINTER(SynConfig), C.c_int, C.c_uint64, C.c_uint64,
@@ -313,6 +314,10 @@ class Context:
                         d_text: int, d_off: int):
         self._check(lib.bk_generate_device(self.handle, C.byref(cfg), mate, seed, first_idx, n,
                                            d_text, d_off))
+
+    def kernel_variant(self) -> int:
+        """4 / 5 = the extract kernel in use, 0 = still being chosen (see bk_kernel_variant)."""
+        return lib.bk_kernel_variant(self.handle)
 
     def extract_device(self, n, m1: MateIn, m2: MateIn | None, d_out1, cap1, d_out2=0, cap2=0,
                        d_match1=0, d_match2=0, iters=1) -> Result:

@@ -40,6 +40,8 @@ def build(force=False, verbose=False):
         cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-lpthread"]
         if os.environ.get("BK_PROFILE_PHASES"):
             cmd.insert(1, "-DBK_PROFILE_PHASES")
+        for d in os.environ.get("BK_DEFINES", "").split():
+            cmd.insert(1, "-D" + d)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)

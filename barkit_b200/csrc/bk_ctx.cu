@@ -16,6 +16,7 @@
 #include "../../include/barkit_b200.h"
 #include "bk_internal.h"
 #include "bk_extract.cuh"
+#include "bk_extract5.cuh"
 #include "bk_tokenize.cuh"
 
 namespace {
@@ -44,7 +45,18 @@ struct Slot {
   uint64_t out_cap[2] = {0, 0};
   bool busy = false;
   uint32_t launches = 0;
+  int variant = 4;  // kernel the batch in flight was launched with
 };
+
+// Launches whose patterns are all anchored at the read start can run on either extract kernel
+// (identical output); which one is faster depends on the pattern and the record shape, so the first
+// large batches of a context try both (twice each) and the context keeps the faster.
+struct Tuner {
+  int choice = 0;  // 0 = still trying, else 4 or 5
+  int trials[2] = {0, 0};
+  double best[2] = {1e30, 1e30};  // ms per record
+};
+constexpr uint32_t kTuneMinRecords = 200000;
 
 }  // namespace
 
@@ -56,6 +68,7 @@ struct bk_ctx {
   int sm_count = 0;
   Slot slot[kSlots];
   DevBuf tok;  // bk_tokenize_device scratch: block counts + TokResult
+  Tuner tuner;
   std::string last_error;
 };
 
@@ -141,6 +154,83 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   return BK_OK;
 }
 
+// extract_kernel5 (bk_extract5.cuh) serves launches whose patterns are all anchored at the read start
+// (and short enough for the scout's window); BK_KERNEL=4 keeps every launch on extract_kernel.
+bool v5_eligible(const bk_ctx* ctx) {
+  if (needs_general(ctx)) return false;
+  for (int m = 0; m < 2; ++m)
+    if (ctx->prog[m].present && (!ctx->prog[m].anchor_start || ctx->prog[m].total_len > bk::v5::kMaxPatLen)) return false;
+  return true;
+}
+
+// 4 = extract_kernel, 5 = extract_kernel5.  BK_KERNEL=4|5 pins the choice (tests, profiling).
+int pick_variant(bk_ctx* ctx, uint32_t n) {
+  if (!v5_eligible(ctx)) return 4;
+  const char* k = getenv("BK_KERNEL");
+  if (k && (k[0] == '4' || k[0] == '5')) return k[0] - '0';
+  if (ctx->tuner.choice) return ctx->tuner.choice;
+  if (n < kTuneMinRecords) return 4;
+  return ctx->tuner.trials[1] < ctx->tuner.trials[0] ? 5 : 4;
+}
+
+void report_variant(bk_ctx* ctx, int variant, uint32_t n, double ms) {
+  Tuner& t = ctx->tuner;
+  if (t.choice || n < kTuneMinRecords || !v5_eligible(ctx) || ms <= 0) return;
+  const int i = variant == 5 ? 1 : 0;
+  t.trials[i] += 1;
+  t.best[i] = std::min(t.best[i], ms / n);
+  if (t.trials[0] >= 2 && t.trials[1] >= 2) {
+    t.choice = t.best[1] < t.best[0] ? 5 : 4;
+    if (getenv("BK_DEBUG"))
+      fprintf(stderr, "[bk] tuner: extract_kernel %.3f ns/record, extract_kernel5 %.3f ns/record -> %d\n", t.best[0] * 1e6,
+              t.best[1] * 1e6, t.choice);
+  }
+}
+
+size_t smem_for5(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_t in_cap[2], uint32_t out_cap[2]) {
+  size_t total = 0;
+  int nm = ctx->paired ? 2 : 1;
+  for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
+  for (int m = 0; m < nm; ++m) {
+    uint32_t growth = ctx->prog[m].present ? ctx->prog[m].hdr_growth : 0;
+    in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
+    out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
+    total += bk::v5::kData * (size_t)in_cap[m] + out_cap[m];
+  }
+  return total;
+}
+
+template <bool PAIRED>
+int plan_launch5(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, bk::v5::extract_kernel5<PAIRED>));
+  // two CTAs per SM: 228 KB per SM, 1 KB reserved per CTA, the kernel's static shared memory on top
+  const size_t target = (233472 / 2 - 1024 - fa.sharedSizeBytes) & ~size_t(127);
+  uint32_t R = bk::kTileRecs;
+  while (R > 8 && smem_for5(ctx, R, maxrec, lp->in_cap, lp->out_cap) > target) --R;
+  while (R > 0 && smem_for5(ctx, R, maxrec, lp->in_cap, lp->out_cap) > kMaxDynSmem) --R;
+  if (R == 0) {
+    ctx->last_error = "record too long for the on-chip staging buffer";
+    return BK_E_CAPACITY;
+  }
+  lp->tile_recs = R;
+  lp->smem = smem_for5(ctx, R, maxrec, lp->in_cap, lp->out_cap);
+  lp->ntiles = (n + R - 1) / R;
+  CK(cudaFuncSetAttribute(bk::v5::extract_kernel5<PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp->smem));
+  CK(cudaFuncSetAttribute(bk::v5::extract_kernel5<PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          cudaSharedmemCarveoutMaxShared));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::v5::extract_kernel5<PAIRED>, bk::v5::cta_warps(PAIRED) * 32, lp->smem));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)per_sm * ctx->sm_count;
+  if (grid > (long long)lp->ntiles) grid = lp->ntiles;
+  lp->grid = (int)std::max<long long>(grid, 1);
+  if (getenv("BK_DEBUG"))
+    fprintf(stderr, "[bk] v5 tile_recs %u smem %zu B (+%zu static) ctas/sm %d grid %d ntiles %u\n", lp->tile_recs, lp->smem,
+            (size_t)fa.sharedSizeBytes, per_sm, lp->grid, lp->ntiles);
+  return BK_OK;
+}
+
 // [512 B header | tile descriptors, 8 B each | block descriptors (one per 32 tiles), 16 B each | block accumulators, 16 B each]
 size_t block_desc_offset(uint32_t ntiles) { return 512 + (((size_t)ntiles * 8 + 15) & ~size_t(15)); }
 size_t block_acc_offset(uint32_t ntiles) { return block_desc_offset(ntiles) + ((size_t)ntiles / 32 + 1) * 16; }
@@ -154,7 +244,7 @@ size_t scratch_bytes(uint32_t ntiles) { return events_offset(ntiles); }
 // enqueue: scratch reset + extract kernel.  All pointers are device pointers.
 int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
                     const bk_mate_in* in2, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
-                    int32_t* match1, int32_t* match2, uint32_t* launches) {
+                    int32_t* match1, int32_t* match2, uint32_t* launches, int variant) {
   if (ctx->paired && !in2) { ctx->last_error = "paired context needs two mates"; return BK_E_ARG; }
   if (!ctx->paired && in2) { ctx->last_error = "single-end context got two mates"; return BK_E_ARG; }
   const bk_mate_in* in[2] = {in1, in2};
@@ -172,7 +262,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   }
   LaunchPlan lp;
   const bool general = needs_general(ctx);
-  int rc = ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))
+  const bool v5 = variant == 5 && v5_eligible(ctx);
+  int rc = v5 ? (ctx->paired ? plan_launch5<true>(ctx, n, maxrec, &lp) : plan_launch5<false>(ctx, n, maxrec, &lp))
+           : ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))
                        : (general ? plan_launch<false, true>(ctx, n, maxrec, &lp) : plan_launch<false, false>(ctx, n, maxrec, &lp));
   if (rc != BK_OK) return rc;
   rc = ensure(ctx, &s->scratch.buf, scratch_bytes(lp.ntiles));
@@ -205,7 +297,11 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.tile_recs = lp.tile_recs;
   P.flags = ctx->flags;
   if (n > 0) {
-    if (ctx->paired && general)
+    if (v5 && ctx->paired)
+      bk::v5::extract_kernel5<true><<<lp.grid, bk::v5::cta_warps(true) * 32, lp.smem, stream>>>(P);
+    else if (v5)
+      bk::v5::extract_kernel5<false><<<lp.grid, bk::v5::cta_warps(false) * 32, lp.smem, stream>>>(P);
+    else if (ctx->paired && general)
       bk::extract_kernel<true, true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
     else if (ctx->paired)
       bk::extract_kernel<true, false><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
@@ -362,10 +458,11 @@ int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk
     dev[m].rec_off = (const uint32_t*)s.off[m].p;
   }
   s.launches = 0;
+  s.variant = pick_variant(ctx, n);
   CK(cudaEventRecord(s.ev0, s.stream));
   int rc = enqueue_extract(ctx, &s, s.stream, n, &dev[0], ctx->paired ? &dev[1] : nullptr,
                            (uint8_t*)s.out[0].p, s.out_cap[0], (uint8_t*)s.out[1].p, s.out_cap[1], nullptr,
-                           nullptr, &s.launches);
+                           nullptr, &s.launches, s.variant);
   if (rc != BK_OK) return rc;
   CK(cudaEventRecord(s.ev1, s.stream));
   CK(cudaMemcpyAsync(s.h_res, (uint8_t*)s.scratch.buf.p + 64, sizeof(bk::DevResult), cudaMemcpyDeviceToHost,
@@ -397,6 +494,7 @@ int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, 
   CK(cudaStreamSynchronize(s.stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+  report_variant(ctx, s.variant, s.n, ms);
   fill_result(res, r, s.n, ms, s.launches);
   return BK_OK;
 }
@@ -441,10 +539,11 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
   Slot& s = ctx->slot[0];
   if (s.busy) { ctx->last_error = "slot 0 is busy"; return BK_E_ARG; }
   uint32_t launches = 0;
+  const int variant = pick_variant(ctx, n);
   CK(cudaEventRecord(s.ev0, s.stream));
   for (int it = 0; it < iters; ++it) {
     int rc = enqueue_extract(ctx, &s, s.stream, n, d_in1, d_in2, d_out1, cap1, d_out2, cap2, d_match1, d_match2,
-                             &launches);
+                             &launches, variant);
     if (rc != BK_OK) return rc;
   }
   CK(cudaEventRecord(s.ev1, s.stream));
@@ -454,8 +553,17 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
   bk::DevResult r = *s.h_res;
+  report_variant(ctx, variant, n, ms / iters);
   fill_result(res, r, n, ms / iters, launches);
   return check_dev_result(ctx, r);
+}
+
+int bk_kernel_variant(const bk_ctx* ctx) {
+  if (!ctx) return BK_E_ARG;
+  if (!v5_eligible(ctx)) return 4;
+  const char* k = getenv("BK_KERNEL");
+  if (k && (k[0] == '4' || k[0] == '5')) return k[0] - '0';
+  return ctx->tuner.choice;
 }
 
 int bk_debug_events(bk_ctx* ctx, uint32_t ntiles, uint32_t first_tile, uint32_t count, uint64_t* out) {

@@ -158,6 +158,13 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
                       uint8_t* d_out1, uint64_t cap1, uint8_t* d_out2, uint64_t cap2,
                       int32_t* d_match1, int32_t* d_match2, int iters, bk_result* res);
 
+/* Which extract kernel this context's launches use: 4 = extract_kernel (bk_extract.cuh, any pattern),
+ * 5 = extract_kernel5 (bk_extract5.cuh, patterns anchored at the read start), 0 = both qualify and the
+ * context is still timing them on its first large batches (two launches each; output is identical).
+ * The environment variable BK_KERNEL=4|5 pins the choice.  No counterpart in the reference: its
+ * per-read work has one implementation (parse.rs:58-68). */
+int bk_kernel_variant(const bk_ctx* ctx);
+
 /* Debug: the pipeline event trace of the last device launch on slot 0 -- 16 clock64() stamps per tile
  * (tools/phases.py names them) for tiles [first_tile, first_tile + count) of a launch that had `ntiles`
  * tiles.  Fails unless the library was built with -DBK_PROFILE_PHASES. */

@@ -17,6 +17,15 @@ from tests.util import CONFIG_PATTERNS, lib_syn_config, ragged_fastq
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["4", "5"])
+def kernel_variant(request, monkeypatch):
+    """Every parity test runs once per extract kernel: BK_KERNEL=4 pins extract_kernel (bk_extract.cuh),
+    BK_KERNEL=5 sends every launch that qualifies (patterns anchored at the read start, no -r) to
+    extract_kernel5 (bk_extract5.cuh); the library reads the variable at each launch."""
+    monkeypatch.setenv("BK_KERNEL", request.param)
+    return request.param
+
+
 def make_ctx(p1, p2=None, k=1, paired=False, skip=False, rc=False):
     P1 = _lib.Program(p1, k) if p1 is not None else None
     P2 = _lib.Program(p2, k) if p2 is not None else None
@@ -189,6 +198,62 @@ def test_runs_of_unchanged_records(period):
     # and with the roles of the mates swapped (pattern on mate 2: five back warps there, three here)
     o2, o1, res = run_pe(fq2, fq1, None, p1, 0)
     assert o1 == e1 and o2 == e2
+
+
+@pytest.mark.parametrize("mode", ["se", "pe1", "pe2", "pe12"])
+def test_header_lengths_around_the_scout_window(mode):
+    """extract_kernel5 parses and matches inside a 144-byte window at the record start; headers that push
+    the pattern (or the header's own line end) past it take the bytewise path.  Sweep header lengths
+    0..220 across that boundary, with CR line ends, '+' comments and unequal seq/qual lines mixed in."""
+    rnd = random.Random(7)
+    n = 2600
+    heads = [i % 221 for i in range(n)]
+    fq1 = ragged_fastq(rnd, n, 1, plant=[b"ATGCCAT"], head_lens=heads, min_len=20, max_len=90)
+    fq2 = ragged_fastq(rnd, n, 2, plant=[b"ATGCCAT"], head_lens=heads, plus_comment=True)
+    p_long = "^(?P<CB>[ATGCN]{16})atgccat(?P<UMI>[ATGCN]{12})(?P<SB>[ACGTN]{20})"   # 55 bytes
+    p_short = "^(?P<UMI>[ATGCN]{12})"
+    if mode == "se":
+        for pat in (p_long, p_short, "^(?P<UMI>[ATGCN]{8})acgt$"):
+            out, _ = run_se(fq1, pat, 1)
+            assert out == bo.extract_se(fq1, pat, 1, False, False), pat
+        return
+    p1, p2 = {"pe1": (p_long, None), "pe2": (None, p_short), "pe12": (p_short, p_long)}[mode]
+    for k, skip in ((1, False), (2, True)):
+        o1, o2, _ = run_pe(fq1, fq2, p1, p2, k, skip=skip)
+        e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, k, rc_barcodes=False, skip_trimming=skip)
+        assert o1 == e1 and o2 == e2, (mode, k)
+
+
+def test_crlf_paired_anchored():
+    """CR line ends on both mates with `^` patterns: every record leaves the writer's framing."""
+    rnd = random.Random(11)
+    n = 1500
+    heads = [rnd.choice([0, 1, 23, 130]) for _ in range(n)]
+    fq1 = ragged_fastq(rnd, n, 1, plant=[b"ATGCCAT"], head_lens=heads, crlf=True)
+    fq2 = ragged_fastq(rnd, n, 2, plant=[b"ATGCCAT"], head_lens=heads, crlf=True, final_newline=False)
+    p1, p2 = "^(?P<CB>[ATGCN]{16})atgccat(?P<UMI>[ATGCN]{12})", "^(?P<SB>[ATGCN]{5})"
+    o1, o2, _ = run_pe(fq1, fq2, p1, p2, 1)
+    e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, 1, rc_barcodes=False, skip_trimming=False)
+    assert o1 == e1 and o2 == e2
+
+
+def test_kernel_autotune_keeps_output_identical(monkeypatch):
+    """Without BK_KERNEL the context tries both kernels on its first large batches and keeps the faster;
+    whichever runs, the bytes are the same."""
+    monkeypatch.delenv("BK_KERNEL", raising=False)
+    p1, p2, paired = CONFIG_PATTERNS["C2"]
+    ctx = make_ctx(p1, p2, k=1, paired=True)
+    n = 250000
+    mates, rl = _device_batch(ctx, "C2", 0, n)
+    cap = n * (rl + 120)
+    d_o1, d_o2 = ctx.dev_alloc(cap), ctx.dev_alloc(cap)
+    crcs = set()
+    for _ in range(6):   # 2 + 2 trial launches, then the chosen kernel
+        res = ctx.extract_device(n, mates[0], mates[1], d_o1, cap, d_o2, cap)
+        crcs.add((zlib.crc32(ctx.d2h(d_o1, res.out1_len).tobytes()), zlib.crc32(ctx.d2h(d_o2, res.out2_len).tobytes()),
+                  res.n_out))
+    assert len(crcs) == 1
+    ctx.close()
 
 
 def test_empty_and_tiny_inputs():
