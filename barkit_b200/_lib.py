@@ -39,7 +39,8 @@ class MateIn(C.Structure):
 class Result(C.Structure):
     _fields_ = [("out1_len", C.c_uint64), ("out2_len", C.c_uint64), ("n_in", C.c_uint64),
                 ("n_out", C.c_uint64), ("n_match1", C.c_uint64), ("n_match2", C.c_uint64),
-                ("kernel_ms", C.c_float), ("launches", C.c_uint32)]
+                ("kernel_ms", C.c_float), ("launches", C.c_uint32),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class ProgramInfo(C.Structure):

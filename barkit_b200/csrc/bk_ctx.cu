@@ -8,10 +8,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <new>
 #include <string>
+#include <thread>
 
 #include "../../include/barkit_b200.h"
 #include "bk_internal.h"
@@ -38,6 +40,7 @@ struct Scratch {  // [tile counter | DevResult | desc stream 0 | desc stream 1]
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evh0 = nullptr, evh1 = nullptr;  // around the host -> device copies of a pass-through batch
   DevBuf text[2], off[2], out[2];
   Scratch scratch;
   bk::DevResult* h_res = nullptr;  // pinned
@@ -46,6 +49,14 @@ struct Slot {
   bool busy = false;
   uint32_t launches = 0;
   int variant = 4;  // kernel the batch in flight was launched with
+  // host pass-through of the mate without a pattern (see bk_submit)
+  bool passthrough = false;
+  int pt = -1;                   // index of the mate kept on the host for the batch in flight
+  bk_mate_in host_pt = {};       // the caller's buffers of that mate: read again in bk_wait
+  DevBuf match;                  // the other mate's match table on the device
+  int32_t* h_match = nullptr;    // ... and its pinned host copy
+  size_t h_match_cap = 0;
+  uint64_t h2d_bytes = 0;        // of the batch in flight
 };
 
 // Launches whose patterns are all anchored at the read start can run on either extract kernel
@@ -69,6 +80,17 @@ struct bk_ctx {
   Slot slot[kSlots];
   DevBuf tok;  // bk_tokenize_device scratch: block counts + TokResult
   Tuner tuner;
+  // Paired mode with exactly one pattern: the mate without one stays on the host (pass_mate = its index)
+  // and `solo` is the single-end view of this context that processes the other mate.
+  int pass_mate = -1;
+  bk_ctx* solo = nullptr;
+  int host_threads = 1;
+  // The host copy is worth it while it takes less time than the bus would need for the same mate.
+  // Both are measured on every large pass-through batch; when the host side is the slower one twice in
+  // a row (few or slow host cores, several GPUs sharing the host's memory bandwidth) the context
+  // sends both mates to the device from then on.  BK_HOST_PASSTHROUGH=1 pins the host copy.
+  bool pass_pinned = false;
+  int pass_slow = 0;
   std::string last_error;
 };
 
@@ -331,6 +353,7 @@ void fill_result(bk_result* res, const bk::DevResult& r, uint32_t n, float ms, u
   res->n_match2 = r.n_match[1];
   res->kernel_ms = ms;
   res->launches = launches;
+  res->h2d_bytes = res->d2h_bytes = 0;
 }
 
 }  // namespace
@@ -381,11 +404,29 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
     Slot& s = ctx->slot[i];
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&s.ev0) != cudaSuccess || cudaEventCreate(&s.ev1) != cudaSuccess ||
+        cudaEventCreate(&s.evh0) != cudaSuccess || cudaEventCreate(&s.evh1) != cudaSuccess ||
         cudaHostAlloc((void**)&s.h_res, sizeof(bk::DevResult), cudaHostAllocDefault) != cudaSuccess) {
       std::string m = std::string("CUDA resource creation failed: ") + cudaGetErrorString(cudaGetLastError());
       bk_ctx_destroy(ctx);
       return fail(BK_E_CUDA, m);
     }
+  }
+  const char* hp = getenv("BK_HOST_PASSTHROUGH");
+  if (ctx->paired && (p1 == nullptr) != (p2 == nullptr) && !(hp && hp[0] == '0')) {
+    bk_ctx* solo = new (std::nothrow) bk_ctx();
+    if (!solo) { bk_ctx_destroy(ctx); return fail(BK_E_CAPACITY, "out of memory"); }
+    ctx->pass_mate = p1 ? 1 : 0;
+    solo->device = device;
+    solo->flags = flags & ~(uint32_t)BK_FLAG_PAIRED;
+    solo->paired = false;
+    solo->sm_count = ctx->sm_count;
+    memset(solo->prog, 0, sizeof solo->prog);
+    solo->prog[0] = ctx->prog[1 - ctx->pass_mate];
+    ctx->solo = solo;
+    const char* ht = getenv("BK_HOST_THREADS");
+    int nt = ht ? atoi(ht) : (int)std::thread::hardware_concurrency();
+    ctx->host_threads = std::max(1, std::min(nt, 32));
+    ctx->pass_pinned = hp && hp[0] == '1';
   }
   if (status) *status = BK_OK;
   if (err && errcap) err[0] = 0;
@@ -404,12 +445,17 @@ void bk_ctx_destroy(bk_ctx* ctx) {
       if (s.out[m].p) cudaFree(s.out[m].p);
     }
     if (s.scratch.buf.p) cudaFree(s.scratch.buf.p);
+    if (s.match.p) cudaFree(s.match.p);
+    if (s.h_match) cudaFreeHost(s.h_match);
     if (s.h_res) cudaFreeHost(s.h_res);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
+    if (s.evh0) cudaEventDestroy(s.evh0);
+    if (s.evh1) cudaEventDestroy(s.evh1);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   if (ctx->tok.p) cudaFree(ctx->tok.p);
+  delete ctx->solo;
   delete ctx;
 }
 
@@ -445,7 +491,57 @@ int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk
   for (int m = 0; m < nm; ++m) {
     if (!in[m]->text || !in[m]->rec_off) { ctx->last_error = "null batch pointer"; return BK_E_ARG; }
     if (in[m]->text_len >= (1ull << 32)) { ctx->last_error = "batch text must be < 4 GiB per mate"; return BK_E_CAPACITY; }
+  }
+  s.passthrough = ctx->pass_mate >= 0;
+  s.pt = ctx->pass_mate;
+  if (s.passthrough) {
+    // Exactly one mate has a pattern.  The other one is only ever copied or dropped (run.rs:149-160), and the
+    // caller's buffer already holds it: send the pattern's mate alone, as a single-end batch (an unmatched
+    // read of it drops the pair either way, run.rs:71-78), fetch its match table with the output, and let
+    // bk_wait assemble the pattern-less mate's output from the host copy (bk_fastq.cc, gather_kept).
+    const int pm = 1 - ctx->pass_mate;
+    bk_ctx* solo = ctx->solo;
     int rc;
+    if ((rc = ensure(ctx, &s.text[pm], in[pm]->text_len + 64)) != BK_OK) return rc;
+    if ((rc = ensure(ctx, &s.off[pm], ((size_t)n + 1) * 4)) != BK_OK) return rc;
+    const uint64_t ob = bk_out_bound(ctx, pm + 1, n, in[pm]->text_len);
+    if ((rc = ensure(ctx, &s.out[pm], ob)) != BK_OK) return rc;
+    if ((rc = ensure(ctx, &s.match, ((size_t)n + 1) * 4)) != BK_OK) return rc;
+    if (s.h_match_cap < (size_t)n + 1) {
+      if (s.h_match) CK(cudaFreeHost(s.h_match));
+      s.h_match = nullptr;
+      s.h_match_cap = 0;
+      const size_t want = (size_t)n + 1 + n / 8;
+      CK(cudaHostAlloc((void**)&s.h_match, want * 4, cudaHostAllocDefault));
+      s.h_match_cap = want;
+    }
+    s.out_cap[pm] = ob;
+    s.h2d_bytes = in[pm]->text_len + ((uint64_t)n + 1) * 4;
+    s.host_pt = *in[ctx->pass_mate];
+    CK(cudaEventRecord(s.evh0, s.stream));
+    CK(cudaMemcpyAsync(s.text[pm].p, in[pm]->text, in[pm]->text_len, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.off[pm].p, in[pm]->rec_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaEventRecord(s.evh1, s.stream));
+    bk_mate_in d = *in[pm];
+    d.text = (const uint8_t*)s.text[pm].p;
+    d.rec_off = (const uint32_t*)s.off[pm].p;
+    s.launches = 0;
+    s.variant = pick_variant(solo, n);
+    CK(cudaEventRecord(s.ev0, s.stream));
+    rc = enqueue_extract(solo, &s, s.stream, n, &d, nullptr, (uint8_t*)s.out[pm].p, ob, nullptr, 0,
+                         (int32_t*)s.match.p, nullptr, &s.launches, s.variant);
+    if (rc != BK_OK) { ctx->last_error = solo->last_error; return rc; }
+    CK(cudaEventRecord(s.ev1, s.stream));
+    CK(cudaMemcpyAsync(s.h_res, (uint8_t*)s.scratch.buf.p + 64, sizeof(bk::DevResult), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(s.h_match, s.match.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
+    s.n = n;
+    s.busy = true;
+    return BK_OK;
+  }
+  s.h2d_bytes = 0;
+  for (int m = 0; m < nm; ++m) {
+    int rc;
+    s.h2d_bytes += in[m]->text_len + ((uint64_t)n + 1) * 4;
     if ((rc = ensure(ctx, &s.text[m], in[m]->text_len + 64)) != BK_OK) return rc;
     if ((rc = ensure(ctx, &s.off[m], ((size_t)n + 1) * 4)) != BK_OK) return rc;
     uint64_t ob = bk_out_bound(ctx, m + 1, n, in[m]->text_len);
@@ -482,6 +578,48 @@ int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, 
   bk::DevResult r = *s.h_res;
   int rc = check_dev_result(ctx, r);
   if (rc != BK_OK) return rc;
+  if (s.passthrough) {
+    const int pt = s.pt, pm = 1 - pt;
+    uint8_t* const out[2] = {out1, out2};
+    const uint64_t cap[2] = {cap1, cap2};
+    if (!out1 || !out2) { ctx->last_error = "out1 and out2 are required in paired mode"; return BK_E_ARG; }
+    if (r.out_len[0] > cap[pm]) { ctx->last_error = "output buffer too small"; return BK_E_CAPACITY; }
+    // the device's output of the pattern's mate comes back while the host assembles the other mate's
+    if (r.out_len[0]) CK(cudaMemcpyAsync(out[pm], s.out[pm].p, r.out_len[0], cudaMemcpyDeviceToHost, s.stream));
+    timespec ta, tb;
+    clock_gettime(CLOCK_MONOTONIC, &ta);
+    const uint64_t got = bk::gather_kept(s.host_pt.text, s.host_pt.rec_off, s.n, s.h_match, out[pt], cap[pt], ctx->host_threads);
+    clock_gettime(CLOCK_MONOTONIC, &tb);
+    const double gather_ms = (tb.tv_sec - ta.tv_sec) * 1e3 + (tb.tv_nsec - ta.tv_nsec) / 1e6;
+    float h2d_ms = 0;
+    CK(cudaEventElapsedTime(&h2d_ms, s.evh0, s.evh1));
+    // what the bus would have needed for this mate's text, at the rate the other mate's just moved
+    const double bus_ms = h2d_ms * (double)s.host_pt.text_len / (double)std::max<uint64_t>(s.h2d_bytes, 1);
+    if (!ctx->pass_pinned && s.n >= kTuneMinRecords) {
+      ctx->pass_slow = gather_ms > h2d_ms + bus_ms ? ctx->pass_slow + 1 : 0;
+      if (ctx->pass_slow >= 2) ctx->pass_mate = -1;  // (slots in flight finish as they were submitted)
+    }
+    if (getenv("BK_DEBUG"))
+      fprintf(stderr, "[bk] host gather: %u records, %llu bytes, %d threads, %.2f ms; bus: %.2f ms for the other mate, "
+              "%.2f ms more for this one%s\n", s.n, (unsigned long long)got, ctx->host_threads, gather_ms, h2d_ms, bus_ms,
+              ctx->pass_mate < 0 ? " -> both mates go to the device from now on" : "");
+    CK(cudaStreamSynchronize(s.stream));
+    if (got == UINT64_MAX) { ctx->last_error = "output buffer too small"; return BK_E_CAPACITY; }
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+    report_variant(ctx->solo, s.variant, s.n, ms);
+    bk::DevResult rr = r;  // single-end result -> this context's mates
+    rr.out_len[pm] = r.out_len[0];
+    rr.out_len[pt] = got;
+    rr.n_match[pm] = r.n_match[0];
+    rr.n_match[pt] = 0;
+    fill_result(res, rr, s.n, ms, s.launches);
+    if (res) {
+      res->h2d_bytes = s.h2d_bytes;
+      res->d2h_bytes = sizeof(bk::DevResult) + (uint64_t)s.n * 4 + r.out_len[0];
+    }
+    return BK_OK;
+  }
   if (r.out_len[0] > cap1 || (ctx->paired && r.out_len[1] > cap2)) {
     ctx->last_error = "output buffer too small";
     return BK_E_CAPACITY;
@@ -496,6 +634,10 @@ int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, 
   CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
   report_variant(ctx, s.variant, s.n, ms);
   fill_result(res, r, s.n, ms, s.launches);
+  if (res) {
+    res->h2d_bytes = s.h2d_bytes;
+    res->d2h_bytes = sizeof(bk::DevResult) + r.out_len[0] + (ctx->paired ? r.out_len[1] : 0);
+  }
   return BK_OK;
 }
 

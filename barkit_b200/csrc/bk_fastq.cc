@@ -60,3 +60,155 @@ extern "C" int bk_tokenize(const uint8_t* text, uint64_t len, int final_chunk, u
   if (max_rec_bytes) *max_rec_bytes = maxrec;
   return rc;
 }
+
+// ---- a mate without a pattern never has to cross the bus ------------------------------------------
+//
+// In paired mode a mate whose pattern is `None` (run.rs:233-245) is never rewritten: get_new_reads
+// (run.rs:149-160) copies its record when the other mate matched and drops it otherwise, and the
+// writer (fastq.rs:259-263) frames it as `@head LF seq LF + LF qual LF`.  The host already holds
+// that text, so bk_submit sends only the other mate to the device and bk_wait assembles this mate's
+// output here from the caller's input buffer and the device's match table: kept records in input
+// order, runs of consecutive kept records that already have the writer's framing as one memcpy.
+#include <algorithm>
+#include <thread>
+#include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+namespace bk {
+
+namespace {
+
+inline const uint8_t* find_lf(const uint8_t* p, const uint8_t* e) {
+  const void* q = p < e ? memchr(p, '\n', (size_t)(e - p)) : nullptr;
+  return q ? (const uint8_t*)q : e;
+}
+inline const uint8_t* strip_cr(const uint8_t* b, const uint8_t* e) { return (e > b && e[-1] == '\r') ? e - 1 : e; }
+
+// Copy of a long run with streaming stores: the output is written once and not read again here, so
+// fetching its cache lines first (what plain stores do) would add a third of the pass's memory traffic.
+inline void copy_stream(uint8_t* dst, const uint8_t* src, size_t n) {
+#if defined(__SSE2__)
+  if (n >= 256) {
+    const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+      const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+      const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32)), d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+      _mm_stream_si128((__m128i*)(dst + i), a);
+      _mm_stream_si128((__m128i*)(dst + i + 16), b);
+      _mm_stream_si128((__m128i*)(dst + i + 32), c);
+      _mm_stream_si128((__m128i*)(dst + i + 48), d);
+    }
+    memcpy(dst + i, src + i, n - i);
+    return;
+  }
+#endif
+  memcpy(dst, src, n);
+}
+
+// the record [b, e) is byte for byte what the writer would produce (parse_record's closed form, bk_kernels.cuh)
+inline bool writer_framed(const uint8_t* b, const uint8_t* e) {
+  const uint8_t* nl1 = find_lf(b, e);
+  if (nl1 == e || nl1 == b) return false;
+  const uint8_t* sb = nl1 + 1;
+  const size_t rem = (size_t)(e - sb);
+  if (rem < 4 || (rem & 1)) return false;
+  const size_t L = (rem - 4) >> 1;
+  if (!(sb[L] == '\n' && sb[L + 1] == '+' && sb[L + 2] == '\n' && e[-1] == '\n')) return false;
+  if (L != 0 && (sb[L - 1] == '\r' || e[-2] == '\r')) return false;
+  return !(nl1 > b + 1 && nl1[-1] == '\r');
+}
+
+// any other shape: cut the four lines as seq_io does (CR stripped, text after '+' dropped) and re-frame
+inline uint8_t* reframe(const uint8_t* b, const uint8_t* e, uint8_t* out) {
+  const uint8_t* nl1 = find_lf(b, e);
+  const uint8_t* hb = b + 1 <= e ? b + 1 : e;
+  const uint8_t* he = strip_cr(hb, nl1 > hb ? nl1 : hb);
+  const uint8_t* sb = nl1 + 1 < e ? nl1 + 1 : e;
+  const uint8_t* nl2 = find_lf(sb, e);
+  const uint8_t* se = strip_cr(sb, nl2);
+  const uint8_t* pb = nl2 + 1 < e ? nl2 + 1 : e;
+  const uint8_t* nl3 = find_lf(pb, e);
+  const uint8_t* qb = nl3 + 1 < e ? nl3 + 1 : e;
+  const uint8_t* nl4 = find_lf(qb, e);
+  const uint8_t* qe = strip_cr(qb, nl4);
+  *out++ = '@';
+  memcpy(out, hb, (size_t)(he - hb)); out += he - hb;
+  *out++ = '\n';
+  memcpy(out, sb, (size_t)(se - sb)); out += se - sb;
+  *out++ = '\n'; *out++ = '+'; *out++ = '\n';
+  memcpy(out, qb, (size_t)(qe - qb)); out += qe - qb;
+  *out++ = '\n';
+  return out;
+}
+
+}  // namespace
+
+// Kept records (keep[i] >= 0) of text/off[0..n] -> out, in the writer's framing.  Returns the bytes
+// written, or UINT64_MAX when `cap` cannot hold them.  A re-framed record is never longer than its
+// input, except that the batch's very last record gains one byte when it had no EOL; so every thread
+// can write at the offset its kept records' input lengths give, and if some record came out shorter
+// the parts are closed up afterwards.
+uint64_t gather_kept(const uint8_t* text, const uint32_t* off, uint32_t n, const int32_t* keep, uint8_t* out,
+                     uint64_t cap, int max_threads) {
+  if (n == 0) return 0;
+  int T = n < 50000 ? 1 : std::max(1, std::min(max_threads, 32));
+  std::vector<uint64_t> raw((size_t)T + 1, 0), wrote((size_t)T, 0);
+  std::vector<uint32_t> lo((size_t)T + 1);
+  for (int t = 0; t <= T; ++t) lo[t] = (uint32_t)((uint64_t)n * t / T);
+  auto count = [&](int t) {
+    uint64_t s = 0;
+    for (uint32_t i = lo[t]; i < lo[t + 1]; ++i)
+      if (keep[i] >= 0) s += off[i + 1] - off[i];
+    raw[t + 1] = s;
+  };
+  auto copy = [&](int t) {
+    uint8_t* o = out + raw[t];
+    uint8_t* const o0 = o;
+    uint32_t i = lo[t];
+    const uint32_t hi = lo[t + 1];
+    while (i < hi) {
+      if (keep[i] < 0) { ++i; continue; }
+      // maximal run of kept, writer-framed records: one copy
+      uint32_t j = i;
+      while (j < hi && keep[j] >= 0 && writer_framed(text + off[j], text + off[j + 1])) ++j;
+      if (j > i) {
+        copy_stream(o, text + off[i], off[j] - off[i]);
+        o += off[j] - off[i];
+        i = j;
+      } else {
+        o = reframe(text + off[i], text + off[i + 1], o);
+        ++i;
+      }
+    }
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+    wrote[t] = (uint64_t)(o - o0);
+  };
+  auto run = [&](auto&& fn) {
+    if (T == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(fn, t);
+    fn(0);
+    for (auto& x : th) x.join();
+  };
+  run(count);
+  for (int t = 0; t < T; ++t) raw[t + 1] += raw[t];
+  if (raw[T] + 1 > cap) return UINT64_MAX;  // (+1: a final record without EOL gains one)
+  run(copy);
+  // close the parts up (moves nothing when every part is exactly as long as its input records)
+  uint64_t pos = 0;
+  for (int t = 0; t < T; ++t) {
+    const uint64_t from = raw[t];
+    if (from != pos && wrote[t]) memmove(out + pos, out + from, wrote[t]);
+    pos += wrote[t];
+  }
+  return pos;
+}
+
+}  // namespace bk

@@ -30,6 +30,10 @@ int expand(const std::string& pattern, size_t k, std::string* out, std::vector<F
            std::string* err);
 int compile(const std::string& pattern, size_t max_error, Program* prog, std::string* err);
 
+// bk_fastq.cc: output of a mate without a pattern, assembled on the host (kept records, writer's framing)
+uint64_t gather_kept(const uint8_t* text, const uint32_t* off, uint32_t n, const int32_t* keep, uint8_t* out,
+                     uint64_t cap, int max_threads);
+
 }  // namespace bk
 
 struct bk_program {

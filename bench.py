@@ -334,10 +334,10 @@ def main():
             rc = _lib.lib.bk_wait(ctx.handle, slot, hbuf[a][0], hbuf[a][1], hbuf[b][0], hbuf[b][1], C.byref(res))
             if rc != 0:
                 raise SystemExit("bk_wait failed: %s" % _lib.lib.bk_last_error(ctx.handle).decode())
-            return res.out1_len + res.out2_len
+            return (res.h2d_bytes, res.d2h_bytes)
 
         def e2e_run(nsteps):
-            d2h = 0
+            d2h = (0, 0)
             submit(0)
             for s in range(nsteps):
                 if s + 1 < nsteps:
@@ -352,10 +352,12 @@ def main():
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * args.steps * Q / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": 2 * nb + 2 * (Q + 1) * 4, "d2h_bytes_per_step": int(d2h) + 56,
+               "h2d_bytes_per_step": int(d2h[0]), "d2h_bytes_per_step": int(d2h[1]),
                "pairs_per_step": Q, "ms_per_step": 1e3 * e2e_s / args.steps,
-               "note": "bk_submit/bk_wait with pinned host buffers, 2 slots in flight; offsets from bk_tokenize-"
-                       "equivalent arrays are part of the H2D bytes"}
+               "note": "bk_submit/bk_wait with pinned host buffers, 2 slots in flight; h2d/d2h bytes as the "
+                       "library counts them (text + record offsets in, FASTQ text + result + match table out). "
+                       "R2 has no pattern in this config: it stays on the host and its output (the kept "
+                       "pairs' records) is assembled there from the input buffer, inside the timed region"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) --------------------------------------
     cpu = None

@@ -124,6 +124,8 @@ typedef struct bk_result {
   uint64_t n_match2;
   float kernel_ms;   /* device time of the extract kernel(s), CUDA events on the ctx stream */
   uint32_t launches; /* kernels launched for this batch */
+  uint64_t h2d_bytes; /* bytes copied host -> device for this batch (0 for the device-resident form) */
+  uint64_t d2h_bytes; /* bytes copied device -> host */
 } bk_result;
 
 /* The batch map + writer framing: parse_se_reads (run.rs:63-80) / parse_pe_reads (run.rs:163-195)
@@ -134,7 +136,16 @@ typedef struct bk_result {
 int bk_extract_host(bk_ctx* ctx, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2,
                     uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2, bk_result* res);
 
-/* double-buffered form of the same call: slot in [0, bk_ctx_nslots) */
+/* A mate without a pattern stays on the host.  In paired mode with exactly one pattern the other mate's
+ * records are only ever copied (the pair is kept) or dropped (run.rs:149-160), so bk_submit sends the
+ * pattern's mate alone and bk_wait assembles the pattern-less mate's output from the CALLER'S INPUT
+ * BUFFER and the device's match table (kept records in input order, in the writer's framing,
+ * fastq.rs:259-263), on up to BK_HOST_THREADS host threads (default: all).  Consequence for every
+ * caller: the in1 / in2 buffers of a batch must stay valid and unchanged until bk_wait for its slot
+ * returns.  BK_HOST_PASSTHROUGH=0 (read by bk_ctx_create) sends both mates to the device instead.
+ * bk_result.h2d_bytes / d2h_bytes report what actually crossed the bus.
+ *
+ * double-buffered form of the same call: slot in [0, bk_ctx_nslots) */
 int bk_ctx_nslots(const bk_ctx* ctx);
 int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2);
 int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,

@@ -256,6 +256,39 @@ def test_kernel_autotune_keeps_output_identical(monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("which", ["p1", "p2"])
+def test_host_side_mate_matches_the_device_path(which, monkeypatch):
+    """Paired mode with one pattern: the pattern-less mate is assembled on the host from the caller's input
+    buffer (bk_submit / bk_wait, several threads above 50 000 records).  Same bytes as with both mates on
+    the device (BK_HOST_PASSTHROUGH=0) and as the oracle; CR line ends, '+' comments and a last record
+    without EOL included, so that re-framed records shift the parts of the threaded copy."""
+    rnd = random.Random(21)
+    n = 61000
+    heads = [rnd.choice([5, 23, 40]) for _ in range(n)]
+    fq1 = ragged_fastq(rnd, n, 1, plant=[b"ATGCCAT"], head_lens=heads, min_len=30, max_len=60, plus_comment=True)
+    fq2 = ragged_fastq(rnd, n, 2, plant=[b"ATGCCAT"], head_lens=heads, min_len=30, max_len=60, plus_comment=True,
+                       final_newline=False)
+    # sprinkle CR line ends over some records of both mates
+    def crlf_some(fq):
+        recs = bo.read_fastq(fq)
+        out = []
+        for i, r in enumerate(recs):
+            eol = b"\r\n" if i % 97 == 0 else b"\n"
+            out.append(b"@" + r.head + eol + r.seq + eol + b"+" + (r.head if i % 5 == 0 else b"") + eol + r.qual + eol)
+        return b"".join(out)
+    fq1, fq2 = crlf_some(fq1), crlf_some(fq2)[:-1]
+    pat = "^(?P<CB>[ATGCN]{16})atgccat(?P<UMI>[ATGCN]{6})"
+    p1, p2 = (pat, None) if which == "p1" else (None, pat)
+    o1, o2, res = run_pe(fq1, fq2, p1, p2, 1)
+    monkeypatch.setenv("BK_HOST_PASSTHROUGH", "0")
+    d1, d2, res_d = run_pe(fq1, fq2, p1, p2, 1)
+    assert res_d.h2d_bytes > 1.9 * res.h2d_bytes          # the second mate never crossed the bus
+    assert (o1, o2) == (d1, d2)
+    assert (res.n_out, res.n_match1, res.n_match2) == (res_d.n_out, res_d.n_match1, res_d.n_match2)
+    e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, 1, rc_barcodes=False, skip_trimming=False)
+    assert o1 == e1 and o2 == e2
+
+
 def test_empty_and_tiny_inputs():
     ctx = make_ctx("^(?P<UMI>[ATGCN]{4})")
     out, res = ctx.extract_text(b"")
