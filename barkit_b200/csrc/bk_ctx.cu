@@ -757,13 +757,13 @@ int bk_tokenize_device(bk_ctx* ctx, const uint8_t* d_text, uint64_t len, int fin
   }
   if (eff == 0) return BK_OK;
   const uint32_t nblocks = (uint32_t)((eff + bk::kTokChunk - 1) / bk::kTokChunk);
-  int rc = ensure(ctx, &ctx->tok, (size_t)nblocks * 4 + 64);
+  int rc = ensure(ctx, &ctx->tok, (size_t)nblocks * 8 + 128);
   if (rc != BK_OK) return rc;
-  uint32_t* counts = (uint32_t*)((uint8_t*)ctx->tok.p + 64);
   bk::TokResult* d_res = (bk::TokResult*)ctx->tok.p;
-  bk::tok_count_kernel<<<nblocks, bk::kTokThreads, 0, st>>>(d_text, eff, counts);
-  bk::tok_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, d_res);
-  bk::tok_emit_kernel<<<nblocks, bk::kTokThreads, 0, st>>>(d_text, eff, counts, d_rec_off, cap_records);
+  unsigned int* ticket = (unsigned int*)((uint8_t*)ctx->tok.p + 64);
+  unsigned long long* desc = (unsigned long long*)((uint8_t*)ctx->tok.p + 128);
+  bk::tok_init_kernel<<<(nblocks + 255) / 256, 256, 0, st>>>(d_res, desc, nblocks, ticket);
+  bk::tok_fused_kernel<<<nblocks, bk::kTokThreads, 0, st>>>(d_text, eff, d_rec_off, cap_records, desc, ticket, nblocks, d_res);
   CK(cudaGetLastError());
   bk::TokResult r;
   CK(cudaMemcpyAsync(&r, d_res, sizeof r, cudaMemcpyDeviceToHost, st));
@@ -793,8 +793,8 @@ int bk_tokenize_device(bk_ctx* ctx, const uint8_t* d_text, uint64_t len, int fin
     CK(cudaMemcpyAsync(&last_end, d_rec_off + n, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
-  if (n) {
-    bk::tok_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_text, d_rec_off, (uint32_t)n, last_end, d_res);
+  if (have_last_end) {  // the final record without EOL is the one record the single pass did not see the end of
+    bk::tok_check_kernel<<<1, 32, 0, st>>>(d_text, d_rec_off, (uint32_t)n - 1, (uint32_t)n, last_end, d_res);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&r, d_res, sizeof r, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

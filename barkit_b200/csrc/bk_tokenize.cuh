@@ -3,12 +3,11 @@
 // batch can be shipped as raw text and the host tokenizer (bk_fastq.cc, same contract) drops out of
 // the end-to-end path.  A record is four lines; its start is the byte after every fourth newline.
 //
-//   count : newlines per 4 KiB block (16 bytes per thread, SWAR zero-byte test)
-//   scan  : exclusive prefix of the block counts (one CTA)
-//   emit  : newline number g (0-based, text order) with g % 4 == 3 ends record g / 4:
-//           rec_off[g / 4 + 1] = its position + 1
-//   check : one thread per record -- '@' and '+' line starts, seq / qual lengths equal after CR
-//           stripping (the conditions bk_tokenize reports as BK_E_FORMAT), longest record
+// One pass over the text (tok_fused_kernel): newlines per 16 KiB chunk (SWAR zero-byte test), their
+// numbers in the whole text by a decoupled look-back over the chunks, rec_off[g / 4 + 1] = position + 1
+// of every newline g with g % 4 == 3, and the record checks -- '@' and '+' line starts, seq / qual
+// lengths equal after CR stripping (the conditions bk_tokenize reports as BK_E_FORMAT), longest record.
+// tok_check_kernel is the same check one thread per record, used for a final record without EOL.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,7 +15,8 @@
 namespace bk {
 
 constexpr int kTokThreads = 256;
-constexpr uint32_t kTokChunk = kTokThreads * 16u;  // bytes per block
+constexpr int kTokPieces = 4;                                     // 16-byte pieces per thread, kTokThreads * 16 bytes apart
+constexpr uint32_t kTokChunk = kTokThreads * 16u * kTokPieces;  // bytes per block
 
 struct TokResult {
   unsigned long long newlines;  // in the whole text
@@ -64,60 +64,193 @@ __device__ __forceinline__ uint32_t tok_block_sum(uint32_t v, uint32_t* excl) { 
   return total;
 }
 
-__global__ void __launch_bounds__(kTokThreads) tok_count_kernel(const uint8_t* text, uint64_t len, uint32_t* block_count) {
-  const uint64_t pos = (uint64_t)blockIdx.x * kTokChunk + threadIdx.x * 16u;
-  uint32_t excl;
-  const uint32_t total = tok_block_sum(__popc(tok_nl_mask(text, pos, len)), &excl);
-  if (threadIdx.x == 0) block_count[blockIdx.x] = total;
-}
+// ---- single pass: count + scan + emit + check ---------------------------------------------------------
+//
+// One CTA per 16 KiB of text, taken in ticket order.  The chunk is read once (coalesced 16-byte
+// loads, kept in shared memory), every thread turns its 64 contiguous bytes into a newline mask, a
+// block scan numbers the chunk's newlines, a decoupled look-back over the earlier chunks' counts
+// (one 8-byte descriptor per chunk: aggregate, then inclusive prefix) gives the number of the chunk's
+// first newline in the whole text, and the thread that owns newline g with g % 4 == 3 writes
+// rec_off[g / 4 + 1] and validates record g / 4 -- from the chunk when the record's five newlines lie
+// in it, otherwise (one record per chunk boundary) by walking the text backwards in global memory.
+constexpr uint32_t kTokMaxNl = 4096;  // newline positions kept per chunk (more only in malformed text)
+constexpr unsigned long long kTokAgg = 1ull << 62, kTokIncl = 2ull << 62, kTokVal = (1ull << 62) - 1;
 
-// in-place exclusive scan of block_count[0..nblocks); one CTA walks it 1024 entries at a time
-__global__ void __launch_bounds__(1024) tok_scan_kernel(uint32_t* block_count, uint32_t nblocks, TokResult* res) {
-  __shared__ unsigned long long warp_tot[32];
-  __shared__ unsigned long long carry_s;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < nblocks; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const unsigned long long v = i < nblocks ? block_count[i] : 0;
-    unsigned long long incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    unsigned long long wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-    const unsigned long long carry = carry_s;
-    // newline counts beyond 2^32 cannot occur: the text is < 4 GiB
-    if (i < nblocks) block_count[i] = (uint32_t)(carry + wbase + incl - v);
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + wbase + incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    res->newlines = carry_s;
+__global__ void tok_init_kernel(TokResult* res, unsigned long long* desc, uint32_t nblocks, unsigned int* ticket) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nblocks) desc[i] = 0;
+  if (i == 0) {
+    res->newlines = 0;
     res->first_bad = 0xFFFFFFFFu;
     res->max_rec_bytes = 0;
+    *ticket = 0;
   }
 }
 
-__global__ void __launch_bounds__(kTokThreads) tok_emit_kernel(const uint8_t* text, uint64_t len, const uint32_t* block_base,
-                                                               uint32_t* rec_off, uint32_t cap_records) {
-  const uint64_t pos = (uint64_t)blockIdx.x * kTokChunk + threadIdx.x * 16u;
-  uint32_t m = tok_nl_mask(text, pos, len);
-  uint32_t excl;
-  tok_block_sum(__popc(m), &excl);
-  uint32_t g = block_base[blockIdx.x] + excl;  // number of this thread's first newline
-  if (blockIdx.x == 0 && threadIdx.x == 0) rec_off[0] = 0;
-  for (; m; m &= m - 1u, ++g) {
-    if ((g & 3u) == 3u) {
-      const uint32_t rec = (g >> 2) + 1u;
-      if (rec <= cap_records) rec_off[rec] = (uint32_t)(pos + (uint32_t)(__ffs(m) - 1) + 1u);
+// the record [s, p4] with line ends p1 < p2 < p3 < p4, bytes through `at`: the BK_E_FORMAT conditions of bk_tokenize
+template <class At>
+__device__ __forceinline__ bool tok_record_ok(At at, uint64_t s, uint64_t p1, uint64_t p2, uint64_t p3, uint64_t p4) {
+  uint64_t sl = p2 - (p1 + 1), ql = p4 - (p3 + 1);
+  if (sl && at(p2 - 1) == '\r') --sl;
+  if (ql && at(p4 - 1) == '\r') --ql;
+  return at(s) == '@' && at(p2 + 1) == '+' && sl == ql;
+}
+
+__global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* text, uint64_t len, uint32_t* rec_off,
+                                                                 uint32_t cap_records, unsigned long long* desc,
+                                                                 unsigned int* ticket, uint32_t nblocks, TokResult* res) {
+  __shared__ uint4 chunk[kTokChunk / 16];
+  __shared__ uint16_t nlpos[kTokMaxNl];
+  __shared__ uint32_t s_bid;
+  __shared__ unsigned long long s_base;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t bid = s_bid;
+  const uint64_t cbase = (uint64_t)bid * kTokChunk;
+#pragma unroll
+  for (int i = 0; i < kTokPieces; ++i) {
+    const uint64_t pos = cbase + ((uint64_t)i * kTokThreads + threadIdx.x) * 16u;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (pos < len) v = *reinterpret_cast<const uint4*>(text + pos);  // 16-byte aligned, >= 16 bytes of slack behind len
+    chunk[i * kTokThreads + threadIdx.x] = v;
+  }
+  __syncthreads();
+  // this thread's 64 contiguous bytes: chunk bytes [64 t, 64 t + 64)
+  unsigned long long m = 0;
+  {
+    const uint64_t tpos = cbase + (uint64_t)threadIdx.x * 64u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 v = chunk[threadIdx.x * 4 + j];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t mm = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t x = w[i] ^ 0x0A0A0A0Au;
+        const uint32_t z = (~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u) >> 7;  // 1 in bit 0 of every '\n' byte
+        mm |= ((z * 0x01020408u) >> 24) << (4 * i);  // the four flags gathered into a nibble
+      }
+      m |= (unsigned long long)mm << (16 * j);
     }
+    // bytes at or behind len do not count (zero-filled pieces have no newline; only a piece straddling len needs the mask)
+    if (tpos + 64u > len) m = tpos >= len ? 0ull : m & ((1ull << (len - tpos)) - 1ull);
+  }
+  uint32_t excl;
+  const uint32_t total = tok_block_sum(__popcll(m), &excl);
+  // ---- number of the chunk's first newline: decoupled look-back (warp 0) ----------------------------------
+  if (threadIdx.x < 32) {
+    if (lane == 0) {
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(desc + bid), "l"((bid == 0 ? kTokIncl : kTokAgg) | total) : "memory");
+    }
+    unsigned long long ex = 0;
+    if (bid > 0) {
+      int look = (int)bid - 1;
+      while (true) {
+        unsigned long long d = kTokIncl;  // chunks before 0 read as "prefix 0"
+        if (look - lane >= 0) {
+          do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(d) : "l"(desc + (look - lane)) : "memory");
+          } while ((d >> 62) == 0);
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+        const int first = pm ? __ffs(pm) - 1 : 32;
+        unsigned long long part = lane <= first ? (d & kTokVal) : 0ull;  // aggregates up to and including the nearest prefix
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        ex += part;
+        if (pm) break;
+        look -= 32;
+      }
+      if (lane == 0)
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(desc + bid), "l"(kTokIncl | (ex + total)) : "memory");
+    }
+    if (lane == 0) {
+      s_base = ex;
+      if (bid == nblocks - 1) res->newlines = ex + total;
+      if (bid == 0) rec_off[0] = 0;
+    }
+  }
+  // ---- newline positions of the chunk, record ends --------------------------------------------------------
+  {
+    uint32_t k = excl;
+    for (unsigned long long mm = m; mm; mm &= mm - 1ull, ++k)
+      if (k < kTokMaxNl) nlpos[k] = (uint16_t)(threadIdx.x * 64u + (uint32_t)(__ffsll((long long)mm) - 1));
+  }
+  __syncthreads();
+  const unsigned long long base = s_base;
+  uint32_t bad = 0xFFFFFFFFu, longest = 0;
+  uint32_t k = excl;
+  for (unsigned long long mm = m; mm; mm &= mm - 1ull, ++k) {
+    const unsigned long long g = base + k;
+    if ((g & 3ull) != 3ull) continue;
+    const uint64_t p4 = cbase + threadIdx.x * 64u + (uint32_t)(__ffsll((long long)mm) - 1);
+    const unsigned long long rec = g >> 2;
+    if (rec + 1 <= cap_records) rec_off[rec + 1] = (uint32_t)(p4 + 1);
+    if (rec >= cap_records) continue;
+    bool ok;
+    uint64_t s;
+    if (k < kTokMaxNl && (k >= 4 || g == 3)) {  // the whole record lies in this chunk
+      const uint64_t p1 = cbase + nlpos[k - 3], p2 = cbase + nlpos[k - 2], p3 = cbase + nlpos[k - 1];
+      s = g == 3 ? 0 : cbase + nlpos[k - 4] + 1u;
+      const uint8_t* cb = reinterpret_cast<const uint8_t*>(chunk);
+      ok = tok_record_ok([&](uint64_t p) { return (uint32_t)cb[p - cbase]; }, s, p1, p2, p3, p4);
+    } else if (k < 4) {
+      continue;  // the record began in an earlier chunk: warp 0 looks at it below
+    } else {  // more newlines in one chunk than nlpos holds (records of a few bytes): walk back bytewise
+      uint64_t q[4] = {0, 0, 0, 0};  // p3, p2, p1, p0
+      int found = 0;
+      uint64_t p = p4;
+      while (p > 0 && found < 4) {
+        --p;
+        if (text[p] == '\n') q[found++] = p;
+      }
+      s = found == 4 ? q[3] + 1 : 0;
+      ok = found >= 3 && tok_record_ok([&](uint64_t x) { return (uint32_t)text[x]; }, s, q[2], q[1], q[0], p4);
+    }
+    if (!ok && (uint32_t)rec < bad) bad = (uint32_t)rec;
+    longest = max(longest, (uint32_t)(p4 + 1 - s));
+  }
+  // ---- the record that straddles the chunk's start: its end is the chunk's newline kb < 4, its other
+  // newlines are the chunk's first kb and the last 4 - kb before the chunk.  Warp 0 finds those together,
+  // 512 bytes of text per step (one L2 round trip), instead of one thread walking ~300 dependent bytes.
+  if (threadIdx.x < 32 && bid > 0) {
+    const uint32_t kb = (3u - (uint32_t)(base & 3ull)) & 3u;
+    const unsigned long long rec = (base + kb) >> 2;
+    if (kb < total && rec < cap_records) {  // (warp-uniform)
+      uint64_t before[4];  // the four newlines before the record's last one, nearest first
+      uint32_t found = 0;
+      for (; found < kb; ++found) before[found] = cbase + nlpos[kb - 1u - found];
+      uint64_t wend = cbase;
+      while (found < 4u && wend > 0) {
+        const uint64_t wstart = wend >= 512u ? wend - 512u : 0u;  // cbase is a multiple of 512
+        uint32_t mm = 0;
+        const uint64_t pos = wstart + 16u * lane;
+        if (pos < wend) mm = tok_nl_mask(text, pos, wend);
+        for (int l = 31; l >= 0 && found < 4u; --l) {  // every lane keeps the same list
+          uint32_t ml = __shfl_sync(0xffffffffu, mm, l);
+          while (ml && found < 4u) {
+            const uint32_t bit = 31u - (uint32_t)__clz(ml);
+            before[found++] = wstart + 16u * l + bit;
+            ml &= ~(1u << bit);
+          }
+        }
+        wend = wstart;
+      }
+      if (lane == 0) {
+        const uint64_t p4 = cbase + nlpos[kb];
+        const uint64_t s = found == 4u ? before[3] + 1 : 0;
+        const bool ok = found == 4u && tok_record_ok([&](uint64_t x) { return (uint32_t)text[x]; }, s, before[2], before[1], before[0], p4);
+        if (!ok && (uint32_t)rec < bad) bad = (uint32_t)rec;
+        longest = max(longest, (uint32_t)(p4 + 1 - s));
+      }
+    }
+  }
+  bad = __reduce_min_sync(0xffffffffu, bad);
+  longest = __reduce_max_sync(0xffffffffu, longest);
+  if (lane == 0) {
+    if (bad != 0xFFFFFFFFu) atomicMin(&res->first_bad, bad);
+    if (longest > *reinterpret_cast<volatile unsigned int*>(&res->max_rec_bytes)) atomicMax(&res->max_rec_bytes, longest);
   }
 }
 
@@ -127,13 +260,14 @@ __device__ __forceinline__ uint32_t tok_find_nl(const uint8_t* text, uint32_t b,
   return b;
 }
 
-__global__ void tok_check_kernel(const uint8_t* text, const uint32_t* rec_off, uint32_t n, uint32_t last_end,
+// records [first, n) one thread each (the general form of the check: used for a final record without EOL)
+__global__ void tok_check_kernel(const uint8_t* text, const uint32_t* rec_off, uint32_t first, uint32_t n, uint32_t last_end,
                                  TokResult* res) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const uint32_t b = rec_off[r], e = r + 1 == n ? last_end : rec_off[r + 1];
-  bool ok = e > b && text[b] == '@';
-  if (ok) {
+  const uint32_t r = first + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < n;
+  const uint32_t b = live ? rec_off[r] : 0, e = !live ? 0 : r + 1 == n ? last_end : rec_off[r + 1];
+  bool ok = !live || (e > b && text[b] == '@');
+  if (ok && live) {
     const uint32_t nl1 = tok_find_nl(text, b, e);
     const uint32_t sb = nl1 + 1 < e ? nl1 + 1 : e;
     // the writer's own framing `seq LF + LF qual LF` in closed form first, the general scan otherwise
@@ -153,8 +287,13 @@ __global__ void tok_check_kernel(const uint8_t* text, const uint32_t* rec_off, u
       ok = nl2 < e && nl3 < e && pb < e && text[pb] == '+' && sl == ql;
     }
   }
-  if (!ok) atomicMin(&res->first_bad, r);
-  atomicMax(&res->max_rec_bytes, e - b);
+  // one atomic per warp, and only when it changes the result
+  const uint32_t bad = __reduce_min_sync(0xffffffffu, ok ? 0xFFFFFFFFu : r);
+  const uint32_t longest = __reduce_max_sync(0xffffffffu, e - b);
+  if ((threadIdx.x & 31) == 0) {
+    if (bad != 0xFFFFFFFFu) atomicMin(&res->first_bad, bad);
+    if (longest > *reinterpret_cast<volatile unsigned int*>(&res->max_rec_bytes)) atomicMax(&res->max_rec_bytes, longest);
+  }
 }
 
 }  // namespace bk
