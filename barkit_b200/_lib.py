@@ -98,6 +98,7 @@ SYMBOLS = {
     "bk_tokenize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, u32p,
                                      C.POINTER(C.c_uint64), u32p]),
     "bk_kernel_variant": (C.c_int, [C.c_void_p]),
+    "bk_program_nvariants": (C.c_int, [C.c_void_p]),
     "bk_debug_events": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bk_reverse_complement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "bk_generate_device": (C.c_int, [C.c_void_p, C.POINTER(SynConfig), C.c_int, C.c_uint64, C.c_uint64,
@@ -167,6 +168,10 @@ class Program:
     def barcode_types(self):
         return [lib.bk_program_cap_name(self.handle, i).decode()
                 for i in range(lib.bk_program_ncaps(self.handle))]
+
+    def nvariants(self) -> int:
+        """Fixed-length programs the pattern lowers to (1 unless it has {m,n} / ? repetition)."""
+        return lib.bk_program_nvariants(self.handle)
 
     def info(self) -> ProgramInfo:
         info = ProgramInfo()

@@ -14,6 +14,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "../../include/barkit_b200.h"
 #include "bk_internal.h"
@@ -76,6 +77,10 @@ struct bk_ctx {
   uint32_t flags = 0;
   bool paired = false;
   bk_devprog prog[2];
+  // bounded variable repetition: a mate's pattern as several fixed-length programs (prog[m] is the first)
+  std::vector<bk_devprog> var[2];
+  DevBuf vdev[2];          // ... and their copy in device memory (nullptr when there is one variant)
+  uint32_t growth[2] = {0, 0};  // largest header growth over the variants
   int sm_count = 0;
   Slot slot[kSlots];
   DevBuf tok;  // bk_tokenize_device scratch: block counts + TokResult
@@ -131,7 +136,7 @@ size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_
   int nm = ctx->paired ? 2 : 1;
   for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
   for (int m = 0; m < nm; ++m) {
-    uint32_t growth = ctx->prog[m].present ? ctx->prog[m].hdr_growth : 0;
+    uint32_t growth = ctx->prog[m].present ? ctx->growth[m] : 0;
     in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
     out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
     total += bk::kStages * (size_t)in_cap[m] + out_cap[m];
@@ -140,14 +145,17 @@ size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_
 }
 
 // extract_kernel<PAIRED, GENERAL>: GENERAL iff a pattern needs a search (not anchored) or -r is set
+bool has_variants(const bk_ctx* ctx) { return ctx->var[0].size() > 1 || ctx->var[1].size() > 1; }
+
 bool needs_general(const bk_ctx* ctx) {
   if (ctx->flags & BK_FLAG_RC) return true;
+  if (has_variants(ctx)) return true;
   for (int m = 0; m < 2; ++m)
     if (ctx->prog[m].present && !ctx->prog[m].anchor_start && !ctx->prog[m].anchor_end) return true;
   return false;
 }
 
-template <bool PAIRED, bool GENERAL>
+template <bool PAIRED, bool GENERAL, bool VAR = false>
 int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
   uint32_t R = bk::kTileRecs;
   // prefer several resident tiles per SM; never go below 8 records unless a tile would not fit
@@ -160,12 +168,12 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   lp->tile_recs = R;
   lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap);
   lp->ntiles = (n + R - 1) / R;
-  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)lp->smem));
-  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL>, bk::cta_warps(PAIRED) * 32, lp->smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR>, bk::cta_warps(PAIRED) * 32, lp->smem));
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
@@ -214,7 +222,7 @@ size_t smem_for5(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32
   int nm = ctx->paired ? 2 : 1;
   for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
   for (int m = 0; m < nm; ++m) {
-    uint32_t growth = ctx->prog[m].present ? ctx->prog[m].hdr_growth : 0;
+    uint32_t growth = ctx->prog[m].present ? ctx->growth[m] : 0;
     in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
     out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
     total += bk::v5::kData * (size_t)in_cap[m] + out_cap[m];
@@ -285,7 +293,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   LaunchPlan lp;
   const bool general = needs_general(ctx);
   const bool v5 = variant == 5 && v5_eligible(ctx);
+  const bool var = has_variants(ctx);
   int rc = v5 ? (ctx->paired ? plan_launch5<true>(ctx, n, maxrec, &lp) : plan_launch5<false>(ctx, n, maxrec, &lp))
+           : var ? (ctx->paired ? plan_launch<true, true, true>(ctx, n, maxrec, &lp) : plan_launch<false, true, true>(ctx, n, maxrec, &lp))
            : ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))
                        : (general ? plan_launch<false, true>(ctx, n, maxrec, &lp) : plan_launch<false, false>(ctx, n, maxrec, &lp));
   if (rc != BK_OK) return rc;
@@ -304,6 +314,8 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     P.text_len[m] = (uint32_t)in[m]->text_len;
     P.in_cap[m] = lp.in_cap[m];
     P.out_cap[m] = lp.out_cap[m];
+    P.nvar[m] = (uint32_t)ctx->var[m].size();
+    P.vprog[m] = (const bk_devprog*)ctx->vdev[m].p;
   }
   P.out[0] = out1; P.out[1] = out2;
   P.cap[0] = cap1; P.cap[1] = cap2;
@@ -323,6 +335,10 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
       bk::v5::extract_kernel5<true><<<lp.grid, bk::v5::cta_warps(true) * 32, lp.smem, stream>>>(P);
     else if (v5)
       bk::v5::extract_kernel5<false><<<lp.grid, bk::v5::cta_warps(false) * 32, lp.smem, stream>>>(P);
+    else if (var && ctx->paired)
+      bk::extract_kernel<true, true, true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
+    else if (var)
+      bk::extract_kernel<false, true, true><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
     else if (ctx->paired && general)
       bk::extract_kernel<true, true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
     else if (ctx->paired)
@@ -398,8 +414,24 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
   ctx->paired = (flags & BK_FLAG_PAIRED) != 0;
   ctx->sm_count = prop.multiProcessorCount;
   memset(ctx->prog, 0, sizeof ctx->prog);
-  if (p1) ctx->prog[0] = p1->prog.dev;
-  if (p2) ctx->prog[1] = p2->prog.dev;
+  const bk_program* pp[2] = {p1, p2};
+  for (int m = 0; m < 2; ++m) {
+    if (!pp[m]) continue;
+    ctx->prog[m] = pp[m]->prog.dev;
+    ctx->var[m] = pp[m]->prog.variants;
+    if (ctx->var[m].empty()) ctx->var[m].push_back(pp[m]->prog.dev);
+    for (const bk_devprog& v : ctx->var[m]) ctx->growth[m] = std::max(ctx->growth[m], v.hdr_growth);
+    if (ctx->var[m].size() > 1) {
+      const size_t bytes = ctx->var[m].size() * sizeof(bk_devprog);
+      if (cudaMalloc(&ctx->vdev[m].p, bytes) != cudaSuccess ||
+          cudaMemcpy(ctx->vdev[m].p, ctx->var[m].data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        std::string msg = std::string("CUDA error uploading the pattern's variants: ") + cudaGetErrorString(cudaGetLastError());
+        bk_ctx_destroy(ctx);
+        return fail(BK_E_CUDA, msg);
+      }
+      ctx->vdev[m].cap = bytes;
+    }
+  }
   for (int i = 0; i < kSlots; ++i) {
     Slot& s = ctx->slot[i];
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -422,6 +454,9 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
     solo->sm_count = ctx->sm_count;
     memset(solo->prog, 0, sizeof solo->prog);
     solo->prog[0] = ctx->prog[1 - ctx->pass_mate];
+    solo->var[0] = ctx->var[1 - ctx->pass_mate];
+    solo->vdev[0] = ctx->vdev[1 - ctx->pass_mate];  // (shared, owned by ctx)
+    solo->growth[0] = ctx->growth[1 - ctx->pass_mate];
     ctx->solo = solo;
     const char* ht = getenv("BK_HOST_THREADS");
     int nt = ht ? atoi(ht) : (int)std::thread::hardware_concurrency();
@@ -455,6 +490,8 @@ void bk_ctx_destroy(bk_ctx* ctx) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   if (ctx->tok.p) cudaFree(ctx->tok.p);
+  for (int m = 0; m < 2; ++m)
+    if (ctx->vdev[m].p) cudaFree(ctx->vdev[m].p);
   delete ctx->solo;
   delete ctx;
 }
@@ -476,7 +513,7 @@ uint64_t bk_out_bound(const bk_ctx* ctx, int mate, uint32_t n, uint64_t text_len
   if (!ctx || mate < 1 || mate > 2) return 0;
   const bk_devprog& pg = ctx->prog[mate - 1];
   // out record <= in record + 1 (a final record without EOL gains one) + header growth
-  return text_len + (uint64_t)n * ((pg.present ? pg.hdr_growth : 0) + 1) + 16;
+  return text_len + (uint64_t)n * ((pg.present ? ctx->growth[mate - 1] : 0) + 1) + 16;
 }
 
 int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2) {

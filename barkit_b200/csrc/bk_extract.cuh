@@ -163,8 +163,12 @@ constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + 
 // GENERAL = false: every pattern is anchored and there is no reverse-complement retry -- the common
 // case, compiled without the search code, because every kilobyte of this kernel competes for the
 // SM's instruction cache.
-template <bool PAIRED, bool GENERAL>
+// VAR (only with GENERAL): a mate's pattern may be a list of fixed-length variants (bounded variable
+// repetition, bk_pattern.cc); the matched variant travels with the match start (start | variant << 24) and
+// supplies the capture offsets, the match length and the header growth of that record.
+template <bool PAIRED, bool GENERAL, bool VAR = false>
 __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(const __grid_constant__ KParams P) {
+  static_assert(!VAR || GENERAL, "variants are matched by the general kernel");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
   __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_empty[2][kStages];
@@ -328,7 +332,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
     const bool un_me = pg.present && !pg.anchor_start && !pg.anchor_end;
     const bk_devprog& pgo = P.prog[PAIRED ? m ^ 1 : m];
     const bool un_other = PAIRED && pgo.present && !pgo.anchor_start && !pgo.anchor_end;
-    const bool split = GENERAL && PAIRED && !rc && un_me != un_other;
+    const bool var_me = VAR && P.nvar[m] > 1u;
+    const bool split = GENERAL && !VAR && PAIRED && !rc && un_me != un_other;
     const uint32_t tab_other = smem_u32(&cls_tab[PAIRED ? m ^ 1 : m][0]);
     for (uint32_t k = fp;; k += kFrontPairs) {
       const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
@@ -354,7 +359,12 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         __syncwarp();
         if (m == 0) { EVT(tile, 4) }
         const bool can = active && pg.present && rv.qual_len == rv.seq_len;  // unequal lengths never leave bk_tokenize
-        if (GENERAL && un_me) {
+        if (VAR && var_me) {  // (lane per read, bytewise: see match_variants)
+          if (can) {
+            ms = match_variants<false>(P.vprog[m], P.nvar[m], tab, rv.seq, rv.seq_len);
+            if (ms < 0 && rc) ms = match_variants<true>(P.vprog[m], P.nvar[m], tab, rv.seq, rv.seq_len);
+          }
+        } else if (GENERAL && un_me) {
           if (split) {  // lower half here, upper half on the other mate's front warp
             s_share[fp][xb][0][lane] = rv.seq;
             s_share[fp][xb][1][lane] = rv.seq_len;
@@ -365,7 +375,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         } else if (can) {
           ms = match_read<false>(tab, rv.seq, rv.seq_len);  // lane per read
         }
-        if (GENERAL && can && ms < 0 && rc) ms = match_read<true>(tab, rv.seq, rv.seq_len);  // parse.rs:61-66
+        if (GENERAL && !(VAR && var_me) && can && ms < 0 && rc) ms = match_read<true>(tab, rv.seq, rv.seq_len);  // parse.rs:61-66
       } else {
         if (lane == 0) atomicOr(&P.result->error, 2u);
         if (GENERAL && split && un_me) {  // keep the pair's barriers in step: nothing to search
@@ -394,12 +404,13 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
           if (un_me) { if (!too_big) ms = h; } else if (ms_other != kSkipTile) ms_other = h;
         }
       }
-      if (!too_big && active && P.match[m]) P.match[m][r0 + lane] = ms;
+      if (!too_big && active && P.match[m]) P.match[m][r0 + lane] = (VAR && ms >= 0) ? (ms & 0xFFFFFF) : ms;
       // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
       const bool keep = !skip && active && (ms >= 0 || ms_other >= 0);
 
       // ---- size + scan, publish the aggregate -------------------------------------------------------
-      const uint32_t olen = keep ? out_bytes(pg, rv, ms, trim) : 0;
+      const bk_devprog& pe = (VAR && var_me && ms >= 0) ? P.vprog[m][ms >> 24] : pg;  // the record's variant
+      const uint32_t olen = keep ? out_bytes(pe, rv, ms, trim) : 0;
       uint32_t incl = olen;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -501,7 +512,9 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         const uint32_t qf = tm.qual_len_fast[lane];
         rv.qual_len = qf >> 1;
         rv.fast = qf & 1u;
-        const int ms = tm.ms[lane];
+        const int msv = tm.ms[lane];
+        const int ms = (VAR && msv >= 0) ? (msv & 0xFFFFFF) : msv;
+        const bk_devprog& pe = (VAR && msv >= 0 && P.nvar[m] > 1u) ? P.vprog[m][msv >> 24] : pg;
         const uint32_t dst = out_s + phase + ooff;
         // lane per record, warp per part: part bj of every rewritten record (and of a record in foreign
         // framing: CR line ends, text after '+') through the stream writer
@@ -510,7 +523,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
         const uint32_t nxt = __shfl_down_sync(0xffffffffu, ooff, 1);
         const bool even = kept && lane < 31 && nxt != kNotKept && ((nxt - ooff) & 31u) == 0;
         const uint32_t rot = __popc(__ballot_sync(0xffffffffu, even)) >= 8 ? ((uint32_t)lane & 7u) + 1u : 0u;
-        if (kept && !unc) emit_part(pg, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
+        if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
         // warp per pass: maximal runs of consecutive unchanged records
         const unsigned um = __ballot_sync(0xffffffffu, unc);
         if (um) {

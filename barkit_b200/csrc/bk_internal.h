@@ -19,8 +19,11 @@ struct FuzzySpan {   // a `( alt | alt | ... )` group produced by the expansion,
 };
 
 struct Program {
-  bk_devprog dev;
+  bk_devprog dev;        // the first (highest-priority) fixed-length program
   std::string expanded;  // what the reference would pass to Regex::new (pattern.rs:182)
+  // Bounded variable repetition ({m,n}, ?) lowers to one fixed-length program per length combination, in
+  // the regex crate's backtracking order; a fixed-length pattern has exactly one (== dev).
+  std::vector<bk_devprog> variants;
 };
 
 std::vector<Span> find_fuzzy_runs(const std::string& pattern);

@@ -53,6 +53,10 @@ struct KParams {
   uint32_t in_cap[2];  // shared-memory bytes for the staged input / assembled output per mate
   uint32_t out_cap[2];
   uint32_t flags;
+  // Bounded variable repetition (bk_pattern.cc): a mate's pattern as nvar > 1 fixed-length programs in
+  // priority order, in device memory (prog[m] is the first).  Only extract_kernel<.., true, true> reads them.
+  uint32_t nvar[2];
+  const bk_devprog* vprog[2];
 };
 
 constexpr unsigned long long kFlagAgg = 1ull << 62;
@@ -423,6 +427,54 @@ __device__ __noinline__ int match_read(uint32_t tab, uint32_t seq, uint32_t L) {
       if (match_at<RC, true>(tab, seq, L, s)) return (int)s;
   }
   return -1;
+}
+
+// ---- variable repetition: a program given as a list of fixed-length variants ------------------------------
+//
+// Leftmost-first over the variants = smallest start at which any variant matches, and among the variants
+// matching there the first in the list (the regex crate's backtracking order, bk_pattern.cc).  The variants
+// live in global memory and are evaluated bytewise, one lane per read: this path widens what is accepted;
+// it is not tuned.
+template <bool RC>
+__device__ __forceinline__ bool match_at_variant(const bk_devprog& pv, uint32_t tab, uint32_t seq, uint32_t L, uint32_t s) {
+  for (uint32_t o = 0; o < pv.nops; ++o) {
+    const bk_op op = pv.ops[o];
+    const uint32_t base = s + op.off;
+    if (op.kind == BK_OP_LIT) {
+      uint32_t mism = 0, bad = 0;
+      for (uint32_t i = 0; i < op.len; ++i) {
+        const uint32_t c = fetch<RC>(tab, seq, L, base + i);
+        const uint32_t ne = (c != pv.lit[op.idx + i]);
+        mism += ne;
+        bad |= ne & (uint32_t)((c >= 0x80u) | (c == '\n'));
+      }
+      if (mism > op.k || bad) return false;
+    } else {
+      for (uint32_t i = 0; i < op.len; ++i) {
+        const uint32_t c = fetch<RC>(tab, seq, L, base + i);
+        if (c >= 128u || !((pv.cls[op.idx][c >> 5] >> (c & 31u)) & 1u)) return false;
+      }
+    }
+  }
+  return true;
+}
+
+// -> match start (or -1) and the variant that matched, packed as start | variant << 24
+template <bool RC>
+__device__ __noinline__ int match_variants(const bk_devprog* vp, uint32_t nvar, uint32_t tab, uint32_t seq, uint32_t L) {
+  uint32_t best = 0xFFFFFFFFu;
+  for (uint32_t v = 0; v < nvar; ++v) {
+    const bk_devprog& pv = vp[v];
+    const uint32_t T = pv.total_len;
+    if (L < T) continue;
+    uint32_t s0 = 0, s1 = L - T;  // candidate starts
+    if (pv.anchor_start && pv.anchor_end) { if (L != T) continue; }
+    else if (pv.anchor_start) s1 = 0;
+    else if (pv.anchor_end) s0 = s1;
+    for (uint32_t s = s0; s <= s1 && s < (best & 0xFFFFFFu); ++s)  // a later variant only wins with a smaller start
+      if (match_at_variant<RC>(pv, tab, seq, L, s)) { best = s | (v << 24); break; }
+  }
+  return (int)best;  // 0xFFFFFFFF = -1: no variant matches
 }
 
 // Unanchored forward search, one warp per read: the 32 lanes test 32 consecutive candidate starts

@@ -378,7 +378,7 @@ struct Lowering {
 
 }  // namespace
 
-int compile(const std::string& pattern, size_t max_error, Program* prog, std::string* err) {
+static int compile_fixed(const std::string& pattern, size_t max_error, Program* prog, std::string* err) {
   std::vector<FuzzySpan> spans;
   std::string expanded;
   int rc = expand(pattern, max_error, &expanded, &spans, err);
@@ -479,6 +479,148 @@ int compile(const std::string& pattern, size_t max_error, Program* prog, std::st
   return BK_OK;
 }
 
+// ---- bounded variable repetition -------------------------------------------------
+//
+// `X{m,n}` and `X?` on a class, `.` or a literal byte (greedy, or lazy with a trailing `?`).  The regex
+// crate resolves them by backtracking: the first quantifier tries its lengths in priority order
+// (longest first when greedy), for each of them the second one does, and so on; the first combination
+// under which the rest of the pattern matches wins (pattern.rs:225-230, leftmost-first).  Every
+// combination is a fixed-length pattern, so the pattern is lowered to the list of those fixed-length
+// programs IN THAT ORDER, and the kernel takes, among the smallest match starts, the first program
+// that matches there.  Unbounded repetition (`*`, `+`, `{m,}`) and quantified groups are refused.
+
+namespace {
+
+struct Quant {
+  size_t begin, end;  // the quantifier's text in the pattern
+  long lo, hi;
+  bool lazy;
+};
+
+int find_quantifiers(const std::string& p, std::vector<Quant>* out, std::string* err) {
+  auto unsupported = [&](const std::string& what) {
+    *err = "unsupported pattern construct (" + what + "): repetition must be {n}, {m,n} or ? on a class, `.` or a "
+           "literal, with at most " + std::to_string(BK_MAX_VARIANTS) + " length combinations";
+    return BK_E_UNSUPPORTED;
+  };
+  bool in_class = false;
+  size_t class_open = 0;
+  char prev = 0;  // last character of the atom before position i (outside classes)
+  for (size_t i = 0; i < p.size();) {
+    const char c = p[i];
+    if (in_class) {
+      const bool first = i == class_open + 1 || (i == class_open + 2 && p[class_open + 1] == '^');
+      if (c == ']' && !first) { in_class = false; prev = ']'; }
+      ++i;
+      continue;
+    }
+    if (c == '\\') { i += 2; prev = 'x'; continue; }  // (refused by the lowering)
+    if (c == '[') { in_class = true; class_open = i; ++i; continue; }
+    if (c == '(') {
+      ++i;
+      if (i < p.size() && p[i] == '?') {  // group flags are not quantifiers
+        if (p.compare(i, 3, "?P<") == 0 || (p.compare(i, 2, "?<") == 0 && i + 2 < p.size() && p[i + 2] != '=' && p[i + 2] != '!')) {
+          while (i < p.size() && p[i] != '>') ++i;
+          if (i < p.size()) ++i;
+        } else {
+          i += 2;
+        }
+      }
+      prev = '(';
+      continue;
+    }
+    if (c == '*' || c == '+') return unsupported(std::string("unbounded repetition ") + c);
+    if (c == '?' || c == '{') {
+      Quant q{i, i, 0, 0, false};
+      if (c == '?') {
+        q.lo = 0; q.hi = 1; q.end = i + 1;
+      } else {
+        size_t j = i + 1;
+        long lo = 0, hi = 0;
+        size_t d1 = 0, d2 = 0;
+        while (j < p.size() && p[j] >= '0' && p[j] <= '9' && lo < 100000) { lo = lo * 10 + (p[j] - '0'); ++j; ++d1; }
+        if (d1 == 0 || j >= p.size() || p[j] != ',') { i = j; prev = '}'; continue; }  // {n} or malformed: the lowering's business
+        ++j;
+        while (j < p.size() && p[j] >= '0' && p[j] <= '9' && hi < 100000) { hi = hi * 10 + (p[j] - '0'); ++j; ++d2; }
+        if (d2 == 0) return unsupported("unbounded repetition {m,}");
+        if (j >= p.size() || p[j] != '}') { *err = "Regex error: unclosed counted repetition"; return BK_E_PATTERN; }
+        if (hi < lo) { *err = "Regex error: invalid repetition count range, the start must be <= the end"; return BK_E_PATTERN; }
+        q.lo = lo; q.hi = hi; q.end = j + 1;
+      }
+      if (prev == ')' || prev == '(' || prev == 0 || prev == '^') {
+        if (prev == ')') return unsupported("variable repetition of a group");
+        *err = "Regex error: repetition operator missing expression";
+        return BK_E_PATTERN;
+      }
+      if (q.end < p.size() && p[q.end] == '?') { q.lazy = true; ++q.end; }
+      if (q.end < p.size() && (p[q.end] == '?' || p[q.end] == '*' || p[q.end] == '+' || p[q.end] == '{'))
+        return unsupported("stacked repetition");
+      out->push_back(q);
+      i = q.end;
+      prev = '}';
+      continue;
+    }
+    prev = c;
+    ++i;
+  }
+  return BK_OK;
+}
+
+}  // namespace
+
+int compile(const std::string& pattern, size_t max_error, Program* prog, std::string* err) {
+  std::vector<Quant> qs;
+  int rc = find_quantifiers(pattern, &qs, err);
+  if (rc != BK_OK) return rc;
+  prog->variants.clear();
+  if (qs.empty()) {
+    rc = compile_fixed(pattern, max_error, prog, err);
+    if (rc == BK_OK) prog->variants.push_back(prog->dev);
+    return rc;
+  }
+  size_t total = 1;
+  for (const auto& q : qs) {
+    total *= (size_t)(q.hi - q.lo + 1);
+    if (total > BK_MAX_VARIANTS) {
+      *err = "unsupported pattern construct (variable repetition): more than " + std::to_string(BK_MAX_VARIANTS) +
+             " length combinations";
+      return BK_E_UNSUPPORTED;
+    }
+  }
+  // the expanded text the reference would hand to Regex::new keeps its quantifiers (pattern.rs:93-109)
+  {
+    std::vector<FuzzySpan> spans;
+    rc = expand(pattern, max_error, &prog->expanded, &spans, err);
+    if (rc != BK_OK) return rc;
+  }
+  const std::string expanded = prog->expanded;
+  std::vector<long> len(qs.size());
+  for (size_t i = 0; i < qs.size(); ++i) len[i] = qs[i].lazy ? qs[i].lo : qs[i].hi;
+  for (size_t v = 0; v < total; ++v) {
+    std::string fixed;
+    size_t at = 0;
+    for (size_t i = 0; i < qs.size(); ++i) {
+      fixed.append(pattern, at, qs[i].begin - at);
+      fixed += "{" + std::to_string(len[i]) + "}";
+      at = qs[i].end;
+    }
+    fixed.append(pattern, at, std::string::npos);
+    Program one;
+    rc = compile_fixed(fixed, max_error, &one, err);
+    if (rc != BK_OK) return rc;
+    prog->variants.push_back(one.dev);
+    // next combination in backtracking order: the LAST quantifier moves first
+    for (size_t i = qs.size(); i-- > 0;) {
+      const long step = qs[i].lazy ? 1 : -1, last = qs[i].lazy ? qs[i].hi : qs[i].lo;
+      if (len[i] != last) { len[i] += step; break; }
+      len[i] = qs[i].lazy ? qs[i].lo : qs[i].hi;
+    }
+  }
+  prog->dev = prog->variants[0];
+  prog->expanded = expanded;
+  return BK_OK;
+}
+
 }  // namespace bk
 
 // ---- C ABI ---------------------------------------------------------------------------------------
@@ -550,6 +692,8 @@ const char* bk_program_cap_name(const bk_program* p, int i) {
   if (c.name_len == 3) return "UMI";
   return c.name[0] == 'C' ? "CB" : "SB";
 }
+
+int bk_program_nvariants(const bk_program* p) { return p ? (int)p->prog.variants.size() : 0; }
 
 int bk_program_get_info(const bk_program* p, bk_program_info* info) {
   if (!p || !info) return BK_E_ARG;

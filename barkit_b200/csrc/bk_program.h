@@ -13,6 +13,7 @@
 #define BK_MAX_LIT 512
 #define BK_MAX_CAPS 3
 #define BK_MAX_TOTAL_LEN 4096
+#define BK_MAX_VARIANTS 24
 
 enum : uint8_t {
   BK_OP_CLASS = 0,  // every byte of the run must be in class `idx`

@@ -61,6 +61,11 @@ void bk_program_destroy(bk_program* p);
 int bk_program_ncaps(const bk_program* p);
 const char* bk_program_cap_name(const bk_program* p, int i); /* "UMI" | "CB" | "SB" */
 
+/* Bounded variable repetition (`X{m,n}`, `X?` on a class, `.` or a literal; lazy forms too) lowers to one
+ * fixed-length program per length combination, in the regex crate's backtracking order (pattern.rs:182,
+ * :225-230); a fixed-length pattern has 1.  bk_program_get_info / bk_program_dump describe the first. */
+int bk_program_nvariants(const bk_program* p);
+
 typedef struct bk_program_info {
   uint32_t total_len;    /* bytes consumed by a match (all segments are fixed-length) */
   uint32_t anchor_start; /* pattern starts with ^ */

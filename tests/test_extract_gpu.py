@@ -289,6 +289,46 @@ def test_host_side_mate_matches_the_device_path(which, monkeypatch):
     assert o1 == e1 and o2 == e2
 
 
+VARLEN_PATTERNS = [
+    ("^(?P<UMI>[ATGCN]{8,10})atgccat", 1),            # greedy: the longest barcode the linker allows
+    ("^(?P<UMI>[ATGCN]{8,10}?)atgccat", 1),           # lazy: the shortest
+    ("(?P<CB>[ACGT]{3,5})gattaca(?P<UMI>[ATGCN]{2,4})", 1),   # unanchored, two ranges
+    ("^N?(?P<UMI>[ACGT]{6})", 0),                     # optional byte
+    ("(?P<UMI>[ATGCN]{4,6})acgt$", 1),                # anchored at the end
+    ("^(?P<SB>[ACGT]{0,2})(?P<UMI>[ATGCN]{3})T{1,2}", 0),     # a capture that may be empty
+]
+
+
+@pytest.mark.parametrize("pat,k", VARLEN_PATTERNS)
+def test_variable_repetition_single_end(pat, k):
+    """Bounded {m,n} / ? repetition: the pattern runs as its fixed-length variants in
+    the regex crate's backtracking order; output must equal the oracle's (Python `re`, same leftmost-first
+    semantics), with trimming, -s and -r."""
+    rnd = random.Random(zlib.crc32(pat.encode()))
+    fq = ragged_fastq(rnd, 3000, plant=[b"GATTACA", b"ATGCCAT", b"ACGT"], crlf=False, plus_comment=True,
+                      min_len=0, max_len=80)
+    for skip, rc in ((False, False), (True, False), (False, True)):
+        out, res = run_se(fq, pat, k, skip, rc)
+        assert out == bo.extract_se(fq, pat, k, rc, skip), (pat, k, skip, rc)
+        assert 0 < res.n_out < 3000
+
+
+def test_variable_repetition_paired_end():
+    rnd = random.Random(5)
+    n = 2500
+    heads = [rnd.choice([3, 23, 60]) for _ in range(n)]
+    fq1 = ragged_fastq(rnd, n, 1, plant=[b"ATGCCAT"], head_lens=heads, min_len=10, max_len=70)
+    fq2 = ragged_fastq(rnd, n, 2, plant=[b"GATTACA"], head_lens=heads, min_len=0, max_len=70)
+    combos = [("^(?P<UMI>[ATGCN]{8,10})atgccat", "(?P<CB>[ACGT]{3,5})gattaca"),
+              ("^(?P<UMI>[ATGCN]{8,10})atgccat", None), (None, "(?P<CB>[ACGT]{3,5}?)gattaca(?P<SB>[ACGT]{0,3})"),
+              ("^(?P<UMI>[ATGCN]{12})", "^(?P<CB>[ACGT]{3,5})gattaca")]
+    for p1, p2 in combos:
+        for k, skip, rc in ((1, False, False), (2, True, False), (0, False, True)):
+            o1, o2, _ = run_pe(fq1, fq2, p1, p2, k, skip=skip, rc=rc)
+            e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, k, rc_barcodes=rc, skip_trimming=skip)
+            assert o1 == e1 and o2 == e2, (p1, p2, k, skip, rc)
+
+
 def test_empty_and_tiny_inputs():
     ctx = make_ctx("^(?P<UMI>[ATGCN]{4})")
     out, res = ctx.extract_text(b"")

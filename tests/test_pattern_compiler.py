@@ -61,7 +61,9 @@ def test_error_messages_follow_error_rs():
 
 
 @pytest.mark.parametrize("pattern", [
-    "^(?P<UMI>[ATGCN]+)", "^(?P<UMI>[ATGCN]{2,4})", "^(?P<UMI>[ATGCN]*)", "^(?P<UMI>A|C)",
+    "^(?P<UMI>[ATGCN]+)", "^(?P<UMI>[ATGCN]{2,})", "^(?P<UMI>[ATGCN]*)", "^(?P<UMI>A|C)",
+    "^(?P<UMI>[ATGCN]{1,30})", "^(?P<UMI>[ATGCN]{1,5})[ACGT]{0,5}", "^((?P<UMI>[ATGCN]{4})A){1,2}", "^(?P<UMI>[ATGCN]{2,4}+)",
+    "^(?P<UMI>[ATGCN]{4,2})", "?(?P<UMI>[ATGCN]{4})",
     r"^(?P<UMI>\w{4})", "(?i)(?P<UMI>[ATGCN]{4})", "^(?P<UMI>[ATGCN]{4})?", "(?P<UMI>[ATGCN]{4})^",
     "(?=A)(?P<UMI>[ATGCN]{4})", "((?P<UMI>[ATGCN]{4})){2}", "(?P<UMI>[[:alpha:]]{4})",
     "^(?P<UMI>[^atg-z]{4})", "é(?P<UMI>A)",
@@ -70,6 +72,21 @@ def test_unsupported_constructs_are_refused(pattern):
     with pytest.raises(_lib.BarkitError) as e:
         _lib.Program(pattern, 1)
     assert e.value.status in (_lib.BK_E_UNSUPPORTED, _lib.BK_E_PATTERN)
+
+
+# ---- bounded variable repetition -> fixed-length variants in backtracking order -----------
+
+def test_variable_repetition_lowers_to_variants_in_priority_order():
+    p = _lib.Program("^(?P<UMI>[ATGCN]{8,10})atgccat", 1)
+    assert p.nvariants() == 3
+    assert p.info().total_len == 17 and list(p.info().cap_len)[:1] == [10]        # greedy: the longest first
+    assert _lib.Program("^(?P<UMI>[ATGCN]{8,10}?)atgccat", 1).info().total_len == 15   # lazy: the shortest first
+    assert _lib.Program("^(?P<UMI>[ATGCN]{12})", 1).nvariants() == 1
+    assert _lib.Program("^N?(?P<CB>[ACGT]{4,6})T{0,1}(?P<UMI>[ACGT]{2})", 0).nvariants() == 2 * 3 * 2
+    # the text the reference would hand to the regex crate keeps its quantifiers (pattern.rs:93-109)
+    assert _lib.expand("^(?P<UMI>[ATGCN]{8,10})at", 1) == bo.BarcodePattern("^(?P<UMI>[ATGCN]{8,10})at", 1).get_pattern_with_errors()
+    # [?{] inside a class and the ? of group syntax are not quantifiers
+    assert _lib.Program("^(?P<UMI>[?{}*+]{3})(?:A)", 0).nvariants() == 1
 
 
 # ---- expansion text == oracle on generated patterns ---------------------------------------------
