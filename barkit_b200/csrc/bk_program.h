@@ -4,7 +4,8 @@
 // A program is what `regex::bytes::Regex` is to the reference (pattern.rs:161-167), restricted to
 // the grammar whose matches have a fixed length: every element sits at a fixed offset from the
 // match start, so "leftmost-first" (pattern.rs:226) reduces to "smallest start at which every
-// compare run passes".
+// compare run passes".  A pattern with bounded variable repetition ({m,n}, ?) is a list of such programs,
+// one per length combination, in the regex crate's backtracking order (bk_pattern.cc, BK_MAX_VARIANTS).
 #pragma once
 #include <stdint.h>
 
