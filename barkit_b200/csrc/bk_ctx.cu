@@ -765,7 +765,7 @@ int bk_tokenize_device(bk_ctx* ctx, const uint8_t* d_text, uint64_t len, int fin
                        uint32_t cap_records, uint32_t* n_out, uint64_t* consumed, uint32_t* max_rec_bytes) {
   if (!ctx || !d_rec_off || !n_out || (len && !d_text)) return BK_E_ARG;
   if (((uintptr_t)d_text & 15) != 0) { ctx->last_error = "batch text must be 16-byte aligned"; return BK_E_ARG; }
-  if (len >= (1ull << 32) - 1) { ctx->last_error = "batch text must be < 4 GiB"; return BK_E_CAPACITY; }
+  if (len >= (1ull << 32) - 65536) { ctx->last_error = "batch text must be < 4 GiB - 64 KiB"; return BK_E_CAPACITY; }  // 32-bit positions, 16 KiB chunks
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->slot[0].stream;
   *n_out = 0;
@@ -794,13 +794,13 @@ int bk_tokenize_device(bk_ctx* ctx, const uint8_t* d_text, uint64_t len, int fin
   }
   if (eff == 0) return BK_OK;
   const uint32_t nblocks = (uint32_t)((eff + bk::kTokChunk - 1) / bk::kTokChunk);
-  int rc = ensure(ctx, &ctx->tok, (size_t)nblocks * 8 + 128);
+  int rc = ensure(ctx, &ctx->tok, bk::tok_desc_words(nblocks) * 8 + 128);
   if (rc != BK_OK) return rc;
   bk::TokResult* d_res = (bk::TokResult*)ctx->tok.p;
   unsigned int* ticket = (unsigned int*)((uint8_t*)ctx->tok.p + 64);
   unsigned long long* desc = (unsigned long long*)((uint8_t*)ctx->tok.p + 128);
-  bk::tok_init_kernel<<<(nblocks + 255) / 256, 256, 0, st>>>(d_res, desc, nblocks, ticket);
-  bk::tok_fused_kernel<<<nblocks, bk::kTokThreads, 0, st>>>(d_text, eff, d_rec_off, cap_records, desc, ticket, nblocks, d_res);
+  bk::tok_init_kernel<<<(unsigned)((bk::tok_desc_words(nblocks) + 255) / 256), 256, 0, st>>>(d_res, desc, nblocks, ticket);
+  bk::tok_fused_kernel<<<nblocks, bk::kTokThreads, 0, st>>>(d_text, (uint32_t)eff, d_rec_off, cap_records, desc, ticket, nblocks, d_res);
   CK(cudaGetLastError());
   bk::TokResult r;
   CK(cudaMemcpyAsync(&r, d_res, sizeof r, cudaMemcpyDeviceToHost, st));

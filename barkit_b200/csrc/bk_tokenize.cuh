@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bk_extract.cuh"  // lookback, descriptor helpers
+
 namespace bk {
 
 constexpr int kTokThreads = 256;
@@ -76,9 +78,12 @@ __device__ __forceinline__ uint32_t tok_block_sum(uint32_t v, uint32_t* excl) { 
 constexpr uint32_t kTokMaxNl = 4096;  // newline positions kept per chunk (more only in malformed text)
 constexpr unsigned long long kTokAgg = 1ull << 62, kTokIncl = 2ull << 62, kTokVal = (1ull << 62) - 1;
 
+// descriptor words: nblocks + 2 chunk descriptors, then 2 per group of 32 chunks (aggregate / prefix), then 2 per group (accumulators)
+__host__ __device__ inline size_t tok_desc_words(uint32_t nblocks) { return (size_t)nblocks + 2 + 4 * ((size_t)nblocks / 32 + 1); }
+
 __global__ void tok_init_kernel(TokResult* res, unsigned long long* desc, uint32_t nblocks, unsigned int* ticket) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nblocks) desc[i] = 0;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < tok_desc_words(nblocks)) desc[i] = 0;
   if (i == 0) {
     res->newlines = 0;
     res->first_bad = 0xFFFFFFFFu;
@@ -87,87 +92,76 @@ __global__ void tok_init_kernel(TokResult* res, unsigned long long* desc, uint32
   }
 }
 
-// the record [s, p4] with line ends p1 < p2 < p3 < p4, bytes through `at`: the BK_E_FORMAT conditions of bk_tokenize
-template <class At>
-__device__ __forceinline__ bool tok_record_ok(At at, uint64_t s, uint64_t p1, uint64_t p2, uint64_t p3, uint64_t p4) {
-  uint64_t sl = p2 - (p1 + 1), ql = p4 - (p3 + 1);
-  if (sl && at(p2 - 1) == '\r') --sl;
-  if (ql && at(p4 - 1) == '\r') --ql;
-  return at(s) == '@' && at(p2 + 1) == '+' && sl == ql;
+// the record [s, p4] with line ends p1 < p2 < p3 < p4: the BK_E_FORMAT conditions of bk_tokenize
+// (text < 4 GiB: positions are 32-bit)
+__device__ __forceinline__ bool tok_record_ok(const uint8_t* text, uint32_t s, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4) {
+  uint32_t sl = p2 - (p1 + 1u), ql = p4 - (p3 + 1u);
+  const uint32_t c0 = text[s], c1 = text[p2 + 1u], c2 = text[p2 - 1u], c3 = text[p4 - 1u];  // (the chunk was just read: L1 hits)
+  if (sl && c2 == '\r') --sl;
+  if (ql && c3 == '\r') --ql;
+  return c0 == '@' && c1 == '+' && sl == ql;
 }
 
-__global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* text, uint64_t len, uint32_t* rec_off,
+// 16-bit mask of the '\n' bytes of a 16-byte piece
+__device__ __forceinline__ uint32_t tok_mask16(const uint4 v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t mm = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t x = w[i] ^ 0x0A0A0A0Au;
+    const uint32_t z = (~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u) >> 7;  // 1 in bit 0 of every '\n' byte
+    mm |= ((z * 0x01020408u) >> 24) << (4 * i);  // the four flags gathered into a nibble
+  }
+  return mm;
+}
+
+__global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* text, uint32_t len, uint32_t* rec_off,
                                                                  uint32_t cap_records, unsigned long long* desc,
                                                                  unsigned int* ticket, uint32_t nblocks, TokResult* res) {
-  __shared__ uint4 chunk[kTokChunk / 16];
   __shared__ uint16_t nlpos[kTokMaxNl];
   __shared__ uint32_t s_bid;
-  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_base;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
   __syncthreads();
   const uint32_t bid = s_bid;
-  const uint64_t cbase = (uint64_t)bid * kTokChunk;
-#pragma unroll
-  for (int i = 0; i < kTokPieces; ++i) {
-    const uint64_t pos = cbase + ((uint64_t)i * kTokThreads + threadIdx.x) * 16u;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (pos < len) v = *reinterpret_cast<const uint4*>(text + pos);  // 16-byte aligned, >= 16 bytes of slack behind len
-    chunk[i * kTokThreads + threadIdx.x] = v;
-  }
-  __syncthreads();
-  // this thread's 64 contiguous bytes: chunk bytes [64 t, 64 t + 64)
+  const uint32_t cbase = bid * kTokChunk;           // (< 2^32: the text is)
+  const uint32_t tpos = cbase + threadIdx.x * 64u;  // this thread's 64 contiguous bytes
+  // The text allocation is 16-byte aligned with >= 16 bytes of slack behind len; pieces at or behind len are not read.
   unsigned long long m = 0;
   {
-    const uint64_t tpos = cbase + (uint64_t)threadIdx.x * 64u;
+    uint4 v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 v = chunk[threadIdx.x * 4 + j];
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      uint32_t mm = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t x = w[i] ^ 0x0A0A0A0Au;
-        const uint32_t z = (~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u) >> 7;  // 1 in bit 0 of every '\n' byte
-        mm |= ((z * 0x01020408u) >> 24) << (4 * i);  // the four flags gathered into a nibble
-      }
-      m |= (unsigned long long)mm << (16 * j);
+      v[j] = make_uint4(0, 0, 0, 0);
+      if (tpos + 16u * j < len) v[j] = *reinterpret_cast<const uint4*>(text + tpos + 16u * j);
     }
-    // bytes at or behind len do not count (zero-filled pieces have no newline; only a piece straddling len needs the mask)
-    if (tpos + 64u > len) m = tpos >= len ? 0ull : m & ((1ull << (len - tpos)) - 1ull);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m |= (unsigned long long)tok_mask16(v[j]) << (16 * j);
+    if (tpos + 64u > len) m = tpos >= len ? 0ull : m & ((1ull << (len - tpos)) - 1ull);  // only a piece straddling len needs it
   }
   uint32_t excl;
   const uint32_t total = tok_block_sum(__popcll(m), &excl);
-  // ---- number of the chunk's first newline: decoupled look-back (warp 0) ----------------------------------
+  // ---- number of the chunk's first newline: the two-level decoupled look-back of the extract kernel
+  // (bk_extract.cuh: chunk descriptors within a group of 32, group descriptors across).  A flat look-back
+  // walks every chunk still in flight -- ~1200 of them, 32 per L2 round trip -- and its own latency keeps
+  // more chunks in flight.
   if (threadIdx.x < 32) {
+    unsigned long long* const tdesc = desc;
+    unsigned long long* const bdesc = desc + nblocks + 2;
+    unsigned long long* const acc = bdesc + 2 * ((size_t)nblocks / 32 + 1);
     if (lane == 0) {
-      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(desc + bid), "l"((bid == 0 ? kTokIncl : kTokAgg) | total) : "memory");
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(tdesc + bid)), "r"(total | kTileReady) : "memory");
+      const unsigned long long old = atomicAdd(acc + 2 * (size_t)(bid >> 5), (1ull << 48) | (unsigned long long)total);
+      const uint32_t in_grp = min(32u, nblocks - ((bid >> 5) << 5));
+      if ((uint32_t)(old >> 48) + 1u == in_grp)  // whoever completes a group publishes its aggregate
+        desc_raise(bdesc + 2 * (size_t)(bid >> 5), kFlagAgg | ((old & ((1ull << 48) - 1)) + total));
     }
-    unsigned long long ex = 0;
-    if (bid > 0) {
-      int look = (int)bid - 1;
-      while (true) {
-        unsigned long long d = kTokIncl;  // chunks before 0 read as "prefix 0"
-        if (look - lane >= 0) {
-          do {
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(d) : "l"(desc + (look - lane)) : "memory");
-          } while ((d >> 62) == 0);
-        }
-        const unsigned pm = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-        const int first = pm ? __ffs(pm) - 1 : 32;
-        unsigned long long part = lane <= first ? (d & kTokVal) : 0ull;  // aggregates up to and including the nearest prefix
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        ex += part;
-        if (pm) break;
-        look -= 32;
-      }
-      if (lane == 0)
-        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(desc + bid), "l"(kTokIncl | (ex + total)) : "memory");
-    }
+    __syncwarp();
+    const ulonglong2 g = lookback<false>(tdesc, bdesc, bid, total, 0u, lane);
     if (lane == 0) {
-      s_base = ex;
-      if (bid == nblocks - 1) res->newlines = ex + total;
+      s_base = (uint32_t)g.x;  // (< 2^32 newlines in < 4 GiB)
+      if (bid == nblocks - 1) res->newlines = g.x + total;
       if (bid == 0) rec_off[0] = 0;
     }
   }
@@ -178,55 +172,53 @@ __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* t
       if (k < kTokMaxNl) nlpos[k] = (uint16_t)(threadIdx.x * 64u + (uint32_t)(__ffsll((long long)mm) - 1));
   }
   __syncthreads();
-  const unsigned long long base = s_base;
+  const uint32_t base = s_base;
   uint32_t bad = 0xFFFFFFFFu, longest = 0;
   uint32_t k = excl;
   for (unsigned long long mm = m; mm; mm &= mm - 1ull, ++k) {
-    const unsigned long long g = base + k;
-    if ((g & 3ull) != 3ull) continue;
-    const uint64_t p4 = cbase + threadIdx.x * 64u + (uint32_t)(__ffsll((long long)mm) - 1);
-    const unsigned long long rec = g >> 2;
-    if (rec + 1 <= cap_records) rec_off[rec + 1] = (uint32_t)(p4 + 1);
+    const uint32_t g = base + k;
+    if ((g & 3u) != 3u) continue;
+    const uint32_t p4 = tpos + (uint32_t)(__ffsll((long long)mm) - 1);
+    const uint32_t rec = g >> 2;
+    if (rec < cap_records) rec_off[rec + 1u] = p4 + 1u;
     if (rec >= cap_records) continue;
     bool ok;
-    uint64_t s;
-    if (k < kTokMaxNl && (k >= 4 || g == 3)) {  // the whole record lies in this chunk
-      const uint64_t p1 = cbase + nlpos[k - 3], p2 = cbase + nlpos[k - 2], p3 = cbase + nlpos[k - 1];
-      s = g == 3 ? 0 : cbase + nlpos[k - 4] + 1u;
-      const uint8_t* cb = reinterpret_cast<const uint8_t*>(chunk);
-      ok = tok_record_ok([&](uint64_t p) { return (uint32_t)cb[p - cbase]; }, s, p1, p2, p3, p4);
-    } else if (k < 4) {
+    uint32_t s;
+    if (k < kTokMaxNl && (k >= 4u || g == 3u)) {  // the whole record lies in this chunk
+      s = g == 3u ? 0u : cbase + nlpos[k - 4u] + 1u;
+      ok = tok_record_ok(text, s, cbase + nlpos[k - 3u], cbase + nlpos[k - 2u], cbase + nlpos[k - 1u], p4);
+    } else if (k < 4u) {
       continue;  // the record began in an earlier chunk: warp 0 looks at it below
     } else {  // more newlines in one chunk than nlpos holds (records of a few bytes): walk back bytewise
-      uint64_t q[4] = {0, 0, 0, 0};  // p3, p2, p1, p0
+      uint32_t q[4] = {0, 0, 0, 0};  // p3, p2, p1, p0
       int found = 0;
-      uint64_t p = p4;
+      uint32_t p = p4;
       while (p > 0 && found < 4) {
         --p;
         if (text[p] == '\n') q[found++] = p;
       }
-      s = found == 4 ? q[3] + 1 : 0;
-      ok = found >= 3 && tok_record_ok([&](uint64_t x) { return (uint32_t)text[x]; }, s, q[2], q[1], q[0], p4);
+      s = found == 4 ? q[3] + 1u : 0u;
+      ok = found >= 3 && tok_record_ok(text, s, q[2], q[1], q[0], p4);
     }
-    if (!ok && (uint32_t)rec < bad) bad = (uint32_t)rec;
-    longest = max(longest, (uint32_t)(p4 + 1 - s));
+    if (!ok && rec < bad) bad = rec;
+    longest = max(longest, p4 + 1u - s);
   }
   // ---- the record that straddles the chunk's start: its end is the chunk's newline kb < 4, its other
   // newlines are the chunk's first kb and the last 4 - kb before the chunk.  Warp 0 finds those together,
   // 512 bytes of text per step (one L2 round trip), instead of one thread walking ~300 dependent bytes.
   if (threadIdx.x < 32 && bid > 0) {
-    const uint32_t kb = (3u - (uint32_t)(base & 3ull)) & 3u;
-    const unsigned long long rec = (base + kb) >> 2;
+    const uint32_t kb = (3u - (base & 3u)) & 3u;
+    const uint32_t rec = (base + kb) >> 2;
     if (kb < total && rec < cap_records) {  // (warp-uniform)
-      uint64_t before[4];  // the four newlines before the record's last one, nearest first
+      uint32_t before[4];  // the four newlines before the record's last one, nearest first
       uint32_t found = 0;
       for (; found < kb; ++found) before[found] = cbase + nlpos[kb - 1u - found];
-      uint64_t wend = cbase;
+      uint32_t wend = cbase;
       while (found < 4u && wend > 0) {
-        const uint64_t wstart = wend >= 512u ? wend - 512u : 0u;  // cbase is a multiple of 512
+        const uint32_t wstart = wend >= 512u ? wend - 512u : 0u;  // cbase is a multiple of 512
         uint32_t mm = 0;
-        const uint64_t pos = wstart + 16u * lane;
-        if (pos < wend) mm = tok_nl_mask(text, pos, wend);
+        const uint32_t pos = wstart + 16u * lane;
+        if (pos < wend) mm = tok_mask16(*reinterpret_cast<const uint4*>(text + pos));
         for (int l = 31; l >= 0 && found < 4u; --l) {  // every lane keeps the same list
           uint32_t ml = __shfl_sync(0xffffffffu, mm, l);
           while (ml && found < 4u) {
@@ -238,11 +230,11 @@ __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* t
         wend = wstart;
       }
       if (lane == 0) {
-        const uint64_t p4 = cbase + nlpos[kb];
-        const uint64_t s = found == 4u ? before[3] + 1 : 0;
-        const bool ok = found == 4u && tok_record_ok([&](uint64_t x) { return (uint32_t)text[x]; }, s, before[2], before[1], before[0], p4);
-        if (!ok && (uint32_t)rec < bad) bad = (uint32_t)rec;
-        longest = max(longest, (uint32_t)(p4 + 1 - s));
+        const uint32_t p4 = cbase + nlpos[kb];
+        const uint32_t s = found == 4u ? before[3] + 1u : 0u;
+        const bool ok = found == 4u && tok_record_ok(text, s, before[2], before[1], before[0], p4);
+        if (!ok && rec < bad) bad = rec;
+        longest = max(longest, p4 + 1u - s);
       }
     }
   }
