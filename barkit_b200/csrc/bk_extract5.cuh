@@ -327,9 +327,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel5(con
         if (nt < P.ntiles) {
           bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(P.off[m]) + (((size_t)nt * R * 4u) & ~size_t(15)), ((4u * R + 15u) & ~15u) + 16u);
           const unsigned long long est = (unsigned long long)gbase + (unsigned long long)gridDim.x * (oe - o0);
-#ifndef BK_NO_TEXT_PREFETCH
           if (est + bytes + 256u <= P.text_len[m]) bulk_prefetch_l2(T + (est & ~15ull), bytes + 256u);
-#endif
         }
       }
       cp_async_wait_all();

@@ -26,23 +26,6 @@ struct TokResult {
   unsigned int max_rec_bytes;
 };
 
-// bit i set iff byte i of the 16 bytes at text[pos..] (clipped to len) is '\n'
-__device__ __forceinline__ uint32_t tok_nl_mask(const uint8_t* text, uint64_t pos, uint64_t len) {
-  if (pos >= len) return 0;
-  const uint4 v = *reinterpret_cast<const uint4*>(text + pos);  // text is 16-byte aligned with >= 16 bytes of slack
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t m = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t x = w[i] ^ 0x0A0A0A0Au;
-    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;  // 0x80 where the byte is '\n' (exact)
-    const uint32_t b = z >> 7;
-    m |= ((b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u)) << (4 * i);
-  }
-  const uint64_t left = len - pos;
-  return left >= 16 ? m : m & ((1u << left) - 1u);
-}
-
 __device__ __forceinline__ uint32_t tok_block_sum(uint32_t v, uint32_t* excl) {  // block-wide sum; *excl = sum over lower threads
   __shared__ uint32_t warp_tot[kTokThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -76,7 +59,6 @@ __device__ __forceinline__ uint32_t tok_block_sum(uint32_t v, uint32_t* excl) { 
 // rec_off[g / 4 + 1] and validates record g / 4 -- from the chunk when the record's five newlines lie
 // in it, otherwise (one record per chunk boundary) by walking the text backwards in global memory.
 constexpr uint32_t kTokMaxNl = 4096;  // newline positions kept per chunk (more only in malformed text)
-constexpr unsigned long long kTokAgg = 1ull << 62, kTokIncl = 2ull << 62, kTokVal = (1ull << 62) - 1;
 
 // descriptor words: nblocks + 2 chunk descriptors, then 2 per group of 32 chunks (aggregate / prefix), then 2 per group (accumulators)
 __host__ __device__ inline size_t tok_desc_words(uint32_t nblocks) { return (size_t)nblocks + 2 + 4 * ((size_t)nblocks / 32 + 1); }
