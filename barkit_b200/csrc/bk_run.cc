@@ -190,6 +190,8 @@ void set_err(const std::string& m, char* err, size_t cap) {
 
 struct Batch { uint64_t rec0, rec1; };
 
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 }  // namespace
 
 extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
@@ -211,6 +213,8 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   Logger log;
   log.quiet = a->quiet != 0;
   log.message("Estimating reads count...");  // run.rs:97 / :215
+  const bool dbg = getenv("BK_DEBUG") != nullptr;
+  const double t_begin = now_s();
 
   Mapped in1, in2;
   if (!map_file(a->fq1, &in1, &e)) { set_err(e, err, errcap); return BK_E_IO; }
@@ -227,6 +231,7 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   if (pe && !record_starts(in2, host_threads, &st2, &e)) { set_err(e, err, errcap); return BK_E_FORMAT; }
   uint64_t nrec = st1.size() - 1;
   if (pe) nrec = std::min<uint64_t>(nrec, st2.size() - 1);  // run.rs:172-173 zip truncates
+  if (dbg) fprintf(stderr, "[bk_run] map + record starts: %.3f s\n", now_s() - t_begin);
 
   int fd1 = open_output(a->out_fq1, a->force != 0, &e);  // run.rs:106-111 / :225-229
   if (fd1 < 0) { set_err(e, err, errcap); return BK_E_IO; }
@@ -264,8 +269,8 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   }
   int ngpu = a->n_gpus > 0 ? std::min(a->n_gpus, ndev) : ndev;
 
-  // batches: contiguous record ranges, sized by bytes (-m MB per mate when given, else 256 MiB)
-  size_t batch_bytes = a->max_memory_mb ? a->max_memory_mb << 20 : (size_t)256 << 20;
+  // batches: contiguous record ranges, sized by bytes (-m MB per mate when given, else 64 MiB: small enough to pipeline, large enough for the kernel)
+  size_t batch_bytes = a->max_memory_mb ? a->max_memory_mb << 20 : (size_t)64 << 20;
   batch_bytes = std::min<size_t>(std::max<size_t>(batch_bytes, 1 << 20), (size_t)3 << 30);
   std::vector<Batch> batches;
   for (uint64_t r = 0; r < nrec;) {
@@ -298,95 +303,202 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   const uint32_t flags = (pe ? BK_FLAG_PAIRED : 0) | (a->skip_trimming ? BK_FLAG_SKIP_TRIM : 0) |
                          (a->rc_barcodes ? BK_FLAG_RC : 0);
 
+  // One worker per GPU: stage batch k (all host threads: copy into pinned memory, offsets, record checks)
+  // -> submit k -> wait k-1 -> hand k-1 to the worker's writer thread, so that staging, the device and the
+  // output files all work at the same time.  Three host buffer sets per worker, two device slots (bk_ctx).
+  const unsigned stage_threads = std::max(1u, std::min(host_threads / (unsigned)ngpu, 32u));
   auto worker = [&](int dev) {
     char emsg[512];
     int cst = BK_OK;
+    double t_ctx = now_s(), t_stage = 0, t_submit = 0, t_wait = 0, t_write = 0, t_setwait = 0;
     bk_ctx* ctx = bk_ctx_create(dev, p1, p2, flags, &cst, emsg, sizeof emsg);
     if (!ctx) { fail(cst, emsg); return; }
+    t_ctx = now_s() - t_ctx;
     const int nm = pe ? 2 : 1;
-    struct SlotBuf { uint8_t* text[2] = {nullptr, nullptr}; uint32_t* off[2] = {nullptr, nullptr};
+    constexpr int kSets = 3;
+    struct HostSet { uint8_t* text[2] = {nullptr, nullptr}; uint32_t* off[2] = {nullptr, nullptr};
                      uint8_t* out[2] = {nullptr, nullptr};
                      size_t tcap[2] = {0, 0}, ocap[2] = {0, 0}, fcap[2] = {0, 0};
-                     size_t batch = SIZE_MAX; } sb[2];
+                     size_t batch = SIZE_MAX; bk_result res; bool busy = false; } hs[kSets];
+    std::mutex smu;                 // guards hs[].busy, the writer's queue
+    std::condition_variable scv;
+    std::vector<int> wq;            // sets waiting to be written, in submission order
+    bool wdone = false;
+    double t_alloc = 0;
     auto ensure_host = [&](void** p, size_t* cap, size_t need) {
       if (*cap >= need) return true;
+      const double t0 = now_s();
       if (*p) bk_host_free(*p);
       *p = bk_host_alloc(need + need / 8 + 4096);
       *cap = *p ? need + need / 8 + 4096 : 0;
+      t_alloc += now_s() - t0;
       return *p != nullptr;
     };
-    auto submit = [&](int s, size_t bi) -> bool {
+    // the BK_E_FORMAT conditions of bk_tokenize for one record [b, e) (its four lines are given by the record starts)
+    auto record_ok = [](const uint8_t* b, const uint8_t* e) {
+      if (e - b < 4 || b[0] != '@') return false;
+      const uint8_t* nl1 = (const uint8_t*)memchr(b, '\n', e - b);
+      if (!nl1 || nl1 + 1 >= e) return false;
+      const uint8_t* nl2 = (const uint8_t*)memchr(nl1 + 1, '\n', e - nl1 - 1);
+      if (!nl2 || nl2 + 1 >= e || nl2[1] != '+') return false;
+      const uint8_t* nl3 = (const uint8_t*)memchr(nl2 + 1, '\n', e - nl2 - 1);
+      if (!nl3) return false;
+      const uint8_t* nl4 = nl3 + 1 < e ? (const uint8_t*)memchr(nl3 + 1, '\n', e - nl3 - 1) : nullptr;
+      if (!nl4) nl4 = e;  // the file's last record may lack its EOL
+      size_t sl = nl2 - (nl1 + 1), ql = nl4 - (nl3 + 1);
+      if (sl && nl2[-1] == '\r') --sl;
+      if (ql && nl4[-1] == '\r') --ql;
+      return sl == ql;
+    };
+    auto stage = [&](int hi, size_t bi, bk_mate_in* in) -> bool {
+      HostSet& h = hs[hi];
       const Batch& b = batches[bi];
       const uint32_t n = (uint32_t)(b.rec1 - b.rec0);
-      bk_mate_in in[2];
       const Mapped* mp[2] = {&in1, &in2};
       const std::vector<uint64_t>* stp[2] = {&st1, &st2};
       for (int m = 0; m < nm; ++m) {
         const uint64_t t0 = (*stp[m])[b.rec0], t1 = (*stp[m])[b.rec1];
-        if (!ensure_host((void**)&sb[s].text[m], &sb[s].tcap[m], t1 - t0 + 64)) return false;
-        if (!ensure_host((void**)&sb[s].off[m], &sb[s].fcap[m], ((size_t)n + 2) * 4)) return false;
-        memcpy(sb[s].text[m], mp[m]->p + t0, t1 - t0);
-        uint32_t maxrec = 0;
-        for (uint32_t i = 0; i <= n; ++i) {
-          const uint32_t o = (uint32_t)((*stp[m])[b.rec0 + i] - t0);
-          sb[s].off[m][i] = o;
-          if (i && o - sb[s].off[m][i - 1] > maxrec) maxrec = o - sb[s].off[m][i - 1];
-        }
-        // record-level validation ('@', '+', equal lengths) of this batch
-        {
-          uint32_t nn = 0, mr = 0;
-          uint64_t consumed = 0;
-          std::vector<uint32_t> chk((size_t)n + 2);
-          int rc = bk_tokenize(sb[s].text[m], t1 - t0, 1, chk.data(), n + 1, &nn, &consumed, &mr);
-          if (rc != BK_OK || nn != n) { fail(BK_E_FORMAT, "malformed FASTQ record"); return false; }
-        }
-        in[m].text = sb[s].text[m];
-        in[m].rec_off = sb[s].off[m];
-        in[m].text_len = t1 - t0;
-        in[m].max_rec_bytes = std::max<uint32_t>(maxrec, 1);
-        in[m].reserved = 0;
-        if (!ensure_host((void**)&sb[s].out[m], &sb[s].ocap[m], bk_out_bound(ctx, m + 1, n, t1 - t0))) return false;
+        if (!ensure_host((void**)&h.text[m], &h.tcap[m], t1 - t0 + 64)) return false;
+        if (!ensure_host((void**)&h.off[m], &h.fcap[m], ((size_t)n + 2) * 4)) return false;
+        if (!ensure_host((void**)&h.out[m], &h.ocap[m], bk_out_bound(ctx, m + 1, n, t1 - t0))) return false;
       }
-      int rc = bk_submit(ctx, s, n, &in[0], pe ? &in[1] : nullptr);
-      if (rc != BK_OK) { fail(rc, bk_last_error(ctx)); return false; }
-      sb[s].batch = bi;
+      const unsigned T = n < 20000 ? 1u : stage_threads;
+      std::vector<uint32_t> maxrec((size_t)T * 2, 0);
+      std::atomic<bool> bad{false};
+      auto part = [&](unsigned t) {
+        const uint64_t r0 = b.rec0 + (uint64_t)n * t / T, r1 = b.rec0 + (uint64_t)n * (t + 1) / T;
+        for (int m = 0; m < nm; ++m) {
+          const std::vector<uint64_t>& st = *stp[m];
+          const uint64_t base = st[b.rec0];
+          memcpy(h.text[m] + (st[r0] - base), mp[m]->p + st[r0], st[r1] - st[r0]);
+          uint32_t mr = 0;
+          for (uint64_t r = r0; r < r1; ++r) {
+            h.off[m][r - b.rec0] = (uint32_t)(st[r] - base);
+            const uint64_t len = st[r + 1] - st[r];
+            if (len > mr) mr = (uint32_t)len;
+            if (!record_ok(mp[m]->p + st[r], mp[m]->p + st[r + 1])) bad = true;
+          }
+          if (t + 1 == T) h.off[m][n] = (uint32_t)(st[b.rec1] - base);
+          maxrec[(size_t)t * 2 + m] = mr;
+        }
+      };
+      if (T == 1) part(0);
+      else {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; ++t) th.emplace_back(part, t);
+        part(0);
+        for (auto& x : th) x.join();
+      }
+      if (bad.load()) { fail(BK_E_FORMAT, "malformed FASTQ record"); return false; }
+      for (int m = 0; m < nm; ++m) {
+        uint32_t mr = 1;
+        for (unsigned t = 0; t < T; ++t) mr = std::max(mr, maxrec[(size_t)t * 2 + m]);
+        in[m].text = h.text[m];
+        in[m].rec_off = h.off[m];
+        in[m].text_len = (*stp[m])[b.rec1] - (*stp[m])[b.rec0];
+        in[m].max_rec_bytes = mr;
+        in[m].reserved = 0;
+      }
+      h.batch = bi;
       return true;
     };
-    auto finish = [&](int s) -> bool {
-      bk_result res;
-      int rc = bk_wait(ctx, s, sb[s].out[0], sb[s].ocap[0], sb[s].out[1], sb[s].ocap[1], &res);
+    // writer: sets in submission order; the files in batch order across all workers (run.rs:79,194)
+    std::thread writer([&] {
+      for (;;) {
+        int hi;
+        {
+          std::unique_lock<std::mutex> lk(smu);
+          scv.wait(lk, [&] { return !wq.empty() || wdone; });
+          if (wq.empty()) return;
+          hi = wq.front();
+          wq.erase(wq.begin());
+        }
+        HostSet& h = hs[hi];
+        const double tw = now_s();
+        bool ok = true;
+        {
+          std::unique_lock<std::mutex> lk(wmu);
+          wcv.wait(lk, [&] { return next_to_write == h.batch || status.load() != BK_OK; });
+          ok = status.load() == BK_OK;
+        }
+        if (ok) {  // (only the holder of the turn writes: no lock needed while it does)
+          std::thread w2;
+          bool ok2 = true;
+          if (pe) w2 = std::thread([&] { ok2 = write_all(fd2, h.out[1], h.res.out2_len); });
+          ok = write_all(fd1, h.out[0], h.res.out1_len);
+          if (pe) w2.join();
+          ok = ok && ok2;
+          if (!ok) fail(BK_E_IO, io_error(strerror(errno)));
+          {
+            std::lock_guard<std::mutex> lk(wmu);
+            ++next_to_write;
+          }
+          wcv.notify_all();
+        }
+        t_write += now_s() - tw;
+        {
+          std::lock_guard<std::mutex> lk(smu);
+          h.busy = false;
+          h.batch = SIZE_MAX;
+        }
+        scv.notify_all();
+      }
+    });
+    auto finish = [&](int dslot, int hi) -> bool {  // wait for the device, hand the set to the writer
+      HostSet& h = hs[hi];
+      const double tw0 = now_s();
+      int rc = bk_wait(ctx, dslot, h.out[0], h.ocap[0], h.out[1], h.ocap[1], &h.res);
+      t_wait += now_s() - tw0;
       if (rc != BK_OK) { fail(rc, bk_last_error(ctx)); return false; }
-      std::unique_lock<std::mutex> lk(wmu);  // ordered writer: batch order == input order (run.rs:79,194)
-      wcv.wait(lk, [&] { return next_to_write == sb[s].batch || status.load() != BK_OK; });
-      if (status.load() != BK_OK) return false;
-      bool ok = write_all(fd1, sb[s].out[0], res.out1_len) && (!pe || write_all(fd2, sb[s].out[1], res.out2_len));
-      ++next_to_write;
-      lk.unlock();
-      wcv.notify_all();
-      if (!ok) { fail(BK_E_IO, io_error(strerror(errno))); return false; }
-      sb[s].batch = SIZE_MAX;
+      {
+        std::lock_guard<std::mutex> lk(smu);
+        wq.push_back(hi);
+      }
+      scv.notify_all();
       return true;
     };
-    int s = 0;
     bool ok = true;
-    for (;;) {
+    long k = 0;            // batches this worker has submitted
+    int prev_set = -1;     // set of batch k-1, still on the device
+    for (;; ++k) {
       size_t bi = next_batch.fetch_add(1);
       if (bi >= batches.size() || status.load() != BK_OK) break;
-      if (sb[s].batch != SIZE_MAX && !(ok = finish(s))) break;  // free this slot first
-      if (!(ok = submit(s, bi))) { if (status.load() == BK_OK) fail(BK_E_CAPACITY, "pinned host allocation failed"); break; }
-      s ^= 1;
+      const int hi = (int)(k % kSets);
+      {
+        const double t0 = now_s();
+        std::unique_lock<std::mutex> lk(smu);
+        scv.wait(lk, [&] { return !hs[hi].busy; });
+        hs[hi].busy = true;
+        t_setwait += now_s() - t0;
+      }
+      bk_mate_in in[2];
+      const double ts0 = now_s();
+      if (!(ok = stage(hi, bi, in))) { if (status.load() == BK_OK) fail(BK_E_CAPACITY, "pinned host allocation failed"); break; }
+      const double ts1 = now_s();
+      t_stage += ts1 - ts0;
+      int rc = bk_submit(ctx, (int)(k & 1), (uint32_t)(batches[bi].rec1 - batches[bi].rec0), &in[0], pe ? &in[1] : nullptr);
+      t_submit += now_s() - ts1;
+      if (rc != BK_OK) { fail(rc, bk_last_error(ctx)); ok = false; break; }
+      if (prev_set >= 0 && !(ok = finish((int)((k - 1) & 1), prev_set))) { prev_set = -1; break; }
+      prev_set = hi;
     }
-    for (int k = 0; k < 2 && ok; ++k) {  // drain in submission order
-      if (sb[s].batch != SIZE_MAX) ok = finish(s);
-      s ^= 1;
+    if (ok && prev_set >= 0) ok = finish((int)((k - 1) & 1), prev_set);
+    {
+      std::lock_guard<std::mutex> lk(smu);
+      wdone = true;
     }
-    for (auto& b : sb)
+    scv.notify_all();
+    writer.join();
+    for (auto& h : hs)
       for (int m = 0; m < 2; ++m) {
-        if (b.text[m]) bk_host_free(b.text[m]);
-        if (b.off[m]) bk_host_free(b.off[m]);
-        if (b.out[m]) bk_host_free(b.out[m]);
+        if (h.text[m]) bk_host_free(h.text[m]);
+        if (h.off[m]) bk_host_free(h.off[m]);
+        if (h.out[m]) bk_host_free(h.out[m]);
       }
     bk_ctx_destroy(ctx);
+    if (dbg) fprintf(stderr, "[bk_run] gpu %d: context %.3f s, stage %.3f s (%u threads), submit %.3f s, wait %.3f s, "
+                     "writer busy %.3f s, waiting for a free buffer set %.3f s; pinned allocation inside stage %.3f s\n", dev, t_ctx, t_stage,
+                     stage_threads, t_submit, t_wait, t_write, t_setwait, t_alloc);
   };
 
   if (!batches.empty()) {
@@ -396,6 +508,7 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   }
   free_programs();
   close_outputs();
+  if (dbg) fprintf(stderr, "[bk_run] total %.3f s, %zu batches\n", now_s() - t_begin, batches.size());
   if (status.load() != BK_OK) { set_err(first_error, err, errcap); return status.load(); }
   log.final_message();
   return BK_OK;
