@@ -329,6 +329,25 @@ def test_variable_repetition_paired_end():
             assert o1 == e1 and o2 == e2, (p1, p2, k, skip, rc)
 
 
+def test_host_side_mate_falls_back_when_the_host_copy_is_slow(monkeypatch):
+    """The context measures the host copy of the pattern-less mate against what the bus would need and sends
+    both mates to the device once the host side loses twice in a row (here: one host thread).  The bytes do
+    not change, the traffic does."""
+    monkeypatch.setenv("BK_HOST_THREADS", "1")
+    p1, p2, _ = CONFIG_PATTERNS["C3"]
+    n = 400000
+    fq1, fq2 = bksyn.generate_pair(bksyn.CONFIGS["C3"], 0, 2000)
+    fq1, fq2 = fq1 * (n // 2000), fq2 * (n // 2000)   # (repeated records: only sizes and timing matter here)
+    ctx = make_ctx(p1, p2, k=1, paired=True)
+    seen = []
+    for _ in range(5):
+        o1, o2, res = ctx.extract_text(fq1, fq2)
+        seen.append((zlib.crc32(o1), zlib.crc32(o2), res.n_out, res.h2d_bytes))
+    ctx.close()
+    assert len({s[:3] for s in seen}) == 1
+    assert seen[0][3] < 0.6 * seen[-1][3], seen          # first batches: one mate over the bus; later: both
+
+
 def test_empty_and_tiny_inputs():
     ctx = make_ctx("^(?P<UMI>[ATGCN]{4})")
     out, res = ctx.extract_text(b"")
