@@ -16,7 +16,7 @@
 
 namespace bk {
 
-constexpr int kTokThreads = 256;
+constexpr int kTokThreads = 512;
 constexpr int kTokPieces = 4;                                     // 16-byte pieces per thread, kTokThreads * 16 bytes apart
 constexpr uint32_t kTokChunk = kTokThreads * 16u * kTokPieces;  // bytes per block
 
@@ -51,7 +51,7 @@ __device__ __forceinline__ uint32_t tok_block_sum(uint32_t v, uint32_t* excl) { 
 
 // ---- single pass: count + scan + emit + check ---------------------------------------------------------
 //
-// One CTA per 16 KiB of text, taken in ticket order.  The chunk is read once (coalesced 16-byte
+// One CTA per 32 KiB of text (512 threads x 64 bytes), taken in ticket order.  The chunk is read once (coalesced 16-byte
 // loads, kept in shared memory), every thread turns its 64 contiguous bytes into a newline mask, a
 // block scan numbers the chunk's newlines, a decoupled look-back over the earlier chunks' counts
 // (one 8-byte descriptor per chunk: aggregate, then inclusive prefix) gives the number of the chunk's
