@@ -244,6 +244,9 @@ def main():
     if _lib.device_count() <= local_rank:
         raise SystemExit("bench.py: no CUDA device %d; the extract path has no CPU fallback" % local_rank)
     prog = _lib.Program(PATTERN1, MAX_ERROR)
+    # one process per GPU: the host threads of the library (output of the pattern-less mate) are shared out
+    # among the ranks of this box instead of every rank starting one per core
+    os.environ.setdefault("BK_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // max(world, 1))))
     ctx = _lib.Context(prog, None, paired=True, device=local_rank)
     cfg = _lib.syn_config(READ_LEN, plant1=(b"ATGCCAT", 16, 0))
     rl = bksyn.record_len(READ_LEN)
