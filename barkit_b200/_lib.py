@@ -98,6 +98,7 @@ SYMBOLS = {
     "bk_tokenize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, u32p,
                                      C.POINTER(C.c_uint64), u32p]),
     "bk_kernel_variant": (C.c_int, [C.c_void_p]),
+    "bk_warmup": (C.c_int, [C.c_int]),
     "bk_program_nvariants": (C.c_int, [C.c_void_p]),
     "bk_debug_events": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bk_reverse_complement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

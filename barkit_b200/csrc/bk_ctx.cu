@@ -382,6 +382,14 @@ int bk_device_count(void) {
   return n;
 }
 
+int bk_warmup(int device) {
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) {
+    cudaGetLastError();
+    return BK_E_CUDA;
+  }
+  return BK_OK;
+}
+
 bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, uint32_t flags, int* status,
                       char* err, size_t errcap) {
   auto fail = [&](int st, const std::string& m) -> bk_ctx* {

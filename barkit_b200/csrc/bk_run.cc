@@ -216,6 +216,13 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   const bool dbg = getenv("BK_DEBUG") != nullptr;
   const double t_begin = now_s();
 
+  // the CUDA contexts come up while the host scans the input
+  std::thread warm([&] {
+    const int nd = bk_device_count();
+    const int ng = a->n_gpus > 0 ? std::min(a->n_gpus, nd) : nd;
+    for (int d = 0; d < ng; ++d) bk_warmup(d);
+  });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warm_join{warm};
   Mapped in1, in2;
   if (!map_file(a->fq1, &in1, &e)) { set_err(e, err, errcap); return BK_E_IO; }
   if (pe && !map_file(a->fq2, &in2, &e)) { set_err(e, err, errcap); return BK_E_IO; }
@@ -261,6 +268,7 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
 
   log.message("Extracting barcodes from reads...");  // run.rs:120 / :247
 
+  if (warm.joinable()) warm.join();
   int ndev = bk_device_count();
   if (ndev <= 0) {
     free_programs(); close_outputs();

@@ -97,6 +97,9 @@ int bk_tokenize(const uint8_t* text, uint64_t len, int final_chunk, uint32_t* re
 /* ---- device context ------------------------------------------------------------------------- */
 
 int bk_device_count(void);
+/* Initialises the CUDA runtime's context on `device` (a few hundred ms the first time in a process), so that a
+ * host program can overlap that with its own start-up work; bk_ctx_create does it implicitly otherwise. */
+int bk_warmup(int device);
 
 /* One context per GPU.  p1 / p2 may be NULL (run.rs:233-245: a mate without a pattern); at least
  * one must be given.  Without BK_FLAG_PAIRED, p2 must be NULL (run.rs:43). */
