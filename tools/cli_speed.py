@@ -37,6 +37,10 @@ for run in range(3):
     if os.environ.get("BK_DEBUG"):
         print(r.stderr.strip())
     osz = os.path.getsize(d + "/o1.fq") + os.path.getsize(d + "/o2.fq")
+    if run == 0:
+        import zlib
+        crc = [zlib.crc32(np.fromfile(d + "/" + f, np.uint8).tobytes()) for f in ("o1.fq", "o2.fq")]
+        print("output crc32 (identical for any number of GPUs):", crc, "GPUs visible:", _lib.device_count())
     print("barkit extract: %d pairs, %.2f GB in, %.2f GB out: %.3f s = %.1f M pairs/s, %.2f GB/s in+out"
           % (P, 2 * P * rl / 1e9, osz / 1e9, dt, P / dt / 1e6, (2 * P * rl + osz) / dt / 1e9), flush=True)
 for f in os.listdir(d):
