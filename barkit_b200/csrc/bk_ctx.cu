@@ -157,23 +157,35 @@ bool needs_general(const bk_ctx* ctx) {
 
 template <bool PAIRED, bool GENERAL, bool VAR = false>
 int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
+  // Two CTAs per SM (228 KB of shared memory per SM, each CTA's static part included) whenever the records
+  // allow it: the kernel is bound by ring slots in flight, and the instantiations differ in static shared
+  // memory (the general ones carry the search-sharing buffers), so the budget is taken from the kernel itself.
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR>));
+  const size_t target = std::min<size_t>(kTargetDynSmem, (233472 / 2 - fa.sharedSizeBytes) & ~size_t(127));
   uint32_t R = bk::kTileRecs;
   // prefer several resident tiles per SM; never go below 8 records unless a tile would not fit
-  while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > kTargetDynSmem) --R;
+  while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > target) --R;
   while (R > 0 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > kMaxDynSmem) --R;
   if (R == 0) {
     ctx->last_error = "record too long for the on-chip staging buffer";
     return BK_E_CAPACITY;
   }
-  lp->tile_recs = R;
-  lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap);
-  lp->ntiles = (n + R - 1) / R;
-  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)lp->smem));
   CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR>, bk::cta_warps(PAIRED) * 32, lp->smem));
+  int per_sm = 0, other = 0;  // `other`: CTAs per SM that registers and threads allow
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, bk::extract_kernel<PAIRED, GENERAL, VAR>, bk::cta_warps(PAIRED) * 32, 0));
+  for (;;) {
+    lp->tile_recs = R;
+    lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap);
+    CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)lp->smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR>,
+                                                     bk::cta_warps(PAIRED) * 32, lp->smem));
+    if (per_sm >= 2 || other < 2 || R <= 8) break;  // (records too long to share the SM: the tile stays as it is)
+    --R;
+  }
+  lp->ntiles = (n + R - 1) / R;
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
