@@ -205,11 +205,15 @@ bool v5_eligible(const bk_ctx* ctx) {
   return true;
 }
 
-// 4 = extract_kernel, 5 = extract_kernel5.  BK_KERNEL=4|5 pins the choice (tests, profiling).
+// 4 = extract_kernel, 5 = extract_kernel5.  extract_kernel is the default: on every BASELINE config it is the
+// faster one.  BK_KERNEL=5 sends every launch that qualifies to extract_kernel5;
+// BK_KERNEL=auto lets the context time both on its first large batches and keep the faster.
 int pick_variant(bk_ctx* ctx, uint32_t n) {
   if (!v5_eligible(ctx)) return 4;
   const char* k = getenv("BK_KERNEL");
-  if (k && (k[0] == '4' || k[0] == '5')) return k[0] - '0';
+  if (!k || k[0] == '4') return 4;
+  if (k[0] == '5') return 5;
+  if (k[0] != 'a') return 4;
   if (ctx->tuner.choice) return ctx->tuner.choice;
   if (n < kTuneMinRecords) return 4;
   return ctx->tuner.trials[1] < ctx->tuner.trials[0] ? 5 : 4;
@@ -217,7 +221,8 @@ int pick_variant(bk_ctx* ctx, uint32_t n) {
 
 void report_variant(bk_ctx* ctx, int variant, uint32_t n, double ms) {
   Tuner& t = ctx->tuner;
-  if (t.choice || n < kTuneMinRecords || !v5_eligible(ctx) || ms <= 0) return;
+  const char* k = getenv("BK_KERNEL");
+  if (!k || k[0] != 'a' || t.choice || n < kTuneMinRecords || !v5_eligible(ctx) || ms <= 0) return;
   const int i = variant == 5 ? 1 : 0;
   t.trials[i] += 1;
   t.best[i] = std::min(t.best[i], ms / n);
@@ -761,8 +766,9 @@ int bk_kernel_variant(const bk_ctx* ctx) {
   if (!ctx) return BK_E_ARG;
   if (!v5_eligible(ctx)) return 4;
   const char* k = getenv("BK_KERNEL");
-  if (k && (k[0] == '4' || k[0] == '5')) return k[0] - '0';
-  return ctx->tuner.choice;
+  if (!k || k[0] == '4') return 4;
+  if (k[0] == '5') return 5;
+  return k[0] == 'a' ? ctx->tuner.choice : 4;
 }
 
 int bk_debug_events(bk_ctx* ctx, uint32_t ntiles, uint32_t first_tile, uint32_t count, uint64_t* out) {

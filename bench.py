@@ -274,8 +274,9 @@ def main():
         m = batches[i % nbatch]
         return ctx.extract_device(P, m[0], m[1], d_o1, cap1, d_o2, cap2)
 
-    # set-up, untimed: a context whose patterns qualify for both extract kernels times them on its
-    # first large batches (two launches each) and keeps the faster; let it settle before the warm-up
+    # set-up, untimed: with BK_KERNEL=auto a context whose patterns qualify for both extract kernels times them
+    # on its first large batches (two launches each) and keeps the faster; let it settle before the warm-up
+    # (by default every launch uses extract_kernel and this loop does nothing)
     for i in range(8):
         if ctx.kernel_variant() != 0:
             break

@@ -177,11 +177,11 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
                       uint8_t* d_out1, uint64_t cap1, uint8_t* d_out2, uint64_t cap2,
                       int32_t* d_match1, int32_t* d_match2, int iters, bk_result* res);
 
-/* Which extract kernel this context's launches use: 4 = extract_kernel (bk_extract.cuh, any pattern),
- * 5 = extract_kernel5 (bk_extract5.cuh, patterns anchored at the read start), 0 = both qualify and the
- * context is still timing them on its first large batches (two launches each; output is identical).
- * The environment variable BK_KERNEL=4|5 pins the choice.  No counterpart in the reference: its
- * per-read work has one implementation (parse.rs:58-68). */
+/* Which extract kernel this context's launches use: 4 = extract_kernel (bk_extract.cuh, any pattern; the
+ * default), 5 = extract_kernel5 (bk_extract5.cuh, patterns anchored at the read start; BK_KERNEL=5), 0 = the
+ * context is still timing both on its first large batches (BK_KERNEL=auto: two launches each, then the
+ * faster; output is identical either way).  No counterpart in the reference: its per-read work has one
+ * implementation (parse.rs:58-68). */
 int bk_kernel_variant(const bk_ctx* ctx);
 
 /* Debug: the pipeline event trace of the last device launch on slot 0 -- 16 clock64() stamps per tile

@@ -238,9 +238,9 @@ def test_crlf_paired_anchored():
 
 
 def test_kernel_autotune_keeps_output_identical(monkeypatch):
-    """Without BK_KERNEL the context tries both kernels on its first large batches and keeps the faster;
+    """With BK_KERNEL=auto the context tries both kernels on its first large batches and keeps the faster;
     whichever runs, the bytes are the same."""
-    monkeypatch.delenv("BK_KERNEL", raising=False)
+    monkeypatch.setenv("BK_KERNEL", "auto")
     p1, p2, paired = CONFIG_PATTERNS["C2"]
     ctx = make_ctx(p1, p2, k=1, paired=True)
     n = 250000
@@ -253,6 +253,7 @@ def test_kernel_autotune_keeps_output_identical(monkeypatch):
         crcs.add((zlib.crc32(ctx.d2h(d_o1, res.out1_len).tobytes()), zlib.crc32(ctx.d2h(d_o2, res.out2_len).tobytes()),
                   res.n_out))
     assert len(crcs) == 1
+    assert ctx.kernel_variant() in (4, 5)     # settled after 2 + 2 trial launches
     ctx.close()
 
 

@@ -29,7 +29,7 @@ rc = _lib.lib.bk_debug_events(ctx.handle, ntiles, lo, n, ev.ctypes.data)
 assert rc == 0, rc
 ev = ev.astype(np.int64)
 print("kernel_ms", r.kernel_ms, "Mpairs/s", P / r.kernel_ms / 1e3, "tiles", ntiles)
-V5 = os.environ.get("BK_KERNEL", "5") != "4" and NAME in ("C1", "C2", "C3")
+V5 = os.environ.get("BK_KERNEL", "4") == "5" and NAME in ("C1", "C2", "C3")
 def iv(a, b, label):
     d = ev[:, b] - ev[:, a]
     d = d[(ev[:, a] > 0) & (ev[:, b] > 0)]
