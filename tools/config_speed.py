@@ -7,7 +7,10 @@ from tests.util import CONFIG_PATTERNS, lib_syn_config
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 4000000
 rl = 329
+ONLY = os.environ.get("BK_ONLY")   # e.g. BK_ONLY=C4: one config (k = 1), for profiling
 for name, k in (("C1", 1), ("C2", 1), ("C3", 1), ("C4", 0), ("C4", 1), ("C4", 2)):
+    if ONLY and (name != ONLY or k != 1):
+        continue
     p1, p2, paired = CONFIG_PATTERNS[name]
     prog1 = _lib.Program(p1, k) if p1 else None
     prog2 = _lib.Program(p2, k) if p2 else None
