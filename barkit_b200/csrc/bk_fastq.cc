@@ -70,6 +70,7 @@ extern "C" int bk_tokenize(const uint8_t* text, uint64_t len, int final_chunk, u
 // output here from the caller's input buffer and the device's match table: kept records in input
 // order, runs of consecutive kept records that already have the writer's framing as one memcpy.
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <vector>
 #if defined(__SSE2__)
@@ -157,7 +158,7 @@ uint64_t gather_kept(const uint8_t* text, const uint32_t* off, uint32_t n, const
                      uint64_t cap, int max_threads) {
   if (n == 0) return 0;
   int T = n < 50000 ? 1 : std::max(1, std::min(max_threads, 32));
-  std::vector<uint64_t> raw((size_t)T + 1, 0), wrote((size_t)T, 0);
+  std::vector<uint64_t> raw((size_t)T + 1, 0), wrote((size_t)T, 0), start((size_t)T, 0);
   std::vector<uint32_t> lo((size_t)T + 1);
   for (int t = 0; t <= T; ++t) lo[t] = (uint32_t)((uint64_t)n * t / T);
   auto count = [&](int t) {
@@ -167,7 +168,7 @@ uint64_t gather_kept(const uint8_t* text, const uint32_t* off, uint32_t n, const
     raw[t + 1] = s;
   };
   auto copy = [&](int t) {
-    uint8_t* o = out + raw[t];
+    uint8_t* o = out + start[t];
     uint8_t* const o0 = o;
     uint32_t i = lo[t];
     const uint32_t hi = lo[t + 1];
@@ -190,21 +191,36 @@ uint64_t gather_kept(const uint8_t* text, const uint32_t* off, uint32_t n, const
 #endif
     wrote[t] = (uint64_t)(o - o0);
   };
-  auto run = [&](auto&& fn) {
-    if (T == 1) { fn(0); return; }
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; ++t) th.emplace_back(fn, t);
-    fn(0);
-    for (auto& x : th) x.join();
+  // one set of threads for both passes: every thread counts its part, they meet (the counts are all it takes
+  // to place the parts), then every thread copies its part
+  std::atomic<int> counted{0};
+  std::atomic<bool> too_big{false};
+  auto both = [&](int t) {
+    count(t);
+    counted.fetch_add(1, std::memory_order_acq_rel);
+    while (counted.load(std::memory_order_acquire) < T) std::this_thread::yield();
+    uint64_t before = 0, all = 0;
+    for (int u = 0; u < T; ++u) {
+      if (u < t) before += raw[u + 1];
+      all += raw[u + 1];
+    }
+    if (all + 1 > cap) { too_big = true; return; }  // (+1: a final record without EOL gains one)
+    start[t] = before;
+    copy(t);
   };
-  run(count);
-  for (int t = 0; t < T; ++t) raw[t + 1] += raw[t];
-  if (raw[T] + 1 > cap) return UINT64_MAX;  // (+1: a final record without EOL gains one)
-  run(copy);
+  if (T == 1) {
+    both(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(both, t);
+    both(0);
+    for (auto& x : th) x.join();
+  }
+  if (too_big.load()) return UINT64_MAX;
   // close the parts up (moves nothing when every part is exactly as long as its input records)
   uint64_t pos = 0;
   for (int t = 0; t < T; ++t) {
-    const uint64_t from = raw[t];
+    const uint64_t from = start[t];
     if (from != pos && wrote[t]) memmove(out + pos, out + from, wrote[t]);
     pos += wrote[t];
   }
