@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(cons
           }
           ms = match_unanchored(tab, rv.seq, rv.seq_len, can && !(split && lane >= 16), lane);  // warp per read
         } else if (can) {
-          ms = match_read<false>(tab, rv.seq, rv.seq_len);  // lane per read
+          ms = GENERAL ? match_read_shared(tab, rv.seq, rv.seq_len) : match_read<false>(tab, rv.seq, rv.seq_len);  // lane per read
         }
         if (GENERAL && !(VAR && var_me) && can && ms < 0 && rc) ms = match_read<true>(tab, rv.seq, rv.seq_len);  // parse.rs:61-66
       } else {

@@ -410,6 +410,22 @@ __device__ __forceinline__ bool match_at(uint32_t tab, uint32_t seq, uint32_t L,
   return ok;
 }
 
+// One out-of-line copy of the forward matcher for the general kernels, whose hot code is past the instruction
+// cache: the anchored mate's match and the verification step of the unanchored search
+// share it instead of carrying an inlined copy each.
+__device__ __noinline__ bool match_at_fwd_shared(uint32_t tab, uint32_t seq, uint32_t s) {
+  return match_at_fwd<false>(tab, seq, s);
+}
+// match_read<false> on top of it
+__device__ __noinline__ int match_read_shared(uint32_t tab, uint32_t seq, uint32_t L) {
+  const uint4 h = lds128(tab + kTabHdr);  // nops, total_len, anchor_start, anchor_end
+  const uint32_t T = h.y;
+  if (L < T || !(h.z || h.w)) return -1;
+  if (h.z && h.w && L != T) return -1;
+  const uint32_t s = h.w ? L - T : 0;
+  return match_at_fwd_shared(tab, seq, s) ? (int)s : -1;
+}
+
 // leftmost match start or -1, one lane per read.  Forward strand:
 // anchored patterns only (one candidate start); the unanchored forward search is match_unanchored.
 template <bool RC>
@@ -528,7 +544,7 @@ __device__ __noinline__ int match_unanchored(uint32_t tab, uint32_t seq, uint32_
     if (pend) {
       if (cand < 0) {
         pend = false;
-      } else if (!filt || match_at<false, false>(tab, seq, 0u, (uint32_t)cand)) {
+      } else if (!filt || match_at_fwd_shared(tab, seq, (uint32_t)cand)) {
         ms = cand;
         pend = false;
       } else {
