@@ -358,6 +358,7 @@ def main():
         e2e = {"value": world * args.steps * Q / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(d2h[0]), "d2h_bytes_per_step": int(d2h[1]),
                "pairs_per_step": Q, "ms_per_step": 1e3 * e2e_s / args.steps,
+               "host_threads": int(os.environ.get("BK_HOST_THREADS", "0")),
                "note": "bk_submit/bk_wait with pinned host buffers, 2 slots in flight; h2d/d2h bytes as the "
                        "library counts them (text + record offsets in, FASTQ text + result + match table out). "
                        "R2 has no pattern in this config: it stays on the host and its output (the kept "
