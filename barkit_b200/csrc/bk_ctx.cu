@@ -162,7 +162,8 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   // memory (the general ones carry the search-sharing buffers), so the budget is taken from the kernel itself.
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR>));
-  const size_t target = std::min<size_t>(kTargetDynSmem, (233472 / 2 - fa.sharedSizeBytes) & ~size_t(127));
+  constexpr int kWant = PAIRED ? 2 : 4;  // CTAs per SM the kernel is compiled for (launch bounds): 30-36 warps per SM
+  const size_t target = std::min<size_t>(kTargetDynSmem, (233472 / kWant - fa.sharedSizeBytes) & ~size_t(127));
   uint32_t R = bk::kTileRecs;
   // prefer several resident tiles per SM; never go below 8 records unless a tile would not fit
   while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > target) --R;
@@ -182,7 +183,7 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
                             (int)lp->smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR>,
                                                      bk::cta_warps(PAIRED) * 32, lp->smem));
-    if (per_sm >= 2 || other < 2 || R <= 8) break;  // (records too long to share the SM: the tile stays as it is)
+    if (per_sm >= kWant || other < kWant || R <= 24) break;  // (long records: the tile stays as it is, fewer CTAs share the SM)
     --R;
   }
   lp->ntiles = (n + R - 1) / R;

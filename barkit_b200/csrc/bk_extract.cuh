@@ -167,7 +167,7 @@ constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + 
 // repetition, bk_pattern.cc); the matched variant travels with the match start (start | variant << 24) and
 // supplies the capture offsets, the match length and the header growth of that record.
 template <bool PAIRED, bool GENERAL, bool VAR = false>
-__global__ void __launch_bounds__(cta_warps(PAIRED) * 32, 2) extract_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extract_kernel(const __grid_constant__ KParams P) {
   static_assert(!VAR || GENERAL, "variants are matched by the general kernel");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
