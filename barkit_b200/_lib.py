@@ -25,6 +25,7 @@ BK_OK = 0
 BK_E_PATTERN, BK_E_UNSUPPORTED, BK_E_CUDA, BK_E_CAPACITY, BK_E_IO, BK_E_ARG, BK_E_FORMAT = \
     -1, -2, -3, -4, -5, -6, -7
 FLAG_PAIRED, FLAG_SKIP_TRIM, FLAG_RC = 1, 2, 4
+FLAG_DEVICE_BOTH_MATES, FLAG_HOST_MATE_PINNED, FLAG_VERBOSE = 8, 16, 32
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -59,7 +60,8 @@ class RunArgs(C.Structure):
                 ("pattern2", C.c_char_p), ("out_fq1", C.c_char_p), ("out_fq2", C.c_char_p),
                 ("max_memory_mb", C.c_size_t), ("threads", C.c_size_t), ("rc_barcodes", C.c_int),
                 ("skip_trimming", C.c_int), ("max_error", C.c_size_t), ("compression", C.c_int),
-                ("quiet", C.c_int), ("force", C.c_int), ("n_gpus", C.c_int)]
+                ("quiet", C.c_int), ("force", C.c_int), ("n_gpus", C.c_int), ("verbose", C.c_int),
+                ("ctx_flags", C.c_uint32)]
 
 
 # every symbol include/barkit_b200.h declares: (restype, argtypes)
@@ -97,7 +99,7 @@ SYMBOLS = {
                                     C.c_void_p, C.c_int, C.POINTER(Result)]),
     "bk_tokenize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, u32p,
                                      C.POINTER(C.c_uint64), u32p]),
-    "bk_kernel_variant": (C.c_int, [C.c_void_p]),
+    "bk_ctx_set_host_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "bk_warmup": (C.c_int, [C.c_int]),
     "bk_program_nvariants": (C.c_int, [C.c_void_p]),
     "bk_debug_events": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
@@ -215,9 +217,10 @@ class Context:
     """bk_ctx handle: one GPU, compiled programs, run.rs flags."""
 
     def __init__(self, p1: Program | None, p2: Program | None = None, paired: bool = False,
-                 skip_trimming: bool = False, rc_barcodes: bool = False, device: int = 0):
+                 skip_trimming: bool = False, rc_barcodes: bool = False, device: int = 0,
+                 extra_flags: int = 0, host_threads: int | None = None):
         flags = (FLAG_PAIRED if paired else 0) | (FLAG_SKIP_TRIM if skip_trimming else 0) | \
-                (FLAG_RC if rc_barcodes else 0)
+                (FLAG_RC if rc_barcodes else 0) | extra_flags
         err = C.create_string_buffer(1024)
         st = C.c_int(0)
         self.handle = lib.bk_ctx_create(device, p1.handle if p1 else None, p2.handle if p2 else None,
@@ -226,6 +229,8 @@ class Context:
             raise BarkitError(st.value, err.value.decode())
         self.paired = paired
         self._keep = (p1, p2)
+        if host_threads is not None:
+            self._check(lib.bk_ctx_set_host_threads(self.handle, host_threads))
 
     def close(self):
         if self.handle:
@@ -321,10 +326,6 @@ class Context:
                         d_text: int, d_off: int):
         self._check(lib.bk_generate_device(self.handle, C.byref(cfg), mate, seed, first_idx, n,
                                            d_text, d_off))
-
-    def kernel_variant(self) -> int:
-        """4 / 5 = the extract kernel in use, 0 = still being chosen (see bk_kernel_variant)."""
-        return lib.bk_kernel_variant(self.handle)
 
     def extract_device(self, n, m1: MateIn, m2: MateIn | None, d_out1, cap1, d_out2=0, cap2=0,
                        d_match1=0, d_match2=0, iters=1) -> Result:

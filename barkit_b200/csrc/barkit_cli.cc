@@ -1,6 +1,6 @@
 // `barkit` command line: flag-for-flag the clap definition of the reference (src/lib.rs:3-114,
-// src/main.rs:3-38), forwarding to bk_run (= run::run).  One extension: --gpus N (default: all
-// visible devices).
+// src/main.rs:3-38), forwarding to bk_run (= run::run).  Extensions: --gpus N (default: one GPU per
+// 2 GiB of input text per mate, at most all visible devices) and --verbose.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -50,7 +50,8 @@ static void usage_extract(FILE* f) {
       "  -f, --force                 Overwrite output files\n"
       "  -s, --skip-trimming         Skip trimming the adapter sequence from the read\n"
       "  -e, --max-error <MAX_ERROR> Max error (mismatch) between provided pattern and read sequence [default: 1]\n"
-      "      --gpus <N>              GPUs to use [default: all visible] (B200 build only)\n"
+      "      --gpus <N>              GPUs to use [default: one per 2 GiB of input per mate, at most all visible] (B200 build only)\n"
+      "      --verbose               Per-stage timings on stderr (B200 build only)\n"
       "  -h, --help                  Print help\n",
       f);
 }
@@ -74,7 +75,7 @@ int main(int argc, char** argv) {
   bool has_fq1 = false, has_fq2 = false, has_out1 = false, has_out2 = false, has_p1 = false, has_p2 = false;
   bool gz = false, bgz = false, mgz = false, lz4 = false, rc = false, skip = false, quiet = false, force = false;
   size_t max_memory = 0, threads = 1, max_error = 1, gpus = 0;
-  bool in_extract = false;
+  bool in_extract = false, verbose = false;
 
   std::vector<std::string> args(argv + 1, argv + argc);
   size_t i = 0;
@@ -139,6 +140,8 @@ int main(int argc, char** argv) {
       if (!parse_size(value(name, inl, has_inl).c_str(), &max_error)) die_usage("invalid value for '--max-error <MAX_ERROR>'");
     } else if (name == "--gpus") {
       if (!parse_size(value(name, inl, has_inl).c_str(), &gpus)) die_usage("invalid value for '--gpus <N>'");
+    } else if (name == "--verbose") {
+      verbose = true;
     } else {
       die_usage("unexpected argument '" + a + "' found");
     }
@@ -176,6 +179,7 @@ int main(int argc, char** argv) {
   ra.quiet = quiet;
   ra.force = force;
   ra.n_gpus = (int)gpus;
+  ra.verbose = verbose;
   char err[2048];
   err[0] = 0;
   int rc_run = bk_run(&ra, err, sizeof err);

@@ -19,13 +19,13 @@
 #include "../../include/barkit_b200.h"
 #include "bk_internal.h"
 #include "bk_extract.cuh"
-#include "bk_extract5.cuh"
 #include "bk_tokenize.cuh"
 
 namespace {
 
 constexpr int kSlots = 2;
 constexpr size_t kMaxDynSmem = 200 * 1024;    // leave room for >= 1 CTA/SM with static smem
+constexpr uint32_t kPassMinRecords = 200000;  // batches large enough to judge the host copy against the bus
 constexpr size_t kTargetDynSmem = 101 * 1024 + 512;  // aim for >= 3 resident CTAs (input ring + output tile) per SM
 
 struct DevBuf {
@@ -49,7 +49,6 @@ struct Slot {
   uint64_t out_cap[2] = {0, 0};
   bool busy = false;
   uint32_t launches = 0;
-  int variant = 4;  // kernel the batch in flight was launched with
   // host pass-through of the mate without a pattern (see bk_submit)
   bool passthrough = false;
   int pt = -1;                   // index of the mate kept on the host for the batch in flight
@@ -59,16 +58,6 @@ struct Slot {
   size_t h_match_cap = 0;
   uint64_t h2d_bytes = 0;        // of the batch in flight
 };
-
-// Launches whose patterns are all anchored at the read start can run on either extract kernel
-// (identical output); which one is faster depends on the pattern and the record shape, so the first
-// large batches of a context try both (twice each) and the context keeps the faster.
-struct Tuner {
-  int choice = 0;  // 0 = still trying, else 4 or 5
-  int trials[2] = {0, 0};
-  double best[2] = {1e30, 1e30};  // ms per record
-};
-constexpr uint32_t kTuneMinRecords = 200000;
 
 }  // namespace
 
@@ -84,7 +73,6 @@ struct bk_ctx {
   int sm_count = 0;
   Slot slot[kSlots];
   DevBuf tok;  // bk_tokenize_device scratch: block counts + TokResult
-  Tuner tuner;
   // Paired mode with exactly one pattern: the mate without one stays on the host (pass_mate = its index)
   // and `solo` is the single-end view of this context that processes the other mate.
   int pass_mate = -1;
@@ -93,7 +81,7 @@ struct bk_ctx {
   // The host copy is worth it while it takes less time than the bus would need for the same mate.
   // Both are measured on every large pass-through batch; when the host side is the slower one twice in
   // a row (few or slow host cores, several GPUs sharing the host's memory bandwidth) the context
-  // sends both mates to the device from then on.  BK_HOST_PASSTHROUGH=1 pins the host copy.
+  // sends both mates to the device from then on.  BK_FLAG_HOST_MATE_PINNED pins the host copy.
   bool pass_pinned = false;
   int pass_slow = 0;
   std::string last_error;
@@ -191,91 +179,9 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
   lp->grid = (int)std::max<long long>(grid, 1);
-  if (getenv("BK_DEBUG"))
+  if (ctx->flags & BK_FLAG_VERBOSE)
     fprintf(stderr, "[bk] tile_recs %u smem %zu B ctas/sm %d grid %d ntiles %u\n", lp->tile_recs, lp->smem, per_sm,
             lp->grid, lp->ntiles);
-  return BK_OK;
-}
-
-// extract_kernel5 (bk_extract5.cuh) serves launches whose patterns are all anchored at the read start
-// (and short enough for the scout's window); BK_KERNEL=4 keeps every launch on extract_kernel.
-bool v5_eligible(const bk_ctx* ctx) {
-  if (needs_general(ctx)) return false;
-  for (int m = 0; m < 2; ++m)
-    if (ctx->prog[m].present && (!ctx->prog[m].anchor_start || ctx->prog[m].total_len > bk::v5::kMaxPatLen)) return false;
-  return true;
-}
-
-// 4 = extract_kernel, 5 = extract_kernel5.  extract_kernel is the default: on every BASELINE config it is the
-// faster one.  BK_KERNEL=5 sends every launch that qualifies to extract_kernel5;
-// BK_KERNEL=auto lets the context time both on its first large batches and keep the faster.
-int pick_variant(bk_ctx* ctx, uint32_t n) {
-  if (!v5_eligible(ctx)) return 4;
-  const char* k = getenv("BK_KERNEL");
-  if (!k || k[0] == '4') return 4;
-  if (k[0] == '5') return 5;
-  if (k[0] != 'a') return 4;
-  if (ctx->tuner.choice) return ctx->tuner.choice;
-  if (n < kTuneMinRecords) return 4;
-  return ctx->tuner.trials[1] < ctx->tuner.trials[0] ? 5 : 4;
-}
-
-void report_variant(bk_ctx* ctx, int variant, uint32_t n, double ms) {
-  Tuner& t = ctx->tuner;
-  const char* k = getenv("BK_KERNEL");
-  if (!k || k[0] != 'a' || t.choice || n < kTuneMinRecords || !v5_eligible(ctx) || ms <= 0) return;
-  const int i = variant == 5 ? 1 : 0;
-  t.trials[i] += 1;
-  t.best[i] = std::min(t.best[i], ms / n);
-  if (t.trials[0] >= 2 && t.trials[1] >= 2) {
-    t.choice = t.best[1] < t.best[0] ? 5 : 4;
-    if (getenv("BK_DEBUG"))
-      fprintf(stderr, "[bk] tuner: extract_kernel %.3f ns/record, extract_kernel5 %.3f ns/record -> %d\n", t.best[0] * 1e6,
-              t.best[1] * 1e6, t.choice);
-  }
-}
-
-size_t smem_for5(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_t in_cap[2], uint32_t out_cap[2]) {
-  size_t total = 0;
-  int nm = ctx->paired ? 2 : 1;
-  for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
-  for (int m = 0; m < nm; ++m) {
-    uint32_t growth = ctx->prog[m].present ? ctx->growth[m] : 0;
-    in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
-    out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
-    total += bk::v5::kData * (size_t)in_cap[m] + out_cap[m];
-  }
-  return total;
-}
-
-template <bool PAIRED>
-int plan_launch5(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
-  cudaFuncAttributes fa;
-  CK(cudaFuncGetAttributes(&fa, bk::v5::extract_kernel5<PAIRED>));
-  // two CTAs per SM: 228 KB per SM, 1 KB reserved per CTA, the kernel's static shared memory on top
-  const size_t target = (233472 / 2 - 1024 - fa.sharedSizeBytes) & ~size_t(127);
-  uint32_t R = bk::kTileRecs;
-  while (R > 8 && smem_for5(ctx, R, maxrec, lp->in_cap, lp->out_cap) > target) --R;
-  while (R > 0 && smem_for5(ctx, R, maxrec, lp->in_cap, lp->out_cap) > kMaxDynSmem) --R;
-  if (R == 0) {
-    ctx->last_error = "record too long for the on-chip staging buffer";
-    return BK_E_CAPACITY;
-  }
-  lp->tile_recs = R;
-  lp->smem = smem_for5(ctx, R, maxrec, lp->in_cap, lp->out_cap);
-  lp->ntiles = (n + R - 1) / R;
-  CK(cudaFuncSetAttribute(bk::v5::extract_kernel5<PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp->smem));
-  CK(cudaFuncSetAttribute(bk::v5::extract_kernel5<PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                          cudaSharedmemCarveoutMaxShared));
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::v5::extract_kernel5<PAIRED>, bk::v5::cta_warps(PAIRED) * 32, lp->smem));
-  if (per_sm < 1) per_sm = 1;
-  long long grid = (long long)per_sm * ctx->sm_count;
-  if (grid > (long long)lp->ntiles) grid = lp->ntiles;
-  lp->grid = (int)std::max<long long>(grid, 1);
-  if (getenv("BK_DEBUG"))
-    fprintf(stderr, "[bk] v5 tile_recs %u smem %zu B (+%zu static) ctas/sm %d grid %d ntiles %u\n", lp->tile_recs, lp->smem,
-            (size_t)fa.sharedSizeBytes, per_sm, lp->grid, lp->ntiles);
   return BK_OK;
 }
 
@@ -292,7 +198,7 @@ size_t scratch_bytes(uint32_t ntiles) { return events_offset(ntiles); }
 // enqueue: scratch reset + extract kernel.  All pointers are device pointers.
 int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
                     const bk_mate_in* in2, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
-                    int32_t* match1, int32_t* match2, uint32_t* launches, int variant) {
+                    int32_t* match1, int32_t* match2, uint32_t* launches) {
   if (ctx->paired && !in2) { ctx->last_error = "paired context needs two mates"; return BK_E_ARG; }
   if (!ctx->paired && in2) { ctx->last_error = "single-end context got two mates"; return BK_E_ARG; }
   const bk_mate_in* in[2] = {in1, in2};
@@ -310,10 +216,8 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   }
   LaunchPlan lp;
   const bool general = needs_general(ctx);
-  const bool v5 = variant == 5 && v5_eligible(ctx);
   const bool var = has_variants(ctx);
-  int rc = v5 ? (ctx->paired ? plan_launch5<true>(ctx, n, maxrec, &lp) : plan_launch5<false>(ctx, n, maxrec, &lp))
-           : var ? (ctx->paired ? plan_launch<true, true, true>(ctx, n, maxrec, &lp) : plan_launch<false, true, true>(ctx, n, maxrec, &lp))
+  int rc = var ? (ctx->paired ? plan_launch<true, true, true>(ctx, n, maxrec, &lp) : plan_launch<false, true, true>(ctx, n, maxrec, &lp))
            : ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))
                        : (general ? plan_launch<false, true>(ctx, n, maxrec, &lp) : plan_launch<false, false>(ctx, n, maxrec, &lp));
   if (rc != BK_OK) return rc;
@@ -349,11 +253,7 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.tile_recs = lp.tile_recs;
   P.flags = ctx->flags;
   if (n > 0) {
-    if (v5 && ctx->paired)
-      bk::v5::extract_kernel5<true><<<lp.grid, bk::v5::cta_warps(true) * 32, lp.smem, stream>>>(P);
-    else if (v5)
-      bk::v5::extract_kernel5<false><<<lp.grid, bk::v5::cta_warps(false) * 32, lp.smem, stream>>>(P);
-    else if (var && ctx->paired)
+    if (var && ctx->paired)
       bk::extract_kernel<true, true, true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
     else if (var)
       bk::extract_kernel<false, true, true><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
@@ -469,13 +369,12 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
       return fail(BK_E_CUDA, m);
     }
   }
-  const char* hp = getenv("BK_HOST_PASSTHROUGH");
-  if (ctx->paired && (p1 == nullptr) != (p2 == nullptr) && !(hp && hp[0] == '0')) {
+  if (ctx->paired && (p1 == nullptr) != (p2 == nullptr) && !(flags & BK_FLAG_DEVICE_BOTH_MATES)) {
     bk_ctx* solo = new (std::nothrow) bk_ctx();
     if (!solo) { bk_ctx_destroy(ctx); return fail(BK_E_CAPACITY, "out of memory"); }
     ctx->pass_mate = p1 ? 1 : 0;
     solo->device = device;
-    solo->flags = flags & ~(uint32_t)BK_FLAG_PAIRED;
+    solo->flags = flags & ~(uint32_t)(BK_FLAG_PAIRED | BK_FLAG_DEVICE_BOTH_MATES | BK_FLAG_HOST_MATE_PINNED);
     solo->paired = false;
     solo->sm_count = ctx->sm_count;
     memset(solo->prog, 0, sizeof solo->prog);
@@ -484,11 +383,9 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
     solo->vdev[0] = ctx->vdev[1 - ctx->pass_mate];  // (shared, owned by ctx)
     solo->growth[0] = ctx->growth[1 - ctx->pass_mate];
     ctx->solo = solo;
-    const char* ht = getenv("BK_HOST_THREADS");
-    int nt = ht ? atoi(ht) : (int)std::thread::hardware_concurrency();
-    ctx->host_threads = std::max(1, std::min(nt, 32));
-    ctx->pass_pinned = hp && hp[0] == '1';
+    ctx->pass_pinned = (flags & BK_FLAG_HOST_MATE_PINNED) != 0;
   }
+  ctx->host_threads = std::max(1, std::min((int)std::thread::hardware_concurrency(), 32));
   if (status) *status = BK_OK;
   if (err && errcap) err[0] = 0;
   return ctx;
@@ -534,6 +431,12 @@ void bk_host_free(void* p) {
 }
 
 int bk_ctx_nslots(const bk_ctx* ctx) { return ctx ? kSlots : 0; }
+
+int bk_ctx_set_host_threads(bk_ctx* ctx, int n) {
+  if (!ctx || n < 1) return BK_E_ARG;
+  ctx->host_threads = std::min(n, 64);
+  return BK_OK;
+}
 
 uint64_t bk_out_bound(const bk_ctx* ctx, int mate, uint32_t n, uint64_t text_len) {
   if (!ctx || mate < 1 || mate > 2) return 0;
@@ -589,10 +492,9 @@ int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk
     d.text = (const uint8_t*)s.text[pm].p;
     d.rec_off = (const uint32_t*)s.off[pm].p;
     s.launches = 0;
-    s.variant = pick_variant(solo, n);
     CK(cudaEventRecord(s.ev0, s.stream));
     rc = enqueue_extract(solo, &s, s.stream, n, &d, nullptr, (uint8_t*)s.out[pm].p, ob, nullptr, 0,
-                         (int32_t*)s.match.p, nullptr, &s.launches, s.variant);
+                         (int32_t*)s.match.p, nullptr, &s.launches);
     if (rc != BK_OK) { ctx->last_error = solo->last_error; return rc; }
     CK(cudaEventRecord(s.ev1, s.stream));
     CK(cudaMemcpyAsync(s.h_res, (uint8_t*)s.scratch.buf.p + 64, sizeof(bk::DevResult), cudaMemcpyDeviceToHost, s.stream));
@@ -617,11 +519,10 @@ int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk
     dev[m].rec_off = (const uint32_t*)s.off[m].p;
   }
   s.launches = 0;
-  s.variant = pick_variant(ctx, n);
   CK(cudaEventRecord(s.ev0, s.stream));
   int rc = enqueue_extract(ctx, &s, s.stream, n, &dev[0], ctx->paired ? &dev[1] : nullptr,
                            (uint8_t*)s.out[0].p, s.out_cap[0], (uint8_t*)s.out[1].p, s.out_cap[1], nullptr,
-                           nullptr, &s.launches, s.variant);
+                           nullptr, &s.launches);
   if (rc != BK_OK) return rc;
   CK(cudaEventRecord(s.ev1, s.stream));
   CK(cudaMemcpyAsync(s.h_res, (uint8_t*)s.scratch.buf.p + 64, sizeof(bk::DevResult), cudaMemcpyDeviceToHost,
@@ -636,7 +537,12 @@ int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, 
   CK(cudaSetDevice(ctx->device));
   Slot& s = ctx->slot[slot];
   if (!s.busy) { ctx->last_error = "slot has no batch in flight"; return BK_E_ARG; }
-  s.busy = false;
+  // On every path out of here -- errors included -- whatever is still enqueued on the slot's stream (the
+  // output copies below read the slot's device buffers) has finished before the slot counts as free again.
+  struct Drain {
+    Slot& s;
+    ~Drain() { cudaStreamSynchronize(s.stream); s.busy = false; }
+  } drain{s};
   CK(cudaStreamSynchronize(s.stream));
   bk::DevResult r = *s.h_res;
   int rc = check_dev_result(ctx, r);
@@ -658,11 +564,11 @@ int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, 
     CK(cudaEventElapsedTime(&h2d_ms, s.evh0, s.evh1));
     // what the bus would have needed for this mate's text, at the rate the other mate's just moved
     const double bus_ms = h2d_ms * (double)s.host_pt.text_len / (double)std::max<uint64_t>(s.h2d_bytes, 1);
-    if (!ctx->pass_pinned && s.n >= kTuneMinRecords) {
+    if (!ctx->pass_pinned && s.n >= kPassMinRecords) {
       ctx->pass_slow = gather_ms > h2d_ms + bus_ms ? ctx->pass_slow + 1 : 0;
       if (ctx->pass_slow >= 2) ctx->pass_mate = -1;  // (slots in flight finish as they were submitted)
     }
-    if (getenv("BK_DEBUG"))
+    if (ctx->flags & BK_FLAG_VERBOSE)
       fprintf(stderr, "[bk] host gather: %u records, %llu bytes, %d threads, %.2f ms; bus: %.2f ms for the other mate, "
               "%.2f ms more for this one%s\n", s.n, (unsigned long long)got, ctx->host_threads, gather_ms, h2d_ms, bus_ms,
               ctx->pass_mate < 0 ? " -> both mates go to the device from now on" : "");
@@ -670,7 +576,6 @@ int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, 
     if (got == UINT64_MAX) { ctx->last_error = "output buffer too small"; return BK_E_CAPACITY; }
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
-    report_variant(ctx->solo, s.variant, s.n, ms);
     bk::DevResult rr = r;  // single-end result -> this context's mates
     rr.out_len[pm] = r.out_len[0];
     rr.out_len[pt] = got;
@@ -695,7 +600,6 @@ int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, 
   CK(cudaStreamSynchronize(s.stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
-  report_variant(ctx, s.variant, s.n, ms);
   fill_result(res, r, s.n, ms, s.launches);
   if (res) {
     res->h2d_bytes = s.h2d_bytes;
@@ -744,11 +648,10 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
   Slot& s = ctx->slot[0];
   if (s.busy) { ctx->last_error = "slot 0 is busy"; return BK_E_ARG; }
   uint32_t launches = 0;
-  const int variant = pick_variant(ctx, n);
   CK(cudaEventRecord(s.ev0, s.stream));
   for (int it = 0; it < iters; ++it) {
     int rc = enqueue_extract(ctx, &s, s.stream, n, d_in1, d_in2, d_out1, cap1, d_out2, cap2, d_match1, d_match2,
-                             &launches, variant);
+                             &launches);
     if (rc != BK_OK) return rc;
   }
   CK(cudaEventRecord(s.ev1, s.stream));
@@ -758,18 +661,8 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
   bk::DevResult r = *s.h_res;
-  report_variant(ctx, variant, n, ms / iters);
   fill_result(res, r, n, ms / iters, launches);
   return check_dev_result(ctx, r);
-}
-
-int bk_kernel_variant(const bk_ctx* ctx) {
-  if (!ctx) return BK_E_ARG;
-  if (!v5_eligible(ctx)) return 4;
-  const char* k = getenv("BK_KERNEL");
-  if (!k || k[0] == '4') return 4;
-  if (k[0] == '5') return 5;
-  return k[0] == 'a' ? ctx->tuner.choice : 4;
 }
 
 int bk_debug_events(bk_ctx* ctx, uint32_t ntiles, uint32_t first_tile, uint32_t count, uint64_t* out) {

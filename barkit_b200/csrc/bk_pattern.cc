@@ -506,6 +506,11 @@ int find_quantifiers(const std::string& p, std::vector<Quant>* out, std::string*
   bool in_class = false;
   size_t class_open = 0;
   char prev = 0;  // last character of the atom before position i (outside classes)
+  // A group that contains a variable quantifier must not be repeated: `(A?C){3}` gives every copy its own
+  // length in the regex crate (8 combinations), while substituting one length per quantifier would give all
+  // copies the same one.  Such patterns are refused, not approximated.
+  std::vector<char> open_has_var;  // one entry per open group: a variable quantifier was seen inside
+  bool closed_has_var = false;     // ... for the group that was closed last (valid while prev == ')')
   for (size_t i = 0; i < p.size();) {
     const char c = p[i];
     if (in_class) {
@@ -527,6 +532,15 @@ int find_quantifiers(const std::string& p, std::vector<Quant>* out, std::string*
         }
       }
       prev = '(';
+      open_has_var.push_back(0);
+      continue;
+    }
+    if (c == ')') {
+      closed_has_var = !open_has_var.empty() && open_has_var.back();
+      if (!open_has_var.empty()) open_has_var.pop_back();
+      if (closed_has_var && !open_has_var.empty()) open_has_var.back() = 1;  // the enclosing group contains it too
+      prev = ')';
+      ++i;
       continue;
     }
     if (c == '*' || c == '+') return unsupported(std::string("unbounded repetition ") + c);
@@ -539,7 +553,11 @@ int find_quantifiers(const std::string& p, std::vector<Quant>* out, std::string*
         long lo = 0, hi = 0;
         size_t d1 = 0, d2 = 0;
         while (j < p.size() && p[j] >= '0' && p[j] <= '9' && lo < 100000) { lo = lo * 10 + (p[j] - '0'); ++j; ++d1; }
-        if (d1 == 0 || j >= p.size() || p[j] != ',') { i = j; prev = '}'; continue; }  // {n} or malformed: the lowering's business
+        if (d1 == 0 || j >= p.size() || p[j] != ',') {  // {n} or malformed: the lowering's business
+          if (d1 > 0 && prev == ')' && closed_has_var && lo != 1)
+            return unsupported("repetition of a group that contains variable repetition");
+          i = j; prev = '}'; continue;
+        }
         ++j;
         while (j < p.size() && p[j] >= '0' && p[j] <= '9' && hi < 100000) { hi = hi * 10 + (p[j] - '0'); ++j; ++d2; }
         if (d2 == 0) return unsupported("unbounded repetition {m,}");
@@ -556,6 +574,7 @@ int find_quantifiers(const std::string& p, std::vector<Quant>* out, std::string*
       if (q.end < p.size() && (p[q.end] == '?' || p[q.end] == '*' || p[q.end] == '+' || p[q.end] == '{'))
         return unsupported("stacked repetition");
       out->push_back(q);
+      for (char& g : open_has_var) g = 1;
       i = q.end;
       prev = '}';
       continue;

@@ -213,7 +213,7 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   Logger log;
   log.quiet = a->quiet != 0;
   log.message("Estimating reads count...");  // run.rs:97 / :215
-  const bool dbg = getenv("BK_DEBUG") != nullptr;
+  const bool dbg = a->verbose != 0;
   const double t_begin = now_s();
 
   // the CUDA contexts come up while the host scans the input
@@ -308,12 +308,18 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   std::string first_error;
   std::mutex emu;
   auto fail = [&](int code, const std::string& m) {
-    std::lock_guard<std::mutex> g(emu);
-    if (status.load() == BK_OK) { status = code; first_error = m; }
+    {
+      std::lock_guard<std::mutex> g(emu);
+      if (status.load() == BK_OK) { first_error = m; status = code; }
+    }
+    // The writers test `status` under wmu before they block: taking it here closes the window between
+    // their test and their wait, in which a notification would be lost and the run would hang.
+    { std::lock_guard<std::mutex> lk(wmu); }
     wcv.notify_all();
   };
   const uint32_t flags = (pe ? BK_FLAG_PAIRED : 0) | (a->skip_trimming ? BK_FLAG_SKIP_TRIM : 0) |
-                         (a->rc_barcodes ? BK_FLAG_RC : 0);
+                         (a->rc_barcodes ? BK_FLAG_RC : 0) | (dbg ? BK_FLAG_VERBOSE : 0) |
+                         (a->ctx_flags & (BK_FLAG_DEVICE_BOTH_MATES | BK_FLAG_HOST_MATE_PINNED));
 
   // One worker per GPU: stage batch k (all host threads: copy into pinned memory, offsets, record checks)
   // -> submit k -> wait k-1 -> hand k-1 to the worker's writer thread, so that staging, the device and the

@@ -1,7 +1,8 @@
 """Host-side sharding logic shared by bench.py (one process per GPU under torchrun) and the tests.
 
-The extract path shards by batch: batch b of a run goes to rank b mod world (the `barkit` CLI does
-the same with threads inside one process, bk_run.cc).  There is no collective on the data path;
+The extract path shards by batch: in bench.py and these helpers batch b of a run goes to rank b mod world.
+(The `barkit` CLI shards by batch too, but inside one process and dynamically: bk_run.cc's per-GPU workers
+take the next unclaimed batch with a fetch_add and an ordered writer restores batch order.)  There is no collective on the data path;
 torch.distributed is used only to (a) line the ranks up before and after the timed region and
 (b) take the max over ranks of the device time.  Outputs are reassembled in batch order, which makes
 the N-rank bytes identical to the 1-rank bytes (run.rs:79,194 ordering).

@@ -35,6 +35,24 @@ extern "C" {
 #define BK_FLAG_PAIRED 1u
 #define BK_FLAG_SKIP_TRIM 2u
 #define BK_FLAG_RC 4u
+/* Library behaviour that has no counterpart in run.rs (every knob is an argument; the library reads no
+ * environment variable):
+ *   BK_FLAG_DEVICE_BOTH_MATES  paired mode with one pattern: send the pattern-less mate to the device as well
+ *                              instead of assembling its output on the host (see bk_submit)
+ *   BK_FLAG_HOST_MATE_PINNED   ... keep assembling it on the host even when the context measures the host copy
+ *                              to be slower than the bus
+ *   BK_FLAG_VERBOSE            launch plans and per-batch timings on stderr */
+#define BK_FLAG_DEVICE_BOTH_MATES 8u
+#define BK_FLAG_HOST_MATE_PINNED 16u
+#define BK_FLAG_VERBOSE 32u
+
+/* Layout guards: a binding written against this header (rust/barkit-extract/src/ffi.rs) must
+ * agree with these sizes; they only ever grow at the end, together with the numbers here. */
+#if defined(__cplusplus)
+#define BK_STATIC_ASSERT(cond, msg) static_assert(cond, msg)
+#else
+#define BK_STATIC_ASSERT(cond, msg) _Static_assert(cond, msg)
+#endif
 
 typedef struct bk_program bk_program; /* replaces pattern::BarcodeRegex (pattern.rs:161-235) */
 typedef struct bk_ctx bk_ctx;         /* one GPU; used by one host thread at a time          */
@@ -76,6 +94,7 @@ typedef struct bk_program_info {
   uint32_t cap_off[3];   /* capture offsets / lengths relative to the match start */
   uint32_t cap_len[3];
 } bk_program_info;
+BK_STATIC_ASSERT(sizeof(bk_program_info) == 48, "bk_program_info layout");
 int bk_program_get_info(const bk_program* p, bk_program_info* info);
 
 /* Text dump of the lowered program, one line per item (debug / tests):
@@ -105,6 +124,9 @@ int bk_warmup(int device);
  * one must be given.  Without BK_FLAG_PAIRED, p2 must be NULL (run.rs:43). */
 bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, uint32_t flags,
                       int* status, char* err, size_t errcap);
+/* Host threads bk_wait may use for the output of a pattern-less mate (default: all cores; the reference's
+ * rayon pool is sized the same way, run.rs:70,172).  Callers that run one context per GPU share the cores out. */
+int bk_ctx_set_host_threads(bk_ctx* ctx, int n);
 void bk_ctx_destroy(bk_ctx* ctx);
 const char* bk_last_error(const bk_ctx* ctx);
 
@@ -122,6 +144,7 @@ typedef struct bk_mate_in {
   uint32_t max_rec_bytes;
   uint32_t reserved;
 } bk_mate_in;
+BK_STATIC_ASSERT(sizeof(bk_mate_in) == 32, "bk_mate_in layout");
 
 typedef struct bk_result {
   uint64_t out1_len; /* bytes of FASTQ text produced for -o */
@@ -135,6 +158,7 @@ typedef struct bk_result {
   uint64_t h2d_bytes; /* bytes copied host -> device for this batch (0 for the device-resident form) */
   uint64_t d2h_bytes; /* bytes copied device -> host */
 } bk_result;
+BK_STATIC_ASSERT(sizeof(bk_result) == 72, "bk_result layout");
 
 /* The batch map + writer framing: parse_se_reads (run.rs:63-80) / parse_pe_reads (run.rs:163-195)
  * followed by FastqWriter::write_all (fastq.rs:265-271, :296-305).  HOST buffers in, HOST buffers
@@ -148,9 +172,9 @@ int bk_extract_host(bk_ctx* ctx, uint32_t n, const bk_mate_in* in1, const bk_mat
  * records are only ever copied (the pair is kept) or dropped (run.rs:149-160), so bk_submit sends the
  * pattern's mate alone and bk_wait assembles the pattern-less mate's output from the CALLER'S INPUT
  * BUFFER and the device's match table (kept records in input order, in the writer's framing,
- * fastq.rs:259-263), on up to BK_HOST_THREADS host threads (default: all).  Consequence for every
+ * fastq.rs:259-263), on the host threads set with bk_ctx_set_host_threads.  Consequence for every
  * caller: the in1 / in2 buffers of a batch must stay valid and unchanged until bk_wait for its slot
- * returns.  BK_HOST_PASSTHROUGH=0 (read by bk_ctx_create) sends both mates to the device instead.
+ * returns.  BK_FLAG_DEVICE_BOTH_MATES sends both mates to the device instead.
  * bk_result.h2d_bytes / d2h_bytes report what actually crossed the bus.
  *
  * double-buffered form of the same call: slot in [0, bk_ctx_nslots) */
@@ -176,13 +200,6 @@ int bk_memcpy_d2h(bk_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk_mate_in* d_in2,
                       uint8_t* d_out1, uint64_t cap1, uint8_t* d_out2, uint64_t cap2,
                       int32_t* d_match1, int32_t* d_match2, int iters, bk_result* res);
-
-/* Which extract kernel this context's launches use: 4 = extract_kernel (bk_extract.cuh, any pattern; the
- * default), 5 = extract_kernel5 (bk_extract5.cuh, patterns anchored at the read start; BK_KERNEL=5), 0 = the
- * context is still timing both on its first large batches (BK_KERNEL=auto: two launches each, then the
- * faster; output is identical either way).  No counterpart in the reference: its per-read work has one
- * implementation (parse.rs:58-68). */
-int bk_kernel_variant(const bk_ctx* ctx);
 
 /* Debug: the pipeline event trace of the last device launch on slot 0 -- 16 clock64() stamps per tile
  * (tools/phases.py names them) for tiles [first_tile, first_tile + count) of a launch that had `ntiles`
@@ -210,6 +227,7 @@ typedef struct bk_syn_config {
   uint32_t plant_jitter[2];
   char plant_lit[2][32];
 } bk_syn_config;
+BK_STATIC_ASSERT(sizeof(bk_syn_config) == 92, "bk_syn_config layout");
 int bk_generate_device(bk_ctx* ctx, const bk_syn_config* cfg, int mate, uint64_t seed,
                        uint64_t first_idx, uint32_t n, uint8_t* d_text, uint32_t* d_rec_off);
 
@@ -222,15 +240,19 @@ typedef struct bk_run_args {
   const char* out_fq1;
   const char* out_fq2;  /* nullable */
   size_t max_memory_mb; /* 0 = unset (-m) */
-  size_t threads;       /* -t (host tokenizer threads) */
+  size_t threads;       /* -t: (de)compression threads, as in the reference (fastq.rs:119,237,243); the per-read
+                           work has no host threads, and host staging uses all cores like the reference's rayon pool */
   int rc_barcodes;
   int skip_trimming;
   size_t max_error;
   int compression;      /* 0 none; others rejected with BK_E_UNSUPPORTED */
   int quiet;
   int force;
-  int n_gpus;           /* 0 = all visible devices */
+  int n_gpus;           /* 0 = automatic: one GPU per 2 GiB of input text per mate, at most all visible devices */
+  int verbose;          /* != 0: per-stage timing lines on stderr */
+  uint32_t ctx_flags;   /* extra BK_FLAG_* bits for the workers' contexts (BK_FLAG_DEVICE_BOTH_MATES, ...) */
 } bk_run_args;
+BK_STATIC_ASSERT(sizeof(void*) != 8 || sizeof(bk_run_args) == 104, "bk_run_args layout");
 int bk_run(const bk_run_args* args, char* err, size_t errcap);
 
 #ifdef __cplusplus

@@ -17,19 +17,11 @@ from tests.util import CONFIG_PATTERNS, lib_syn_config, ragged_fastq
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["4", "5"])
-def kernel_variant(request, monkeypatch):
-    """Every parity test runs once per extract kernel: BK_KERNEL=4 pins extract_kernel (bk_extract.cuh),
-    BK_KERNEL=5 sends every launch that qualifies (patterns anchored at the read start, no -r) to
-    extract_kernel5 (bk_extract5.cuh); the library reads the variable at each launch."""
-    monkeypatch.setenv("BK_KERNEL", request.param)
-    return request.param
-
-
-def make_ctx(p1, p2=None, k=1, paired=False, skip=False, rc=False):
+def make_ctx(p1, p2=None, k=1, paired=False, skip=False, rc=False, extra_flags=0, host_threads=None):
     P1 = _lib.Program(p1, k) if p1 is not None else None
     P2 = _lib.Program(p2, k) if p2 is not None else None
-    return _lib.Context(P1, P2, paired=paired, skip_trimming=skip, rc_barcodes=rc)
+    return _lib.Context(P1, P2, paired=paired, skip_trimming=skip, rc_barcodes=rc, extra_flags=extra_flags,
+                        host_threads=host_threads)
 
 
 def run_se(fq, pattern, k=1, skip=False, rc=False):
@@ -39,8 +31,8 @@ def run_se(fq, pattern, k=1, skip=False, rc=False):
     return out, res
 
 
-def run_pe(fq1, fq2, p1, p2, k=1, skip=False, rc=False):
-    ctx = make_ctx(p1, p2, k=k, paired=True, skip=skip, rc=rc)
+def run_pe(fq1, fq2, p1, p2, k=1, skip=False, rc=False, extra_flags=0):
+    ctx = make_ctx(p1, p2, k=k, paired=True, skip=skip, rc=rc, extra_flags=extra_flags)
     o1, o2, res = ctx.extract_text(fq1, fq2)
     ctx.close()
     return o1, o2, res
@@ -237,31 +229,11 @@ def test_crlf_paired_anchored():
     assert o1 == e1 and o2 == e2
 
 
-def test_kernel_autotune_keeps_output_identical(monkeypatch):
-    """With BK_KERNEL=auto the context tries both kernels on its first large batches and keeps the faster;
-    whichever runs, the bytes are the same."""
-    monkeypatch.setenv("BK_KERNEL", "auto")
-    p1, p2, paired = CONFIG_PATTERNS["C2"]
-    ctx = make_ctx(p1, p2, k=1, paired=True)
-    n = 250000
-    mates, rl = _device_batch(ctx, "C2", 0, n)
-    cap = n * (rl + 120)
-    d_o1, d_o2 = ctx.dev_alloc(cap), ctx.dev_alloc(cap)
-    crcs = set()
-    for _ in range(6):   # 2 + 2 trial launches, then the chosen kernel
-        res = ctx.extract_device(n, mates[0], mates[1], d_o1, cap, d_o2, cap)
-        crcs.add((zlib.crc32(ctx.d2h(d_o1, res.out1_len).tobytes()), zlib.crc32(ctx.d2h(d_o2, res.out2_len).tobytes()),
-                  res.n_out))
-    assert len(crcs) == 1
-    assert ctx.kernel_variant() in (4, 5)     # settled after 2 + 2 trial launches
-    ctx.close()
-
-
 @pytest.mark.parametrize("which", ["p1", "p2"])
-def test_host_side_mate_matches_the_device_path(which, monkeypatch):
+def test_host_side_mate_matches_the_device_path(which):
     """Paired mode with one pattern: the pattern-less mate is assembled on the host from the caller's input
     buffer (bk_submit / bk_wait, several threads above 50 000 records).  Same bytes as with both mates on
-    the device (BK_HOST_PASSTHROUGH=0) and as the oracle; CR line ends, '+' comments and a last record
+    the device (BK_FLAG_DEVICE_BOTH_MATES) and as the oracle; CR line ends, '+' comments and a last record
     without EOL included, so that re-framed records shift the parts of the threaded copy."""
     rnd = random.Random(21)
     n = 61000
@@ -281,8 +253,7 @@ def test_host_side_mate_matches_the_device_path(which, monkeypatch):
     pat = "^(?P<CB>[ATGCN]{16})atgccat(?P<UMI>[ATGCN]{6})"
     p1, p2 = (pat, None) if which == "p1" else (None, pat)
     o1, o2, res = run_pe(fq1, fq2, p1, p2, 1)
-    monkeypatch.setenv("BK_HOST_PASSTHROUGH", "0")
-    d1, d2, res_d = run_pe(fq1, fq2, p1, p2, 1)
+    d1, d2, res_d = run_pe(fq1, fq2, p1, p2, 1, extra_flags=_lib.FLAG_DEVICE_BOTH_MATES)
     assert res_d.h2d_bytes > 1.9 * res.h2d_bytes          # the second mate never crossed the bus
     assert (o1, o2) == (d1, d2)
     assert (res.n_out, res.n_match1, res.n_match2) == (res_d.n_out, res_d.n_match1, res_d.n_match2)
@@ -330,16 +301,15 @@ def test_variable_repetition_paired_end():
             assert o1 == e1 and o2 == e2, (p1, p2, k, skip, rc)
 
 
-def test_host_side_mate_falls_back_when_the_host_copy_is_slow(monkeypatch):
+def test_host_side_mate_falls_back_when_the_host_copy_is_slow():
     """The context measures the host copy of the pattern-less mate against what the bus would need and sends
     both mates to the device once the host side loses twice in a row (here: one host thread).  The bytes do
     not change, the traffic does."""
-    monkeypatch.setenv("BK_HOST_THREADS", "1")
     p1, p2, _ = CONFIG_PATTERNS["C3"]
     n = 400000
     fq1, fq2 = bksyn.generate_pair(bksyn.CONFIGS["C3"], 0, 2000)
     fq1, fq2 = fq1 * (n // 2000), fq2 * (n // 2000)   # (repeated records: only sizes and timing matter here)
-    ctx = make_ctx(p1, p2, k=1, paired=True)
+    ctx = make_ctx(p1, p2, k=1, paired=True, host_threads=1)
     seen = []
     for _ in range(5):
         o1, o2, res = ctx.extract_text(fq1, fq2)

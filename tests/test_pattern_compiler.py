@@ -67,6 +67,10 @@ def test_error_messages_follow_error_rs():
     r"^(?P<UMI>\w{4})", "(?i)(?P<UMI>[ATGCN]{4})", "^(?P<UMI>[ATGCN]{4})?", "(?P<UMI>[ATGCN]{4})^",
     "(?=A)(?P<UMI>[ATGCN]{4})", "((?P<UMI>[ATGCN]{4})){2}", "(?P<UMI>[[:alpha:]]{4})",
     "^(?P<UMI>[^atg-z]{4})", "é(?P<UMI>A)",
+    # a repeated group that contains variable repetition: every copy has its own length in the regex crate
+    # (4 and 8 combinations); one length per quantifier would be an approximation, so these are refused
+    "(?P<UMI>[ACGT]{4})([AT]{1,2}G){2}", "(?P<UMI>[ACGT]{4})(A?C){3}", "(?P<UMI>[ACGT]{4})((A?C)T){2}",
+    "(?P<UMI>[ACGT]{4})(A{1,2}?C){0}",
 ])
 def test_unsupported_constructs_are_refused(pattern):
     with pytest.raises(_lib.BarkitError) as e:
@@ -87,6 +91,9 @@ def test_variable_repetition_lowers_to_variants_in_priority_order():
     assert _lib.expand("^(?P<UMI>[ATGCN]{8,10})at", 1) == bo.BarcodePattern("^(?P<UMI>[ATGCN]{8,10})at", 1).get_pattern_with_errors()
     # [?{] inside a class and the ? of group syntax are not quantifiers
     assert _lib.Program("^(?P<UMI>[?{}*+]{3})(?:A)", 0).nvariants() == 1
+    # variable repetition inside a group is fine as long as the group itself is taken once
+    assert _lib.Program("(?P<UMI>[ACGT]{4})([AT]{1,2}G)", 0).nvariants() == 2
+    assert _lib.Program("(?P<UMI>[ACGT]{4})(A?C){1}(GT){2}", 0).nvariants() == 2
 
 
 # ---- expansion text == oracle on generated patterns ---------------------------------------------

@@ -7,7 +7,7 @@ import numpy as np
 from barkit_b200 import _lib
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 4000000
-R = int(sys.argv[2]) if len(sys.argv) > 2 else 30          # records per tile the launch plan picks (BK_DEBUG=1 prints it)
+R = int(sys.argv[2]) if len(sys.argv) > 2 else 30          # records per tile the launch plan picks (BK_FLAG_VERBOSE prints it)
 NAME = sys.argv[3] if len(sys.argv) > 3 else "C3"          # BASELINE.json config
 K = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 from tests.util import CONFIG_PATTERNS, lib_syn_config
@@ -29,38 +29,12 @@ rc = _lib.lib.bk_debug_events(ctx.handle, ntiles, lo, n, ev.ctypes.data)
 assert rc == 0, rc
 ev = ev.astype(np.int64)
 print("kernel_ms", r.kernel_ms, "Mpairs/s", P / r.kernel_ms / 1e3, "tiles", ntiles)
-V5 = os.environ.get("BK_KERNEL", "4") == "5" and NAME in ("C1", "C2", "C3")
 def iv(a, b, label):
     d = ev[:, b] - ev[:, a]
     d = d[(ev[:, a] > 0) & (ev[:, b] > 0)]
     if len(d) == 0:
         return
     print("%-44s mean %7.0f  p10 %7.0f  p50 %7.0f  p90 %7.0f  p99 %7.0f" % (label, d.mean(), *np.percentile(d, [10, 50, 90, 99])))
-if V5:  # extract_kernel5 (bk_extract5.cuh): 0 meta slot free, 1 claimed, 2 offsets in, 3 windows landed, 5 matched,
-        # 6 published, 7 handed over, 8/9 scan, 15 tma issued, 10 back start, 11 emit done, 12 all parts, 13 stored
-    iv(0, 1, "meta slot free -> claimed")
-    iv(1, 2, "claimed -> offsets in")
-    iv(2, 3, "offsets -> windows landed")
-    iv(3, 5, "scout: parse + match")
-    iv(5, 6, "scout: exchange + size + publish")
-    iv(6, 7, "scout: meta + hand over")
-    iv(1, 6, "CLAIM -> PUBLISH (mate 0)")
-    iv(1, 14, "claim -> publish (mate 1)")
-    iv(7, 8, "handed over -> scan starts (scan queue)")
-    iv(8, 9, "scan: look-back")
-    iv(6, 9, "PUBLISH -> READY")
-    iv(7, 15, "handed over -> tma issued (data slot wait)")
-    iv(15, 10, "tma issued -> back starts")
-    iv(9, 10, "ready -> back starts")
-    iv(10, 11, "back warp (0,0): emit")
-    iv(11, 12, "back: wait for the other parts")
-    iv(12, 4, "back: store: bulk issue")
-    iv(4, 13, "back: store: ragged edges")
-    iv(12, 13, "back: store")
-    iv(10, 13, "BACK total")
-    iv(15, 12, "DATA SLOT HELD (tma issued -> released)")
-    iv(0, 12, "META SLOT ROUND TRIP")
-    sys.exit(0)
 names = ["slot free", "claimed", "tma issued", "F0 data landed", "F0 parsed", "F0 matched", "F0 published", "F0 handed over",
          "S start", "S ready", "B00 start", "B00 emit done", "B0 all parts done", "B0 stored", "F1 published", "B03 emit done"]
 iv(0, 1, "slot free -> claimed (atomic)")
