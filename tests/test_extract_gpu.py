@@ -35,6 +35,13 @@ def run_pe(fq1, fq2, p1, p2, k=1, skip=False, rc=False, extra_flags=0):
     ctx = make_ctx(p1, p2, k=k, paired=True, skip=skip, rc=rc, extra_flags=extra_flags)
     o1, o2, res = ctx.extract_text(fq1, fq2)
     ctx.close()
+    if (p1 is None) != (p2 is None) and extra_flags == 0:
+        # One pattern: by default the pattern-less mate is assembled on the host (bk_submit) and the kernel sees a
+        # single-end batch.  Every such test also runs the paired kernel (the pattern-less mate copied on the
+        # device, global -> global) and must get the same bytes.
+        d1, d2, res_d = run_pe(fq1, fq2, p1, p2, k, skip, rc, extra_flags=_lib.FLAG_DEVICE_BOTH_MATES)
+        assert (o1, o2) == (d1, d2), "host-side mate and device-side mate differ"
+        assert (res.n_out, res.n_match1, res.n_match2) == (res_d.n_out, res_d.n_match1, res_d.n_match2)
     return o1, o2, res
 
 
