@@ -106,6 +106,8 @@ SYMBOLS = {
     "bk_reverse_complement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "bk_generate_device": (C.c_int, [C.c_void_p, C.POINTER(SynConfig), C.c_int, C.c_uint64, C.c_uint64,
                                      C.c_uint32, C.c_void_p, C.c_void_p]),
+    "bk_bus_probe": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                               C.POINTER(C.c_double)]),
     "bk_run": (C.c_int, [C.POINTER(RunArgs), C.c_char_p, C.c_size_t]),
 }
 
@@ -326,6 +328,12 @@ class Context:
                         d_text: int, d_off: int):
         self._check(lib.bk_generate_device(self.handle, C.byref(cfg), mate, seed, first_idx, n,
                                            d_text, d_off))
+
+    def bus_probe(self, nbytes: int = 256 << 20, iters: int = 6):
+        """-> (h2d, d2h, duplex) GB/s of this GPU's host link (pinned memory, see bk_bus_probe)."""
+        a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._check(lib.bk_bus_probe(self.handle, nbytes, iters, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def extract_device(self, n, m1: MateIn, m2: MateIn | None, d_out1, cap1, d_out2=0, cap2=0,
                        d_match1=0, d_match2=0, iters=1) -> Result:

@@ -118,16 +118,18 @@ struct LaunchPlan {
   int grid;
 };
 
+// `stages` ring slots per staged mate + one output tile; `bypass` >= 0: that mate is never staged (extract_kernel's BYP form)
 size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_t in_cap[2],
-                uint32_t out_cap[2]) {
+                uint32_t out_cap[2], int stages, int bypass) {
   size_t total = 0;
   int nm = ctx->paired ? 2 : 1;
   for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
   for (int m = 0; m < nm; ++m) {
+    if (m == bypass) continue;
     uint32_t growth = ctx->prog[m].present ? ctx->growth[m] : 0;
     in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
     out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
-    total += bk::kStages * (size_t)in_cap[m] + out_cap[m];
+    total += (size_t)stages * in_cap[m] + out_cap[m];
   }
   return total;
 }
@@ -143,34 +145,42 @@ bool needs_general(const bk_ctx* ctx) {
   return false;
 }
 
-template <bool PAIRED, bool GENERAL, bool VAR = false>
+// the bypass form (bk_extract.cuh): paired, exactly one mate has a pattern, and it needs no search
+bool wants_bypass(const bk_ctx* ctx) {
+  return ctx->paired && !needs_general(ctx) && (ctx->prog[0].present != 0) != (ctx->prog[1].present != 0);
+}
+
+template <bool PAIRED, bool GENERAL, bool VAR = false, bool BYP = false>
 int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
+  constexpr int kSt = bk::stages<BYP>();
+  const int byp = BYP ? (ctx->prog[0].present ? 1 : 0) : -1;
+  constexpr int kThreads = bk::cta_warps(PAIRED, BYP) * 32;
   // Two CTAs per SM (228 KB of shared memory per SM, each CTA's static part included) whenever the records
   // allow it: the kernel is bound by ring slots in flight, and the instantiations differ in static shared
   // memory (the general ones carry the search-sharing buffers), so the budget is taken from the kernel itself.
   cudaFuncAttributes fa;
-  CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR>));
+  CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>));
   constexpr int kWant = PAIRED ? 2 : 4;  // CTAs per SM the kernel is compiled for (launch bounds): 30-36 warps per SM
   const size_t target = std::min<size_t>(kTargetDynSmem, (233472 / kWant - fa.sharedSizeBytes) & ~size_t(127));
   uint32_t R = bk::kTileRecs;
   // prefer several resident tiles per SM; never go below 8 records unless a tile would not fit
-  while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > target) --R;
-  while (R > 0 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > kMaxDynSmem) --R;
+  while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, kSt, byp) > target) --R;
+  while (R > 0 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, kSt, byp) > kMaxDynSmem) --R;
   if (R == 0) {
     ctx->last_error = "record too long for the on-chip staging buffer";
     return BK_E_CAPACITY;
   }
-  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0, other = 0;  // `other`: CTAs per SM that registers and threads allow
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, bk::extract_kernel<PAIRED, GENERAL, VAR>, bk::cta_warps(PAIRED) * 32, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>, kThreads, 0));
   for (;;) {
     lp->tile_recs = R;
-    lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap);
-    CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, kSt, byp);
+    CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)lp->smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR>,
-                                                     bk::cta_warps(PAIRED) * 32, lp->smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>,
+                                                     kThreads, lp->smem));
     if (per_sm >= kWant || other < kWant || R <= 24) break;  // (long records: the tile stays as it is, fewer CTAs share the SM)
     --R;
   }
@@ -217,7 +227,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   LaunchPlan lp;
   const bool general = needs_general(ctx);
   const bool var = has_variants(ctx);
-  int rc = var ? (ctx->paired ? plan_launch<true, true, true>(ctx, n, maxrec, &lp) : plan_launch<false, true, true>(ctx, n, maxrec, &lp))
+  const bool byp = wants_bypass(ctx);
+  int rc = byp ? plan_launch<true, false, false, true>(ctx, n, maxrec, &lp)
+           : var ? (ctx->paired ? plan_launch<true, true, true>(ctx, n, maxrec, &lp) : plan_launch<false, true, true>(ctx, n, maxrec, &lp))
            : ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))
                        : (general ? plan_launch<false, true>(ctx, n, maxrec, &lp) : plan_launch<false, false>(ctx, n, maxrec, &lp));
   if (rc != BK_OK) return rc;
@@ -253,7 +265,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.tile_recs = lp.tile_recs;
   P.flags = ctx->flags;
   if (n > 0) {
-    if (var && ctx->paired)
+    if (byp)
+      bk::extract_kernel<true, false, false, true><<<lp.grid, bk::cta_warps(true, true) * 32, lp.smem, stream>>>(P);
+    else if (var && ctx->paired)
       bk::extract_kernel<true, true, true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
     else if (var)
       bk::extract_kernel<false, true, true><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
@@ -768,6 +782,51 @@ int bk_tokenize_device(bk_ctx* ctx, const uint8_t* d_text, uint64_t len, int fin
   if (consumed) *consumed = (rc == BK_OK && final_chunk && eff != len && last_end == eff) ? len : last_end;
   if (max_rec_bytes) *max_rec_bytes = n ? r.max_rec_bytes : 0;
   return rc;
+}
+
+int bk_bus_probe(bk_ctx* ctx, uint64_t bytes, int iters, double* h2d_gbs, double* d2h_gbs, double* duplex_gbs) {
+  if (!ctx || bytes == 0 || iters < 1) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->slot[0].busy || ctx->slot[1].busy) { ctx->last_error = "a slot is busy"; return BK_E_ARG; }
+  void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+  auto cleanup = [&]() {
+    if (h_in) cudaFreeHost(h_in);
+    if (h_out) cudaFreeHost(h_out);
+    if (d_in) cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+  };
+  if (cudaHostAlloc(&h_in, bytes, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc(&h_out, bytes, cudaHostAllocDefault) != cudaSuccess ||
+      cudaMalloc(&d_in, bytes) != cudaSuccess || cudaMalloc(&d_out, bytes) != cudaSuccess) {
+    ctx->last_error = std::string("bus probe: allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    cleanup();
+    return BK_E_CUDA;
+  }
+  memset(h_in, 0x5a, bytes);
+  memset(h_out, 0, bytes);
+  cudaStream_t s0 = ctx->slot[0].stream, s1 = ctx->slot[1].stream;
+  auto now = []() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; };
+  auto run = [&](bool up, bool down) -> double {  // seconds for `iters` copies per active direction
+    cudaStreamSynchronize(s0);
+    cudaStreamSynchronize(s1);
+    const double t0 = now();
+    for (int i = 0; i < iters; ++i) {
+      if (up) cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, s0);
+      if (down) cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, s1);
+    }
+    cudaStreamSynchronize(s0);
+    cudaStreamSynchronize(s1);
+    return now() - t0;
+  };
+  run(true, true);  // warm-up: page tables, link power state
+  const double gb = (double)bytes * iters / 1e9;
+  const double tu = run(true, false), td = run(false, true), tb = run(true, true);
+  if (h2d_gbs) *h2d_gbs = gb / tu;
+  if (d2h_gbs) *d2h_gbs = gb / td;
+  if (duplex_gbs) *duplex_gbs = 2.0 * gb / tb;
+  const cudaError_t e = cudaGetLastError();
+  cleanup();
+  if (e != cudaSuccess) { ctx->last_error = std::string("bus probe: ") + cudaGetErrorString(e); return BK_E_CUDA; }
+  return BK_OK;
 }
 
 int bk_reverse_complement(bk_ctx* ctx, const uint8_t* seq, size_t n, uint8_t* out) {

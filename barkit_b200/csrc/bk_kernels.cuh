@@ -207,10 +207,6 @@ struct RecView {    // seq_io field definitions: lines without EOL and without a
   uint32_t qual_len;
 };
 
-__device__ __forceinline__ uint32_t strip_cr(uint32_t b, uint32_t e) {
-  return (e > b && lds8(e - 1) == '\r') ? e - 1 : e;
-}
-
 // find_nl for the header line, four words per turn (independent loads: one shared-memory round trip
 // per 16 bytes instead of one per word)
 __device__ __forceinline__ uint32_t find_nl_head(uint32_t from, uint32_t end) {
@@ -235,39 +231,103 @@ __device__ __forceinline__ uint32_t find_nl_head(uint32_t from, uint32_t end) {
   return end;
 }
 
+// The same searches on text that stays in global memory (a mate that is never staged on chip, see
+// extract_kernel's BYP form): positions are byte offsets into `t`, whose base is 16-byte aligned and whose
+// allocation extends 16 bytes past the text (include/barkit_b200.h, bk_mate_in).  16 bytes per load.
+__device__ __forceinline__ uint32_t nl_mask16(const uint4 v, uint32_t first_valid, uint32_t base) {
+  // -> position (base + byte index) of the first '\n' among bytes >= first_valid of the chunk, or 0xFFFFFFFF
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t pos = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 3; i >= 0; --i) {
+    const uint32_t x = w[i] ^ 0x0A0A0A0Au;
+    uint32_t m = (x - 0x01010101u) & ~x & 0x80808080u;
+    const uint32_t lo = 4u * i;  // bytes of this word below first_valid are masked off
+    if (first_valid > lo) m &= first_valid - lo >= 4u ? 0u : 0xFFFFFFFFu << (8u * (first_valid - lo));
+    pos = m ? base + lo + ((__ffs(m) - 1) >> 3) : pos;
+  }
+  return pos;
+}
+__device__ __noinline__ uint32_t find_nl_g(const uint8_t* t, uint32_t from, uint32_t end) {
+  uint32_t p = from & ~15u, fv = from & 15u;
+#pragma unroll 1
+  while (p < end) {
+    const uint32_t pos = nl_mask16(__ldg(reinterpret_cast<const uint4*>(t + p)), fv, p);
+    if (pos != 0xFFFFFFFFu) return pos < end ? pos : end;
+    fv = 0;
+    p += 16u;
+  }
+  return end;
+}
+// header line: the first 64 bytes in one round trip (four independent loads), longer headers chunk by chunk
+__device__ __forceinline__ uint32_t find_nl_head_g(const uint8_t* t, uint32_t from, uint32_t end) {
+  const uint32_t p = from & ~15u;
+  uint4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = p + 16u * i < end ? __ldg(reinterpret_cast<const uint4*>(t + p + 16u * i)) : make_uint4(0, 0, 0, 0);
+  uint32_t pos = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 3; i >= 0; --i) {
+    const uint32_t q = nl_mask16(v[i], i == 0 ? (from & 15u) : 0u, p + 16u * i);
+    pos = q != 0xFFFFFFFFu ? q : pos;
+  }
+  if (pos != 0xFFFFFFFFu) return pos < end ? pos : end;
+  return p + 64u < end ? find_nl_g(t, p + 64u, end) : end;
+}
+
+// where a record's bytes are read from: the staged tile (absolute shared-memory addresses) or global text
+struct MemS {
+  __device__ __forceinline__ uint32_t b(uint32_t a) const { return lds8(a); }
+  __device__ __forceinline__ uint32_t nl(uint32_t from, uint32_t end) const { return find_nl(from, end); }
+  __device__ __forceinline__ uint32_t nl_head(uint32_t from, uint32_t end) const { return find_nl_head(from, end); }
+};
+struct MemG {
+  const uint8_t* t;
+  __device__ __forceinline__ uint32_t b(uint32_t a) const { return __ldg(t + a); }
+  __device__ __forceinline__ uint32_t nl(uint32_t from, uint32_t end) const { return find_nl_g(t, from, end); }
+  __device__ __forceinline__ uint32_t nl_head(uint32_t from, uint32_t end) const { return find_nl_head_g(t, from, end); }
+};
+
+template <class M>
+__device__ __forceinline__ uint32_t strip_cr(const M& mem, uint32_t b, uint32_t e) {
+  return (e > b && mem.b(e - 1) == '\r') ? e - 1 : e;
+}
+
 // the general case: any line ends, text after '+', a last line without EOL (rare; kept out of line so that
 // the common path below stays small in the instruction cache)
-__device__ __noinline__ RecView parse_record_slow(uint32_t b, uint32_t e, uint32_t nl1) {
+template <class M>
+__device__ __noinline__ RecView parse_record_slow(const M mem, uint32_t b, uint32_t e, uint32_t nl1) {
   RecView r;
   r.beg = b;
   r.end = e;
   r.fast = 0;
-  r.head_len = strip_cr(b + 1, nl1 > b ? nl1 : b + 1) - (b + 1);
+  r.head_len = strip_cr(mem, b + 1, nl1 > b ? nl1 : b + 1) - (b + 1);
   const uint32_t sb = nl1 + 1 < e ? nl1 + 1 : e;
-  const uint32_t nl2 = find_nl(sb, e);
+  const uint32_t nl2 = mem.nl(sb, e);
   r.seq = sb;
-  r.seq_len = strip_cr(sb, nl2) - sb;
+  r.seq_len = strip_cr(mem, sb, nl2) - sb;
   const uint32_t pb = nl2 + 1 < e ? nl2 + 1 : e;
-  const uint32_t nl3 = find_nl(pb, e);
+  const uint32_t nl3 = mem.nl(pb, e);
   const uint32_t qb = nl3 + 1 < e ? nl3 + 1 : e;
-  const uint32_t nl4 = find_nl(qb, e);
+  const uint32_t nl4 = mem.nl(qb, e);
   r.qual = qb;
-  r.qual_len = strip_cr(qb, nl4) - qb;
+  r.qual_len = strip_cr(mem, qb, nl4) - qb;
   return r;
 }
 
-__device__ __noinline__ RecView parse_record(uint32_t b, uint32_t e) {
-  const uint32_t nl1 = find_nl_head(b, e);
+template <class M>
+__device__ __forceinline__ RecView parse_record_t(const M& mem, uint32_t b, uint32_t e) {
+  const uint32_t nl1 = mem.nl_head(b, e);
   const uint32_t sb = nl1 + 1 < e ? nl1 + 1 : e;
   // Fast path for the writer's own framing `@h LF seq LF + LF qual LF`: then e - sb = 2L + 4.  A record
   // of any other shape (CR line ends, text after '+', missing final LF) cannot pass the probes with
   // the L this formula gives (newlines only exist at the line ends), so it takes the scanning path.
-  // All probes are fetched together: one shared-memory round trip, not one per condition.
+  // All probes are fetched together: one memory round trip, not one per condition.
   const uint32_t rem = e - sb;
   const uint32_t L = (rem - 4u) >> 1;
   if (rem >= 4u && !(rem & 1u) && nl1 > b) {
-    const uint32_t c0 = lds8(sb + L), c1 = lds8(sb + L + 1u), c2 = lds8(sb + L + 2u), c3 = lds8(e - 1u);
-    const uint32_t c4 = lds8(sb + L - 1u), c5 = lds8(e - 2u), c6 = lds8(nl1 - 1u);  // (c4 is the header's LF when L == 0)
+    const uint32_t c0 = mem.b(sb + L), c1 = mem.b(sb + L + 1u), c2 = mem.b(sb + L + 2u), c3 = mem.b(e - 1u);
+    const uint32_t c4 = mem.b(sb + L - 1u), c5 = mem.b(e - 2u), c6 = mem.b(nl1 - 1u);  // (c4 is the header's LF when L == 0)
     const bool framed = (c0 == '\n') & (c1 == '+') & (c2 == '\n') & (c3 == '\n');
     const bool cr = (c4 == '\r') | (c5 == '\r');
     if (framed && (L == 0 || !cr)) {
@@ -284,8 +344,10 @@ __device__ __noinline__ RecView parse_record(uint32_t b, uint32_t e) {
       return r;
     }
   }
-  return parse_record_slow(b, e, nl1);
+  return parse_record_slow<M>(mem, b, e, nl1);
 }
+__device__ __noinline__ RecView parse_record(uint32_t b, uint32_t e) { return parse_record_t(MemS{}, b, e); }
+__device__ __noinline__ RecView parse_record_g(const uint8_t* t, uint32_t b, uint32_t e) { return parse_record_t(MemG{t}, b, e); }
 
 // ---- matching --------------------------------------------------------------------------------------
 
@@ -770,8 +832,10 @@ constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is
 __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
                                           uint32_t part, uint32_t nparts, uint32_t rot) {
   OutStream o;
-  // jobs of this part, bit 0 = A ... bit 4 = E
-  const uint32_t jobs = nparts == 5 ? 1u << part : nparts == 4 ? (part == 0 ? 3u : 2u << part) : (part == 0 ? 5u : 4u << part);
+  // jobs of this part, bit 0 = A ... bit 4 = E; with seven parts D and E are two parts each (half 1 and 2)
+  const uint32_t jobs = nparts == 7 ? (part < 3u ? 1u << part : part < 5u ? 8u : 16u)
+                        : nparts == 5 ? 1u << part : nparts == 4 ? (part == 0 ? 3u : 2u << part) : (part == 0 ? 5u : 4u << part);
+  const uint32_t half = nparts == 7 && part >= 3u ? 1u + ((part - 3u) & 1u) : 0u;
   const uint32_t ncaps = ms >= 0 ? pg.ncaps : 0u;
   const uint32_t csplit = (ncaps + 1u) >> 1;
   const uint32_t H = r.head_len, L = r.seq_len;
@@ -814,7 +878,26 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
   const uint32_t ps = cs < ll ? cs : ll, pe = ce < ll ? ce : ll;
   const uint32_t sep = isD ? (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16) : (uint32_t)'\n';
   const uint32_t nsep = isD ? 3u : 1u;
-  os_begin(o, d + 2u + H + G + (isD ? 0u : L - (ce - cs) + 3u));
+  const uint32_t dpos = d + 2u + H + G + (isD ? 0u : L - (ce - cs) + 3u);
+  if (half && r.fast) {
+    // two warps share the line: its output is the byte stream src[0, ps) ++ src[pe, ll + nsep) (the line end
+    // travels with the text), cut in the middle; each warp writes its side (they meet at an arbitrary byte)
+    const uint32_t tail = ll - pe + nsep, tot = ps + tail, mid = (tot >> 1) & ~3u;
+    const uint32_t lo = half == 1u ? 0u : mid, hi = half == 1u ? mid : tot;
+    if (hi > lo) {
+      os_begin(o, dpos + lo);
+      o.rot = rot;
+      if (lo < ps) os_run(o, src + lo, (hi < ps ? hi : ps) - lo);
+      if (hi > ps) {
+        const uint32_t a = (lo > ps ? lo : ps) - ps;
+        os_run(o, src + pe + a, hi - ps - a);
+      }
+      os_end(o);
+    }
+    return;
+  }
+  if (half == 2u) return;  // (foreign framing: the first half's warp writes the whole line)
+  os_begin(o, dpos);
   o.rot = rot;
   if (ps) os_run(o, src, ps);
   if (r.fast) {
@@ -824,6 +907,61 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
     os_put(o, sep, nsep);
   }
   os_end(o);
+}
+
+// ---- a mate that is never staged on chip: its kept records go global -> global ---------------------------
+//
+// In paired mode a mate without a pattern is only ever copied or dropped (run.rs:149-160).  Maximal runs of
+// consecutive kept records that already have the writer's framing are contiguous in the input text and in the
+// output, so they move like bulk16 moves them inside shared memory, with both sides in global memory:
+// consecutive lanes own consecutive 16-byte aligned destination chunks, load the two aligned source chunks
+// under them (the second is the next lane's first: L1 serves it) and funnel-shift by the run's relative
+// misalignment.  The run's ragged ends (< 16 bytes each) are copied bytewise, one lane per byte.
+//   run descriptor: x = source offset in the text, y = destination offset in the tile's output, z = bytes
+__device__ __forceinline__ void gcopy_run(const uint8_t* text, uint8_t* tile_out, const uint4 r, int lane, uint32_t t0,
+                                          uint32_t tstep, bool fringes) {
+  const uint8_t* const sp = text + r.x;
+  uint8_t* const dp = tile_out + r.y;
+  const uint32_t n = r.z;
+  const uintptr_t A = reinterpret_cast<uintptr_t>(dp);
+  const uintptr_t D0 = (A + 15u) & ~uintptr_t(15), D1 = (A + n) & ~uintptr_t(15);
+  const uintptr_t S0 = reinterpret_cast<uintptr_t>(sp) + (D0 - A);  // source of the first full chunk
+  const uint32_t sh = (uint32_t)(S0 & 15u), bits = (sh & 3u) * 8u;
+  const bool q1 = (sh & 4u) != 0, q2 = (sh & 8u) != 0;  // (warp-uniform)
+  const uint4* const sa = reinterpret_cast<const uint4*>(S0 & ~uintptr_t(15));
+  for (uintptr_t D = D0 + 16u * (32u * t0 + (uint32_t)lane); D < D1; D += 512u * tstep) {
+    const size_t c = (D - D0) >> 4;
+    const uint4 x = __ldg(sa + c);
+    uint4 y = x;
+    if (sh) y = __ldg(sa + c + 1);
+    const uint32_t a0 = q2 ? x.z : x.x, a1 = q2 ? x.w : x.y, a2 = q2 ? y.x : x.z, a3 = q2 ? y.y : x.w;
+    const uint32_t a4 = q2 ? y.z : y.x, a5 = q2 ? y.w : y.y;
+    const uint32_t b0 = q1 ? a1 : a0, b1 = q1 ? a2 : a1, b2 = q1 ? a3 : a2, b3 = q1 ? a4 : a3, b4 = q1 ? a5 : a4;
+    *reinterpret_cast<uint4*>(D) = make_uint4(__funnelshift_r(b0, b1, bits), __funnelshift_r(b1, b2, bits),
+                                              __funnelshift_r(b2, b3, bits), __funnelshift_r(b3, b4, bits));
+  }
+  if (fringes) {
+    uint32_t pad = (uint32_t)((16u - (A & 15u)) & 15u);
+    pad = pad < n ? pad : n;
+    const uint32_t t = (uint32_t)(D1 - A);  // (wraps when the run ends before its first aligned chunk)
+    const uint32_t tlo = (int32_t)t > (int32_t)pad ? t : pad;
+    if ((uint32_t)lane < pad) dp[lane] = (uint8_t)__ldg(sp + lane);
+    const uint32_t j = tlo + ((uint32_t)lane - 16u);
+    if (lane >= 16 && j < n) dp[j] = (uint8_t)__ldg(sp + j);
+  }
+}
+
+// a kept record of such a mate in foreign framing (CR line ends, text after '+', no final EOL): re-framed
+// bytewise by its lane (rare)
+__device__ __noinline__ void emit_record_g(const uint8_t* t, uint32_t beg, uint32_t head_len, uint32_t seq, uint32_t seq_len,
+                                           uint32_t qual, uint32_t qual_len, uint8_t* o) {
+  *o++ = '@';
+  for (uint32_t i = 0; i < head_len; ++i) *o++ = (uint8_t)__ldg(t + beg + 1u + i);
+  *o++ = '\n';
+  for (uint32_t i = 0; i < seq_len; ++i) *o++ = (uint8_t)__ldg(t + seq + i);
+  *o++ = '\n'; *o++ = '+'; *o++ = '\n';
+  for (uint32_t i = 0; i < qual_len; ++i) *o++ = (uint8_t)__ldg(t + qual + i);
+  *o++ = '\n';
 }
 
 // parse::get_reverse_complement as a stand-alone op (API parity; the extract kernel never materialises it)

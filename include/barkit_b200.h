@@ -231,6 +231,12 @@ BK_STATIC_ASSERT(sizeof(bk_syn_config) == 92, "bk_syn_config layout");
 int bk_generate_device(bk_ctx* ctx, const bk_syn_config* cfg, int mate, uint64_t seed,
                        uint64_t first_idx, uint32_t n, uint8_t* d_text, uint32_t* d_rec_off);
 
+/* Measurement aid (bench.py, tools/bus_peak.py; not a reference feature): the rate of this context's GPU's host
+ * link.  Copies `bytes` between pinned host memory and the device `iters` times: host -> device alone, device ->
+ * host alone, then both directions at once on two streams.  GB/s (1e9 bytes); duplex = both directions summed.
+ * Several contexts probing at the same time share the host's memory system, which is the point. */
+int bk_bus_probe(bk_ctx* ctx, uint64_t bytes, int iters, double* h2d_gbs, double* d2h_gbs, double* duplex_gbs);
+
 /* ---- whole-run form: run::run (run.rs:10-60), file in -> file out ---------------------------- */
 typedef struct bk_run_args {
   const char* fq1;
