@@ -25,7 +25,7 @@ BK_OK = 0
 BK_E_PATTERN, BK_E_UNSUPPORTED, BK_E_CUDA, BK_E_CAPACITY, BK_E_IO, BK_E_ARG, BK_E_FORMAT = \
     -1, -2, -3, -4, -5, -6, -7
 FLAG_PAIRED, FLAG_SKIP_TRIM, FLAG_RC = 1, 2, 4
-FLAG_DEVICE_BOTH_MATES, FLAG_HOST_MATE_PINNED, FLAG_VERBOSE = 8, 16, 32
+FLAG_DEVICE_BOTH_MATES, FLAG_HOST_MATE_PINNED, FLAG_VERBOSE, FLAG_STAGE_BOTH_MATES = 8, 16, 32, 64
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -89,6 +89,8 @@ SYMBOLS = {
     "bk_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(MateIn), C.POINTER(MateIn)]),
     "bk_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                           C.POINTER(Result)]),
+    "bk_submit_text": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                 C.c_uint32]),
     "bk_out_bound": (C.c_uint64, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint64]),
     "bk_dev_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "bk_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),

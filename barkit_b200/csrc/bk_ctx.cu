@@ -20,6 +20,7 @@
 #include "bk_internal.h"
 #include "bk_extract.cuh"
 #include "bk_tokenize.cuh"
+#include "bk_compact.cuh"
 
 namespace {
 
@@ -57,6 +58,15 @@ struct Slot {
   int32_t* h_match = nullptr;    // ... and its pinned host copy
   size_t h_match_cap = 0;
   uint64_t h2d_bytes = 0;        // of the batch in flight
+  // two-kernel form of a paired launch with one pattern (enqueue_split): hand-over and the compaction's look-back state
+  DevBuf split_match, split_hlen, split_scratch;
+  // raw-text batches (bk_submit_text): record offsets are made on the device
+  bool raw = false;
+  DevBuf tok[2];                      // per mate: TokResult | ticket | look-back descriptors
+  bk::TokResult* h_tok = nullptr;     // pinned, one per mate
+  uint64_t raw_len[2] = {0, 0};
+  bool raw_no_eol[2] = {false, false};  // the mate's last record has no line end
+  uint32_t raw_maxrec[2] = {0, 0};    // what the launch in flight was planned with
 };
 
 }  // namespace
@@ -78,6 +88,7 @@ struct bk_ctx {
   int pass_mate = -1;
   bk_ctx* solo = nullptr;
   int host_threads = 1;
+  uint32_t maxrec_seen[2] = {0, 0};  // longest record of earlier raw-text batches, per mate (bk_submit_text)
   // The host copy is worth it while it takes less time than the bus would need for the same mate.
   // Both are measured on every large pass-through batch; when the host side is the slower one twice in
   // a row (few or slow host cores, several GPUs sharing the host's memory bandwidth) the context
@@ -118,18 +129,16 @@ struct LaunchPlan {
   int grid;
 };
 
-// `stages` ring slots per staged mate + one output tile; `bypass` >= 0: that mate is never staged (extract_kernel's BYP form)
 size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_t in_cap[2],
-                uint32_t out_cap[2], int stages, int bypass) {
+                uint32_t out_cap[2]) {
   size_t total = 0;
   int nm = ctx->paired ? 2 : 1;
   for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
   for (int m = 0; m < nm; ++m) {
-    if (m == bypass) continue;
     uint32_t growth = ctx->prog[m].present ? ctx->growth[m] : 0;
     in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
     out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
-    total += (size_t)stages * in_cap[m] + out_cap[m];
+    total += bk::kStages * (size_t)in_cap[m] + out_cap[m];
   }
   return total;
 }
@@ -145,41 +154,34 @@ bool needs_general(const bk_ctx* ctx) {
   return false;
 }
 
-// the bypass form (bk_extract.cuh): paired, exactly one mate has a pattern, and it needs no search
-bool wants_bypass(const bk_ctx* ctx) {
-  return ctx->paired && !needs_general(ctx) && (ctx->prog[0].present != 0) != (ctx->prog[1].present != 0);
-}
-
-template <bool PAIRED, bool GENERAL, bool VAR = false, bool BYP = false>
+template <bool PAIRED, bool GENERAL, bool VAR = false>
 int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
-  constexpr int kSt = bk::stages<BYP>();
-  const int byp = BYP ? (ctx->prog[0].present ? 1 : 0) : -1;
-  constexpr int kThreads = bk::cta_warps(PAIRED, BYP) * 32;
+  constexpr int kThreads = bk::cta_warps(PAIRED) * 32;
   // Two CTAs per SM (228 KB of shared memory per SM, each CTA's static part included) whenever the records
   // allow it: the kernel is bound by ring slots in flight, and the instantiations differ in static shared
   // memory (the general ones carry the search-sharing buffers), so the budget is taken from the kernel itself.
   cudaFuncAttributes fa;
-  CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>));
+  CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR>));
   constexpr int kWant = PAIRED ? 2 : 4;  // CTAs per SM the kernel is compiled for (launch bounds): 30-36 warps per SM
   const size_t target = std::min<size_t>(kTargetDynSmem, (233472 / kWant - fa.sharedSizeBytes) & ~size_t(127));
   uint32_t R = bk::kTileRecs;
   // prefer several resident tiles per SM; never go below 8 records unless a tile would not fit
-  while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, kSt, byp) > target) --R;
-  while (R > 0 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, kSt, byp) > kMaxDynSmem) --R;
+  while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > target) --R;
+  while (R > 0 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > kMaxDynSmem) --R;
   if (R == 0) {
     ctx->last_error = "record too long for the on-chip staging buffer";
     return BK_E_CAPACITY;
   }
-  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0, other = 0;  // `other`: CTAs per SM that registers and threads allow
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>, kThreads, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, bk::extract_kernel<PAIRED, GENERAL, VAR>, kThreads, 0));
   for (;;) {
     lp->tile_recs = R;
-    lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, kSt, byp);
-    CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap);
+    CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)lp->smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR, BYP>,
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR>,
                                                      kThreads, lp->smem));
     if (per_sm >= kWant || other < kWant || R <= 24) break;  // (long records: the tile stays as it is, fewer CTAs share the SM)
     --R;
@@ -208,8 +210,64 @@ size_t scratch_bytes(uint32_t ntiles) { return events_offset(ntiles); }
 // enqueue: scratch reset + extract kernel.  All pointers are device pointers.
 int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
                     const bk_mate_in* in2, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
-                    int32_t* match1, int32_t* match2, uint32_t* launches) {
+                    int32_t* match1, int32_t* match2, uint32_t* launches, uint32_t* hlen1 = nullptr);
+
+// A paired launch with exactly one pattern, as two kernels (bk_compact.cuh): the single-end extract kernel on the
+// pattern's mate, leaving its match table and header lengths on the device, then the ordered compaction of the
+// other mate.  `ctx->solo` is the single-end view of the context.
+int enqueue_split(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2,
+                  uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2, int32_t* match1, int32_t* match2,
+                  uint32_t* launches) {
+  const int pm = ctx->prog[0].present ? 0 : 1, pt = 1 - pm;
+  const bk_mate_in* in[2] = {in1, in2};
+  uint8_t* const out[2] = {out1, out2};
+  const uint64_t cap[2] = {cap1, cap2};
+  int32_t* const user_match[2] = {match1, match2};
+  if (!in[pt] || !in[pt]->text || !in[pt]->rec_off) { ctx->last_error = "null batch pointer"; return BK_E_ARG; }
+  if (in[pt]->text_len >= (1ull << 32)) { ctx->last_error = "batch text must be < 4 GiB per mate"; return BK_E_CAPACITY; }
+  if (((uintptr_t)in[pt]->text & 15) != 0) { ctx->last_error = "batch text must be 16-byte aligned"; return BK_E_ARG; }
+  int rc;
+  if ((rc = ensure(ctx, &s->split_match, ((size_t)n + 1) * 4)) != BK_OK) return rc;
+  if ((rc = ensure(ctx, &s->split_hlen, ((size_t)n + 1) * 4)) != BK_OK) return rc;
+  int32_t* const keep = user_match[pm] ? user_match[pm] : (int32_t*)s->split_match.p;
+  rc = enqueue_extract(ctx->solo, s, stream, n, in[pm], nullptr, out[pm], cap[pm], nullptr, 0, keep, nullptr, launches,
+                       (uint32_t*)s->split_hlen.p);
+  if (rc != BK_OK) { ctx->last_error = ctx->solo->last_error; return rc; }
+  if (user_match[pt]) CK(cudaMemsetAsync(user_match[pt], 0xFF, (size_t)n * 4, stream));  // no pattern: nothing matches (-1)
+  if (n == 0) return BK_OK;
+  const uint32_t ntiles = (n + bk::kCompactRecs - 1) / bk::kCompactRecs;
+  if ((rc = ensure(ctx, &s->split_scratch, scratch_bytes(ntiles))) != BK_OK) return rc;
+  uint8_t* sc = (uint8_t*)s->split_scratch.p;
+  CK(cudaMemsetAsync(sc, 0, scratch_bytes(ntiles), stream));
+  bk::CompactParams C;
+  memset(&C, 0, sizeof C);
+  C.text = in[pt]->text;
+  C.off = in[pt]->rec_off;
+  C.keep = keep;
+  C.hlen = (const uint32_t*)s->split_hlen.p;
+  C.out = out[pt];
+  C.cap = cap[pt];
+  C.desc[0] = (unsigned long long*)(sc + 512);
+  C.desc[1] = (unsigned long long*)(sc + block_desc_offset(ntiles));
+  C.desc[2] = (unsigned long long*)(sc + block_acc_offset(ntiles));
+  C.ticket = (unsigned int*)sc;
+  C.result = (bk::DevResult*)((uint8_t*)s->scratch.buf.p + 64);  // the single-end launch's: this kernel completes it
+  C.n = n;
+  C.ntiles = ntiles;
+  C.text_len = (uint32_t)in[pt]->text_len;
+  C.stream = (uint32_t)pt;
+  bk::compact_kernel<<<ntiles, bk::kCompactThreads, 0, stream>>>(C);
+  CK(cudaGetLastError());
+  if (launches) *launches += 1;
+  return BK_OK;
+}
+
+int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
+                    const bk_mate_in* in2, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
+                    int32_t* match1, int32_t* match2, uint32_t* launches, uint32_t* hlen1) {
   if (ctx->paired && !in2) { ctx->last_error = "paired context needs two mates"; return BK_E_ARG; }
+  if (ctx->paired && ctx->solo && !(ctx->flags & BK_FLAG_STAGE_BOTH_MATES))
+    return enqueue_split(ctx, s, stream, n, in1, in2, out1, cap1, out2, cap2, match1, match2, launches);
   if (!ctx->paired && in2) { ctx->last_error = "single-end context got two mates"; return BK_E_ARG; }
   const bk_mate_in* in[2] = {in1, in2};
   uint32_t maxrec[2] = {0, 0};
@@ -227,9 +285,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   LaunchPlan lp;
   const bool general = needs_general(ctx);
   const bool var = has_variants(ctx);
-  const bool byp = wants_bypass(ctx);
-  int rc = byp ? plan_launch<true, false, false, true>(ctx, n, maxrec, &lp)
-           : var ? (ctx->paired ? plan_launch<true, true, true>(ctx, n, maxrec, &lp) : plan_launch<false, true, true>(ctx, n, maxrec, &lp))
+  bk::KParams P;
+  memset(&P, 0, sizeof P);
+  int rc = var ? (ctx->paired ? plan_launch<true, true, true>(ctx, n, maxrec, &lp) : plan_launch<false, true, true>(ctx, n, maxrec, &lp))
            : ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))
                        : (general ? plan_launch<false, true>(ctx, n, maxrec, &lp) : plan_launch<false, false>(ctx, n, maxrec, &lp));
   if (rc != BK_OK) return rc;
@@ -238,8 +296,6 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   uint8_t* sc = (uint8_t*)s->scratch.buf.p;
   CK(cudaMemsetAsync(sc, 0, scratch_bytes(lp.ntiles), stream));
 
-  bk::KParams P;
-  memset(&P, 0, sizeof P);
   P.prog[0] = ctx->prog[0];
   P.prog[1] = ctx->prog[1];
   for (int m = 0; m < (ctx->paired ? 2 : 1); ++m) {
@@ -254,6 +310,7 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.out[0] = out1; P.out[1] = out2;
   P.cap[0] = cap1; P.cap[1] = cap2;
   P.match[0] = match1; P.match[1] = match2;
+  P.hlen[0] = hlen1;
   P.tile_counter = (unsigned int*)sc;
   P.result = (bk::DevResult*)(sc + 64);
   P.prof = (unsigned long long*)(sc + events_offset(lp.ntiles));  // only written by a BK_PROFILE_PHASES build
@@ -265,9 +322,7 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.tile_recs = lp.tile_recs;
   P.flags = ctx->flags;
   if (n > 0) {
-    if (byp)
-      bk::extract_kernel<true, false, false, true><<<lp.grid, bk::cta_warps(true, true) * 32, lp.smem, stream>>>(P);
-    else if (var && ctx->paired)
+    if (var && ctx->paired)
       bk::extract_kernel<true, true, true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
     else if (var)
       bk::extract_kernel<false, true, true><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
@@ -383,20 +438,23 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
       return fail(BK_E_CUDA, m);
     }
   }
-  if (ctx->paired && (p1 == nullptr) != (p2 == nullptr) && !(flags & BK_FLAG_DEVICE_BOTH_MATES)) {
+  if (ctx->paired && (p1 == nullptr) != (p2 == nullptr)) {
+    // One pattern: `solo` is the single-end view of this context for the pattern's mate.  It serves the host
+    // pass-through (bk_submit: the other mate never leaves the host) and the two-kernel device form (enqueue_split).
     bk_ctx* solo = new (std::nothrow) bk_ctx();
     if (!solo) { bk_ctx_destroy(ctx); return fail(BK_E_CAPACITY, "out of memory"); }
-    ctx->pass_mate = p1 ? 1 : 0;
+    const int pm = p1 ? 0 : 1;
     solo->device = device;
-    solo->flags = flags & ~(uint32_t)(BK_FLAG_PAIRED | BK_FLAG_DEVICE_BOTH_MATES | BK_FLAG_HOST_MATE_PINNED);
+    solo->flags = flags & ~(uint32_t)(BK_FLAG_PAIRED | BK_FLAG_DEVICE_BOTH_MATES | BK_FLAG_HOST_MATE_PINNED | BK_FLAG_STAGE_BOTH_MATES);
     solo->paired = false;
     solo->sm_count = ctx->sm_count;
     memset(solo->prog, 0, sizeof solo->prog);
-    solo->prog[0] = ctx->prog[1 - ctx->pass_mate];
-    solo->var[0] = ctx->var[1 - ctx->pass_mate];
-    solo->vdev[0] = ctx->vdev[1 - ctx->pass_mate];  // (shared, owned by ctx)
-    solo->growth[0] = ctx->growth[1 - ctx->pass_mate];
+    solo->prog[0] = ctx->prog[pm];
+    solo->var[0] = ctx->var[pm];
+    solo->vdev[0] = ctx->vdev[pm];  // (shared, owned by ctx)
+    solo->growth[0] = ctx->growth[pm];
     ctx->solo = solo;
+    if (!(flags & BK_FLAG_DEVICE_BOTH_MATES)) ctx->pass_mate = 1 - pm;
     ctx->pass_pinned = (flags & BK_FLAG_HOST_MATE_PINNED) != 0;
   }
   ctx->host_threads = std::max(1, std::min((int)std::thread::hardware_concurrency(), 32));
@@ -419,6 +477,12 @@ void bk_ctx_destroy(bk_ctx* ctx) {
     if (s.scratch.buf.p) cudaFree(s.scratch.buf.p);
     if (s.match.p) cudaFree(s.match.p);
     if (s.h_match) cudaFreeHost(s.h_match);
+    if (s.h_tok) cudaFreeHost(s.h_tok);
+    if (s.split_match.p) cudaFree(s.split_match.p);
+    if (s.split_hlen.p) cudaFree(s.split_hlen.p);
+    if (s.split_scratch.p) cudaFree(s.split_scratch.p);
+    for (int m = 0; m < 2; ++m)
+      if (s.tok[m].p) cudaFree(s.tok[m].p);
     if (s.h_res) cudaFreeHost(s.h_res);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
@@ -472,6 +536,7 @@ int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk
     if (!in[m]->text || !in[m]->rec_off) { ctx->last_error = "null batch pointer"; return BK_E_ARG; }
     if (in[m]->text_len >= (1ull << 32)) { ctx->last_error = "batch text must be < 4 GiB per mate"; return BK_E_CAPACITY; }
   }
+  s.raw = false;
   s.passthrough = ctx->pass_mate >= 0;
   s.pt = ctx->pass_mate;
   if (s.passthrough) {
@@ -546,6 +611,101 @@ int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk
   return BK_OK;
 }
 
+namespace {
+
+// enqueue the device tokenizer for one mate's text (already on the device): rec_off[0..n], TokResult in tok->p
+int enqueue_tokenize(bk_ctx* ctx, cudaStream_t st, const uint8_t* d_text, uint64_t len, bool no_eol, uint32_t n,
+                     uint32_t* d_rec_off, DevBuf* tok) {
+  const uint32_t nblocks = (uint32_t)((len + bk::kTokChunk - 1) / bk::kTokChunk);
+  int rc = ensure(ctx, tok, bk::tok_desc_words(nblocks) * 8 + 128);
+  if (rc != BK_OK) return rc;
+  bk::TokResult* d_res = (bk::TokResult*)tok->p;
+  unsigned int* ticket = (unsigned int*)((uint8_t*)tok->p + 64);
+  unsigned long long* desc = (unsigned long long*)((uint8_t*)tok->p + 128);
+  bk::tok_init_kernel<<<(unsigned)((bk::tok_desc_words(nblocks) + 255) / 256), 256, 0, st>>>(d_res, desc, nblocks, ticket);
+  bk::tok_fused_kernel<<<nblocks, bk::kTokThreads, 0, st>>>(d_text, (uint32_t)len, d_rec_off, n, desc, ticket, nblocks, d_res);
+  if (no_eol) {  // the text's last record ends with the text: its end offset and its check come from here
+    bk::tok_set_end_kernel<<<1, 32, 0, st>>>(d_rec_off, n, (uint32_t)len);
+    bk::tok_check_kernel<<<1, 32, 0, st>>>(d_text, d_rec_off, n - 1, n, (uint32_t)len, d_res);
+  }
+  CK(cudaGetLastError());
+  return BK_OK;
+}
+
+int enqueue_raw_extract(bk_ctx* ctx, Slot& s) {
+  bk_mate_in dev[2];
+  const int nm = ctx->paired ? 2 : 1;
+  for (int m = 0; m < nm; ++m) {
+    dev[m].text = (const uint8_t*)s.text[m].p;
+    dev[m].rec_off = (const uint32_t*)s.off[m].p;
+    dev[m].text_len = s.raw_len[m];
+    dev[m].max_rec_bytes = s.raw_maxrec[m];
+    dev[m].reserved = 0;
+  }
+  CK(cudaEventRecord(s.ev0, s.stream));
+  int rc = enqueue_extract(ctx, &s, s.stream, s.n, &dev[0], ctx->paired ? &dev[1] : nullptr, (uint8_t*)s.out[0].p,
+                           s.out_cap[0], (uint8_t*)s.out[1].p, s.out_cap[1], nullptr, nullptr, &s.launches);
+  if (rc != BK_OK) return rc;
+  CK(cudaEventRecord(s.ev1, s.stream));
+  CK(cudaMemcpyAsync(s.h_res, (uint8_t*)s.scratch.buf.p + 64, sizeof(bk::DevResult), cudaMemcpyDeviceToHost, s.stream));
+  return BK_OK;
+}
+
+}  // namespace
+
+int bk_submit_text(bk_ctx* ctx, int slot, uint32_t n, const uint8_t* text1, uint64_t len1, const uint8_t* text2,
+                   uint64_t len2, uint32_t max_rec_hint) {
+  if (!ctx || slot < 0 || slot >= kSlots || !text1) return BK_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[slot];
+  if (s.busy) { ctx->last_error = "slot is busy: call bk_wait first"; return BK_E_ARG; }
+  if (ctx->paired != (text2 != nullptr)) { ctx->last_error = "mate count does not match the context mode"; return BK_E_ARG; }
+  if (n == 0) { ctx->last_error = "empty batch"; return BK_E_ARG; }
+  const uint8_t* text[2] = {text1, text2};
+  const uint64_t len[2] = {len1, len2};
+  const int nm = ctx->paired ? 2 : 1;
+  if (!s.h_tok) CK(cudaHostAlloc((void**)&s.h_tok, 2 * sizeof(bk::TokResult), cudaHostAllocDefault));
+  s.raw = true;
+  s.passthrough = false;
+  s.h2d_bytes = 0;
+  s.launches = 0;
+  bool need_sync = false;
+  for (int m = 0; m < nm; ++m) {
+    if (len[m] == 0 || len[m] >= (1ull << 32) - 65536) { ctx->last_error = "batch text must be 1 byte .. 4 GiB - 64 KiB per mate"; return BK_E_CAPACITY; }
+    int rc;
+    if ((rc = ensure(ctx, &s.text[m], len[m] + 64)) != BK_OK) return rc;
+    if ((rc = ensure(ctx, &s.off[m], ((size_t)n + 2) * 4)) != BK_OK) return rc;
+    const uint64_t ob = bk_out_bound(ctx, m + 1, n, len[m]);
+    if ((rc = ensure(ctx, &s.out[m], ob)) != BK_OK) return rc;
+    s.out_cap[m] = ob;
+    s.raw_len[m] = len[m];
+    s.raw_no_eol[m] = text[m][len[m] - 1] != '\n';
+    s.h2d_bytes += len[m];
+    CK(cudaMemcpyAsync(s.text[m].p, text[m], len[m], cudaMemcpyHostToDevice, s.stream));
+    if ((rc = enqueue_tokenize(ctx, s.stream, (const uint8_t*)s.text[m].p, len[m], s.raw_no_eol[m], n, (uint32_t*)s.off[m].p,
+                               &s.tok[m])) != BK_OK) return rc;
+    CK(cudaMemcpyAsync(&s.h_tok[m], s.tok[m].p, sizeof(bk::TokResult), cudaMemcpyDeviceToHost, s.stream));
+    // The launch plan (tile size) needs the longest record before the tokenizer has answered: the caller's hint, else
+    // what earlier batches of this context showed (with headroom).  A batch whose records turn out longer is launched
+    // again by bk_wait with the exact figure; the first batch of a context without a hint waits for the tokenizer here.
+    uint32_t mr = std::max(max_rec_hint, ctx->maxrec_seen[m] + ctx->maxrec_seen[m] / 8);
+    if (mr == 0) need_sync = true;
+    s.raw_maxrec[m] = mr;
+  }
+  s.n = n;
+  if (need_sync) {
+    CK(cudaStreamSynchronize(s.stream));
+    for (int m = 0; m < nm; ++m) {
+      s.raw_maxrec[m] = std::max(s.raw_maxrec[m], std::max(s.h_tok[m].max_rec_bytes, 1u));
+      ctx->maxrec_seen[m] = std::max(ctx->maxrec_seen[m], s.h_tok[m].max_rec_bytes);
+    }
+  }
+  int rc = enqueue_raw_extract(ctx, s);
+  if (rc != BK_OK) return rc;
+  s.busy = true;
+  return BK_OK;
+}
+
 int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2, bk_result* res) {
   if (!ctx || slot < 0 || slot >= kSlots) return BK_E_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -558,6 +718,25 @@ int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, 
     ~Drain() { cudaStreamSynchronize(s.stream); s.busy = false; }
   } drain{s};
   CK(cudaStreamSynchronize(s.stream));
+  if (s.raw) {
+    // what the device tokenizer found: every mate must hold exactly n well-formed records
+    bool relaunch = false;
+    for (int m = 0; m < (ctx->paired ? 2 : 1); ++m) {
+      const bk::TokResult t = s.h_tok[m];
+      const unsigned long long want = 4ull * s.n - (s.raw_no_eol[m] ? 1 : 0);
+      if (t.newlines != want || t.first_bad != 0xFFFFFFFFu) {
+        ctx->last_error = "malformed FASTQ text";
+        return BK_E_FORMAT;
+      }
+      ctx->maxrec_seen[m] = std::max(ctx->maxrec_seen[m], t.max_rec_bytes);
+      if (t.max_rec_bytes > s.raw_maxrec[m]) { s.raw_maxrec[m] = t.max_rec_bytes; relaunch = true; }
+    }
+    if (relaunch && (s.h_res->error & 2u)) {  // tiles did not fit the staging ring that the hint sized: once more, exactly
+      int rc2 = enqueue_raw_extract(ctx, s);
+      if (rc2 != BK_OK) return rc2;
+      CK(cudaStreamSynchronize(s.stream));
+    }
+  }
   bk::DevResult r = *s.h_res;
   int rc = check_dev_result(ctx, r);
   if (rc != BK_OK) return rc;

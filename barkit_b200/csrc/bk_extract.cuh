@@ -5,13 +5,8 @@
 
 namespace bk {
 
-// Input ring depth per mate (the loader runs at most this far ahead).  BYP (below) stages one mate only and
-// spends the shared memory that frees on two more slots.
-template <bool BYP> __host__ __device__ constexpr int stages() { return BYP ? 6 : 4; }
+constexpr int kStages = 4;  // input ring depth per mate (the loader runs at most this far ahead)
 constexpr int kBackWarps = kEmitParts;  // back warps per mate: warp j writes part j of every record (emit_part)
-// BYP: seven back warps assemble the rewritten mate (header | captures | captures | seq x 2 | qual x 2), three
-// copy warps move the other mate's kept records global -> global
-constexpr int kBackWarpsByp = 7, kCopyWarps = 3;
 
 // ---- ordered compaction: two-level decoupled look-back ---------------------------------------------------
 //
@@ -130,17 +125,16 @@ __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned 
 #define EVT(tile, idx)
 #endif
 
-// Named barriers (16 per CTA): 0 __syncthreads, 1 the first front pair's exchange, 2-3 the back warps of
-// mate 0 / 1 among themselves, then one per ring slot for fronts -> scan ("aggregates published") and
-// scan -> backs ("offsets known"), then the second front pair's exchange.  BYP has six ring slots: its copy
-// warps need no barrier among themselves, so 3 is the second pair's exchange there and 4..15 the slots'.
+// named barrier of one mate's back warps (ids 2 and 3; 0 is __syncthreads, 1 the front warps')
+__device__ __forceinline__ void back_sync(int m, uint32_t nwarps) { nbar_sync(2u + (uint32_t)m, 32u * nwarps); }
+
+// Named barriers (16 per CTA): 0 __syncthreads, 1 the front warps' exchange, 2-3 back_sync, then one
+// per ring slot for fronts -> scan ("aggregates published") and scan -> backs ("offsets known").
 // A slot's barrier is reused only after the slot went round the ring, i.e. after every consumer
 // has left it.
-template <bool BYP> __device__ __forceinline__ void back_sync(int m, uint32_t nwarps) { nbar_sync(BYP ? 2u : 2u + (uint32_t)m, 32u * nwarps); }
-template <bool BYP> __device__ __forceinline__ uint32_t pub_id(uint32_t s) { return 4u + s; }
-template <bool BYP> __device__ __forceinline__ uint32_t ready_id(uint32_t s) { return 4u + stages<BYP>() + s; }
-template <bool BYP> __device__ __forceinline__ uint32_t exch_id(int fp) { return fp == 0 ? 1u : BYP ? 3u : 4u + 2u * stages<BYP>(); }
-static_assert(4 + 2 * stages<false>() + 1 <= 16 && 4 + 2 * stages<true>() <= 16, "16 named barriers per CTA");
+static_assert(kStages <= 5, "barrier ids 4..15: two per ring slot, then the second front pair's exchange");
+__device__ __forceinline__ uint32_t pub_id(uint32_t s) { return 4u + s; }
+__device__ __forceinline__ uint32_t ready_id(uint32_t s) { return 4u + kStages + s; }
 constexpr int kScanWarps = 2;  // scan warp j resolves the tiles of ring rounds k with k % 2 == j
 
 constexpr int kSkipTile = -2147483647 - 1;
@@ -163,12 +157,8 @@ constexpr int kFrontPairs = 2;  // front warps per mate: warp p takes the ring r
 // A ring slot's barriers must always meet the same scan warp and front pair.  With an odd ring depth
 // round k and round k + kStages share their barrier ids but belong to different scan warps, and the
 // one running ahead completes the other's barrier generation (observed: a 3-deep ring hangs).
-static_assert(stages<false>() % kScanWarps == 0 && stages<false>() % kFrontPairs == 0 && stages<true>() % kScanWarps == 0 &&
-              stages<true>() % kFrontPairs == 0, "ring depth must be a multiple of the scan / front warp counts");
-constexpr int cta_warps(bool paired, bool byp = false) {
-  return byp ? kBackWarpsByp + kCopyWarps + kScanWarps + 2 * kFrontPairs + 1
-             : (paired ? 2 : 1) * (kFrontPairs + kBackWarps) + kScanWarps + 1;
-}
+static_assert(kStages % kScanWarps == 0 && kStages % kFrontPairs == 0, "ring depth must be a multiple of the scan / front warp counts");
+constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + kBackWarps) + kScanWarps + 1; }
 
 // GENERAL = false: every pattern is anchored and there is no reverse-complement retry -- the common
 // case, compiled without the search code, because every kilobyte of this kernel competes for the
@@ -176,19 +166,11 @@ constexpr int cta_warps(bool paired, bool byp = false) {
 // VAR (only with GENERAL): a mate's pattern may be a list of fixed-length variants (bounded variable
 // repetition, bk_pattern.cc); the matched variant travels with the match start (start | variant << 24) and
 // supplies the capture offsets, the match length and the header growth of that record.
-// BYP (paired, exactly one mate has a pattern): the pattern-less mate BYPASSES shared memory.  Its records are only
-// ever copied or dropped (run.rs:149-160), so its text is never staged: its front warps parse from global memory
-// (the first sectors of each record, warmed in L2 by the loader's prefetch), and its copy warps move the kept
-// records global -> global once the tile's output offset is known (gcopy_run).  The shared memory that frees
-// holds two more ring slots of the rewritten mate -- the kernel is bound by tiles in flight x their latency
-//  -- and that mate gets seven back warps, so that no warp carries more than half a line.
-template <bool PAIRED, bool GENERAL, bool VAR = false, bool BYP = false>
-__global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) extract_kernel(const __grid_constant__ KParams P) {
+template <bool PAIRED, bool GENERAL, bool VAR = false>
+__global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extract_kernel(const __grid_constant__ KParams P) {
   static_assert(!VAR || GENERAL, "variants are matched by the general kernel");
-  static_assert(!BYP || (PAIRED && !GENERAL), "the bypass form serves paired launches with one anchored pattern");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
-  constexpr int kStages = stages<BYP>();
   __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_empty[2][kStages];
   __shared__ __align__(16) uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, complement table, program
   __shared__ int s_ms[kFrontPairs][2][2][32];  // [front pair][round parity][mate][lane]
@@ -197,13 +179,12 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
   __shared__ uint32_t s_share[GENERAL && PAIRED ? kFrontPairs : 1][2][3][32];
   __shared__ int s_help[GENERAL && PAIRED ? kFrontPairs : 1][2][32];
   __shared__ TileMeta meta[NM][kStages];
-  __shared__ uint4 run_desc[BYP ? kCopyWarps : NM][32];  // copy descriptors of the tile's runs of unchanged records (BYP: one list per copy warp)
+  __shared__ uint4 run_desc[NM][32];  // copy descriptors of the tile's runs of unchanged records
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   // Warp roles, lowest warp ids first: back, scan, front, loader.
-  constexpr int NB = BYP ? kBackWarpsByp + kCopyWarps : NM * kBackWarps;
-  const int pt = BYP ? (P.prog[0].present ? 1 : 0) : -1;  // BYP: the mate that is never staged
+  constexpr int NB = NM * kBackWarps;
   const bool is_back = warp < NB;
   const bool is_scan = !is_back && warp < NB + kScanWarps;
   const bool is_front = !is_back && !is_scan && warp < NB + kScanWarps + NM * kFrontPairs;
@@ -211,8 +192,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
   const int fw = warp - NB - kScanWarps;  // front warp index
   // Back warps per mate: four each, or five and three when only one mate's reads are rewritten (its
   // records cost more to assemble than the other mate's verbatim copies).
-  const uint32_t nb0 = BYP ? (pt == 1 ? kBackWarpsByp : kCopyWarps)
-                       : !PAIRED ? kBackWarps
+  const uint32_t nb0 = !PAIRED ? kBackWarps
                        : (P.prog[0].present && !P.prog[1].present) ? kBackWarps + 1
                        : (!P.prog[0].present && P.prog[1].present) ? kBackWarps - 1 : kBackWarps;
   const int m = is_back ? (warp < (int)nb0 ? 0 : 1) : is_front ? fw % NM : 0;  // mate = output stream
@@ -309,11 +289,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
         if (lane == (int)nrec - 1) onext = oem;
         const uint32_t gbase = __shfl_sync(0xffffffffu, om, 0) & ~15u;
         const uint32_t bytes = ((oem + 15u) & ~15u) - gbase;
-        const bool byp = BYP && mm == pt;            // record bounds stay offsets into the global text
-        const bool too_big = !byp && bytes > P.in_cap[mm];  // host sized the ring from max_rec_bytes
+        const bool too_big = bytes > P.in_cap[mm];  // host sized the ring from max_rec_bytes
         const uint32_t in_s = smem_base + (mm ? kStages * P.in_cap[0] : 0) + s * P.in_cap[mm];
-        tm.beg[lane] = byp ? om : in_s + (om - gbase);
-        tm.end[lane] = byp ? onext : in_s + (onext - gbase);
+        tm.beg[lane] = in_s + (om - gbase);
+        tm.end[lane] = in_s + (onext - gbase);
         if (lane == 0) {
           tm.tile = tile;
           tm.nrec = nrec;
@@ -321,7 +300,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
         }
         __syncwarp();
         if (lane == 0) {
-          if (too_big || byp) {
+          if (too_big) {
             mbar_arrive(&bar_full[mm][s]);
           } else {
             mbar_arrive_expect_tx(&bar_full[mm][s], bytes);
@@ -363,7 +342,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
       mbar_wait(&bar_full[m][s], ph);  // offsets written, text landed
       const uint32_t tile = tm.tile;
       if (tile == kEndTile || tile == kEndTile2) {  // one end marker per front pair (and per scan warp)
-        nbar_arrive(pub_id<BYP>(s), kPubCount);
+        nbar_arrive(pub_id(s), kPubCount);
         break;
       }
       if (m == 0) { EVT(tile, 3) }
@@ -376,7 +355,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
       int ms = -1;
       if (!too_big) {
         // ---- parse + match (lane per record) ---------------------------------------------------
-        if (active) rv = (BYP && m == pt) ? parse_record_g(P.text[m], tm.beg[lane], tm.end[lane]) : parse_record(tm.beg[lane], tm.end[lane]);
+        if (active) rv = parse_record(tm.beg[lane], tm.end[lane]);
         __syncwarp();
         if (m == 0) { EVT(tile, 4) }
         const bool can = active && pg.present && rv.qual_len == rv.seq_len;  // unequal lengths never leave bk_tokenize
@@ -390,7 +369,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
             s_share[fp][xb][0][lane] = rv.seq;
             s_share[fp][xb][1][lane] = rv.seq_len;
             s_share[fp][xb][2][lane] = can;
-            nbar_sync(exch_id<BYP>(fp), 64);
+            nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);
           }
           ms = match_unanchored(tab, rv.seq, rv.seq_len, can && !(split && lane >= 16), lane);  // warp per read
         } else if (can) {
@@ -401,11 +380,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
         if (lane == 0) atomicOr(&P.result->error, 2u);
         if (GENERAL && split && un_me) {  // keep the pair's barriers in step: nothing to search
           s_share[fp][xb][2][lane] = 0;
-          nbar_sync(exch_id<BYP>(fp), 64);
+          nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);
         }
       }
       if (GENERAL && split && !un_me) {  // the other mate searches: take the upper half of its reads
-        nbar_sync(exch_id<BYP>(fp), 64);
+        nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);
         const int h = match_unanchored(tab_other, s_share[fp][xb][0][lane], s_share[fp][xb][1][lane],
                                        s_share[fp][xb][2][lane] != 0 && lane >= 16, lane);
         s_help[fp][xb][lane] = h;
@@ -417,7 +396,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
       bool skip = too_big;
       if (PAIRED) {
         s_ms[fp][xb][m][lane] = too_big ? kSkipTile : ms;
-        nbar_sync(exch_id<BYP>(fp), 64);  // the two mates' front warps of this pair
+        nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);  // the two mates' front warps of this pair
         ms_other = s_ms[fp][xb][m ^ 1][lane];
         skip = skip || (s_ms[fp][xb][m ^ 1][0] == kSkipTile);
         if (GENERAL && split && lane >= 16) {  // the upper half's search results come from the helper
@@ -426,6 +405,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
         }
       }
       if (!too_big && active && P.match[m]) P.match[m][r0 + lane] = (VAR && ms >= 0) ? (ms & 0xFFFFFF) : ms;
+      if (!PAIRED && !too_big && active && P.hlen[0]) P.hlen[0][r0 + lane] = rv.head_len;  // (the other mate's compaction guesses with it)
       // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
       const bool keep = !skip && active && (ms >= 0 || ms_other >= 0);
 
@@ -461,7 +441,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
       tm.ooff[lane] = keep ? incl - olen : kNotKept;
       if (lane == 0) tm.total = total;
       __syncwarp();
-      nbar_arrive(pub_id<BYP>(s), kPubCount);
+      nbar_arrive(pub_id(s), kPubCount);
       if (m == 0) { EVT(tile, 7) }
       // whoever completes a block publishes its aggregate (the answer of the atomic is needed only now)
       if (lane == 0) {
@@ -483,7 +463,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
     const int sj = warp - NB;
     for (uint32_t k = sj;; k += kScanWarps) {
       const uint32_t s = k % kStages;
-      nbar_sync(pub_id<BYP>(s), kPubCount);
+      nbar_sync(pub_id(s), kPubCount);
       const uint32_t tile = meta[0][s].tile;
       if (tile == kEndTile2) break;
       if (tile != kEndTile) {
@@ -496,58 +476,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
         EVT(tile, 9)
       }
       __syncwarp();
-      nbar_arrive(ready_id<BYP>(s), kReadyCount);
+      nbar_arrive(ready_id(s), kReadyCount);
       if (tile == kEndTile) break;
-    }
-  } else if (BYP && m == pt) {
-    // =============================== COPY (BYP: the mate that is never staged) ====================
-    // Kept records of this mate, global -> global: maximal runs of consecutive kept records in the writer's own
-    // framing are contiguous on both sides (gcopy_run: every copy warp takes every third pass of every run and
-    // every third run's ragged ends); a kept record in foreign framing is re-framed bytewise by its lane.
-    uint8_t* const gdst = P.out[m];
-    const uint8_t* const gsrc = P.text[m];
-    uint4* const rd = run_desc[bj];
-    for (uint32_t k = 0;; ++k) {
-      const uint32_t s = k % kStages;
-      const TileMeta& tm = meta[m][s];
-      nbar_sync(ready_id<BYP>(s), kReadyCount);
-      const uint32_t tile = tm.tile;
-      if (tile == kEndTile) break;
-      const uint32_t total = tm.total;
-      const unsigned long long gout = tm.gout;
-      if (lane == 0 && bj == 0 && tile == P.ntiles - 1) P.result->out_len[m] = gout + total;
-      const bool fits = gout + total <= P.cap[m];
-      if (!fits && lane == 0 && bj == 0) atomicOr(&P.result->error, 1u);
-      if (fits && total) {
-        const uint32_t ooff = tm.ooff[lane];
-        const bool kept = ooff != kNotKept;
-        const uint32_t beg = tm.beg[lane], end = tm.end[lane], qf = tm.qual_len_fast[lane];
-        const bool unc = kept && (qf & 1u);
-        uint8_t* const tile_out = gdst + gout;
-        const unsigned um = __ballot_sync(0xffffffffu, unc);
-        if (um) {
-          const unsigned below = ~um & ((1u << lane) - 1u);
-          const int i0 = unc ? (below ? 32 - __clz(below) : 0) : lane;
-          const unsigned above = ~(um >> lane);  // first zero at or above this lane ends the run
-          const int i1 = unc ? (above ? lane + __ffs(above) - 2 : 31) : lane;
-          const uint32_t run_n = __shfl_sync(0xffffffffu, end, i1) - beg;
-          const bool first = unc && i0 == lane;
-          const unsigned starts = __ballot_sync(0xffffffffu, first);
-          if (first) rd[__popc(starts & ((1u << lane) - 1u))] = make_uint4(beg, ooff, run_n, 0u);
-          __syncwarp();
-          const uint32_t nruns = __popc(starts);
-          uint32_t t0 = (uint32_t)bj, fr = (uint32_t)bj;  // first pass / fringe duty rotate from run to run
-          for (uint32_t r = 0; r < nruns; ++r) {
-            gcopy_run(gsrc, tile_out, rd[r], lane, t0, (uint32_t)kCopyWarps, fr == 0);
-            t0 = t0 == 0 ? kCopyWarps - 1u : t0 - 1u;
-            fr = fr == 0 ? kCopyWarps - 1u : fr - 1u;
-          }
-        }
-        if (bj == 0 && kept && !unc)
-          emit_record_g(gsrc, beg, tm.head_len[lane], tm.seq[lane], tm.seq_len[lane], tm.qual[lane], qf >> 1, tile_out + ooff);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_empty[m][s]);  // this warp is done with the slot's meta
     }
   } else {
     // =============================== BACK =======================================================
@@ -555,7 +485,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
     for (uint32_t k = 0;; ++k) {
       const uint32_t s = k % kStages;
       const TileMeta& tm = meta[m][s];
-      nbar_sync(ready_id<BYP>(s), kReadyCount);
+      nbar_sync(ready_id(s), kReadyCount);
       const uint32_t tile = tm.tile;
       if (tile == kEndTile) break;
       if (m == 0 && bj == 0) { EVT(tile, 10) }
@@ -568,7 +498,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
       // The output tile may be overwritten once the engine has read the previous tile out of it.  That
       // wait sits here, behind the wait for this tile's offset, rather than behind the store itself.
       if (bj == 0 && lane == 0) bulk_wait_read0();
-      back_sync<BYP>(m, nparts);
+      back_sync(m, nparts);
       if (fits && total) {
         // ---- assemble the tile's output in shared memory (same 16-byte phase as the global destination)
         const uint32_t ooff = tm.ooff[lane];
@@ -595,10 +525,9 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
         const bool even = kept && lane < 31 && nxt != kNotKept && ((nxt - ooff) & 31u) == 0;
         const uint32_t rot = __popc(__ballot_sync(0xffffffffu, even)) >= 8 ? ((uint32_t)lane & 7u) + 1u : 0u;
         if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
-        // warp per pass: maximal runs of consecutive unchanged records (BYP: a kept record of the rewritten
-        // mate always matched, so there are none)
-        const unsigned um = BYP ? 0u : __ballot_sync(0xffffffffu, unc);
-        if (!BYP && um) {
+        // warp per pass: maximal runs of consecutive unchanged records
+        const unsigned um = __ballot_sync(0xffffffffu, unc);
+        if (um) {
           // lane i learns its run [i0, i1]; the run's first lane files the copy descriptor (every back
           // warp of the mate writes the same list) and the runs' ragged ends go to warps 0 and 1
           const unsigned below = ~um & ((1u << lane) - 1u);
@@ -640,7 +569,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED, BYP) * 32, PAIRED ? 2 : 4) e
       if (lane == 0) mbar_arrive(&bar_empty[m][s]);  // ring slot (input tile + meta) is free again
       if (fits && total) fence_proxy_async_smem();
       // all shares written -> one warp stores; nobody overwrites the tile until the store has read it
-      back_sync<BYP>(m, nparts);
+      back_sync(m, nparts);
       if (m == 0 && bj == 0) { EVT(tile, 12) }
       if (fits && total && bj == 0) {
         // ---- store: aligned middle by TMA, ragged edges by the lanes ---------------------------------

@@ -57,6 +57,9 @@ struct KParams {
   // priority order, in device memory (prog[m] is the first).  Only extract_kernel<.., true, true> reads them.
   uint32_t nvar[2];
   const bk_devprog* vprog[2];
+  // Optional: the header length of every read (the compaction of a pattern-less mate uses its partner's as the guess
+  // for its own, bk_compact.cuh).
+  uint32_t* hlen[2];
 };
 
 constexpr unsigned long long kFlagAgg = 1ull << 62;
@@ -832,10 +835,8 @@ constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is
 __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
                                           uint32_t part, uint32_t nparts, uint32_t rot) {
   OutStream o;
-  // jobs of this part, bit 0 = A ... bit 4 = E; with seven parts D and E are two parts each (half 1 and 2)
-  const uint32_t jobs = nparts == 7 ? (part < 3u ? 1u << part : part < 5u ? 8u : 16u)
-                        : nparts == 5 ? 1u << part : nparts == 4 ? (part == 0 ? 3u : 2u << part) : (part == 0 ? 5u : 4u << part);
-  const uint32_t half = nparts == 7 && part >= 3u ? 1u + ((part - 3u) & 1u) : 0u;
+  // jobs of this part, bit 0 = A ... bit 4 = E
+  const uint32_t jobs = nparts == 5 ? 1u << part : nparts == 4 ? (part == 0 ? 3u : 2u << part) : (part == 0 ? 5u : 4u << part);
   const uint32_t ncaps = ms >= 0 ? pg.ncaps : 0u;
   const uint32_t csplit = (ncaps + 1u) >> 1;
   const uint32_t H = r.head_len, L = r.seq_len;
@@ -879,24 +880,6 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
   const uint32_t sep = isD ? (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16) : (uint32_t)'\n';
   const uint32_t nsep = isD ? 3u : 1u;
   const uint32_t dpos = d + 2u + H + G + (isD ? 0u : L - (ce - cs) + 3u);
-  if (half && r.fast) {
-    // two warps share the line: its output is the byte stream src[0, ps) ++ src[pe, ll + nsep) (the line end
-    // travels with the text), cut in the middle; each warp writes its side (they meet at an arbitrary byte)
-    const uint32_t tail = ll - pe + nsep, tot = ps + tail, mid = (tot >> 1) & ~3u;
-    const uint32_t lo = half == 1u ? 0u : mid, hi = half == 1u ? mid : tot;
-    if (hi > lo) {
-      os_begin(o, dpos + lo);
-      o.rot = rot;
-      if (lo < ps) os_run(o, src + lo, (hi < ps ? hi : ps) - lo);
-      if (hi > ps) {
-        const uint32_t a = (lo > ps ? lo : ps) - ps;
-        os_run(o, src + pe + a, hi - ps - a);
-      }
-      os_end(o);
-    }
-    return;
-  }
-  if (half == 2u) return;  // (foreign framing: the first half's warp writes the whole line)
   os_begin(o, dpos);
   o.rot = rot;
   if (ps) os_run(o, src, ps);
@@ -909,46 +892,31 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
   os_end(o);
 }
 
-// ---- a mate that is never staged on chip: its kept records go global -> global ---------------------------
-//
-// In paired mode a mate without a pattern is only ever copied or dropped (run.rs:149-160).  Maximal runs of
-// consecutive kept records that already have the writer's framing are contiguous in the input text and in the
-// output, so they move like bulk16 moves them inside shared memory, with both sides in global memory:
-// consecutive lanes own consecutive 16-byte aligned destination chunks, load the two aligned source chunks
-// under them (the second is the next lane's first: L1 serves it) and funnel-shift by the run's relative
-// misalignment.  The run's ragged ends (< 16 bytes each) are copied bytewise, one lane per byte.
-//   run descriptor: x = source offset in the text, y = destination offset in the tile's output, z = bytes
-__device__ __forceinline__ void gcopy_run(const uint8_t* text, uint8_t* tile_out, const uint4 r, int lane, uint32_t t0,
-                                          uint32_t tstep, bool fringes) {
-  const uint8_t* const sp = text + r.x;
-  uint8_t* const dp = tile_out + r.y;
-  const uint32_t n = r.z;
-  const uintptr_t A = reinterpret_cast<uintptr_t>(dp);
-  const uintptr_t D0 = (A + 15u) & ~uintptr_t(15), D1 = (A + n) & ~uintptr_t(15);
-  const uintptr_t S0 = reinterpret_cast<uintptr_t>(sp) + (D0 - A);  // source of the first full chunk
-  const uint32_t sh = (uint32_t)(S0 & 15u), bits = (sh & 3u) * 8u;
-  const bool q1 = (sh & 4u) != 0, q2 = (sh & 8u) != 0;  // (warp-uniform)
-  const uint4* const sa = reinterpret_cast<const uint4*>(S0 & ~uintptr_t(15));
-  for (uintptr_t D = D0 + 16u * (32u * t0 + (uint32_t)lane); D < D1; D += 512u * tstep) {
-    const size_t c = (D - D0) >> 4;
-    const uint4 x = __ldg(sa + c);
-    uint4 y = x;
-    if (sh) y = __ldg(sa + c + 1);
-    const uint32_t a0 = q2 ? x.z : x.x, a1 = q2 ? x.w : x.y, a2 = q2 ? y.x : x.z, a3 = q2 ? y.y : x.w;
-    const uint32_t a4 = q2 ? y.z : y.x, a5 = q2 ? y.w : y.y;
-    const uint32_t b0 = q1 ? a1 : a0, b1 = q1 ? a2 : a1, b2 = q1 ? a3 : a2, b3 = q1 ? a4 : a3, b4 = q1 ? a5 : a4;
-    *reinterpret_cast<uint4*>(D) = make_uint4(__funnelshift_r(b0, b1, bits), __funnelshift_r(b1, b2, bits),
-                                              __funnelshift_r(b2, b3, bits), __funnelshift_r(b3, b4, bits));
-  }
-  if (fringes) {
-    uint32_t pad = (uint32_t)((16u - (A & 15u)) & 15u);
-    pad = pad < n ? pad : n;
-    const uint32_t t = (uint32_t)(D1 - A);  // (wraps when the run ends before its first aligned chunk)
-    const uint32_t tlo = (int32_t)t > (int32_t)pad ? t : pad;
-    if ((uint32_t)lane < pad) dp[lane] = (uint8_t)__ldg(sp + lane);
-    const uint32_t j = tlo + ((uint32_t)lane - 16u);
-    if (lane >= 16 && j < n) dp[j] = (uint8_t)__ldg(sp + j);
-  }
+// A record of the never-staged mate, parsed with probes instead of a scan.  `H` is a guess of its header length
+// (the other mate's, which is the same in every FASTQ pair the common tools write).  If the record is in the
+// writer's framing with that header length, its bytes at four positions are line ends:
+//   '@' H bytes LF | L bytes LF | '+' LF | L bytes LF          with L = (e - b - H - 6) / 2.
+// A record holds exactly four line ends (its bounds come from bk_tokenize: every fourth newline), so four
+// distinct ones found are all of them and the lines are as assumed.  Anything else (another header length, CR
+// line ends, text after '+', no final EOL) returns false and takes the scanning parser.  One round trip.
+__device__ __forceinline__ bool parse_probe_g(const uint8_t* t, uint32_t b, uint32_t e, uint32_t H, RecView& r) {
+  const uint32_t sb = b + H + 2u;
+  if (e < sb + 4u || ((e - sb) & 1u)) return false;
+  const uint32_t L = (e - sb - 4u) >> 1;
+  const uint32_t ch = __ldg(t + sb - 1u), c0 = __ldg(t + sb + L), c1 = __ldg(t + sb + L + 1u), c2 = __ldg(t + sb + L + 2u);
+  const uint32_t c3 = __ldg(t + e - 1u), c4 = __ldg(t + sb + L - 1u), c5 = __ldg(t + e - 2u), c6 = __ldg(t + sb - 2u);
+  const bool framed = (ch == '\n') & (c0 == '\n') & (c1 == '+') & (c2 == '\n') & (c3 == '\n');
+  const bool cr = ((L != 0) & ((c4 == '\r') | (c5 == '\r'))) | ((H != 0) & (c6 == '\r'));
+  if (!framed || cr) return false;
+  r.beg = b;
+  r.end = e;
+  r.fast = 1;
+  r.head_len = H;
+  r.seq = sb;
+  r.seq_len = L;
+  r.qual = sb + L + 3u;
+  r.qual_len = L;
+  return true;
 }
 
 // a kept record of such a mate in foreign framing (CR line ends, text after '+', no final EOL): re-framed

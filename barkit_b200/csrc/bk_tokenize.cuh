@@ -228,6 +228,11 @@ __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* t
   }
 }
 
+// rec_off[n] = end (a last record without line end: no newline writes its end offset)
+__global__ void tok_set_end_kernel(uint32_t* rec_off, uint32_t n, uint32_t end) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) rec_off[n] = end;
+}
+
 // first '\n' in [b, e) or e
 __device__ __forceinline__ uint32_t tok_find_nl(const uint8_t* text, uint32_t b, uint32_t e) {
   while (b < e && text[b] != '\n') ++b;

@@ -45,6 +45,11 @@ extern "C" {
 #define BK_FLAG_DEVICE_BOTH_MATES 8u
 #define BK_FLAG_HOST_MATE_PINNED 16u
 #define BK_FLAG_VERBOSE 32u
+/*   BK_FLAG_STAGE_BOTH_MATES   paired mode with one pattern, both mates on the device: run the paired form of the
+ *                              extract kernel (both mates staged through shared memory) instead of the default
+ *                              two-kernel form (single-end extract of the pattern's mate + compaction of the
+ *                              other); for measurements and tests, the output is identical */
+#define BK_FLAG_STAGE_BOTH_MATES 64u
 
 /* Layout guards: a binding written against this header (rust/barkit-extract/src/ffi.rs) must
  * agree with these sizes; they only ever grow at the end, together with the numbers here. */
@@ -182,6 +187,18 @@ int bk_ctx_nslots(const bk_ctx* ctx);
 int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2);
 int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
             bk_result* res);
+
+/* Raw-text form of bk_submit (seq_io's tokenising, fastq.rs:166-172, moves to the device).
+ * The caller hands over the FASTQ text of exactly n whole records per mate -- it only has to know where a record
+ * boundary is, e.g. from counting line ends -- and no offsets: bk_tokenize_device's kernels make them on the
+ * device, asynchronously, in front of the extract kernel.  bk_wait (same call as for bk_submit) returns BK_E_FORMAT
+ * when a mate does not hold n well-formed records.  Both mates go to the device in this form.  The text need not be
+ * aligned; it must stay valid until bk_wait returns.  A last record without a line end is accepted (text ends
+ * with it).  max_rec_hint: an upper bound of the longest record if the caller has one, else 0 (the first batch of
+ * a context then waits for the tokenizer once; later batches go by what earlier ones showed, and a batch with a
+ * longer record is launched again inside bk_wait). */
+int bk_submit_text(bk_ctx* ctx, int slot, uint32_t n, const uint8_t* text1, uint64_t len1, const uint8_t* text2,
+                   uint64_t len2, uint32_t max_rec_hint);
 
 uint64_t bk_out_bound(const bk_ctx* ctx, int mate, uint32_t n, uint64_t text_len);
 

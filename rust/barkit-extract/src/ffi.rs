@@ -77,6 +77,7 @@ pub const BK_FLAG_RC: u32 = 4;
 pub const BK_FLAG_DEVICE_BOTH_MATES: u32 = 8;
 pub const BK_FLAG_HOST_MATE_PINNED: u32 = 16;
 pub const BK_FLAG_VERBOSE: u32 = 32;
+pub const BK_FLAG_STAGE_BOTH_MATES: u32 = 64;
 
 extern "C" {
     // pattern.rs
@@ -105,6 +106,8 @@ extern "C" {
     pub fn bk_out_bound(ctx: *const BkCtx, mate: c_int, n: u32, text_len: u64) -> u64;
     pub fn bk_ctx_nslots(ctx: *const BkCtx) -> c_int;
     pub fn bk_submit(ctx: *mut BkCtx, slot: c_int, n: u32, in1: *const BkMateIn, in2: *const BkMateIn) -> c_int;
+    pub fn bk_submit_text(ctx: *mut BkCtx, slot: c_int, n: u32, text1: *const u8, len1: u64, text2: *const u8, len2: u64,
+                          max_rec_hint: u32) -> c_int;
     pub fn bk_wait(ctx: *mut BkCtx, slot: c_int, out1: *mut u8, cap1: u64, out2: *mut u8, cap2: u64,
                    res: *mut BkResult) -> c_int;
     pub fn bk_extract_host(ctx: *mut BkCtx, n: u32, in1: *const BkMateIn, in2: *const BkMateIn, out1: *mut u8,

@@ -51,7 +51,8 @@ iv(8, 9, "scan: look-back")
 iv(6, 9, "PUBLISH -> READY")
 iv(9, 10, "ready -> back starts (back queue)")
 iv(10, 11, "back warp (0,0): emit")
-iv(10, 15, "back warp (0,3): emit")
+iv(10, 15, "back warp (0,3): emit  [BYP: ready -> copy warp 0 done]")
+iv(9, 15, "S ready -> copy warp 0 done (BYP)")
 iv(11, 12, "back: wait for the other parts")
 iv(12, 13, "back: store + second sync")
 iv(10, 13, "BACK total")
