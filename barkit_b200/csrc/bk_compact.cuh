@@ -33,12 +33,20 @@ namespace bk {
 
 constexpr int kCompactRecs = 256;     // records per tile = threads per CTA
 constexpr int kCompactThreads = 256;
+#ifndef BK_COMPACT_UNROLL
+#define BK_COMPACT_UNROLL 4
+#endif
+#ifndef BK_POLL_NS
+#define BK_POLL_NS 500
+#endif
+constexpr int kCompactUnroll = BK_COMPACT_UNROLL;  // 16-byte chunks per lane and turn of the copy loop
 
 struct CompactParams {
   const uint8_t* text;
   const uint32_t* off;
-  const int32_t* keep;      // the other mate's match table: >= 0 keeps the pair
-  const uint32_t* hlen;     // the other mate's header lengths (guesses), nullable
+  const unsigned long long* kmask;  // the other mate's keep masks, one per tile of ITS kernel: 1 << 63 | bit i = read i stays
+  uint32_t kmask_recs;      // reads per such tile
+  const uint32_t* hlen;     // the other mate's header lengths (guesses only: read without synchronisation), nullable
   uint8_t* out;
   unsigned long long cap;
   unsigned long long* desc[3];  // tile descriptors, block descriptors, block accumulators (8 bytes per entry, one stream)
@@ -60,12 +68,24 @@ __device__ __forceinline__ uint4 realign16(const uint4 x, const uint4 y, uint32_
                     __funnelshift_r(b3, b4, bits));
 }
 
-__global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_constant__ CompactParams P) {
+__global__ void __launch_bounds__(kCompactThreads, 6) compact_kernel(const __grid_constant__ CompactParams P) {
   __shared__ uint32_t s_warp[kCompactThreads / 32];
   __shared__ uint32_t s_tile;
   __shared__ unsigned long long s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_tile = atomicAdd(P.ticket, 1u);
+  if (warp == 0) {
+    // The hand-over from the other mate's extract kernel is its tiles' keep masks, one self-contained 8-byte message
+    // per tile: this kernel depends on nothing else of that launch, and a mask that is not there yet is waited for
+    // (so the two kernels may also overlap; one warp polls, the CTA's other warps block on the barrier).
+    uint32_t tk = 0;
+    if (lane == 0) tk = atomicAdd(P.ticket, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    const uint32_t f = tk * kCompactRecs, l = min(f + (uint32_t)kCompactRecs, P.n) - 1u;
+    const uint32_t k0 = f / P.kmask_recs, k1 = l / P.kmask_recs;
+    for (uint32_t k = k0 + (uint32_t)lane; k <= k1; k += 32u)
+      while (!(ld_relaxed_u64(P.kmask + k) >> 63)) __nanosleep(BK_POLL_NS);
+    if (lane == 0) s_tile = tk;
+  }
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t r0 = tile * kCompactRecs;
@@ -78,11 +98,12 @@ __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_c
   rv.beg = rv.end = rv.fast = rv.head_len = rv.seq = rv.seq_len = rv.qual = rv.qual_len = 0;
   bool kept = false;
   if (t < nrec) {
-    kept = P.keep[r0 + t] >= 0;
-    if (kept) {
-      const uint32_t b = P.off[r0 + t], e = P.off[r0 + t + 1u];
-      if (!(P.hlen && parse_probe_g(text, b, e, P.hlen[r0 + t], rv))) rv = parse_record_g(text, b, e);
-    }
+    const uint32_t b = P.off[r0 + t], e = P.off[r0 + t + 1u];
+    const uint32_t hl = P.hlen ? __ldcg(P.hlen + r0 + t) : 0u;
+    const uint32_t kt = (r0 + t) / P.kmask_recs, kb = (r0 + t) - kt * P.kmask_recs;
+    const unsigned long long km = ld_relaxed_u64(P.kmask + kt);  // (complete: warp 0 saw it)
+    kept = (km >> kb) & 1ull;
+    if (kept && !(P.hlen && parse_probe_g(text, b, e, hl, rv))) rv = parse_record_g(text, b, e);
   }
   const bool verb = kept && rv.fast;  // goes out verbatim
   const uint32_t size = !kept ? 0u : verb ? rv.end - rv.beg : 1u + rv.head_len + 1u + rv.seq_len + 3u + rv.qual_len + 1u;
@@ -119,21 +140,7 @@ __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_c
   }
   __syncthreads();
   const unsigned long long gbase = s_base;
-  if (threadIdx.x == 0 && tile == P.ntiles - 1) {
-    // the batch's last tile: this mate's output length; and the pair's result as the caller expects it (the
-    // single-end kernel before this one filed its mate's figures under index 0)
-    DevResult* r = P.result;
-    const unsigned long long mine = gbase + total;
-    if (P.stream == 0) {
-      r->out_len[1] = r->out_len[0];
-      r->n_match[1] = r->n_match[0];
-      r->out_len[0] = mine;
-      r->n_match[0] = 0;
-    } else {
-      r->out_len[1] = mine;
-      r->n_match[1] = 0;
-    }
-  }
+  if (threadIdx.x == 0 && tile == P.ntiles - 1) P.result->out_len[P.stream] = gbase + total;  // the batch's last tile
   if (gbase + total > P.cap) {
     if (threadIdx.x == 0) atomicOr(&P.result->error, 1u);
     return;
@@ -158,7 +165,21 @@ __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_c
     const uintptr_t S0 = reinterpret_cast<uintptr_t>(sp) + (D0 - A);  // source of the first whole chunk
     const uint32_t sh = (uint32_t)(S0 & 15u);
     const uint4* const sa = reinterpret_cast<const uint4*>(S0 & ~uintptr_t(15));
-    for (uintptr_t D = D0 + 16u * (uint32_t)lane; D < D1; D += 512u) {
+    uintptr_t D = D0 + 16u * (uint32_t)lane;
+#pragma unroll 1
+    for (; D + 512u * (kCompactUnroll - 1) < D1; D += 512u * kCompactUnroll) {  // all loads of a turn in flight together
+      const size_t c = (D - D0) >> 4;
+      uint4 x[kCompactUnroll], y[kCompactUnroll];
+#pragma unroll
+      for (int u = 0; u < kCompactUnroll; ++u) {
+        x[u] = __ldg(sa + c + 32 * u);
+        y[u] = sh ? __ldg(sa + c + 32 * u + 1) : x[u];
+      }
+#pragma unroll
+      for (int u = 0; u < kCompactUnroll; ++u) *reinterpret_cast<uint4*>(D + 512u * u) = realign16(x[u], y[u], sh);
+    }
+#pragma unroll 1
+    for (; D < D1; D += 512u) {
       const size_t c = (D - D0) >> 4;
       const uint4 x = __ldg(sa + c);
       const uint4 y = sh ? __ldg(sa + c + 1) : x;

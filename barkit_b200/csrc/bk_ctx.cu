@@ -130,7 +130,7 @@ struct LaunchPlan {
 };
 
 size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_t in_cap[2],
-                uint32_t out_cap[2]) {
+                uint32_t out_cap[2], int stages) {
   size_t total = 0;
   int nm = ctx->paired ? 2 : 1;
   for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
@@ -138,7 +138,7 @@ size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_
     uint32_t growth = ctx->prog[m].present ? ctx->growth[m] : 0;
     in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
     out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
-    total += bk::kStages * (size_t)in_cap[m] + out_cap[m];
+    total += (size_t)stages * in_cap[m] + out_cap[m];
   }
   return total;
 }
@@ -154,40 +154,41 @@ bool needs_general(const bk_ctx* ctx) {
   return false;
 }
 
-template <bool PAIRED, bool GENERAL, bool VAR = false>
+template <bool PAIRED, bool GENERAL, bool VAR = false, int ST = bk::kStages>
 int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
   constexpr int kThreads = bk::cta_warps(PAIRED) * 32;
   // Two CTAs per SM (228 KB of shared memory per SM, each CTA's static part included) whenever the records
   // allow it: the kernel is bound by ring slots in flight, and the instantiations differ in static shared
   // memory (the general ones carry the search-sharing buffers), so the budget is taken from the kernel itself.
   cudaFuncAttributes fa;
-  CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR>));
-  constexpr int kWant = PAIRED ? 2 : 4;  // CTAs per SM the kernel is compiled for (launch bounds): 30-36 warps per SM
+  CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR, ST>));
+  constexpr int kWant = PAIRED ? 2 : 4;  // CTAs per SM the kernel is compiled for (launch bounds): 30-40 warps per SM
   const size_t target = std::min<size_t>(kTargetDynSmem, (233472 / kWant - fa.sharedSizeBytes) & ~size_t(127));
   uint32_t R = bk::kTileRecs;
   // prefer several resident tiles per SM; never go below 8 records unless a tile would not fit
-  while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > target) --R;
-  while (R > 0 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap) > kMaxDynSmem) --R;
+  while (R > 8 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, ST) > target) --R;
+  while (R > 0 && smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, ST) > kMaxDynSmem) --R;
   if (R == 0) {
     ctx->last_error = "record too long for the on-chip staging buffer";
     return BK_E_CAPACITY;
   }
-  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, ST>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0, other = 0;  // `other`: CTAs per SM that registers and threads allow
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, bk::extract_kernel<PAIRED, GENERAL, VAR>, kThreads, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, bk::extract_kernel<PAIRED, GENERAL, VAR, ST>, kThreads, 0));
   for (;;) {
     lp->tile_recs = R;
-    lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap);
-    CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, ST);
+    CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)lp->smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR>,
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR, ST>,
                                                      kThreads, lp->smem));
     if (per_sm >= kWant || other < kWant || R <= 24) break;  // (long records: the tile stays as it is, fewer CTAs share the SM)
     --R;
   }
   lp->ntiles = (n + R - 1) / R;
   if (per_sm < 1) per_sm = 1;
+  if (per_sm > kWant) per_sm = kWant;
   long long grid = (long long)per_sm * ctx->sm_count;
   if (grid > (long long)lp->ntiles) grid = lp->ntiles;
   lp->grid = (int)std::max<long long>(grid, 1);
@@ -208,9 +209,17 @@ size_t scratch_bytes(uint32_t ntiles) { return events_offset(ntiles); }
 #endif
 
 // enqueue: scratch reset + extract kernel.  All pointers are device pointers.
+// `co`: the launch is the first half of a split paired batch (enqueue_split): single-end, keep masks for the compaction
+// that follows it, figures filed under the mate's own index.
+struct CoLaunch {
+  uint32_t* hlen;              // in: where the header lengths go
+  uint32_t rslot;              // in: 0 / 1
+  unsigned long long* kmask;   // out
+  uint32_t tile_recs;          // out
+};
 int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
                     const bk_mate_in* in2, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
-                    int32_t* match1, int32_t* match2, uint32_t* launches, uint32_t* hlen1 = nullptr);
+                    int32_t* match1, int32_t* match2, uint32_t* launches, CoLaunch* co = nullptr);
 
 // A paired launch with exactly one pattern, as two kernels (bk_compact.cuh): the single-end extract kernel on the
 // pattern's mate, leaving its match table and header lengths on the device, then the ordered compaction of the
@@ -227,35 +236,49 @@ int enqueue_split(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const b
   if (in[pt]->text_len >= (1ull << 32)) { ctx->last_error = "batch text must be < 4 GiB per mate"; return BK_E_CAPACITY; }
   if (((uintptr_t)in[pt]->text & 15) != 0) { ctx->last_error = "batch text must be 16-byte aligned"; return BK_E_ARG; }
   int rc;
-  if ((rc = ensure(ctx, &s->split_match, ((size_t)n + 1) * 4)) != BK_OK) return rc;
   if ((rc = ensure(ctx, &s->split_hlen, ((size_t)n + 1) * 4)) != BK_OK) return rc;
-  int32_t* const keep = user_match[pm] ? user_match[pm] : (int32_t*)s->split_match.p;
-  rc = enqueue_extract(ctx->solo, s, stream, n, in[pm], nullptr, out[pm], cap[pm], nullptr, 0, keep, nullptr, launches,
-                       (uint32_t*)s->split_hlen.p);
-  if (rc != BK_OK) { ctx->last_error = ctx->solo->last_error; return rc; }
+  // everything the compaction needs zeroed goes in front of the extract kernel: the two kernels must be adjacent in
+  // the stream for the programmatic dependent launch
+  const uint32_t ntiles = n ? (n + bk::kCompactRecs - 1) / bk::kCompactRecs : 0;
+  uint8_t* sc = nullptr;
+  if (n) {
+    if ((rc = ensure(ctx, &s->split_scratch, scratch_bytes(ntiles))) != BK_OK) return rc;
+    sc = (uint8_t*)s->split_scratch.p;
+    CK(cudaMemsetAsync(sc, 0, scratch_bytes(ntiles), stream));
+  }
   if (user_match[pt]) CK(cudaMemsetAsync(user_match[pt], 0xFF, (size_t)n * 4, stream));  // no pattern: nothing matches (-1)
+  CoLaunch co;
+  co.hlen = (uint32_t*)s->split_hlen.p;
+  co.rslot = (uint32_t)pm;
+  co.kmask = nullptr;
+  co.tile_recs = 0;
+  rc = enqueue_extract(ctx->solo, s, stream, n, in[pm], nullptr, out[pm], cap[pm], nullptr, 0, user_match[pm], nullptr,
+                       launches, &co);
+  if (rc != BK_OK) { ctx->last_error = ctx->solo->last_error; return rc; }
   if (n == 0) return BK_OK;
-  const uint32_t ntiles = (n + bk::kCompactRecs - 1) / bk::kCompactRecs;
-  if ((rc = ensure(ctx, &s->split_scratch, scratch_bytes(ntiles))) != BK_OK) return rc;
-  uint8_t* sc = (uint8_t*)s->split_scratch.p;
-  CK(cudaMemsetAsync(sc, 0, scratch_bytes(ntiles), stream));
   bk::CompactParams C;
   memset(&C, 0, sizeof C);
   C.text = in[pt]->text;
   C.off = in[pt]->rec_off;
-  C.keep = keep;
-  C.hlen = (const uint32_t*)s->split_hlen.p;
+  C.kmask = co.kmask;
+  C.kmask_recs = co.tile_recs;
+  C.hlen = co.hlen;
   C.out = out[pt];
   C.cap = cap[pt];
   C.desc[0] = (unsigned long long*)(sc + 512);
   C.desc[1] = (unsigned long long*)(sc + block_desc_offset(ntiles));
   C.desc[2] = (unsigned long long*)(sc + block_acc_offset(ntiles));
   C.ticket = (unsigned int*)sc;
-  C.result = (bk::DevResult*)((uint8_t*)s->scratch.buf.p + 64);  // the single-end launch's: this kernel completes it
+  C.result = (bk::DevResult*)((uint8_t*)s->scratch.buf.p + 64);  // the single-end launch's
   C.n = n;
   C.ntiles = ntiles;
   C.text_len = (uint32_t)in[pt]->text_len;
   C.stream = (uint32_t)pt;
+  // (Launched behind the extract kernel in the ordinary way.  Running the two side by side -- programmatic dependent
+  // launch, the single-end kernel at three CTAs per SM with a 6-deep ring, this kernel following it tile by tile
+  // through the keep masks -- was built and measured: 3.66 ms against 3.11 ms per 10 M pairs of C3.  The few CTAs of
+  // this kernel that fit next to the extract kernel's have too few bytes in flight to keep up, and what they do add
+  // lengthens the extract kernel's memory round trips, which is what bounds it.  DESIGN.md section 4c.)
   bk::compact_kernel<<<ntiles, bk::kCompactThreads, 0, stream>>>(C);
   CK(cudaGetLastError());
   if (launches) *launches += 1;
@@ -264,7 +287,7 @@ int enqueue_split(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const b
 
 int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
                     const bk_mate_in* in2, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
-                    int32_t* match1, int32_t* match2, uint32_t* launches, uint32_t* hlen1) {
+                    int32_t* match1, int32_t* match2, uint32_t* launches, CoLaunch* co) {
   if (ctx->paired && !in2) { ctx->last_error = "paired context needs two mates"; return BK_E_ARG; }
   if (ctx->paired && ctx->solo && !(ctx->flags & BK_FLAG_STAGE_BOTH_MATES))
     return enqueue_split(ctx, s, stream, n, in1, in2, out1, cap1, out2, cap2, match1, match2, launches);
@@ -291,10 +314,12 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
            : ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))
                        : (general ? plan_launch<false, true>(ctx, n, maxrec, &lp) : plan_launch<false, false>(ctx, n, maxrec, &lp));
   if (rc != BK_OK) return rc;
-  rc = ensure(ctx, &s->scratch.buf, scratch_bytes(lp.ntiles));
+  const size_t kmask_off = (scratch_bytes(lp.ntiles) + 15) & ~size_t(15);  // (keep masks behind everything else)
+  const size_t sc_bytes = co ? kmask_off + (size_t)lp.ntiles * 8 : scratch_bytes(lp.ntiles);
+  rc = ensure(ctx, &s->scratch.buf, sc_bytes);
   if (rc != BK_OK) return rc;
   uint8_t* sc = (uint8_t*)s->scratch.buf.p;
-  CK(cudaMemsetAsync(sc, 0, scratch_bytes(lp.ntiles), stream));
+  CK(cudaMemsetAsync(sc, 0, sc_bytes, stream));
 
   P.prog[0] = ctx->prog[0];
   P.prog[1] = ctx->prog[1];
@@ -310,7 +335,12 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.out[0] = out1; P.out[1] = out2;
   P.cap[0] = cap1; P.cap[1] = cap2;
   P.match[0] = match1; P.match[1] = match2;
-  P.hlen[0] = hlen1;
+  if (co) {
+    P.hlen[0] = co->hlen;
+    P.rslot = co->rslot;
+    P.kmask = co->kmask = (unsigned long long*)(sc + kmask_off);
+    co->tile_recs = lp.tile_recs;
+  }
   P.tile_counter = (unsigned int*)sc;
   P.result = (bk::DevResult*)(sc + 64);
   P.prof = (unsigned long long*)(sc + events_offset(lp.ntiles));  // only written by a BK_PROFILE_PHASES build

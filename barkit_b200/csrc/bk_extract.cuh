@@ -132,9 +132,9 @@ __device__ __forceinline__ void back_sync(int m, uint32_t nwarps) { nbar_sync(2u
 // per ring slot for fronts -> scan ("aggregates published") and scan -> backs ("offsets known").
 // A slot's barrier is reused only after the slot went round the ring, i.e. after every consumer
 // has left it.
-static_assert(kStages <= 5, "barrier ids 4..15: two per ring slot, then the second front pair's exchange");
-__device__ __forceinline__ uint32_t pub_id(uint32_t s) { return 4u + s; }
-__device__ __forceinline__ uint32_t ready_id(uint32_t s) { return 4u + kStages + s; }
+// (16 ids: a paired CTA may have at most 5 ring slots, a single-end one, which has no exchange, 6)
+template <int ST> __device__ __forceinline__ uint32_t pub_id(uint32_t s) { return 4u + s; }
+template <int ST> __device__ __forceinline__ uint32_t ready_id(uint32_t s) { return 4u + ST + s; }
 constexpr int kScanWarps = 2;  // scan warp j resolves the tiles of ring rounds k with k % 2 == j
 
 constexpr int kSkipTile = -2147483647 - 1;
@@ -157,7 +157,6 @@ constexpr int kFrontPairs = 2;  // front warps per mate: warp p takes the ring r
 // A ring slot's barriers must always meet the same scan warp and front pair.  With an odd ring depth
 // round k and round k + kStages share their barrier ids but belong to different scan warps, and the
 // one running ahead completes the other's barrier generation (observed: a 3-deep ring hangs).
-static_assert(kStages % kScanWarps == 0 && kStages % kFrontPairs == 0, "ring depth must be a multiple of the scan / front warp counts");
 constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + kBackWarps) + kScanWarps + 1; }
 
 // GENERAL = false: every pattern is anchored and there is no reverse-complement retry -- the common
@@ -166,19 +165,20 @@ constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + 
 // VAR (only with GENERAL): a mate's pattern may be a list of fixed-length variants (bounded variable
 // repetition, bk_pattern.cc); the matched variant travels with the match start (start | variant << 24) and
 // supplies the capture offsets, the match length and the header growth of that record.
-template <bool PAIRED, bool GENERAL, bool VAR = false>
+template <bool PAIRED, bool GENERAL, bool VAR = false, int ST = kStages>
 __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extract_kernel(const __grid_constant__ KParams P) {
   static_assert(!VAR || GENERAL, "variants are matched by the general kernel");
+  static_assert(ST % kScanWarps == 0 && ST % kFrontPairs == 0 && 4 + 2 * ST + (PAIRED ? 1 : 0) <= 16, "ring depth: a multiple of the scan / front warp counts, and 16 named barriers");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
-  __shared__ __align__(8) uint64_t bar_full[2][kStages], bar_empty[2][kStages];
+  __shared__ __align__(8) uint64_t bar_full[2][ST], bar_empty[2][ST];
   __shared__ __align__(16) uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, complement table, program
   __shared__ int s_ms[kFrontPairs][2][2][32];  // [front pair][round parity][mate][lane]
   // search sharing (GENERAL, paired, exactly one mate unanchored): the searching mate's reads {seq, len, can}
   // for the other mate's front warp, and that warp's results for the upper half of the tile
   __shared__ uint32_t s_share[GENERAL && PAIRED ? kFrontPairs : 1][2][3][32];
   __shared__ int s_help[GENERAL && PAIRED ? kFrontPairs : 1][2][32];
-  __shared__ TileMeta meta[NM][kStages];
+  __shared__ TileMeta meta[NM][ST];
   __shared__ uint4 run_desc[NM][32];  // copy descriptors of the tile's runs of unchanged records
 
   const int lane = threadIdx.x & 31;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
   // dynamic shared memory: [mate0 ring][mate1 ring][out0][out1]
   // (32-bit shared-space addresses; see the note at the top of bk_kernels.cuh)
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t out_s = smem_base + kStages * (P.in_cap[0] + (PAIRED ? P.in_cap[1] : 0)) + (m ? P.out_cap[0] : 0);
+  const uint32_t out_s = smem_base + ST * (P.in_cap[0] + (PAIRED ? P.in_cap[1] : 0)) + (m ? P.out_cap[0] : 0);
   const uint32_t tab = smem_u32(&cls_tab[m][0]);
 
   if (is_front && fp == 0) {
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
     for (int i = lane; i < 2 * BK_MAX_OPS; i += 32) tw[kTabOps / 4 + i] = reinterpret_cast<const uint32_t*>(pg.ops)[i];
     for (int i = lane; i < BK_MAX_LIT / 4; i += 32) tw[kTabLit / 4 + i] = reinterpret_cast<const uint32_t*>(pg.lit)[i];
     if (lane == 0)
-      for (int s = 0; s < kStages; ++s) {
+      for (int s = 0; s < ST; ++s) {
         mbar_init(&bar_full[m][s], 1);
         mbar_init(&bar_empty[m][s], m ? NB - nb0 : nb0);
       }
@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
   if (is_loader) {
     // =============================== LOADER =====================================================
     for (uint32_t k = 0;; ++k) {
-      const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
-      // slot free on every mate (passes immediately for the first kStages tiles)
+      const uint32_t s = k % ST, ph = (k / ST) & 1u;
+      // slot free on every mate (passes immediately for the first ST tiles)
 #pragma unroll
       for (int mm = 0; mm < NM; ++mm) mbar_wait(&bar_empty[mm][s], ph ^ 1u);
 #ifdef BK_PROFILE_PHASES
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       if (tile >= P.ntiles) {
         // two end markers in consecutive slots: one per scan warp (they take alternate rounds); the
         // first one also stops the back warps
-        const uint32_t s2 = (k + 1) % kStages, ph2 = ((k + 1) / kStages) & 1u;
+        const uint32_t s2 = (k + 1) % ST, ph2 = ((k + 1) / ST) & 1u;
 #pragma unroll
         for (int mm = 0; mm < NM; ++mm) mbar_wait(&bar_empty[mm][s2], ph2 ^ 1u);
         if (lane == 0)
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         const uint32_t gbase = __shfl_sync(0xffffffffu, om, 0) & ~15u;
         const uint32_t bytes = ((oem + 15u) & ~15u) - gbase;
         const bool too_big = bytes > P.in_cap[mm];  // host sized the ring from max_rec_bytes
-        const uint32_t in_s = smem_base + (mm ? kStages * P.in_cap[0] : 0) + s * P.in_cap[mm];
+        const uint32_t in_s = smem_base + (mm ? ST * P.in_cap[0] : 0) + s * P.in_cap[mm];
         tm.beg[lane] = in_s + (om - gbase);
         tm.end[lane] = in_s + (onext - gbase);
         if (lane == 0) {
@@ -336,13 +336,13 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
     const bool split = GENERAL && !VAR && PAIRED && !rc && un_me != un_other;
     const uint32_t tab_other = smem_u32(&cls_tab[PAIRED ? m ^ 1 : m][0]);
     for (uint32_t k = fp;; k += kFrontPairs) {
-      const uint32_t s = k % kStages, ph = (k / kStages) & 1u;
+      const uint32_t s = k % ST, ph = (k / ST) & 1u;
       const uint32_t xb = (k / kFrontPairs) & 1u;  // exchange buffer of this pair's round
       TileMeta& tm = meta[m][s];
       mbar_wait(&bar_full[m][s], ph);  // offsets written, text landed
       const uint32_t tile = tm.tile;
       if (tile == kEndTile || tile == kEndTile2) {  // one end marker per front pair (and per scan warp)
-        nbar_arrive(pub_id(s), kPubCount);
+        nbar_arrive(pub_id<ST>(s), kPubCount);
         break;
       }
       if (m == 0) { EVT(tile, 3) }
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
             s_share[fp][xb][0][lane] = rv.seq;
             s_share[fp][xb][1][lane] = rv.seq_len;
             s_share[fp][xb][2][lane] = can;
-            nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);
+            nbar_sync(fp == 0 ? 1u : 4u + 2u * ST, 64);
           }
           ms = match_unanchored(tab, rv.seq, rv.seq_len, can && !(split && lane >= 16), lane);  // warp per read
         } else if (can) {
@@ -380,11 +380,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         if (lane == 0) atomicOr(&P.result->error, 2u);
         if (GENERAL && split && un_me) {  // keep the pair's barriers in step: nothing to search
           s_share[fp][xb][2][lane] = 0;
-          nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);
+          nbar_sync(fp == 0 ? 1u : 4u + 2u * ST, 64);
         }
       }
       if (GENERAL && split && !un_me) {  // the other mate searches: take the upper half of its reads
-        nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);
+        nbar_sync(fp == 0 ? 1u : 4u + 2u * ST, 64);
         const int h = match_unanchored(tab_other, s_share[fp][xb][0][lane], s_share[fp][xb][1][lane],
                                        s_share[fp][xb][2][lane] != 0 && lane >= 16, lane);
         s_help[fp][xb][lane] = h;
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       bool skip = too_big;
       if (PAIRED) {
         s_ms[fp][xb][m][lane] = too_big ? kSkipTile : ms;
-        nbar_sync(fp == 0 ? 1u : 4u + 2u * kStages, 64);  // the two mates' front warps of this pair
+        nbar_sync(fp == 0 ? 1u : 4u + 2u * ST, 64);  // the two mates' front warps of this pair
         ms_other = s_ms[fp][xb][m ^ 1][lane];
         skip = skip || (s_ms[fp][xb][m ^ 1][0] == kSkipTile);
         if (GENERAL && split && lane >= 16) {  // the upper half's search results come from the helper
@@ -408,6 +408,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       if (!PAIRED && !too_big && active && P.hlen[0]) P.hlen[0][r0 + lane] = rv.head_len;  // (the other mate's compaction guesses with it)
       // run.rs:71-78 (SE: unmatched reads vanish), run.rs:149-160 (PE: keep iff either mate matched)
       const bool keep = !skip && active && (ms >= 0 || ms_other >= 0);
+      if (!PAIRED && P.kmask) {  // which reads of this tile stay: all the other mate's compaction needs (bk_compact.cuh)
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) st_relaxed_u64(P.kmask + tile, (1ull << 63) | (too_big ? 1ull << 62 : 0ull) | km);
+      }
 
       // ---- size + scan, publish the aggregate -------------------------------------------------------
       const bk_devprog& pe = (VAR && var_me && ms >= 0) ? P.vprog[m][ms >> 24] : pg;  // the record's variant
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       tm.ooff[lane] = keep ? incl - olen : kNotKept;
       if (lane == 0) tm.total = total;
       __syncwarp();
-      nbar_arrive(pub_id(s), kPubCount);
+      nbar_arrive(pub_id<ST>(s), kPubCount);
       if (m == 0) { EVT(tile, 7) }
       // whoever completes a block publishes its aggregate (the answer of the atomic is needed only now)
       if (lane == 0) {
@@ -455,15 +459,15 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       const uint32_t nk = __reduce_add_sync(0xffffffffu, n_kept), nm = __reduce_add_sync(0xffffffffu, n_matched);
       if (lane == 0) {
         if (m == 0 && nk) atomicAdd(&P.result->n_out, (unsigned long long)nk);
-        if (nm) atomicAdd(&P.result->n_match[m], (unsigned long long)nm);
+        if (nm) atomicAdd(&P.result->n_match[m + P.rslot], (unsigned long long)nm);
       }
     }
   } else if (is_scan) {
     // =============================== SCAN =======================================================
     const int sj = warp - NB;
     for (uint32_t k = sj;; k += kScanWarps) {
-      const uint32_t s = k % kStages;
-      nbar_sync(pub_id(s), kPubCount);
+      const uint32_t s = k % ST;
+      nbar_sync(pub_id<ST>(s), kPubCount);
       const uint32_t tile = meta[0][s].tile;
       if (tile == kEndTile2) break;
       if (tile != kEndTile) {
@@ -476,22 +480,22 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         EVT(tile, 9)
       }
       __syncwarp();
-      nbar_arrive(ready_id(s), kReadyCount);
+      nbar_arrive(ready_id<ST>(s), kReadyCount);
       if (tile == kEndTile) break;
     }
   } else {
     // =============================== BACK =======================================================
     uint8_t* const gdst = P.out[m];
     for (uint32_t k = 0;; ++k) {
-      const uint32_t s = k % kStages;
+      const uint32_t s = k % ST;
       const TileMeta& tm = meta[m][s];
-      nbar_sync(ready_id(s), kReadyCount);
+      nbar_sync(ready_id<ST>(s), kReadyCount);
       const uint32_t tile = tm.tile;
       if (tile == kEndTile) break;
       if (m == 0 && bj == 0) { EVT(tile, 10) }
       const uint32_t total = tm.total;
       const unsigned long long gout = tm.gout;
-      if (lane == 0 && bj == 0 && tile == P.ntiles - 1) P.result->out_len[m] = gout + total;
+      if (lane == 0 && bj == 0 && tile == P.ntiles - 1) P.result->out_len[m + P.rslot] = gout + total;
       const bool fits = gout + total <= P.cap[m];
       if (!fits && lane == 0) atomicOr(&P.result->error, 1u);
       const uint32_t phase = (uint32_t)(gout & 15ull);

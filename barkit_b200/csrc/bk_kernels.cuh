@@ -60,6 +60,11 @@ struct KParams {
   // Optional: the header length of every read (the compaction of a pattern-less mate uses its partner's as the guess
   // for its own, bk_compact.cuh).
   uint32_t* hlen[2];
+  // Optional (single-end launches): per tile 1 << 63 | keep bits of its reads, written once the tile is matched --
+  // the hand-over to a compact_kernel running next to this kernel; and the index under which this launch files its
+  // mate's figures in `result` (0, or 1 when it works on the second mate of a pair).
+  unsigned long long* kmask;
+  uint32_t rslot;
 };
 
 constexpr unsigned long long kFlagAgg = 1ull << 62;
@@ -900,6 +905,7 @@ __device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r
 // distinct ones found are all of them and the lines are as assumed.  Anything else (another header length, CR
 // line ends, text after '+', no final EOL) returns false and takes the scanning parser.  One round trip.
 __device__ __forceinline__ bool parse_probe_g(const uint8_t* t, uint32_t b, uint32_t e, uint32_t H, RecView& r) {
+  if (H > e - b) return false;  // (the guess may be anything)
   const uint32_t sb = b + H + 2u;
   if (e < sb + 4u || ((e - sb) & 1u)) return false;
   const uint32_t L = (e - sb - 4u) >> 1;
