@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     srcs = [os.path.join(CSRC, s) for s in LIB_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if force or _stale(LIB, srcs):
-        cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-lpthread"]
+        cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-lpthread", "-lz"]
         if os.environ.get("BK_PROFILE_PHASES"):
             cmd.insert(1, "-DBK_PROFILE_PHASES")
         for d in os.environ.get("BK_DEFINES", "").split():

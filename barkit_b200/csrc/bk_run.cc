@@ -1,14 +1,21 @@
-// File -> file runtime: the replacement of barkit-extract/src/run.rs (`run::run`, run.rs:10-60 and
-// the two loops process_single_end_fastq :83-146 / process_pair_end_fastq :198-276) on top of the
-// batch ABI.  Host side only: memory-mapped plain FASTQ in, parallel record-boundary scan, batches
-// dealt to one worker thread per GPU (each with its own bk_ctx, two slots in flight, pinned staging),
-// outputs written strictly in batch order so that 1/2/4/8-GPU runs produce identical bytes.
-// No collective and no peer traffic: batches are independent (SURVEY.md §8e).
+// File -> file runtime: the replacement of barkit-extract/src/run.rs (`run::run`, run.rs:10-60 and the two loops
+// process_single_end_fastq :83-146 / process_pair_end_fastq :198-276) on top of the batch ABI.  Host side only, and
+// it never looks inside a read:
+//
+//   reader   one thread streams the inputs (plain: parallel pread; gzip family: zlib, one thread per mate) straight
+//            into pinned batch buffers, counts line ends to cut each batch at a record boundary common to both
+//            mates, and carries the rest over into the next batch.  Record offsets, the '@' / '+' / length checks
+//            (seq_io's reader, fastq.rs:166-172) and everything per read happen on the device (bk_submit_text).
+//   workers  one thread per GPU, own bk_ctx, two batches in flight (bk_submit_text / bk_wait).
+//   writers  finished batches get their file offsets in batch order (a prefix sum over output lengths, so 1 / 2 / 4 /
+//            8-GPU runs write identical files, run.rs:79,194) and are then written concurrently with pwrite;
+//            compressed outputs are deflated per batch on the pool first.
+//
+// No collective and no peer traffic: batches are independent (SURVEY.md section 8e).
 #include <errno.h>
 #include <fcntl.h>
 #include <stdio.h>
 #include <string.h>
-#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -16,108 +23,19 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/barkit_b200.h"
+#include "bk_io.h"
 
 namespace {
 
-struct Mapped {
-  const uint8_t* p = nullptr;
-  size_t len = 0;
-  int fd = -1;
-  ~Mapped() {
-    if (p && len) munmap((void*)p, len);
-    if (fd >= 0) close(fd);
-  }
-};
-
 std::string io_error(const std::string& m) { return "I/O error: " + m; }  // error.rs:15-16
-
-bool map_file(const char* path, Mapped* m, std::string* err) {
-  m->fd = open(path, O_RDONLY);
-  if (m->fd < 0) {  // the reference panics here (fastq.rs:110); we report and exit 1
-    *err = std::string("couldn't open file ") + path;
-    return false;
-  }
-  struct stat st;
-  if (fstat(m->fd, &st) != 0) { *err = io_error(strerror(errno)); return false; }
-  m->len = (size_t)st.st_size;
-  if (m->len == 0) return true;
-  void* p = mmap(nullptr, m->len, PROT_READ, MAP_PRIVATE, m->fd, 0);
-  if (p == MAP_FAILED) { *err = io_error(strerror(errno)); return false; }
-  madvise(p, m->len, MADV_SEQUENTIAL);
-  m->p = (const uint8_t*)p;
-  return true;
-}
-
-// CompressionType::detect (fastq.rs:82-99): compressed inputs are recognised and refused
-const char* compressed_kind(const Mapped& m) {
-  if (m.len >= 2 && m.p[0] == 0x1f && m.p[1] == 0x8b) return "gzip";
-  if (m.len >= 4 && m.p[0] == 0x04 && m.p[1] == 0x22 && m.p[2] == 0x4d && m.p[3] == 0x18) return "lz4";
-  return nullptr;
-}
-
-// Record starts of a whole file.  FASTQ as seq_io reads it is four lines per record, so record k
-// starts at line 4k: count newlines per chunk in parallel, prefix-sum, then emit the starts.
-bool record_starts(const Mapped& m, unsigned threads, std::vector<uint64_t>* starts, std::string* err) {
-  starts->clear();
-  if (m.len == 0) { starts->push_back(0); return true; }
-  threads = std::max(1u, threads);
-  const size_t chunk = std::max<size_t>((m.len + threads - 1) / threads, 1 << 20);
-  const size_t nchunks = (m.len + chunk - 1) / chunk;
-  std::vector<uint64_t> nl(nchunks + 1, 0);
-  auto count = [&](size_t c) {
-    const uint8_t* p = m.p + c * chunk;
-    const uint8_t* e = m.p + std::min(m.len, (c + 1) * chunk);
-    uint64_t n = 0;
-    while (p < e) {
-      const void* q = memchr(p, '\n', e - p);
-      if (!q) break;
-      ++n;
-      p = (const uint8_t*)q + 1;
-    }
-    nl[c + 1] = n;
-  };
-  {
-    std::vector<std::thread> th;
-    for (size_t c = 0; c < nchunks; ++c) th.emplace_back(count, c);
-    for (auto& t : th) t.join();
-  }
-  for (size_t c = 0; c < nchunks; ++c) nl[c + 1] += nl[c];
-  // a final line without EOL still counts (seq_io accepts a last record without trailing newline)
-  const uint64_t data_lines = nl[nchunks] + (m.p[m.len - 1] != '\n' ? 1 : 0);
-  if (data_lines % 4 != 0) { *err = "malformed FASTQ: line count is not a multiple of 4"; return false; }
-  const uint64_t nrec = data_lines / 4;
-  starts->assign(nrec + 1, 0);
-  auto emit = [&](size_t c) {
-    const uint8_t* base = m.p;
-    const uint8_t* p = base + c * chunk;
-    const uint8_t* e = base + std::min(m.len, (c + 1) * chunk);
-    uint64_t line = nl[c];  // index of the line that contains / starts at p's predecessor newline
-    // a line starts at p iff p == base or p[-1] == '\n'
-    if (c == 0) (*starts)[0] = 0;
-    while (p < e) {
-      const void* q = memchr(p, '\n', e - p);
-      if (!q) break;
-      ++line;  // `line` newlines seen so far: the next line has index `line`
-      const uint64_t pos = (const uint8_t*)q - base + 1;
-      if (line % 4 == 0 && line / 4 <= nrec) (*starts)[line / 4] = pos;
-      p = (const uint8_t*)q + 1;
-    }
-  };
-  {
-    std::vector<std::thread> th;
-    for (size_t c = 0; c < nchunks; ++c) th.emplace_back(emit, c);
-    for (auto& t : th) t.join();
-  }
-  if ((*starts)[nrec] == 0 && nrec > 0) (*starts)[nrec] = m.len;  // last record without trailing EOL
-  // '@' / '+' / equal lengths are checked per batch by bk_tokenize
-  return true;
-}
 
 std::string human_duration(double secs) {  // indicatif::HumanDuration (logger.rs:108-110)
   struct U { double s; const char* one; const char* many; };
@@ -188,9 +106,81 @@ void set_err(const std::string& m, char* err, size_t cap) {
   err[k] = 0;
 }
 
-struct Batch { uint64_t rec0, rec1; };
 
 inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+size_t count_nl(const uint8_t* p, size_t n) {  // (the plain loop vectorises: compare + horizontal add)
+  size_t total = 0;
+  while (n) {
+    const size_t k = std::min<size_t>(n, 1 << 15);
+    unsigned c = 0;
+    for (size_t i = 0; i < k; ++i) c += p[i] == '\n';
+    total += c;
+    p += k;
+    n -= k;
+  }
+  return total;
+}
+
+// one batch on its way through the pipeline, with its pinned buffers
+struct Set {
+  uint8_t* text[2] = {nullptr, nullptr};
+  uint8_t* out[2] = {nullptr, nullptr};
+  size_t tcap[2] = {0, 0}, ocap[2] = {0, 0};
+  size_t len[2] = {0, 0};   // bytes of text of this batch (whole records)
+  uint32_t n = 0;           // records (pairs)
+  size_t batch = 0;         // index in input order
+  bk_result res;
+  std::vector<std::vector<uint8_t>> pieces[2];  // compressed outputs
+  uint64_t woff[2] = {0, 0};  // file offsets, assigned in batch order
+  uint64_t wlen[2] = {0, 0};
+};
+
+template <class T>
+class Queue {  // blocking FIFO; close() lets the consumers drain it and leave, abort() wakes everybody at once
+ public:
+  void push(T v) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      q_.push_back(v);
+    }
+    cv_.notify_one();
+  }
+  bool pop(T* v) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return !q_.empty() || closed_ || aborted_; });
+    if (aborted_ || q_.empty()) return false;
+    *v = q_.front();
+    q_.pop_front();
+    return true;
+  }
+  void close() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      closed_ = true;
+    }
+    cv_.notify_all();
+  }
+  void abort() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      aborted_ = true;
+    }
+    cv_.notify_all();
+  }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<T> q_;
+  bool closed_ = false, aborted_ = false;
+};
+
+struct Output {
+  int fd = -1;
+  bool seekable = true;
+  uint64_t pos = 0;  // next free offset (assigned in batch order)
+};
 
 }  // namespace
 
@@ -205,49 +195,55 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
             "files and patterns.\n");  // run.rs:56-58: message, normal return
     return BK_OK;
   }
-  if (a->compression != 0) {
-    set_err("compressed output (--gz/--bgz/--mgz/--lz4) is not supported by this build", err, errcap);
-    return BK_E_UNSUPPORTED;
+  // a->compression: 0 none, 1 --gz, 2 --bgz, 3 --mgz, 4 --lz4 (src/main.rs:14-19).  CompressionType::select
+  // (fastq.rs:71-79) maps --bgz to Mgzip and --mgz to Bgzf; the swap is kept.
+  bkio::OutFormat fmt = bkio::OutFormat::Plain;
+  switch (a->compression) {
+    case 0: break;
+    case 1: fmt = bkio::OutFormat::Gzip; break;
+    case 2: fmt = bkio::OutFormat::Mgzip; break;
+    case 3: fmt = bkio::OutFormat::Bgzf; break;
+    default:
+      set_err("lz4 output (--lz4) is not supported by this build", err, errcap);
+      return BK_E_UNSUPPORTED;
   }
   std::string e;
   Logger log;
   log.quiet = a->quiet != 0;
-  log.message("Estimating reads count...");  // run.rs:97 / :215
+  log.message("Estimating reads count...");  // run.rs:97 / :215 (the count only feeds the progress bar, which is not drawn)
   const bool dbg = a->verbose != 0;
   const double t_begin = now_s();
+  const int nm = pe ? 2 : 1;
 
-  // the CUDA contexts come up while the host scans the input
+  // the CUDA contexts come up while the host opens its files
   std::thread warm([&] {
     const int nd = bk_device_count();
     const int ng = a->n_gpus > 0 ? std::min(a->n_gpus, nd) : std::min(nd, 1);  // (further devices come up in their workers)
     for (int d = 0; d < ng; ++d) bk_warmup(d);
   });
   struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warm_join{warm};
-  Mapped in1, in2;
-  if (!map_file(a->fq1, &in1, &e)) { set_err(e, err, errcap); return BK_E_IO; }
-  if (pe && !map_file(a->fq2, &in2, &e)) { set_err(e, err, errcap); return BK_E_IO; }
-  for (const Mapped* m : {&in1, &in2}) {
-    if (const char* k = m->p ? compressed_kind(*m) : nullptr) {
-      set_err(std::string(k) + " input is not supported by this build (plain FASTQ only)", err, errcap);
+
+  bkio::Input in[2];
+  if (!in[0].open(a->fq1, &e)) { set_err(e, err, errcap); return BK_E_IO; }
+  if (pe && !in[1].open(a->fq2, &e)) { set_err(e, err, errcap); return BK_E_IO; }
+  for (int m = 0; m < nm; ++m)
+    if (in[m].codec() == bkio::Codec::Lz4) {
+      set_err("lz4 input is not supported by this build (plain or gzip / bgzf / mgzip FASTQ)", err, errcap);
       return BK_E_UNSUPPORTED;
     }
-  }
-  const unsigned host_threads = std::max<unsigned>(1, std::max<unsigned>((unsigned)a->threads, std::thread::hardware_concurrency()));
-  std::vector<uint64_t> st1, st2;
-  if (!record_starts(in1, host_threads, &st1, &e)) { set_err(e, err, errcap); return BK_E_FORMAT; }
-  if (pe && !record_starts(in2, host_threads, &st2, &e)) { set_err(e, err, errcap); return BK_E_FORMAT; }
-  uint64_t nrec = st1.size() - 1;
-  if (pe) nrec = std::min<uint64_t>(nrec, st2.size() - 1);  // run.rs:172-173 zip truncates
-  if (dbg) fprintf(stderr, "[bk_run] map + record starts: %.3f s\n", now_s() - t_begin);
 
-  int fd1 = open_output(a->out_fq1, a->force != 0, &e);  // run.rs:106-111 / :225-229
-  if (fd1 < 0) { set_err(e, err, errcap); return BK_E_IO; }
-  int fd2 = -1;
+  Output outp[2];
+  outp[0].fd = open_output(a->out_fq1, a->force != 0, &e);  // run.rs:106-111 / :225-229
+  if (outp[0].fd < 0) { set_err(e, err, errcap); return BK_E_IO; }
   if (pe) {
-    fd2 = open_output(a->out_fq2, a->force != 0, &e);
-    if (fd2 < 0) { close(fd1); set_err(e, err, errcap); return BK_E_IO; }
+    outp[1].fd = open_output(a->out_fq2, a->force != 0, &e);
+    if (outp[1].fd < 0) { close(outp[0].fd); set_err(e, err, errcap); return BK_E_IO; }
   }
-  auto close_outputs = [&]() { close(fd1); if (fd2 >= 0) close(fd2); };
+  for (int m = 0; m < nm; ++m) {
+    struct stat st;
+    outp[m].seekable = fstat(outp[m].fd, &st) == 0 && S_ISREG(st.st_mode);
+  }
+  auto close_outputs = [&]() { for (int m = 0; m < nm; ++m) close(outp[m].fd); };
 
   log.message("Parsing barcode patterns...");  // run.rs:113 / :231
   bk_program *p1 = nullptr, *p2 = nullptr;
@@ -269,264 +265,383 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   log.message("Extracting barcodes from reads...");  // run.rs:120 / :247
 
   if (warm.joinable()) warm.join();
-  int ndev = bk_device_count();
+  const int ndev = bk_device_count();
   if (ndev <= 0) {
     free_programs(); close_outputs();
     set_err("no CUDA device available; this build has no CPU path", err, errcap);
     return BK_E_CUDA;
   }
-  int ngpu = a->n_gpus > 0 ? std::min(a->n_gpus, ndev) : ndev;
+  // Batch size per mate: -m MiB when given, else 32 MiB: large enough for the kernels and the bus, small enough to
+  // pipeline and to keep the pinned pools (and their allocation time) small.
+  size_t batch_bytes = a->max_memory_mb ? a->max_memory_mb << 20 : (size_t)32 << 20;
+  batch_bytes = std::min<size_t>(std::max<size_t>(batch_bytes, 1 << 20), (size_t)2 << 30);
+  // GPUs: as many as asked for; otherwise one per 2 GiB of plain input per mate (one GPU streams a file faster than
+  // most file systems deliver it, and every further context costs its start-up), one for compressed or piped input.
+  int ngpu = 1;
+  if (a->n_gpus > 0) ngpu = std::min(a->n_gpus, ndev);
+  else if (in[0].codec() == bkio::Codec::Plain && in[0].regular())
+    ngpu = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ndev, in[0].file_size() >> 31));
 
-  // batches: contiguous record ranges, sized by bytes (-m MB per mate when given, else 64 MiB: small enough to pipeline, large enough for the kernel)
-  size_t batch_bytes = a->max_memory_mb ? a->max_memory_mb << 20 : (size_t)64 << 20;
-  batch_bytes = std::min<size_t>(std::max<size_t>(batch_bytes, 1 << 20), (size_t)3 << 30);
-  std::vector<Batch> batches;
-  for (uint64_t r = 0; r < nrec;) {
-    uint64_t lo = r, hi = nrec;  // largest r1 with both mates' bytes <= batch_bytes
-    auto fits = [&](uint64_t r1) {
-      return st1[r1] - st1[r] <= batch_bytes && (!pe || st2[r1] - st2[r] <= batch_bytes) && r1 - r < (1u << 30);
-    };
-    while (lo < hi) {
-      uint64_t mid = lo + (hi - lo + 1) / 2;
-      if (fits(mid)) lo = mid; else hi = mid - 1;
-    }
-    if (lo == r) lo = r + 1;  // a single record larger than the budget still goes through
-    batches.push_back({r, lo});
-    r = lo;
-  }
-  ngpu = std::max(1, std::min<int>(ngpu, (int)std::max<size_t>(batches.size(), 1)));
-  // Unless the caller asked for a number of GPUs: one per 32 batches (2 GiB of text per mate).  The files, not the
-  // device, bound this path (one GPU streams ~9 M pairs/s against 3.2 G on the device), and every further
-  // context costs its start-up and pinned buffers (2 GPUs on a 2 GB input: 2.2 s instead of 1.5 s).
-  if (a->n_gpus <= 0) ngpu = std::max(1, std::min<int>(ngpu, (int)(batches.size() / 32)));
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const unsigned host_threads = std::min(64u, std::max<unsigned>((unsigned)a->threads, hw));
+  bkio::Pool pool(host_threads > 1 ? host_threads - 1 : 0);
 
-  std::atomic<size_t> next_batch{0};
-  std::mutex wmu;
-  std::condition_variable wcv;
-  size_t next_to_write = 0;
   std::atomic<int> status{BK_OK};
   std::string first_error;
   std::mutex emu;
+  Queue<Set*> free_sets, ready, tasks;
   auto fail = [&](int code, const std::string& m) {
     {
       std::lock_guard<std::mutex> g(emu);
       if (status.load() == BK_OK) { first_error = m; status = code; }
     }
-    // The writers test `status` under wmu before they block: taking it here closes the window between
-    // their test and their wait, in which a notification would be lost and the run would hang.
-    { std::lock_guard<std::mutex> lk(wmu); }
-    wcv.notify_all();
+    free_sets.abort(); ready.abort(); tasks.abort();
   };
-  const uint32_t flags = (pe ? BK_FLAG_PAIRED : 0) | (a->skip_trimming ? BK_FLAG_SKIP_TRIM : 0) |
-                         (a->rc_barcodes ? BK_FLAG_RC : 0) | (dbg ? BK_FLAG_VERBOSE : 0) |
-                         (a->ctx_flags & (BK_FLAG_DEVICE_BOTH_MATES | BK_FLAG_HOST_MATE_PINNED));
 
-  // One worker per GPU: stage batch k (all host threads: copy into pinned memory, offsets, record checks)
-  // -> submit k -> wait k-1 -> hand k-1 to the worker's writer thread, so that staging, the device and the
-  // output files all work at the same time.  Three host buffer sets per worker, two device slots (bk_ctx).
-  const unsigned stage_threads = std::max(1u, std::min(host_threads / (unsigned)ngpu, 32u));
+  const int nsets = 3 * ngpu + 2;
+  std::vector<Set> sets((size_t)nsets);
+  for (auto& s : sets) free_sets.push(&s);
+  double t_alloc = 0;
+  std::mutex amu;
+  auto ensure_host = [&](uint8_t** p, size_t* cap, size_t need) {
+    if (*cap >= need) return true;
+    const double t0 = now_s();
+    if (*p) bk_host_free(*p);
+    const size_t want = need + need / 16 + 4096;
+    *p = (uint8_t*)bk_host_alloc(want);
+    *cap = *p ? want : 0;
+    {
+      std::lock_guard<std::mutex> g(amu);
+      t_alloc += now_s() - t0;
+    }
+    return *p != nullptr;
+  };
+
+  // ---- reader ------------------------------------------------------------------------------------------------------
+  double t_read = 0, t_count = 0, t_free_wait = 0;
+  size_t nbatches = 0;
+  uint64_t nrec_total = 0;
+  std::thread reader([&] {
+    std::vector<uint8_t> carry[2];
+    size_t target[2] = {batch_bytes, batch_bytes};
+    constexpr size_t kSlice = 256 << 10;
+    for (size_t bi = 0;; ++bi) {
+      Set* s = nullptr;
+      const double tf = now_s();
+      if (!free_sets.pop(&s)) return;
+      t_free_wait += now_s() - tf;
+      size_t len[2] = {0, 0};
+      for (int m = 0; m < nm; ++m) {
+        const size_t need = std::max(target[m], carry[m].size()) + 64;
+        if (!ensure_host(&s->text[m], &s->tcap[m], std::max(need, batch_bytes + 64))) { fail(BK_E_CAPACITY, "pinned host allocation failed"); return; }
+        if (!carry[m].empty()) memcpy(s->text[m], carry[m].data(), carry[m].size());
+        len[m] = carry[m].size();
+        carry[m].clear();
+      }
+      const double tr = now_s();
+      std::string ferr[2];
+      bool fok[2] = {true, true};
+      auto fill = [&](int m) {
+        const size_t goal = std::min(std::max(target[m], len[m]), s->tcap[m] - 64);
+        while (len[m] < goal && !in[m].eof()) {
+          const ssize_t r = in[m].fill(s->text[m] + len[m], goal - len[m], &pool, &ferr[m]);
+          if (r < 0) { fok[m] = false; return; }
+          len[m] += (size_t)r;
+        }
+      };
+      if (pe) {  // (gzip inputs inflate on one thread each)
+        std::thread t2(fill, 1);
+        fill(0);
+        t2.join();
+      } else {
+        fill(0);
+      }
+      for (int m = 0; m < nm; ++m)
+        if (!fok[m]) { fail(BK_E_IO, ferr[m]); return; }
+      t_read += now_s() - tr;
+      const double tc = now_s();
+      // line ends per slice, both mates on the pool at once
+      std::vector<uint32_t> cnt[2];
+      size_t nsl[2] = {0, 0};
+      for (int m = 0; m < nm; ++m) {
+        if (in[m].eof()) {  // blank lines after the last record are not records (seq_io accepts them)
+          uint8_t* t = s->text[m];
+          size_t& L = len[m];
+          while (L && t[L - 1] == '\n') {
+            if (L == 1 || t[L - 2] == '\n') L -= 1;
+            else if (t[L - 2] == '\r' && (L == 2 || t[L - 3] == '\n')) L -= 2;
+            else break;
+          }
+        }
+        nsl[m] = (len[m] + kSlice - 1) / kSlice;
+        cnt[m].assign(nsl[m] + 1, 0);
+      }
+      pool.parallel_for(nsl[0] + nsl[1], [&](size_t i) {
+        const int m = i < nsl[0] ? 0 : 1;
+        const size_t sl = m ? i - nsl[0] : i;
+        const size_t b = sl * kSlice;
+        cnt[m][sl + 1] = (uint32_t)count_nl(s->text[m] + b, std::min(kSlice, len[m] - b));
+      });
+      uint64_t avail[2] = {UINT64_MAX, UINT64_MAX}, lines[2] = {0, 0}, nl[2] = {0, 0};
+      bool ended = false;
+      for (int m = 0; m < nm; ++m) {
+        for (size_t i = 0; i < nsl[m]; ++i) cnt[m][i + 1] += cnt[m][i];
+        nl[m] = cnt[m][nsl[m]];
+        const bool open_line = len[m] && s->text[m][len[m] - 1] != '\n';
+        lines[m] = nl[m] + (in[m].eof() && open_line ? 1 : 0);  // a last record without EOL is a record (seq_io)
+        avail[m] = lines[m] / 4;
+        if (in[m].eof() && avail[m] == 0) {
+          if (lines[m] != 0) { fail(BK_E_FORMAT, "malformed FASTQ: the input ends inside a record"); return; }
+          ended = true;  // (in paired mode the shorter input ends the run: zip, run.rs:172-173)
+        }
+      }
+      uint64_t n = std::min(avail[0], pe ? avail[1] : avail[0]);
+      n = std::min<uint64_t>(n, 1u << 30);
+      if (ended || n == 0) {
+        if (!ended) { fail(BK_E_CAPACITY, "a record is longer than the batch buffer (raise -m)"); return; }
+        free_sets.push(s);
+        break;
+      }
+      for (int m = 0; m < nm; ++m) {
+        // end of record n = one past line end number 4n (or the end of the text for an unterminated last record)
+        size_t end = len[m];
+        const uint64_t want = 4 * n;
+        if (want <= nl[m]) {
+          size_t sl = (size_t)(std::lower_bound(cnt[m].begin(), cnt[m].end(), (uint32_t)want) - cnt[m].begin());  // first slice prefix >= want
+          // the line end lies in slice sl - 1
+          size_t pos = (sl - 1) * kSlice;
+          uint64_t seen = cnt[m][sl - 1];
+          const uint8_t* t = s->text[m];
+          while (seen < want) {
+            const uint8_t* q = (const uint8_t*)memchr(t + pos, '\n', len[m] - pos);
+            pos = (size_t)(q - t) + 1;
+            ++seen;
+          }
+          end = pos;
+        }
+        if (in[m].eof() && avail[m] == n && lines[m] % 4 != 0) {  // what follows the last whole record is a fragment
+          fail(BK_E_FORMAT, "malformed FASTQ: the input ends inside a record");
+          return;
+        }
+        carry[m].assign(s->text[m] + end, s->text[m] + len[m]);
+        s->len[m] = end;
+      }
+      // next batch: read so that both mates bring about the same number of records
+      if (pe) {
+        const double a0 = (double)s->len[0] / (double)n, a1 = (double)s->len[1] / (double)n;
+        const double nt = std::min((double)batch_bytes / a0, (double)batch_bytes / a1);
+        target[0] = std::min(batch_bytes, (size_t)(nt * a0 * 1.02) + 65536);
+        target[1] = std::min(batch_bytes, (size_t)(nt * a1 * 1.02) + 65536);
+      }
+      t_count += now_s() - tc;
+      s->n = (uint32_t)n;
+      s->batch = bi;
+      ++nbatches;
+      nrec_total += n;
+      ready.push(s);
+    }
+    ready.close();
+  });
+
+  // ---- sequencer + writers -------------------------------------------------------------------------------------------
+  std::mutex qmu;                       // guards pending / turn / positions / outstanding
+  std::condition_variable qcv;
+  std::map<size_t, Set*> pending;       // finished (and compressed) batches that wait for their turn
+  size_t turn = 0;
+  size_t outstanding = 0;               // batches between bk_wait and the end of their write
+  bool workers_done = false;
+  double t_write = 0, t_comp = 0;
+  std::mutex tmu;
+  const bool direct = outp[0].seekable && (!pe || outp[1].seekable);
+  auto write_set = [&](Set* s) -> bool {  // the bytes of one batch at their offsets (or appended, for a pipe)
+    const double t0 = now_s();
+    std::atomic<int> bad{0};
+    for (int m = 0; m < nm; ++m) {
+      if (fmt == bkio::OutFormat::Plain) {
+        const uint64_t n = s->wlen[m];
+        if (!direct) {
+          if (!write_all(outp[m].fd, s->out[m], n)) bad = errno ? errno : EIO;
+          continue;
+        }
+        const size_t slice = 4 << 20, ns = (size_t)((n + slice - 1) / slice);
+        pool.parallel_for(ns, [&](size_t i) {
+          int en = 0;
+          const uint64_t b = (uint64_t)i * slice;
+          if (!bkio::pwrite_all(outp[m].fd, s->out[m] + b, (size_t)std::min<uint64_t>(slice, n - b), s->woff[m] + b, &en)) bad = en;
+        });
+      } else {
+        uint64_t off = s->woff[m];
+        for (auto& pc : s->pieces[m]) {
+          int en = 0;
+          const bool ok = direct ? bkio::pwrite_all(outp[m].fd, pc.data(), pc.size(), off, &en)
+                                 : write_all(outp[m].fd, pc.data(), pc.size());
+          if (!ok) { bad = en ? en : (errno ? errno : EIO); break; }
+          off += pc.size();
+        }
+        s->pieces[m].clear();
+      }
+    }
+    {
+      std::lock_guard<std::mutex> g(tmu);
+      t_write += now_s() - t0;
+    }
+    if (bad.load()) { fail(BK_E_IO, io_error(strerror(bad.load()))); return false; }
+    return true;
+  };
+  // a finished batch joins the line; every batch whose turn has come gets its offsets and goes to the writers
+  auto sequence = [&](Set* s) {
+    std::vector<Set*> go;
+    {
+      std::lock_guard<std::mutex> g(qmu);
+      pending[s->batch] = s;
+      for (auto it = pending.find(turn); it != pending.end(); it = pending.find(turn)) {
+        Set* x = it->second;
+        pending.erase(it);
+        for (int m = 0; m < nm; ++m) {
+          x->woff[m] = outp[m].pos;
+          outp[m].pos += x->wlen[m];
+        }
+        ++turn;
+        if (direct) go.push_back(x);
+        else {  // pipes: in order, here
+          write_set(x);
+          --outstanding;
+          if (workers_done && outstanding == 0) tasks.close();
+          free_sets.push(x);
+        }
+      }
+    }
+    for (Set* x : go) tasks.push(x);
+    qcv.notify_all();
+  };
+  // task kinds share one queue: a set with wlen == UINT64_MAX still has to be compressed
+  auto writer = [&] {
+    Set* s = nullptr;
+    while (tasks.pop(&s)) {
+      if (s->wlen[0] == UINT64_MAX) {
+        const double t0 = now_s();
+        bool ok = true;
+        for (int m = 0; m < nm; ++m) {
+          const uint64_t n = m ? s->res.out2_len : s->res.out1_len;
+          ok = ok && bkio::compress_batch(s->out[m], (size_t)n, fmt, &pool, &s->pieces[m]);
+          uint64_t tot = 0;
+          for (auto& pc : s->pieces[m]) tot += pc.size();
+          s->wlen[m] = tot;
+        }
+        {
+          std::lock_guard<std::mutex> g(tmu);
+          t_comp += now_s() - t0;
+        }
+        if (!ok) { fail(BK_E_IO, "I/O error: deflate failed"); return; }
+        sequence(s);
+        continue;
+      }
+      if (!write_set(s)) return;
+      {
+        std::lock_guard<std::mutex> g(qmu);
+        --outstanding;
+        if (workers_done && outstanding == 0) tasks.close();
+      }
+      free_sets.push(s);
+    }
+  };
+  auto complete = [&](Set* s) {  // called by a worker after bk_wait
+    {
+      std::lock_guard<std::mutex> g(qmu);
+      ++outstanding;
+    }
+    if (fmt == bkio::OutFormat::Plain) {
+      s->wlen[0] = s->res.out1_len;
+      s->wlen[1] = pe ? s->res.out2_len : 0;
+      sequence(s);
+    } else {
+      s->wlen[0] = s->wlen[1] = UINT64_MAX;
+      tasks.push(s);
+    }
+  };
+  const int nwriters = fmt == bkio::OutFormat::Plain ? 2 : std::max(2, ngpu);
+  std::vector<std::thread> wth;
+  for (int i = 0; i < nwriters; ++i) wth.emplace_back(writer);
+
+  // ---- workers: one per GPU ----------------------------------------------------------------------------------------
+  const uint32_t flags = (pe ? BK_FLAG_PAIRED : 0) | (a->skip_trimming ? BK_FLAG_SKIP_TRIM : 0) |
+                         (a->rc_barcodes ? BK_FLAG_RC : 0) | (dbg ? BK_FLAG_VERBOSE : 0) | BK_FLAG_DEVICE_BOTH_MATES;
   auto worker = [&](int dev) {
     char emsg[512];
     int cst = BK_OK;
-    double t_ctx = now_s(), t_stage = 0, t_submit = 0, t_wait = 0, t_write = 0, t_setwait = 0;
+    double t_ctx = now_s(), t_submit = 0, t_wait = 0, t_pop = 0;
     bk_ctx* ctx = bk_ctx_create(dev, p1, p2, flags, &cst, emsg, sizeof emsg);
     if (!ctx) { fail(cst, emsg); return; }
     t_ctx = now_s() - t_ctx;
-    const int nm = pe ? 2 : 1;
-    constexpr int kSets = 3;
-    struct HostSet { uint8_t* text[2] = {nullptr, nullptr}; uint32_t* off[2] = {nullptr, nullptr};
-                     uint8_t* out[2] = {nullptr, nullptr};
-                     size_t tcap[2] = {0, 0}, ocap[2] = {0, 0}, fcap[2] = {0, 0};
-                     size_t batch = SIZE_MAX; bk_result res; bool busy = false; } hs[kSets];
-    std::mutex smu;                 // guards hs[].busy, the writer's queue
-    std::condition_variable scv;
-    std::vector<int> wq;            // sets waiting to be written, in submission order
-    bool wdone = false;
-    double t_alloc = 0;
-    auto ensure_host = [&](void** p, size_t* cap, size_t need) {
-      if (*cap >= need) return true;
+    auto finish = [&](int dslot, Set* s) -> bool {
       const double t0 = now_s();
-      if (*p) bk_host_free(*p);
-      *p = bk_host_alloc(need + need / 8 + 4096);
-      *cap = *p ? need + need / 8 + 4096 : 0;
-      t_alloc += now_s() - t0;
-      return *p != nullptr;
-    };
-    // the BK_E_FORMAT conditions of bk_tokenize for one record [b, e) (its four lines are given by the record starts)
-    auto record_ok = [](const uint8_t* b, const uint8_t* e) {
-      if (e - b < 4 || b[0] != '@') return false;
-      const uint8_t* nl1 = (const uint8_t*)memchr(b, '\n', e - b);
-      if (!nl1 || nl1 + 1 >= e) return false;
-      const uint8_t* nl2 = (const uint8_t*)memchr(nl1 + 1, '\n', e - nl1 - 1);
-      if (!nl2 || nl2 + 1 >= e || nl2[1] != '+') return false;
-      const uint8_t* nl3 = (const uint8_t*)memchr(nl2 + 1, '\n', e - nl2 - 1);
-      if (!nl3) return false;
-      const uint8_t* nl4 = nl3 + 1 < e ? (const uint8_t*)memchr(nl3 + 1, '\n', e - nl3 - 1) : nullptr;
-      if (!nl4) nl4 = e;  // the file's last record may lack its EOL
-      size_t sl = nl2 - (nl1 + 1), ql = nl4 - (nl3 + 1);
-      if (sl && nl2[-1] == '\r') --sl;
-      if (ql && nl4[-1] == '\r') --ql;
-      return sl == ql;
-    };
-    auto stage = [&](int hi, size_t bi, bk_mate_in* in) -> bool {
-      HostSet& h = hs[hi];
-      const Batch& b = batches[bi];
-      const uint32_t n = (uint32_t)(b.rec1 - b.rec0);
-      const Mapped* mp[2] = {&in1, &in2};
-      const std::vector<uint64_t>* stp[2] = {&st1, &st2};
-      for (int m = 0; m < nm; ++m) {
-        const uint64_t t0 = (*stp[m])[b.rec0], t1 = (*stp[m])[b.rec1];
-        if (!ensure_host((void**)&h.text[m], &h.tcap[m], t1 - t0 + 64)) return false;
-        if (!ensure_host((void**)&h.off[m], &h.fcap[m], ((size_t)n + 2) * 4)) return false;
-        if (!ensure_host((void**)&h.out[m], &h.ocap[m], bk_out_bound(ctx, m + 1, n, t1 - t0))) return false;
-      }
-      const unsigned T = n < 20000 ? 1u : stage_threads;
-      std::vector<uint32_t> maxrec((size_t)T * 2, 0);
-      std::atomic<bool> bad{false};
-      auto part = [&](unsigned t) {
-        const uint64_t r0 = b.rec0 + (uint64_t)n * t / T, r1 = b.rec0 + (uint64_t)n * (t + 1) / T;
-        for (int m = 0; m < nm; ++m) {
-          const std::vector<uint64_t>& st = *stp[m];
-          const uint64_t base = st[b.rec0];
-          memcpy(h.text[m] + (st[r0] - base), mp[m]->p + st[r0], st[r1] - st[r0]);
-          uint32_t mr = 0;
-          for (uint64_t r = r0; r < r1; ++r) {
-            h.off[m][r - b.rec0] = (uint32_t)(st[r] - base);
-            const uint64_t len = st[r + 1] - st[r];
-            if (len > mr) mr = (uint32_t)len;
-            if (!record_ok(mp[m]->p + st[r], mp[m]->p + st[r + 1])) bad = true;
-          }
-          if (t + 1 == T) h.off[m][n] = (uint32_t)(st[b.rec1] - base);
-          maxrec[(size_t)t * 2 + m] = mr;
-        }
-      };
-      if (T == 1) part(0);
-      else {
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < T; ++t) th.emplace_back(part, t);
-        part(0);
-        for (auto& x : th) x.join();
-      }
-      if (bad.load()) { fail(BK_E_FORMAT, "malformed FASTQ record"); return false; }
-      for (int m = 0; m < nm; ++m) {
-        uint32_t mr = 1;
-        for (unsigned t = 0; t < T; ++t) mr = std::max(mr, maxrec[(size_t)t * 2 + m]);
-        in[m].text = h.text[m];
-        in[m].rec_off = h.off[m];
-        in[m].text_len = (*stp[m])[b.rec1] - (*stp[m])[b.rec0];
-        in[m].max_rec_bytes = mr;
-        in[m].reserved = 0;
-      }
-      h.batch = bi;
-      return true;
-    };
-    // writer: sets in submission order; the files in batch order across all workers (run.rs:79,194)
-    std::thread writer([&] {
-      for (;;) {
-        int hi;
-        {
-          std::unique_lock<std::mutex> lk(smu);
-          scv.wait(lk, [&] { return !wq.empty() || wdone; });
-          if (wq.empty()) return;
-          hi = wq.front();
-          wq.erase(wq.begin());
-        }
-        HostSet& h = hs[hi];
-        const double tw = now_s();
-        bool ok = true;
-        {
-          std::unique_lock<std::mutex> lk(wmu);
-          wcv.wait(lk, [&] { return next_to_write == h.batch || status.load() != BK_OK; });
-          ok = status.load() == BK_OK;
-        }
-        if (ok) {  // (only the holder of the turn writes: no lock needed while it does)
-          std::thread w2;
-          bool ok2 = true;
-          if (pe) w2 = std::thread([&] { ok2 = write_all(fd2, h.out[1], h.res.out2_len); });
-          ok = write_all(fd1, h.out[0], h.res.out1_len);
-          if (pe) w2.join();
-          ok = ok && ok2;
-          if (!ok) fail(BK_E_IO, io_error(strerror(errno)));
-          {
-            std::lock_guard<std::mutex> lk(wmu);
-            ++next_to_write;
-          }
-          wcv.notify_all();
-        }
-        t_write += now_s() - tw;
-        {
-          std::lock_guard<std::mutex> lk(smu);
-          h.busy = false;
-          h.batch = SIZE_MAX;
-        }
-        scv.notify_all();
-      }
-    });
-    auto finish = [&](int dslot, int hi) -> bool {  // wait for the device, hand the set to the writer
-      HostSet& h = hs[hi];
-      const double tw0 = now_s();
-      int rc = bk_wait(ctx, dslot, h.out[0], h.ocap[0], h.out[1], h.ocap[1], &h.res);
-      t_wait += now_s() - tw0;
+      const int rc = bk_wait(ctx, dslot, s->out[0], s->ocap[0], s->out[1], s->ocap[1], &s->res);
+      t_wait += now_s() - t0;
       if (rc != BK_OK) { fail(rc, bk_last_error(ctx)); return false; }
-      {
-        std::lock_guard<std::mutex> lk(smu);
-        wq.push_back(hi);
-      }
-      scv.notify_all();
+      complete(s);
       return true;
     };
+    Set* prev = nullptr;
+    long k = 0;
     bool ok = true;
-    long k = 0;            // batches this worker has submitted
-    int prev_set = -1;     // set of batch k-1, still on the device
     for (;; ++k) {
-      size_t bi = next_batch.fetch_add(1);
-      if (bi >= batches.size() || status.load() != BK_OK) break;
-      const int hi = (int)(k % kSets);
-      {
-        const double t0 = now_s();
-        std::unique_lock<std::mutex> lk(smu);
-        scv.wait(lk, [&] { return !hs[hi].busy; });
-        hs[hi].busy = true;
-        t_setwait += now_s() - t0;
-      }
-      bk_mate_in in[2];
-      const double ts0 = now_s();
-      if (!(ok = stage(hi, bi, in))) { if (status.load() == BK_OK) fail(BK_E_CAPACITY, "pinned host allocation failed"); break; }
-      const double ts1 = now_s();
-      t_stage += ts1 - ts0;
-      int rc = bk_submit(ctx, (int)(k & 1), (uint32_t)(batches[bi].rec1 - batches[bi].rec0), &in[0], pe ? &in[1] : nullptr);
-      t_submit += now_s() - ts1;
+      Set* s = nullptr;
+      const double t0 = now_s();
+      if (!ready.pop(&s)) break;
+      t_pop += now_s() - t0;
+      for (int m = 0; m < nm && ok; ++m)
+        ok = ensure_host(&s->out[m], &s->ocap[m], std::max<size_t>(bk_out_bound(ctx, m + 1, s->n, s->len[m]), batch_bytes + batch_bytes / 4));
+      if (!ok) { fail(BK_E_CAPACITY, "pinned host allocation failed"); break; }
+      const double t1 = now_s();
+      const int rc = bk_submit_text(ctx, (int)(k & 1), s->n, s->text[0], s->len[0], pe ? s->text[1] : nullptr, pe ? s->len[1] : 0, 0);
+      t_submit += now_s() - t1;
       if (rc != BK_OK) { fail(rc, bk_last_error(ctx)); ok = false; break; }
-      if (prev_set >= 0 && !(ok = finish((int)((k - 1) & 1), prev_set))) { prev_set = -1; break; }
-      prev_set = hi;
+      if (prev && !(ok = finish((int)((k - 1) & 1), prev))) { prev = nullptr; break; }
+      prev = s;
     }
-    if (ok && prev_set >= 0) ok = finish((int)((k - 1) & 1), prev_set);
-    {
-      std::lock_guard<std::mutex> lk(smu);
-      wdone = true;
-    }
-    scv.notify_all();
-    writer.join();
-    for (auto& h : hs)
-      for (int m = 0; m < 2; ++m) {
-        if (h.text[m]) bk_host_free(h.text[m]);
-        if (h.off[m]) bk_host_free(h.off[m]);
-        if (h.out[m]) bk_host_free(h.out[m]);
-      }
+    if (ok && prev && status.load() == BK_OK) finish((int)((k - 1) & 1), prev);
     bk_ctx_destroy(ctx);
-    if (dbg) fprintf(stderr, "[bk_run] gpu %d: context %.3f s, stage %.3f s (%u threads), submit %.3f s, wait %.3f s, "
-                     "writer busy %.3f s, waiting for a free buffer set %.3f s; pinned allocation inside stage %.3f s\n", dev, t_ctx, t_stage,
-                     stage_threads, t_submit, t_wait, t_write, t_setwait, t_alloc);
+    if (dbg) fprintf(stderr, "[bk_run] gpu %d: context %.3f s, waiting for a batch %.3f s, submit %.3f s, wait %.3f s\n", dev,
+                     t_ctx, t_pop, t_submit, t_wait);
   };
-
-  if (!batches.empty()) {
+  {
     std::vector<std::thread> th;
     for (int d = 0; d < ngpu; ++d) th.emplace_back(worker, d);
     for (auto& t : th) t.join();
   }
+  reader.join();
+  {
+    std::lock_guard<std::mutex> g(qmu);
+    workers_done = true;
+    if (outstanding == 0) tasks.close();
+  }
+  for (auto& t : wth) t.join();
+
+  // the formats' closing pieces: BGZF ends with an empty block, and a gzip file holds at least one member
+  if (status.load() == BK_OK && fmt != bkio::OutFormat::Plain) {
+    for (int m = 0; m < nm; ++m) {
+      if (fmt == bkio::OutFormat::Bgzf || outp[m].pos == 0) {
+        std::vector<uint8_t> tail;
+        bkio::gzip_member(nullptr, 0, fmt, &tail);
+        int en = 0;
+        const bool ok = direct ? bkio::pwrite_all(outp[m].fd, tail.data(), tail.size(), outp[m].pos, &en)
+                               : write_all(outp[m].fd, tail.data(), tail.size());
+        if (!ok) fail(BK_E_IO, io_error(strerror(en ? en : errno)));
+        outp[m].pos += tail.size();
+      }
+    }
+  }
+  for (auto& s : sets)
+    for (int m = 0; m < 2; ++m) {
+      if (s.text[m]) bk_host_free(s.text[m]);
+      if (s.out[m]) bk_host_free(s.out[m]);
+    }
   free_programs();
   close_outputs();
-  if (dbg) fprintf(stderr, "[bk_run] total %.3f s, %zu batches\n", now_s() - t_begin, batches.size());
+  if (dbg)
+    fprintf(stderr, "[bk_run] total %.3f s, %zu batches, %llu records, %d GPU(s), %u host threads; reader: waiting for a free buffer set "
+            "%.3f s, read %.3f s, line ends %.3f s; pinned allocation %.3f s; deflate %.3f s; write %.3f s\n", now_s() - t_begin,
+            nbatches, (unsigned long long)nrec_total, ngpu, host_threads, t_free_wait, t_read, t_count, t_alloc, t_comp, t_write);
   if (status.load() != BK_OK) { set_err(first_error, err, errcap); return status.load(); }
   log.final_message();
   return BK_OK;

@@ -31,7 +31,7 @@ for run in range(3):
         except FileNotFoundError: pass
     t0 = time.perf_counter()
     r = subprocess.run([cli, "--quiet", "extract", "-1", d + "/r1.fq", "-2", d + "/r2.fq", "-o", d + "/o1.fq", "-O", d + "/o2.fq",
-                        "-p", p1, "-e", "1"], capture_output=True, text=True)
+                        "-p", p1, "-e", "1"] + (["--verbose"] if os.environ.get("BK_DEBUG") else []) + os.environ.get("BK_CLI_ARGS", "").split(), capture_output=True, text=True)
     dt = time.perf_counter() - t0
     assert r.returncode == 0, r.stderr
     if os.environ.get("BK_DEBUG"):
