@@ -8,9 +8,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <time.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -529,13 +532,59 @@ void bk_ctx_destroy(bk_ctx* ctx) {
 
 const char* bk_last_error(const bk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 
+// Pinned host memory.  Anonymous memory on transparent huge pages, touched and then registered with CUDA, comes up
+// 2-3 times faster than cudaHostAlloc (measured on the B200 hosts: 0.04 s against 0.10 s per 256 MiB, and five times
+// faster to release), because the driver pins 2 MiB pages instead of 4 KiB ones; a file -> file run allocates several
+// hundred MiB of batch buffers before its first batch moves.  cudaHostAlloc is the fallback.
+namespace {
+std::mutex g_host_mu;
+std::map<void*, size_t> g_host_maps;  // registered mappings: base -> length
+}  // namespace
+
 void* bk_host_alloc(size_t bytes) {
+  if (!bytes) bytes = 1;
+  constexpr size_t kHuge = 2u << 20;
+  if (bytes >= 4 * kHuge) {
+    const size_t len = (bytes + kHuge - 1) & ~(kHuge - 1);
+    void* raw = mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (raw != MAP_FAILED) {
+      // keep the 2 MiB-aligned part, give the rest back
+      uint8_t* base = (uint8_t*)(((uintptr_t)raw + kHuge - 1) & ~(uintptr_t)(kHuge - 1));
+      if (base > (uint8_t*)raw) munmap(raw, (size_t)(base - (uint8_t*)raw));
+      uint8_t* end = (uint8_t*)raw + len + kHuge;
+      if (end > base + len) munmap(base + len, (size_t)(end - (base + len)));
+      madvise(base, len, MADV_HUGEPAGE);
+      for (size_t o = 0; o < len; o += 4096) base[o] = 0;  // fault the pages in (huge ones where the kernel gives them)
+      if (cudaHostRegister(base, len, cudaHostRegisterDefault) == cudaSuccess) {
+        std::lock_guard<std::mutex> g(g_host_mu);
+        g_host_maps[base] = len;
+        return base;
+      }
+      cudaGetLastError();
+      munmap(base, len);
+    }
+  }
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
   return p;
 }
 void bk_host_free(void* p) {
-  if (p) cudaFreeHost(p);
+  if (!p) return;
+  size_t len = 0;
+  {
+    std::lock_guard<std::mutex> g(g_host_mu);
+    auto it = g_host_maps.find(p);
+    if (it != g_host_maps.end()) {
+      len = it->second;
+      g_host_maps.erase(it);
+    }
+  }
+  if (len) {
+    cudaHostUnregister(p);
+    munmap(p, len);
+  } else {
+    cudaFreeHost(p);
+  }
 }
 
 int bk_ctx_nslots(const bk_ctx* ctx) { return ctx ? kSlots : 0; }

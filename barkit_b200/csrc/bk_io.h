@@ -144,6 +144,15 @@ class Input {
   }
   Codec codec() const { return codec_; }
   bool regular() const { return regular_; }
+  // plain regular files may be read by the caller itself, in slices and in parallel: pread at position() + k, then advance()
+  bool direct() const { return codec_ == Codec::Plain && regular_; }
+  int fd() const { return fd_; }
+  uint64_t position() const { return pos_; }
+  uint64_t remaining() const { return size_ - pos_; }
+  void advance(uint64_t n) {
+    pos_ += n;
+    if (pos_ >= size_) eof_ = true;
+  }
   uint64_t file_size() const { return size_; }
   bool eof() const { return eof_; }
 

@@ -134,6 +134,7 @@ struct Set {
   std::vector<std::vector<uint8_t>> pieces[2];  // compressed outputs
   uint64_t woff[2] = {0, 0};  // file offsets, assigned in batch order
   uint64_t wlen[2] = {0, 0};
+  std::atomic<int> writes_left{0};
 };
 
 template <class T>
@@ -179,7 +180,7 @@ class Queue {  // blocking FIFO; close() lets the consumers drain it and leave, 
 struct Output {
   int fd = -1;
   bool seekable = true;
-  uint64_t pos = 0;  // next free offset (assigned in batch order)
+  uint64_t pos = 0;    // next free offset (assigned in batch order)
 };
 
 }  // namespace
@@ -265,6 +266,7 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   log.message("Extracting barcodes from reads...");  // run.rs:120 / :247
 
   if (warm.joinable()) warm.join();
+  const double t_warm = now_s() - t_begin;
   const int ndev = bk_device_count();
   if (ndev <= 0) {
     free_programs(); close_outputs();
@@ -290,15 +292,16 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   std::string first_error;
   std::mutex emu;
   Queue<Set*> free_sets, ready, tasks;
+  Queue<Set*> wq[2];                    // per output file, in batch order
   auto fail = [&](int code, const std::string& m) {
     {
       std::lock_guard<std::mutex> g(emu);
       if (status.load() == BK_OK) { first_error = m; status = code; }
     }
-    free_sets.abort(); ready.abort(); tasks.abort();
+    free_sets.abort(); ready.abort(); tasks.abort(); wq[0].abort(); wq[1].abort();
   };
 
-  const int nsets = 3 * ngpu + 2;
+  const int nsets = 2 * ngpu + 3;  // per GPU two on the device; one being read, two on their way out
   std::vector<Set> sets((size_t)nsets);
   for (auto& s : sets) free_sets.push(&s);
   double t_alloc = 0;
@@ -318,13 +321,12 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   };
 
   // ---- reader ------------------------------------------------------------------------------------------------------
-  double t_read = 0, t_count = 0, t_free_wait = 0;
+  double t_read = 0, t_count = 0, t_free_wait = 0, t_first_ready = 0, t_reader_done = 0, t_workers_done = 0;
   size_t nbatches = 0;
   uint64_t nrec_total = 0;
   std::thread reader([&] {
     std::vector<uint8_t> carry[2];
     size_t target[2] = {batch_bytes, batch_bytes};
-    constexpr size_t kSlice = 256 << 10;
     for (size_t bi = 0;; ++bi) {
       Set* s = nullptr;
       const double tf = now_s();
@@ -339,54 +341,95 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
         carry[m].clear();
       }
       const double tr = now_s();
+      // Segments of the batch text: the carried-over front, then the new bytes in 1 MiB pieces.  Plain files are read
+      // piece by piece on the pool, each piece's line ends counted while it is still in the core's cache; other
+      // inputs (gzip, pipes) are filled first, one thread per mate, and counted afterwards.
+      struct Seg { int m; size_t b, e; uint64_t fpos; bool read; uint32_t nl; };
+      std::vector<Seg> segs;
+      constexpr size_t kSeg = 1 << 20;
       std::string ferr[2];
       bool fok[2] = {true, true};
+      auto goal_of = [&](int m) { return std::min(std::max(target[m], len[m]), s->tcap[m] - 64); };
       auto fill = [&](int m) {
-        const size_t goal = std::min(std::max(target[m], len[m]), s->tcap[m] - 64);
+        const size_t goal = goal_of(m);
         while (len[m] < goal && !in[m].eof()) {
-          const ssize_t r = in[m].fill(s->text[m] + len[m], goal - len[m], &pool, &ferr[m]);
+          const ssize_t r = in[m].fill(s->text[m] + len[m], goal - len[m], nullptr, &ferr[m]);
           if (r < 0) { fok[m] = false; return; }
           len[m] += (size_t)r;
         }
       };
-      if (pe) {  // (gzip inputs inflate on one thread each)
+      size_t old_len[2] = {len[0], len[1]};
+      if (pe && !in[0].direct() && !in[1].direct()) {
         std::thread t2(fill, 1);
         fill(0);
         t2.join();
       } else {
-        fill(0);
+        for (int m = 0; m < nm; ++m)
+          if (!in[m].direct()) fill(m);
       }
-      for (int m = 0; m < nm; ++m)
-        if (!fok[m]) { fail(BK_E_IO, ferr[m]); return; }
-      t_read += now_s() - tr;
-      const double tc = now_s();
-      // line ends per slice, both mates on the pool at once
-      std::vector<uint32_t> cnt[2];
-      size_t nsl[2] = {0, 0};
       for (int m = 0; m < nm; ++m) {
-        if (in[m].eof()) {  // blank lines after the last record are not records (seq_io accepts them)
-          uint8_t* t = s->text[m];
-          size_t& L = len[m];
-          while (L && t[L - 1] == '\n') {
-            if (L == 1 || t[L - 2] == '\n') L -= 1;
-            else if (t[L - 2] == '\r' && (L == 2 || t[L - 3] == '\n')) L -= 2;
-            else break;
+        if (!fok[m]) { fail(BK_E_IO, ferr[m]); return; }
+        if (old_len[m]) segs.push_back({m, 0, old_len[m], 0, false, 0});
+        if (in[m].direct()) {
+          const size_t goal = goal_of(m);
+          const size_t n = goal > len[m] ? (size_t)std::min<uint64_t>(goal - len[m], in[m].remaining()) : 0;
+          for (size_t o = 0; o < n; o += kSeg)
+            segs.push_back({m, len[m] + o, len[m] + std::min(n, o + kSeg), in[m].position() + o, true, 0});
+          len[m] += n;
+          in[m].advance(n);
+        } else {
+          for (size_t o = old_len[m]; o < len[m]; o += kSeg) segs.push_back({m, o, std::min(len[m], o + kSeg), 0, false, 0});
+        }
+      }
+      std::atomic<int> rbad{0};
+      pool.parallel_for(segs.size(), [&](size_t i) {
+        Seg& g = segs[i];
+        uint8_t* t = s->text[g.m];
+        if (g.read) {
+          size_t o = g.b;
+          while (o < g.e) {
+            const ssize_t r = pread(in[g.m].fd(), t + o, g.e - o, (off_t)(g.fpos + (o - g.b)));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) { rbad = r < 0 ? errno : EIO; return; }
+            o += (size_t)r;
           }
         }
-        nsl[m] = (len[m] + kSlice - 1) / kSlice;
-        cnt[m].assign(nsl[m] + 1, 0);
-      }
-      pool.parallel_for(nsl[0] + nsl[1], [&](size_t i) {
-        const int m = i < nsl[0] ? 0 : 1;
-        const size_t sl = m ? i - nsl[0] : i;
-        const size_t b = sl * kSlice;
-        cnt[m][sl + 1] = (uint32_t)count_nl(s->text[m] + b, std::min(kSlice, len[m] - b));
+        g.nl = (uint32_t)count_nl(t + g.b, g.e - g.b);
       });
+      if (rbad.load()) { fail(BK_E_IO, io_error(strerror(rbad.load()))); return; }
+      t_read += now_s() - tr;
+      const double tc = now_s();
+      for (int m = 0; m < nm; ++m) {
+        if (!in[m].eof()) continue;
+        // blank lines after the last record are not records (seq_io accepts them): cut them off, recount the tail
+        uint8_t* t = s->text[m];
+        size_t& L = len[m];
+        const size_t L0 = L;
+        while (L && t[L - 1] == '\n') {
+          if (L == 1 || t[L - 2] == '\n') L -= 1;
+          else if (t[L - 2] == '\r' && (L == 2 || t[L - 3] == '\n')) L -= 2;
+          else break;
+        }
+        if (L != L0)
+          for (Seg& g : segs)
+            if (g.m == m && g.e > L) {
+              g.e = L;
+              g.b = std::min(g.b, L);
+              g.nl = (uint32_t)count_nl(t + g.b, g.e - g.b);
+            }
+      }
+      // per mate: segment bounds and running line-end counts
+      std::vector<size_t> sb[2];
+      std::vector<uint64_t> cnt[2];
+      for (int m = 0; m < nm; ++m) { sb[m].push_back(0); cnt[m].push_back(0); }
+      for (const Seg& g : segs) {
+        sb[g.m].push_back(g.e);
+        cnt[g.m].push_back(cnt[g.m].back() + g.nl);
+      }
       uint64_t avail[2] = {UINT64_MAX, UINT64_MAX}, lines[2] = {0, 0}, nl[2] = {0, 0};
       bool ended = false;
       for (int m = 0; m < nm; ++m) {
-        for (size_t i = 0; i < nsl[m]; ++i) cnt[m][i + 1] += cnt[m][i];
-        nl[m] = cnt[m][nsl[m]];
+        nl[m] = cnt[m].back();
         const bool open_line = len[m] && s->text[m][len[m] - 1] != '\n';
         lines[m] = nl[m] + (in[m].eof() && open_line ? 1 : 0);  // a last record without EOL is a record (seq_io)
         avail[m] = lines[m] / 4;
@@ -407,9 +450,9 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
         size_t end = len[m];
         const uint64_t want = 4 * n;
         if (want <= nl[m]) {
-          size_t sl = (size_t)(std::lower_bound(cnt[m].begin(), cnt[m].end(), (uint32_t)want) - cnt[m].begin());  // first slice prefix >= want
-          // the line end lies in slice sl - 1
-          size_t pos = (sl - 1) * kSlice;
+          const size_t sl = (size_t)(std::lower_bound(cnt[m].begin(), cnt[m].end(), want) - cnt[m].begin());  // first running count >= want
+          // the line end lies in segment sl - 1
+          size_t pos = sb[m][sl - 1];
           uint64_t seen = cnt[m][sl - 1];
           const uint8_t* t = s->text[m];
           while (seen < want) {
@@ -436,113 +479,98 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
       t_count += now_s() - tc;
       s->n = (uint32_t)n;
       s->batch = bi;
+      if (!nbatches) t_first_ready = now_s() - t_begin;
       ++nbatches;
       nrec_total += n;
       ready.push(s);
     }
+    t_reader_done = now_s() - t_begin;
     ready.close();
   });
 
   // ---- sequencer + writers -------------------------------------------------------------------------------------------
+  // Finished batches get their file offsets in batch order; each output file then has ONE writer thread that takes
+  // the batches in that order.  (write(2) holds the file's lock for the whole call, so several threads writing one
+  // file get one thread's rate and pay for the hand-overs: tools/fs_peak.py, 4 GB/s per tmpfs file from 1 or 16
+  // threads, 9 GB/s into two files.  A shared mapping filled by all threads reaches 7.5 / 14.6 GB/s in isolation,
+  // but inside this process its page faults and unmaps fight the pinned allocations and the DMA set-up for the
+  // address-space lock: measured slower end to end, and "disk full" becomes SIGBUS.)
   std::mutex qmu;                       // guards pending / turn / positions / outstanding
-  std::condition_variable qcv;
   std::map<size_t, Set*> pending;       // finished (and compressed) batches that wait for their turn
   size_t turn = 0;
-  size_t outstanding = 0;               // batches between bk_wait and the end of their write
+  size_t outstanding = 0;               // batches between bk_wait and the end of their last write
   bool workers_done = false;
-  double t_write = 0, t_comp = 0;
+  double t_write[2] = {0, 0}, t_comp = 0;
   std::mutex tmu;
-  const bool direct = outp[0].seekable && (!pe || outp[1].seekable);
-  auto write_set = [&](Set* s) -> bool {  // the bytes of one batch at their offsets (or appended, for a pipe)
-    const double t0 = now_s();
-    std::atomic<int> bad{0};
-    for (int m = 0; m < nm; ++m) {
+  auto close_if_drained = [&] {         // (qmu held)
+    if (workers_done && outstanding == 0) { tasks.close(); wq[0].close(); wq[1].close(); }
+  };
+  auto sequence = [&](Set* s) {
+    std::lock_guard<std::mutex> g(qmu);
+    pending[s->batch] = s;
+    for (auto it = pending.find(turn); it != pending.end(); it = pending.find(turn)) {
+      Set* x = it->second;
+      pending.erase(it);
+      for (int m = 0; m < nm; ++m) {
+        x->woff[m] = outp[m].pos;
+        outp[m].pos += x->wlen[m];
+      }
+      ++turn;
+      x->writes_left = nm;
+      for (int m = 0; m < nm; ++m) wq[m].push(x);
+    }
+  };
+  auto file_writer = [&](int m) {
+    Set* s = nullptr;
+    while (wq[m].pop(&s)) {
+      const double t0 = now_s();
+      int en = 0;
+      bool ok = true;
+      auto put = [&](const uint8_t* p, size_t n, uint64_t off) {
+        if (outp[m].seekable) return bkio::pwrite_all(outp[m].fd, p, n, off, &en);
+        if (!write_all(outp[m].fd, p, n)) { en = errno ? errno : EIO; return false; }
+        return true;
+      };
       if (fmt == bkio::OutFormat::Plain) {
-        const uint64_t n = s->wlen[m];
-        if (!direct) {
-          if (!write_all(outp[m].fd, s->out[m], n)) bad = errno ? errno : EIO;
-          continue;
-        }
-        const size_t slice = 4 << 20, ns = (size_t)((n + slice - 1) / slice);
-        pool.parallel_for(ns, [&](size_t i) {
-          int en = 0;
-          const uint64_t b = (uint64_t)i * slice;
-          if (!bkio::pwrite_all(outp[m].fd, s->out[m] + b, (size_t)std::min<uint64_t>(slice, n - b), s->woff[m] + b, &en)) bad = en;
-        });
+        ok = put(s->out[m], (size_t)s->wlen[m], s->woff[m]);
       } else {
         uint64_t off = s->woff[m];
         for (auto& pc : s->pieces[m]) {
-          int en = 0;
-          const bool ok = direct ? bkio::pwrite_all(outp[m].fd, pc.data(), pc.size(), off, &en)
-                                 : write_all(outp[m].fd, pc.data(), pc.size());
-          if (!ok) { bad = en ? en : (errno ? errno : EIO); break; }
+          if (!(ok = put(pc.data(), pc.size(), off))) break;
           off += pc.size();
         }
         s->pieces[m].clear();
       }
-    }
-    {
-      std::lock_guard<std::mutex> g(tmu);
-      t_write += now_s() - t0;
-    }
-    if (bad.load()) { fail(BK_E_IO, io_error(strerror(bad.load()))); return false; }
-    return true;
-  };
-  // a finished batch joins the line; every batch whose turn has come gets its offsets and goes to the writers
-  auto sequence = [&](Set* s) {
-    std::vector<Set*> go;
-    {
-      std::lock_guard<std::mutex> g(qmu);
-      pending[s->batch] = s;
-      for (auto it = pending.find(turn); it != pending.end(); it = pending.find(turn)) {
-        Set* x = it->second;
-        pending.erase(it);
-        for (int m = 0; m < nm; ++m) {
-          x->woff[m] = outp[m].pos;
-          outp[m].pos += x->wlen[m];
-        }
-        ++turn;
-        if (direct) go.push_back(x);
-        else {  // pipes: in order, here
-          write_set(x);
+      t_write[m] += now_s() - t0;
+      if (!ok) { fail(BK_E_IO, io_error(strerror(en))); return; }
+      if (s->writes_left.fetch_sub(1) == 1) {
+        {
+          std::lock_guard<std::mutex> g(qmu);
           --outstanding;
-          if (workers_done && outstanding == 0) tasks.close();
-          free_sets.push(x);
+          close_if_drained();
         }
+        free_sets.push(s);
       }
     }
-    for (Set* x : go) tasks.push(x);
-    qcv.notify_all();
   };
-  // task kinds share one queue: a set with wlen == UINT64_MAX still has to be compressed
-  auto writer = [&] {
+  auto compressor = [&] {  // compressed outputs: deflate a batch (all cores), then it joins the line
     Set* s = nullptr;
     while (tasks.pop(&s)) {
-      if (s->wlen[0] == UINT64_MAX) {
-        const double t0 = now_s();
-        bool ok = true;
-        for (int m = 0; m < nm; ++m) {
-          const uint64_t n = m ? s->res.out2_len : s->res.out1_len;
-          ok = ok && bkio::compress_batch(s->out[m], (size_t)n, fmt, &pool, &s->pieces[m]);
-          uint64_t tot = 0;
-          for (auto& pc : s->pieces[m]) tot += pc.size();
-          s->wlen[m] = tot;
-        }
-        {
-          std::lock_guard<std::mutex> g(tmu);
-          t_comp += now_s() - t0;
-        }
-        if (!ok) { fail(BK_E_IO, "I/O error: deflate failed"); return; }
-        sequence(s);
-        continue;
+      const double t0 = now_s();
+      bool ok = true;
+      for (int m = 0; m < nm; ++m) {
+        const uint64_t n = m ? s->res.out2_len : s->res.out1_len;
+        ok = ok && bkio::compress_batch(s->out[m], (size_t)n, fmt, &pool, &s->pieces[m]);
+        uint64_t tot = 0;
+        for (auto& pc : s->pieces[m]) tot += pc.size();
+        s->wlen[m] = tot;
       }
-      if (!write_set(s)) return;
       {
-        std::lock_guard<std::mutex> g(qmu);
-        --outstanding;
-        if (workers_done && outstanding == 0) tasks.close();
+        std::lock_guard<std::mutex> g(tmu);
+        t_comp += now_s() - t0;
       }
-      free_sets.push(s);
+      if (!ok) { fail(BK_E_IO, "I/O error: deflate failed"); return; }
+      sequence(s);
     }
   };
   auto complete = [&](Set* s) {  // called by a worker after bk_wait
@@ -555,13 +583,13 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
       s->wlen[1] = pe ? s->res.out2_len : 0;
       sequence(s);
     } else {
-      s->wlen[0] = s->wlen[1] = UINT64_MAX;
       tasks.push(s);
     }
   };
-  const int nwriters = fmt == bkio::OutFormat::Plain ? 2 : std::max(2, ngpu);
   std::vector<std::thread> wth;
-  for (int i = 0; i < nwriters; ++i) wth.emplace_back(writer);
+  for (int m = 0; m < nm; ++m) wth.emplace_back(file_writer, m);
+  if (fmt != bkio::OutFormat::Plain)
+    for (int i = 0; i < std::max(2, ngpu); ++i) wth.emplace_back(compressor);
 
   // ---- workers: one per GPU ----------------------------------------------------------------------------------------
   const uint32_t flags = (pe ? BK_FLAG_PAIRED : 0) | (a->skip_trimming ? BK_FLAG_SKIP_TRIM : 0) |
@@ -610,12 +638,14 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
     for (auto& t : th) t.join();
   }
   reader.join();
+  t_workers_done = now_s() - t_begin;
   {
     std::lock_guard<std::mutex> g(qmu);
     workers_done = true;
-    if (outstanding == 0) tasks.close();
+    close_if_drained();
   }
   for (auto& t : wth) t.join();
+  const double t_writers_done = now_s() - t_begin;
 
   // the formats' closing pieces: BGZF ends with an empty block, and a gzip file holds at least one member
   if (status.load() == BK_OK && fmt != bkio::OutFormat::Plain) {
@@ -624,8 +654,8 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
         std::vector<uint8_t> tail;
         bkio::gzip_member(nullptr, 0, fmt, &tail);
         int en = 0;
-        const bool ok = direct ? bkio::pwrite_all(outp[m].fd, tail.data(), tail.size(), outp[m].pos, &en)
-                               : write_all(outp[m].fd, tail.data(), tail.size());
+        const bool ok = outp[m].seekable ? bkio::pwrite_all(outp[m].fd, tail.data(), tail.size(), outp[m].pos, &en)
+                                         : write_all(outp[m].fd, tail.data(), tail.size());
         if (!ok) fail(BK_E_IO, io_error(strerror(en ? en : errno)));
         outp[m].pos += tail.size();
       }
@@ -639,9 +669,12 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   free_programs();
   close_outputs();
   if (dbg)
+    fprintf(stderr, "[bk_run] timeline: CUDA up %.3f s, first batch read %.3f s, input read %.3f s, device done %.3f s, "
+            "outputs written %.3f s\n", t_warm, t_first_ready, t_reader_done, t_workers_done, t_writers_done);
+  if (dbg)
     fprintf(stderr, "[bk_run] total %.3f s, %zu batches, %llu records, %d GPU(s), %u host threads; reader: waiting for a free buffer set "
-            "%.3f s, read %.3f s, line ends %.3f s; pinned allocation %.3f s; deflate %.3f s; write %.3f s\n", now_s() - t_begin,
-            nbatches, (unsigned long long)nrec_total, ngpu, host_threads, t_free_wait, t_read, t_count, t_alloc, t_comp, t_write);
+            "%.3f s, read %.3f s, line ends %.3f s; pinned allocation %.3f s; deflate %.3f s; write %.3f + %.3f s\n", now_s() - t_begin,
+            nbatches, (unsigned long long)nrec_total, ngpu, host_threads, t_free_wait, t_read, t_count, t_alloc, t_comp, t_write[0], t_write[1]);
   if (status.load() != BK_OK) { set_err(first_error, err, errcap); return status.load(); }
   log.final_message();
   return BK_OK;
