@@ -68,6 +68,13 @@ __device__ __forceinline__ uint4 realign16(const uint4 x, const uint4 y, uint32_
                     __funnelshift_r(b3, b4, bits));
 }
 
+// CAREFUL = false, the default: every kept record is taken to be in the writer's own framing, so its size is e - b and
+// nothing of the text is touched before the copy itself reads it -- framing probes in front of the look-back pulled
+// sectors into L2 that the copy, 10-20 us later and behind ~100 MB of other tiles' traffic, had to fetch from DRAM
+// again (ncu: 4.06 GB read for 3.0 GB of kept text).  The probes run AFTER the copy, on lines the warp has just
+// read; a record that fails them raises bit 2 of `error`, and the host runs the batch's compaction again with
+// CAREFUL = true (sizes from the parsed records, foreign framing re-framed), and keeps doing so for that context.
+template <bool CAREFUL>
 __global__ void __launch_bounds__(kCompactThreads, 6) compact_kernel(const __grid_constant__ CompactParams P) {
   __shared__ uint32_t s_warp[kCompactThreads / 32];
   __shared__ uint32_t s_tile;
@@ -103,7 +110,14 @@ __global__ void __launch_bounds__(kCompactThreads, 6) compact_kernel(const __gri
     const uint32_t kt = (r0 + t) / P.kmask_recs, kb = (r0 + t) - kt * P.kmask_recs;
     const unsigned long long km = ld_relaxed_u64(P.kmask + kt);  // (complete: warp 0 saw it)
     kept = (km >> kb) & 1ull;
-    if (kept && !(P.hlen && parse_probe_g(text, b, e, hl, rv))) rv = parse_record_g(text, b, e);
+    if (CAREFUL) {
+      if (kept && !(P.hlen && parse_probe_g(text, b, e, hl, rv))) rv = parse_record_g(text, b, e);
+    } else {
+      rv.beg = b;
+      rv.end = e;
+      rv.fast = 1;
+      rv.head_len = hl;  // (the guess, for the check behind the copy)
+    }
   }
   const bool verb = kept && rv.fast;  // goes out verbatim
   const uint32_t size = !kept ? 0u : verb ? rv.end - rv.beg : 1u + rv.head_len + 1u + rv.seq_len + 3u + rv.qual_len + 1u;
@@ -165,25 +179,31 @@ __global__ void __launch_bounds__(kCompactThreads, 6) compact_kernel(const __gri
     const uintptr_t S0 = reinterpret_cast<uintptr_t>(sp) + (D0 - A);  // source of the first whole chunk
     const uint32_t sh = (uint32_t)(S0 & 15u);
     const uint4* const sa = reinterpret_cast<const uint4*>(S0 & ~uintptr_t(15));
-    uintptr_t D = D0 + 16u * (uint32_t)lane;
+    // One turn = kCompactUnroll x 512 destination bytes.  Every source chunk is loaded exactly once: a lane's second
+    // chunk is its neighbour's first and comes over by shuffle (lane 31's is lane 0's of the next 512 bytes, which
+    // lane 0 loads as one extra chunk per turn).  Loading both chunks per lane doubled the requests to L2, and a fifth
+    // of the doubles went all the way to DRAM (ncu: 3.8 GB read for 3.0 GB of kept text).
 #pragma unroll 1
-    for (; D + 512u * (kCompactUnroll - 1) < D1; D += 512u * kCompactUnroll) {  // all loads of a turn in flight together
-      const size_t c = (D - D0) >> 4;
-      uint4 x[kCompactUnroll], y[kCompactUnroll];
+    for (uintptr_t Dw = D0; Dw < D1; Dw += 512u * kCompactUnroll) {
+      uint4 x[kCompactUnroll + 1];
 #pragma unroll
-      for (int u = 0; u < kCompactUnroll; ++u) {
-        x[u] = __ldg(sa + c + 32 * u);
-        y[u] = sh ? __ldg(sa + c + 32 * u + 1) : x[u];
+      for (int u = 0; u <= kCompactUnroll; ++u) {
+        const uintptr_t Au = Dw + 512u * u + 16u * (uint32_t)lane;
+        const bool ld = (u < kCompactUnroll || lane == 0) && Au < D1 + 16u;  // (one chunk past the last: its low bytes end the run)
+        x[u] = ld ? __ldg(sa + ((Au - D0) >> 4)) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < kCompactUnroll; ++u) *reinterpret_cast<uint4*>(D + 512u * u) = realign16(x[u], y[u], sh);
-    }
-#pragma unroll 1
-    for (; D < D1; D += 512u) {
-      const size_t c = (D - D0) >> 4;
-      const uint4 x = __ldg(sa + c);
-      const uint4 y = sh ? __ldg(sa + c + 1) : x;
-      *reinterpret_cast<uint4*>(D) = realign16(x, y, sh);
+      for (int u = 0; u < kCompactUnroll; ++u) {
+        const uint4 v = lane == 0 ? x[u + 1] : x[u];
+        const int from = (lane + 1) & 31;
+        uint4 y;
+        y.x = __shfl_sync(0xffffffffu, v.x, from);
+        y.y = __shfl_sync(0xffffffffu, v.y, from);
+        y.z = __shfl_sync(0xffffffffu, v.z, from);
+        y.w = __shfl_sync(0xffffffffu, v.w, from);
+        const uintptr_t Au = Dw + 512u * u + 16u * (uint32_t)lane;
+        if (Au < D1) *reinterpret_cast<uint4*>(Au) = realign16(x[u], y, sh);
+      }
     }
     uint32_t pad = (uint32_t)((16u - (A & 15u)) & 15u);
     pad = pad < n ? pad : n;
@@ -191,6 +211,11 @@ __global__ void __launch_bounds__(kCompactThreads, 6) compact_kernel(const __gri
     const uint32_t tlo = (int32_t)tl > (int32_t)pad ? tl : pad;
     const uint32_t j = lane < 16 ? (uint32_t)lane : tlo + ((uint32_t)lane - 16u);
     if (lane < 16 ? j < pad : j < n) dp[j] = (uint8_t)__ldg(sp + j);
+  }
+  if (!CAREFUL && kept) {  // the framing that the sizes assumed (the lines are in L1 / L2 now)
+    RecView chk;
+    if (!(P.hlen && parse_probe_g(text, rv.beg, rv.end, rv.head_len, chk)) && !parse_record_g(text, rv.beg, rv.end).fast)
+      atomicOr(&P.result->error, 4u);
   }
 }
 

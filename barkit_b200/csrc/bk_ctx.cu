@@ -63,6 +63,8 @@ struct Slot {
   uint64_t h2d_bytes = 0;        // of the batch in flight
   // two-kernel form of a paired launch with one pattern (enqueue_split): hand-over and the compaction's look-back state
   DevBuf split_match, split_hlen, split_scratch;
+  bk::CompactParams cpar;   // the compaction in flight, should it have to run again (compact_redo)
+  bool cpar_valid = false;
   // raw-text batches (bk_submit_text): record offsets are made on the device
   bool raw = false;
   DevBuf tok[2];                      // per mate: TokResult | ticket | look-back descriptors
@@ -92,6 +94,7 @@ struct bk_ctx {
   bk_ctx* solo = nullptr;
   int host_threads = 1;
   uint32_t maxrec_seen[2] = {0, 0};  // longest record of earlier raw-text batches, per mate (bk_submit_text)
+  bool compact_careful = false;      // a batch's pattern-less mate was not in the writer's framing: size from the text first
   // The host copy is worth it while it takes less time than the bus would need for the same mate.
   // Both are measured on every large pass-through batch; when the host side is the slower one twice in
   // a row (few or slow host cores, several GPUs sharing the host's memory bandwidth) the context
@@ -282,8 +285,11 @@ int enqueue_split(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const b
   // through the keep masks -- was built and measured: 3.66 ms against 3.11 ms per 10 M pairs of C3.  The few CTAs of
   // this kernel that fit next to the extract kernel's have too few bytes in flight to keep up, and what they do add
   // lengthens the extract kernel's memory round trips, which is what bounds it.  DESIGN.md section 4c.)
-  bk::compact_kernel<<<ntiles, bk::kCompactThreads, 0, stream>>>(C);
+  if (ctx->compact_careful) bk::compact_kernel<true><<<ntiles, bk::kCompactThreads, 0, stream>>>(C);
+  else bk::compact_kernel<false><<<ntiles, bk::kCompactThreads, 0, stream>>>(C);
   CK(cudaGetLastError());
+  s->cpar = C;
+  s->cpar_valid = true;
   if (launches) *launches += 1;
   return BK_OK;
 }
@@ -370,6 +376,21 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     CK(cudaGetLastError());
     if (launches) *launches += 1;
   }
+  return BK_OK;
+}
+
+// After the stream has been synchronised: the optimistic compaction met a record in foreign framing (bit 2) -- run
+// that compaction again with sizes taken from the text, and stay careful for this context's later batches.
+int compact_redo(bk_ctx* ctx, Slot& s) {
+  if (!(s.h_res->error & 4u) || !s.cpar_valid) return BK_OK;
+  ctx->compact_careful = true;
+  const bk::CompactParams& C = s.cpar;
+  CK(cudaMemsetAsync(s.split_scratch.p, 0, scratch_bytes(C.ntiles), s.stream));
+  CK(cudaMemsetAsync(&C.result->error, 0, sizeof(unsigned int), s.stream));
+  bk::compact_kernel<true><<<C.ntiles, bk::kCompactThreads, 0, s.stream>>>(C);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(s.h_res, C.result, sizeof(bk::DevResult), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   return BK_OK;
 }
 
@@ -816,6 +837,10 @@ int bk_wait(bk_ctx* ctx, int slot, uint8_t* out1, uint64_t cap1, uint8_t* out2, 
       CK(cudaStreamSynchronize(s.stream));
     }
   }
+  {
+    const int rcc = compact_redo(ctx, s);
+    if (rcc != BK_OK) return rcc;
+  }
   bk::DevResult r = *s.h_res;
   int rc = check_dev_result(ctx, r);
   if (rc != BK_OK) return rc;
@@ -932,6 +957,10 @@ int bk_extract_device(bk_ctx* ctx, uint32_t n, const bk_mate_in* d_in1, const bk
   CK(cudaStreamSynchronize(s.stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+  {
+    const int rcc = compact_redo(ctx, s);
+    if (rcc != BK_OK) return rcc;
+  }
   bk::DevResult r = *s.h_res;
   fill_result(res, r, n, ms / iters, launches);
   return check_dev_result(ctx, r);

@@ -628,9 +628,10 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
       prev = s;
     }
     if (ok && prev && status.load() == BK_OK) finish((int)((k - 1) & 1), prev);
+    const double td = now_s();
     bk_ctx_destroy(ctx);
-    if (dbg) fprintf(stderr, "[bk_run] gpu %d: context %.3f s, waiting for a batch %.3f s, submit %.3f s, wait %.3f s\n", dev,
-                     t_ctx, t_pop, t_submit, t_wait);
+    if (dbg) fprintf(stderr, "[bk_run] gpu %d: context %.3f s, waiting for a batch %.3f s, submit %.3f s, wait %.3f s, context released in %.3f s\n", dev,
+                     t_ctx, t_pop, t_submit, t_wait, now_s() - td);
   };
   {
     std::vector<std::thread> th;
@@ -661,16 +662,18 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
       }
     }
   }
+  const double t_free0 = now_s();
   for (auto& s : sets)
     for (int m = 0; m < 2; ++m) {
       if (s.text[m]) bk_host_free(s.text[m]);
       if (s.out[m]) bk_host_free(s.out[m]);
     }
+  const double t_free = now_s() - t_free0;
   free_programs();
   close_outputs();
   if (dbg)
     fprintf(stderr, "[bk_run] timeline: CUDA up %.3f s, first batch read %.3f s, input read %.3f s, device done %.3f s, "
-            "outputs written %.3f s\n", t_warm, t_first_ready, t_reader_done, t_workers_done, t_writers_done);
+            "outputs written %.3f s, pinned buffers released in %.3f s\n", t_warm, t_first_ready, t_reader_done, t_workers_done, t_writers_done, t_free);
   if (dbg)
     fprintf(stderr, "[bk_run] total %.3f s, %zu batches, %llu records, %d GPU(s), %u host threads; reader: waiting for a free buffer set "
             "%.3f s, read %.3f s, line ends %.3f s; pinned allocation %.3f s; deflate %.3f s; write %.3f + %.3f s\n", now_s() - t_begin,

@@ -278,8 +278,11 @@ def free_batch(ctx, mates):
 
 
 def kernel_name(paired, one_pattern, general):
-    if paired and one_pattern and not general:
-        return "bk::extract_kernel<PAIRED, GENERAL=false, VAR=false, BYP=true>"
+    if paired and one_pattern:
+        # two kernels per step (bk_compact.cuh): the single-end extract kernel on the pattern's mate, then the ordered
+        # compaction of the other mate; timed together
+        return ("bk::extract_kernel<PAIRED=false, GENERAL=%s> on the pattern's mate + bk::compact_kernel on the other"
+                % ("true" if general else "false"))
     return "bk::extract_kernel<PAIRED=%s, GENERAL=%s>" % ("true" if paired else "false", "true" if general else "false")
 
 
@@ -373,12 +376,13 @@ def file_e2e(_lib, ctx, cfg, pairs, world):
         crcs = {}
         for g in sorted({1, world}):
             best = None
-            for rep in range(2):
+            for rep in range(3):
                 for f in ("o1.fq", "o2.fq"):
                     try:
                         os.remove(os.path.join(d, f))
                     except FileNotFoundError:
                         pass
+                time.sleep(1.0)   # (the previous run's process is still being torn down by the driver)
                 t0 = time.perf_counter()
                 r = subprocess.run([CLI, "--quiet", "extract", "-1", d + "/r1.fq", "-2", d + "/r2.fq", "-o", d + "/o1.fq",
                                     "-O", d + "/o2.fq", "-p", PATTERN1, "-e", str(MAX_ERROR), "--gpus", str(g)],
@@ -390,6 +394,28 @@ def file_e2e(_lib, ctx, cfg, pairs, world):
             crcs[g] = (crc_file(d + "/o1.fq"), crc_file(d + "/o2.fq"))
             res["gpus_%d" % g] = {"wall_s": best, "pairs_per_s": pairs / best}
         res["bytes_out"] = os.path.getsize(d + "/o1.fq") + os.path.getsize(d + "/o2.fq")
+        # what the file system itself takes: two new files written side by side, one thread each (write(2) holds the
+        # file's lock, more threads per file add nothing: tools/fs_peak.py)
+        try:
+            from concurrent.futures import ThreadPoolExecutor
+            blk = np.full(8 << 20, 65, np.uint8)
+            per_file = min(res["bytes_out"] // 2, 2 << 30)
+
+            def wr(i):
+                fd = os.open(os.path.join(d, "fs%d" % i), os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+                for o in range(0, per_file, len(blk)):
+                    os.pwrite(fd, blk, o)
+                os.close(fd)
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(2) as ex:
+                list(ex.map(wr, range(2)))
+            dt = time.perf_counter() - t0
+            res["fs_write_gbs_two_files"] = 2 * per_file / dt / 1e9
+            res["fs_bound_pairs_per_s"] = pairs / (res["bytes_out"] / (2 * per_file / dt))
+            for i in range(2):
+                os.remove(os.path.join(d, "fs%d" % i))
+        except Exception as e:   # noqa: BLE001
+            res["fs_write_gbs_two_files"] = "failed: %s" % e
         res["gpus"] = world
         res["pairs_per_s"] = res["gpus_%d" % world]["pairs_per_s"]
         res["crc_equal_to_1gpu"] = (crcs[world] == crcs[1]) if world > 1 else None
@@ -424,25 +450,33 @@ def measure_traffic(pairs):
     fd, path = tempfile.mkstemp(suffix=".csv")
     os.close(fd)
     try:
-        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
-               "regex:extract_kernel", "-s", "1", "-c", "1", "--csv", "--log-file", path, sys.executable,
-               os.path.abspath(__file__), "--steps", "1", "--warmup", "1", "--pairs", str(pairs), "--child"]
+        # the second step's two launches (extract on R1, compaction of R2), serialised by ncu
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control",
+               "none", "-k", "regex:extract_kernel|compact_kernel", "-s", "2", "-c", "2", "--csv", "--log-file", path,
+               sys.executable, os.path.abspath(__file__), "--steps", "1", "--warmup", "1", "--pairs", str(pairs), "--child"]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
         tot = 0.0
         seen = 0
+        shares = {}
         import csv
         for row in csv.reader(open(path)):
-            if len(row) > 3 and row[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if len(row) > 5 and row[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
                 v = float(row[-1].replace(",", ""))
                 unit = row[-2].lower()
+                kname = "compact_kernel" if "compact_kernel" in ",".join(row) else "extract_kernel"
+                if row[-3] == "gpu__time_duration.sum":
+                    v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit.replace("second", "s").replace("nsecond", "ns"), 1e-6)
+                    shares.setdefault(kname, {})["ms_under_ncu"] = v
+                    continue
                 v *= {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(unit, 1)
+                shares.setdefault(kname, {})["dram_bytes"] = shares.get(kname, {}).get("dram_bytes", 0.0) + v
                 tot += v
                 seen += 1
-        if seen == 2:
-            return tot / pairs, "ncu capture of this run's build on this box (child process, %d pairs)" % pairs
-        return None, "ncu produced no counters (rc %d): %s" % (r.returncode, (r.stderr or r.stdout).strip()[-160:])
+        if seen == 4:
+            return tot / pairs, "ncu capture of this run's build on this box (child process, %d pairs; both kernels of a step)" % pairs, shares
+        return None, "ncu produced no counters (rc %d): %s" % (r.returncode, (r.stderr or r.stdout).strip()[-160:]), None
     except Exception as e:   # noqa: BLE001
-        return None, "ncu failed: %s" % e
+        return None, "ncu failed: %s" % e, None
     finally:
         try:
             os.unlink(path)
@@ -459,7 +493,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=10_000_000, help="read pairs per step (device-resident)")
     ap.add_argument("--e2e-pairs", type=int, default=2_000_000, help="read pairs per e2e step (host buffers)")
     ap.add_argument("--config-units", type=int, default=10_000_000, help="units per launch of the other configs")
-    ap.add_argument("--file-pairs", type=int, default=4_000_000, help="read pairs of the file -> file leg")
+    ap.add_argument("--file-pairs", type=int, default=10_000_000, help="read pairs of the file -> file leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
@@ -702,10 +736,10 @@ def main():
                 time.sleep(0.05)
 
     if rank == 0:
-        traffic, traffic_src = None, None
+        traffic, traffic_src, shares = None, None, None
         if world == 1 and not args.no_traffic:
             tp = min(P, 2_000_000)
-            per_pair, traffic_src = measure_traffic(tp)
+            per_pair, traffic_src, shares = measure_traffic(tp)
             if per_pair is not None:
                 traffic = per_pair * P
         if traffic is None:
@@ -730,7 +764,8 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_step": alg_bytes / args.steps,
-                         "kernel": kernel_name(True, True, False) + " (1 launch per step)"},
+                         "kernel": kernel_name(True, True, False) + " (2 launches per step, timed together)",
+                         "kernel_shares": shares},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "configs": configs,
