@@ -153,11 +153,15 @@ struct TileMeta {  // hand-over between the roles, one per (mate, stage); SoA so
   unsigned long long gout;  // global output offset of the tile on this stream (scan)
 };
 
-constexpr int kFrontPairs = 2;  // front warps per mate: warp p takes the ring rounds k with k % 2 == p
+#ifndef BK_SE_FRONTS
+#define BK_SE_FRONTS 2
+#endif
+// front warps per mate: warp p takes the ring rounds k with k % front_pairs == p
+__host__ __device__ constexpr int front_pairs(bool paired) { return paired ? 2 : BK_SE_FRONTS; }
 // A ring slot's barriers must always meet the same scan warp and front pair.  With an odd ring depth
 // round k and round k + kStages share their barrier ids but belong to different scan warps, and the
 // one running ahead completes the other's barrier generation (observed: a 3-deep ring hangs).
-constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + kBackWarps) + kScanWarps + 1; }
+__host__ __device__ constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (front_pairs(paired) + kBackWarps) + kScanWarps + 1; }
 
 // GENERAL = false: every pattern is anchored and there is no reverse-complement retry -- the common
 // case, compiled without the search code, because every kilobyte of this kernel competes for the
@@ -168,6 +172,7 @@ constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (kFrontPairs + 
 template <bool PAIRED, bool GENERAL, bool VAR = false, int ST = kStages>
 __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extract_kernel(const __grid_constant__ KParams P) {
   static_assert(!VAR || GENERAL, "variants are matched by the general kernel");
+  constexpr int kFrontPairs = PAIRED ? 2 : BK_SE_FRONTS;
   static_assert(ST % kScanWarps == 0 && ST % kFrontPairs == 0 && 4 + 2 * ST + (PAIRED ? 1 : 0) <= 16, "ring depth: a multiple of the scan / front warp counts, and 16 named barriers");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
@@ -255,18 +260,18 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
       tile = __shfl_sync(0xffffffffu, tile, 0);
       if (tile >= P.ntiles) {
-        // two end markers in consecutive slots: one per scan warp (they take alternate rounds); the
-        // first one also stops the back warps
-        const uint32_t s2 = (k + 1) % ST, ph2 = ((k + 1) / ST) & 1u;
-#pragma unroll
-        for (int mm = 0; mm < NM; ++mm) mbar_wait(&bar_empty[mm][s2], ph2 ^ 1u);
-        if (lane == 0)
-          for (int mm = 0; mm < NM; ++mm) {
-            meta[mm][s].tile = kEndTile;
-            mbar_arrive(&bar_full[mm][s]);
-            meta[mm][s2].tile = kEndTile2;
-            mbar_arrive(&bar_full[mm][s2]);
-          }
+        // end markers in consecutive slots, one per front warp of a mate (>= one per scan warp: both take the ring
+        // rounds in turn); the first one also stops the back warps
+        for (uint32_t j = 0; j < (uint32_t)kFrontPairs; ++j) {
+          const uint32_t sj = (k + j) % ST, phj = ((k + j) / ST) & 1u;
+          if (j)
+            for (int mm = 0; mm < NM; ++mm) mbar_wait(&bar_empty[mm][sj], phj ^ 1u);
+          if (lane == 0)
+            for (int mm = 0; mm < NM; ++mm) {
+              meta[mm][sj].tile = j ? kEndTile2 : kEndTile;
+              mbar_arrive(&bar_full[mm][sj]);
+            }
+        }
         break;
       }
 #ifdef BK_PROFILE_PHASES
