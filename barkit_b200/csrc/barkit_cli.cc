@@ -176,7 +176,7 @@ int main(int argc, char** argv) {
   ra.skip_trimming = skip;
   ra.max_error = max_error;
   // src/main.rs:14-19: which flag was given; bk_run applies CompressionType::select (fastq.rs:71-79, with its
-  // bgz/mgz swap) and refuses lz4
+  // bgz/mgz swap)
   ra.compression = gz ? 1 : bgz ? 2 : mgz ? 3 : lz4 ? 4 : 0;
   ra.quiet = quiet;
   ra.force = force;

@@ -19,6 +19,8 @@
 #include <thread>
 #include <vector>
 
+#include "bk_lz4.h"
+
 namespace bkio {
 
 // ---- thread pool: parallel_for with the caller taking part --------------------------------------------------------
@@ -160,6 +162,11 @@ class Input {
   ssize_t fill(uint8_t* dst, size_t cap, Pool* pool, std::string* err) {
     if (eof_ || cap == 0) return 0;
     if (codec_ == Codec::Plain) return fill_plain(dst, cap, pool, err);
+    if (codec_ == Codec::Lz4) {  // lz4::Decoder (fastq.rs:116)
+      const long r = lz4_.read(dst, cap, [&](uint8_t* b, size_t n) { return (long)raw_read(b, n, err); }, err);
+      if (r >= 0 && (size_t)r < cap) eof_ = true;
+      return (ssize_t)r;
+    }
     return fill_gzip(dst, cap, err);
   }
 
@@ -255,13 +262,14 @@ class Input {
   z_stream zs_;
   bool zinit_ = false, in_member_ = false;
   std::vector<uint8_t> zbuf_;
+  bklz4::Decoder lz4_;
 };
 
 // ---- outputs -----------------------------------------------------------------------------------------------------
 
 // What --gz / --bgz / --mgz select (fastq.rs:71-79; --bgz gives Mgzip and --mgz gives Bgzf there, SURVEY F15, and so
 // they do here: bk_run maps the flags).
-enum class OutFormat { Plain = 0, Gzip = 1, Bgzf = 2, Mgzip = 3 };
+enum class OutFormat { Plain = 0, Gzip = 1, Bgzf = 2, Mgzip = 3, Lz4 = 4 };
 
 inline void put16(std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); }
 inline void put32(std::vector<uint8_t>& v, uint32_t x) { put16(v, x); put16(v, x >> 16); }
@@ -311,6 +319,17 @@ inline bool gzip_member(const uint8_t* src, size_t n, OutFormat fmt, std::vector
 
 // the text of one batch as a run of members, compressed on the pool; `pieces` in order
 inline bool compress_batch(const uint8_t* src, size_t n, OutFormat fmt, Pool* pool, std::vector<std::vector<uint8_t>>* pieces) {
+  if (fmt == OutFormat::Lz4) {  // blocks of the file's one frame (bk_run writes its header and end mark)
+    const size_t nb = (n + bklz4::kBlock - 1) / bklz4::kBlock;
+    pieces->assign(nb, std::vector<uint8_t>());
+    auto task = [&](size_t t) {
+      const size_t b = t * bklz4::kBlock;
+      bklz4::frame_block(src + b, std::min(bklz4::kBlock, n - b), &(*pieces)[t]);
+    };
+    if (pool) pool->parallel_for(nb, task);
+    else for (size_t t = 0; t < nb; ++t) task(t);
+    return true;
+  }
   // BGZF blocks hold at most 64 KiB; gzip / mgzip members are sized for parallelism, not for the format
   const size_t unit = fmt == OutFormat::Bgzf ? 0xff00 : (size_t)1 << 20;
   const size_t group = fmt == OutFormat::Bgzf ? 16 : 1;  // members per task

@@ -197,16 +197,17 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
     return BK_OK;
   }
   // a->compression: 0 none, 1 --gz, 2 --bgz, 3 --mgz, 4 --lz4 (src/main.rs:14-19).  CompressionType::select
-  // (fastq.rs:71-79) maps --bgz to Mgzip and --mgz to Bgzf; the swap is kept.
+  // (fastq.rs:71-79) maps --bgz to Mgzip and --mgz to Bgzf; the swap is kept.  --lz4: one LZ4 frame.
   bkio::OutFormat fmt = bkio::OutFormat::Plain;
   switch (a->compression) {
     case 0: break;
     case 1: fmt = bkio::OutFormat::Gzip; break;
     case 2: fmt = bkio::OutFormat::Mgzip; break;
     case 3: fmt = bkio::OutFormat::Bgzf; break;
+    case 4: fmt = bkio::OutFormat::Lz4; break;
     default:
-      set_err("lz4 output (--lz4) is not supported by this build", err, errcap);
-      return BK_E_UNSUPPORTED;
+      set_err("unknown compression selector", err, errcap);
+      return BK_E_ARG;
   }
   std::string e;
   Logger log;
@@ -227,12 +228,6 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   bkio::Input in[2];
   if (!in[0].open(a->fq1, &e)) { set_err(e, err, errcap); return BK_E_IO; }
   if (pe && !in[1].open(a->fq2, &e)) { set_err(e, err, errcap); return BK_E_IO; }
-  for (int m = 0; m < nm; ++m)
-    if (in[m].codec() == bkio::Codec::Lz4) {
-      set_err("lz4 input is not supported by this build (plain or gzip / bgzf / mgzip FASTQ)", err, errcap);
-      return BK_E_UNSUPPORTED;
-    }
-
   Output outp[2];
   outp[0].fd = open_output(a->out_fq1, a->force != 0, &e);  // run.rs:106-111 / :225-229
   if (outp[0].fd < 0) { set_err(e, err, errcap); return BK_E_IO; }
@@ -245,6 +240,14 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
     outp[m].seekable = fstat(outp[m].fd, &st) == 0 && S_ISREG(st.st_mode);
   }
   auto close_outputs = [&]() { for (int m = 0; m < nm; ++m) close(outp[m].fd); };
+  if (fmt == bkio::OutFormat::Lz4) {  // one frame per file: its header now, blocks per batch, the end mark last
+    std::vector<uint8_t> head;
+    bklz4::frame_header(&head);
+    for (int m = 0; m < nm; ++m) {
+      if (!write_all(outp[m].fd, head.data(), head.size())) { close_outputs(); set_err(io_error(strerror(errno)), err, errcap); return BK_E_IO; }
+      outp[m].pos = head.size();
+    }
+  }
 
   log.message("Parsing barcode patterns...");  // run.rs:113 / :231
   bk_program *p1 = nullptr, *p2 = nullptr;
@@ -651,9 +654,10 @@ extern "C" int bk_run(const bk_run_args* a, char* err, size_t errcap) {
   // the formats' closing pieces: BGZF ends with an empty block, and a gzip file holds at least one member
   if (status.load() == BK_OK && fmt != bkio::OutFormat::Plain) {
     for (int m = 0; m < nm; ++m) {
-      if (fmt == bkio::OutFormat::Bgzf || outp[m].pos == 0) {
+      if (fmt == bkio::OutFormat::Lz4 || fmt == bkio::OutFormat::Bgzf || outp[m].pos == 0) {
         std::vector<uint8_t> tail;
-        bkio::gzip_member(nullptr, 0, fmt, &tail);
+        if (fmt == bkio::OutFormat::Lz4) tail.assign(4, 0);
+        else bkio::gzip_member(nullptr, 0, fmt, &tail);
         int en = 0;
         const bool ok = outp[m].seekable ? bkio::pwrite_all(outp[m].fd, tail.data(), tail.size(), outp[m].pos, &en)
                                          : write_all(outp[m].fd, tail.data(), tail.size());

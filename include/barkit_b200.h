@@ -263,12 +263,15 @@ typedef struct bk_run_args {
   const char* out_fq1;
   const char* out_fq2;  /* nullable */
   size_t max_memory_mb; /* 0 = unset (-m) */
-  size_t threads;       /* -t: (de)compression threads, as in the reference (fastq.rs:119,237,243); the per-read
-                           work has no host threads, and host staging uses all cores like the reference's rayon pool */
+  size_t threads;       /* -t: a floor, not a cap: the host pool (file reads, line-end counts, deflate; fastq.rs:119,237,243)
+                           has max(-t, cores) threads like the reference's rayon pool; the per-read work has no host threads */
   int rc_barcodes;
   int skip_trimming;
   size_t max_error;
-  int compression;      /* 0 none; others rejected with BK_E_UNSUPPORTED */
+  int compression;      /* which flag was given (src/main.rs:14-19): 0 none, 1 --gz, 2 --bgz, 3 --mgz, 4 --lz4.  bk_run applies
+                           CompressionType::select (fastq.rs:71-79): --gz gzip members, --bgz Mgzip, --mgz Bgzf (the
+                           reference's swap is kept), --lz4 one LZ4 frame.  Inputs are sniffed by magic bytes
+                           (fastq.rs:82-99): gzip / bgzf / mgzip / lz4 are read. */
   int quiet;
   int force;
   int n_gpus;           /* 0 = automatic: one GPU per 2 GiB of input text per mate, at most all visible devices */

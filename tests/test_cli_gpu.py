@@ -185,3 +185,25 @@ def test_output_to_a_pipe(tmp_path):
                        (CLI, tmp_path / "r1.fq", pat, tmp_path / "o.fq"), shell=True, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert (tmp_path / "o.fq").read_bytes() == bo.extract_se(fq, pat, 1)
+
+
+def test_lz4_in_and_out(tmp_path):
+    """--lz4 writes one LZ4 frame (lz4::EncoderBuilder, fastq.rs:244); inputs with the LZ4 magic are decoded
+    (fastq.rs:91,116).  Checked against pyarrow's LZ4 frame codec."""
+    pa = pytest.importorskip("pyarrow")
+    fq1, fq2 = bksyn.generate_pair(bksyn.CONFIGS["C3"], 6, 25000)
+    p1 = CONFIG_PATTERNS["C3"][0]
+    (tmp_path / "r1.fq.lz4").write_bytes(pa.compress(fq1, codec="lz4", asbytes=True))
+    (tmp_path / "r2.fq").write_bytes(fq2)
+    r = run_cli("-m", "2", "--quiet", "extract", "-1", str(tmp_path / "r1.fq.lz4"), "-2", str(tmp_path / "r2.fq"),
+                "-o", str(tmp_path / "o1.lz4"), "-O", str(tmp_path / "o2.lz4"), "-p", p1, "--lz4")
+    assert r.returncode == 0, r.stderr
+    e1, e2 = bo.extract_pe(fq1, fq2, p1, None, 1)
+    z1, z2 = (tmp_path / "o1.lz4").read_bytes(), (tmp_path / "o2.lz4").read_bytes()
+    assert z1[:4] == b"\x04\x22\x4d\x18" and z1[-4:] == b"\0\0\0\0"
+    assert pa.decompress(z1, decompressed_size=len(e1), codec="lz4", asbytes=True) == e1
+    assert pa.decompress(z2, decompressed_size=len(e2), codec="lz4", asbytes=True) == e2
+    r = run_cli("--quiet", "extract", "-1", str(tmp_path / "o2.lz4"), "-o", str(tmp_path / "again.fq"), "-p",
+                "^(?P<UMI>[ATGCN]{5})")
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "again.fq").read_bytes() == bo.extract_se(e2, "^(?P<UMI>[ATGCN]{5})", 1)

@@ -87,14 +87,14 @@ def test_invalid_shape_message_and_exit_0(fq, tmp_path):   # run.rs:56-58
     assert _lib.lib.bk_run(C.byref(a), err, 256) == 0
 
 
-def test_lz4_is_refused(fq, tmp_path):
-    """gzip / bgzf / mgzip are read and written (tests/test_cli_gpu.py); lz4 is named and refused."""
-    r = run_cli("--quiet", "extract", "-1", fq, "-o", str(tmp_path / "o"), "-p", "^(?P<UMI>[ATGC]{4})", "--lz4")
-    assert r.returncode == 1 and "lz4 output (--lz4) is not supported" in r.stderr
-    z = tmp_path / "in.lz4"
-    z.write_bytes(b"\x04\x22\x4d\x18" + b"\0" * 30)       # CompressionType::detect, fastq.rs:91
-    r = run_cli("--quiet", "extract", "-1", str(z), "-o", str(tmp_path / "o2"), "-p", "^(?P<UMI>[ATGC]{4})")
-    assert r.returncode == 1 and "lz4 input is not supported" in r.stderr
+def test_codecs_are_recognised_before_the_device_is_needed(fq, tmp_path):
+    """gzip / bgzf / mgzip / lz4 are read and written (tests/test_cli_gpu.py, tests/test_lz4_codec.py); an unknown
+    compression selector is an argument error."""
+    import ctypes as C
+    a = _lib.RunArgs()
+    a.fq1, a.out_fq1, a.pattern1, a.compression, a.quiet = fq.encode(), str(tmp_path / "o").encode(), b"^(?P<UMI>[ATGC]{4})", 9, 1
+    err = C.create_string_buffer(256)
+    assert _lib.lib.bk_run(C.byref(a), err, 256) == _lib.BK_E_ARG and b"compression" in err.value
 
 
 @pytest.mark.skipif(_lib.device_count() > 0, reason="only meaningful on a box without a GPU")

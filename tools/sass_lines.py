@@ -40,4 +40,4 @@ for (f, l), n in per_line.most_common(top):
             src[f] = []
     text = src[f][l - 1].strip()[:90] if 0 < l <= len(src[f]) else ""
     print("%6.2f KB  %-16s %4d | %s" % (n * 16 / 1024, f, l, text))
-print("opcodes:", ", ".join("%s %d" % kv for kv in ops.most_common(45)))
+print("opcodes:", ", ".join("%s %d" % kv for kv in ops.most_common()))
