@@ -615,9 +615,12 @@ def main():
         outs = [("o1a", "o2a"), ("o1b", "o2b")]
         res = _lib.Result()
 
-        def e2e_mode(c, nsteps, nwarm):
+        def e2e_mode(c, nsteps, nwarm, raw=False):
             def submit(slot):
-                rc = _lib.lib.bk_submit(c.handle, slot, Q, C.byref(h1), C.byref(h2))
+                if raw:   # raw FASTQ text in, record offsets made on the device (bk_submit_text)
+                    rc = _lib.lib.bk_submit_text(c.handle, slot, Q, hbuf["t1"][0], nb, hbuf["t2"][0], nb, RL)
+                else:
+                    rc = _lib.lib.bk_submit(c.handle, slot, Q, C.byref(h1), C.byref(h2))
                 if rc != 0:
                     raise SystemExit("bk_submit failed: %s" % _lib.lib.bk_last_error(c.handle).decode())
 
@@ -653,6 +656,9 @@ def main():
             c2 = _lib.Context(prog, None, paired=True, device=local_rank, extra_flags=flag, host_threads=lib_threads)
             v, _, l2, _ = e2e_mode(c2, short, 2)
             modes[name] = {"value": v, "h2d_bytes_per_step": int(l2[0]), "d2h_bytes_per_step": int(l2[1])}
+            if name == "device_both_mates":
+                v, _, l2, _ = e2e_mode(c2, short, 2, raw=True)
+                modes["raw_text_device_tokenizer"] = {"value": v, "h2d_bytes_per_step": int(l2[0]), "d2h_bytes_per_step": int(l2[1])}
             c2.close()
         # the box's host-link ceiling with every rank's GPU copying both ways at once
         barrier()
@@ -670,7 +676,9 @@ def main():
                        "library counts them (text + record offsets in, FASTQ text + result + match table out). "
                        "value = the library's default: R2 has no pattern in this config, so it stays on the host and "
                        "its output is assembled there from the input buffer inside the timed region, unless the context "
-                       "measures that to be slower than the bus. modes = the two choices pinned. bus_peak_gbs = pinned "
+                       "measures that to be slower than the bus. modes = the two choices pinned, and raw_text_device_tokenizer = "
+                       "bk_submit_text: no offsets from the host, both mates tokenised on the device in front of the extract "
+                       "kernels (what the `barkit` command line uses). bus_peak_gbs = pinned "
                        "H2D + D2H at once on every rank's GPU (sum over ranks), measured in this run."}
     else:
         e2e_launches = 0

@@ -1,6 +1,9 @@
 #!/bin/bash
-# ncu captures of the kernels next to the bench's one: the device tokenizer and the general (unanchored) extract kernel on C4.
+# ncu captures of the kernels next to the bench's: the device tokenizer and the general (unanchored) extract kernel on C4.
+tag=${1:-r2}
 set -x
-ncu --set full --clock-control none --import-source on -k regex:tok_fused -s 2 -c 1 -o gpurun_out/r1_tok_full -f python tools/tokenize_speed.py > gpurun_out/r1_tok_ncu.log 2>&1
-BK_ONLY=C4 ncu --set full --clock-control none --import-source on -k regex:extract_kernel -s 3 -c 1 -o gpurun_out/r1_c4_full -f python tools/config_speed.py 4000000 > gpurun_out/r1_c4_ncu.log 2>&1
+python tools/tokenize_speed.py > gpurun_out/${tag}_tok_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:tok_fused -s 2 -c 1 -o gpurun_out/${tag}_tok_full -f python tools/tokenize_speed.py > gpurun_out/${tag}_tok_ncu.log 2>&1
+BK_ONLY=C4 python tools/config_speed.py 4000000 > gpurun_out/${tag}_c4_plain.log 2>&1 && \
+BK_ONLY=C4 ncu --set full --clock-control none --import-source on -k regex:extract_kernel -s 3 -c 1 -o gpurun_out/${tag}_c4_full -f python tools/config_speed.py 4000000 > gpurun_out/${tag}_c4_ncu.log 2>&1
 ls -la gpurun_out | tail -4
