@@ -367,7 +367,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         if (VAR && var_me) {  // (lane per read, bytewise: see match_variants)
           if (can) {
             ms = match_variants<false>(P.vprog[m], P.nvar[m], tab, rv.seq, rv.seq_len);
-            if (ms < 0 && rc) ms = match_variants<true>(P.vprog[m], P.nvar[m], tab, rv.seq, rv.seq_len);
+            if (ms < 0 && rc) {
+              ms = match_variants<true>(P.vprog[m], P.nvar[m], tab, rv.seq, rv.seq_len);
+              if (ms >= 0 && !caps_utf8_ok(P.vprog[m][ms >> 24], rv.seq, (uint32_t)ms & 0xFFFFFFu)) ms = -1;
+            }
           }
         } else if (GENERAL && un_me) {
           if (split) {  // lower half here, upper half on the other mate's front warp
@@ -380,7 +383,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         } else if (can) {
           ms = GENERAL ? match_read_shared(tab, rv.seq, rv.seq_len) : match_read<false>(tab, rv.seq, rv.seq_len);  // lane per read
         }
-        if (GENERAL && !(VAR && var_me) && can && ms < 0 && rc) ms = match_read<true>(tab, rv.seq, rv.seq_len);  // parse.rs:61-66
+        if (GENERAL && !(VAR && var_me) && can && ms < 0 && rc) {  // parse.rs:61-66
+          ms = match_read<true>(tab, rv.seq, rv.seq_len);
+          if (ms >= 0 && !caps_utf8_ok(pg, rv.seq, (uint32_t)ms)) ms = -1;
+        }
       } else {
         if (lane == 0) atomicOr(&P.result->error, 2u);
         if (GENERAL && split && un_me) {  // keep the pair's barriers in step: nothing to search

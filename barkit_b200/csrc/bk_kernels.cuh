@@ -515,6 +515,38 @@ __device__ __noinline__ int match_read(uint32_t tab, uint32_t seq, uint32_t L) {
   return -1;
 }
 
+// parse.rs:166 `from_utf8(barcode_seq)?`: a capture that is not well-formed UTF-8 makes create_read_with_new_header
+// fail, and the read counts as unmatched (parse.rs:74-79 `.ok()?`).  A forward match cannot capture such bytes (here
+// a byte >= 0x80 matches nothing), but a reverse-complement match is found on the complemented text -- where every
+// byte is a letter -- and its offsets are then applied to the FORWARD read (parse.rs:58-68), so it can.
+// Well-formed = Unicode table 3-7; the capture is validated on its own, so a sequence cut off by its end is ill-formed.
+__device__ __noinline__ bool caps_utf8_ok(const bk_devprog& pg, uint32_t seq, uint32_t ms) {
+  for (uint32_t c = 0; c < pg.ncaps; ++c) {
+    const uint32_t b = seq + ms + pg.caps[c].off, e = b + pg.caps[c].len;
+    for (uint32_t i = b; i < e;) {
+      const uint32_t x = lds8(i);
+      if (x < 0x80u) { ++i; continue; }
+      uint32_t need, lo = 0x80u, hi = 0xBFu;
+      if (x >= 0xC2u && x <= 0xDFu) need = 1;
+      else if (x == 0xE0u) { need = 2; lo = 0xA0u; }
+      else if (x == 0xEDu) { need = 2; hi = 0x9Fu; }
+      else if (x >= 0xE1u && x <= 0xEFu) need = 2;
+      else if (x == 0xF0u) { need = 3; lo = 0x90u; }
+      else if (x == 0xF4u) { need = 3; hi = 0x8Fu; }
+      else if (x >= 0xF1u && x <= 0xF3u) need = 3;
+      else return false;
+      if (i + need >= e) return false;
+      for (uint32_t j = 1; j <= need; ++j) {
+        const uint32_t y = lds8(i + j);
+        if (y < lo || y > hi) return false;
+        lo = 0x80u; hi = 0xBFu;
+      }
+      i += need + 1u;
+    }
+  }
+  return true;
+}
+
 // ---- variable repetition: a program given as a list of fixed-length variants ------------------------------
 //
 // Leftmost-first over the variants = smallest start at which any variant matches, and among the variants

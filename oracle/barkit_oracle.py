@@ -129,9 +129,45 @@ class BarcodeType:
         raise UnexpectedCaptureGroupName(name)
 
 
+# `.` of regex::bytes::Regex in its default Unicode mode (pattern.rs:6,182): one UTF-8 encoded scalar value other
+# than '\n' -- one to four bytes; a byte >= 0x80 that is not part of a well-formed sequence matches nothing.
+# (`re` on bytes would take any single byte.)  The well-formed ranges are those of the Unicode standard, table 3-7.
+_UTF8_DOT = (r"(?:[\x00-\x09\x0b-\x7f]|[\xc2-\xdf][\x80-\xbf]|\xe0[\xa0-\xbf][\x80-\xbf]|[\xe1-\xec\xee\xef][\x80-\xbf]{2}"
+             r"|\xed[\x80-\x9f][\x80-\xbf]|\xf0[\x90-\xbf][\x80-\xbf]{2}|[\xf1-\xf3][\x80-\xbf]{3}|\xf4[\x80-\x8f][\x80-\xbf]{2})")
+
+
 def _rust_regex_to_py(pattern: str) -> str:
-    """The Rust `regex` crate accepts `(?<name>` and `(?P<name>`; `re` only the latter."""
-    return re.sub(r"\(\?<(?![=!])", "(?P<", pattern)
+    """The Rust `regex` crate accepts `(?<name>` and `(?P<name>`; `re` only the latter.  `.` outside a class becomes
+    the UTF-8 scalar alternation above."""
+    pattern = re.sub(r"\(\?<(?![=!])", "(?P<", pattern)
+    out, in_class, i = [], False, 0
+    while i < len(pattern):
+        c = pattern[i]
+        if c == "\\" and i + 1 < len(pattern):
+            out.append(pattern[i:i + 2])
+            i += 2
+            continue
+        if in_class:
+            in_class = c != "]"
+        elif c == "[":
+            in_class = True
+            if pattern[i + 1:i + 2] == "^":          # `[^...]`, `[]...]`: the first member is literal
+                out.append("[^")
+                i += 2
+                c = ""
+            if pattern[i + (1 if c else 0):i + (2 if c else 1)] == "]":
+                out.append(c + "]")
+                i += 2 if c else 1
+                continue
+            if not c:
+                continue
+        elif c == ".":
+            out.append(_UTF8_DOT)
+            i += 1
+            continue
+        out.append(c)
+        i += 1
+    return "".join(out)
 
 
 class BarcodeRegex:

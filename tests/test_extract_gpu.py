@@ -466,3 +466,55 @@ def test_full_size_properties_c3():
         total += r.out1_len
     assert total == res.out1_len and crc == whole1
     ctx.close()
+
+
+# ---- bytes >= 0x80 (declared divergence) ----------------------------------------------------
+
+def _fq(seqs):
+    return b"".join(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)) for i, s in enumerate(seqs))
+
+
+def test_invalid_utf8_bytes_never_match():
+    """regex::bytes::Regex runs in Unicode mode (pattern.rs:6,182): a byte >= 0x80 outside a well-formed UTF-8
+    sequence matches neither `.` (a fuzzy run's wildcard slot) nor a class.  The oracle states that (its `.` is the
+    UTF-8 scalar alternation); the kernel's rule -- bytes >= 0x80 never match -- gives the same bytes here."""
+    rnd = random.Random(2)
+    pat = "^(?P<UMI>[ATGCN]{4})atgc(?P<CB>[ATGCN]{3})"
+    seqs = []
+    for i in range(4000):
+        s = bytearray(b"ACGT" + b"ATGC" + b"TTT" + bytes(rnd.choice(b"ACGT") for _ in range(rnd.randrange(0, 40))))
+        for _ in range(rnd.choice([0, 1, 1, 2])):
+            s[rnd.randrange(0, min(len(s), 14))] = rnd.choice([0x80, 0xA9, 0xBF, 0xC0, 0xC1, 0xF5, 0xFF, 0xFE, ord("N"), ord("x")])
+        # (continuation bytes and the never-valid lead bytes only: no well-formed multi-byte sequence can arise)
+        seqs.append(bytes(s))
+    fq = _fq(seqs)
+    for k in (0, 1, 2):
+        out, res = run_se(fq, pat, k=k)
+        assert out == bo.extract_se(fq, pat, k)
+        assert 0 < res.n_out < len(seqs)
+    # unanchored search and the reverse-complement retry go through other code
+    upat = "(?P<UMI>[ATGCN]{4})atgc"
+    assert run_se(fq, upat, k=1)[0] == bo.extract_se(fq, upat, 1)
+    # -r: the reverse-complement match is found on complemented text (every byte a letter) and its offsets applied to
+    # the forward read (SURVEY F7), so a capture CAN hold such bytes: from_utf8 fails and the read is dropped (parse.rs:166)
+    out_rc, res_rc = run_se(fq, pat, k=1, rc=True)
+    assert out_rc == bo.extract_se(fq, pat, 1, rc_barcodes=True)
+    # ... and kept when the captured bytes are a well-formed sequence
+    seqs2 = [b"AAA" + b"GCAT" + b"ACGT", b"AAA" + b"GCAT" + b"A\xc3\xa9T", b"AAA" + b"GCAT" + b"AC\xffT", b"AAA" + b"GCAT" + b"AC\xc3"]
+    fq2 = _fq(seqs2)
+    out2, res2 = run_se(fq2, pat, k=0, rc=True)
+    assert out2 == bo.extract_se(fq2, pat, 0, rc_barcodes=True) and res2.n_out == 2
+
+
+def test_well_formed_multibyte_sequences_are_the_declared_divergence():
+    """A WELL-FORMED multi-byte sequence under a wildcard slot is one `.` for the regex crate (the match grows by the
+    extra bytes); here no byte >= 0x80 ever matches, so such a read is simply unmatched.  Sequence lines of FASTQ are
+    ASCII; this pins the behaviour that DESIGN.md declares instead of leaving it unobserved."""
+    pat = "^(?P<UMI>[ATGCN]{4})atgc"
+    plain, odd = b"ACGTATGCAAAA", b"ACGTA\xc3\xa9GCAAAA"          # U+00E9 in the wildcard slot of A.GC
+    fq = _fq([plain, odd, plain])
+    ref = bo.extract_se(fq, pat, 1)
+    assert ref.count(b"\n") == 12                                 # the reference keeps all three reads
+    out, res = run_se(fq, pat, k=1)
+    recs = [b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)) for i, s in enumerate([plain, odd, plain])]
+    assert res.n_out == 2 and out == bo.extract_se(recs[0] + recs[2], pat, 1)
