@@ -92,3 +92,32 @@ def test_extract_from_device_tokenized_text(ctx):
     assert _lib.lib.bk_extract_host(ctx.handle, len(off) - 1, C.byref(m), None, out.ctypes.data, cap, None, 0,
                                     C.byref(res)) == _lib.BK_OK
     assert out[:res.out1_len].tobytes() == bo.extract_se(fq, "^(?P<UMI>[ATGCN]{4})", 1)
+
+
+# ---- against the oracle's reader (oracle/barkit_oracle.py: read_fastq = seq_io's field definitions) ----------------
+
+@pytest.mark.parametrize("seed", range(5))
+def test_offsets_cut_the_oracles_records(ctx, seed):
+    """The device's record offsets against the ORACLE's tokeniser, not the product's own host one: the text between
+    consecutive offsets must be exactly one record for read_fastq, and the records in order must be read_fastq's of
+    the whole text."""
+    rnd = random.Random(100 + seed)
+    fq = ragged_fastq(rnd, 2500 + 7 * seed, crlf=(seed == 1), plus_comment=(seed in (2, 3)), final_newline=(seed != 4))
+    want = bo.read_fastq(fq)
+    rc, off, consumed, maxrec = ctx.tokenize_device(fq, True, None)
+    assert rc == _lib.BK_OK and len(off) == len(want) + 1 and off[0] == 0 and consumed == len(fq)
+    longest = 0
+    for r, rec in enumerate(want):
+        piece = fq[off[r]:off[r + 1]] if r + 1 < len(want) else fq[off[r]:]
+        got = bo.read_fastq(piece)
+        assert len(got) == 1 and got[0] == rec, r
+        longest = max(longest, len(piece))
+    assert maxrec == longest
+
+
+def test_malformed_text_is_refused_where_the_oracle_refuses_it(ctx):
+    rec = b"@r\nACGT\n+\nIIII\n"
+    for bad in (rec + b"r\nACGT\n+\nIIII\n" + rec, rec + b"@r\nACGT\n-\nIIII\n" + rec, rec * 2 + rec[:9]):
+        with pytest.raises(ValueError):
+            bo.read_fastq(bad)
+        assert ctx.tokenize_device(bad, True, None)[0] == _lib.BK_E_FORMAT
