@@ -207,3 +207,23 @@ def test_lz4_in_and_out(tmp_path):
                 "^(?P<UMI>[ATGCN]{5})")
     assert r.returncode == 0, r.stderr
     assert (tmp_path / "again.fq").read_bytes() == bo.extract_se(e2, "^(?P<UMI>[ATGCN]{5})", 1)
+
+
+def test_input_from_a_pipe_and_empty_input(tmp_path):
+    fq = bksyn.generate(bksyn.CONFIGS["C1"], 1, 0, 30000)
+    (tmp_path / "r1.fq").write_bytes(fq)
+    pat = CONFIG_PATTERNS["C1"][0]
+    r = subprocess.run("cat %s | %s -m 1 --quiet extract -1 /dev/stdin -o %s -p '%s'" %
+                       (tmp_path / "r1.fq", CLI, tmp_path / "o.fq", pat), shell=True, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "o.fq").read_bytes() == bo.extract_se(fq, pat, 1)
+    (tmp_path / "empty.fq").write_bytes(b"")
+    for flag, want in (([], b""), (["--gz"], None)):
+        out = tmp_path / ("e" + "".join(flag))
+        r = run_cli("--quiet", "extract", "-1", str(tmp_path / "empty.fq"), "-o", str(out), "-p", pat, *flag)
+        assert r.returncode == 0, r.stderr
+        if want is None:
+            import gzip
+            assert gzip.decompress(out.read_bytes()) == b""       # a gzip file holds at least one member
+        else:
+            assert out.read_bytes() == want
