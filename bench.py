@@ -651,7 +651,7 @@ def main():
 
         v_auto, s_auto, last, e2e_launches = e2e_mode(ctx, args.steps, max(2, min(args.warmup, 3)))
         modes = {}
-        short = max(3, min(args.steps, 5))
+        short = max(3, args.steps)   # (same length as the default mode: a short run is dominated by filling and draining the two slots)
         for name, flag in (("host_mate_pinned", _lib.FLAG_HOST_MATE_PINNED), ("device_both_mates", _lib.FLAG_DEVICE_BOTH_MATES)):
             c2 = _lib.Context(prog, None, paired=True, device=local_rank, extra_flags=flag, host_threads=lib_threads)
             v, _, l2, _ = e2e_mode(c2, short, 2)
