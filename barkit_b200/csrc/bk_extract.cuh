@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
   // for the other mate's front warp, and that warp's results for the upper half of the tile
   __shared__ uint32_t s_share[GENERAL && PAIRED ? kFrontPairs : 1][2][3][32];
   __shared__ int s_help[GENERAL && PAIRED ? kFrontPairs : 1][2][32];
+  __shared__ int s_res[GENERAL && PAIRED ? kFrontPairs : 1][2][2][32];  // match_unanchored shared by two warps: [round parity][warp][lane]
   __shared__ TileMeta meta[NM][ST];
   __shared__ uint4 run_desc[NM][32];  // copy descriptors of the tile's runs of unchanged records
 
@@ -235,6 +236,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
     }
     for (int i = lane; i < 2 * BK_MAX_OPS; i += 32) tw[kTabOps / 4 + i] = reinterpret_cast<const uint32_t*>(pg.ops)[i];
     for (int i = lane; i < BK_MAX_LIT / 4; i += 32) tw[kTabLit / 4 + i] = reinterpret_cast<const uint32_t*>(pg.lit)[i];
+    if (GENERAL && lane < 8) {  // bit planes of the first literal (match_unanchored): bits 1 and 2 of byte `lane`
+      const uint32_t c = pg.nops && pg.ops[0].kind == BK_OP_LIT ? (uint32_t)pg.lit[pg.ops[0].idx + lane] : 0u;
+      tw[kTabSA / 4 + 2 * lane] = (c & 2u) ? 0xFFFFFFFFu : 0u;
+      tw[kTabSA / 4 + 2 * lane + 1] = (c & 4u) ? 0xFFFFFFFFu : 0u;
+    }
     if (lane == 0)
       for (int s = 0; s < ST; ++s) {
         mbar_init(&bar_full[m][s], 1);
@@ -338,7 +344,12 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
     const bk_devprog& pgo = P.prog[PAIRED ? m ^ 1 : m];
     const bool un_other = PAIRED && pgo.present && !pgo.anchor_start && !pgo.anchor_end;
     const bool var_me = VAR && P.nvar[m] > 1u;
-    const bool split = GENERAL && !VAR && PAIRED && !rc && un_me != un_other;
+    // (by lane halves for the warp-per-read sweep; by windows of starts for the bit-parallel scan: match_unanchored)
+    const bk_devprog& pgs = un_me ? pg : pgo;
+    const bool scan_form = pgs.nops && bs_eligible(pgs.ops[0].kind, pgs.ops[0].len, pgs.ops[0].k);
+    const bool share = GENERAL && !VAR && PAIRED && !rc && un_me != un_other;
+    const bool split = share && !scan_form, split2 = share && scan_form;
+    const uint32_t pair_bar = fp == 0 ? 1u : 4u + 2u * ST;
     const uint32_t tab_other = smem_u32(&cls_tab[PAIRED ? m ^ 1 : m][0]);
     for (uint32_t k = fp;; k += kFrontPairs) {
       const uint32_t s = k % ST, ph = (k / ST) & 1u;
@@ -373,13 +384,14 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
             }
           }
         } else if (GENERAL && un_me) {
-          if (split) {  // lower half here, upper half on the other mate's front warp
+          if (split || split2) {  // the other mate's front warp takes the upper half of the reads / every other window
             s_share[fp][xb][0][lane] = rv.seq;
             s_share[fp][xb][1][lane] = rv.seq_len;
             s_share[fp][xb][2][lane] = can;
-            nbar_sync(fp == 0 ? 1u : 4u + 2u * ST, 64);
+            nbar_sync(pair_bar, 64);
           }
-          ms = match_unanchored(tab, rv.seq, rv.seq_len, can && !(split && lane >= 16), lane);  // warp per read
+          ms = match_unanchored(tab, rv.seq, rv.seq_len, can && !(split && lane >= 16), lane, 0, split2 ? 2 : 1,
+                                &s_res[fp][0][0][0], pair_bar);
         } else if (can) {
           ms = GENERAL ? match_read_shared(tab, rv.seq, rv.seq_len) : match_read<false>(tab, rv.seq, rv.seq_len);  // lane per read
         }
@@ -389,15 +401,16 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         }
       } else {
         if (lane == 0) atomicOr(&P.result->error, 2u);
-        if (GENERAL && split && un_me) {  // keep the pair's barriers in step: nothing to search
+        if (GENERAL && (split || split2) && un_me) {  // keep the pair's barriers in step: nothing to search
           s_share[fp][xb][2][lane] = 0;
-          nbar_sync(fp == 0 ? 1u : 4u + 2u * ST, 64);
+          nbar_sync(pair_bar, 64);
         }
       }
-      if (GENERAL && split && !un_me) {  // the other mate searches: take the upper half of its reads
-        nbar_sync(fp == 0 ? 1u : 4u + 2u * ST, 64);
+      if (GENERAL && (split || split2) && !un_me) {  // the other mate searches: take our share of it
+        nbar_sync(pair_bar, 64);
         const int h = match_unanchored(tab_other, s_share[fp][xb][0][lane], s_share[fp][xb][1][lane],
-                                       s_share[fp][xb][2][lane] != 0 && lane >= 16, lane);
+                                       s_share[fp][xb][2][lane] != 0 && !(split && lane < 16), lane, 1, split2 ? 2 : 1,
+                                       &s_res[fp][0][0][0], pair_bar);
         s_help[fp][xb][lane] = h;
       }
       __syncwarp();

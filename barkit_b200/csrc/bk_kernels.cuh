@@ -379,7 +379,8 @@ __device__ __forceinline__ uint32_t complement(uint32_t c) {
 // into the kernel's parameter space from a non-inlined function, every field access was a
 // generic-address load with global-memory latency.
 constexpr uint32_t kTabComp = 256, kTabHdr = 512, kTabOps = 528, kTabLit = kTabOps + 8u * BK_MAX_OPS;
-constexpr uint32_t kTabBytes = kTabLit + BK_MAX_LIT;
+constexpr uint32_t kTabSA = kTabLit + BK_MAX_LIT;  // 8 x 2 words: bit planes of the program's first literal (match_unanchored)
+constexpr uint32_t kTabBytes = kTabSA + 64u;
 struct MOp { uint32_t off, len, kind, k, idx; };
 __device__ __forceinline__ MOp tab_op(uint32_t tab, uint32_t o) {  // bk_op, little endian
   const uint2 v = lds64(tab + kTabOps + 8u * o);
@@ -595,64 +596,119 @@ __device__ __noinline__ int match_variants(const bk_devprog* vp, uint32_t nvar, 
   return (int)best;  // 0xFFFFFFFF = -1: no variant matches
 }
 
-// Unanchored forward search, one warp per read: the 32 lanes test 32 consecutive candidate starts
-// at once and a ballot + find-first-set picks the smallest start at which every run passes, which
-// is the regex crate's leftmost-first match (pattern.rs:225-230).  Lane-per-read scanning made the
-// whole warp wait for its unluckiest read (a read without a match walks all its starts).  Called by
-// all lanes together; `can` = this lane's read takes part; returns this lane's read's result.
-__device__ __noinline__ int match_unanchored(uint32_t tab, uint32_t seq, uint32_t L, bool can, int lane) {
+// Unanchored forward search (pattern.rs:225-230: the leftmost start at which the whole program passes).
+//
+// The program's first run is its most selective one (bk_pattern.cc puts literals first).  When it is a literal of up
+// to 8 bytes with k <= 3, every lane scans ITS read bit-parallel, 32 candidate starts per step:
+//   * the text is reduced to two bit planes, bit 1 and bit 2 of every byte (A, C, G, T differ in them; every other
+//     byte falls onto one of the four), 32 bytes per 32-bit word: four bytes at a time, `(w >> 1) & 0x01010101`
+//     gathered into a nibble with one multiply;
+//   * for literal position i the planes shifted by i (a funnel shift over two words) are compared with the
+//     literal's two bits, which gives the mismatch mask of position i for 32 starts at once;
+//   * the masks are summed in three bit-sliced counter words (half adders, the top one sticky), and `count <= k` is
+//     a word of candidate starts.
+// The reduction can only lose mismatches, so the candidates are a superset of the literal's k-mismatch occurrences;
+// each lane verifies its candidates against the whole program (match_at_fwd_shared), lowest first, all lanes of the
+// warp together.  ~6.5 instructions per candidate start for the 32 reads of a warp.  The previous form -- one warp per
+// read, 32 starts per step, ~35 instructions per step of ONE read -- was what bounded BASELINE config C4; a byte-serial
+// shift-add scan (one 4-bit counter per alignment) was also built and measured: ~13 instructions per text byte, slower.
+//
+// Two warps can share a search (`nwarps` = 2: the front warps of the two mates, when only one mate searches): they take
+// alternate windows of 32 starts, exchange their windows' results through `res` behind the pair's named barrier
+// `bid`, and both go on to the next two windows while any read is undecided -- the leftmost match of a read is the
+// one in its lowest window.  Programs whose first run is not such a literal are swept one warp per read as before.
+// Called by all lanes together; `can` = this lane's read takes part; returns this lane's read's result.
+template <int NW>
+__device__ __forceinline__ void bs_planes(uint32_t addr, uint32_t& p0, uint32_t& p1) {  // bit planes of the 4 * NW bytes at addr
+  const uint32_t base = addr & ~3u, sh = (addr & 3u) * 8u;
+  uint32_t prev = lds32(base);
+  p0 = p1 = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    const uint32_t nxt = lds32(base + 4u * w + 4u);
+    const uint32_t v = __funnelshift_r(prev, nxt, sh);
+    prev = nxt;
+    p0 |= ((((v >> 1) & 0x01010101u) * 0x01020408u) >> 24) << (4 * w);
+    p1 |= ((((v >> 2) & 0x01010101u) * 0x01020408u) >> 24) << (4 * w);
+  }
+}
+
+__device__ __forceinline__ bool bs_eligible(uint32_t kind, uint32_t len, uint32_t k) { return kind == BK_OP_LIT && len <= 8u && k <= 3u; }
+
+__device__ __noinline__ int match_unanchored(uint32_t tab, uint32_t seq, uint32_t L, bool can, int lane, int which, int nwarps,
+                                              int* res, uint32_t bid) {
   const uint32_t T = lds32(tab + kTabHdr + 4u);
-  // The program's first run is its most selective one (bk_pattern.cc puts literals first).  When it
-  // is a literal of up to 8 bytes it is kept in registers and the warp-per-read sweep tests only
-  // it -- three loads and a dozen ALU operations per candidate start.  The candidates found (one per
-  // read) are then verified against the whole program one lane per read, all reads at once; a
-  // read whose candidate fails resumes its sweep behind it.
   const MOp op0 = tab_op(tab, 0);
-  const bool filt = op0.kind == BK_OP_LIT && op0.len <= 8u;
-  const uint32_t lit0 = lds32(tab + kTabLit + op0.idx), lit1 = lds32(tab + kTabLit + op0.idx + 4u);
-  const uint32_t m0 = op0.len >= 4u ? 0xFFFFFFFFu : (1u << (8u * op0.len)) - 1u;
-  const uint32_t m1 = op0.len <= 4u ? 0u : op0.len >= 8u ? 0xFFFFFFFFu : (1u << (8u * (op0.len - 4u))) - 1u;
   int ms = -1;
-  uint32_t from = 0;
   bool pend = can && L >= T;
-  for (unsigned todo = __ballot_sync(0xffffffffu, pend); todo; todo = __ballot_sync(0xffffffffu, pend)) {
-    int cand = -1;
-    for (; todo; todo &= todo - 1u) {
-      const int r = __ffs(todo) - 1;
-      const uint32_t rseq = __shfl_sync(0xffffffffu, seq, r), last = __shfl_sync(0xffffffffu, L, r) - T;
-      int found = -1;
-      for (uint32_t s0 = __shfl_sync(0xffffffffu, from, r); s0 <= last; s0 += 32u) {
-        const uint32_t s = s0 + (uint32_t)lane;
-        bool ok = s <= last;
-        if (filt) {
-          const uint32_t base = rseq + s + op0.off, p = base & ~3u, sh = (base & 3u) * 8u;
-          const uint32_t w0 = lds32(p), w1 = lds32(p + 4u), w2 = lds32(p + 8u);
-          const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
-          const uint32_t x0 = (v0 ^ lit0) & m0, x1 = (v1 ^ lit1) & m1;
-          const uint32_t z0 = (((x0 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x0) & 0x80808080u;  // 0x80 per differing byte
-          const uint32_t z1 = (((x1 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x1) & 0x80808080u;
-          ok = ok && (uint32_t)(__popc(z0) + __popc(z1)) <= op0.k && !((z0 & v0) | (z1 & v1));
-        } else if (ok) {
-          ok = match_at<false, true>(tab, rseq, 0u, s);
+  if (bs_eligible(op0.kind, op0.len, op0.k)) {
+    const uint32_t last = pend ? L - T : 0u;  // this read's last candidate start
+    const uint32_t smax = __reduce_max_sync(0xffffffffu, last);
+    if (!__any_sync(0xffffffffu, pend)) return -1;
+    const uint32_t nwin = smax / 32u + 1u;
+    for (uint32_t r = 0; r * (uint32_t)nwarps < nwin; ++r) {
+      const uint32_t w = r * (uint32_t)nwarps + (uint32_t)which;
+      int mine = -1;
+      if (w < nwin) {
+        const uint32_t q = 32u * w, cb = seq + q + op0.off;
+        // (unrolled: a rolled, out-of-line form is 1 KB smaller and measured slower, 6.35 against 6.15 ms on C4)
+        uint32_t a0, a1, b0, b1;
+        bs_planes<8>(cb, a0, a1);
+        bs_planes<2>(cb + 32u, b0, b1);  // (the literal reaches at most 7 bytes into the next 32)
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < op0.len; ++i) {
+          const uint2 x = lds64(tab + kTabSA + 8u * i);
+          const uint32_t mm = (__funnelshift_r(a0, b0, i) ^ x.x) | (__funnelshift_r(a1, b1, i) ^ x.y);
+          const uint32_t carry = c0 & mm;
+          c0 ^= mm;
+          c2 |= c1 & carry;
+          c1 ^= carry;
         }
-        const unsigned hit = __ballot_sync(0xffffffffu, ok);
-        if (hit) {
-          found = (int)s0 + __ffs(hit) - 1;
-          break;
+        uint32_t cand = ~c2 & (op0.k == 0u ? ~(c0 | c1) : op0.k == 1u ? ~c1 : op0.k == 2u ? ~(c1 & c0) : 0xFFFFFFFFu);
+        if (!pend || q > last) cand = 0;
+        else if (last - q < 31u) cand &= (2u << (last - q)) - 1u;
+        while (__any_sync(0xffffffffu, cand != 0u)) {  // every lane's lowest candidate, verified together
+          const bool have = cand != 0u;
+          const uint32_t st = q + (have ? (uint32_t)__ffs(cand) - 1u : 0u);
+          if (have && match_at_fwd_shared(tab, seq, st)) {
+            mine = (int)st;
+            cand = 0;
+          } else if (have) {
+            cand &= cand - 1u;
+          }
         }
       }
-      if (lane == r) cand = found;
+      if (nwarps == 2) {  // the other warp's window of this round
+        int* const rr = res + (r & 1u) * 64u;
+        rr[which * 32 + lane] = mine;
+        nbar_sync(bid, 64);
+        const int ra = rr[lane], rb = rr[32 + lane];
+        mine = ra >= 0 ? ra : rb;
+      }
+      if (pend && mine >= 0) {
+        ms = mine;
+        pend = false;
+      }
+      if (!__any_sync(0xffffffffu, pend)) break;
     }
-    if (pend) {
-      if (cand < 0) {
-        pend = false;
-      } else if (!filt || match_at_fwd_shared(tab, seq, (uint32_t)cand)) {
-        ms = cand;
-        pend = false;
-      } else {
-        from = (uint32_t)cand + 1u;
+    return ms;
+  }
+  // general first run: one warp per read, the 32 lanes test 32 consecutive starts against the whole program
+  for (unsigned todo = __ballot_sync(0xffffffffu, pend); todo; todo &= todo - 1u) {
+    const int r = __ffs(todo) - 1;
+    const uint32_t rseq = __shfl_sync(0xffffffffu, seq, r), last = __shfl_sync(0xffffffffu, L, r) - T;
+    int found = -1;
+    for (uint32_t s0 = 0; s0 <= last; s0 += 32u) {
+      const uint32_t s = s0 + (uint32_t)lane;
+      const bool ok = s <= last && match_at_fwd_shared(tab, rseq, s);
+      const unsigned hit = __ballot_sync(0xffffffffu, ok);
+      if (hit) {
+        found = (int)s0 + __ffs(hit) - 1;
+        break;
       }
     }
+    if (lane == r) ms = found;
   }
   return ms;
 }
