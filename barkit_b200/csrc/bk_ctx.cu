@@ -24,6 +24,7 @@
 #include "bk_extract.cuh"
 #include "bk_tokenize.cuh"
 #include "bk_compact.cuh"
+#include "bk_match.cuh"
 
 namespace {
 
@@ -63,6 +64,9 @@ struct Slot {
   uint64_t h2d_bytes = 0;        // of the batch in flight
   // two-kernel form of a paired launch with one pattern (enqueue_split): hand-over and the compaction's look-back state
   DevBuf split_match, split_hlen, split_scratch;
+  DevBuf tab_err;
+  DevBuf tab_extras[2];     // ... and, for a parametric program, the extras of every match
+  DevBuf tab_match[2];      // match tables of a paired batch that runs as match_kernel + two single-end launches (enqueue_tabled)
   bk::CompactParams cpar;   // the compaction in flight, should it have to run again (compact_redo)
   bool cpar_valid = false;
   // raw-text batches (bk_submit_text): record offsets are made on the device
@@ -92,6 +96,8 @@ struct bk_ctx {
   // and `solo` is the single-end view of this context that processes the other mate.
   int pass_mate = -1;
   bk_ctx* solo = nullptr;
+  // Paired mode with two patterns: the single-end views of the two mates (enqueue_tabled)
+  bk_ctx* view[2] = {nullptr, nullptr};
   int host_threads = 1;
   uint32_t maxrec_seen[2] = {0, 0};  // longest record of earlier raw-text batches, per mate (bk_submit_text)
   bool compact_careful = false;      // a batch's pattern-less mate was not in the writer's framing: size from the text first
@@ -135,13 +141,25 @@ struct LaunchPlan {
   int grid;
 };
 
+// A parametric program's header growth depends on the read: every extra copy of an atom inside a capture group adds a
+// sequence and a quality byte to the header.  Upper bound for a record of at most `maxrec` bytes (its sequence line
+// is less than half of it).
+uint64_t par_growth(const bk_devprog& pg, uint64_t maxrec) {
+  uint64_t g = 0;
+  for (uint32_t i = 0; i < pg.nins; ++i) {
+    const uint64_t e = std::min<uint64_t>(pg.ins[i].max_extra == 0xFFFF ? maxrec / 2 : pg.ins[i].max_extra, maxrec / 2);
+    g += 2 * e * (uint64_t)__builtin_popcount(pg.ins[i].capmask);
+  }
+  return g;
+}
+
 size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_t in_cap[2],
                 uint32_t out_cap[2], int stages) {
   size_t total = 0;
   int nm = ctx->paired ? 2 : 1;
   for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
   for (int m = 0; m < nm; ++m) {
-    uint32_t growth = ctx->prog[m].present ? ctx->growth[m] : 0;
+    uint32_t growth = ctx->prog[m].present ? ctx->growth[m] + (uint32_t)par_growth(ctx->prog[m], maxrec[m]) : 0;
     in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
     out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
     total += (size_t)stages * in_cap[m] + out_cap[m];
@@ -160,14 +178,14 @@ bool needs_general(const bk_ctx* ctx) {
   return false;
 }
 
-template <bool PAIRED, bool GENERAL, bool VAR = false, int ST = bk::kStages>
+template <bool PAIRED, bool GENERAL, bool VAR = false, int ST = bk::kStages, bool TABLE = false>
 int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* lp) {
   constexpr int kThreads = bk::cta_warps(PAIRED) * 32;
   // Two CTAs per SM (228 KB of shared memory per SM, each CTA's static part included) whenever the records
   // allow it: the kernel is bound by ring slots in flight, and the instantiations differ in static shared
   // memory (the general ones carry the search-sharing buffers), so the budget is taken from the kernel itself.
   cudaFuncAttributes fa;
-  CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR, ST>));
+  CK(cudaFuncGetAttributes(&fa, bk::extract_kernel<PAIRED, GENERAL, VAR, ST, TABLE>));
   constexpr int kWant = PAIRED ? 2 : 4;  // CTAs per SM the kernel is compiled for (launch bounds): 30-40 warps per SM
   const size_t target = std::min<size_t>(kTargetDynSmem, (233472 / kWant - fa.sharedSizeBytes) & ~size_t(127));
   uint32_t R = bk::kTileRecs;
@@ -178,16 +196,16 @@ int plan_launch(bk_ctx* ctx, uint32_t n, const uint32_t maxrec[2], LaunchPlan* l
     ctx->last_error = "record too long for the on-chip staging buffer";
     return BK_E_CAPACITY;
   }
-  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, ST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, ST, TABLE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   int per_sm = 0, other = 0;  // `other`: CTAs per SM that registers and threads allow
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, bk::extract_kernel<PAIRED, GENERAL, VAR, ST>, kThreads, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, bk::extract_kernel<PAIRED, GENERAL, VAR, ST, TABLE>, kThreads, 0));
   for (;;) {
     lp->tile_recs = R;
     lp->smem = smem_for(ctx, R, maxrec, lp->in_cap, lp->out_cap, ST);
-    CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(bk::extract_kernel<PAIRED, GENERAL, VAR, ST, TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)lp->smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR, ST>,
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::extract_kernel<PAIRED, GENERAL, VAR, ST, TABLE>,
                                                      kThreads, lp->smem));
     if (per_sm >= kWant || other < kWant || R <= 24) break;  // (long records: the tile stays as it is, fewer CTAs share the SM)
     --R;
@@ -218,14 +236,36 @@ size_t scratch_bytes(uint32_t ntiles) { return events_offset(ntiles); }
 // `co`: the launch is the first half of a split paired batch (enqueue_split): single-end, keep masks for the compaction
 // that follows it, figures filed under the mate's own index.
 struct CoLaunch {
-  uint32_t* hlen;              // in: where the header lengths go
-  uint32_t rslot;              // in: 0 / 1
-  unsigned long long* kmask;   // out
-  uint32_t tile_recs;          // out
+  uint32_t* hlen = nullptr;              // in: where the header lengths go (nullable)
+  uint32_t rslot = 0;                    // in: 0 / 1
+  bool want_kmask = false;               // in
+  unsigned long long* kmask = nullptr;   // out
+  uint32_t tile_recs = 0;                // out
+  // match tables (enqueue_tabled): this mate's own, made by match_kernel (the launch then matches nothing itself),
+  // and the other mate's of the pair (keep rule)
+  const int32_t* tab_own = nullptr;
+  const unsigned long long* xtab = nullptr;  // with tab_own, for a parametric program
+  const int32_t* tab_other = nullptr;
+  DevBuf* scratch = nullptr;             // in: the launch's look-back state goes here instead of the slot's buffer ...
+  bk::DevResult* result = nullptr;       // in: ... and its figures into this result, which it does not reset
+  bool no_nout = false;                  // in: the other mate's launch counts the kept pairs
 };
 int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1,
                     const bk_mate_in* in2, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
                     int32_t* match1, int32_t* match2, uint32_t* launches, CoLaunch* co = nullptr);
+
+int enqueue_tabled(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2,
+                   uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2, int32_t* match1, int32_t* match2,
+                   uint32_t* launches);
+int enqueue_match(bk_ctx* ctx, int m, Slot* s, int ti, cudaStream_t stream, uint32_t n, const bk_mate_in* in,
+                  bk::DevResult* result, uint32_t* launches);
+// a mate whose pattern needs more than one anchored test per read
+bool is_hard(const bk_ctx* ctx, int m) {
+  const bk_devprog& pg = ctx->prog[m];
+  return pg.present && ((ctx->flags & BK_FLAG_RC) || ctx->var[m].size() > 1 || pg.nins > 0 || (!pg.anchor_start && !pg.anchor_end));
+}
+// parametric programs (unbounded repetition) are only ever matched by match_kernel
+bool is_parametric(const bk_ctx* ctx) { return ctx->prog[0].nins > 0 || ctx->prog[1].nins > 0; }
 
 // A paired launch with exactly one pattern, as two kernels (bk_compact.cuh): the single-end extract kernel on the
 // pattern's mate, leaving its match table and header lengths on the device, then the ordered compaction of the
@@ -256,8 +296,7 @@ int enqueue_split(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const b
   CoLaunch co;
   co.hlen = (uint32_t*)s->split_hlen.p;
   co.rslot = (uint32_t)pm;
-  co.kmask = nullptr;
-  co.tile_recs = 0;
+  co.want_kmask = true;
   rc = enqueue_extract(ctx->solo, s, stream, n, in[pm], nullptr, out[pm], cap[pm], nullptr, 0, user_match[pm], nullptr,
                        launches, &co);
   if (rc != BK_OK) { ctx->last_error = ctx->solo->last_error; return rc; }
@@ -298,7 +337,7 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
                     const bk_mate_in* in2, uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2,
                     int32_t* match1, int32_t* match2, uint32_t* launches, CoLaunch* co) {
   if (ctx->paired && !in2) { ctx->last_error = "paired context needs two mates"; return BK_E_ARG; }
-  if (ctx->paired && ctx->solo && !(ctx->flags & BK_FLAG_STAGE_BOTH_MATES))
+  if (ctx->paired && ctx->solo && (is_parametric(ctx) || !(ctx->flags & BK_FLAG_STAGE_BOTH_MATES)))
     return enqueue_split(ctx, s, stream, n, in1, in2, out1, cap1, out2, cap2, match1, match2, launches);
   if (!ctx->paired && in2) { ctx->last_error = "single-end context got two mates"; return BK_E_ARG; }
   const bk_mate_in* in[2] = {in1, in2};
@@ -314,20 +353,55 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     ctx->last_error = "output buffers must be 16-byte aligned";
     return BK_E_ARG;
   }
+  if (ctx->paired && ctx->view[0] && (is_hard(ctx, 0) || is_hard(ctx, 1)) &&
+      (is_parametric(ctx) || !(ctx->flags & (BK_FLAG_STAGE_BOTH_MATES | BK_FLAG_MATCH_IN_KERNEL))))
+    return enqueue_tabled(ctx, s, stream, n, in1, in2, out1, cap1, out2, cap2, match1, match2, launches);
+  // A single-end launch whose pattern needs a search: match_kernel first, this launch takes its matches from the table
+  // (unless the caller has done that already: enqueue_tabled)
+  const int32_t* self_tab = nullptr;
+  const unsigned long long* self_xtab = nullptr;
+  bk::DevResult* merr = nullptr;
+  // -- when its pattern is a list of variants or a parametric program: those matchers are lane-per-read loops that
+  // gain from match_kernel's occupancy (unanchored {m,n}: 1.75 x) and must not sit next to the emit code; a plain
+  // unanchored pattern or a -r retry is as fast or faster inside the extract kernel (one read of the text).
+  const bool self_match = !ctx->paired && n && !(co && co->tab_own) &&
+                          (ctx->prog[0].nins > 0 || (ctx->var[0].size() > 1 && !(ctx->flags & BK_FLAG_MATCH_IN_KERNEL)));
+  if (self_match) {
+    const int ti = co ? (int)co->rslot : 0;
+    int rcm;
+    if ((rcm = ensure(ctx, &s->tab_err, 64)) != BK_OK) return rcm;
+    merr = (bk::DevResult*)s->tab_err.p;
+    CK(cudaMemsetAsync(merr, 0, sizeof(bk::DevResult), stream));
+    if ((rcm = enqueue_match(ctx, 0, s, ti, stream, n, in1, merr, launches)) != BK_OK) return rcm;
+    self_tab = (const int32_t*)s->tab_match[ti].p;
+    self_xtab = (const unsigned long long*)s->tab_extras[ti].p;
+  }
   LaunchPlan lp;
-  const bool general = needs_general(ctx);
+  const bool table = self_tab || (co && co->tab_own);
+  const bool general = !table && needs_general(ctx);
   const bool var = has_variants(ctx);
+  // which instantiation: 0..5 as before, 6 / 7 = single-end with the matches taken from a table (plain / variants)
+  const int kid = table ? (var || ctx->prog[0].nins ? 7 : 6) : var ? (ctx->paired ? 0 : 1) : ctx->paired ? (general ? 2 : 3) : (general ? 4 : 5);
   bk::KParams P;
   memset(&P, 0, sizeof P);
-  int rc = var ? (ctx->paired ? plan_launch<true, true, true>(ctx, n, maxrec, &lp) : plan_launch<false, true, true>(ctx, n, maxrec, &lp))
-           : ctx->paired ? (general ? plan_launch<true, true>(ctx, n, maxrec, &lp) : plan_launch<true, false>(ctx, n, maxrec, &lp))
-                       : (general ? plan_launch<false, true>(ctx, n, maxrec, &lp) : plan_launch<false, false>(ctx, n, maxrec, &lp));
+  int rc;
+  switch (kid) {
+    case 0: rc = plan_launch<true, true, true>(ctx, n, maxrec, &lp); break;
+    case 1: rc = plan_launch<false, true, true>(ctx, n, maxrec, &lp); break;
+    case 2: rc = plan_launch<true, true>(ctx, n, maxrec, &lp); break;
+    case 3: rc = plan_launch<true, false>(ctx, n, maxrec, &lp); break;
+    case 4: rc = plan_launch<false, true>(ctx, n, maxrec, &lp); break;
+    case 5: rc = plan_launch<false, false>(ctx, n, maxrec, &lp); break;
+    case 6: rc = plan_launch<false, false, false, bk::kStages, true>(ctx, n, maxrec, &lp); break;
+    default: rc = plan_launch<false, false, true, bk::kStages, true>(ctx, n, maxrec, &lp); break;
+  }
   if (rc != BK_OK) return rc;
   const size_t kmask_off = (scratch_bytes(lp.ntiles) + 15) & ~size_t(15);  // (keep masks behind everything else)
-  const size_t sc_bytes = co ? kmask_off + (size_t)lp.ntiles * 8 : scratch_bytes(lp.ntiles);
-  rc = ensure(ctx, &s->scratch.buf, sc_bytes);
+  const size_t sc_bytes = co && co->want_kmask ? kmask_off + (size_t)lp.ntiles * 8 : scratch_bytes(lp.ntiles);
+  DevBuf* const scbuf = co && co->scratch ? co->scratch : &s->scratch.buf;
+  rc = ensure(ctx, scbuf, sc_bytes);
   if (rc != BK_OK) return rc;
-  uint8_t* sc = (uint8_t*)s->scratch.buf.p;
+  uint8_t* sc = (uint8_t*)scbuf->p;
   CK(cudaMemsetAsync(sc, 0, sc_bytes, stream));
 
   P.prog[0] = ctx->prog[0];
@@ -344,14 +418,20 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.out[0] = out1; P.out[1] = out2;
   P.cap[0] = cap1; P.cap[1] = cap2;
   P.match[0] = match1; P.match[1] = match2;
+  P.result = (bk::DevResult*)(sc + 64);
+  P.tab_in[0] = self_tab;
+  P.xtab = self_xtab;
   if (co) {
     P.hlen[0] = co->hlen;
     P.rslot = co->rslot;
-    P.kmask = co->kmask = (unsigned long long*)(sc + kmask_off);
+    if (co->want_kmask) P.kmask = co->kmask = (unsigned long long*)(sc + kmask_off);
     co->tile_recs = lp.tile_recs;
+    if (co->tab_own) { P.tab_in[0] = co->tab_own; P.xtab = co->xtab; }
+    P.tab_in[1] = co->tab_other;
+    P.no_nout = co->no_nout ? 1u : 0u;
+    if (co->result) P.result = co->result;
   }
   P.tile_counter = (unsigned int*)sc;
-  P.result = (bk::DevResult*)(sc + 64);
   P.prof = (unsigned long long*)(sc + events_offset(lp.ntiles));  // only written by a BK_PROFILE_PHASES build
   P.desc[0] = (unsigned long long*)(sc + 512);
   P.desc[1] = (unsigned long long*)(sc + block_desc_offset(lp.ntiles));
@@ -361,20 +441,132 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.tile_recs = lp.tile_recs;
   P.flags = ctx->flags;
   if (n > 0) {
-    if (var && ctx->paired)
-      bk::extract_kernel<true, true, true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
-    else if (var)
-      bk::extract_kernel<false, true, true><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
-    else if (ctx->paired && general)
-      bk::extract_kernel<true, true><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
-    else if (ctx->paired)
-      bk::extract_kernel<true, false><<<lp.grid, bk::cta_warps(true) * 32, lp.smem, stream>>>(P);
-    else if (general)
-      bk::extract_kernel<false, true><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
-    else
-      bk::extract_kernel<false, false><<<lp.grid, bk::cta_warps(false) * 32, lp.smem, stream>>>(P);
+    const int tp = bk::cta_warps(true) * 32, ts = bk::cta_warps(false) * 32;
+    switch (kid) {
+      case 0: bk::extract_kernel<true, true, true><<<lp.grid, tp, lp.smem, stream>>>(P); break;
+      case 1: bk::extract_kernel<false, true, true><<<lp.grid, ts, lp.smem, stream>>>(P); break;
+      case 2: bk::extract_kernel<true, true><<<lp.grid, tp, lp.smem, stream>>>(P); break;
+      case 3: bk::extract_kernel<true, false><<<lp.grid, tp, lp.smem, stream>>>(P); break;
+      case 4: bk::extract_kernel<false, true><<<lp.grid, ts, lp.smem, stream>>>(P); break;
+      case 5: bk::extract_kernel<false, false><<<lp.grid, ts, lp.smem, stream>>>(P); break;
+      case 6: bk::extract_kernel<false, false, false, bk::kStages, true><<<lp.grid, ts, lp.smem, stream>>>(P); break;
+      default: bk::extract_kernel<false, false, true, bk::kStages, true><<<lp.grid, ts, lp.smem, stream>>>(P); break;
+    }
+    if (merr) bk::merge_error_kernel<<<1, 1, 0, stream>>>(P.result, merr);
     CK(cudaGetLastError());
     if (launches) *launches += 1;
+  }
+  return BK_OK;
+}
+
+// match_kernel for one mate: its match table (start | variant << 24, or -1) into `table`
+// -> s->tab_match[ti] (and s->tab_extras[ti] for a parametric program)
+int enqueue_match(bk_ctx* ctx, int m, Slot* s, int ti, cudaStream_t stream, uint32_t n, const bk_mate_in* in,
+                  bk::DevResult* result, uint32_t* launches) {
+  int rce;
+  if ((rce = ensure(ctx, &s->tab_match[ti], ((size_t)n + 1) * 4)) != BK_OK) return rce;
+  if (ctx->prog[m].nins && (rce = ensure(ctx, &s->tab_extras[ti], ((size_t)n + 1) * 8)) != BK_OK) return rce;
+  if (n == 0) return BK_OK;
+  const uint32_t maxrec = in->max_rec_bytes;
+  // 32 reads per warp and two CTAs per SM while the records allow it; long records: fewer reads per tile, then fewer
+  // warps per CTA (one warp may take nearly all of the SM's shared memory)
+  const size_t half = (233472 / 2 - 2048) & ~size_t(127);
+  uint32_t R = bk::kTileRecs;
+  int W = bk::kMatchWarps;
+  auto cap_of = [&](uint32_t r) { return (uint32_t)(((size_t)r * maxrec + 48 + 15) & ~size_t(15)); };
+  while (R > 8 && (size_t)W * cap_of(R) + 64 > half) --R;
+  while (R > 1 && (size_t)W * cap_of(R) + 64 > kMaxDynSmem) --R;
+  while (W > 1 && (size_t)W * cap_of(R) + 64 > kMaxDynSmem) --W;
+  if ((size_t)W * cap_of(R) + 64 > kMaxDynSmem) {
+    ctx->last_error = "record too long for the on-chip staging buffer";
+    return BK_E_CAPACITY;
+  }
+  bk::MatchParams M;
+  memset(&M, 0, sizeof M);
+  M.prog = ctx->prog[m];
+  M.text = in->text;
+  M.off = in->rec_off;
+  M.match = (int32_t*)s->tab_match[ti].p;
+  M.extras = (unsigned long long*)s->tab_extras[ti].p;
+  M.result = result;
+  M.nvar = (uint32_t)ctx->var[m].size();
+  M.vprog = (const bk_devprog*)ctx->vdev[m].p;
+  M.n = n;
+  M.tile_recs = R;
+  M.ntiles = (n + R - 1) / R;
+  M.cap = cap_of(R);
+  M.rc = (ctx->flags & BK_FLAG_RC) ? 1u : 0u;
+  const size_t smem = (size_t)W * M.cap + 64;
+  CK(cudaFuncSetAttribute(bk::match_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(bk::match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::match_kernel, W * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = std::min<long long>((long long)per_sm * ctx->sm_count, ((long long)M.ntiles + W - 1) / W);
+  if (ctx->flags & BK_FLAG_VERBOSE)
+    fprintf(stderr, "[bk] match_kernel mate %d: tile_recs %u cap %u warps %d ctas/sm %d grid %lld\n", m + 1, R, M.cap, W, per_sm, grid);
+  bk::match_kernel<<<(int)std::max<long long>(grid, 1), W * 32, smem, stream>>>(M);
+  CK(cudaGetLastError());
+  if (launches) *launches += 1;
+  return BK_OK;
+}
+
+// A paired batch with two patterns of which at least one needs a search (not anchored, -r, variable repetition), as
+// separate launches on one stream: match_kernel on every such mate, then one single-end extract launch per mate.
+// A mate whose pattern is a plain anchored one is matched by its own extract launch, which runs first and leaves its
+// table for the other's keep rule (run.rs:149-160); a matched mate's launch takes its matches from the table.
+// Against the paired general kernel this reads a searched mate's text twice (once here, once staged for the emit),
+// and gains the single-end kernel's four CTAs per SM and an emit path without any search code next to it.
+int enqueue_tabled(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2,
+                   uint8_t* out1, uint64_t cap1, uint8_t* out2, uint64_t cap2, int32_t* match1, int32_t* match2,
+                   uint32_t* launches) {
+  const bk_mate_in* in[2] = {in1, in2};
+  uint8_t* const out[2] = {out1, out2};
+  const uint64_t cap[2] = {cap1, cap2};
+  int32_t* const user_match[2] = {match1, match2};
+  for (int m = 0; m < 2; ++m) {
+    if (!in[m] || !in[m]->text || !in[m]->rec_off) { ctx->last_error = "null batch pointer"; return BK_E_ARG; }
+    if (in[m]->text_len >= (1ull << 32)) { ctx->last_error = "batch text must be < 4 GiB per mate"; return BK_E_CAPACITY; }
+    if (((uintptr_t)in[m]->text & 15) != 0) { ctx->last_error = "batch text must be 16-byte aligned"; return BK_E_ARG; }
+    if (in[m]->max_rec_bytes == 0) { ctx->last_error = "max_rec_bytes must be set"; return BK_E_ARG; }
+  }
+  int rc;
+  for (int m = 0; m < 2; ++m)
+    if ((rc = ensure(ctx, &s->tab_match[m], ((size_t)n + 1) * 4)) != BK_OK) return rc;
+  if ((rc = ensure(ctx, &s->tab_err, 64)) != BK_OK) return rc;
+  for (int m = 0; m < 2; ++m)  // (before the table pointers are taken: enqueue_match only finds them large enough)
+    if (ctx->prog[m].nins && (rc = ensure(ctx, &s->tab_extras[m], ((size_t)n + 1) * 8)) != BK_OK) return rc;
+  const bool hard[2] = {is_hard(ctx, 0), is_hard(ctx, 1)};
+  const int first = hard[0] && !hard[1] ? 1 : 0;  // the mate whose extract launch runs first
+  int32_t* const tab[2] = {(int32_t*)s->tab_match[0].p, (int32_t*)s->tab_match[1].p};
+  // 1. the matchers.  They run before the launch that resets the batch's result, so a tile that does not fit their
+  // buffers is flagged in a result of their own and merged at the end.
+  bk::DevResult* const merr = (bk::DevResult*)s->tab_err.p;
+  CK(cudaMemsetAsync(merr, 0, sizeof(bk::DevResult), stream));
+  for (int m = 0; m < 2; ++m)
+    if (hard[m] && (rc = enqueue_match(ctx, m, s, m, stream, n, in[m], merr, launches)) != BK_OK) return rc;
+  // 2. one single-end extract launch per mate
+  for (int k = 0; k < 2; ++k) {
+    const int m = k == 0 ? first : 1 - first;
+    CoLaunch co;
+    co.rslot = (uint32_t)m;
+    co.tab_other = tab[1 - m];
+    co.tab_own = hard[m] ? tab[m] : nullptr;
+    co.xtab = (const unsigned long long*)s->tab_extras[m].p;
+    if (k == 1) {
+      co.scratch = &s->split_scratch;
+      co.result = (bk::DevResult*)((uint8_t*)s->scratch.buf.p + 64);  // the first launch's, which has reset it
+      co.no_nout = true;
+    }
+    // a mate that matches for itself leaves its table for the other's keep rule
+    int32_t* const mout = hard[m] ? user_match[m] : tab[m];
+    rc = enqueue_extract(ctx->view[m], s, stream, n, in[m], nullptr, out[m], cap[m], nullptr, 0, mout, nullptr, launches, &co);
+    if (rc != BK_OK) { ctx->last_error = ctx->view[m]->last_error; return rc; }
+    if (!hard[m] && user_match[m] && n) CK(cudaMemcpyAsync(user_match[m], tab[m], (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (n) {
+    bk::merge_error_kernel<<<1, 1, 0, stream>>>((bk::DevResult*)((uint8_t*)s->scratch.buf.p + 64), merr);
+    CK(cudaGetLastError());
   }
   return BK_OK;
 }
@@ -511,6 +703,22 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
     if (!(flags & BK_FLAG_DEVICE_BOTH_MATES)) ctx->pass_mate = 1 - pm;
     ctx->pass_pinned = (flags & BK_FLAG_HOST_MATE_PINNED) != 0;
   }
+  if (ctx->paired && p1 && p2) {
+    for (int m = 0; m < 2; ++m) {  // single-end views of the two mates (enqueue_tabled)
+      bk_ctx* v = new (std::nothrow) bk_ctx();
+      if (!v) { bk_ctx_destroy(ctx); return fail(BK_E_CAPACITY, "out of memory"); }
+      v->device = device;
+      v->flags = flags & ~(uint32_t)(BK_FLAG_PAIRED | BK_FLAG_DEVICE_BOTH_MATES | BK_FLAG_HOST_MATE_PINNED | BK_FLAG_STAGE_BOTH_MATES);
+      v->paired = false;
+      v->sm_count = ctx->sm_count;
+      memset(v->prog, 0, sizeof v->prog);
+      v->prog[0] = ctx->prog[m];
+      v->var[0] = ctx->var[m];
+      v->vdev[0] = ctx->vdev[m];  // (shared, owned by ctx)
+      v->growth[0] = ctx->growth[m];
+      ctx->view[m] = v;
+    }
+  }
   ctx->host_threads = std::max(1, std::min((int)std::thread::hardware_concurrency(), 32));
   if (status) *status = BK_OK;
   if (err && errcap) err[0] = 0;
@@ -535,6 +743,11 @@ void bk_ctx_destroy(bk_ctx* ctx) {
     if (s.split_match.p) cudaFree(s.split_match.p);
     if (s.split_hlen.p) cudaFree(s.split_hlen.p);
     if (s.split_scratch.p) cudaFree(s.split_scratch.p);
+    if (s.tab_err.p) cudaFree(s.tab_err.p);
+    for (int m = 0; m < 2; ++m) {
+      if (s.tab_match[m].p) cudaFree(s.tab_match[m].p);
+      if (s.tab_extras[m].p) cudaFree(s.tab_extras[m].p);
+    }
     for (int m = 0; m < 2; ++m)
       if (s.tok[m].p) cudaFree(s.tok[m].p);
     if (s.h_res) cudaFreeHost(s.h_res);
@@ -548,6 +761,8 @@ void bk_ctx_destroy(bk_ctx* ctx) {
   for (int m = 0; m < 2; ++m)
     if (ctx->vdev[m].p) cudaFree(ctx->vdev[m].p);
   delete ctx->solo;
+  delete ctx->view[0];
+  delete ctx->view[1];
   delete ctx;
 }
 
@@ -620,7 +835,8 @@ uint64_t bk_out_bound(const bk_ctx* ctx, int mate, uint32_t n, uint64_t text_len
   if (!ctx || mate < 1 || mate > 2) return 0;
   const bk_devprog& pg = ctx->prog[mate - 1];
   // out record <= in record + 1 (a final record without EOL gains one) + header growth
-  return text_len + (uint64_t)n * ((pg.present ? ctx->growth[mate - 1] : 0) + 1) + 16;
+  // (a parametric program: its captures may also grow by the read's own bytes, par_growth summed over the records)
+  return text_len + (uint64_t)n * ((pg.present ? ctx->growth[mate - 1] : 0) + 1) + 16 + (pg.present ? par_growth(pg, text_len) : 0);
 }
 
 int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2) {

@@ -96,6 +96,35 @@ __device__ __noinline__ ulonglong2 lookback(unsigned long long* tdesc, unsigned 
   return make_ulonglong2(e0, e1);
 }
 
+// A mate's lookup block in shared memory (layout: bk_kernels.cuh, kTabComp .. kTabSA), filled by one warp.
+__device__ __forceinline__ void fill_tab(uint8_t* t, const bk_devprog& pg, int lane, bool general) {
+  // byte -> "which classes contain it" table, so a class test is one shared-memory lookup
+  for (int c = lane; c < 256; c += 32) {
+    uint32_t mask = 0;
+    if (c < 128)
+      for (int k = 0; k < BK_MAX_CLASSES; ++k) mask |= ((pg.cls[k][c >> 5] >> (c & 31)) & 1u) << k;
+    t[c] = (uint8_t)mask;
+    t[kTabComp + c] = (uint8_t)complement((uint32_t)c);
+  }
+  // ... and the program behind them (layout: kTabHdr, kTabOps, kTabLit)
+  uint32_t* const tw = reinterpret_cast<uint32_t*>(t);
+  if (lane == 0) {
+    tw[kTabHdr / 4 + 0] = pg.nops;
+    tw[kTabHdr / 4 + 1] = pg.total_len;
+    tw[kTabHdr / 4 + 2] = pg.anchor_start;
+    tw[kTabHdr / 4 + 3] = pg.anchor_end;
+  }
+  for (int i = lane; i < 2 * BK_MAX_OPS; i += 32) tw[kTabOps / 4 + i] = reinterpret_cast<const uint32_t*>(pg.ops)[i];
+  for (int i = lane; i < BK_MAX_LIT / 4; i += 32) tw[kTabLit / 4 + i] = reinterpret_cast<const uint32_t*>(pg.lit)[i];
+  if (lane == 0) tw[kTabIns / 4] = pg.nins;  // parametric programs: the insertion points (match_par)
+  if (lane < 2 * BK_MAX_INS) tw[kTabIns / 4 + 2 + lane] = reinterpret_cast<const uint32_t*>(pg.ins)[lane];
+  if (general && lane < 8) {  // bit planes of the first literal (match_unanchored): bits 1 and 2 of byte `lane`
+    const uint32_t c = pg.nops && pg.ops[0].kind == BK_OP_LIT ? (uint32_t)pg.lit[pg.ops[0].idx + lane] : 0u;
+    tw[kTabSA / 4 + 2 * lane] = (c & 2u) ? 0xFFFFFFFFu : 0u;
+    tw[kTabSA / 4 + 2 * lane + 1] = (c & 4u) ? 0xFFFFFFFFu : 0u;
+  }
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------
 //
 // One LOADER warp per CTA feeds a ring of kStages staged input tiles per mate (one mate for
@@ -169,9 +198,14 @@ __host__ __device__ constexpr int cta_warps(bool paired) { return (paired ? 2 : 
 // VAR (only with GENERAL): a mate's pattern may be a list of fixed-length variants (bounded variable
 // repetition, bk_pattern.cc); the matched variant travels with the match start (start | variant << 24) and
 // supplies the capture offsets, the match length and the header growth of that record.
-template <bool PAIRED, bool GENERAL, bool VAR = false, int ST = kStages>
+// TABLE (single-end launches only): nothing is matched here -- the read's match (start | variant << 24, or -1) was
+// left in P.tab_in[0] by match_kernel (bk_match.cuh) earlier in the stream, so this instantiation carries no search
+// code at all.  Independently of TABLE, a single-end launch that is one mate of a pair takes the OTHER mate's match
+// table from P.tab_in[1] for the keep rule (run.rs:149-160).
+template <bool PAIRED, bool GENERAL, bool VAR = false, int ST = kStages, bool TABLE = false>
 __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extract_kernel(const __grid_constant__ KParams P) {
-  static_assert(!VAR || GENERAL, "variants are matched by the general kernel");
+  static_assert(!VAR || GENERAL || TABLE, "variants are matched by the general kernel or by match_kernel");
+  static_assert(!TABLE || (!PAIRED && !GENERAL), "a launch that takes its matches from a table is single-end and has no search code");
   constexpr int kFrontPairs = PAIRED ? 2 : BK_SE_FRONTS;
   static_assert(ST % kScanWarps == 0 && ST % kFrontPairs == 0 && 4 + 2 * ST + (PAIRED ? 1 : 0) <= 16, "ring depth: a multiple of the scan / front warp counts, and 16 named barriers");
   extern __shared__ __align__(128) uint8_t smem[];
@@ -218,29 +252,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
   const uint32_t tab = smem_u32(&cls_tab[m][0]);
 
   if (is_front && fp == 0) {
-    // byte -> "which classes contain it" table, so a class test is one shared-memory lookup
-    for (int c = lane; c < 256; c += 32) {
-      uint32_t mask = 0;
-      if (c < 128)
-        for (int k = 0; k < BK_MAX_CLASSES; ++k) mask |= ((pg.cls[k][c >> 5] >> (c & 31)) & 1u) << k;
-      cls_tab[m][c] = (uint8_t)mask;
-      cls_tab[m][kTabComp + c] = (uint8_t)complement((uint32_t)c);
-    }
-    // ... and the program behind them (layout: kTabHdr, kTabOps, kTabLit)
-    uint32_t* const tw = reinterpret_cast<uint32_t*>(&cls_tab[m][0]);
-    if (lane == 0) {
-      tw[kTabHdr / 4 + 0] = pg.nops;
-      tw[kTabHdr / 4 + 1] = pg.total_len;
-      tw[kTabHdr / 4 + 2] = pg.anchor_start;
-      tw[kTabHdr / 4 + 3] = pg.anchor_end;
-    }
-    for (int i = lane; i < 2 * BK_MAX_OPS; i += 32) tw[kTabOps / 4 + i] = reinterpret_cast<const uint32_t*>(pg.ops)[i];
-    for (int i = lane; i < BK_MAX_LIT / 4; i += 32) tw[kTabLit / 4 + i] = reinterpret_cast<const uint32_t*>(pg.lit)[i];
-    if (GENERAL && lane < 8) {  // bit planes of the first literal (match_unanchored): bits 1 and 2 of byte `lane`
-      const uint32_t c = pg.nops && pg.ops[0].kind == BK_OP_LIT ? (uint32_t)pg.lit[pg.ops[0].idx + lane] : 0u;
-      tw[kTabSA / 4 + 2 * lane] = (c & 2u) ? 0xFFFFFFFFu : 0u;
-      tw[kTabSA / 4 + 2 * lane + 1] = (c & 4u) ? 0xFFFFFFFFu : 0u;
-    }
+    if (!TABLE) fill_tab(&cls_tab[m][0], pg, lane, GENERAL);
     if (lane == 0)
       for (int s = 0; s < ST; ++s) {
         mbar_init(&bar_full[m][s], 1);
@@ -366,6 +378,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       const uint32_t nrec = tm.nrec;
       const bool active = lane < (int)nrec;
       const bool too_big = tm.too_big != 0;
+      int t_own = -1, t_oth = -1;  // match tables of earlier launches (issued here: the loads overlap the parse)
+      if (!PAIRED) {
+        if (TABLE && active) t_own = __ldg(P.tab_in[0] + r0 + lane);
+        if (P.tab_in[1] && active) t_oth = __ldg(P.tab_in[1] + r0 + lane);
+      }
       RecView rv;
       rv.beg = rv.end = rv.fast = rv.head_len = rv.seq = rv.seq_len = rv.qual = rv.qual_len = 0;
       int ms = -1;
@@ -375,7 +392,9 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         __syncwarp();
         if (m == 0) { EVT(tile, 4) }
         const bool can = active && pg.present && rv.qual_len == rv.seq_len;  // unequal lengths never leave bk_tokenize
-        if (VAR && var_me) {  // (lane per read, bytewise: see match_variants)
+        if (TABLE) {
+          ms = t_own;
+        } else if (VAR && var_me) {  // (lane per read, bytewise: see match_variants)
           if (can) {
             ms = match_variants<false>(P.vprog[m], P.nvar[m], tab, rv.seq, rv.seq_len);
             if (ms < 0 && rc) {
@@ -395,7 +414,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         } else if (can) {
           ms = GENERAL ? match_read_shared(tab, rv.seq, rv.seq_len) : match_read<false>(tab, rv.seq, rv.seq_len);  // lane per read
         }
-        if (GENERAL && !(VAR && var_me) && can && ms < 0 && rc) {  // parse.rs:61-66
+        if (GENERAL && !TABLE && !(VAR && var_me) && can && ms < 0 && rc) {  // parse.rs:61-66
           ms = match_read<true>(tab, rv.seq, rv.seq_len);
           if (ms >= 0 && !caps_utf8_ok(pg, rv.seq, (uint32_t)ms)) ms = -1;
         }
@@ -416,7 +435,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       __syncwarp();
       if (m == 0) { EVT(tile, 5) }
       // ---- exchange match decisions with the other mate's front warp -----------------------------
-      int ms_other = -1;
+      int ms_other = PAIRED ? -1 : t_oth;
       bool skip = too_big;
       if (PAIRED) {
         s_ms[fp][xb][m][lane] = too_big ? kSkipTile : ms;
@@ -439,7 +458,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
 
       // ---- size + scan, publish the aggregate -------------------------------------------------------
       const bk_devprog& pe = (VAR && var_me && ms >= 0) ? P.vprog[m][ms >> 24] : pg;  // the record's variant
-      const uint32_t olen = keep ? out_bytes(pe, rv, ms, trim) : 0;
+      uint32_t olen = keep ? out_bytes(pe, rv, ms, trim) : 0;
+      if (VAR && TABLE && pg.nins && keep && ms >= 0) {  // a parametric program: this record's own lengths
+        const EmitProg ep = emit_prog(pg, P.xtab[r0 + lane]);
+        olen = out_bytes(ep, rv, ms, trim);
+      }
       uint32_t incl = olen;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -482,7 +505,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
     {  // statistics of this warp's tiles
       const uint32_t nk = __reduce_add_sync(0xffffffffu, n_kept), nm = __reduce_add_sync(0xffffffffu, n_matched);
       if (lane == 0) {
-        if (m == 0 && nk) atomicAdd(&P.result->n_out, (unsigned long long)nk);
+        if (m == 0 && nk && !P.no_nout) atomicAdd(&P.result->n_out, (unsigned long long)nk);
         if (nm) atomicAdd(&P.result->n_match[m + P.rslot], (unsigned long long)nm);
       }
     }
@@ -552,7 +575,12 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         const uint32_t nxt = __shfl_down_sync(0xffffffffu, ooff, 1);
         const bool even = kept && lane < 31 && nxt != kNotKept && ((nxt - ooff) & 31u) == 0;
         const uint32_t rot = __popc(__ballot_sync(0xffffffffu, even)) >= 8 ? ((uint32_t)lane & 7u) + 1u : 0u;
-        if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
+        if (VAR && TABLE && pg.nins) {
+          if (kept && !unc) {
+            const EmitProg ep = emit_prog(pg, ms >= 0 ? P.xtab[tile * R + lane] : 0ull);
+            emit_part(ep, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
+          }
+        } else if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
         // warp per pass: maximal runs of consecutive unchanged records
         const unsigned um = __ballot_sync(0xffffffffu, unc);
         if (um) {

@@ -65,6 +65,12 @@ struct KParams {
   // mate's figures in `result` (0, or 1 when it works on the second mate of a pair).
   unsigned long long* kmask;
   uint32_t rslot;
+  // Optional (single-end launches): match tables left by earlier launches on the stream -- [0] this mate's own
+  // (extract_kernel<.., TABLE = true> matches nothing itself), [1] the other mate's of the pair (keep rule); and
+  // whether this launch leaves the count of kept pairs to the other mate's launch.
+  const int32_t* tab_in[2];
+  const unsigned long long* xtab;  // with tab_in[0], parametric programs: the extras of every match (match_kernel)
+  uint32_t no_nout;
 };
 
 constexpr unsigned long long kFlagAgg = 1ull << 62;
@@ -380,7 +386,8 @@ __device__ __forceinline__ uint32_t complement(uint32_t c) {
 // generic-address load with global-memory latency.
 constexpr uint32_t kTabComp = 256, kTabHdr = 512, kTabOps = 528, kTabLit = kTabOps + 8u * BK_MAX_OPS;
 constexpr uint32_t kTabSA = kTabLit + BK_MAX_LIT;  // 8 x 2 words: bit planes of the program's first literal (match_unanchored)
-constexpr uint32_t kTabBytes = kTabSA + 64u;
+constexpr uint32_t kTabIns = kTabSA + 64u;  // nins, pad, then BK_MAX_INS x bk_ins (8 bytes each): parametric programs (match_par)
+constexpr uint32_t kTabBytes = kTabIns + 8u + 8u * BK_MAX_INS;
 struct MOp { uint32_t off, len, kind, k, idx; };
 __device__ __forceinline__ MOp tab_op(uint32_t tab, uint32_t o) {  // bk_op, little endian
   const uint2 v = lds64(tab + kTabOps + 8u * o);
@@ -521,9 +528,8 @@ __device__ __noinline__ int match_read(uint32_t tab, uint32_t seq, uint32_t L) {
 // a byte >= 0x80 matches nothing), but a reverse-complement match is found on the complemented text -- where every
 // byte is a letter -- and its offsets are then applied to the FORWARD read (parse.rs:58-68), so it can.
 // Well-formed = Unicode table 3-7; the capture is validated on its own, so a sequence cut off by its end is ill-formed.
-__device__ __noinline__ bool caps_utf8_ok(const bk_devprog& pg, uint32_t seq, uint32_t ms) {
-  for (uint32_t c = 0; c < pg.ncaps; ++c) {
-    const uint32_t b = seq + ms + pg.caps[c].off, e = b + pg.caps[c].len;
+__device__ __noinline__ bool span_utf8_ok(uint32_t b, uint32_t e) {
+  {
     for (uint32_t i = b; i < e;) {
       const uint32_t x = lds8(i);
       if (x < 0x80u) { ++i; continue; }
@@ -546,6 +552,50 @@ __device__ __noinline__ bool caps_utf8_ok(const bk_devprog& pg, uint32_t seq, ui
     }
   }
   return true;
+}
+__device__ __forceinline__ bool caps_utf8_ok(const bk_devprog& pg, uint32_t seq, uint32_t ms) {
+  for (uint32_t c = 0; c < pg.ncaps; ++c) {
+    const uint32_t b = seq + ms + pg.caps[c].off;
+    if (!span_utf8_ok(b, b + pg.caps[c].len)) return false;
+  }
+  return true;
+}
+// capture c of a parametric program under the extras `ex` (16 bits per insertion): insertions in front of the group
+// move it, insertions inside it lengthen it
+__device__ __forceinline__ void par_cap(const bk_devprog& pg, uint32_t c, unsigned long long ex, uint32_t& off, uint32_t& len) {
+  off = pg.caps[c].off;
+  len = pg.caps[c].len;
+  for (uint32_t i = 0; i < pg.nins; ++i) {
+    const uint32_t e = (uint32_t)(ex >> (16u * i)) & 0xFFFFu;
+    if (i < pg.cap_ins_before[c]) off += e;
+    else if ((pg.ins[i].capmask >> c) & 1u) len += e;
+  }
+}
+// what emit_part and out_bytes read of a program; for a parametric one, the record's own figures
+struct EmitProg {
+  uint32_t ncaps, hdr_growth, total_len;
+  bk_cap caps[BK_MAX_CAPS];
+};
+__device__ __forceinline__ EmitProg emit_prog(const bk_devprog& pg, unsigned long long ex) {
+  EmitProg ep;
+  ep.ncaps = pg.ncaps;
+  ep.hdr_growth = pg.hdr_growth;
+  ep.total_len = pg.total_len;
+#pragma unroll
+  for (uint32_t c = 0; c < BK_MAX_CAPS; ++c) ep.caps[c] = pg.caps[c];
+  if (pg.nins) {
+    for (uint32_t i = 0; i < pg.nins; ++i) ep.total_len += (uint32_t)(ex >> (16u * i)) & 0xFFFFu;
+#pragma unroll
+    for (uint32_t c = 0; c < BK_MAX_CAPS; ++c)
+      if (c < pg.ncaps) {
+        uint32_t off, len;
+        par_cap(pg, c, ex, off, len);
+        ep.hdr_growth += 2u * (len - ep.caps[c].len);
+        ep.caps[c].off = (uint16_t)off;
+        ep.caps[c].len = (uint16_t)len;
+      }
+  }
+  return ep;
 }
 
 // ---- variable repetition: a program given as a list of fixed-length variants ------------------------------
@@ -594,6 +644,101 @@ __device__ __noinline__ int match_variants(const bk_devprog* vp, uint32_t nvar, 
       if (match_at_variant<RC>(pv, tab, seq, L, s)) { best = s | (v << 24); break; }
   }
   return (int)best;  // 0xFFFFFFFF = -1: no variant matches
+}
+
+// ---- variable repetition without a small bound: a parametric program (bk_program.h, bk_ins) ----------------
+//
+// The pattern is S_0 X_0{e_0} S_1 X_1{e_1} .. S_Q with fixed pieces S_j (the ops of segment j, laid out with every
+// atom at its minimum count) and e_i in [0, max_extra_i] further copies of the one-byte atom X_i.  The regex crate's
+// leftmost-first match is the backtracking one: the smallest start s, and for it the first (e_0, .., e_{Q-1}) in
+// priority order -- e_0 outermost, each from its longest run down (greedy) or from 0 up (lazy) -- under which all
+// pieces match (and the match ends at the read's end when the pattern is `$`-anchored).  One lane per read, bytewise
+// (fetch<RC>: also on the reverse complement), depth-first with an explicit stack: a piece is compared once the
+// extras in front of it are chosen, so a failing piece prunes everything behind it.  Returns the start or -1 and the
+// chosen extras, 16 bits each.
+template <bool RC>
+__device__ __forceinline__ bool par_segment_ok(uint32_t tab, uint32_t seq, uint32_t L, uint32_t o0, uint32_t o1, uint32_t base) {
+  for (uint32_t o = o0; o < o1; ++o) {
+    const MOp op = tab_op(tab, o);
+    const uint32_t b = base + op.off;
+    if (op.kind == BK_OP_LIT) {
+      uint32_t mism = 0, bad = 0;
+      for (uint32_t i = 0; i < op.len; ++i) {
+        const uint32_t c = fetch<RC>(tab, seq, L, b + i);
+        const uint32_t ne = (c != lds8(tab + kTabLit + op.idx + i));
+        mism += ne;
+        bad |= ne & (uint32_t)((c >= 0x80u) | (c == '\n'));
+      }
+      if (mism > op.k || bad) return false;
+    } else {
+      for (uint32_t i = 0; i < op.len; ++i)
+        if (!((lds8(tab + fetch<RC>(tab, seq, L, b + i)) >> op.idx) & 1u)) return false;
+    }
+  }
+  return true;
+}
+
+template <bool RC>
+__device__ __noinline__ int match_par(uint32_t tab, uint32_t seq, uint32_t L, unsigned long long* extras) {
+  const uint4 h = lds128(tab + kTabHdr);  // nops, total_len (minimum), anchor_start, anchor_end
+  const uint32_t nops = h.x, T = h.y, nins = lds32(tab + kTabIns);
+  *extras = 0ull;
+  if (L < T) return -1;
+  const uint32_t s_last = h.z ? 0u : L - T;
+  for (uint32_t s = 0; s <= s_last; ++s) {
+    uint32_t e[BK_MAX_INS], r[BK_MAX_INS];
+    uint32_t shift = 0, d = 0;
+    if (!par_segment_ok<RC>(tab, seq, L, 0u, nins ? (lds32(tab + kTabIns + 8u + 4u) >> 24) : nops, s)) continue;
+    bool enter = true, found = false;
+    while (true) {
+      if (enter) {
+        if (d == nins) {
+          if (!h.w || s + T + shift == L) { found = true; break; }
+          enter = false;  // `$`: the match must end with the read
+          if (d == 0) break;
+          --d;
+          shift -= e[d];
+          continue;
+        }
+        // longest run of the atom at this insertion, as far as the rest of the minimum still fits the read
+        const uint2 in = lds64(tab + kTabIns + 8u + 8u * d);  // pos | max_extra << 16, cls | lazy << 8 | capmask << 16 | op_end << 24
+        const uint32_t a = s + (in.x & 0xFFFFu) + shift, room = L - (s + T + shift);
+        const uint32_t lim = min(in.x >> 16, room), cls = in.y & 0xFFu;
+        uint32_t run = 0;
+        while (run < lim && ((lds8(tab + fetch<RC>(tab, seq, L, a + run)) >> cls) & 1u)) ++run;
+        r[d] = run;
+        e[d] = ((in.y >> 8) & 0xFFu) ? 0u : run;
+      } else {
+        // next choice at level d, or give the level up
+        const uint32_t lazy = (lds32(tab + kTabIns + 8u + 8u * d + 4u) >> 8) & 0xFFu;
+        if (lazy ? e[d] < r[d] : e[d] > 0u) {
+          e[d] = lazy ? e[d] + 1u : e[d] - 1u;
+        } else {
+          if (d == 0) break;
+          --d;
+          shift -= e[d];
+          continue;
+        }
+      }
+      // the piece behind insertion d under this choice
+      const uint32_t o0 = lds32(tab + kTabIns + 8u + 8u * d + 4u) >> 24;
+      const uint32_t o1 = d + 1u < nins ? lds32(tab + kTabIns + 8u + 8u * (d + 1u) + 4u) >> 24 : nops;
+      if (par_segment_ok<RC>(tab, seq, L, o0, o1, s + shift + e[d])) {
+        shift += e[d];
+        ++d;
+        enter = true;
+      } else {
+        enter = false;
+      }
+    }
+    if (found) {
+      unsigned long long x = 0;
+      for (uint32_t i = 0; i < nins; ++i) x |= (unsigned long long)e[i] << (16u * i);
+      *extras = x;
+      return (int)s;
+    }
+  }
+  return -1;
 }
 
 // Unanchored forward search (pattern.rs:225-230: the leftmost start at which the whole program passes).
@@ -716,7 +861,8 @@ __device__ __noinline__ int match_unanchored(uint32_t tab, uint32_t seq, uint32_
 // ---- emit ----------------------------------------------------------------------------------------------
 
 // output bytes of a kept record (qual_len == seq_len whenever ms >= 0, see emit_part)
-__device__ __forceinline__ uint32_t out_bytes(const bk_devprog& pg, const RecView& r, int ms, bool trim) {
+template <class PG>
+__device__ __forceinline__ uint32_t out_bytes(const PG& pg, const RecView& r, int ms, bool trim) {
   uint32_t sl = r.seq_len, ql = r.qual_len, g = 0;
   if (ms >= 0) {
     g = pg.hdr_growth;  // sum of " NAME:" seq ":" qual   (parse.rs:161-168)
@@ -925,7 +1071,8 @@ constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is
 // whole words.  (A record that is copied unchanged and already has the writer's framing is not
 // written here but as part of a run, see bulk16.)  Requires qual_len == seq_len for matched records
 // (the front warp treats anything else as unmatched; bk_tokenize never produces it).
-__device__ __forceinline__ void emit_part(const bk_devprog& pg, const RecView& r, int ms, bool trim, uint32_t d,
+template <class PG>
+__device__ __forceinline__ void emit_part(const PG& pg, const RecView& r, int ms, bool trim, uint32_t d,
                                           uint32_t part, uint32_t nparts, uint32_t rot) {
   OutStream o;
   // jobs of this part, bit 0 = A ... bit 4 = E

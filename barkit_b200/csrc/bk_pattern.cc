@@ -157,8 +157,13 @@ struct Lowering {
   std::vector<Pos> pos;
   std::vector<Class128> classes;
   std::vector<size_t> group_k;           // per fuzzy group
-  struct CapRec { std::string name; size_t off, len; };
+  struct CapRec { std::string name; size_t off, len; size_t ins_before = 0; };
   std::vector<CapRec> caps;
+  // variable repetition of a one-byte atom, kept as an insertion point (parametric lowering, compile_par below)
+  bool allow_var = false;
+  struct InsRec { size_t pos; long max_extra; bool lazy; int cls; uint32_t capmask; };
+  std::vector<InsRec> ins;
+  std::vector<size_t> open_caps;  // named groups the parser is inside of
   std::string err;
   int status = BK_OK;
 
@@ -194,29 +199,61 @@ struct Lowering {
     return (int)classes.size() - 1;
   }
 
-  // Parses `{n}` at s[i] if present.  Returns false on error.  *rep = -1 when there is no
-  // repetition operator at i.
-  bool parse_repeat(size_t& i, long* rep) {
+  // Parses a repetition operator at s[i] if present.  Returns false on error.  *rep = -1 when there is none, n for
+  // `{n}`; any other operator is variable repetition: refused unless allow_var, else *rep = -2 and [*lo, *hi]
+  // (*hi = -1: unbounded), *lazy.
+  bool parse_repeat(size_t& i, long* rep, long* lo, long* hi, bool* lazy) {
     *rep = -1;
+    *lazy = false;
     if (i >= s.size()) return true;
     char c = s[i];
-    if (c == '?' || c == '*' || c == '+') return unsupported(std::string("repetition operator ") + c);
-    if (c != '{') return true;
-    size_t j = i + 1;
-    long v = 0;
-    size_t digits = 0;
-    while (j < s.size() && s[j] >= '0' && s[j] <= '9') {
-      v = v * 10 + (s[j] - '0');
-      if (v > BK_MAX_TOTAL_LEN) return unsupported("repetition count too large");
-      ++j; ++digits;
+    if (c == '?' || c == '*' || c == '+') {
+      if (!allow_var) return unsupported(std::string("repetition operator ") + c);
+      *lo = c == '+' ? 1 : 0;
+      *hi = c == '?' ? 1 : -1;
+      ++i;
+    } else if (c == '{') {
+      size_t j = i + 1;
+      long v = 0;
+      size_t digits = 0;
+      while (j < s.size() && s[j] >= '0' && s[j] <= '9') {
+        v = v * 10 + (s[j] - '0');
+        if (v > BK_MAX_TOTAL_LEN) return unsupported("repetition count too large");
+        ++j; ++digits;
+      }
+      if (digits == 0) return regex_error("repetition quantifier expects a valid decimal");
+      if (j < s.size() && s[j] == ',') {
+        if (!allow_var) return unsupported("{m,n} variable repetition");
+        ++j;
+        long w = 0;
+        size_t d2 = 0;
+        while (j < s.size() && s[j] >= '0' && s[j] <= '9') {
+          w = w * 10 + (s[j] - '0');
+          if (w > 60000) return unsupported("repetition count too large");
+          ++j; ++d2;
+        }
+        if (j >= s.size() || s[j] != '}') return regex_error("unclosed counted repetition");
+        if (d2 && w < v) return regex_error("invalid repetition count range, the start must be <= the end");
+        *lo = v;
+        *hi = d2 ? w : -1;
+        i = j + 1;
+      } else {
+        if (j >= s.size() || s[j] != '}') return regex_error("unclosed counted repetition");
+        i = j + 1;
+        if (allow_var && i < s.size() && s[i] == '?') ++i;  // `{n}?`: laziness changes nothing
+        if (i < s.size() && (s[i] == '?' || s[i] == '*' || s[i] == '+' || s[i] == '{'))
+          return unsupported("stacked repetition / lazy quantifier");
+        *rep = v;
+        return true;
+      }
+    } else {
+      return true;
     }
-    if (digits == 0) return regex_error("repetition quantifier expects a valid decimal");
-    if (j < s.size() && s[j] == ',') return unsupported("{m,n} variable repetition");
-    if (j >= s.size() || s[j] != '}') return regex_error("unclosed counted repetition");
-    i = j + 1;
+    if (i < s.size() && s[i] == '?') { *lazy = true; ++i; }
     if (i < s.size() && (s[i] == '?' || s[i] == '*' || s[i] == '+' || s[i] == '{'))
-      return unsupported("stacked repetition / lazy quantifier");
-    *rep = v;
+      return unsupported("stacked repetition");
+    if (*hi == *lo) { *rep = *lo; return true; }  // `{n,n}`
+    *rep = -2;
     return true;
   }
 
@@ -268,7 +305,7 @@ struct Lowering {
         return true;
       }
       size_t item_begin = pos.size();
-      bool item_named = false;
+      bool item_named = false, item_group = false;
       if (const FuzzySpan* f = span_at(i)) {
         int g = (int)group_k.size();
         group_k.push_back(f->k);
@@ -304,14 +341,19 @@ struct Lowering {
         size_t cap_slot = 0;
         if (named) {
           cap_slot = caps.size();
-          caps.push_back({name, pos.size(), 0});  // pattern order = order of opening parens
+          caps.push_back({name, pos.size(), 0, ins.size()});  // pattern order = order of opening parens
           item_named = true;
+          open_caps.push_back(cap_slot);
         }
         bool inner_named = false;
+        item_group = true;
         if (!parse_seq(i, depth + 1, &inner_named)) return false;
         if (i >= s.size() || s[i] != ')') return regex_error("unclosed group");
         ++i;
-        if (named) caps[cap_slot].len = pos.size() - caps[cap_slot].off;
+        if (named) {
+          caps[cap_slot].len = pos.size() - caps[cap_slot].off;
+          open_caps.pop_back();
+        }
         item_named = item_named || inner_named;
       } else if (c == '[') {
         Class128 cl;
@@ -339,9 +381,33 @@ struct Lowering {
         ++i;
       }
       if (item_named && has_named) *has_named = true;
-      long rep;
-      if (!parse_repeat(i, &rep)) return false;
-      if (rep >= 0 && rep != 1) {
+      long rep, rlo = 0, rhi = 0;
+      bool rlazy = false;
+      const size_t ins_before_item = ins.size();
+      if (!parse_repeat(i, &rep, &rlo, &rhi, &rlazy)) return false;
+      if (rep == -2) {
+        // variable repetition of a one-byte atom: its minimum number of copies, then an insertion point
+        if (item_group) return unsupported("variable repetition of a group");
+        if (pos.size() != item_begin + 1 || pos[item_begin].group >= 0)
+          return unsupported("variable repetition of a lowercase run");
+        const Pos atom = pos[item_begin];
+        pos.resize(item_begin);
+        for (long r = 0; r < rlo; ++r) {
+          pos.push_back(atom);
+          if (pos.size() > BK_MAX_TOTAL_LEN) return unsupported("pattern longer than 4096 bytes");
+        }
+        int cls = atom.cls;
+        if (atom.kind == 1) {  // a literal byte repeats as the class that holds just that byte
+          Class128 one{{0, 0, 0, 0}};
+          one.w[atom.byte >> 5] |= 1u << (atom.byte & 31);
+          cls = class_index(one);
+        }
+        uint32_t mask = 0;
+        for (size_t c : open_caps) mask |= 1u << c;
+        if (ins.size() >= BK_MAX_INS) return unsupported("more than 4 variable repetitions");
+        ins.push_back(InsRec{pos.size(), rhi < 0 ? -1 : rhi - rlo, rlazy, cls, mask});
+      } else if (rep >= 0 && rep != 1) {
+        if (ins.size() != ins_before_item) return unsupported("repetition of a group that contains variable repetition");
         if (item_named) return unsupported("repetition of a named capture group");
         std::vector<Pos> item(pos.begin() + item_begin, pos.end());
         pos.resize(item_begin);
@@ -378,7 +444,8 @@ struct Lowering {
 
 }  // namespace
 
-static int compile_fixed(const std::string& pattern, size_t max_error, Program* prog, std::string* err) {
+// allow_var: variable repetition of one-byte atoms is lowered to insertion points (a parametric program, bk_program.h)
+static int compile_fixed(const std::string& pattern, size_t max_error, Program* prog, std::string* err, bool allow_var = false) {
   std::vector<FuzzySpan> spans;
   std::string expanded;
   int rc = expand(pattern, max_error, &expanded, &spans, err);
@@ -398,6 +465,7 @@ static int compile_fixed(const std::string& pattern, size_t max_error, Program* 
   }
 
   Lowering lw(body, spans);
+  lw.allow_var = allow_var;
   size_t i = 0;
   bool named = false;
   if (!lw.parse_seq(i, 0, &named)) {
@@ -428,14 +496,26 @@ static int compile_fixed(const std::string& pattern, size_t max_error, Program* 
   d.total_len = (uint32_t)lw.pos.size();
   for (size_t c = 0; c < lw.classes.size(); ++c) memcpy(d.cls[c], lw.classes[c].w, 16);
 
-  // runs: literals first (most selective), then classes; each in pattern order
+  // runs: literals first (most selective), then classes; each in pattern order.  A parametric program's runs end at
+  // its insertion points and are ordered by segment first.
+  auto is_ins_pos = [&](size_t q) {
+    for (const auto& in : lw.ins)
+      if (in.pos == q) return true;
+    return false;
+  };
+  auto segment_of = [&](size_t off) {
+    size_t g = 0;
+    for (const auto& in : lw.ins)
+      if (in.pos <= off) ++g;
+    return g;
+  };
   std::vector<bk_op> lits, clss;
   size_t nlit = 0;
   for (size_t p = 0; p < lw.pos.size();) {
     size_t q = p + 1;
     const Pos& a = lw.pos[p];
     while (q < lw.pos.size() && lw.pos[q].kind == a.kind && lw.pos[q].group == a.group &&
-           (a.kind == 1 || lw.pos[q].cls == a.cls))
+           (a.kind == 1 || lw.pos[q].cls == a.cls) && !is_ins_pos(q))
       ++q;
     bk_op op;
     op.off = (uint16_t)p;
@@ -464,8 +544,28 @@ static int compile_fixed(const std::string& pattern, size_t max_error, Program* 
     *err = "unsupported pattern: more than 48 compare runs";
     return BK_E_UNSUPPORTED;
   }
-  for (auto& o : lits) d.ops[d.nops++] = o;
-  for (auto& o : clss) d.ops[d.nops++] = o;
+  for (size_t g = 0; g <= lw.ins.size(); ++g) {
+    for (auto& o : lits)
+      if (segment_of(o.off) == g) d.ops[d.nops++] = o;
+    for (auto& o : clss)
+      if (segment_of(o.off) == g) d.ops[d.nops++] = o;
+    if (g < lw.ins.size()) {
+      const auto& in = lw.ins[g];
+      bk_ins& di = d.ins[g];
+      di.pos = (uint16_t)in.pos;
+      di.max_extra = (uint16_t)(in.max_extra < 0 || in.max_extra > 0xFFFE ? 0xFFFF : in.max_extra);
+      di.cls = (uint8_t)in.cls;
+      di.lazy = in.lazy ? 1 : 0;
+      di.capmask = (uint8_t)in.capmask;
+      di.op_end = (uint8_t)d.nops;
+    }
+  }
+  d.nins = (uint32_t)lw.ins.size();
+  if (lw.classes.size() > BK_MAX_CLASSES) {  // (a repeated literal byte adds a class)
+    *err = "unsupported pattern: more than 8 distinct character classes";
+    return BK_E_UNSUPPORTED;
+  }
+  for (size_t c = 0; c < lw.classes.size(); ++c) memcpy(d.cls[c], lw.classes[c].w, 16);
 
   d.ncaps = (uint32_t)lw.caps.size();  // <= 3: names are unique and drawn from {UMI, CB, SB}
   d.hdr_growth = 0;
@@ -475,6 +575,7 @@ static int compile_fixed(const std::string& pattern, size_t max_error, Program* 
     d.caps[c].name_len = (uint8_t)lw.caps[c].name.size();
     memcpy(d.caps[c].name, lw.caps[c].name.data(), lw.caps[c].name.size());
     d.hdr_growth += 3 + d.caps[c].name_len + 2 * d.caps[c].len;
+    d.cap_ins_before[c] = (uint8_t)lw.caps[c].ins_before;
   }
   return BK_OK;
 }
@@ -499,8 +600,8 @@ struct Quant {
 
 int find_quantifiers(const std::string& p, std::vector<Quant>* out, std::string* err) {
   auto unsupported = [&](const std::string& what) {
-    *err = "unsupported pattern construct (" + what + "): repetition must be {n}, {m,n} or ? on a class, `.` or a "
-           "literal, with at most " + std::to_string(BK_MAX_VARIANTS) + " length combinations";
+    *err = "unsupported pattern construct (" + what + "): repetition ({n} {m,n} {m,} ? * +, greedy or lazy) applies to "
+           "a class, `.` or a literal byte; a group is taken a fixed number of times";
     return BK_E_UNSUPPORTED;
   };
   bool in_class = false;
@@ -543,11 +644,12 @@ int find_quantifiers(const std::string& p, std::vector<Quant>* out, std::string*
       ++i;
       continue;
     }
-    if (c == '*' || c == '+') return unsupported(std::string("unbounded repetition ") + c);
-    if (c == '?' || c == '{') {
+    if (c == '?' || c == '{' || c == '*' || c == '+') {
       Quant q{i, i, 0, 0, false};
       if (c == '?') {
         q.lo = 0; q.hi = 1; q.end = i + 1;
+      } else if (c == '*' || c == '+') {
+        q.lo = c == '+' ? 1 : 0; q.hi = -1; q.end = i + 1;  // (hi = -1: unbounded)
       } else {
         size_t j = i + 1;
         long lo = 0, hi = 0;
@@ -560,9 +662,9 @@ int find_quantifiers(const std::string& p, std::vector<Quant>* out, std::string*
         }
         ++j;
         while (j < p.size() && p[j] >= '0' && p[j] <= '9' && hi < 100000) { hi = hi * 10 + (p[j] - '0'); ++j; ++d2; }
-        if (d2 == 0) return unsupported("unbounded repetition {m,}");
         if (j >= p.size() || p[j] != '}') { *err = "Regex error: unclosed counted repetition"; return BK_E_PATTERN; }
-        if (hi < lo) { *err = "Regex error: invalid repetition count range, the start must be <= the end"; return BK_E_PATTERN; }
+        if (d2 == 0) hi = -1;
+        else if (hi < lo) { *err = "Regex error: invalid repetition count range, the start must be <= the end"; return BK_E_PATTERN; }
         q.lo = lo; q.hi = hi; q.end = j + 1;
       }
       if (prev == ')' || prev == '(' || prev == 0 || prev == '^') {
@@ -597,14 +699,20 @@ int compile(const std::string& pattern, size_t max_error, Program* prog, std::st
     if (rc == BK_OK) prog->variants.push_back(prog->dev);
     return rc;
   }
+  // Few length combinations: one fixed-length program each (below).  Unbounded repetition (`*`, `+`, `{m,}`) or more
+  // than BK_MAX_VARIANTS combinations: ONE parametric program whose insertion points the matcher fills by backtracking
+  // (bk_program.h, bk_ins).
   size_t total = 1;
+  bool parametric = false;
   for (const auto& q : qs) {
+    if (q.hi < 0) { parametric = true; break; }
     total *= (size_t)(q.hi - q.lo + 1);
-    if (total > BK_MAX_VARIANTS) {
-      *err = "unsupported pattern construct (variable repetition): more than " + std::to_string(BK_MAX_VARIANTS) +
-             " length combinations";
-      return BK_E_UNSUPPORTED;
-    }
+    if (total > BK_MAX_VARIANTS) { parametric = true; break; }
+  }
+  if (parametric) {
+    rc = compile_fixed(pattern, max_error, prog, err, true);
+    if (rc == BK_OK) prog->variants.push_back(prog->dev);
+    return rc;
   }
   // the expanded text the reference would hand to Regex::new keeps its quantifiers (pattern.rs:93-109)
   {
@@ -756,6 +864,11 @@ int bk_program_dump(const bk_program* p, char* out, size_t cap) {
       }
     }
     s += "\n";
+  }
+  for (uint32_t i = 0; i < d.nins; ++i) {  // insertion points of a parametric program
+    snprintf(line, sizeof line, "ins %u %u %u %u %u %u\n", d.ins[i].pos, d.ins[i].max_extra, d.ins[i].lazy, d.ins[i].cls,
+             d.ins[i].capmask, d.ins[i].op_end);
+    s += line;
   }
   for (uint32_t c = 0; c < d.ncaps; ++c) {
     snprintf(line, sizeof line, "cap %.*s %u %u\n", (int)d.caps[c].name_len, d.caps[c].name, d.caps[c].off,

@@ -15,6 +15,7 @@
 #define BK_MAX_CAPS 3
 #define BK_MAX_TOTAL_LEN 4096
 #define BK_MAX_VARIANTS 24
+#define BK_MAX_INS 4
 
 enum : uint8_t {
   BK_OP_CLASS = 0,  // every byte of the run must be in class `idx`
@@ -36,6 +37,20 @@ struct bk_cap {
   char name[3];      // "UMI" | "CB" | "SB"
 };
 
+// Unbounded (or widely bounded) repetition of a one-byte atom, `X*  X+  X{m,}  X{m,n}`: the program is laid out with
+// every such atom taken its minimum number of times, and each insertion point says where up to max_extra further
+// copies may sit.  With e_i extra copies at insertion i, everything behind it moves by e_i: an op of segment j
+// (= the ops between insertions j - 1 and j) is compared at start + off + e_0 + .. + e_{j-1}.  The matcher
+// (match_par, bk_match.cuh) tries the e_i in the regex crate's backtracking order.
+struct bk_ins {
+  uint16_t pos;        // offset in the minimal layout at which the extra copies are inserted
+  uint16_t max_extra;  // hi - lo; 0xFFFF = unbounded
+  uint8_t cls;         // class index of the repeated atom
+  uint8_t lazy;        // fewest copies first
+  uint8_t capmask;     // bit c: capture c contains the atom (its length grows with e_i)
+  uint8_t op_end;      // ops [0, op_end) belong to segments 0..i
+};
+
 struct bk_devprog {
   uint32_t present;  // 0: this mate has no pattern (run.rs:233-245 `None`)
   uint32_t anchor_start;
@@ -44,9 +59,11 @@ struct bk_devprog {
   uint32_t nops;
   uint32_t ncaps;
   uint32_t hdr_growth;  // sum over caps of 3 + name_len + 2*len  (parse.rs:161-168)
-  uint32_t pad;
+  uint32_t nins;        // > 0: a parametric program (ops ordered by segment; total_len, caps, hdr_growth = the minimum)
   bk_op ops[BK_MAX_OPS];
   uint32_t cls[BK_MAX_CLASSES][4];  // 128-bit ASCII membership bitmaps (bytes >= 0x80 never match)
   alignas(4) uint8_t lit[BK_MAX_LIT];  // literals, each starting on a 4-byte boundary, zero padded
   bk_cap caps[BK_MAX_CAPS];
+  bk_ins ins[BK_MAX_INS];
+  uint8_t cap_ins_before[4];  // capture c starts behind the insertions [0, cap_ins_before[c])
 };

@@ -50,6 +50,12 @@ extern "C" {
  *                              two-kernel form (single-end extract of the pattern's mate + compaction of the
  *                              other); for measurements and tests, the output is identical */
 #define BK_FLAG_STAGE_BOTH_MATES 64u
+/*   BK_FLAG_MATCH_IN_KERNEL    a pattern that needs a search (not anchored, -r, variable repetition) is by default
+ *                              matched by a pass of its own (match_kernel) that leaves a match table for the
+ *                              extract launches; with this flag the search runs inside the extract kernel as in
+ *                              round 1 (one launch; with two patterns: the paired kernel with both mates staged);
+ *                              for measurements and tests, the output is identical */
+#define BK_FLAG_MATCH_IN_KERNEL 128u
 
 /* Layout guards: a binding written against this header (rust/barkit-extract/src/ffi.rs) must
  * agree with these sizes; they only ever grow at the end, together with the numbers here. */

@@ -78,6 +78,7 @@ pub const BK_FLAG_DEVICE_BOTH_MATES: u32 = 8;
 pub const BK_FLAG_HOST_MATE_PINNED: u32 = 16;
 pub const BK_FLAG_VERBOSE: u32 = 32;
 pub const BK_FLAG_STAGE_BOTH_MATES: u32 = 64;
+pub const BK_FLAG_MATCH_IN_KERNEL: u32 = 128;
 
 extern "C" {
     // pattern.rs

@@ -24,10 +24,17 @@ def make_ctx(p1, p2=None, k=1, paired=False, skip=False, rc=False, extra_flags=0
                         host_threads=host_threads)
 
 
-def run_se(fq, pattern, k=1, skip=False, rc=False):
-    ctx = make_ctx(pattern, k=k, skip=skip, rc=rc)
+def run_se(fq, pattern, k=1, skip=False, rc=False, extra_flags=0):
+    ctx = make_ctx(pattern, k=k, skip=skip, rc=rc, extra_flags=extra_flags)
     out, res = ctx.extract_text(fq)
     ctx.close()
+    if extra_flags == 0:
+        # A pattern that needs a search is matched by match_kernel ahead of the extract launch; the same search inside
+        # the extract kernel (BK_FLAG_MATCH_IN_KERNEL) must give the same bytes.  (For an anchored pattern the flag
+        # changes nothing.)
+        out_k, res_k = run_se(fq, pattern, k, skip, rc, extra_flags=_lib.FLAG_MATCH_IN_KERNEL)
+        assert out == out_k, "match_kernel + table and the in-kernel search differ"
+        assert (res.n_out, res.n_match1) == (res_k.n_out, res_k.n_match1)
     return out, res
 
 
@@ -35,6 +42,10 @@ def run_pe(fq1, fq2, p1, p2, k=1, skip=False, rc=False, extra_flags=0):
     ctx = make_ctx(p1, p2, k=k, paired=True, skip=skip, rc=rc, extra_flags=extra_flags)
     o1, o2, res = ctx.extract_text(fq1, fq2)
     ctx.close()
+    if extra_flags == 0:   # ... and the search inside the extract kernel (see run_se)
+        k1, k2, res_k = run_pe(fq1, fq2, p1, p2, k, skip, rc, extra_flags=_lib.FLAG_MATCH_IN_KERNEL | _lib.FLAG_DEVICE_BOTH_MATES)
+        assert (o1, o2) == (k1, k2), "match_kernel + table and the in-kernel search differ"
+        assert (res.n_out, res.n_match1, res.n_match2) == (res_k.n_out, res_k.n_match1, res_k.n_match2)
     if (p1 is None) != (p2 is None) and extra_flags == 0:
         # One pattern: by default the pattern-less mate is assembled on the host (bk_submit) and the kernel sees a
         # single-end batch.  Every such test also runs the paired kernel (the pattern-less mate copied on the
@@ -308,6 +319,47 @@ def test_variable_repetition_paired_end():
             assert o1 == e1 and o2 == e2, (p1, p2, k, skip, rc)
 
 
+UNBOUNDED = [
+    ("^(?P<UMI>[ATGC]+)", 0), ("^(?P<UMI>[ATGCN]{3,})gattaca", 1), ("(?P<UMI>[ACGT]*?)atgccat(?P<CB>[ACGT]{2,})", 1),
+    ("^N*(?P<CB>[ACGT]{4,})T+?(?P<UMI>[ACGT]{2})$", 0), ("(?P<UMI>[ACGT]{1,40})gattaca", 2), ("(?P<SB>A+)(?P<UMI>.*)$", 0),
+    ("^(?P<UMI>.{2,}?)acgt(?P<CB>[ATGCN]*)", 1), ("(?P<CB>[ATGCN]{5,})atgccat(?P<UMI>[ATGCN]{0,30})", 1),
+    ("^(?P<UMI>[ATGC]{2,6}?)G*C{1,}(?P<CB>[ACGTN]+)", 0),
+]
+
+
+@pytest.mark.parametrize("pat,k", UNBOUNDED)
+def test_unbounded_repetition_single_end(pat, k):
+    """`* + {m,}` and widely bounded `{m,n}` on a class, `.` or a literal byte: the pattern
+    is one parametric program whose insertion points match_kernel fills by backtracking in the regex crate's order
+    (greedy: longest first, lazy: shortest first, the first quantifier outermost), and the extract launch rewrites
+    every record with ITS capture offsets and lengths.  Output must equal the oracle's (Python `re`: the same
+    backtracking semantics), with trimming, -s and -r."""
+    assert _lib.Program(pat, k).nvariants() == 1
+    rnd = random.Random(zlib.crc32(pat.encode()))
+    fq = ragged_fastq(rnd, 3000, plant=[b"GATTACA", b"ATGCCAT", b"ACGT"], crlf=False, plus_comment=True,
+                      min_len=0, max_len=80)
+    for skip, rc in ((False, False), (True, False), (False, True)):
+        out, res = run_se(fq, pat, k, skip, rc)
+        assert out == bo.extract_se(fq, pat, k, rc, skip), (pat, k, skip, rc)
+        assert 0 < res.n_out <= 3000
+
+
+def test_unbounded_repetition_paired_end():
+    rnd = random.Random(11)
+    n = 2500
+    heads = [rnd.choice([3, 23, 60]) for _ in range(n)]
+    fq1 = ragged_fastq(rnd, n, 1, plant=[b"ATGCCAT"], head_lens=heads, min_len=10, max_len=70)
+    fq2 = ragged_fastq(rnd, n, 2, plant=[b"GATTACA"], head_lens=heads, min_len=0, max_len=70, crlf=True)
+    combos = [("^(?P<UMI>[ATGCN]+)atgccat", "(?P<CB>[ACGT]{3,})gattaca"),
+              ("^(?P<UMI>[ATGCN]{8,})atgccat", None), (None, "(?P<CB>[ACGT]*?)gattaca(?P<SB>[ACGT]+)"),
+              ("^(?P<UMI>[ATGCN]{12})", "^(?P<CB>[ACGT]+)gattaca"), ("(?P<UMI>[ATGCN]{4})atgccat", "(?P<CB>N*[ACGT]{2,}?)gattaca")]
+    for p1, p2 in combos:
+        for k, skip, rc in ((1, False, False), (2, True, False), (0, False, True)):
+            o1, o2, _ = run_pe(fq1, fq2, p1, p2, k, skip=skip, rc=rc)
+            e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, k, rc_barcodes=rc, skip_trimming=skip)
+            assert o1 == e1 and o2 == e2, (p1, p2, k, skip, rc)
+
+
 def test_host_side_mate_falls_back_when_the_host_copy_is_slow():
     """The context measures the host copy of the pattern-less mate against what the bus would need and sends
     both mates to the device once the host side loses twice in a row (here: one host thread).  The bytes do
@@ -417,7 +469,7 @@ def test_device_resident_matches_oracle_and_match_table():
         ma, mb = r1.regex.search(a.seq), r2.regex.search(b.seq)
         assert m1[i] == (ma.start() if ma else -1)
         assert m2[i] == (mb.start() if mb else -1)
-    assert res.launches == 2 and res.kernel_ms > 0
+    assert res.launches == 6 and res.kernel_ms > 0   # per iteration: match_kernel on R2, one single-end launch per mate
     ctx.close()
 
 

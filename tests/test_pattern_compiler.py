@@ -61,8 +61,8 @@ def test_error_messages_follow_error_rs():
 
 
 @pytest.mark.parametrize("pattern", [
-    "^(?P<UMI>[ATGCN]+)", "^(?P<UMI>[ATGCN]{2,})", "^(?P<UMI>[ATGCN]*)", "^(?P<UMI>A|C)",
-    "^(?P<UMI>[ATGCN]{1,30})", "^(?P<UMI>[ATGCN]{1,5})[ACGT]{0,5}", "^((?P<UMI>[ATGCN]{4})A){1,2}", "^(?P<UMI>[ATGCN]{2,4}+)",
+    "^(?P<UMI>A|C)", "^(?P<UMI>([ATGCN])+)", "^(?P<UMI>[ATGCN]{4})+", "^(?P<UMI>[ATGCN]+)(A*C){2}", "^(?P<UMI>[ATGCN]+)a*",
+    "^(?P<UMI>A*C*G*T*N*)", "^((?P<UMI>[ATGCN]{4})A){1,2}", "^(?P<UMI>[ATGCN]{2,4}+)", "^(?P<UMI>[ATGCN]{2,}*)",
     "^(?P<UMI>[ATGCN]{4,2})", "?(?P<UMI>[ATGCN]{4})",
     r"^(?P<UMI>\w{4})", "(?i)(?P<UMI>[ATGCN]{4})", "^(?P<UMI>[ATGCN]{4})?", "(?P<UMI>[ATGCN]{4})^",
     "(?=A)(?P<UMI>[ATGCN]{4})", "((?P<UMI>[ATGCN]{4})){2}", "(?P<UMI>[[:alpha:]]{4})",
@@ -94,6 +94,25 @@ def test_variable_repetition_lowers_to_variants_in_priority_order():
     # variable repetition inside a group is fine as long as the group itself is taken once
     assert _lib.Program("(?P<UMI>[ACGT]{4})([AT]{1,2}G)", 0).nvariants() == 2
     assert _lib.Program("(?P<UMI>[ACGT]{4})(A?C){1}(GT){2}", 0).nvariants() == 2
+
+
+def test_unbounded_repetition_lowers_to_one_parametric_program():
+    """`* + {m,}` and {m,n} with more than 24 length combinations: ONE program laid out at the minimum counts, plus
+    insertion points (bk_program.h: bk_ins) that the device matcher fills by backtracking."""
+    p = _lib.Program("^N*(?P<CB>[ACGT]{4,})T+?(?P<UMI>[ACGT]{2})$", 0)
+    assert p.nvariants() == 1 and p.info().total_len == 4 + 1 + 2
+    ins = [l.split() for l in p.dump().splitlines() if l.startswith("ins ")]
+    #          pos  max_extra  lazy  capmask
+    assert [(int(f[1]), int(f[2]), int(f[3]), int(f[5])) for f in ins] == [(0, 65535, 0, 0), (4, 65535, 0, 1), (5, 65535, 1, 0)]
+    assert p.barcode_types() == ["CB", "UMI"]
+    # bounded but wide: the same form, with the bound kept
+    p = _lib.Program("(?P<UMI>[ACGT]{1,40})gattaca", 1)
+    ins = [l.split() for l in p.dump().splitlines() if l.startswith("ins ")]
+    assert p.nvariants() == 1 and [(int(f[1]), int(f[2])) for f in ins] == [(1, 39)]
+    # up to 24 combinations stay fixed-length variants
+    assert _lib.Program("(?P<UMI>[ACGT]{1,24})gattaca", 1).nvariants() == 24
+    # the text the reference would hand to the regex crate keeps its quantifiers (pattern.rs:93-109)
+    assert _lib.expand("^(?P<UMI>[ATGCN]+)at", 1) == bo.BarcodePattern("^(?P<UMI>[ATGCN]+)at", 1).get_pattern_with_errors()
 
 
 # ---- expansion text == oracle on generated patterns ---------------------------------------------
