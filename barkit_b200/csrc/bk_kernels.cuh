@@ -387,7 +387,8 @@ __device__ __forceinline__ uint32_t complement(uint32_t c) {
 constexpr uint32_t kTabComp = 256, kTabHdr = 512, kTabOps = 528, kTabLit = kTabOps + 8u * BK_MAX_OPS;
 constexpr uint32_t kTabSA = kTabLit + BK_MAX_LIT;  // 8 x 2 words: bit planes of the program's first literal (match_unanchored)
 constexpr uint32_t kTabIns = kTabSA + 64u;  // nins, pad, then BK_MAX_INS x bk_ins (8 bytes each): parametric programs (match_par)
-constexpr uint32_t kTabBytes = kTabIns + 8u + 8u * BK_MAX_INS;
+constexpr uint32_t kTabBytes = kTabIns + 16u + 8u * BK_MAX_INS;  // (a multiple of 16: the blocks of the two mates sit back to back)
+static_assert(kTabBytes % 16u == 0, "lookup blocks are read with 16-byte loads");
 struct MOp { uint32_t off, len, kind, k, idx; };
 __device__ __forceinline__ MOp tab_op(uint32_t tab, uint32_t o) {  // bk_op, little endian
   const uint2 v = lds64(tab + kTabOps + 8u * o);
@@ -1171,6 +1172,67 @@ __device__ __noinline__ void emit_record_g(const uint8_t* t, uint32_t beg, uint3
   *o++ = '\n'; *o++ = '+'; *o++ = '\n';
   for (uint32_t i = 0; i < qual_len; ++i) *o++ = (uint8_t)__ldg(t + qual + i);
   *o++ = '\n';
+}
+
+// ---- unanchored search over a list of variants (match_kernel) ---------------------------------------------------
+//
+// Bounded repetition in front of or behind a literal -- `(?P<CB>[ATGCN]{14,16})atgccat` -- gives variants that all carry
+// the SAME first literal (bytes, length, mismatch budget), only at different offsets.  Every lane scans its read as
+// match_unanchored does: the bit planes of 64 text bytes from the window's first start + the smallest literal
+// offset are made once, and per variant only the counter loop runs, on the planes shifted by that variant's offset;
+// that leaves one word of candidate starts per variant.  The candidates are then verified in the regex crate's
+// order -- ascending start, and at one start the variants in list order -- against the variant's whole program.
+// Requires (checked by the caller): no anchors, every variant's ops[0] an eligible literal equal to variant 0's,
+// offsets within 24 bytes of each other.  `voff` = the variants' literal offsets (shared memory, one byte each).
+__device__ __noinline__ int match_variants_scan(const bk_devprog* vp, uint32_t nvar, uint32_t tab, uint32_t voff, uint32_t off_min,
+                                                 uint32_t seq, uint32_t L, bool can) {
+  const MOp op0 = tab_op(tab, 0);
+  uint32_t tmin = 0xFFFFFFFFu;  // the shortest variant bounds the candidate starts
+  for (uint32_t v = 0; v < nvar; ++v) tmin = min(tmin, vp[v].total_len);
+  bool pend = can && L >= tmin;
+  const uint32_t last = pend ? L - tmin : 0u;
+  const uint32_t smax = __reduce_max_sync(0xffffffffu, last);
+  if (!__any_sync(0xffffffffu, pend)) return -1;
+  int ms = -1;
+  for (uint32_t q = 0; q <= smax; q += 32u) {
+    uint32_t cand[BK_MAX_VARIANTS];
+    uint32_t any = 0;
+    if (pend && q <= last) {
+      const uint32_t cb = seq + q + off_min;
+      uint32_t a0, a1, b0, b1;
+      bs_planes<8>(cb, a0, a1);
+      bs_planes<8>(cb + 32u, b0, b1);
+      for (uint32_t v = 0; v < nvar; ++v) {
+        const uint32_t dlt = lds8(voff + v) - off_min;  // <= 24
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < op0.len; ++i) {
+          const uint2 x = lds64(tab + kTabSA + 8u * i);
+          const uint32_t mm = (__funnelshift_r(a0, b0, i + dlt) ^ x.x) | (__funnelshift_r(a1, b1, i + dlt) ^ x.y);
+          const uint32_t carry = c0 & mm;
+          c0 ^= mm;
+          c2 |= c1 & carry;
+          c1 ^= carry;
+        }
+        uint32_t cv = ~c2 & (op0.k == 0u ? ~(c0 | c1) : op0.k == 1u ? ~c1 : op0.k == 2u ? ~(c1 & c0) : 0xFFFFFFFFu);
+        const uint32_t T = vp[v].total_len;  // this variant's own last start
+        if (L < T || q > L - T) cv = 0;
+        else if (L - T - q < 31u) cv &= (2u << (L - T - q)) - 1u;
+        cand[v] = cv;
+        any |= cv;
+      }
+    }
+    while (any) {  // (per lane: candidates are a few per read)
+      const uint32_t b = (uint32_t)__ffs(any) - 1u;
+      for (uint32_t v = 0; v < nvar && ms < 0; ++v)
+        if (((cand[v] >> b) & 1u) && match_at_variant<false>(vp[v], tab, seq, L, q + b)) ms = (int)((q + b) | (v << 24));
+      if (ms >= 0) break;
+      any &= any - 1u;
+    }
+    if (ms >= 0) pend = false;
+    if (!__any_sync(0xffffffffu, pend)) break;
+  }
+  return ms;
 }
 
 // parse::get_reverse_complement as a stand-alone op (API parity; the extract kernel never materialises it)

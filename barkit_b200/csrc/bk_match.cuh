@@ -54,6 +54,26 @@ __global__ void __launch_bounds__(kMatchWarps * 32) match_kernel(const __grid_co
   const uint32_t R = P.tile_recs;
   const bool unanch = !pg.anchor_start && !pg.anchor_end;
   const bool var = P.nvar > 1u;
+  // variants that share their first literal can be searched with the bit-parallel scan (match_variants_scan)
+  __shared__ uint8_t s_voff[BK_MAX_VARIANTS];
+  __shared__ uint32_t s_scan;  // 0: no; else 1 + the smallest literal offset
+  if (warp == 0 && var) {
+    bool ok = unanch && lane < (int)P.nvar;
+    uint32_t off = 0;
+    if (lane < (int)P.nvar) {
+      const bk_devprog& pv = P.vprog[lane];
+      const bk_op a = pv.ops[0], z = P.vprog[0].ops[0];
+      ok = ok && pv.nops && !pv.anchor_start && !pv.anchor_end && bs_eligible(a.kind, a.len, a.k) && a.len == z.len && a.k == z.k;
+      for (uint32_t i = 0; ok && i < a.len; ++i) ok = pv.lit[a.idx + i] == P.vprog[0].lit[z.idx + i];
+      off = a.off;
+      s_voff[lane] = (uint8_t)off;
+    }
+    const bool all_ok = __all_sync(0xffffffffu, ok || lane >= (int)P.nvar) && unanch;
+    const uint32_t omin = __reduce_min_sync(0xffffffffu, lane < (int)P.nvar ? off : 0xFFFFFFFFu);
+    const uint32_t omax = __reduce_max_sync(0xffffffffu, lane < (int)P.nvar ? off : 0u);
+    if (lane == 0) s_scan = all_ok && omax - omin <= 24u && omax < 256u ? 1u + omin : 0u;
+  }
+  __syncthreads();
   uint32_t ph = 0;
   for (uint32_t tile = blockIdx.x * W + warp; tile < P.ntiles; tile += gridDim.x * W) {
     const uint32_t r0 = tile * R, nrec = min(R, P.n - r0);
@@ -93,6 +113,12 @@ __global__ void __launch_bounds__(kMatchWarps * 32) match_kernel(const __grid_co
           }
         }
         if (active) P.extras[r0 + lane] = ex;
+      } else if (var && s_scan) {
+        ms = match_variants_scan(P.vprog, P.nvar, tab, smem_u32(s_voff), s_scan - 1u, rv.seq, rv.seq_len, can);
+        if (can && ms < 0 && P.rc) {
+          ms = match_variants<true>(P.vprog, P.nvar, tab, rv.seq, rv.seq_len);
+          if (ms >= 0 && !caps_utf8_ok(P.vprog[ms >> 24], rv.seq, (uint32_t)ms & 0xFFFFFFu)) ms = -1;
+        }
       } else if (var) {
         if (can) {
           ms = match_variants<false>(P.vprog, P.nvar, tab, rv.seq, rv.seq_len);
