@@ -1174,6 +1174,89 @@ __device__ __noinline__ void emit_record_g(const uint8_t* t, uint32_t beg, uint3
   *o++ = '\n';
 }
 
+// ---- unanchored search with the windows dealt out again every round (match_kernel) ----------------------------------
+//
+// match_unanchored gives every lane the windows of ITS read, one per round, and the warp runs until its slowest read is
+// done: on BASELINE config C4 nine reads in ten match in their first window, but nearly every tile holds a read
+// without a match, so all tiles run all four rounds with three lanes in thirty-two still working.  Here the warp deals
+// the open windows out again each round: with P reads undecided, every one of them gets g = min(32 / P, windows
+// left) consecutive windows, one lane each (the lane fetches that read's bounds by shuffle), and the read's owner takes
+// the lowest hit of its g lanes -- the leftmost match is the one in the lowest window.  The first round is the old
+// one (P = 32, g = 1); the second usually finishes the tile.
+__device__ __noinline__ int match_unanchored_rd(uint32_t tab, uint32_t seq, uint32_t L, bool can, int lane) {
+  const uint32_t T = lds32(tab + kTabHdr + 4u);
+  const MOp op0 = tab_op(tab, 0);
+  if (!bs_eligible(op0.kind, op0.len, op0.k)) return match_unanchored(tab, seq, L, can, lane, 0, 1, nullptr, 0u);
+  bool pend = can && L >= T;
+  const uint32_t last = pend ? L - T : 0u;  // this read's last candidate start
+  const uint32_t nwin = last / 32u + 1u;
+  uint32_t wnext = 0;  // this read's first window not searched yet
+  int ms = -1;
+  while (true) {
+    const unsigned pm = __ballot_sync(0xffffffffu, pend);
+    if (!pm) break;
+    const uint32_t P = (uint32_t)__popc(pm);
+    const uint32_t maxrem = __reduce_max_sync(0xffffffffu, pend ? nwin - wnext : 0u);
+    const uint32_t g = min(32u / P, maxrem);  // >= 1
+    // this lane's share: window wi of the j-th undecided read
+    const uint32_t j = (uint32_t)lane / g, wi = (uint32_t)lane - j * g;
+    const bool work = j < P;
+    // the lane of the j-th undecided read = the largest t with fewer than j + 1 set bits of pm below it (binary search;
+    // the __fns intrinsic is a 32-step loop and was 12 % of this kernel's instructions)
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t step = 16u; step; step >>= 1)
+      if ((uint32_t)__popc(pm & ((1u << (r + step)) - 1u)) <= j) r += step;
+    if (!work) r = 0;
+    const uint32_t rseq = __shfl_sync(0xffffffffu, seq, (int)r), rlast = __shfl_sync(0xffffffffu, last, (int)r);
+    const uint32_t q = 32u * (__shfl_sync(0xffffffffu, wnext, (int)r) + wi);
+    uint32_t cand = 0;
+    if (work && q <= rlast) {
+      const uint32_t cb = rseq + q + op0.off;
+      uint32_t a0, a1, b0, b1;
+      bs_planes<8>(cb, a0, a1);
+      bs_planes<2>(cb + 32u, b0, b1);  // (the literal reaches at most 7 bytes into the next 32)
+      uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll 1
+      for (uint32_t i = 0; i < op0.len; ++i) {
+        const uint2 x = lds64(tab + kTabSA + 8u * i);
+        const uint32_t mm = (__funnelshift_r(a0, b0, i) ^ x.x) | (__funnelshift_r(a1, b1, i) ^ x.y);
+        const uint32_t carry = c0 & mm;
+        c0 ^= mm;
+        c2 |= c1 & carry;
+        c1 ^= carry;
+      }
+      cand = ~c2 & (op0.k == 0u ? ~(c0 | c1) : op0.k == 1u ? ~c1 : op0.k == 2u ? ~(c1 & c0) : 0xFFFFFFFFu);
+      if (rlast - q < 31u) cand &= (2u << (rlast - q)) - 1u;
+    }
+    uint32_t mine = 0xFFFFFFFFu;
+    while (__any_sync(0xffffffffu, cand != 0u)) {  // every lane's lowest candidate, verified together
+      const bool have = cand != 0u;
+      const uint32_t st = q + (have ? (uint32_t)__ffs(cand) - 1u : 0u);
+      if (have && match_at_fwd_shared(tab, rseq, st)) {
+        mine = st;
+        cand = 0;
+      } else if (have) {
+        cand &= cand - 1u;
+      }
+    }
+    // the owner of an undecided read collects its g lanes
+    const uint32_t myj = (uint32_t)__popc(pm & ((1u << lane) - 1u));
+    uint32_t best = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < g; ++i) best = min(best, __shfl_sync(0xffffffffu, mine, (int)((myj * g + i) & 31u)));
+    if (pend) {
+      if (best != 0xFFFFFFFFu) {
+        ms = (int)best;
+        pend = false;
+      } else {
+        wnext += g;
+        pend = wnext < nwin;
+      }
+    }
+  }
+  return ms;
+}
+
 // ---- unanchored search over a list of variants (match_kernel) ---------------------------------------------------
 //
 // Bounded repetition in front of or behind a literal -- `(?P<CB>[ATGCN]{14,16})atgccat` -- gives variants that all carry

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kMatchWarps * 32) match_kernel(const __grid_co
           }
         }
       } else {
-        if (unanch) ms = match_unanchored(tab, rv.seq, rv.seq_len, can, lane, 0, 1, nullptr, 0u);
+        if (unanch) ms = match_unanchored_rd(tab, rv.seq, rv.seq_len, can, lane);
         else if (can) ms = match_read_shared(tab, rv.seq, rv.seq_len);
         if (can && ms < 0 && P.rc) {
           ms = match_read<true>(tab, rv.seq, rv.seq_len);

@@ -283,6 +283,11 @@ def kernel_name(paired, one_pattern, general):
         # compaction of the other mate; timed together
         return ("bk::extract_kernel<PAIRED=false, GENERAL=%s> on the pattern's mate + bk::compact_kernel on the other"
                 % ("true" if general else "false"))
+    if paired and general:
+        # two patterns, one of them needs a search: match_kernel on that mate, then one single-end extract launch per
+        # mate (the searched mate's takes its matches from the table); timed together
+        return ("bk::match_kernel on the searched mate + bk::extract_kernel<PAIRED=false, GENERAL=false> on the anchored "
+                "mate + bk::extract_kernel<PAIRED=false, TABLE=true> on the searched mate")
     return "bk::extract_kernel<PAIRED=%s, GENERAL=%s>" % ("true" if paired else "false", "true" if general else "false")
 
 

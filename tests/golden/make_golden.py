@@ -72,6 +72,22 @@ def main():
     write("varlen_pe_out1.fq", o1); write("varlen_pe_out2.fq", o2)
     manifest.append({"tag": "varlen_pe", "pattern1": p1, "pattern2": p2, "paired": True, "max_error": 1,
                      "rc_barcodes": False, "skip_trimming": False})
+    # unbounded repetition (* + {m,}): SURVEY.md section 8f-2, the CUDA path's parametric programs
+    rnd = random.Random(4713)
+    heads = [rnd.choice([3, 23, 60]) for _ in range(80)]
+    fq1 = ragged_fastq(rnd, 80, 1, plant=[b"ATGCCAT"], head_lens=heads, min_len=10, max_len=60)
+    fq2 = ragged_fastq(rnd, 80, 2, plant=[b"GATTACA"], head_lens=heads, min_len=0, max_len=60, plus_comment=True)
+    p1 = "^(?P<UMI>[ATGCN]{3,})atgccat(?P<CB>[ACGT]*)"
+    write("unbounded_se_in1.fq", fq1)
+    write("unbounded_se_out1.fq", bo.extract_se(fq1, p1, 1))
+    manifest.append({"tag": "unbounded_se", "pattern1": p1, "pattern2": None, "paired": False, "max_error": 1,
+                     "rc_barcodes": False, "skip_trimming": False})
+    p1, p2 = "^N*(?P<UMI>[ACGT]+)", "(?P<CB>[ACGT]{2,})gattaca(?P<SB>[ACGT]{0,30})"
+    o1, o2 = bo.extract_pe(fq1, fq2, p1, p2, 1)
+    write("unbounded_pe_in1.fq", fq1); write("unbounded_pe_in2.fq", fq2)
+    write("unbounded_pe_out1.fq", o1); write("unbounded_pe_out2.fq", o2)
+    manifest.append({"tag": "unbounded_pe", "pattern1": p1, "pattern2": p2, "paired": True, "max_error": 1,
+                     "rc_barcodes": False, "skip_trimming": False})
     with open(os.path.join(HERE, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)
     print("wrote %d cases" % len(manifest))

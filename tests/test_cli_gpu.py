@@ -63,6 +63,27 @@ def test_ragged_input_without_final_newline(tmp_path):
     assert (tmp_path / "o.fq").read_bytes() == bo.extract_se(fq, pat, 1)
 
 
+def test_unbounded_repetition_through_the_cli(tmp_path):
+    """`+ * {m,}` patterns (parametric programs: match_kernel + table) file -> file, single-end and paired, several
+    batches; the header of a record may grow by the read's own length, which bk_out_bound accounts for."""
+    rnd = random.Random(21)
+    n = 30000
+    heads = [rnd.choice([3, 23, 60]) for _ in range(n)]
+    fq1 = ragged_fastq(rnd, n, 1, plant=[b"ATGCCAT"], head_lens=heads, min_len=10, max_len=90)
+    fq2 = ragged_fastq(rnd, n, 2, plant=[b"GATTACA"], head_lens=heads, min_len=0, max_len=90)
+    (tmp_path / "r1.fq").write_bytes(fq1)
+    (tmp_path / "r2.fq").write_bytes(fq2)
+    p1, p2 = "^(?P<UMI>[ATGCN]+)atgccat(?P<SB>[ACGT]*)", "(?P<CB>[ACGT]{3,})gattaca"
+    r = run_cli("-m", "1", "--quiet", "extract", "-1", str(tmp_path / "r1.fq"), "-o", str(tmp_path / "o.fq"), "-p", p1, "-e", "1")
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "o.fq").read_bytes() == bo.extract_se(fq1, p1, 1)
+    r = run_cli("-m", "1", "--quiet", "extract", "-1", str(tmp_path / "r1.fq"), "-2", str(tmp_path / "r2.fq"),
+                "-o", str(tmp_path / "o1.fq"), "-O", str(tmp_path / "o2.fq"), "-p", p1, "-P", p2, "-e", "1")
+    assert r.returncode == 0, r.stderr
+    e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, 1)
+    assert (tmp_path / "o1.fq").read_bytes() == e1 and (tmp_path / "o2.fq").read_bytes() == e2
+
+
 def test_malformed_fastq_is_an_error(tmp_path):
     (tmp_path / "bad.fq").write_bytes(b"@a\nACGT\n+\nIII\n")
     r = run_cli("--quiet", "extract", "-1", str(tmp_path / "bad.fq"), "-o", str(tmp_path / "o.fq"), "-p",

@@ -31,6 +31,14 @@ PATTERNS = [
     ("^(?P<UMI>[ATGCN]{8,10}?)atgccat", [1]),
     ("(?P<CB>[ACGT]{3,5})gattaca(?P<UMI>[ATGCN]{2,4})", [1]),
     ("^N?(?P<UMI>[ACGT]{6})", [0]),
+    # unbounded repetition (the CUDA path's parametric programs, tests/test_extract_gpu.py::test_unbounded_*)
+    ("^(?P<UMI>[ATGC]+)", [0]),
+    ("^(?P<UMI>[ATGCN]{3,})gattaca", [0, 1]),
+    ("(?P<UMI>[ACGT]*)atgccat(?P<CB>[ACGT]{2,})", [1]),
+    ("(?P<UMI>[ACGT]*?)atgccat(?P<CB>[ACGT]{2,})", [1]),
+    ("(?P<UMI>[ACGT]{1,40})gattaca", [1, 2]),
+    ("^N*(?P<CB>[ACGT]{4,})T+?(?P<UMI>[ACGT]{2})$", [0]),
+    ("(?P<SB>A+)(?P<UMI>.*)$", [0]),
 ]
 
 _PIECES = ["^", "atgc", "gattaca", "ATGC", "N", "[ATGCN]", "[ACGT]", "{3}", "{2}", "(?P<UMI>[ATGCN]{4})", "(?P<CB>[ACGT]{3})",
