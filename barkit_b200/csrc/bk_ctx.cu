@@ -353,8 +353,7 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     ctx->last_error = "output buffers must be 16-byte aligned";
     return BK_E_ARG;
   }
-  if (ctx->paired && ctx->view[0] && (is_hard(ctx, 0) || is_hard(ctx, 1)) &&
-      (is_parametric(ctx) || !(ctx->flags & (BK_FLAG_STAGE_BOTH_MATES | BK_FLAG_MATCH_IN_KERNEL))))
+  if (ctx->paired && ctx->view[0] && (is_parametric(ctx) || !(ctx->flags & (BK_FLAG_STAGE_BOTH_MATES | BK_FLAG_MATCH_IN_KERNEL))))
     return enqueue_tabled(ctx, s, stream, n, in1, in2, out1, cap1, out2, cap2, match1, match2, launches);
   // A single-end launch whose pattern needs a search: match_kernel first, this launch takes its matches from the table
   // (unless the caller has done that already: enqueue_tabled)
@@ -536,7 +535,10 @@ int enqueue_tabled(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const 
   if ((rc = ensure(ctx, &s->tab_err, 64)) != BK_OK) return rc;
   for (int m = 0; m < 2; ++m)  // (before the table pointers are taken: enqueue_match only finds them large enough)
     if (ctx->prog[m].nins && (rc = ensure(ctx, &s->tab_extras[m], ((size_t)n + 1) * 8)) != BK_OK) return rc;
-  const bool hard[2] = {is_hard(ctx, 0), is_hard(ctx, 1)};
+  // (two anchored patterns: the second mate plays the searched one -- its match is one test per read, but the first
+  // mate's launch needs it before it can size anything)
+  bool hard[2] = {is_hard(ctx, 0), is_hard(ctx, 1)};
+  if (!hard[0] && !hard[1]) hard[1] = true;
   const int first = hard[0] && !hard[1] ? 1 : 0;  // the mate whose extract launch runs first
   int32_t* const tab[2] = {(int32_t*)s->tab_match[0].p, (int32_t*)s->tab_match[1].p};
   // 1. the matchers.  They run before the launch that resets the batch's result, so a tile that does not fit their

@@ -55,7 +55,12 @@ OTHER_CONFIGS = {
     "C2": (None, "^(?P<CB>[ATGCN]{16})atgccat", True, None, (b"ATGCCAT", 16, 0)),
     "C4": ("^(?P<SB>[ATGCN]{8})gtcagtac(?P<UMI>[ATGCN]{12})", "(?P<CB>[ATGCN]{16})atgccat", True,
            (b"GTCAGTAC", 8, 0), (b"ATGCCAT", 16, 40)),
+    # SURVEY.md section 8f-2 (not BASELINE configs): variable repetition on C3's data, pattern on R1 only
+    "F2_unanchored_3_variants": ("(?P<CB>[ATGCN]{14,16})atgccat", None, True, (b"ATGCCAT", 16, 0), None),
+    "F2_unbounded_greedy": ("^(?P<CB>[ATGCN]{14,})atgccat(?P<UMI>[ATGCN]{12})", None, True, (b"ATGCCAT", 16, 0), None),
 }
+F2_KERNELS = ("bk::match_kernel on the pattern's mate + bk::extract_kernel<PAIRED=false, VAR=true, TABLE=true> on it + "
+              "bk::compact_kernel on the other")
 
 
 def measured_peak():
@@ -296,7 +301,7 @@ def other_configs(_lib, units, peak):
     `units` resident units each (fresh input per launch is >> L2)."""
     import numpy as np
     out = {}
-    for name, ks in (("C1", (1,)), ("C2", (1,)), ("C4", (0, 1, 2))):
+    for name, ks in (("C1", (1,)), ("C2", (1,)), ("C4", (0, 1, 2)), ("F2_unanchored_3_variants", (1,)), ("F2_unbounded_greedy", (1,))):
         p1, p2, paired, plant1, plant2 = OTHER_CONFIGS[name]
         cfg = _lib.syn_config(READ_LEN, plant1=plant1, plant2=plant2)
         for k in ks:
@@ -318,7 +323,8 @@ def other_configs(_lib, units, peak):
                 "units": units, "unit": "pairs" if paired else "reads", "units_per_s": units / (t / 1e3),
                 "ms_per_launch": t, "kept_fraction": r.n_out / units, "alg_bytes": alg,
                 "achieved_gbs": alg / (t / 1e3) / 1e9, "frac": alg / (t / 1e3) / 1e9 / peak,
-                "kernel": kernel_name(paired, (p1 is None) != (p2 is None), general), "launches": launches}
+                "kernel": F2_KERNELS if name.startswith("F2") else kernel_name(paired, (p1 is None) != (p2 is None), general),
+                "launches": launches}
             if name == "C1":   # the device tokenizer over the same text, wall time around the call (it ends with small reads)
                 d_off = ctx.dev_alloc((units + 2) * 4)
                 n, consumed, maxrec = C.c_uint32(0), C.c_uint64(0), C.c_uint32(0)

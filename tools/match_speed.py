@@ -13,6 +13,7 @@ CASES = [  # (label, data config, paired, pattern1, pattern2, k)
     ("PE one pattern, 3 variants", "C3", True, "^(?P<CB>[ATGCN]{14,16})atgccat(?P<UMI>[ATGCN]{12})", None, 1),
     ("PE one pattern, 9 variants", "C3", True, "^(?P<CB>[ATGCN]{14,16})atgccat(?P<UMI>[ATGCN]{10,12})", None, 1),
     ("PE one pattern, unanchored 3 variants", "C3", True, "(?P<CB>[ATGCN]{14,16})atgccat", None, 1),
+    ("PE two anchored patterns", "C4", True, "^(?P<SB>[ATGCN]{8})gtcagtac(?P<UMI>[ATGCN]{12})", "^(?P<CB>[ATGCN]{16})", 1),
     ("PE C4", "C4", True, "^(?P<SB>[ATGCN]{8})gtcagtac(?P<UMI>[ATGCN]{12})", "(?P<CB>[ATGCN]{16})atgccat", 1),
 ]
 only = os.environ.get("BK_ONLY")
