@@ -25,7 +25,7 @@ BK_OK = 0
 BK_E_PATTERN, BK_E_UNSUPPORTED, BK_E_CUDA, BK_E_CAPACITY, BK_E_IO, BK_E_ARG, BK_E_FORMAT = \
     -1, -2, -3, -4, -5, -6, -7
 FLAG_PAIRED, FLAG_SKIP_TRIM, FLAG_RC = 1, 2, 4
-FLAG_DEVICE_BOTH_MATES, FLAG_HOST_MATE_PINNED, FLAG_VERBOSE, FLAG_STAGE_BOTH_MATES, FLAG_MATCH_IN_KERNEL = 8, 16, 32, 64, 128
+FLAG_DEVICE_BOTH_MATES, FLAG_HOST_MATE_PINNED, FLAG_VERBOSE, FLAG_STAGE_BOTH_MATES, FLAG_MATCH_IN_KERNEL, FLAG_SPLIT_TWO_PATTERNS = 8, 16, 32, 64, 128, 256
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)

@@ -245,6 +245,10 @@ struct CoLaunch {
   // and the other mate's of the pair (keep rule)
   const int32_t* tab_own = nullptr;
   const unsigned long long* xtab = nullptr;  // with tab_own, for a parametric program
+  // a PAIRED launch in table form: ptab[m] = mate m's table (null: the mate matches for itself), pxtab[m] its extras
+  bool pair_tables = false;
+  const int32_t* ptab[2] = {nullptr, nullptr};
+  const unsigned long long* pxtab[2] = {nullptr, nullptr};
   const int32_t* tab_other = nullptr;
   DevBuf* scratch = nullptr;             // in: the launch's look-back state goes here instead of the slot's buffer ...
   bk::DevResult* result = nullptr;       // in: ... and its figures into this result, which it does not reset
@@ -353,7 +357,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     ctx->last_error = "output buffers must be 16-byte aligned";
     return BK_E_ARG;
   }
-  if (ctx->paired && ctx->view[0] && (is_parametric(ctx) || !(ctx->flags & (BK_FLAG_STAGE_BOTH_MATES | BK_FLAG_MATCH_IN_KERNEL))))
+  // (two anchored patterns stay in the paired kernel: 1.51 against 1.77 ms per 4 M pairs for the split form)
+  if (ctx->paired && ctx->view[0] && !(co && co->pair_tables) && (is_hard(ctx, 0) || is_hard(ctx, 1)) &&
+      (is_parametric(ctx) || !(ctx->flags & (BK_FLAG_STAGE_BOTH_MATES | BK_FLAG_MATCH_IN_KERNEL))))
     return enqueue_tabled(ctx, s, stream, n, in1, in2, out1, cap1, out2, cap2, match1, match2, launches);
   // A single-end launch whose pattern needs a search: match_kernel first, this launch takes its matches from the table
   // (unless the caller has done that already: enqueue_tabled)
@@ -376,11 +382,11 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     self_xtab = (const unsigned long long*)s->tab_extras[ti].p;
   }
   LaunchPlan lp;
-  const bool table = self_tab || (co && co->tab_own);
+  const bool table = self_tab || (co && (co->tab_own || co->pair_tables));
   const bool general = !table && needs_general(ctx);
   const bool var = has_variants(ctx);
   // which instantiation: 0..5 as before, 6 / 7 = single-end with the matches taken from a table (plain / variants)
-  const int kid = table ? (var || ctx->prog[0].nins ? 7 : 6) : var ? (ctx->paired ? 0 : 1) : ctx->paired ? (general ? 2 : 3) : (general ? 4 : 5);
+  const int kid = table && ctx->paired ? (var || is_parametric(ctx) ? 9 : 8) : table ? (var || ctx->prog[0].nins ? 7 : 6) : var ? (ctx->paired ? 0 : 1) : ctx->paired ? (general ? 2 : 3) : (general ? 4 : 5);
   bk::KParams P;
   memset(&P, 0, sizeof P);
   int rc;
@@ -392,7 +398,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     case 4: rc = plan_launch<false, true>(ctx, n, maxrec, &lp); break;
     case 5: rc = plan_launch<false, false>(ctx, n, maxrec, &lp); break;
     case 6: rc = plan_launch<false, false, false, bk::kStages, true>(ctx, n, maxrec, &lp); break;
-    default: rc = plan_launch<false, false, true, bk::kStages, true>(ctx, n, maxrec, &lp); break;
+    case 7: rc = plan_launch<false, false, true, bk::kStages, true>(ctx, n, maxrec, &lp); break;
+    case 8: rc = plan_launch<true, false, false, bk::kStages, true>(ctx, n, maxrec, &lp); break;
+    default: rc = plan_launch<true, false, true, bk::kStages, true>(ctx, n, maxrec, &lp); break;
   }
   if (rc != BK_OK) return rc;
   const size_t kmask_off = (scratch_bytes(lp.ntiles) + 15) & ~size_t(15);  // (keep masks behind everything else)
@@ -419,14 +427,16 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   P.match[0] = match1; P.match[1] = match2;
   P.result = (bk::DevResult*)(sc + 64);
   P.tab_in[0] = self_tab;
-  P.xtab = self_xtab;
+  P.xtab[0] = self_xtab;
   if (co) {
     P.hlen[0] = co->hlen;
     P.rslot = co->rslot;
     if (co->want_kmask) P.kmask = co->kmask = (unsigned long long*)(sc + kmask_off);
     co->tile_recs = lp.tile_recs;
-    if (co->tab_own) { P.tab_in[0] = co->tab_own; P.xtab = co->xtab; }
+    if (co->tab_own) { P.tab_in[0] = co->tab_own; P.xtab[0] = co->xtab; }
     P.tab_in[1] = co->tab_other;
+    if (co->pair_tables)
+      for (int m = 0; m < 2; ++m) { P.tab_in[m] = co->ptab[m]; P.xtab[m] = co->pxtab[m]; }
     P.no_nout = co->no_nout ? 1u : 0u;
     if (co->result) P.result = co->result;
   }
@@ -449,7 +459,9 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
       case 4: bk::extract_kernel<false, true><<<lp.grid, ts, lp.smem, stream>>>(P); break;
       case 5: bk::extract_kernel<false, false><<<lp.grid, ts, lp.smem, stream>>>(P); break;
       case 6: bk::extract_kernel<false, false, false, bk::kStages, true><<<lp.grid, ts, lp.smem, stream>>>(P); break;
-      default: bk::extract_kernel<false, false, true, bk::kStages, true><<<lp.grid, ts, lp.smem, stream>>>(P); break;
+      case 7: bk::extract_kernel<false, false, true, bk::kStages, true><<<lp.grid, ts, lp.smem, stream>>>(P); break;
+      case 8: bk::extract_kernel<true, false, false, bk::kStages, true><<<lp.grid, tp, lp.smem, stream>>>(P); break;
+      default: bk::extract_kernel<true, false, true, bk::kStages, true><<<lp.grid, tp, lp.smem, stream>>>(P); break;
     }
     if (merr) bk::merge_error_kernel<<<1, 1, 0, stream>>>(P.result, merr);
     CK(cudaGetLastError());
@@ -535,10 +547,7 @@ int enqueue_tabled(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const 
   if ((rc = ensure(ctx, &s->tab_err, 64)) != BK_OK) return rc;
   for (int m = 0; m < 2; ++m)  // (before the table pointers are taken: enqueue_match only finds them large enough)
     if (ctx->prog[m].nins && (rc = ensure(ctx, &s->tab_extras[m], ((size_t)n + 1) * 8)) != BK_OK) return rc;
-  // (two anchored patterns: the second mate plays the searched one -- its match is one test per read, but the first
-  // mate's launch needs it before it can size anything)
-  bool hard[2] = {is_hard(ctx, 0), is_hard(ctx, 1)};
-  if (!hard[0] && !hard[1]) hard[1] = true;
+  const bool hard[2] = {is_hard(ctx, 0), is_hard(ctx, 1)};
   const int first = hard[0] && !hard[1] ? 1 : 0;  // the mate whose extract launch runs first
   int32_t* const tab[2] = {(int32_t*)s->tab_match[0].p, (int32_t*)s->tab_match[1].p};
   // 1. the matchers.  They run before the launch that resets the batch's result, so a tile that does not fit their
@@ -547,7 +556,25 @@ int enqueue_tabled(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const 
   CK(cudaMemsetAsync(merr, 0, sizeof(bk::DevResult), stream));
   for (int m = 0; m < 2; ++m)
     if (hard[m] && (rc = enqueue_match(ctx, m, s, m, stream, n, in[m], merr, launches)) != BK_OK) return rc;
-  // 2. one single-end extract launch per mate
+  // 2a. (default) ONE paired launch in table form: both mates staged, a searched mate's front warp reads its table
+  if (!(ctx->flags & BK_FLAG_SPLIT_TWO_PATTERNS)) {
+    CoLaunch co;
+    co.pair_tables = true;
+    for (int m = 0; m < 2; ++m)
+      if (hard[m]) {
+        co.ptab[m] = tab[m];
+        co.pxtab[m] = (const unsigned long long*)s->tab_extras[m].p;
+      }
+    // the kernel writes a mate's matches (variant bits stripped) where the caller asked for them
+    rc = enqueue_extract(ctx, s, stream, n, in1, in2, out1, cap1, out2, cap2, match1, match2, launches, &co);
+    if (rc != BK_OK) return rc;
+    if (n) {
+      bk::merge_error_kernel<<<1, 1, 0, stream>>>((bk::DevResult*)((uint8_t*)s->scratch.buf.p + 64), merr);
+      CK(cudaGetLastError());
+    }
+    return BK_OK;
+  }
+  // 2b. one single-end extract launch per mate
   for (int k = 0; k < 2; ++k) {
     const int m = k == 0 ? first : 1 - first;
     CoLaunch co;

@@ -205,7 +205,7 @@ __host__ __device__ constexpr int cta_warps(bool paired) { return (paired ? 2 : 
 template <bool PAIRED, bool GENERAL, bool VAR = false, int ST = kStages, bool TABLE = false>
 __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extract_kernel(const __grid_constant__ KParams P) {
   static_assert(!VAR || GENERAL || TABLE, "variants are matched by the general kernel or by match_kernel");
-  static_assert(!TABLE || (!PAIRED && !GENERAL), "a launch that takes its matches from a table is single-end and has no search code");
+  static_assert(!TABLE || !GENERAL, "a launch that takes matches from a table has no search code");
   constexpr int kFrontPairs = PAIRED ? 2 : BK_SE_FRONTS;
   static_assert(ST % kScanWarps == 0 && ST % kFrontPairs == 0 && 4 + 2 * ST + (PAIRED ? 1 : 0) <= 16, "ring depth: a multiple of the scan / front warp counts, and 16 named barriers");
   extern __shared__ __align__(128) uint8_t smem[];
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
   const uint32_t tab = smem_u32(&cls_tab[m][0]);
 
   if (is_front && fp == 0) {
-    if (!TABLE) fill_tab(&cls_tab[m][0], pg, lane, GENERAL);
+    if (!TABLE || PAIRED) fill_tab(&cls_tab[m][0], pg, lane, GENERAL);
     if (lane == 0)
       for (int s = 0; s < ST; ++s) {
         mbar_init(&bar_full[m][s], 1);
@@ -382,7 +382,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       if (!PAIRED) {
         if (TABLE && active) t_own = __ldg(P.tab_in[0] + r0 + lane);
         if (P.tab_in[1] && active) t_oth = __ldg(P.tab_in[1] + r0 + lane);
+      } else if (TABLE) {  // paired: tab_in[m] is mate m's own table; a mate without one matches for itself (anchored)
+        if (P.tab_in[m] && active) t_own = __ldg(P.tab_in[m] + r0 + lane);
       }
+      const bool tabbed = TABLE && (!PAIRED || P.tab_in[m] != nullptr);
       RecView rv;
       rv.beg = rv.end = rv.fast = rv.head_len = rv.seq = rv.seq_len = rv.qual = rv.qual_len = 0;
       int ms = -1;
@@ -392,9 +395,9 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         __syncwarp();
         if (m == 0) { EVT(tile, 4) }
         const bool can = active && pg.present && rv.qual_len == rv.seq_len;  // unequal lengths never leave bk_tokenize
-        if (TABLE) {
+        if (tabbed) {
           ms = t_own;
-        } else if (VAR && var_me) {  // (lane per read, bytewise: see match_variants)
+        } else if (VAR && !TABLE && var_me) {  // (lane per read, bytewise: see match_variants)
           if (can) {
             ms = match_variants<false>(P.vprog[m], P.nvar[m], tab, rv.seq, rv.seq_len);
             if (ms < 0 && rc) {
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       const bk_devprog& pe = (VAR && var_me && ms >= 0) ? P.vprog[m][ms >> 24] : pg;  // the record's variant
       uint32_t olen = keep ? out_bytes(pe, rv, ms, trim) : 0;
       if (VAR && TABLE && pg.nins && keep && ms >= 0) {  // a parametric program: this record's own lengths
-        const EmitProg ep = emit_prog(pg, P.xtab[r0 + lane]);
+        const EmitProg ep = emit_prog(pg, P.xtab[m][r0 + lane]);
         olen = out_bytes(ep, rv, ms, trim);
       }
       uint32_t incl = olen;
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         const uint32_t rot = __popc(__ballot_sync(0xffffffffu, even)) >= 8 ? ((uint32_t)lane & 7u) + 1u : 0u;
         if (VAR && TABLE && pg.nins) {
           if (kept && !unc) {
-            const EmitProg ep = emit_prog(pg, ms >= 0 ? P.xtab[tile * R + lane] : 0ull);
+            const EmitProg ep = emit_prog(pg, ms >= 0 ? P.xtab[m][tile * R + lane] : 0ull);
             emit_part(ep, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
           }
         } else if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);

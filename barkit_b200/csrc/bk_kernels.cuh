@@ -68,8 +68,10 @@ struct KParams {
   // Optional (single-end launches): match tables left by earlier launches on the stream -- [0] this mate's own
   // (extract_kernel<.., TABLE = true> matches nothing itself), [1] the other mate's of the pair (keep rule); and
   // whether this launch leaves the count of kept pairs to the other mate's launch.
+  // A paired launch in TABLE form reads them differently: tab_in[m] is mate m's own table, null for a mate that matches
+  // for itself.
   const int32_t* tab_in[2];
-  const unsigned long long* xtab;  // with tab_in[0], parametric programs: the extras of every match (match_kernel)
+  const unsigned long long* xtab[2];  // parametric programs: the extras of every match of mate m (match_kernel)
   uint32_t no_nout;
 };
 

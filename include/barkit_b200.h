@@ -56,6 +56,10 @@ extern "C" {
  *                              round 1 (one launch; with two patterns: the paired kernel with both mates staged);
  *                              for measurements and tests, the output is identical */
 #define BK_FLAG_MATCH_IN_KERNEL 128u
+/*   BK_FLAG_SPLIT_TWO_PATTERNS two patterns of which one needs a search: after match_kernel, one single-end extract
+ *                              launch per mate instead of the default single paired launch that reads the match
+ *                              tables; for measurements and tests, the output is identical */
+#define BK_FLAG_SPLIT_TWO_PATTERNS 256u
 
 /* Layout guards: a binding written against this header (rust/barkit-extract/src/ffi.rs) must
  * agree with these sizes; they only ever grow at the end, together with the numbers here. */

@@ -79,6 +79,7 @@ pub const BK_FLAG_HOST_MATE_PINNED: u32 = 16;
 pub const BK_FLAG_VERBOSE: u32 = 32;
 pub const BK_FLAG_STAGE_BOTH_MATES: u32 = 64;
 pub const BK_FLAG_MATCH_IN_KERNEL: u32 = 128;
+pub const BK_FLAG_SPLIT_TWO_PATTERNS: u32 = 256;
 
 extern "C" {
     // pattern.rs

@@ -46,6 +46,10 @@ def run_pe(fq1, fq2, p1, p2, k=1, skip=False, rc=False, extra_flags=0):
         k1, k2, res_k = run_pe(fq1, fq2, p1, p2, k, skip, rc, extra_flags=_lib.FLAG_MATCH_IN_KERNEL | _lib.FLAG_DEVICE_BOTH_MATES)
         assert (o1, o2) == (k1, k2), "match_kernel + table and the in-kernel search differ"
         assert (res.n_out, res.n_match1, res.n_match2) == (res_k.n_out, res_k.n_match1, res_k.n_match2)
+    if extra_flags == 0 and p1 is not None and p2 is not None:   # ... and the two-launch form behind match_kernel
+        s1, s2, res_s = run_pe(fq1, fq2, p1, p2, k, skip, rc, extra_flags=_lib.FLAG_SPLIT_TWO_PATTERNS)
+        assert (o1, o2) == (s1, s2), "paired table launch and one single-end launch per mate differ"
+        assert (res.n_out, res.n_match1, res.n_match2) == (res_s.n_out, res_s.n_match1, res_s.n_match2)
     if (p1 is None) != (p2 is None) and extra_flags == 0:
         # One pattern: by default the pattern-less mate is assembled on the host (bk_submit) and the kernel sees a
         # single-end batch.  Every such test also runs the paired kernel (the pattern-less mate copied on the
@@ -469,7 +473,7 @@ def test_device_resident_matches_oracle_and_match_table():
         ma, mb = r1.regex.search(a.seq), r2.regex.search(b.seq)
         assert m1[i] == (ma.start() if ma else -1)
         assert m2[i] == (mb.start() if mb else -1)
-    assert res.launches == 6 and res.kernel_ms > 0   # per iteration: match_kernel on R2, one single-end launch per mate
+    assert res.launches == 4 and res.kernel_ms > 0   # per iteration: match_kernel on R2, the paired launch in table form
     ctx.close()
 
 

@@ -20,7 +20,10 @@ only = os.environ.get("BK_ONLY")
 for label, cfgname, paired, p1, p2, k in CASES:
     if only and only not in label:
         continue
-    for flags, fl in ((0, "match_kernel"), (_lib.FLAG_MATCH_IN_KERNEL, "in-kernel")):
+    forms = [(0, "match_kernel"), (_lib.FLAG_MATCH_IN_KERNEL, "in-kernel")]
+    if p2:
+        forms.append((_lib.FLAG_SPLIT_TWO_PATTERNS, "split"))
+    for flags, fl in forms:
         rc = label.endswith("-r")
         ctx = _lib.Context(_lib.Program(p1, k), _lib.Program(p2, k) if p2 else None, paired=paired, rc_barcodes=rc,
                            extra_flags=flags)
