@@ -110,6 +110,7 @@ SYMBOLS = {
                                      C.c_uint32, C.c_void_p, C.c_void_p]),
     "bk_bus_probe": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                C.POINTER(C.c_double)]),
+    "bk_host_mem_probe": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "bk_run": (C.c_int, [C.POINTER(RunArgs), C.c_char_p, C.c_size_t]),
 }
 

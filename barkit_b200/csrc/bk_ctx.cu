@@ -567,12 +567,15 @@ int enqueue_tabled(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const 
       }
     // the kernel writes a mate's matches (variant bits stripped) where the caller asked for them
     rc = enqueue_extract(ctx, s, stream, n, in1, in2, out1, cap1, out2, cap2, match1, match2, launches, &co);
-    if (rc != BK_OK) return rc;
-    if (n) {
-      bk::merge_error_kernel<<<1, 1, 0, stream>>>((bk::DevResult*)((uint8_t*)s->scratch.buf.p + 64), merr);
-      CK(cudaGetLastError());
+    if (rc == BK_OK) {
+      if (n) {
+        bk::merge_error_kernel<<<1, 1, 0, stream>>>((bk::DevResult*)((uint8_t*)s->scratch.buf.p + 64), merr);
+        CK(cudaGetLastError());
+      }
+      return BK_OK;
     }
-    return BK_OK;
+    // records too long to stage both mates at once: the single-end launches below need half the shared memory
+    if (rc != BK_E_CAPACITY) return rc;
   }
   // 2b. one single-end extract launch per mate
   for (int k = 0; k < 2; ++k) {
@@ -1364,6 +1367,37 @@ int bk_bus_probe(bk_ctx* ctx, uint64_t bytes, int iters, double* h2d_gbs, double
   const cudaError_t e = cudaGetLastError();
   cleanup();
   if (e != cudaSuccess) { ctx->last_error = std::string("bus probe: ") + cudaGetErrorString(e); return BK_E_CUDA; }
+  return BK_OK;
+}
+
+int bk_host_mem_probe(uint64_t bytes, int threads, int iters, double* gbs) {
+  if (!gbs || threads < 1 || iters < 1 || bytes < 4096) return BK_E_ARG;
+  std::vector<uint8_t*> src(threads, nullptr), dst(threads, nullptr);
+  bool ok = true;
+  for (int t = 0; t < threads; ++t) {
+    src[t] = (uint8_t*)malloc(bytes);
+    dst[t] = (uint8_t*)malloc(bytes);
+    ok = ok && src[t] && dst[t];
+  }
+  double best = 0;
+  if (ok) {
+    auto pass = [&](int t) { memcpy(dst[t], src[t], bytes); };
+    for (int it = 0; it <= iters; ++it) {  // the first pass faults the pages in
+      if (it == 0)
+        for (int t = 0; t < threads; ++t) memset(src[t], 1 + t, bytes);
+      timespec a, b;
+      clock_gettime(CLOCK_MONOTONIC, &a);
+      std::vector<std::thread> th;
+      for (int t = 0; t < threads; ++t) th.emplace_back(pass, t);
+      for (auto& x : th) x.join();
+      clock_gettime(CLOCK_MONOTONIC, &b);
+      const double s = (b.tv_sec - a.tv_sec) + (b.tv_nsec - a.tv_nsec) / 1e9;
+      if (it > 0 && s > 0) best = std::max(best, 2.0 * (double)bytes * threads / s / 1e9);
+    }
+  }
+  for (int t = 0; t < threads; ++t) { free(src[t]); free(dst[t]); }
+  if (!ok) return BK_E_CAPACITY;
+  *gbs = best;
   return BK_OK;
 }
 

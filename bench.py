@@ -677,12 +677,30 @@ def main():
         barrier()
         bus_sum = sum_over_ranks(duplex)
         moved = (last[0] + last[1]) * world * args.steps / s_auto / 1e9     # GB/s that crossed the links in the default mode
+        for mname, md in modes.items():   # ... and in every pinned mode (all ranks): pairs/s x bytes per pair over the links
+            md["bus_used_gbs"] = md["value"] * (md["h2d_bytes_per_step"] + md["d2h_bytes_per_step"]) / Q / 1e9
+            md["bus_frac"] = md["bus_used_gbs"] / bus_sum if bus_sum else None
+        # The host's memory system: every byte of a pair's input is read from host memory and every byte of its output
+        # written to it exactly once, whichever side does it (DMA engine, or the cores assembling the host-side mate).
+        # What all host cores move with plain copies, measured here with the GPUs idle, bounds that.
+        host_mem_peak = None
+        if rank == 0:
+            g = C.c_double(0.0)
+            if _lib.lib.bk_host_mem_probe(128 << 20, host_threads(), 3, C.byref(g)) == 0:
+                host_mem_peak = g.value
+        barrier()
+        bytes_in_out = 2 * nb + int(res.out1_len) + int(res.out2_len)      # per step: both mates in, both outputs out
+        host_mem_used = v_auto * bytes_in_out / Q / 1e9
         e2e = {"value": v_auto, "unit": UNIT,
                "h2d_bytes_per_step": int(last[0]), "d2h_bytes_per_step": int(last[1]),
                "pairs_per_step": Q, "ms_per_step": 1e3 * s_auto / args.steps, "host_threads": lib_threads,
                "modes": modes,
                "bus_peak_gbs": bus_sum, "bus_h2d_gbs_rank0": up, "bus_d2h_gbs_rank0": down,
                "bus_used_gbs": moved, "bus_frac": moved / bus_sum if bus_sum else None,
+               "host_mem_peak_gbs": host_mem_peak, "host_mem_used_gbs": host_mem_used,
+               "host_mem_frac": host_mem_used / host_mem_peak if host_mem_peak else None,
+               "limiter": ("host memory system" if host_mem_peak and host_mem_used / host_mem_peak >= (moved / bus_sum if bus_sum else 0)
+                           else "host links"),
                "note": "bk_submit/bk_wait with pinned host buffers, 2 slots in flight; h2d/d2h bytes as the "
                        "library counts them (text + record offsets in, FASTQ text + result + match table out). "
                        "value = the library's default: R2 has no pattern in this config, so it stays on the host and "
@@ -690,7 +708,10 @@ def main():
                        "measures that to be slower than the bus. modes = the two choices pinned, and raw_text_device_tokenizer = "
                        "bk_submit_text: no offsets from the host, both mates tokenised on the device in front of the extract "
                        "kernels (what the `barkit` command line uses). bus_peak_gbs = pinned "
-                       "H2D + D2H at once on every rank's GPU (sum over ranks), measured in this run."}
+                       "H2D + D2H at once on every rank's GPU (sum over ranks), measured in this run. host_mem_peak_gbs = "
+                       "read + written bytes per second of plain copies on all host cores with the GPUs idle (bk_host_mem_probe); "
+                       "host_mem_used_gbs = the default mode's pairs/s x (input + output bytes of a pair), each of which crosses "
+                       "host memory once whichever side moves it; limiter = the larger of host_mem_frac and bus_frac."}
     else:
         e2e_launches = 0
 

@@ -263,6 +263,11 @@ int bk_generate_device(bk_ctx* ctx, const bk_syn_config* cfg, int mate, uint64_t
  * host alone, then both directions at once on two streams.  GB/s (1e9 bytes); duplex = both directions summed.
  * Several contexts probing at the same time share the host's memory system, which is the point. */
 int bk_bus_probe(bk_ctx* ctx, uint64_t bytes, int iters, double* h2d_gbs, double* d2h_gbs, double* duplex_gbs);
+/* Measurement aid (bench.py): what the host's memory system moves when `threads` threads each copy `bytes` bytes
+ * from one private buffer to another `iters` times (a plain memcpy: what the host-side assembly of a pattern-less
+ * mate and, from the memory's point of view, the DMA engines do).  GB/s counts bytes read + bytes written.  The end
+ * to end rate of this path is bounded by this figure over the bytes a pair moves through host memory. */
+int bk_host_mem_probe(uint64_t bytes, int threads, int iters, double* gbs);
 
 /* ---- whole-run form: run::run (run.rs:10-60), file in -> file out ---------------------------- */
 typedef struct bk_run_args {

@@ -401,6 +401,33 @@ def test_long_records_shrink_the_tile():
     assert out == bo.extract_se(fq, pat, 1)
 
 
+def test_long_records_through_match_kernel():
+    """match_kernel sizes a warp's buffer from max_rec_bytes: fewer reads per tile first, then fewer warps per CTA
+    (one warp may take most of the SM's shared memory).  Variants, a parametric program and two patterns with a search
+    on reads of 1.5-4 kB and of 10-18 kB; a parametric capture can double the record."""
+    rnd = random.Random(15)
+    for n, lo, hi in ((300, 1500, 4000), (40, 10000, 18000)):
+        heads = [rnd.choice([3, 23, 60]) for _ in range(n)]
+        fq1 = ragged_fastq(rnd, n, 1, plant=[b"GATTACA"], head_lens=heads, min_len=lo, max_len=hi)
+        fq2 = ragged_fastq(rnd, n, 2, plant=[b"ATGCCAT"], head_lens=heads, min_len=lo, max_len=hi)
+        for pat in ("(?P<SB>[ATGC]{2,4})gattaca(?P<UMI>[ATGCN]{6})", "^(?P<UMI>[ATGCN]{100,}?)gattaca(?P<CB>[ACGT]*)"):
+            if hi > 8000 and "*" in pat:
+                # two unbounded captures: the output tile is sized for a record three times its input (par_growth), which
+                # together with the four staged input tiles no longer fits the SM for 36 kB records -> BK_E_CAPACITY
+                with pytest.raises(_lib.BarkitError) as e:
+                    run_se(fq1, pat, 1, extra_flags=_lib.FLAG_VERBOSE)
+                assert e.value.status == _lib.BK_E_CAPACITY
+                continue
+            out, _ = run_se(fq1, pat, 1)
+            assert out == bo.extract_se(fq1, pat, 1), (pat, n)
+        p1, p2 = "^(?P<UMI>[ATGCN]{12})", "(?P<CB>[ACGT]{6})atgccat"
+        # (36 kB records: staging both mates at once does not fit, so neither the paired kernel of
+        # BK_FLAG_MATCH_IN_KERNEL nor the paired table launch can run; the default falls back to one single-end
+        # launch per mate.  Any extra flag keeps run_pe from also trying the other forms.)
+        o1, o2, _ = run_pe(fq1, fq2, p1, p2, 1, extra_flags=_lib.FLAG_HOST_MATE_PINNED if hi > 8000 else 0)
+        assert (o1, o2) == bo.extract_pe(fq1, fq2, p1, p2, 1)
+
+
 def test_output_capacity_error_is_reported():
     ctx = make_ctx("^(?P<UMI>[ATGCN]{12})")
     fq = bksyn.generate(bksyn.CONFIGS["C1"], 1, 0, 1000)
