@@ -681,6 +681,46 @@ __device__ __forceinline__ bool par_segment_ok(uint32_t tab, uint32_t seq, uint3
   return true;
 }
 
+// When the piece behind an insertion begins with a short literal (the usual shape: `[ACGT]{8,}atgccat`), trying every
+// e costs a literal compare each -- up to the read's length of them.  Instead the bit-parallel filter of the unanchored
+// search (bs_planes, below) marks, 32 text positions at a time, where that literal can sit within its mismatch budget,
+// and only those e are tried: the nearest marked position at or below `hi` (greedy) or at or above `lo` (lazy).
+// `lit0` = shared address of the text position the literal has with e = 0.  Forward strand only.
+template <int NW>
+__device__ __forceinline__ void bs_planes(uint32_t addr, uint32_t& p0, uint32_t& p1);
+__device__ __forceinline__ bool bs_eligible(uint32_t kind, uint32_t len, uint32_t k);
+constexpr uint32_t kNoExtra = 0xFFFFFFFFu;
+__device__ __noinline__ uint32_t par_next_lit(uint32_t tab, uint32_t op_len, uint32_t op_k, uint32_t op_idx, uint32_t lit0,
+                                              uint32_t lo, uint32_t hi, uint32_t lazy) {
+  uint32_t w = lazy ? lo : (hi >= 31u && hi - 31u > lo ? hi - 31u : lo);  // first window: [w, w + 31]
+  while (true) {
+    uint32_t a0, a1, b0, b1;
+    bs_planes<8>(lit0 + w, a0, a1);
+    bs_planes<2>(lit0 + w + 32u, b0, b1);
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < op_len; ++i) {
+      const uint32_t c = lds8(tab + kTabLit + op_idx + i);
+      const uint32_t x0 = (c & 2u) ? 0xFFFFFFFFu : 0u, x1 = (c & 4u) ? 0xFFFFFFFFu : 0u;
+      const uint32_t mm = (__funnelshift_r(a0, b0, i) ^ x0) | (__funnelshift_r(a1, b1, i) ^ x1);
+      const uint32_t carry = c0 & mm;
+      c0 ^= mm;
+      c2 |= c1 & carry;
+      c1 ^= carry;
+    }
+    uint32_t cand = ~c2 & (op_k == 0u ? ~(c0 | c1) : op_k == 1u ? ~c1 : op_k == 2u ? ~(c1 & c0) : 0xFFFFFFFFu);
+    if (hi - w < 31u) cand &= (2u << (hi - w)) - 1u;  // (w >= lo always)
+    if (cand) return lazy ? w + (uint32_t)__ffs(cand) - 1u : w + 31u - (uint32_t)__clz(cand);
+    if (lazy) {
+      if (hi - w < 32u) return kNoExtra;
+      w += 32u;
+    } else {
+      if (w == lo) return kNoExtra;
+      w = w >= 32u && w - 32u > lo ? w - 32u : lo;  // (windows may overlap at the low end: harmless)
+    }
+  }
+}
+
 template <bool RC>
 __device__ __noinline__ int match_par(uint32_t tab, uint32_t seq, uint32_t L, unsigned long long* extras) {
   const uint4 h = lds128(tab + kTabHdr);  // nops, total_len (minimum), anchor_start, anchor_end
@@ -688,7 +728,43 @@ __device__ __noinline__ int match_par(uint32_t tab, uint32_t seq, uint32_t L, un
   *extras = 0ull;
   if (L < T) return -1;
   const uint32_t s_last = h.z ? 0u : L - T;
+  // Unanchored: a start can only match if the program's first short literal sits in reach of it -- between its offset
+  // in the minimal layout (fA) and that plus everything the insertions in front of it may add (fB).  The literal's
+  // possible positions come from the same bit-parallel filter, nearest first; starts out of reach are skipped, and
+  // when no position is left the read has no match.
+  bool filt = false;
+  MOp fop;
+  fop.len = fop.k = fop.idx = 0;
+  uint32_t fA = 0, fB = 0, nextp = 0;
+  bool havep = false;
+  if (!RC && !h.z) {
+    for (uint32_t o = 0; o < nops && !filt; ++o) {
+      const MOp op = tab_op(tab, o);
+      if (!bs_eligible(op.kind, op.len, op.k)) continue;
+      uint32_t reach = 0;
+      for (uint32_t i = 0; i < nins; ++i) {
+        const uint2 in = lds64(tab + kTabIns + 8u + 8u * i);
+        if ((in.y >> 24) <= o) reach += min(in.x >> 16, L);  // insertion i lies in front of op o
+      }
+      fop = op;
+      fA = op.off;
+      fB = op.off + min(reach, L);
+      filt = true;
+    }
+  }
   for (uint32_t s = 0; s <= s_last; ++s) {
+    if (filt) {
+      if (!havep || nextp < s + fA) {
+        if (s + fA + fop.len > L) return -1;
+        nextp = par_next_lit(tab, fop.len, fop.k, fop.idx, seq, s + fA, L - fop.len, 1u);
+        havep = true;
+        if (nextp == kNoExtra) return -1;
+      }
+      if (nextp > s + fB) {
+        s = nextp - fB;
+        if (s > s_last) return -1;
+      }
+    }
     uint32_t e[BK_MAX_INS], r[BK_MAX_INS];
     uint32_t shift = 0, d = 0;
     if (!par_segment_ok<RC>(tab, seq, L, 0u, nins ? (lds32(tab + kTabIns + 8u + 4u) >> 24) : nops, s)) continue;
@@ -711,21 +787,39 @@ __device__ __noinline__ int match_par(uint32_t tab, uint32_t seq, uint32_t L, un
         while (run < lim && ((lds8(tab + fetch<RC>(tab, seq, L, a + run)) >> cls) & 1u)) ++run;
         r[d] = run;
         e[d] = ((in.y >> 8) & 0xFFu) ? 0u : run;
-      } else {
-        // next choice at level d, or give the level up
-        const uint32_t lazy = (lds32(tab + kTabIns + 8u + 8u * d + 4u) >> 8) & 0xFFu;
-        if (lazy ? e[d] < r[d] : e[d] > 0u) {
-          e[d] = lazy ? e[d] + 1u : e[d] - 1u;
-        } else {
-          if (d == 0) break;
-          --d;
-          shift -= e[d];
-          continue;
-        }
       }
-      // the piece behind insertion d under this choice
       const uint32_t o0 = lds32(tab + kTabIns + 8u + 8u * d + 4u) >> 24;
       const uint32_t o1 = d + 1u < nins ? lds32(tab + kTabIns + 8u + 8u * (d + 1u) + 4u) >> 24 : nops;
+      const uint32_t lazy = (lds32(tab + kTabIns + 8u + 8u * d + 4u) >> 8) & 0xFFu;
+      // the choices at level d in priority order: every e in [0, run], or -- when the piece behind the insertion begins
+      // with a short literal -- only those at which that literal can sit (par_next_lit)
+      MOp lop;
+      lop.kind = 0xFFu;
+      if (!RC && o0 < o1) lop = tab_op(tab, o0);
+      const bool guided = !RC && o0 < o1 && r[d] >= 8u && bs_eligible(lop.kind, lop.len, lop.k);
+      bool have;
+      if (guided) {
+        const uint32_t lit0 = seq + s + shift + lop.off;
+        uint32_t nx;
+        if (enter) nx = par_next_lit(tab, lop.len, lop.k, lop.idx, lit0, 0u, r[d], lazy);
+        else if (lazy) nx = e[d] < r[d] ? par_next_lit(tab, lop.len, lop.k, lop.idx, lit0, e[d] + 1u, r[d], 1u) : kNoExtra;
+        else nx = e[d] > 0u ? par_next_lit(tab, lop.len, lop.k, lop.idx, lit0, 0u, e[d] - 1u, 0u) : kNoExtra;
+        have = nx != kNoExtra;
+        if (have) e[d] = nx;
+      } else if (enter) {
+        have = true;
+      } else {  // next choice at level d
+        have = lazy ? e[d] < r[d] : e[d] > 0u;
+        if (have) e[d] = lazy ? e[d] + 1u : e[d] - 1u;
+      }
+      if (!have) {  // give the level up
+        enter = false;
+        if (d == 0) break;
+        --d;
+        shift -= e[d];
+        continue;
+      }
+      // the piece behind insertion d under this choice
       if (par_segment_ok<RC>(tab, seq, L, o0, o1, s + shift + e[d])) {
         shift += e[d];
         ++d;
