@@ -784,6 +784,15 @@ __device__ __noinline__ int match_par(uint32_t tab, uint32_t seq, uint32_t L, un
         const uint32_t a = s + (in.x & 0xFFFFu) + shift, room = L - (s + T + shift);
         const uint32_t lim = min(in.x >> 16, room), cls = in.y & 0xFFu;
         uint32_t run = 0;
+        if (!RC) {  // four bytes per step while whole words are in the class (an unbounded run is most of the read)
+          const uint32_t p0 = seq + a;
+          while (run + 4u <= lim) {
+            const uint32_t q = p0 + run, v = __funnelshift_r(lds32(q & ~3u), lds32((q & ~3u) + 4u), (q & 3u) * 8u);
+            const uint32_t m4 = lds8(tab + (v & 0xFFu)) & lds8(tab + ((v >> 8) & 0xFFu)) & lds8(tab + ((v >> 16) & 0xFFu)) & lds8(tab + (v >> 24));
+            if (!((m4 >> cls) & 1u)) break;
+            run += 4u;
+          }
+        }
         while (run < lim && ((lds8(tab + fetch<RC>(tab, seq, L, a + run)) >> cls) & 1u)) ++run;
         r[d] = run;
         e[d] = ((in.y >> 8) & 0xFFu) ? 0u : run;

@@ -112,6 +112,11 @@ def test_derived_examples():
     assert run_se(fqc, "^(?P<UMI>[ATGCN]{4})ccc", 0, rc=True)[0] == b"@q UMI:TTAA:ABCD\nACGT\n+\nHIJK\n"
 
 
+def test_readme_header_format():   # the reference's README.md:37
+    out, _ = run_se(b"@SEQ_ID\nATGCATGCATGCGG\n+\n????????????II\n", "^(?P<UMI>[ATGC]{4})(?P<CB>[ATGC]{4})(?P<SB>[ATGC]{4})", 0)
+    assert out == b"@SEQ_ID UMI:ATGC:???? CB:ATGC:???? SB:ATGC:????\nGG\n+\nII\n"
+
+
 def test_pe_policy():   # run.rs:149-160
     fq1 = b"@a 1\nACGTTTTT\n+\nIIIIHHHH\n@b 1\nNNNNNNNN\n+x\n12345678\n@c 1\nNAAAAAAA\n+\nabcdefgh\n"
     fq2 = b"@a 2\nGGGGCCCC\n+\nJJJJKKKK\n@b 2\nGGGGAAAA\n+\n87654321\n@c 2\nTTTTTTTT\n+\nhgfedcba\n"

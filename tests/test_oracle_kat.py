@@ -131,3 +131,13 @@ def test_pe_policy():
     # pair a: both match; pair b: only mate 2 (mate 1 kept unchanged, '+x' normalised); pair c: dropped
     assert o1 == b"@a 1 UMI:ACGT:IIII\nTTTT\n+\nHHHH\n@b 1\nNNNNNNNN\n+\n12345678\n"
     assert o2 == b"@a 2 CB:GGGG:JJJJ\nCCCC\n+\nKKKK\n@b 2 CB:GGGG:8765\nAAAA\n+\n4321\n"
+
+
+def test_readme_header_format():
+    """README.md:37 of the reference documents the rewritten header: `@SEQ_ID UMI:ATGC:???? CB:ATGC:???? SB:ATGC:????`
+    -- the only statement of row H's output format (parse.rs:161-168) that the reference holds outside its code:
+    one space in front of every barcode, NAME ':' sequence ':' quality, in pattern order."""
+    pat = "^(?P<UMI>[ATGC]{4})(?P<CB>[ATGC]{4})(?P<SB>[ATGC]{4})"
+    out = bo.extract_se(b"@SEQ_ID\nATGCATGCATGCGG\n+\n????????????II\n", pat, 0)
+    assert out.split(b"\n")[0] == b"@SEQ_ID UMI:ATGC:???? CB:ATGC:???? SB:ATGC:????"
+    assert out == b"@SEQ_ID UMI:ATGC:???? CB:ATGC:???? SB:ATGC:????\nGG\n+\nII\n"
