@@ -689,7 +689,329 @@ int find_quantifiers(const std::string& p, std::vector<Quant>* out, std::string*
 
 }  // namespace
 
+// ---- alternation and repeated groups ---------------------------------------------------
+//
+// `(atgccat|gattaca)`, `(AC){1,3}`, `(a|b){2}`: the regex crate resolves these by backtracking as well -- an
+// alternation tries its branches in order, a greedy repetition prefers one more round over stopping -- so a pattern
+// that holds them is a list of fixed-length patterns in that priority order, exactly as bounded `{m,n}` on an atom is.
+// The pattern is parsed into a small tree (sequence, alternation, group, repetition, atom), the tree is unfolded
+// depth-first in the engine's decision order, and every unfolding is lowered by compile_fixed; parts of the tree with a
+// single unfolding are re-emitted as their source text, so nothing else about the pattern changes.  Taken only when
+// the pattern has a `|`, a variable repetition of a group, or a repeated group with choices inside; at most
+// BK_MAX_VARIANTS unfoldings.  Refused, not approximated: named groups inside a branch or a repeated group (a group that
+// may not take part in the match), repetition of a group that can match the empty string, alternation at the top level
+// (anchors would bind to single branches), unbounded repetition of anything but a one-byte atom, and unbounded
+// repetition together with alternatives.
+
+namespace {
+
+struct RNode {
+  enum Type { ATOM, GROUP, CONCAT, ALT, REPEAT } type = ATOM;
+  size_t b = 0, e = 0;        // source span
+  std::string prefix;         // GROUP: "(" | "(?:" | "(?P<NAME>" | "(?<NAME>"
+  bool named = false;         // GROUP
+  long lo = 1, hi = 1;        // REPEAT (hi = -1: unbounded)
+  bool lazy = false;
+  std::vector<RNode> kids;
+};
+
+struct RParser {
+  const std::string& p;
+  std::string err;
+  int status = BK_OK;
+  explicit RParser(const std::string& s) : p(s) {}
+  bool fail(int st, const std::string& m) { if (status == BK_OK) { status = st; err = m; } return false; }
+  bool unsupported(const std::string& what) { return fail(BK_E_UNSUPPORTED, "unsupported pattern construct (" + what + ")"); }
+  bool regex_error(const std::string& m) { return fail(BK_E_PATTERN, "Regex error: " + m); }
+
+  bool parse_alt(size_t& i, int depth, RNode* out) {
+    RNode alt;
+    alt.type = RNode::ALT;
+    alt.b = i;
+    for (;;) {
+      RNode seq;
+      if (!parse_concat(i, depth, &seq)) return false;
+      alt.kids.push_back(seq);
+      if (i < p.size() && p[i] == '|') { ++i; continue; }
+      break;
+    }
+    alt.e = i;
+    if (alt.kids.size() == 1) *out = alt.kids[0];
+    else *out = alt;
+    return true;
+  }
+
+  bool parse_concat(size_t& i, int depth, RNode* out) {
+    out->type = RNode::CONCAT;
+    out->b = i;
+    while (i < p.size() && p[i] != '|') {
+      if (p[i] == ')') {
+        if (depth == 0) return regex_error("unopened group");
+        break;
+      }
+      RNode item;
+      if (!parse_item(i, depth, &item)) return false;
+      out->kids.push_back(item);
+    }
+    out->e = i;
+    return true;
+  }
+
+  bool parse_item(size_t& i, int depth, RNode* out) {
+    RNode atom;
+    atom.b = i;
+    const char c = p[i];
+    if (c == '(') {
+      atom.type = RNode::GROUP;
+      size_t j = i + 1;
+      if (j < p.size() && p[j] == '?') {
+        if (p.compare(j, 3, "?P<") == 0 || (p.compare(j, 2, "?<") == 0 && j + 2 < p.size() && p[j + 2] != '=' && p[j + 2] != '!')) {
+          atom.named = true;
+          while (j < p.size() && p[j] != '>') ++j;
+          if (j >= p.size()) return regex_error("unclosed capture group name");
+          ++j;
+        } else if (p.compare(j, 2, "?:") == 0) {
+          j += 2;
+        } else {
+          return unsupported("group flags / look-around");
+        }
+      }
+      atom.prefix = p.substr(i, j - i);
+      i = j;
+      RNode inner;
+      if (!parse_alt(i, depth + 1, &inner)) return false;
+      if (i >= p.size() || p[i] != ')') return regex_error("unclosed group");
+      ++i;
+      atom.kids.push_back(inner);
+    } else if (c == '[') {
+      size_t j = i + 1;
+      if (j < p.size() && p[j] == '^') ++j;
+      if (j < p.size() && p[j] == ']') ++j;  // a leading ']' is a member
+      while (j < p.size() && p[j] != ']') j += p[j] == '\\' ? 2 : 1;
+      if (j >= p.size()) return regex_error("unclosed character class");
+      i = j + 1;
+    } else if (c == '\\') {
+      if (i + 1 >= p.size()) return regex_error("incomplete escape sequence");
+      i += 2;
+    } else if (c == '?' || c == '*' || c == '+' || c == '{') {
+      return regex_error("repetition operator missing expression");
+    } else {
+      ++i;
+    }
+    atom.e = i;
+    // repetition suffix
+    if (i < p.size() && (p[i] == '?' || p[i] == '*' || p[i] == '+' || p[i] == '{')) {
+      if (c == '^' || c == '$') return regex_error("repetition operator missing expression");
+      RNode rep;
+      rep.type = RNode::REPEAT;
+      rep.b = atom.b;
+      if (p[i] == '?') { rep.lo = 0; rep.hi = 1; ++i; }
+      else if (p[i] == '*') { rep.lo = 0; rep.hi = -1; ++i; }
+      else if (p[i] == '+') { rep.lo = 1; rep.hi = -1; ++i; }
+      else {
+        size_t j = i + 1;
+        long lo = 0, hi = 0;
+        size_t d1 = 0, d2 = 0;
+        while (j < p.size() && p[j] >= '0' && p[j] <= '9' && lo < 100000) { lo = lo * 10 + (p[j] - '0'); ++j; ++d1; }
+        if (d1 == 0) return regex_error("repetition quantifier expects a valid decimal");
+        if (j < p.size() && p[j] == ',') {
+          ++j;
+          while (j < p.size() && p[j] >= '0' && p[j] <= '9' && hi < 100000) { hi = hi * 10 + (p[j] - '0'); ++j; ++d2; }
+          if (d2 == 0) hi = -1;
+          else if (hi < lo) return regex_error("invalid repetition count range, the start must be <= the end");
+        } else {
+          hi = lo;
+        }
+        if (j >= p.size() || p[j] != '}') return regex_error("unclosed counted repetition");
+        rep.lo = lo;
+        rep.hi = hi;
+        i = j + 1;
+      }
+      if (i < p.size() && p[i] == '?') { rep.lazy = true; ++i; }
+      if (i < p.size() && (p[i] == '?' || p[i] == '*' || p[i] == '+' || p[i] == '{')) return unsupported("stacked repetition");
+      rep.e = i;
+      rep.kids.push_back(atom);
+      *out = rep;
+    } else {
+      *out = atom;
+    }
+    return true;
+  }
+};
+
+bool rnode_has(const RNode& n, bool (*pred)(const RNode&)) {
+  if (pred(n)) return true;
+  for (const auto& k : n.kids)
+    if (rnode_has(k, pred)) return true;
+  return false;
+}
+bool is_named_group(const RNode& n) { return n.type == RNode::GROUP && n.named; }
+bool is_variable(const RNode& n) { return (n.type == RNode::REPEAT && n.lo != n.hi) || (n.type == RNode::ALT && n.kids.size() > 1); }
+bool is_unbounded(const RNode& n) { return n.type == RNode::REPEAT && n.hi < 0; }
+bool needs_tree(const RNode& n) {  // what find_quantifiers + substitution cannot express
+  return (n.type == RNode::ALT && n.kids.size() > 1) ||
+         (n.type == RNode::REPEAT && !n.kids.empty() && n.kids[0].type == RNode::GROUP &&
+          (n.lo != n.hi || rnode_has(n.kids[0], is_variable)));
+}
+// fewest bytes a match of n can have (anchors count as atoms here; the lowering refuses them inside a pattern anyway)
+long min_len(const RNode& n) {
+  switch (n.type) {
+    case RNode::ATOM: return 1;
+    case RNode::GROUP: return min_len(n.kids[0]);
+    case RNode::CONCAT: { long t = 0; for (const auto& k : n.kids) t += min_len(k); return t; }
+    case RNode::ALT: { long t = -1; for (const auto& k : n.kids) { const long m = min_len(k); t = t < 0 || m < t ? m : t; } return t < 0 ? 0 : t; }
+    case RNode::REPEAT: return n.lo * min_len(n.kids[0]);
+  }
+  return 0;
+}
+
+struct Unfolder {
+  const std::string& p;
+  std::string err;
+  int status = BK_OK;
+  explicit Unfolder(const std::string& s) : p(s) {}
+  bool unsupported(const std::string& what) {
+    if (status == BK_OK) { status = BK_E_UNSUPPORTED; err = "unsupported pattern construct (" + what + ")"; }
+    return false;
+  }
+  std::string src(const RNode& n) const { return p.substr(n.b, n.e - n.b); }
+
+  // every unfolding of n in the engine's priority order
+  bool unfold(const RNode& n, std::vector<std::string>* out) {
+    out->clear();
+    if (!rnode_has(n, is_variable) || (n.type == RNode::REPEAT && n.hi < 0)) {  // one unfolding: the source text itself
+      out->push_back(src(n));
+      return true;
+    }
+    switch (n.type) {
+      case RNode::ATOM:
+        out->push_back(src(n));
+        return true;
+      case RNode::GROUP: {
+        std::vector<std::string> inner;
+        if (!unfold(n.kids[0], &inner)) return false;
+        for (const auto& s : inner) out->push_back(n.prefix + s + ")");
+        return true;
+      }
+      case RNode::CONCAT: {
+        out->push_back("");
+        for (const auto& k : n.kids) {
+          std::vector<std::string> ks, next;
+          if (!unfold(k, &ks)) return false;
+          if (out->size() * ks.size() > BK_MAX_VARIANTS) return unsupported("more than " + std::to_string(BK_MAX_VARIANTS) + " combinations of alternatives and repetition counts");
+          for (const auto& a : *out)      // the earlier element's choice varies slowest
+            for (const auto& b : ks) next.push_back(a + b);
+          out->swap(next);
+        }
+        return true;
+      }
+      case RNode::ALT: {
+        for (const auto& k : n.kids) {
+          if (rnode_has(k, is_named_group)) return unsupported("named capture group inside an alternative");
+          std::vector<std::string> ks;
+          if (!unfold(k, &ks)) return false;
+          out->insert(out->end(), ks.begin(), ks.end());
+          if (out->size() > BK_MAX_VARIANTS) return unsupported("more than " + std::to_string(BK_MAX_VARIANTS) + " combinations of alternatives and repetition counts");
+        }
+        return true;
+      }
+      case RNode::REPEAT: {
+        const RNode& x = n.kids[0];
+        if (rnode_has(x, is_named_group)) return unsupported("repetition of a named capture group");
+        std::vector<std::string> xs;
+        if (rnode_has(x, is_variable)) {
+          // (a round that may match nothing has engine-specific rules for when the repetition ends)
+          if (min_len(x) == 0) return unsupported("repetition of a group that can match the empty string");
+          if (!unfold(x, &xs)) return false;
+        } else {
+          xs.push_back(src(x));
+        }
+        if (xs.size() == 1) {  // counts only: greedy from the largest, lazy from the smallest
+          for (long r = n.lazy ? n.lo : n.hi; n.lazy ? r <= n.hi : r >= n.lo; r += n.lazy ? 1 : -1) {
+            out->push_back(xs[0] + "{" + std::to_string(r) + "}");
+            if (out->size() > BK_MAX_VARIANTS) return unsupported("more than " + std::to_string(BK_MAX_VARIANTS) + " combinations of alternatives and repetition counts");
+          }
+          return true;
+        }
+        // several unfoldings per round: depth-first in decision order -- at every round the engine prefers another
+        // round (its alternatives in order) over stopping when greedy, stopping first when lazy
+        return rounds(xs, n.lo, n.hi, n.lazy, 0, "", out);
+      }
+    }
+    return true;
+  }
+
+  bool rounds(const std::vector<std::string>& xs, long lo, long hi, bool lazy, long done, const std::string& acc,
+              std::vector<std::string>* out) {
+    const bool may_stop = done >= lo, may_go = done < hi;
+    if (lazy && may_stop) out->push_back(acc);
+    if (may_go)
+      for (const auto& x : xs)
+        if (!rounds(xs, lo, hi, lazy, done + 1, acc + x, out)) return false;
+    if (!lazy && may_stop) out->push_back(acc);
+    if (out->size() > BK_MAX_VARIANTS) return unsupported("more than " + std::to_string(BK_MAX_VARIANTS) + " combinations of alternatives and repetition counts");
+    return true;
+  }
+};
+
+}  // namespace
+
+// -> BK_OK and *handled = true when the pattern went through the tree form; *handled = false: not needed, use the
+// quantifier substitution below
+static int compile_tree(const std::string& pattern, size_t max_error, Program* prog, std::string* err, bool* handled) {
+  *handled = false;
+  // anchors stay outside the tree (they are atoms to it, and only legal at the very ends: compile_fixed checks)
+  RParser ps(pattern);
+  RNode root;
+  size_t i = 0;
+  if (!ps.parse_alt(i, 0, &root)) return BK_OK;  // malformed: the established path reports it in the reference's words
+  if (i != pattern.size()) return BK_OK;
+  if (!rnode_has(root, needs_tree)) return BK_OK;
+  *handled = true;
+  if (rnode_has(root, is_unbounded)) {
+    *err = "unsupported pattern construct (unbounded repetition together with alternatives or repeated groups)";
+    return BK_E_UNSUPPORTED;
+  }
+  if (root.type == RNode::ALT && root.kids.size() > 1) {
+    // a top-level `a|b`: the anchors would bind to single branches (`^a|b$`), which the fixed form cannot say
+    *err = "unsupported pattern construct (alternation at the top level: put it in a group)";
+    return BK_E_UNSUPPORTED;
+  }
+  Unfolder uf(pattern);
+  std::vector<std::string> forms;
+  if (!uf.unfold(root, &forms)) { *err = uf.err; return uf.status; }
+  {
+    std::vector<FuzzySpan> spans;
+    int rc = expand(pattern, max_error, &prog->expanded, &spans, err);
+    if (rc != BK_OK) return rc;
+  }
+  const std::string expanded = prog->expanded;
+  prog->variants.clear();
+  for (const auto& f : forms) {
+    Program one;
+    int rc = compile_fixed(f, max_error, &one, err);
+    if (rc != BK_OK) return rc;
+    if (!prog->variants.empty()) {  // every form must rewrite the header the same way
+      const bk_devprog& a = prog->variants[0];
+      bool same = a.ncaps == one.dev.ncaps && a.anchor_start == one.dev.anchor_start && a.anchor_end == one.dev.anchor_end;
+      for (uint32_t c = 0; same && c < a.ncaps; ++c)
+        same = a.caps[c].name_len == one.dev.caps[c].name_len && !memcmp(a.caps[c].name, one.dev.caps[c].name, 3);
+      if (!same) { *err = "unsupported pattern construct (alternatives with different capture groups)"; return BK_E_UNSUPPORTED; }
+    }
+    prog->variants.push_back(one.dev);
+  }
+  prog->dev = prog->variants[0];
+  prog->expanded = expanded;
+  return BK_OK;
+}
+
 int compile(const std::string& pattern, size_t max_error, Program* prog, std::string* err) {
+  {
+    bool handled = false;
+    const int rct = compile_tree(pattern, max_error, prog, err, &handled);
+    if (handled) return rct;
+    prog->variants.clear();
+  }
   std::vector<Quant> qs;
   int rc = find_quantifiers(pattern, &qs, err);
   if (rc != BK_OK) return rc;

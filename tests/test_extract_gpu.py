@@ -328,6 +328,33 @@ def test_variable_repetition_paired_end():
             assert o1 == e1 and o2 == e2, (p1, p2, k, skip, rc)
 
 
+ALTERNATION = [
+    ("(?P<CB>[ACGT]{6})(atgccat|gattaca)", 1), ("^(?P<UMI>[ACGT]{4})(AC|G|TTT)(?P<CB>[ACGTN]{3})", 0),
+    ("(?P<UMI>[ACGT]{4})(AC){1,3}G", 0), ("^(?P<UMI>[ACGT]{3})(A|CG){1,2}?T", 0), ("(?P<UMI>[ACGT]{4})(A?C){3}", 0),
+    ("(?P<UMI>[ACGT]{4})([AT]{1,2}G){2}", 0), ("(?P<UMI>AC|G[ACGT]{2})gattaca$", 2), ("^(?P<UMI>[ACGT]{4})((A|C)T){2}(?P<CB>[ACGT]{2,3})", 0),
+    ("(?P<SB>[ACGT]{2})(acgt|(TT|GG){1,2})(?P<UMI>[ACGTN]{4})", 1),
+]
+
+
+@pytest.mark.parametrize("pat,k", ALTERNATION)
+def test_alternation_and_repeated_groups(pat, k):
+    """User-written `|` and repetition of groups: the pattern is unfolded into fixed-length
+    variants in the regex crate's decision order; output must equal the oracle's (Python `re`: same backtracking
+    priority), with trimming, -s and -r, single-end and as either mate of a pair."""
+    rnd = random.Random(zlib.crc32(pat.encode()))
+    fq = ragged_fastq(rnd, 3000, plant=[b"GATTACA", b"ATGCCAT", b"ACGT", b"ACACAC"], plus_comment=True, min_len=0, max_len=80)
+    for skip, rc in ((False, False), (True, False), (False, True)):
+        out, res = run_se(fq, pat, k, skip, rc)
+        assert out == bo.extract_se(fq, pat, k, rc, skip), (pat, k, skip, rc)
+        assert 0 < res.n_out <= 3000
+    heads = [rnd.choice([3, 23, 60]) for _ in range(1500)]
+    fq1 = ragged_fastq(rnd, 1500, 1, plant=[b"GATTACA", b"ACGT"], head_lens=heads, min_len=5, max_len=70)
+    fq2 = ragged_fastq(rnd, 1500, 2, plant=[b"ATGCCAT", b"ACACAC"], head_lens=heads, min_len=0, max_len=70)
+    for p1, p2 in ((pat, "^(?P<CB>[ACGT]{5})"), ("(?P<SB>[ACGT]{3})gattaca", pat), (None, pat)):
+        o1, o2, _ = run_pe(fq1, fq2, p1, p2, k)
+        assert (o1, o2) == bo.extract_pe(fq1, fq2, p1, p2, k), (p1, p2, k)
+
+
 UNBOUNDED = [
     ("^(?P<UMI>[ATGC]+)", 0), ("^(?P<UMI>[ATGCN]{3,})gattaca", 1), ("(?P<UMI>[ACGT]*?)atgccat(?P<CB>[ACGT]{2,})", 1),
     ("^N*(?P<CB>[ACGT]{4,})T+?(?P<UMI>[ACGT]{2})$", 0), ("(?P<UMI>[ACGT]{1,40})gattaca", 2), ("(?P<SB>A+)(?P<UMI>.*)$", 0),

@@ -61,16 +61,18 @@ def test_error_messages_follow_error_rs():
 
 
 @pytest.mark.parametrize("pattern", [
-    "^(?P<UMI>A|C)", "^(?P<UMI>([ATGCN])+)", "^(?P<UMI>[ATGCN]{4})+", "^(?P<UMI>[ATGCN]+)(A*C){2}", "^(?P<UMI>[ATGCN]+)a*",
+    "^(?P<UMI>([ATGCN])+)", "^(?P<UMI>[ATGCN]{4})+", "^(?P<UMI>[ATGCN]+)(A*C){2}", "^(?P<UMI>[ATGCN]+)a*",
     "^(?P<UMI>A*C*G*T*N*)", "^((?P<UMI>[ATGCN]{4})A){1,2}", "^(?P<UMI>[ATGCN]{2,4}+)", "^(?P<UMI>[ATGCN]{2,}*)",
     "^(?P<UMI>[ATGCN]{4,2})", "?(?P<UMI>[ATGCN]{4})",
     r"^(?P<UMI>\w{4})", "(?i)(?P<UMI>[ATGCN]{4})", "^(?P<UMI>[ATGCN]{4})?", "(?P<UMI>[ATGCN]{4})^",
     "(?=A)(?P<UMI>[ATGCN]{4})", "((?P<UMI>[ATGCN]{4})){2}", "(?P<UMI>[[:alpha:]]{4})",
     "^(?P<UMI>[^atg-z]{4})", "é(?P<UMI>A)",
-    # a repeated group that contains variable repetition: every copy has its own length in the regex crate
-    # (4 and 8 combinations); one length per quantifier would be an approximation, so these are refused
-    "(?P<UMI>[ACGT]{4})([AT]{1,2}G){2}", "(?P<UMI>[ACGT]{4})(A?C){3}", "(?P<UMI>[ACGT]{4})((A?C)T){2}",
-    "(?P<UMI>[ACGT]{4})(A{1,2}?C){0}",
+    # alternation and repeated groups are unfolded into variants (below); what stays refused:
+    "^(?P<UMI>A)|(?P<CB>C)",                       # alternation at the top level
+    "^(A|(?P<UMI>C))T",                            # a named group that may not take part in the match
+    "^(?P<UMI>[ACGT]{4})(A?){2}",                  # a repeated group that can match the empty string
+    "^(?P<UMI>[ACGT]+)(A|C)",                      # unbounded repetition together with alternatives
+    "^(?P<UMI>[ACGT]{4})(A|C|G|T|N){3}",           # 125 combinations
 ])
 def test_unsupported_constructs_are_refused(pattern):
     with pytest.raises(_lib.BarkitError) as e:
@@ -94,6 +96,23 @@ def test_variable_repetition_lowers_to_variants_in_priority_order():
     # variable repetition inside a group is fine as long as the group itself is taken once
     assert _lib.Program("(?P<UMI>[ACGT]{4})([AT]{1,2}G)", 0).nvariants() == 2
     assert _lib.Program("(?P<UMI>[ACGT]{4})(A?C){1}(GT){2}", 0).nvariants() == 2
+
+
+def test_alternation_and_repeated_groups_unfold_into_variants():
+    """`(a|b)`, `(X){m,n}`, `(a|b){n}`: one fixed-length program per unfolding, in the regex crate's decision order
+    (branches in order; a greedy repetition prefers another round over stopping).  The expanded text the reference would
+    compile keeps the construct."""
+    assert _lib.Program("(?P<CB>[ACGT]{16})(atgccat|gattaca)", 1).nvariants() == 2
+    assert _lib.Program("^(?P<UMI>AA|CCC)G", 0).info().total_len == 3            # first branch first
+    p = _lib.Program("^(?P<UMI>[ACGT]{4})(AC){1,3}G", 0)
+    assert p.nvariants() == 3 and p.info().total_len == 4 + 6 + 1                # greedy: three rounds first
+    assert _lib.Program("^(?P<UMI>[ACGT]{4})(AC){1,3}?G", 0).info().total_len == 4 + 2 + 1
+    assert _lib.Program("^(?P<UMI>[ACGT]{4})(A|C){2}", 0).nvariants() == 4
+    assert _lib.Program("^(?P<UMI>[ACGT]{4})(A|CG){1,2}?T", 0).nvariants() == 6
+    assert _lib.Program("^(?P<UMI>[ACGT]{4})(A?C){3}", 0).nvariants() == 8       # every copy has its own length
+    assert _lib.Program("(?P<UMI>[ACGT]{4})([AT]{1,2}G){2}", 0).nvariants() == 4
+    assert _lib.Program("(?P<UMI>[ACGT]{4})(A{1,2}?C){0}", 0).info().total_len == 4
+    assert _lib.expand("(?P<CB>[ACGT]{4})(at|ga)", 1) == bo.BarcodePattern("(?P<CB>[ACGT]{4})(at|ga)", 1).get_pattern_with_errors()
 
 
 def test_unbounded_repetition_lowers_to_one_parametric_program():

@@ -39,6 +39,13 @@ PATTERNS = [
     ("(?P<UMI>[ACGT]{1,40})gattaca", [1, 2]),
     ("^N*(?P<CB>[ACGT]{4,})T+?(?P<UMI>[ACGT]{2})$", [0]),
     ("(?P<SB>A+)(?P<UMI>.*)$", [0]),
+    # user-written alternation and repeated groups (unfolded into variants by the CUDA path's compiler)
+    ("(?P<CB>[ACGT]{6})(atgccat|gattaca)", [0, 1]),
+    ("^(?P<UMI>[ACGT]{4})(AC|G|TTT)(?P<CB>[ACGTN]{3})", [0]),
+    ("(?P<UMI>[ACGT]{4})(AC){1,3}G", [0]),
+    ("^(?P<UMI>[ACGT]{3})(A|CG){1,2}?T", [0]),
+    ("(?P<UMI>[ACGT]{4})(A?C){3}", [0]),
+    ("(?P<SB>[ACGT]{2})(acgt|(TT|GG){1,2})(?P<UMI>[ACGTN]{4})", [1]),
 ]
 
 _PIECES = ["^", "atgc", "gattaca", "ATGC", "N", "[ATGCN]", "[ACGT]", "{3}", "{2}", "(?P<UMI>[ATGCN]{4})", "(?P<CB>[ACGT]{3})",
