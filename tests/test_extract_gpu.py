@@ -355,6 +355,65 @@ def test_alternation_and_repeated_groups(pat, k):
         assert (o1, o2) == bo.extract_pe(fq1, fq2, p1, p2, k), (p1, p2, k)
 
 
+def _random_pattern(rnd):
+    """A random pattern over the lowered grammar: classes and literals with fixed, bounded and unbounded repetition
+    (greedy or lazy), lowercase fuzzy runs, alternation groups, repeated groups, one to three named captures."""
+    names = ["UMI", "CB", "SB"]
+    rnd.shuffle(names)
+    ncap = rnd.randint(1, 3)
+    cls = lambda: rnd.choice(["[ACGT]", "[ACGTN]", "[AC]", "[GT]", ".", "[^N]"])
+    quant = lambda: rnd.choice(["", "", "{2}", "{3}", "{1,3}", "{2,4}?", "{0,2}", "?", "+", "*", "{2,}", "+?", "{1,30}"])
+    def atom():
+        r = rnd.random()
+        if r < 0.35:
+            return cls() + quant()
+        if r < 0.55:
+            return rnd.choice(["A", "C", "G", "T", "AC", "GT", "TTA"]) + (rnd.choice(["", "", "{2}", "{1,2}"]) if rnd.random() < 0.3 else "")
+        if r < 0.75:
+            return rnd.choice(["acgt", "gattaca", "tt", "atgc", "gg"])
+        if r < 0.9:
+            return "(" + "|".join(rnd.choice(["A", "CG", "TT", "acg", "G[AC]", "[GT]{2}"]) for _ in range(rnd.randint(2, 3))) + ")" + rnd.choice(["", "", "{2}", "{1,2}", "?"])
+        return "(" + rnd.choice(["AC", "G[ACGT]", "T?A", "[AC]{1,2}G"]) + ")" + rnd.choice(["{2}", "{1,2}", "{0,2}?", "{1,3}"])
+    parts = []
+    for i in range(ncap):
+        for _ in range(rnd.randint(0, 2)):
+            parts.append(atom())
+        inner = cls() + rnd.choice(["{2}", "{4}", "{3,5}", "{2,}", "+", "*", "{1,3}?", "{6}"])
+        if rnd.random() < 0.2:
+            inner += rnd.choice(["A", "[CG]", "(A|T)"])
+        parts.append("(?P<%s>%s)" % (names[i], inner))
+    for _ in range(rnd.randint(0, 2)):
+        parts.append(atom())
+    return ("^" if rnd.random() < 0.5 else "") + "".join(parts) + ("$" if rnd.random() < 0.15 else "")
+
+
+def test_random_patterns_against_the_oracle():
+    """Pattern fuzzing on the device: whatever the compiler accepts must give the oracle's bytes (Python `re` on the
+    reference's expanded text), whatever it does not lower must be refused, never approximated."""
+    rnd = random.Random(20241020)
+    fq = ragged_fastq(rnd, 700, plant=[b"GATTACA", b"ACGT", b"ATGC", b"ACACGG", b"TTATTA"], min_len=0, max_len=48)
+    accepted = refused = 0
+    for it in range(260):
+        pat = _random_pattern(rnd)
+        k = rnd.choice([0, 1, 1, 2])
+        skip, rc = rnd.random() < 0.25, rnd.random() < 0.25
+        try:
+            exp = bo.extract_se(fq, pat, k, rc, skip)
+        except Exception:
+            continue      # (not a valid pattern for the oracle's engine either)
+        try:
+            ctx = make_ctx(pat, k=k, skip=skip, rc=rc)
+        except _lib.BarkitError as e:
+            assert e.status in (_lib.BK_E_UNSUPPORTED, _lib.BK_E_PATTERN), (pat, str(e))
+            refused += 1
+            continue
+        out, _ = ctx.extract_text(fq)
+        ctx.close()
+        assert out == exp, (pat, k, skip, rc)
+        accepted += 1
+    assert accepted >= 100, (accepted, refused)
+
+
 UNBOUNDED = [
     ("^(?P<UMI>[ATGC]+)", 0), ("^(?P<UMI>[ATGCN]{3,})gattaca", 1), ("(?P<UMI>[ACGT]*?)atgccat(?P<CB>[ACGT]{2,})", 1),
     ("^N*(?P<CB>[ACGT]{4,})T+?(?P<UMI>[ACGT]{2})$", 0), ("(?P<UMI>[ACGT]{1,40})gattaca", 2), ("(?P<SB>A+)(?P<UMI>.*)$", 0),
