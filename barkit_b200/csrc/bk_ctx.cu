@@ -65,7 +65,7 @@ struct Slot {
   // two-kernel form of a paired launch with one pattern (enqueue_split): hand-over and the compaction's look-back state
   DevBuf split_match, split_hlen, split_scratch;
   DevBuf tab_err;
-  DevBuf tab_extras[2];     // ... and, for a parametric program, the extras of every match
+  DevBuf tab_extras[2];     // ... and, for a program without a fixed shape, the spans of every match (16 bytes per read)
   DevBuf tab_match[2];      // match tables of a paired batch that runs as match_kernel + two single-end launches (enqueue_tabled)
   bk::CompactParams cpar;   // the compaction in flight, should it have to run again (compact_redo)
   bool cpar_valid = false;
@@ -88,6 +88,7 @@ struct bk_ctx {
   // bounded variable repetition: a mate's pattern as several fixed-length programs (prog[m] is the first)
   std::vector<bk_devprog> var[2];
   DevBuf vdev[2];          // ... and their copy in device memory (nullptr when there is one variant)
+  DevBuf vmdev[2];         // the general form (prog[m].vm_len > 0): its instructions in device memory
   uint32_t growth[2] = {0, 0};  // largest header growth over the variants
   int sm_count = 0;
   Slot slot[kSlots];
@@ -150,6 +151,21 @@ uint64_t par_growth(const bk_devprog& pg, uint64_t maxrec) {
     const uint64_t e = std::min<uint64_t>(pg.ins[i].max_extra == 0xFFFF ? maxrec / 2 : pg.ins[i].max_extra, maxrec / 2);
     g += 2 * e * (uint64_t)__builtin_popcount(pg.ins[i].capmask);
   }
+  if (pg.vm_len)  // the general form: caps[c].len = the longest span the capture can have
+    for (uint32_t c = 0; c < pg.ncaps; ++c) g += 2 * std::min<uint64_t>(pg.caps[c].len, maxrec / 2);
+  return g;
+}
+// ... and summed over a batch of n records with text_len bytes in all: a capture grows by at most its bound per record
+// and by no more than the reads' own bytes over the batch
+uint64_t par_growth_total(const bk_devprog& pg, uint64_t n, uint64_t text_len) {
+  uint64_t g = 0;
+  for (uint32_t i = 0; i < pg.nins; ++i) {
+    const uint64_t per = pg.ins[i].max_extra == 0xFFFF ? text_len : 2 * (uint64_t)pg.ins[i].max_extra * n;
+    g += std::min(per, text_len) * (uint64_t)__builtin_popcount(pg.ins[i].capmask);
+  }
+  if (pg.vm_len)
+    for (uint32_t c = 0; c < pg.ncaps; ++c)
+      g += std::min(pg.caps[c].len == 0xFFFF ? text_len : 2 * (uint64_t)pg.caps[c].len * n, text_len);
   return g;
 }
 
@@ -244,11 +260,11 @@ struct CoLaunch {
   // match tables (enqueue_tabled): this mate's own, made by match_kernel (the launch then matches nothing itself),
   // and the other mate's of the pair (keep rule)
   const int32_t* tab_own = nullptr;
-  const unsigned long long* xtab = nullptr;  // with tab_own, for a parametric program
+  const uint4* xtab = nullptr;  // with tab_own, for a parametric program
   // a PAIRED launch in table form: ptab[m] = mate m's table (null: the mate matches for itself), pxtab[m] its extras
   bool pair_tables = false;
   const int32_t* ptab[2] = {nullptr, nullptr};
-  const unsigned long long* pxtab[2] = {nullptr, nullptr};
+  const uint4* pxtab[2] = {nullptr, nullptr};
   const int32_t* tab_other = nullptr;
   DevBuf* scratch = nullptr;             // in: the launch's look-back state goes here instead of the slot's buffer ...
   bk::DevResult* result = nullptr;       // in: ... and its figures into this result, which it does not reset
@@ -266,10 +282,10 @@ int enqueue_match(bk_ctx* ctx, int m, Slot* s, int ti, cudaStream_t stream, uint
 // a mate whose pattern needs more than one anchored test per read
 bool is_hard(const bk_ctx* ctx, int m) {
   const bk_devprog& pg = ctx->prog[m];
-  return pg.present && ((ctx->flags & BK_FLAG_RC) || ctx->var[m].size() > 1 || pg.nins > 0 || (!pg.anchor_start && !pg.anchor_end));
+  return pg.present && ((ctx->flags & BK_FLAG_RC) || ctx->var[m].size() > 1 || bk_free_shape(pg) || (!pg.anchor_start && !pg.anchor_end));
 }
 // parametric programs (unbounded repetition) are only ever matched by match_kernel
-bool is_parametric(const bk_ctx* ctx) { return ctx->prog[0].nins > 0 || ctx->prog[1].nins > 0; }
+bool is_parametric(const bk_ctx* ctx) { return bk_free_shape(ctx->prog[0]) || bk_free_shape(ctx->prog[1]); }
 
 // A paired launch with exactly one pattern, as two kernels (bk_compact.cuh): the single-end extract kernel on the
 // pattern's mate, leaving its match table and header lengths on the device, then the ordered compaction of the
@@ -364,13 +380,13 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
   // A single-end launch whose pattern needs a search: match_kernel first, this launch takes its matches from the table
   // (unless the caller has done that already: enqueue_tabled)
   const int32_t* self_tab = nullptr;
-  const unsigned long long* self_xtab = nullptr;
+  const uint4* self_xtab = nullptr;
   bk::DevResult* merr = nullptr;
   // -- when its pattern is a list of variants or a parametric program: those matchers are lane-per-read loops that
   // gain from match_kernel's occupancy (unanchored {m,n}: 1.75 x) and must not sit next to the emit code; a plain
   // unanchored pattern or a -r retry is as fast or faster inside the extract kernel (one read of the text).
   const bool self_match = !ctx->paired && n && !(co && co->tab_own) &&
-                          (ctx->prog[0].nins > 0 || (ctx->var[0].size() > 1 && !(ctx->flags & BK_FLAG_MATCH_IN_KERNEL)));
+                          (bk_free_shape(ctx->prog[0]) || (ctx->var[0].size() > 1 && !(ctx->flags & BK_FLAG_MATCH_IN_KERNEL)));
   if (self_match) {
     const int ti = co ? (int)co->rslot : 0;
     int rcm;
@@ -379,14 +395,14 @@ int enqueue_extract(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const
     CK(cudaMemsetAsync(merr, 0, sizeof(bk::DevResult), stream));
     if ((rcm = enqueue_match(ctx, 0, s, ti, stream, n, in1, merr, launches)) != BK_OK) return rcm;
     self_tab = (const int32_t*)s->tab_match[ti].p;
-    self_xtab = (const unsigned long long*)s->tab_extras[ti].p;
+    self_xtab = (const uint4*)s->tab_extras[ti].p;
   }
   LaunchPlan lp;
   const bool table = self_tab || (co && (co->tab_own || co->pair_tables));
   const bool general = !table && needs_general(ctx);
   const bool var = has_variants(ctx);
   // which instantiation: 0..5 as before, 6 / 7 = single-end with the matches taken from a table (plain / variants)
-  const int kid = table && ctx->paired ? (var || is_parametric(ctx) ? 9 : 8) : table ? (var || ctx->prog[0].nins ? 7 : 6) : var ? (ctx->paired ? 0 : 1) : ctx->paired ? (general ? 2 : 3) : (general ? 4 : 5);
+  const int kid = table && ctx->paired ? (var || is_parametric(ctx) ? 9 : 8) : table ? (var || bk_free_shape(ctx->prog[0]) ? 7 : 6) : var ? (ctx->paired ? 0 : 1) : ctx->paired ? (general ? 2 : 3) : (general ? 4 : 5);
   bk::KParams P;
   memset(&P, 0, sizeof P);
   int rc;
@@ -476,7 +492,7 @@ int enqueue_match(bk_ctx* ctx, int m, Slot* s, int ti, cudaStream_t stream, uint
                   bk::DevResult* result, uint32_t* launches) {
   int rce;
   if ((rce = ensure(ctx, &s->tab_match[ti], ((size_t)n + 1) * 4)) != BK_OK) return rce;
-  if (ctx->prog[m].nins && (rce = ensure(ctx, &s->tab_extras[ti], ((size_t)n + 1) * 8)) != BK_OK) return rce;
+  if (bk_free_shape(ctx->prog[m]) && (rce = ensure(ctx, &s->tab_extras[ti], ((size_t)n + 1) * 16)) != BK_OK) return rce;
   if (n == 0) return BK_OK;
   const uint32_t maxrec = in->max_rec_bytes;
   // 32 reads per warp and two CTAs per SM while the records allow it; long records: fewer reads per tile, then fewer
@@ -498,7 +514,7 @@ int enqueue_match(bk_ctx* ctx, int m, Slot* s, int ti, cudaStream_t stream, uint
   M.text = in->text;
   M.off = in->rec_off;
   M.match = (int32_t*)s->tab_match[ti].p;
-  M.extras = (unsigned long long*)s->tab_extras[ti].p;
+  M.spans = (uint4*)s->tab_extras[ti].p;
   M.result = result;
   M.nvar = (uint32_t)ctx->var[m].size();
   M.vprog = (const bk_devprog*)ctx->vdev[m].p;
@@ -507,16 +523,19 @@ int enqueue_match(bk_ctx* ctx, int m, Slot* s, int ti, cudaStream_t stream, uint
   M.ntiles = (n + R - 1) / R;
   M.cap = cap_of(R);
   M.rc = (ctx->flags & BK_FLAG_RC) ? 1u : 0u;
+  M.vmcode = (const uint2*)ctx->vmdev[m].p;
+  const bool vm = ctx->prog[m].vm_len > 0;
+  const auto kernel = vm ? bk::match_kernel<true> : bk::match_kernel<false>;
   const size_t smem = (size_t)W * M.cap + 64;
-  CK(cudaFuncSetAttribute(bk::match_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(bk::match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk::match_kernel, W * 32, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, W * 32, smem));
   if (per_sm < 1) per_sm = 1;
   long long grid = std::min<long long>((long long)per_sm * ctx->sm_count, ((long long)M.ntiles + W - 1) / W);
   if (ctx->flags & BK_FLAG_VERBOSE)
     fprintf(stderr, "[bk] match_kernel mate %d: tile_recs %u cap %u warps %d ctas/sm %d grid %lld\n", m + 1, R, M.cap, W, per_sm, grid);
-  bk::match_kernel<<<(int)std::max<long long>(grid, 1), W * 32, smem, stream>>>(M);
+  kernel<<<(int)std::max<long long>(grid, 1), W * 32, smem, stream>>>(M);
   CK(cudaGetLastError());
   if (launches) *launches += 1;
   return BK_OK;
@@ -546,7 +565,7 @@ int enqueue_tabled(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const 
     if ((rc = ensure(ctx, &s->tab_match[m], ((size_t)n + 1) * 4)) != BK_OK) return rc;
   if ((rc = ensure(ctx, &s->tab_err, 64)) != BK_OK) return rc;
   for (int m = 0; m < 2; ++m)  // (before the table pointers are taken: enqueue_match only finds them large enough)
-    if (ctx->prog[m].nins && (rc = ensure(ctx, &s->tab_extras[m], ((size_t)n + 1) * 8)) != BK_OK) return rc;
+    if (bk_free_shape(ctx->prog[m]) && (rc = ensure(ctx, &s->tab_extras[m], ((size_t)n + 1) * 16)) != BK_OK) return rc;
   const bool hard[2] = {is_hard(ctx, 0), is_hard(ctx, 1)};
   const int first = hard[0] && !hard[1] ? 1 : 0;  // the mate whose extract launch runs first
   int32_t* const tab[2] = {(int32_t*)s->tab_match[0].p, (int32_t*)s->tab_match[1].p};
@@ -563,7 +582,7 @@ int enqueue_tabled(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const 
     for (int m = 0; m < 2; ++m)
       if (hard[m]) {
         co.ptab[m] = tab[m];
-        co.pxtab[m] = (const unsigned long long*)s->tab_extras[m].p;
+        co.pxtab[m] = (const uint4*)s->tab_extras[m].p;
       }
     // the kernel writes a mate's matches (variant bits stripped) where the caller asked for them
     rc = enqueue_extract(ctx, s, stream, n, in1, in2, out1, cap1, out2, cap2, match1, match2, launches, &co);
@@ -584,7 +603,7 @@ int enqueue_tabled(bk_ctx* ctx, Slot* s, cudaStream_t stream, uint32_t n, const 
     co.rslot = (uint32_t)m;
     co.tab_other = tab[1 - m];
     co.tab_own = hard[m] ? tab[m] : nullptr;
-    co.xtab = (const unsigned long long*)s->tab_extras[m].p;
+    co.xtab = (const uint4*)s->tab_extras[m].p;
     if (k == 1) {
       co.scratch = &s->split_scratch;
       co.result = (bk::DevResult*)((uint8_t*)s->scratch.buf.p + 64);  // the first launch's, which has reset it
@@ -621,6 +640,10 @@ int compact_redo(bk_ctx* ctx, Slot& s) {
 int check_dev_result(bk_ctx* ctx, const bk::DevResult& r) {
   if (r.error & 2u) { ctx->last_error = "a record is longer than max_rec_bytes"; return BK_E_ARG; }
   if (r.error & 1u) { ctx->last_error = "output buffer too small"; return BK_E_CAPACITY; }
+  if (r.error & 8u) {  // match_vm gave up on a read
+    ctx->last_error = "unsupported pattern construct (a read needs more backtracking states for this pattern than the device matcher keeps)";
+    return BK_E_UNSUPPORTED;
+  }
   return BK_OK;
 }
 
@@ -704,6 +727,16 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
       }
       ctx->vdev[m].cap = bytes;
     }
+    if (ctx->prog[m].vm_len) {
+      const size_t bytes = pp[m]->prog.vm.size() * sizeof(bk_vmop);
+      if (pp[m]->prog.vm.size() != ctx->prog[m].vm_len || cudaMalloc(&ctx->vmdev[m].p, bytes) != cudaSuccess ||
+          cudaMemcpy(ctx->vmdev[m].p, pp[m]->prog.vm.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        std::string msg = std::string("CUDA error uploading the pattern's program: ") + cudaGetErrorString(cudaGetLastError());
+        bk_ctx_destroy(ctx);
+        return fail(BK_E_CUDA, msg);
+      }
+      ctx->vmdev[m].cap = bytes;
+    }
   }
   for (int i = 0; i < kSlots; ++i) {
     Slot& s = ctx->slot[i];
@@ -730,6 +763,7 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
     solo->prog[0] = ctx->prog[pm];
     solo->var[0] = ctx->var[pm];
     solo->vdev[0] = ctx->vdev[pm];  // (shared, owned by ctx)
+    solo->vmdev[0] = ctx->vmdev[pm];
     solo->growth[0] = ctx->growth[pm];
     ctx->solo = solo;
     if (!(flags & BK_FLAG_DEVICE_BOTH_MATES)) ctx->pass_mate = 1 - pm;
@@ -747,6 +781,7 @@ bk_ctx* bk_ctx_create(int device, const bk_program* p1, const bk_program* p2, ui
       v->prog[0] = ctx->prog[m];
       v->var[0] = ctx->var[m];
       v->vdev[0] = ctx->vdev[m];  // (shared, owned by ctx)
+      v->vmdev[0] = ctx->vmdev[m];
       v->growth[0] = ctx->growth[m];
       ctx->view[m] = v;
     }
@@ -790,8 +825,10 @@ void bk_ctx_destroy(bk_ctx* ctx) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   if (ctx->tok.p) cudaFree(ctx->tok.p);
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < 2; ++m) {
     if (ctx->vdev[m].p) cudaFree(ctx->vdev[m].p);
+    if (ctx->vmdev[m].p) cudaFree(ctx->vmdev[m].p);
+  }
   delete ctx->solo;
   delete ctx->view[0];
   delete ctx->view[1];
@@ -868,7 +905,7 @@ uint64_t bk_out_bound(const bk_ctx* ctx, int mate, uint32_t n, uint64_t text_len
   const bk_devprog& pg = ctx->prog[mate - 1];
   // out record <= in record + 1 (a final record without EOL gains one) + header growth
   // (a parametric program: its captures may also grow by the read's own bytes, par_growth summed over the records)
-  return text_len + (uint64_t)n * ((pg.present ? ctx->growth[mate - 1] : 0) + 1) + 16 + (pg.present ? par_growth(pg, text_len) : 0);
+  return text_len + (uint64_t)n * ((pg.present ? ctx->growth[mate - 1] : 0) + 1) + 16 + (pg.present ? par_growth_total(pg, n, text_len) : 0);
 }
 
 int bk_submit(bk_ctx* ctx, int slot, uint32_t n, const bk_mate_in* in1, const bk_mate_in* in2) {

@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       // ---- size + scan, publish the aggregate -------------------------------------------------------
       const bk_devprog& pe = (VAR && var_me && ms >= 0) ? P.vprog[m][ms >> 24] : pg;  // the record's variant
       uint32_t olen = keep ? out_bytes(pe, rv, ms, trim) : 0;
-      if (VAR && TABLE && pg.nins && keep && ms >= 0) {  // a parametric program: this record's own lengths
+      if (VAR && TABLE && bk_free_shape(pg) && keep && ms >= 0) {  // a program without a fixed shape: this record's own spans
         const EmitProg ep = emit_prog(pg, P.xtab[m][r0 + lane]);
         olen = out_bytes(ep, rv, ms, trim);
       }
@@ -578,9 +578,9 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         const uint32_t nxt = __shfl_down_sync(0xffffffffu, ooff, 1);
         const bool even = kept && lane < 31 && nxt != kNotKept && ((nxt - ooff) & 31u) == 0;
         const uint32_t rot = __popc(__ballot_sync(0xffffffffu, even)) >= 8 ? ((uint32_t)lane & 7u) + 1u : 0u;
-        if (VAR && TABLE && pg.nins) {
+        if (VAR && TABLE && bk_free_shape(pg)) {
           if (kept && !unc) {
-            const EmitProg ep = emit_prog(pg, ms >= 0 ? P.xtab[m][tile * R + lane] : 0ull);
+            const EmitProg ep = emit_prog(pg, ms >= 0 ? P.xtab[m][tile * R + lane] : make_uint4(0, 0, 0, 0));
             emit_part(ep, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
           }
         } else if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);

@@ -24,6 +24,8 @@ struct Program {
   // Bounded variable repetition ({m,n}, ?) lowers to one fixed-length program per length combination, in
   // the regex crate's backtracking order; a fixed-length pattern has exactly one (== dev).
   std::vector<bk_devprog> variants;
+  // the general form (bk_program.h: bk_vmop), when dev.vm_len > 0
+  std::vector<bk_vmop> vm;
 };
 
 std::vector<Span> find_fuzzy_runs(const std::string& pattern);

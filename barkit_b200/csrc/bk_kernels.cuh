@@ -71,7 +71,10 @@ struct KParams {
   // A paired launch in TABLE form reads them differently: tab_in[m] is mate m's own table, null for a mate that matches
   // for itself.
   const int32_t* tab_in[2];
-  const unsigned long long* xtab[2];  // parametric programs: the extras of every match of mate m (match_kernel)
+  // Programs whose match has no fixed shape (parametric programs, bk_program.h): the spans of every match of mate m as
+  // match_kernel found them -- uint4 = 8 x u16: match length, then (offset from the match start, length) of up to three
+  // captures, one spare.
+  const uint4* xtab[2];
   uint32_t no_nout;
 };
 
@@ -579,24 +582,22 @@ struct EmitProg {
   uint32_t ncaps, hdr_growth, total_len;
   bk_cap caps[BK_MAX_CAPS];
 };
-__device__ __forceinline__ EmitProg emit_prog(const bk_devprog& pg, unsigned long long ex) {
+// the spans of one match, packed as KParams::xtab holds them
+__device__ __forceinline__ uint4 pack_spans(uint32_t len, const uint32_t* off, const uint32_t* clen) {
+  return make_uint4(len | off[0] << 16, clen[0] | off[1] << 16, clen[1] | off[2] << 16, clen[2]);
+}
+__device__ __forceinline__ EmitProg emit_prog(const bk_devprog& pg, const uint4 sp) {
   EmitProg ep;
   ep.ncaps = pg.ncaps;
-  ep.hdr_growth = pg.hdr_growth;
-  ep.total_len = pg.total_len;
+  ep.total_len = sp.x & 0xFFFFu;
+  const uint32_t off[3] = {sp.x >> 16, sp.y >> 16, sp.z >> 16}, clen[3] = {sp.y & 0xFFFFu, sp.z & 0xFFFFu, sp.w & 0xFFFFu};
+  ep.hdr_growth = 0;
 #pragma unroll
-  for (uint32_t c = 0; c < BK_MAX_CAPS; ++c) ep.caps[c] = pg.caps[c];
-  if (pg.nins) {
-    for (uint32_t i = 0; i < pg.nins; ++i) ep.total_len += (uint32_t)(ex >> (16u * i)) & 0xFFFFu;
-#pragma unroll
-    for (uint32_t c = 0; c < BK_MAX_CAPS; ++c)
-      if (c < pg.ncaps) {
-        uint32_t off, len;
-        par_cap(pg, c, ex, off, len);
-        ep.hdr_growth += 2u * (len - ep.caps[c].len);
-        ep.caps[c].off = (uint16_t)off;
-        ep.caps[c].len = (uint16_t)len;
-      }
+  for (uint32_t c = 0; c < BK_MAX_CAPS; ++c) {
+    ep.caps[c] = pg.caps[c];
+    ep.caps[c].off = (uint16_t)off[c];
+    ep.caps[c].len = (uint16_t)clen[c];
+    if (c < pg.ncaps) ep.hdr_growth += 3u + pg.caps[c].name_len + 2u * clen[c];  // parse.rs:161-168
   }
   return ep;
 }
@@ -1427,6 +1428,153 @@ __device__ __noinline__ int match_variants_scan(const bk_devprog* vp, uint32_t n
 __global__ void rc_kernel(const uint8_t* in, uint8_t* out, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[i] = complement(in[n - 1 - i]);
+}
+
+// ---- the general form: a backtracking program (bk_program.h: bk_vmop; match_kernel<VM = true>) ------------------------
+//
+// One lane per read, the regex crate's leftmost-first semantics by construction (pattern.rs:225-230): starts in ascending
+// order, at every SPLIT the preferred branch first, the other one on a stack in local memory.  An entry is 8 bytes:
+// kind << 30 | rem << 12 | pc and a text position -- BRANCH (continue at pc, pos), RESTORE (capture slot pc gets its old
+// value back), STAR_G / STAR_L (a repeated one-byte class: ONE entry for all its lengths; greedy gives a byte back per
+// visit, lazy takes one more).
+// Plain backtracking is polynomial in the read length (one degree per repetition) where the reference's engine is
+// linear, so the search is memoised the way a bounded backtracker is: the instructions at which paths can meet again --
+// SPLIT, STAR and what follows a STAR -- carry a mark (bk_vmop::c), and a (mark, position) state is entered once per READ:
+// a second arrival, from whichever start, can only fail again (no back-references, and no loop body matches the empty
+// string).  That bounds the work by marks x (length + 1) states.  The visited bits (kVmVisWords words of local memory)
+// must hold them, and kVmStack entries the stack; a read that needs more raises error bit 8 and the batch is refused
+// (BK_E_UNSUPPORTED) -- giving a different answer instead is not an option.
+constexpr uint32_t kVmStack = 384, kVmVisWords = 256, kVmSteps = 32;
+constexpr uint32_t kVmBranch = 0u, kVmRestore = 1u, kVmStarG = 2u, kVmStarL = 3u;
+
+// -> the match's start; -1: no match; -2: a match in which a named group took no part (the read is dropped)
+template <bool RC>
+__device__ __noinline__ int match_vm(uint32_t tab, uint32_t vmc, uint32_t vm_len, uint32_t ncaps, uint32_t seq, uint32_t L,
+                                     uint4* spans, uint32_t* gave_up) {
+  const uint4 h = lds128(tab + kTabHdr);  // marked instructions, shortest match, anchored at the start, -
+  if (L < h.y) return -1;
+  const uint32_t nstates = h.x * (L + 1u);
+  if (L > 0xFFFFu || nstates > 32u * kVmVisWords) { *gave_up = 1u; return -1; }
+  const uint32_t last = h.z ? 0u : L - h.y;
+  // (a greedy run gives its bytes back one visit at a time even when every state behind them is known: up to a
+  // read's length of one-step visits per STAR state)
+  uint32_t budget = kVmSteps * vm_len * (L + 1u) + nstates * (L + 1u);
+  uint32_t cap[2 * BK_MAX_CAPS];
+  uint32_t vis[kVmVisWords];
+  uint2 stk[kVmStack];
+  for (uint32_t i = 0; i <= nstates >> 5; ++i)
+    if (i < kVmVisWords) vis[i] = 0u;
+  for (uint32_t s = 0; s <= last; ++s) {
+    uint32_t sp = 0, pc = 0, pos = s;
+#pragma unroll
+    for (uint32_t c = 0; c < 2 * BK_MAX_CAPS; ++c) cap[c] = 0xFFFFFFFFu;
+    for (;;) {
+      if (budget-- == 0u) { *gave_up = 1u; return -1; }
+      const uint2 w = lds64(vmc + 8u * pc);  // bk_vmop, little endian
+      const uint32_t op = w.x & 0xFFu, k = (w.x >> 8) & 0xFFu, a = w.x >> 16, b = w.y & 0xFFFFu, mark = w.y >> 16;
+      bool ok = true;
+      uint2 push = make_uint2(0xFFFFFFFFu, 0u);  // (x = all ones: nothing to push)
+      if (mark) {  // been in this state before: it failed then, it fails now
+        const uint32_t bit = (mark - 1u) * (L + 1u) + pos, m = 1u << (bit & 31u), v = vis[bit >> 5];
+        ok = !(v & m);
+        vis[bit >> 5] = v | m;
+      }
+      if (!ok) {
+      } else if (op == BK_VM_CLS) {
+        ok = pos + b <= L;
+        if (ok) {
+          uint32_t acc = 0xFFu;
+          for (uint32_t i = 0; i < b; ++i) acc &= lds8(tab + fetch<RC>(tab, seq, L, pos + i));
+          ok = (acc >> a) & 1u;
+          pos += b;
+        }
+        ++pc;
+      } else if (op == BK_VM_LIT) {
+        ok = pos + b <= L;
+        if (ok) {
+          uint32_t mism = 0, bad = 0;
+          for (uint32_t i = 0; i < b; ++i) {
+            const uint32_t c = fetch<RC>(tab, seq, L, pos + i);
+            const uint32_t ne = (c != lds8(tab + kTabLit + a + i));
+            mism += ne;
+            bad |= ne & (uint32_t)((c >= 0x80u) | (c == '\n'));  // a wildcard slot is the regex `.` (pattern.rs:10,71)
+          }
+          ok = mism <= k && !bad;
+          pos += b;
+        }
+        ++pc;
+      } else if (op == BK_VM_SPLIT) {
+        push = make_uint2(kVmBranch << 30 | b, pos);
+        pc = a;
+      } else if (op == BK_VM_JMP) {
+        pc = a;
+      } else if (op == BK_VM_SAVE) {
+        push = make_uint2(kVmRestore << 30 | a, cap[a]);
+        cap[a] = pos;
+        ++pc;
+      } else if (op == BK_VM_BOL) {
+        ok = pos == 0u;
+        ++pc;
+      } else if (op == BK_VM_EOL) {
+        ok = pos == L;
+        ++pc;
+      } else if (op == BK_VM_STAR) {
+        ++pc;
+        if (k == 0u) {  // greedy: the whole run, then a byte less per visit
+          uint32_t n = 0;
+          while (n < b && pos + n < L && ((lds8(tab + fetch<RC>(tab, seq, L, pos + n)) >> a) & 1u)) ++n;
+          if (n) push = make_uint2(kVmStarG << 30 | (n - 1u) << 12 | pc, pos + n - 1u);
+          pos += n;
+        } else if (b) {  // lazy: nothing, then a byte more per visit
+          push = make_uint2(kVmStarL << 30 | b << 12 | (pc - 1u), pos);
+        }
+      } else {  // BK_VM_MATCH
+        uint32_t off[3] = {0, 0, 0}, clen[3] = {0, 0, 0};
+        bool all = true;
+#pragma unroll
+        for (uint32_t c = 0; c < BK_MAX_CAPS; ++c)
+          if (c < ncaps) {
+            // a named group that took no part in the match: get_barcode_match_positions fails and the read is dropped
+            // (parse.rs:127-136, 82 `.ok()?`)
+            if (cap[2 * c] == 0xFFFFFFFFu || cap[2 * c + 1] == 0xFFFFFFFFu) all = false;
+            off[c] = cap[2 * c] - s;
+            clen[c] = cap[2 * c + 1] - cap[2 * c];
+          }
+        if (!all) return -2;  // (a match all the same: no reverse-complement retry, parse.rs:61)
+        *spans = pack_spans(pos - s, off, clen);
+        return (int)s;
+      }
+      if (push.x != 0xFFFFFFFFu) {
+        if (sp == kVmStack) { *gave_up = 1u; return -1; }
+        stk[sp++] = push;
+      }
+      if (ok) continue;
+      // ---- backtrack: the most recent alternative
+      bool resumed = false;
+      while (sp) {
+        const uint2 e = stk[--sp];
+        const uint32_t kind = e.x >> 30, epc = e.x & 0xFFFu, rem = (e.x >> 12) & 0xFFFFu;
+        if (kind == kVmRestore) { cap[epc] = e.y; continue; }
+        if (kind == kVmBranch) { pc = epc; pos = e.y; resumed = true; break; }
+        if (kind == kVmStarG) {
+          pc = epc; pos = e.y;
+          if (rem) stk[sp++] = make_uint2(kVmStarG << 30 | (rem - 1u) << 12 | epc, e.y - 1u);  // (the slot just freed)
+          resumed = true;
+          break;
+        }
+        // kVmStarL: one more byte of the class, if there is one
+        const uint32_t cls = lds32(vmc + 8u * epc) >> 16;
+        if (e.y < L && ((lds8(tab + fetch<RC>(tab, seq, L, e.y)) >> cls) & 1u)) {
+          pc = epc + 1u; pos = e.y + 1u;
+          if (rem > 1u) stk[sp++] = make_uint2(kVmStarL << 30 | (rem - 1u) << 12 | epc, e.y + 1u);
+          resumed = true;
+          break;
+        }
+      }
+      if (!resumed) break;  // no match from this start
+    }
+  }
+  return -1;
 }
 
 // ---- bksyn-v1 generator (bench / tests; oracle/bksyn.py is the normative statement) -------------------------

@@ -25,7 +25,7 @@ struct MatchParams {
   const uint8_t* text;
   const uint32_t* off;
   int32_t* match;          // out
-  unsigned long long* extras;  // out, parametric programs (prog.nins > 0): the match's extra copies per insertion, 16 bits each
+  uint4* spans;            // out, programs without a fixed shape (bk_free_shape): match length and capture spans of every match (KParams::xtab)
   DevResult* result;       // error bit 1 << 1: a tile did not fit the warp's buffer (as in extract_kernel)
   const bk_devprog* vprog; // the pattern's variants when nvar > 1
   uint32_t nvar;
@@ -34,8 +34,12 @@ struct MatchParams {
   uint32_t tile_recs;      // <= 32
   uint32_t cap;            // bytes of one warp's buffer (a multiple of 16)
   uint32_t rc;             // reverse-complement retry (parse.rs:61-66)
+  const uint2* vmcode;     // the general form (prog.vm_len > 0): its instructions (bk_vmop), match_kernel<true>
 };
 
+// VM = true: the general form only (match_vm keeps a backtracking stack in local memory, which the other matchers'
+// launches should not have to carry)
+template <bool VM>
 __global__ void __launch_bounds__(kMatchWarps * 32) match_kernel(const __grid_constant__ MatchParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(16) uint8_t tabs[kTabBytes];
@@ -73,6 +77,9 @@ __global__ void __launch_bounds__(kMatchWarps * 32) match_kernel(const __grid_co
     const uint32_t omax = __reduce_max_sync(0xffffffffu, lane < (int)P.nvar ? off : 0u);
     if (lane == 0) s_scan = all_ok && omax - omin <= 24u && omax < 256u ? 1u + omin : 0u;
   }
+  __shared__ __align__(8) uint2 s_vm[VM ? BK_VM_MAX : 1];
+  if (VM)
+    for (uint32_t i = threadIdx.x; i < pg.vm_len; i += blockDim.x) s_vm[i] = __ldg(P.vmcode + i);
   __syncthreads();
   uint32_t ph = 0;
   for (uint32_t tile = blockIdx.x * W + warp; tile < P.ntiles; tile += gridDim.x * W) {
@@ -99,20 +106,42 @@ __global__ void __launch_bounds__(kMatchWarps * 32) match_kernel(const __grid_co
       if (active) rv = parse_record(buf + (o - gbase), buf + (onext - gbase));
       __syncwarp();
       const bool can = active && rv.qual_len == rv.seq_len;  // unequal lengths never leave bk_tokenize
-      if (pg.nins) {  // unbounded repetition: backtracking over the insertion points
+      if (VM) {  // the general form: a backtracking program
+        uint4 sp = make_uint4(0, 0, 0, 0);
+        uint32_t gave_up = 0;
+        if (can) {
+          ms = match_vm<false>(tab, smem_u32(s_vm), pg.vm_len, pg.ncaps, rv.seq, rv.seq_len, &sp, &gave_up);
+          if (ms == -1 && P.rc) {
+            ms = match_vm<true>(tab, smem_u32(s_vm), pg.vm_len, pg.ncaps, rv.seq, rv.seq_len, &sp, &gave_up);
+            // parse.rs:166 on the forward bytes under the offsets (F7)
+            const uint32_t o3[3] = {sp.x >> 16, sp.y >> 16, sp.z >> 16}, l3[3] = {sp.y & 0xFFFFu, sp.z & 0xFFFFu, sp.w & 0xFFFFu};
+            for (uint32_t c = 0; ms >= 0 && c < pg.ncaps; ++c)
+              if (!span_utf8_ok(rv.seq + (uint32_t)ms + o3[c], rv.seq + (uint32_t)ms + o3[c] + l3[c])) ms = -1;
+          }
+        }
+        if (ms < 0) ms = -1;
+        if (gave_up) atomicOr(&P.result->error, 8u);
+        if (active) P.spans[r0 + lane] = sp;
+      } else if (pg.nins) {  // unbounded repetition: backtracking over the insertion points
         unsigned long long ex = 0;
+        bool was_rc = false;
         if (can) {
           ms = match_par<false>(tab, rv.seq, rv.seq_len, &ex);
           if (ms < 0 && P.rc) {
             ms = match_par<true>(tab, rv.seq, rv.seq_len, &ex);
-            for (uint32_t c = 0; ms >= 0 && c < pg.ncaps; ++c) {  // parse.rs:166 on the forward bytes under the offsets (F7)
-              uint32_t off, len;
-              par_cap(pg, c, ex, off, len);
-              if (!span_utf8_ok(rv.seq + (uint32_t)ms + off, rv.seq + (uint32_t)ms + off + len)) ms = -1;
-            }
+            was_rc = true;
           }
         }
-        if (active) P.extras[r0 + lane] = ex;
+        uint32_t off[3] = {0, 0, 0}, clen[3] = {0, 0, 0}, tlen = pg.total_len;
+        if (ms >= 0) {
+          for (uint32_t i = 0; i < pg.nins; ++i) tlen += (uint32_t)(ex >> (16u * i)) & 0xFFFFu;
+          for (uint32_t c = 0; c < pg.ncaps; ++c) {
+            par_cap(pg, c, ex, off[c], clen[c]);
+            // parse.rs:166 on the forward bytes under the offsets (F7)
+            if (was_rc && !span_utf8_ok(rv.seq + (uint32_t)ms + off[c], rv.seq + (uint32_t)ms + off[c] + clen[c])) ms = -1;
+          }
+        }
+        if (active) P.spans[r0 + lane] = pack_spans(tlen, off, clen);
       } else if (var && s_scan) {
         ms = match_variants_scan(P.vprog, P.nvar, tab, smem_u32(s_voff), s_scan - 1u, rv.seq, rv.seq_len, can);
         if (can && ms < 0 && P.rc) {

@@ -719,6 +719,9 @@ struct RParser {
   const std::string& p;
   std::string err;
   int status = BK_OK;
+  // (general form only) the lowercase runs the reference's finder takes: each is ONE atom, so that a repetition operator
+  // behind it binds to the whole run, as it does to the group the run expands to (pattern.rs:93-109)
+  const std::vector<Span>* fuzzy = nullptr;
   explicit RParser(const std::string& s) : p(s) {}
   bool fail(int st, const std::string& m) { if (status == BK_OK) { status = st; err = m; } return false; }
   bool unsupported(const std::string& what) { return fail(BK_E_UNSUPPORTED, "unsupported pattern construct (" + what + ")"); }
@@ -761,7 +764,13 @@ struct RParser {
     RNode atom;
     atom.b = i;
     const char c = p[i];
-    if (c == '(') {
+    const Span* run = nullptr;
+    if (fuzzy)
+      for (const auto& f : *fuzzy)
+        if (f.begin == i) run = &f;
+    if (run) {
+      i = run->end;
+    } else if (c == '(') {
       atom.type = RNode::GROUP;
       size_t j = i + 1;
       if (j < p.size() && p[j] == '?') {
@@ -1005,7 +1014,326 @@ static int compile_tree(const std::string& pattern, size_t max_error, Program* p
   return BK_OK;
 }
 
+// ---- the general form: a backtracking program (bk_program.h: bk_vmop) -----------------------------------------------
+//
+// For what none of the forms above can express.  The tree of compile_tree (with every lowercase run as one atom) is
+// compiled the way a backtracking regex engine would run it: alternation = SPLIT first branch / rest; X{m,n} = m copies
+// and n - m nested optional copies; X* = a loop whose SPLIT prefers the body (greedy) or the exit (lazy); a named group =
+// SAVE start, body, SAVE end; repetition of a one-byte class is one instruction with one backtracking entry.  Refused: a
+// repeated group that can match the empty string (engines differ on when such a loop ends), escapes, flags, look-around,
+// and a lowercase run inside a character class (the reference's finder would rewrite the class).
+
+namespace {
+
+struct VmGen {
+  const std::string& p;
+  size_t max_error;
+  const std::vector<Span>& runs;     // the lowercase runs (atoms of the tree)
+  std::vector<FuzzySpan> no_spans;
+  Lowering lw;                       // for its class parser and class table
+  std::vector<bk_vmop> code;
+  std::vector<uint8_t> lit;
+  std::vector<std::pair<size_t, std::string>> names;  // named groups in pattern order: (source offset, name)
+  size_t label = 0;                  // code.size() when a jump target was last taken: no literal merges across it
+  std::string err;
+  int status = BK_OK;
+  VmGen(const std::string& s, size_t k, const std::vector<Span>& r) : p(s), max_error(k), runs(r), lw(s, no_spans) {}
+
+  bool fail(int st, const std::string& m) { if (status == BK_OK) { status = st; err = m; } return false; }
+  bool unsupported(const std::string& what) { return fail(BK_E_UNSUPPORTED, "unsupported pattern construct (" + what + ")"); }
+  size_t here() { label = code.size(); return label; }
+  size_t emit(uint8_t op, uint16_t a = 0, uint16_t b = 0, uint8_t k = 0, uint16_t c = 0) {
+    bk_vmop o;
+    o.op = op; o.k = k; o.a = a; o.b = b; o.c = c;
+    code.push_back(o);
+    return code.size() - 1;
+  }
+  bool room() { return code.size() < BK_VM_MAX ? true : unsupported("pattern needs more than " + std::to_string(BK_VM_MAX) + " instructions"); }
+  const Span* run_of(const RNode& n) const {
+    if (n.type != RNode::ATOM) return nullptr;
+    for (const auto& f : runs)
+      if (f.begin == n.b && f.end == n.e) return &f;
+    return nullptr;
+  }
+  bool add_lit(const std::string& bytes, size_t k) {
+    if (lit.size() + bytes.size() > BK_MAX_LIT) return unsupported("literal bytes exceed " + std::to_string(BK_MAX_LIT));
+    const size_t at = lit.size();
+    lit.insert(lit.end(), bytes.begin(), bytes.end());
+    emit(BK_VM_LIT, (uint16_t)at, (uint16_t)bytes.size(), (uint8_t)(k > 255 ? 255 : k));
+    return room();
+  }
+  int dot_class() {
+    Class128 cl{{~0u, ~0u, ~0u, ~0u}};
+    cl.w[0] &= ~(1u << '\n');
+    return lw.class_index(cl);
+  }
+  // class index of a one-byte class atom (`.` or `[...]`), -1 if n is something else
+  int byte_class(const RNode& n, bool* ok) {
+    *ok = true;
+    if (n.type != RNode::ATOM || run_of(n)) return -1;
+    if (p[n.b] == '.' && n.e == n.b + 1) return dot_class();
+    if (p[n.b] == '[') {
+      size_t i = n.b;
+      Class128 cl;
+      if (!lw.parse_class(i, &cl) || i != n.e) {
+        *ok = fail(lw.status != BK_OK ? lw.status : BK_E_UNSUPPORTED, lw.err.empty() ? "unsupported character class" : lw.err);
+        return -1;
+      }
+      return lw.class_index(cl);
+    }
+    return -1;
+  }
+
+  // the named groups, numbered by where they open (Regex::capture_names, pattern.rs:191-205)
+  bool collect_names(const RNode& n) {
+    if (n.type == RNode::GROUP && n.named) {
+      const size_t lt = n.prefix.find('<');
+      const std::string name = n.prefix.substr(lt + 1, n.prefix.size() - lt - 2);
+      if (name.empty()) return fail(BK_E_PATTERN, "Regex error: empty capture group name");
+      for (char ch : name)
+        if (!(is_word((unsigned char)ch) || ch == '.' || ch == '[' || ch == ']')) return fail(BK_E_PATTERN, "Regex error: invalid capture group character");
+      if (name[0] >= '0' && name[0] <= '9') return fail(BK_E_PATTERN, "Regex error: invalid capture group character");
+      for (const auto& nm : names)
+        if (nm.second == name) return fail(BK_E_PATTERN, "Regex error: duplicate capture group name");
+      names.emplace_back(n.b, name);
+    }
+    for (const auto& k : n.kids)
+      if (!collect_names(k)) return false;
+    return true;
+  }
+  int slot_of(const RNode& n) const {
+    for (size_t c = 0; c < names.size(); ++c)
+      if (names[c].first == n.b) return (int)c;
+    return -1;
+  }
+
+  long min_len(const RNode& n) const {
+    if (const Span* f = run_of(n)) return (long)(f->end - f->begin);
+    switch (n.type) {
+      case RNode::ATOM: return (p[n.b] == '^' || p[n.b] == '$') ? 0 : 1;
+      case RNode::GROUP: return min_len(n.kids[0]);
+      case RNode::CONCAT: { long t = 0; for (const auto& k : n.kids) t += min_len(k); return t; }
+      case RNode::ALT: { long t = -1; for (const auto& k : n.kids) { const long m = min_len(k); t = t < 0 || m < t ? m : t; } return t < 0 ? 0 : t; }
+      case RNode::REPEAT: return n.lo * min_len(n.kids[0]);
+    }
+    return 0;
+  }
+  // most bytes a match of n can have, -1 = no bound
+  long max_len(const RNode& n) const {
+    if (const Span* f = run_of(n)) return (long)(f->end - f->begin);
+    switch (n.type) {
+      case RNode::ATOM: return (p[n.b] == '^' || p[n.b] == '$') ? 0 : 1;
+      case RNode::GROUP: return max_len(n.kids[0]);
+      case RNode::CONCAT: { long t = 0; for (const auto& k : n.kids) { const long m = max_len(k); if (m < 0) return -1; t += m; } return t; }
+      case RNode::ALT: { long t = 0; for (const auto& k : n.kids) { const long m = max_len(k); if (m < 0) return -1; t = m > t ? m : t; } return t; }
+      case RNode::REPEAT: { const long m = max_len(n.kids[0]); return m == 0 ? 0 : (n.hi < 0 || m < 0) ? -1 : n.hi * m; }
+    }
+    return 0;
+  }
+
+  bool gen(const RNode& n) {
+    switch (n.type) {
+      case RNode::ATOM: {
+        if (const Span* f = run_of(n)) {  // a lowercase run: Hamming distance <= min(k, len) (pattern.rs:40-79)
+          std::string up = p.substr(f->begin, f->end - f->begin);
+          for (auto& ch : up) ch = ascii_upper(ch);
+          if (max_error >= up.size()) { emit(BK_VM_CLS, (uint16_t)dot_class(), (uint16_t)up.size()); return room(); }
+          return add_lit(up, max_error);
+        }
+        const char c = p[n.b];
+        if (c == '^') { emit(BK_VM_BOL); return room(); }
+        if (c == '$') { emit(BK_VM_EOL); return room(); }
+        if (c == '\\') return unsupported("escape sequence");
+        bool ok;
+        const int cls = byte_class(n, &ok);
+        if (!ok) return false;
+        if (cls >= 0) { emit(BK_VM_CLS, (uint16_t)cls, 1); return room(); }
+        if (c == ']' || c == '}') return unsupported(std::string("unbalanced ") + c);
+        if ((unsigned char)c >= 0x80) return unsupported("non-ASCII literal");
+        // a literal byte joins an exact literal directly in front of it (unless a jump lands between the two)
+        if (code.size() > label && code.back().op == BK_VM_LIT && code.back().k == 0 &&
+            (size_t)code.back().a + code.back().b == lit.size() && lit.size() < BK_MAX_LIT) {
+          lit.push_back((uint8_t)c);
+          code.back().b++;
+          return true;
+        }
+        return add_lit(std::string(1, c), 0);
+      }
+      case RNode::GROUP: {
+        const int c = n.named ? slot_of(n) : -1;
+        if (c >= 0 && c < BK_MAX_CAPS) { emit(BK_VM_SAVE, (uint16_t)(2 * c)); if (!room()) return false; }
+        if (!gen(n.kids[0])) return false;
+        if (c >= 0 && c < BK_MAX_CAPS) { emit(BK_VM_SAVE, (uint16_t)(2 * c + 1)); if (!room()) return false; }
+        return true;
+      }
+      case RNode::CONCAT:
+        for (const auto& k : n.kids)
+          if (!gen(k)) return false;
+        return true;
+      case RNode::ALT: {
+        std::vector<size_t> exits;
+        for (size_t i = 0; i < n.kids.size(); ++i) {
+          const bool last = i + 1 == n.kids.size();
+          size_t split = 0;
+          if (!last) {
+            split = emit(BK_VM_SPLIT);
+            if (!room()) return false;
+            code[split].a = (uint16_t)here();
+          }
+          if (!gen(n.kids[i])) return false;
+          if (!last) {
+            exits.push_back(emit(BK_VM_JMP));
+            if (!room()) return false;
+            code[split].b = (uint16_t)here();
+          }
+        }
+        for (size_t e : exits) code[e].a = (uint16_t)here();
+        return true;
+      }
+      case RNode::REPEAT: {
+        const RNode& x = n.kids[0];
+        bool ok;
+        const int cls = byte_class(x, &ok);
+        if (!ok) return false;
+        if (n.lo > 60000 || n.hi > 60000) return unsupported("repetition count too large");
+        if (cls >= 0) {  // a one-byte class: the required copies, then one instruction for the optional ones
+          if (n.lo > 0) { emit(BK_VM_CLS, (uint16_t)cls, (uint16_t)n.lo); if (!room()) return false; }
+          if (n.hi != n.lo) { emit(BK_VM_STAR, (uint16_t)cls, (uint16_t)(n.hi < 0 ? 0xFFFF : n.hi - n.lo), n.lazy ? 1 : 0); if (!room()) return false; }
+          return true;
+        }
+        // (a round that may match nothing has engine-specific rules for when the repetition ends)
+        if ((n.hi < 0 || n.hi > 1) && min_len(x) == 0) return unsupported("repetition of a group that can match the empty string");
+        if (n.lo > BK_VM_MAX || (n.hi > 0 && n.hi > BK_VM_MAX)) return unsupported("pattern needs more than " + std::to_string(BK_VM_MAX) + " instructions");
+        for (long r = 0; r < n.lo; ++r)
+          if (!gen(x)) return false;
+        if (n.hi < 0) {  // L: SPLIT body, exit | body | JMP L
+          const size_t L = emit(BK_VM_SPLIT);
+          if (!room()) return false;
+          const size_t b = here();
+          if (!gen(x)) return false;
+          emit(BK_VM_JMP, (uint16_t)L);
+          if (!room()) return false;
+          const size_t exit = here();
+          code[L].a = (uint16_t)(n.lazy ? exit : b);
+          code[L].b = (uint16_t)(n.lazy ? b : exit);
+        } else {
+          std::vector<size_t> splits;
+          for (long r = n.lo; r < n.hi; ++r) {
+            const size_t sp = emit(BK_VM_SPLIT);
+            if (!room()) return false;
+            splits.push_back(sp);
+            code[sp].a = (uint16_t)here();  // the body (swapped below when lazy)
+            if (!gen(x)) return false;
+          }
+          const uint16_t exit = (uint16_t)here();
+          for (size_t sp : splits) {
+            const uint16_t b = code[sp].a;
+            code[sp].a = n.lazy ? exit : b;
+            code[sp].b = n.lazy ? b : exit;
+          }
+        }
+        return true;
+      }
+    }
+    return true;
+  }
+};
+
+}  // namespace
+
+static int compile_vm(const std::string& pattern, size_t max_error, Program* prog, std::string* err) {
+  {
+    std::vector<FuzzySpan> spans;
+    int rc = expand(pattern, max_error, &prog->expanded, &spans, err);  // (also the reference's own errors: pattern.rs:56-58)
+    if (rc != BK_OK) return rc;
+  }
+  const std::vector<Span> runs = find_fuzzy_runs(pattern);
+  RParser ps(pattern);
+  ps.fuzzy = &runs;
+  RNode root;
+  size_t i = 0;
+  if (!ps.parse_alt(i, 0, &root)) { *err = ps.err; return ps.status; }
+  if (i != pattern.size()) { *err = "Regex error: unopened group"; return BK_E_PATTERN; }
+  // a lowercase run inside a character class: the reference's finder would rewrite the class itself
+  {
+    bool in_class = false;
+    size_t open = 0;
+    for (size_t q = 0; q < pattern.size(); ++q) {
+      const char c = pattern[q];
+      if (!in_class && c == '\\') { ++q; continue; }
+      if (!in_class && c == '[') { in_class = true; open = q; continue; }
+      if (in_class && c == ']' && q > open + 1 && !(q == open + 2 && pattern[open + 1] == '^')) { in_class = false; continue; }
+      if (in_class)
+        for (const auto& f : runs)
+          if (q >= f.begin && q < f.end) { *err = "unsupported pattern construct (lowercase run inside a character class)"; return BK_E_UNSUPPORTED; }
+    }
+  }
+  VmGen g(pattern, max_error, runs);
+  if (!g.collect_names(root) || !g.gen(root)) { *err = g.err; return g.status; }
+  g.emit(BK_VM_MATCH);
+  if (g.code.size() > BK_VM_MAX) { *err = "unsupported pattern construct (pattern needs more than " + std::to_string(BK_VM_MAX) + " instructions)"; return BK_E_UNSUPPORTED; }
+  for (const auto& nm : g.names)
+    if (nm.second != "UMI" && nm.second != "CB" && nm.second != "SB") { *err = "Provided unexpected barcode capture group " + nm.second; return BK_E_PATTERN; }
+  if (g.names.empty()) { *err = prog->expanded + " capture group not found in your pattern"; return BK_E_PATTERN; }
+  if (g.lw.classes.size() > BK_MAX_CLASSES) { *err = "unsupported pattern: more than 8 distinct character classes"; return BK_E_UNSUPPORTED; }
+  bk_devprog& d = prog->dev;
+  memset(&d, 0, sizeof d);
+  d.present = 1;
+  d.anchor_start = g.code[0].op == BK_VM_BOL;  // (only start 0 can match; `$` stays an instruction)
+  for (size_t c = 0; c < g.lw.classes.size(); ++c) memcpy(d.cls[c], g.lw.classes[c].w, 16);
+  memcpy(d.lit, g.lit.data(), g.lit.size());
+  d.ncaps = (uint32_t)g.names.size();
+  {
+    // longest span of every capture, for the output bound (bk_ctx.cu: par_growth); 0xFFFF = as long as the read
+    struct Finder {
+      const VmGen& g;
+      void walk(const RNode& n, bk_devprog& d) const {
+        if (n.type == RNode::GROUP && n.named) {
+          const int c = g.slot_of(n);
+          const long m = g.max_len(n.kids[0]);
+          if (c >= 0 && c < BK_MAX_CAPS) d.caps[c].len = (uint16_t)(m < 0 || m > 0xFFFF ? 0xFFFF : m);
+        }
+        for (const auto& k : n.kids) walk(k, d);
+      }
+    } finder{g};
+    finder.walk(root, d);
+  }
+  for (size_t c = 0; c < g.names.size(); ++c) {
+    d.caps[c].name_len = (uint8_t)g.names[c].second.size();
+    memcpy(d.caps[c].name, g.names[c].second.data(), g.names[c].second.size());
+    d.hdr_growth += 3 + d.caps[c].name_len;
+  }
+  // the states the device matcher enters once per read (match_vm): where paths can meet again
+  uint32_t marks = 0;
+  for (size_t q = 0; q < g.code.size(); ++q)
+    if (g.code[q].op == BK_VM_SPLIT || g.code[q].op == BK_VM_STAR || (q > 0 && g.code[q - 1].op == BK_VM_STAR)) g.code[q].c = (uint16_t)++marks;
+  d.nops = marks;
+  const long tmin = g.min_len(root);
+  d.total_len = (uint32_t)(tmin > BK_MAX_TOTAL_LEN ? BK_MAX_TOTAL_LEN : tmin);  // shortest match: starts beyond L - total_len are not tried
+  d.vm_len = (uint32_t)g.code.size();
+  prog->vm = g.code;
+  prog->variants.clear();
+  prog->variants.push_back(d);
+  return BK_OK;
+}
+
+static int compile_lowered(const std::string& pattern, size_t max_error, Program* prog, std::string* err);
+
+// The forms in order of preference: fixed / variants / parametric (compile_lowered); what they refuse as outside their
+// grammar goes to the general form, and what that refuses too is reported with the first refusal's message.
 int compile(const std::string& pattern, size_t max_error, Program* prog, std::string* err) {
+  prog->vm.clear();
+  const int rc = compile_lowered(pattern, max_error, prog, err);
+  if (rc != BK_E_UNSUPPORTED) return rc;
+  Program general;
+  std::string gerr;
+  const int rg = compile_vm(pattern, max_error, &general, &gerr);
+  if (rg == BK_OK) { *prog = general; err->clear(); return BK_OK; }
+  if (rg == BK_E_PATTERN) { *err = gerr; return rg; }
+  return rc;
+}
+
+static int compile_lowered(const std::string& pattern, size_t max_error, Program* prog, std::string* err) {
   {
     bool handled = false;
     const int rct = compile_tree(pattern, max_error, prog, err, &handled);
@@ -1168,7 +1496,7 @@ int bk_program_dump(const bk_program* p, char* out, size_t cap) {
   char line[128];
   snprintf(line, sizeof line, "anchor %u %u\ntotal %u\n", d.anchor_start, d.anchor_end, d.total_len);
   s += line;
-  for (uint32_t o = 0; o < d.nops; ++o) {
+  for (uint32_t o = 0; o < (d.vm_len ? 0u : d.nops); ++o) {
     const bk_op& op = d.ops[o];
     if (op.kind == BK_OP_LIT) {
       snprintf(line, sizeof line, "lit %u %u %u ", op.off, op.len, op.k);
@@ -1191,6 +1519,32 @@ int bk_program_dump(const bk_program* p, char* out, size_t cap) {
     snprintf(line, sizeof line, "ins %u %u %u %u %u %u\n", d.ins[i].pos, d.ins[i].max_extra, d.ins[i].lazy, d.ins[i].cls,
              d.ins[i].capmask, d.ins[i].op_end);
     s += line;
+  }
+  if (d.vm_len) {  // the general form: classes by index, then the instructions
+    static const char* const kOp[] = {"cls", "lit", "split", "jmp", "save", "bol", "eol", "match", "star"};
+    for (uint32_t k = 0; k < BK_MAX_CLASSES; ++k) {
+      if (!(d.cls[k][0] | d.cls[k][1] | d.cls[k][2] | d.cls[k][3])) continue;
+      snprintf(line, sizeof line, "vmclass %u ", k);
+      s += line;
+      for (int b = 0; b < 16; ++b) {
+        snprintf(line, sizeof line, "%02x", (d.cls[k][b >> 2] >> (8 * (b & 3))) & 0xFF);
+        s += line;
+      }
+      s += "\n";
+    }
+    for (uint32_t i = 0; i < d.vm_len && i < p->prog.vm.size(); ++i) {
+      const bk_vmop& o = p->prog.vm[i];
+      snprintf(line, sizeof line, "vm %u %s %u %u %u", i, o.op < 9 ? kOp[o.op] : "?", o.k, o.a, o.b);
+      s += line;
+      if (o.op == BK_VM_LIT) {
+        s += " ";
+        for (uint32_t j = 0; j < o.b; ++j) {
+          snprintf(line, sizeof line, "%02x", d.lit[o.a + j]);
+          s += line;
+        }
+      }
+      s += "\n";
+    }
   }
   for (uint32_t c = 0; c < d.ncaps; ++c) {
     snprintf(line, sizeof line, "cap %.*s %u %u\n", (int)d.caps[c].name_len, d.caps[c].name, d.caps[c].off,

@@ -51,6 +51,30 @@ struct bk_ins {
   uint8_t op_end;      // ops [0, op_end) belong to segments 0..i
 };
 
+// The general form (bk_pattern.cc: compile_vm): whatever the fixed, variant and parametric forms cannot express --
+// unbounded repetition of groups or together with alternatives, named groups that may not take part in a match,
+// alternation at the top level -- is compiled to a small backtracking program, executed one lane per read by
+// match_kernel (match_vm) with the regex crate's priorities: SPLIT tries `a` before `b`.
+#define BK_VM_MAX 512
+enum : uint8_t {
+  BK_VM_CLS = 0,    // the next b bytes all in class a
+  BK_VM_LIT = 1,    // the next b bytes = lit[a .. a + b) with at most k mismatches
+  BK_VM_SPLIT = 2,  // continue at a; on failure at b
+  BK_VM_JMP = 3,    // continue at a
+  BK_VM_SAVE = 4,   // slot a (2c: capture c starts here, 2c + 1: ends here)
+  BK_VM_BOL = 5,    // at the start of the read
+  BK_VM_EOL = 6,    // at the end of the read
+  BK_VM_MATCH = 7,
+  BK_VM_STAR = 8,   // up to b (0xFFFF: any number of) further bytes of class a, as many as possible first, or as few (k = 1)
+};
+struct bk_vmop {
+  uint8_t op;
+  uint8_t k;
+  uint16_t a;
+  uint16_t b;
+  uint16_t c;  // 1 + this instruction's index among the marked ones (SPLIT, STAR, what follows a STAR), 0: not marked
+};
+
 struct bk_devprog {
   uint32_t present;  // 0: this mate has no pattern (run.rs:233-245 `None`)
   uint32_t anchor_start;
@@ -66,4 +90,14 @@ struct bk_devprog {
   bk_cap caps[BK_MAX_CAPS];
   bk_ins ins[BK_MAX_INS];
   uint8_t cap_ins_before[4];  // capture c starts behind the insertions [0, cap_ins_before[c])
+  uint32_t vm_len;            // > 0: the general form -- the code itself travels separately (Program::vm); caps[c].len
+                              // is then the longest span capture c can have (0xFFFF: the read's length), total_len the
+                              // shortest match, nops the number of marked instructions
 };
+
+// A program whose matches have no fixed shape -- parametric or general: match_kernel leaves the spans of every match
+// (KParams::xtab) and the extract launches size and assemble every record from those.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline bool bk_free_shape(const bk_devprog& p) { return p.nins > 0 || p.vm_len > 0; }

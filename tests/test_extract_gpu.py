@@ -407,8 +407,10 @@ def test_random_patterns_against_the_oracle():
             assert e.status in (_lib.BK_E_UNSUPPORTED, _lib.BK_E_PATTERN), (pat, str(e))
             refused += 1
             continue
-        out, _ = ctx.extract_text(fq)
-        ctx.close()
+        try:
+            out, _ = ctx.extract_text(fq)
+        finally:
+            ctx.close()
         assert out == exp, (pat, k, skip, rc)
         accepted += 1
     assert accepted >= 100, (accepted, refused)
@@ -453,6 +455,127 @@ def test_unbounded_repetition_paired_end():
             o1, o2, _ = run_pe(fq1, fq2, p1, p2, k, skip=skip, rc=rc)
             e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, k, rc_barcodes=rc, skip_trimming=skip)
             assert o1 == e1 and o2 == e2, (p1, p2, k, skip, rc)
+
+
+GENERAL = [
+    ("^(?P<UMI>[ATGCN]{4})+", 0), ("^(?P<UMI>[ATGCN]+)(A*C){2}", 0), ("^((?P<UMI>[ATGCN]{4})A){1,2}", 0),
+    ("^(?P<UMI>[ATGCN]{4})?", 0), ("^(?P<UMI>A)|(?P<CB>C)", 0), ("^(A|(?P<UMI>C))T", 0), ("^(?P<UMI>[ACGT]+)(A|C)", 0),
+    ("(?P<UMI>[ACGT]{4})(AC)+G", 0), ("(?P<CB>[ACGT]{3,})(atgc)+(?P<UMI>[ACGT]{2})", 1), ("(?P<UMI>A+?)(C|GT)*?T$", 0),
+    ("^(?P<CB>[ACGT]{2})((?P<UMI>A[CG])|T)+", 0), ("(?P<UMI>[ACGT]{4})(atgccat|gattaca)+", 1), ("^(?P<UMI>(AC|A)+)C", 0),
+    ("(?P<UMI>(A|AC)(C|CA)*)T", 0), ("(?P<SB>[ACGT]{2})(gattaca){1,}?(?P<UMI>[ACGT]{3})", 2),
+    ("(?P<UMI>[ACGT]{3})(acgt){2,}|^(?P<CB>N+)", 1), ("^(?P<UMI>[ACGT]{4})(A|C|G|T|N){3}", 0),
+    ("(?P<CB>[ACGT](?P<UMI>[AC]+)G)(T|$)", 0),
+]
+
+
+@pytest.mark.parametrize("pat,k", GENERAL)
+def test_general_form_single_end(pat, k):
+    """What the fixed, variant and parametric forms cannot express -- unbounded repetition of
+    groups and lowercase runs, alternation at the top level, named groups that may take no part in a match (the read is
+    then dropped: parse.rs:127-136), nested named groups -- runs as a backtracking program in match_kernel<VM>
+    (match_vm), one lane per read, and the extract launch rewrites every record from the spans it leaves.  Output must
+    equal the oracle's (Python `re`: the same priorities), with trimming, -s and -r."""
+    assert "vm 0 " in _lib.Program(pat, k).dump()
+    rnd = random.Random(zlib.crc32(pat.encode()))
+    fq = ragged_fastq(rnd, 3000, plant=[b"GATTACA", b"ATGCCAT", b"ACGT", b"ACACAC", b"ACGTACGT"], plus_comment=True,
+                      min_len=0, max_len=80)
+    for skip, rc in ((False, False), (True, False), (False, True)):
+        out, res = run_se(fq, pat, k, skip, rc)
+        assert out == bo.extract_se(fq, pat, k, rc, skip), (pat, k, skip, rc)
+        assert res.n_out == out.count(b"\n") // 4       # (a pattern one of whose groups never takes part keeps nothing)
+
+
+def test_general_form_paired_end():
+    rnd = random.Random(12)
+    n = 2500
+    heads = [rnd.choice([3, 23, 60]) for _ in range(n)]
+    fq1 = ragged_fastq(rnd, n, 1, plant=[b"ATGCCAT", b"ACAC"], head_lens=heads, min_len=10, max_len=70)
+    fq2 = ragged_fastq(rnd, n, 2, plant=[b"GATTACA"], head_lens=heads, min_len=0, max_len=70, crlf=True)
+    combos = [("^(?P<UMI>[ATGCN]{4})+atgccat", "(?P<CB>[ACGT]{3,})(gattaca)+"), ("(?P<UMI>[ACGT]{4})(AC)+G", None),
+              (None, "(?P<CB>[ACGT]*?)(gattaca|ACGT)+(?P<SB>[ACGT]+)"), ("^(?P<UMI>[ATGCN]{12})", "^(?P<CB>[ACGT]+)(gattaca)*T"),
+              ("(?P<UMI>[ATGCN]{4})atgccat", "^(?P<CB>A)|(?P<SB>C[GT]+)"), ("^(?P<UMI>[ATGCN]+)atgccat", "(?P<CB>(AC|GT)+)$")]
+    for p1, p2 in combos:
+        for k, skip, rc in ((1, False, False), (2, True, False), (0, False, True)):
+            o1, o2, _ = run_pe(fq1, fq2, p1, p2, k, skip=skip, rc=rc)
+            e1, e2 = bo.extract_pe(fq1, fq2, p1, p2, k, rc_barcodes=rc, skip_trimming=skip)
+            assert o1 == e1 and o2 == e2, (p1, p2, k, skip, rc)
+
+
+def test_general_form_gives_up_instead_of_guessing():
+    """The reference's engine is linear-time; the device matcher is a memoised backtracker whose visited states (marked
+    instructions x read length) must fit a fixed number of bits per read.  A read that needs more is refused
+    (BK_E_UNSUPPORTED from the batch), never answered differently -- and a pattern that is exponential for a plain
+    backtracker is not a problem below that size."""
+    pat = "^(?P<UMI>(A|AA)+)(C|G)*(T|N)*$"
+    ok = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, b"A" * (3 + i % 9), b"I" * (3 + i % 9)) for i in range(64))
+    ok += b"@x\n%sCT\n+\n%sII\n" % (b"A" * 150, b"I" * 150)     # (one that matches: the ORACLE's engine is exponential on a miss)
+    out, _ = run_se(ok, pat, 0)
+    assert out == bo.extract_se(ok, pat, 0)
+    bad = ok + b"@y\n%sC\n+\n%sI\n" % (b"A" * 3000, b"I" * 3000)
+    with pytest.raises(_lib.BarkitError) as e:
+        run_se(bad, pat, 0)
+    assert e.value.status == _lib.BK_E_UNSUPPORTED and "backtracking" in str(e.value)
+
+
+def _random_general_pattern(rnd):
+    """Random patterns that need the general form: repeated groups without a bound, alternatives at the top level,
+    optional and nested named groups, repeated lowercase runs."""
+    names = ["UMI", "CB", "SB"]
+    rnd.shuffle(names)
+    cls = lambda: rnd.choice(["[ACGT]", "[ACGTN]", "[AC]", "[GT]", ".", "[^N]"])
+    small = lambda: rnd.choice(["A", "CG", "TT", "acg", "G[AC]", "[GT]{2}", "gatt", "[AC]+T", "C?G"])
+    def group():
+        body = "|".join(small() for _ in range(rnd.randint(1, 3)))
+        return "(" + body + ")" + rnd.choice(["+", "*", "+?", "{2,}", "{1,}?", "{1,3}", ""])
+    def cap(i):
+        inner = cls() + rnd.choice(["{2}", "{4}", "{3,5}", "{2,}", "+", "*", "{1,3}?"])
+        if rnd.random() < 0.3:
+            inner += group()
+        return "(?P<%s>%s)" % (names[i], inner) + ("?" if rnd.random() < 0.15 else "")
+    def branch(first):
+        parts = []
+        for i in range(first, first + rnd.randint(1, 2)):
+            if rnd.random() < 0.6:
+                parts.append(group())
+            parts.append(cap(i))
+        if rnd.random() < 0.7:
+            parts.append(group())
+        return ("^" if rnd.random() < 0.4 else "") + "".join(parts) + ("$" if rnd.random() < 0.15 else ""), first + 2
+    b1, nxt = branch(0)
+    if rnd.random() < 0.25:
+        return b1 + "|" + "(?P<%s>%s+)" % (names[2], cls())
+    return b1
+
+
+def test_random_general_patterns_against_the_oracle():
+    rnd = random.Random(20241021)
+    fq = ragged_fastq(rnd, 600, plant=[b"GATTACA", b"ACGT", b"GATT", b"ACGACG", b"TTATTA"], min_len=0, max_len=48)
+    accepted = general = gave_up = 0
+    for it in range(220):
+        pat = _random_general_pattern(rnd)
+        k = rnd.choice([0, 1, 1, 2])
+        skip, rc = rnd.random() < 0.25, rnd.random() < 0.25
+        try:
+            exp = bo.extract_se(fq, pat, k, rc, skip)
+        except Exception:
+            continue
+        try:
+            ctx = make_ctx(pat, k=k, skip=skip, rc=rc)
+        except _lib.BarkitError as e:
+            assert e.status in (_lib.BK_E_UNSUPPORTED, _lib.BK_E_PATTERN), (pat, str(e))
+            continue
+        general += "vm 0 " in _lib.Program(pat, k).dump()
+        try:
+            out, _ = ctx.extract_text(fq)
+        except _lib.BarkitError as e:      # the backtracking budget: refused, not approximated
+            assert e.status == _lib.BK_E_UNSUPPORTED, (pat, str(e))
+            gave_up += 1
+            continue
+        finally:
+            ctx.close()
+        assert out == exp, (pat, k, skip, rc)
+        accepted += 1
+    assert accepted >= 80 and general >= 60 and gave_up <= accepted // 4, (accepted, general, gave_up)
 
 
 def test_host_side_mate_falls_back_when_the_host_copy_is_slow():

@@ -61,18 +61,14 @@ def test_error_messages_follow_error_rs():
 
 
 @pytest.mark.parametrize("pattern", [
-    "^(?P<UMI>([ATGCN])+)", "^(?P<UMI>[ATGCN]{4})+", "^(?P<UMI>[ATGCN]+)(A*C){2}", "^(?P<UMI>[ATGCN]+)a*",
-    "^(?P<UMI>A*C*G*T*N*)", "^((?P<UMI>[ATGCN]{4})A){1,2}", "^(?P<UMI>[ATGCN]{2,4}+)", "^(?P<UMI>[ATGCN]{2,}*)",
+    "^(?P<UMI>[ATGCN]{2,4}+)", "^(?P<UMI>[ATGCN]{2,}*)",       # stacked repetition
     "^(?P<UMI>[ATGCN]{4,2})", "?(?P<UMI>[ATGCN]{4})",
-    r"^(?P<UMI>\w{4})", "(?i)(?P<UMI>[ATGCN]{4})", "^(?P<UMI>[ATGCN]{4})?", "(?P<UMI>[ATGCN]{4})^",
-    "(?=A)(?P<UMI>[ATGCN]{4})", "((?P<UMI>[ATGCN]{4})){2}", "(?P<UMI>[[:alpha:]]{4})",
+    r"^(?P<UMI>\w{4})", "(?i)(?P<UMI>[ATGCN]{4})",
+    "(?=A)(?P<UMI>[ATGCN]{4})", "(?P<UMI>[[:alpha:]]{4})",
     "^(?P<UMI>[^atg-z]{4})", "é(?P<UMI>A)",
-    # alternation and repeated groups are unfolded into variants (below); what stays refused:
-    "^(?P<UMI>A)|(?P<CB>C)",                       # alternation at the top level
-    "^(A|(?P<UMI>C))T",                            # a named group that may not take part in the match
     "^(?P<UMI>[ACGT]{4})(A?){2}",                  # a repeated group that can match the empty string
-    "^(?P<UMI>[ACGT]+)(A|C)",                      # unbounded repetition together with alternatives
-    "^(?P<UMI>[ACGT]{4})(A|C|G|T|N){3}",           # 125 combinations
+    "^(?P<UMI>[ACGT]{4})(A*|C)+",
+    "^(?P<UMI>A)|(?P<XY>C)", "^(?P<UMI>A)|(?P<UMI>C)",
 ])
 def test_unsupported_constructs_are_refused(pattern):
     with pytest.raises(_lib.BarkitError) as e:
@@ -132,6 +128,150 @@ def test_unbounded_repetition_lowers_to_one_parametric_program():
     assert _lib.Program("(?P<UMI>[ACGT]{1,24})gattaca", 1).nvariants() == 24
     # the text the reference would hand to the regex crate keeps its quantifiers (pattern.rs:93-109)
     assert _lib.expand("^(?P<UMI>[ATGCN]+)at", 1) == bo.BarcodePattern("^(?P<UMI>[ATGCN]+)at", 1).get_pattern_with_errors()
+
+
+# ---- the general form: a backtracking program (bk_program.h: bk_vmop) ------------------------------------------------
+
+
+class DumpedVm:
+    """Interpreter of a general-form program's text dump: the statement of what match_vm (bk_kernels.cuh) does."""
+
+    def __init__(self, text):
+        self.code, self.cls, self.caps = [], {}, []
+        for line in text.strip().split("\n"):
+            f = line.split()
+            if f[0] == "anchor":
+                self.a_start = int(f[1])
+            elif f[0] == "total":
+                self.tmin = int(f[1])
+            elif f[0] == "vmclass":
+                self.cls[int(f[1])] = int.from_bytes(bytes.fromhex(f[2]), "little")
+            elif f[0] == "vm":
+                self.code.append((f[2], int(f[3]), int(f[4]), int(f[5]), bytes.fromhex(f[6]) if len(f) > 6 else b""))
+            elif f[0] == "cap":
+                self.caps.append(f[1])
+
+    def inclass(self, c, k):
+        return c < 0x80 and (self.cls[k] >> c) & 1
+
+    def search(self, seq):
+        if len(seq) < self.tmin:
+            return None
+        for s in range((0 if self.a_start else len(seq) - self.tmin) + 1):
+            r = self.run(seq, s)
+            if r is not None:
+                return r
+        return None
+
+    def run(self, seq, s):
+        L, pc, pos, cap, stk = len(seq), 0, s, [-1] * 6, []
+        while True:
+            op, k, a, b, lit = self.code[pc]
+            ok = True
+            if op == "cls":
+                ok = pos + b <= L and all(self.inclass(seq[pos + i], a) for i in range(b))
+                pos += b
+                pc += 1
+            elif op == "lit":
+                ok = pos + b <= L
+                if ok:
+                    bad = [seq[pos + i] for i in range(b) if seq[pos + i] != lit[i]]
+                    ok = len(bad) <= k and not any(c >= 0x80 or c == 10 for c in bad)
+                pos += b
+                pc += 1
+            elif op == "split":
+                stk.append(("b", b, pos))
+                pc = a
+            elif op == "jmp":
+                pc = a
+            elif op == "save":
+                stk.append(("r", a, cap[a]))
+                cap[a] = pos
+                pc += 1
+            elif op == "bol":
+                ok = pos == 0
+                pc += 1
+            elif op == "eol":
+                ok = pos == L
+                pc += 1
+            elif op == "star":
+                pc += 1
+                if k == 0:      # greedy: the whole run, then a byte less per visit
+                    n = 0
+                    while n < b and pos + n < L and self.inclass(seq[pos + n], a):
+                        n += 1
+                    if n:
+                        stk.append(("g", pc, pos + n - 1, n - 1))
+                    pos += n
+                elif b:         # lazy: nothing, then a byte more per visit
+                    stk.append(("l", pc - 1, pos, b))
+            else:
+                return s, pos, cap
+            if ok:
+                continue
+            resumed = False
+            while stk and not resumed:
+                e = stk.pop()
+                if e[0] == "r":
+                    cap[e[1]] = e[2]
+                elif e[0] == "b":
+                    pc, pos, resumed = e[1], e[2], True
+                elif e[0] == "g":
+                    pc, pos, resumed = e[1], e[2], True
+                    if e[3]:
+                        stk.append(("g", e[1], e[2] - 1, e[3] - 1))
+                elif e[2] < L and self.inclass(seq[e[2]], self.code[e[1]][2]):
+                    pc, pos, resumed = e[1] + 1, e[2] + 1, True
+                    if e[3] > 1:
+                        stk.append(("l", e[1], e[2] + 1, e[3] - 1))
+            if not resumed:
+                return None
+
+
+GENERAL = [
+    "^(?P<UMI>([ATGCN])+)", "^(?P<UMI>[ATGCN]{4})+", "^(?P<UMI>[ATGCN]+)(A*C){2}", "^(?P<UMI>[ATGCN]+)a*",
+    "^(?P<UMI>A*C*G*T*N*)", "^((?P<UMI>[ATGCN]{4})A){1,2}", "^(?P<UMI>[ATGCN]{4})?", "(?P<UMI>[ATGCN]{4})^",
+    "((?P<UMI>[ATGCN]{4})){2}", "^(?P<UMI>A)|(?P<CB>C)", "^(A|(?P<UMI>C))T", "^(?P<UMI>[ACGT]+)(A|C)",
+    "^(?P<UMI>[ACGT]{4})(A|C|G|T|N){3}", "(?P<UMI>[ACGT]{4})(AC)+G", "(?P<CB>[ACGT]{3,})(atgc)+(?P<UMI>[ACGT]{2})",
+    "(?P<UMI>A+?)(C|GT)*?T$", "^(?P<CB>[ACGT]{2})((?P<UMI>A[CG])|T)+", "(?P<UMI>[ACGT]{4})(atgc|gatt)+",
+    "^(?P<UMI>(AC|A)+)C", "(?P<UMI>(A|AC)(C|CA)*)T", "(?P<SB>[ACGT]{2})(gattaca){1,}?(?P<UMI>[ACGT]{3})",
+    "(?P<UMI>[ACGT]{3})(acgt){2,}|^(?P<CB>N+)",
+]
+
+
+@pytest.mark.parametrize("pattern", GENERAL)
+def test_general_form_equals_regex(pattern):
+    """What the fixed, variant and parametric forms refuse compiles to a backtracking program; interpreted in Python, it
+    must give the oracle regex's match span and capture spans (a group that took no part in the match: -1, -1)."""
+    rnd = random.Random(zlib.crc32(pattern.encode()))
+    for k in (0, 1):
+        prog = _lib.Program(pattern, k)
+        assert prog.nvariants() == 1 and "vm 0 " in prog.dump(), pattern
+        vm = DumpedVm(prog.dump())
+        rx = bo.BarcodeRegex(pattern, k)
+        assert prog.barcode_types() == rx.get_barcode_types()
+        lits = re.findall(r"[atgcn]{3,}", pattern)
+        matched = 0
+        for _ in range(300):
+            L = rnd.choice([0, 3, 8, 17, 23, 35, 36, 60])
+            alphabet = rnd.choice([b"ACGTACGTACGTN", b"AC", b"ACGT", b"AAAC"])
+            seq = bytearray(rnd.choice(alphabet) for _ in range(L))
+            if lits and L > 30 and rnd.random() < 0.7:
+                lit = bytearray(rnd.choice(lits).upper().encode())
+                for _m in range(rnd.choice([0, 0, 1, 1, 2, 3])):
+                    lit[rnd.randrange(len(lit))] = rnd.choice(b"ACGTN a\r")
+                at = rnd.randrange(0, L - len(lit))
+                seq[at:at + len(lit)] = lit
+            seq = bytes(seq)
+            m = rx.regex.search(seq)
+            r = vm.search(seq)
+            assert (r is None) == (m is None), (pattern, k, seq)
+            if m:
+                matched += 1
+                assert r[:2] == m.span(0), (pattern, k, seq)
+                for c, name in enumerate(vm.caps):
+                    assert (r[2][2 * c], r[2][2 * c + 1]) == m.span(name), (pattern, k, seq, name)
+        assert matched or pattern.endswith("^")
 
 
 # ---- expansion text == oracle on generated patterns ---------------------------------------------

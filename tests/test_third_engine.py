@@ -46,6 +46,12 @@ PATTERNS = [
     ("^(?P<UMI>[ACGT]{3})(A|CG){1,2}?T", [0]),
     ("(?P<UMI>[ACGT]{4})(A?C){3}", [0]),
     ("(?P<SB>[ACGT]{2})(acgt|(TT|GG){1,2})(?P<UMI>[ACGTN]{4})", [1]),
+    # the general form (the CUDA path's backtracking program, tests/test_extract_gpu.py::test_general_form_*)
+    ("^(?P<UMI>[ATGCN]{4})+", [0]), ("^(?P<UMI>[ATGCN]+)(A*C){2}", [0]), ("^((?P<UMI>[ATGCN]{4})A){1,2}", [0]),
+    ("^(?P<UMI>A)|(?P<CB>C)", [0]), ("^(A|(?P<UMI>C))T", [0]), ("(?P<UMI>[ACGT]{4})(AC)+G", [0]),
+    ("(?P<CB>[ACGT]{3,})(atgc)+(?P<UMI>[ACGT]{2})", [0, 1]), ("(?P<UMI>A+?)(C|GT)*?T$", [0]),
+    ("^(?P<CB>[ACGT]{2})((?P<UMI>A[CG])|T)+", [0]), ("^(?P<UMI>(AC|A)+)C", [0]), ("(?P<UMI>(A|AC)(C|CA)*)T", [0]),
+    ("(?P<UMI>[ACGT]{3})(acgt){2,}|^(?P<CB>N+)", [1]),
 ]
 
 _PIECES = ["^", "atgc", "gattaca", "ATGC", "N", "[ATGCN]", "[ACGT]", "{3}", "{2}", "(?P<UMI>[ATGCN]{4})", "(?P<CB>[ACGT]{3})",
