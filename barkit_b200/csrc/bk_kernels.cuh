@@ -1459,6 +1459,7 @@ __device__ __noinline__ int match_vm(uint32_t tab, uint32_t vmc, uint32_t vm_len
   // (a greedy run gives its bytes back one visit at a time even when every state behind them is known: up to a
   // read's length of one-step visits per STAR state)
   uint32_t budget = kVmSteps * vm_len * (L + 1u) + nstates * (L + 1u);
+  uint32_t run_pc = 0xFFFFFFFFu, run_from = 0, run_to = 0;  // the last greedy STAR's run of class bytes: [run_from, run_to)
   uint32_t cap[2 * BK_MAX_CAPS];
   uint32_t vis[kVmVisWords];
   uint2 stk[kVmStack];
@@ -1521,8 +1522,13 @@ __device__ __noinline__ int match_vm(uint32_t tab, uint32_t vmc, uint32_t vm_len
       } else if (op == BK_VM_STAR) {
         ++pc;
         if (k == 0u) {  // greedy: the whole run, then a byte less per visit
-          uint32_t n = 0;
-          while (n < b && pos + n < L && ((lds8(tab + fetch<RC>(tab, seq, L, pos + n)) >> a) & 1u)) ++n;
+          // (an unanchored search arrives here again one byte further on: the run it finds ends where the last did)
+          uint32_t n = run_pc == pc && pos >= run_from && pos <= run_to ? run_to - pos : 0u;
+          if (run_pc != pc || pos < run_from || pos > run_to) {
+            while (pos + n < L && ((lds8(tab + fetch<RC>(tab, seq, L, pos + n)) >> a) & 1u)) ++n;
+            run_pc = pc; run_from = pos; run_to = pos + n;
+          }
+          n = min(n, b);
           if (n) push = make_uint2(kVmStarG << 30 | (n - 1u) << 12 | pc, pos + n - 1u);
           pos += n;
         } else if (b) {  // lazy: nothing, then a byte more per visit
@@ -1557,8 +1563,20 @@ __device__ __noinline__ int match_vm(uint32_t tab, uint32_t vmc, uint32_t vm_len
         if (kind == kVmRestore) { cap[epc] = e.y; continue; }
         if (kind == kVmBranch) { pc = epc; pos = e.y; resumed = true; break; }
         if (kind == kVmStarG) {
-          pc = epc; pos = e.y;
-          if (rem) stk[sp++] = make_uint2(kVmStarG << 30 | (rem - 1u) << 12 | epc, e.y - 1u);  // (the slot just freed)
+          // the lengths left are e.y, e.y - 1 .. e.y - rem; those whose continuation state has been entered before can
+          // only fail again: skip to the longest that has not, a word of visited bits at a time
+          const uint32_t m0 = (lds32(vmc + 8u * epc + 4u) >> 16) - 1u;  // (what follows a STAR is marked)
+          const uint32_t hi = m0 * (L + 1u) + e.y, lo = hi - rem;
+          uint32_t bit = hi, found = 0xFFFFFFFFu;
+          for (;;) {
+            const uint32_t free_bits = ~vis[bit >> 5] & (0xFFFFFFFFu >> (31u - (bit & 31u)));
+            if (free_bits) { found = (bit & ~31u) + 31u - (uint32_t)__clz(free_bits); break; }
+            if ((bit & ~31u) <= lo) break;
+            bit = (bit & ~31u) - 1u;
+          }
+          if (found == 0xFFFFFFFFu || found < lo) continue;  // nothing left of this run
+          pc = epc; pos = e.y - (hi - found);
+          if (found > lo) stk[sp++] = make_uint2(kVmStarG << 30 | (found - lo - 1u) << 12 | epc, pos - 1u);  // (the slot just freed)
           resumed = true;
           break;
         }

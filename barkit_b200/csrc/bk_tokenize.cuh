@@ -92,18 +92,25 @@ __device__ __forceinline__ bool tok_record_ok(const uint8_t* text, uint32_t s, u
   return c0 == '@' && c1 == '+' && sl == ql;
 }
 
-// 16-bit mask of the '\n' bytes of a 16-byte piece
-__device__ __forceinline__ uint32_t tok_mask16(const uint4 v) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t mm = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t x = w[i] ^ 0x0A0A0A0Au;
-    const uint32_t z = (~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u) >> 7;  // 1 in bit 0 of every '\n' byte
-    mm |= ((z * 0x01020408u) >> 24) << (4 * i);  // the four flags gathered into a nibble
-  }
-  return mm;
+// '\n' flags of a word's four bytes in bits 0..3 (junk above): exact zero-byte test of w ^ "\n\n\n\n", then ONE high
+// multiply gathers bits 7, 15, 23, 31 into bits 32..35 of the product (2^25 + 2^18 + 2^11 + 2^4: no two partial products
+// land on the same bit, so nothing carries)
+__device__ __forceinline__ uint32_t tok_nib(uint32_t w) {
+  const uint32_t x = w ^ 0x0A0A0A0Au;
+  const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+  return __umulhi(z, 0x02040810u);
 }
+// the flags of 16 more bytes shifted in at the top of acc (a funnel shift takes the low nibble of every tok_nib)
+__device__ __forceinline__ uint32_t tok_shift16(uint32_t acc, const uint4 v) {
+  acc = __funnelshift_r(acc, tok_nib(v.x), 4);
+  acc = __funnelshift_r(acc, tok_nib(v.y), 4);
+  acc = __funnelshift_r(acc, tok_nib(v.z), 4);
+  return __funnelshift_r(acc, tok_nib(v.w), 4);
+}
+// 16-bit mask of the '\n' bytes of a 16-byte piece
+__device__ __forceinline__ uint32_t tok_mask16(const uint4 v) { return tok_shift16(0u, v) >> 16; }
+
+constexpr int kTokM = 2 * kTokW;  // 32-byte units per thread, one 32-bit newline mask each
 
 __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* text, uint32_t len, uint32_t* rec_off,
                                                                  uint32_t cap_records, unsigned long long* desc,
@@ -116,25 +123,35 @@ __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* t
   __syncthreads();
   const uint32_t bid = s_bid;
   const uint32_t cbase = bid * kTokChunk;           // (< 2^32: the text is)
-  const uint32_t tpos0 = cbase + threadIdx.x * kTokSpan;  // this thread's contiguous bytes, in units of 64
+  const uint32_t tpos0 = cbase + threadIdx.x * kTokSpan;  // this thread's contiguous bytes
   // The text allocation is 16-byte aligned with >= 16 bytes of slack behind len; pieces at or behind len are not read.
-  unsigned long long mw[kTokW];
+  uint32_t mw[kTokM];
   uint32_t mine = 0;
+  if (cbase + kTokChunk <= len) {  // (all chunks but the last: no bounds to look at)
 #pragma unroll
-  for (int u = 0; u < kTokW; ++u) {
-    const uint32_t tpos = tpos0 + 64u * u;
-    unsigned long long m = 0;
-    uint4 v[4];
+    for (int u = 0; u < kTokW; ++u) {
+      uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[j] = make_uint4(0, 0, 0, 0);
-      if (tpos + 16u * j < len) v[j] = *reinterpret_cast<const uint4*>(text + tpos + 16u * j);
+      for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(text + tpos0 + 64u * u + 16u * j);
+      mw[2 * u] = tok_shift16(tok_shift16(0u, v[0]), v[1]);
+      mw[2 * u + 1] = tok_shift16(tok_shift16(0u, v[2]), v[3]);
+      mine += __popc(mw[2 * u]) + __popc(mw[2 * u + 1]);
     }
+  } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) m |= (unsigned long long)tok_mask16(v[j]) << (16 * j);
-    if (tpos + 64u > len) m = tpos >= len ? 0ull : m & ((1ull << (len - tpos)) - 1ull);  // only a piece straddling len needs it
-    mw[u] = m;
-    mine += __popcll(m);
+    for (int u = 0; u < kTokM; ++u) {
+      const uint32_t tpos = tpos0 + 32u * u;
+      uint4 v[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        v[j] = make_uint4(0, 0, 0, 0);
+        if (tpos + 16u * j < len) v[j] = *reinterpret_cast<const uint4*>(text + tpos + 16u * j);
+      }
+      uint32_t m = tok_shift16(tok_shift16(0u, v[0]), v[1]);
+      if (tpos + 32u > len) m = tpos >= len ? 0u : m & ((1u << (len - tpos)) - 1u);  // only a piece straddling len needs it
+      mw[u] = m;
+      mine += __popc(m);
+    }
   }
   uint32_t excl;
   const uint32_t total = tok_block_sum(mine, &excl);
@@ -165,20 +182,20 @@ __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* t
   {
     uint32_t k = excl;
 #pragma unroll
-    for (int u = 0; u < kTokW; ++u)
-      for (unsigned long long mm = mw[u]; mm; mm &= mm - 1ull, ++k)
-        if (k < kTokMaxNl) nlpos[k] = (uint16_t)(threadIdx.x * kTokSpan + 64u * u + (uint32_t)(__ffsll((long long)mm) - 1));
+    for (int u = 0; u < kTokM; ++u)
+      for (uint32_t mm = mw[u]; mm; mm &= mm - 1u, ++k)
+        if (k < kTokMaxNl) nlpos[k] = (uint16_t)(threadIdx.x * kTokSpan + 32u * u + (uint32_t)(__ffs((int)mm) - 1));
   }
   __syncthreads();
   const uint32_t base = s_base;
   uint32_t bad = 0xFFFFFFFFu, longest = 0;
   uint32_t k = excl;
 #pragma unroll
-  for (int u = 0; u < kTokW; ++u)
-  for (unsigned long long mm = mw[u]; mm; mm &= mm - 1ull, ++k) {
+  for (int u = 0; u < kTokM; ++u)
+  for (uint32_t mm = mw[u]; mm; mm &= mm - 1u, ++k) {
     const uint32_t g = base + k;
     if ((g & 3u) != 3u) continue;
-    const uint32_t p4 = tpos0 + 64u * u + (uint32_t)(__ffsll((long long)mm) - 1);
+    const uint32_t p4 = tpos0 + 32u * u + (uint32_t)(__ffs((int)mm) - 1);
     const uint32_t rec = g >> 2;
     if (rec < cap_records) rec_off[rec + 1u] = p4 + 1u;
     if (rec >= cap_records) continue;

@@ -15,6 +15,10 @@ CASES = [  # (label, data config, paired, pattern1, pattern2, k)
     ("PE one pattern, unanchored 3 variants", "C3", True, "(?P<CB>[ATGCN]{14,16})atgccat", None, 1),
     ("PE two anchored patterns", "C4", True, "^(?P<SB>[ATGCN]{8})gtcagtac(?P<UMI>[ATGCN]{12})", "^(?P<CB>[ATGCN]{16})", 1),
     ("PE C4", "C4", True, "^(?P<SB>[ATGCN]{8})gtcagtac(?P<UMI>[ATGCN]{12})", "(?P<CB>[ATGCN]{16})atgccat", 1),
+    # the general form (match_kernel<VM>): no in-kernel variant exists
+    ("PE one pattern, general anchored", "C3", True, "^(?P<CB>[ATGCN]{16})(atgccat)+(?P<UMI>[ATGCN]{12})", None, 1),
+    ("PE one pattern, general unanchored", "C3", True, "(?P<CB>[ATGCN]{14,})(atgccat)+", None, 1),
+    ("PE one pattern, general optional group", "C3", True, "^(?P<CB>[ATGCN]{16})(atgccat|gtcagtac)(?P<UMI>[ATGCN]{12})?", None, 1),
 ]
 only = os.environ.get("BK_ONLY")
 for label, cfgname, paired, p1, p2, k in CASES:
@@ -23,6 +27,8 @@ for label, cfgname, paired, p1, p2, k in CASES:
     forms = [(0, "match_kernel"), (_lib.FLAG_MATCH_IN_KERNEL, "in-kernel")]
     if p2:
         forms.append((_lib.FLAG_SPLIT_TWO_PATTERNS, "split"))
+    if "general" in label:
+        forms = forms[:1]
     for flags, fl in forms:
         rc = label.endswith("-r")
         ctx = _lib.Context(_lib.Program(p1, k), _lib.Program(p2, k) if p2 else None, paired=paired, rc_barcodes=rc,
