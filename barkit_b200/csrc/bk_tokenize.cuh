@@ -66,7 +66,6 @@ __device__ __forceinline__ uint32_t tok_block_sum(uint32_t v, uint32_t* excl) { 
 // first newline in the whole text, and the thread that owns newline g with g % 4 == 3 writes
 // rec_off[g / 4 + 1] and validates record g / 4 -- from the chunk when the record's five newlines lie
 // in it, otherwise (one record per chunk boundary) by walking the text backwards in global memory.
-constexpr uint32_t kTokMaxNl = 4096;  // newline positions kept per chunk (more only in malformed text)
 
 // descriptor words: nblocks + 2 chunk descriptors, then 2 per group of 32 chunks (aggregate / prefix), then 2 per group (accumulators)
 __host__ __device__ inline size_t tok_desc_words(uint32_t nblocks) { return (size_t)nblocks + 2 + 4 * ((size_t)nblocks / 32 + 1); }
@@ -112,10 +111,9 @@ __device__ __forceinline__ uint32_t tok_mask16(const uint4 v) { return tok_shift
 
 constexpr int kTokM = 2 * kTokW;  // 32-byte units per thread, one 32-bit newline mask each
 
-__global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* text, uint32_t len, uint32_t* rec_off,
+__global__ void __launch_bounds__(kTokThreads, 1536 / kTokThreads) tok_fused_kernel(const uint8_t* text, uint32_t len, uint32_t* rec_off,
                                                                  uint32_t cap_records, unsigned long long* desc,
                                                                  unsigned int* ticket, uint32_t nblocks, TokResult* res) {
-  __shared__ uint16_t nlpos[kTokMaxNl];
   __shared__ uint32_t s_bid;
   __shared__ uint32_t s_base;
   const int lane = threadIdx.x & 31;
@@ -125,33 +123,45 @@ __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* t
   const uint32_t cbase = bid * kTokChunk;           // (< 2^32: the text is)
   const uint32_t tpos0 = cbase + threadIdx.x * kTokSpan;  // this thread's contiguous bytes
   // The text allocation is 16-byte aligned with >= 16 bytes of slack behind len; pieces at or behind len are not read.
-  uint32_t mw[kTokM];
-  uint32_t mine = 0;
-  if (cbase + kTokChunk <= len) {  // (all chunks but the last: no bounds to look at)
+  // A thread's 256 contiguous bytes read by that thread alone are 32 different cache lines per load instruction of its
+  // warp, and the L1's tag stage then bounds the kernel (2.9 TB/s).  So a warp reads its threads' 8 KiB together -- lane
+  // l takes the 16-byte piece 32 j + l: 512 contiguous bytes = four lines per instruction --, every lane turns its
+  // piece into 16 newline flags, and the flags change hands through shared memory (2 bytes per piece): thread t then
+  // finds the masks of ITS bytes as 32 contiguous bytes there.
+  __shared__ __align__(16) uint16_t pmask[kTokChunk / 16];
+  constexpr int kPieces = (int)kTokSpan / 16;  // pieces per thread = load instructions per lane
+  const uint32_t wfirst = (uint32_t)(threadIdx.x >> 5) * 32u * kPieces;  // the warp's first piece in the chunk
+  const bool full = cbase + kTokChunk <= len;  // (all chunks but the last: no bounds to look at)
+  if (full) {
 #pragma unroll
-    for (int u = 0; u < kTokW; ++u) {
+    for (int j0 = 0; j0 < kPieces; j0 += 4) {
       uint4 v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(text + tpos0 + 64u * u + 16u * j);
-      mw[2 * u] = tok_shift16(tok_shift16(0u, v[0]), v[1]);
-      mw[2 * u + 1] = tok_shift16(tok_shift16(0u, v[2]), v[3]);
-      mine += __popc(mw[2 * u]) + __popc(mw[2 * u + 1]);
+      for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(text + cbase + 16u * (wfirst + 32u * (j0 + j) + lane));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pmask[wfirst + 32u * (j0 + j) + lane] = (uint16_t)tok_mask16(v[j]);
     }
   } else {
-#pragma unroll
-    for (int u = 0; u < kTokM; ++u) {
-      const uint32_t tpos = tpos0 + 32u * u;
-      uint4 v[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        v[j] = make_uint4(0, 0, 0, 0);
-        if (tpos + 16u * j < len) v[j] = *reinterpret_cast<const uint4*>(text + tpos + 16u * j);
+#pragma unroll 1
+    for (int j = 0; j < kPieces; ++j) {
+      const uint32_t pos = cbase + 16u * (wfirst + 32u * j + lane);
+      uint32_t m = 0;
+      if (pos < len) {
+        m = tok_mask16(*reinterpret_cast<const uint4*>(text + pos));
+        if (pos + 16u > len) m &= (1u << (len - pos)) - 1u;  // only a piece straddling len needs it
       }
-      uint32_t m = tok_shift16(tok_shift16(0u, v[0]), v[1]);
-      if (tpos + 32u > len) m = tpos >= len ? 0u : m & ((1u << (len - tpos)) - 1u);  // only a piece straddling len needs it
-      mw[u] = m;
-      mine += __popc(m);
+      pmask[wfirst + 32u * j + lane] = (uint16_t)m;
     }
+  }
+  __syncwarp();
+  uint32_t mw[kTokM];
+  uint32_t mine = 0;
+  static_assert(kTokM % 4 == 0, "a thread fetches its masks with 16-byte loads");
+#pragma unroll
+  for (int i = 0; i < kTokM / 4; ++i) {
+    const uint4 q = *reinterpret_cast<const uint4*>(&pmask[wfirst + (uint32_t)kPieces * lane + 8u * i]);
+    mw[4 * i] = q.x; mw[4 * i + 1] = q.y; mw[4 * i + 2] = q.z; mw[4 * i + 3] = q.w;
+    mine += __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
   }
   uint32_t excl;
   const uint32_t total = tok_block_sum(mine, &excl);
@@ -178,45 +188,55 @@ __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* t
       if (bid == 0) rec_off[0] = 0;
     }
   }
-  // ---- newline positions of the chunk, record ends --------------------------------------------------------
-  {
-    uint32_t k = excl;
-#pragma unroll
-    for (int u = 0; u < kTokM; ++u)
-      for (uint32_t mm = mw[u]; mm; mm &= mm - 1u, ++k)
-        if (k < kTokMaxNl) nlpos[k] = (uint16_t)(threadIdx.x * kTokSpan + 32u * u + (uint32_t)(__ffs((int)mm) - 1));
-  }
+  // ---- record ends --------------------------------------------------------------------------------------------
+  // The thread's newlines have the numbers base + excl ...; every fourth ends a record.  Such a newline is located in
+  // the thread's masks, and the record's other line ends -- the four newlines in front of it -- by walking the chunk's
+  // masks backwards in shared memory (pmask read as 32-byte words: a 329-byte record is ten of them).  Nothing is kept
+  // per newline.
   __syncthreads();
   const uint32_t base = s_base;
+  const uint32_t* const pm32 = reinterpret_cast<const uint32_t*>(pmask);
   uint32_t bad = 0xFFFFFFFFu, longest = 0;
-  uint32_t k = excl;
+  for (uint32_t i = (3u - (base + excl)) & 3u; i < mine; i += 4u) {
+    // my i-th newline: its word, then its bit
+    uint32_t skip = i, word = 0, uu = 0;
+    bool have = false;
 #pragma unroll
-  for (int u = 0; u < kTokM; ++u)
-  for (uint32_t mm = mw[u]; mm; mm &= mm - 1u, ++k) {
-    const uint32_t g = base + k;
-    if ((g & 3u) != 3u) continue;
-    const uint32_t p4 = tpos0 + 32u * u + (uint32_t)(__ffs((int)mm) - 1);
-    const uint32_t rec = g >> 2;
-    if (rec < cap_records) rec_off[rec + 1u] = p4 + 1u;
-    if (rec >= cap_records) continue;
-    bool ok;
-    uint32_t s;
-    if (k < kTokMaxNl && (k >= 4u || g == 3u)) {  // the whole record lies in this chunk
-      s = g == 3u ? 0u : cbase + nlpos[k - 4u] + 1u;
-      ok = tok_record_ok(text, s, cbase + nlpos[k - 3u], cbase + nlpos[k - 2u], cbase + nlpos[k - 1u], p4);
-    } else if (k < 4u) {
-      continue;  // the record began in an earlier chunk: warp 0 looks at it below
-    } else {  // more newlines in one chunk than nlpos holds (records of a few bytes): walk back bytewise
-      uint32_t q[4] = {0, 0, 0, 0};  // p3, p2, p1, p0
-      int found = 0;
-      uint32_t p = p4;
-      while (p > 0 && found < 4) {
-        --p;
-        if (text[p] == '\n') q[found++] = p;
-      }
-      s = found == 4 ? q[3] + 1u : 0u;
-      ok = found >= 3 && tok_record_ok(text, s, q[2], q[1], q[0], p4);
+    for (int u = 0; u < kTokM; ++u) {
+      const uint32_t c = __popc(mw[u]);
+      if (!have && skip < c) { word = mw[u]; uu = (uint32_t)u; have = true; }
+      if (!have) skip -= c;
     }
+    for (; skip; --skip) word &= word - 1u;
+    const uint32_t bit = (uint32_t)__ffs((int)word) - 1u;
+    uint32_t widx = threadIdx.x * kTokM + uu;  // the word's index in the chunk
+    const uint32_t p4 = cbase + 32u * widx + bit;
+    const uint32_t g = base + excl + i, rec = g >> 2;
+    if (rec >= cap_records) continue;
+    rec_off[rec + 1u] = p4 + 1u;
+    // the four newlines before it, nearest first: q3, q2, q1, q0 (chunk-relative)
+    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0, found = 0;
+    uint32_t w = pm32[widx] & ((1u << bit) - 1u);
+    for (;;) {
+      while (w && found < 4u) {
+        const uint32_t hb = 31u - (uint32_t)__clz(w);
+        q3 = q2; q2 = q1; q1 = q0; q0 = 32u * widx + hb;
+        w &= ~(1u << hb);
+        ++found;
+      }
+      if (found == 4u || widx == 0u) break;
+      w = pm32[--widx];
+    }
+    uint32_t s;
+    if (found == 4u) {
+      s = cbase + q0 + 1u;
+    } else if (g == 3u && found == 3u) {  // the text's first record
+      q3 = q2; q2 = q1; q1 = q0;
+      s = 0u;
+    } else {
+      continue;  // the record began in an earlier chunk: warp 0 looks at it below
+    }
+    const bool ok = tok_record_ok(text, s, cbase + q1, cbase + q2, cbase + q3, p4);
     if (!ok && rec < bad) bad = rec;
     longest = max(longest, p4 + 1u - s);
   }
@@ -227,9 +247,18 @@ __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* t
     const uint32_t kb = (3u - (base & 3u)) & 3u;
     const uint32_t rec = (base + kb) >> 2;
     if (kb < total && rec < cap_records) {  // (warp-uniform)
+      uint32_t first_nl[4];  // the chunk's first kb + 1 newlines (chunk-relative)
+      {
+        uint32_t n = 0, wi = 0, w = pm32[0];
+        while (n <= kb) {
+          while (!w) w = pm32[++wi];  // (total > kb: they exist)
+          first_nl[n++] = 32u * wi + (uint32_t)__ffs((int)w) - 1u;
+          w &= w - 1u;
+        }
+      }
       uint32_t before[4];  // the four newlines before the record's last one, nearest first
       uint32_t found = 0;
-      for (; found < kb; ++found) before[found] = cbase + nlpos[kb - 1u - found];
+      for (; found < kb; ++found) before[found] = cbase + first_nl[kb - 1u - found];
       uint32_t wend = cbase;
       while (found < 4u && wend > 0) {
         const uint32_t wstart = wend >= 512u ? wend - 512u : 0u;  // cbase is a multiple of 512
@@ -247,7 +276,7 @@ __global__ void __launch_bounds__(kTokThreads) tok_fused_kernel(const uint8_t* t
         wend = wstart;
       }
       if (lane == 0) {
-        const uint32_t p4 = cbase + nlpos[kb];
+        const uint32_t p4 = cbase + first_nl[kb];
         const uint32_t s = found == 4u ? before[3] + 1u : 0u;
         const bool ok = found == 4u && tok_record_ok(text, s, before[2], before[1], before[0], p4);
         if (!ok && rec < bad) bad = rec;
