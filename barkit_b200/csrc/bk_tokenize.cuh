@@ -3,7 +3,7 @@
 // batch can be shipped as raw text and the host tokenizer (bk_fastq.cc, same contract) drops out of
 // the end-to-end path.  A record is four lines; its start is the byte after every fourth newline.
 //
-// One pass over the text (tok_fused_kernel): newlines per 16 KiB chunk (SWAR zero-byte test), their
+// One pass over the text (tok_fused_kernel): newlines per 64 KiB chunk (SWAR zero-byte test), their
 // numbers in the whole text by a decoupled look-back over the chunks, rec_off[g / 4 + 1] = position + 1
 // of every newline g with g % 4 == 3, and the record checks -- '@' and '+' line starts, seq / qual
 // lengths equal after CR stripping (the conditions bk_tokenize reports as BK_E_FORMAT), longest record.
@@ -17,7 +17,7 @@
 namespace bk {
 
 #ifndef BK_TOK_THREADS
-#define BK_TOK_THREADS 128
+#define BK_TOK_THREADS 256
 #endif
 #ifndef BK_TOK_W
 #define BK_TOK_W 4
@@ -58,14 +58,18 @@ __device__ __forceinline__ uint32_t tok_block_sum(uint32_t v, uint32_t* excl) { 
 
 // ---- single pass: count + scan + emit + check ---------------------------------------------------------
 //
-// One CTA per 32 KiB of text (128 threads x 256 contiguous bytes: the per-thread scan and hand-over costs are paid per
-// thread, not per byte -- 512 threads x 64 bytes ran at 2.06 TB/s, this at 2.9), taken in ticket order.  The chunk is read once (16-byte
-// loads, kept in shared memory), every thread turns its 64 contiguous bytes into a newline mask, a
-// block scan numbers the chunk's newlines, a decoupled look-back over the earlier chunks' counts
-// (one 8-byte descriptor per chunk: aggregate, then inclusive prefix) gives the number of the chunk's
-// first newline in the whole text, and the thread that owns newline g with g % 4 == 3 writes
-// rec_off[g / 4 + 1] and validates record g / 4 -- from the chunk when the record's five newlines lie
-// in it, otherwise (one record per chunk boundary) by walking the text backwards in global memory.
+// One CTA per 64 KiB of text (256 threads x 256 contiguous bytes each: the block scan, the look-back hand-over and the
+// record logic are paid per thread and per chunk, not per byte), taken in ticket order.  The chunk is read once: a warp
+// reads its threads' 8 KiB with coalesced 16-byte loads, every lane turns its piece into 16 newline flags, and the
+// flags change hands through shared memory so that every thread holds the masks of ITS 256 bytes; a block scan numbers
+// the chunk's newlines, a decoupled look-back over the earlier chunks' counts (one 8-byte descriptor per chunk:
+// aggregate, then inclusive prefix) gives the number of the chunk's first newline in the whole text, and the thread
+// that owns newline g with g % 4 == 3 writes rec_off[g / 4 + 1] and validates record g / 4 -- its other line ends are
+// found by walking the chunk's masks backwards in shared memory; the one record per chunk that began in an earlier
+// chunk is checked by warp 0 from global memory.
+// Geometry measured on 10 M records of 329 bytes (tools/ab.sh, wall time around bk_tokenize_device): 128 threads 3.57,
+// 256 threads 3.83, 512 threads 3.86-3.92, 1024 threads 2.98 TB/s; 512 bytes per thread 3.03; 8 / 16 loads in flight
+// per lane instead of 4: 3.52-3.69 / 3.26.  256 threads keeps 512 chunks in a 32 MiB batch of the file runtime.
 
 // descriptor words: nblocks + 2 chunk descriptors, then 2 per group of 32 chunks (aggregate / prefix), then 2 per group (accumulators)
 __host__ __device__ inline size_t tok_desc_words(uint32_t nblocks) { return (size_t)nblocks + 2 + 4 * ((size_t)nblocks / 32 + 1); }
@@ -110,8 +114,15 @@ __device__ __forceinline__ uint32_t tok_shift16(uint32_t acc, const uint4 v) {
 __device__ __forceinline__ uint32_t tok_mask16(const uint4 v) { return tok_shift16(0u, v) >> 16; }
 
 constexpr int kTokM = 2 * kTokW;  // 32-byte units per thread, one 32-bit newline mask each
+#ifndef BK_TOK_INFLIGHT
+#define BK_TOK_INFLIGHT 4
+#endif
+#ifndef BK_TOK_MINBLOCKS
+#define BK_TOK_MINBLOCKS (1536 / BK_TOK_THREADS)
+#endif
+constexpr int kTokInflight = BK_TOK_INFLIGHT;  // 16-byte loads a lane has in flight
 
-__global__ void __launch_bounds__(kTokThreads, 1536 / kTokThreads) tok_fused_kernel(const uint8_t* text, uint32_t len, uint32_t* rec_off,
+__global__ void __launch_bounds__(kTokThreads, BK_TOK_MINBLOCKS) tok_fused_kernel(const uint8_t* text, uint32_t len, uint32_t* rec_off,
                                                                  uint32_t cap_records, unsigned long long* desc,
                                                                  unsigned int* ticket, uint32_t nblocks, TokResult* res) {
   __shared__ uint32_t s_bid;
@@ -134,12 +145,12 @@ __global__ void __launch_bounds__(kTokThreads, 1536 / kTokThreads) tok_fused_ker
   const bool full = cbase + kTokChunk <= len;  // (all chunks but the last: no bounds to look at)
   if (full) {
 #pragma unroll
-    for (int j0 = 0; j0 < kPieces; j0 += 4) {
-      uint4 v[4];
+    for (int j0 = 0; j0 < kPieces; j0 += kTokInflight) {
+      uint4 v[kTokInflight];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(text + cbase + 16u * (wfirst + 32u * (j0 + j) + lane));
+      for (int j = 0; j < kTokInflight; ++j) v[j] = *reinterpret_cast<const uint4*>(text + cbase + 16u * (wfirst + 32u * (j0 + j) + lane));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pmask[wfirst + 32u * (j0 + j) + lane] = (uint16_t)tok_mask16(v[j]);
+      for (int j = 0; j < kTokInflight; ++j) pmask[wfirst + 32u * (j0 + j) + lane] = (uint16_t)tok_mask16(v[j]);
     }
   } else {
 #pragma unroll 1
