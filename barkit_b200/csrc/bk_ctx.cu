@@ -1320,11 +1320,14 @@ int bk_tokenize_device(bk_ctx* ctx, const uint8_t* d_text, uint64_t len, int fin
   uint64_t n = r.newlines / 4;
   bool truncated = false;  // bytes behind the last complete record that do not make up a record
   uint32_t last_end = 0;
-  bool have_last_end = false;
+  bool have_last_end = false, have_after = false;
+  uint32_t after_n = 0;  // rec_off[n] as the single pass left it
   if (n < cap_records) {
     uint32_t after = 0;  // end of the last record that ends with a newline
     CK(cudaMemcpyAsync(&after, d_rec_off + n, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    after_n = after;
+    have_after = true;
     if (after < eff) {
       if (final_chunk && r.newlines % 4 == 3) {  // the final record's quality line has no EOL
         ++n;
@@ -1338,7 +1341,9 @@ int bk_tokenize_device(bk_ctx* ctx, const uint8_t* d_text, uint64_t len, int fin
   } else {
     n = cap_records;
   }
-  if (!have_last_end) {
+  if (!have_last_end && have_after) {
+    last_end = after_n;  // (read above)
+  } else if (!have_last_end) {
     CK(cudaMemcpyAsync(&last_end, d_rec_off + n, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }

@@ -58,6 +58,8 @@ OTHER_CONFIGS = {
     # SURVEY.md section 8f-2 (not BASELINE configs): variable repetition on C3's data, pattern on R1 only
     "F2_unanchored_3_variants": ("(?P<CB>[ATGCN]{14,16})atgccat", None, True, (b"ATGCCAT", 16, 0), None),
     "F2_unbounded_greedy": ("^(?P<CB>[ATGCN]{14,})atgccat(?P<UMI>[ATGCN]{12})", None, True, (b"ATGCCAT", 16, 0), None),
+    # the general form (a repeated lowercase run: a backtracking program run by match_kernel<VM>)
+    "F2_general_repeated_run": ("^(?P<CB>[ATGCN]{16})(atgccat)+(?P<UMI>[ATGCN]{12})", None, True, (b"ATGCCAT", 16, 0), None),
 }
 F2_KERNELS = ("bk::match_kernel on the pattern's mate + bk::extract_kernel<PAIRED=false, VAR=true, TABLE=true> on it + "
               "bk::compact_kernel on the other")
@@ -301,7 +303,8 @@ def other_configs(_lib, units, peak):
     `units` resident units each (fresh input per launch is >> L2)."""
     import numpy as np
     out = {}
-    for name, ks in (("C1", (1,)), ("C2", (1,)), ("C4", (0, 1, 2)), ("F2_unanchored_3_variants", (1,)), ("F2_unbounded_greedy", (1,))):
+    for name, ks in (("C1", (1,)), ("C2", (1,)), ("C4", (0, 1, 2)), ("F2_unanchored_3_variants", (1,)), ("F2_unbounded_greedy", (1,)),
+                     ("F2_general_repeated_run", (1,))):
         p1, p2, paired, plant1, plant2 = OTHER_CONFIGS[name]
         cfg = _lib.syn_config(READ_LEN, plant1=plant1, plant2=plant2)
         for k in ks:
