@@ -6,7 +6,11 @@
 namespace bk {
 
 constexpr int kStages = 4;  // input ring depth per mate (the loader runs at most this far ahead)
-constexpr int kBackWarps = kEmitParts;  // back warps per mate: warp j writes part j of every record (emit_part)
+constexpr int kBackWarps = kEmitParts;  // back warps per mate of a paired launch: warp j writes part j of every record (emit_part)
+// ... and of a single-end launch.  4: A+B | C | D | E.  6 or 7: the seq and the qual line are written by two warps each
+// (the two long jobs were the back stage's critical path: the slot of a tile is held until its slowest part is done).
+static_assert(BK_SE_BACKS == 4 || BK_SE_BACKS == 5 || BK_SE_BACKS == 6 || BK_SE_BACKS == 7, "emit_part knows 3, 4, 5, 6 or 7 parts");
+__host__ __device__ constexpr int back_warps(bool paired) { return paired ? kBackWarps : BK_SE_BACKS; }
 
 // ---- ordered compaction: two-level decoupled look-back ---------------------------------------------------
 //
@@ -190,7 +194,7 @@ __host__ __device__ constexpr int front_pairs(bool paired) { return paired ? 2 :
 // A ring slot's barriers must always meet the same scan warp and front pair.  With an odd ring depth
 // round k and round k + kStages share their barrier ids but belong to different scan warps, and the
 // one running ahead completes the other's barrier generation (observed: a 3-deep ring hangs).
-__host__ __device__ constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (front_pairs(paired) + kBackWarps) + kScanWarps + 1; }
+__host__ __device__ constexpr int cta_warps(bool paired) { return (paired ? 2 : 1) * (front_pairs(paired) + back_warps(paired)) + kScanWarps + 1; }
 
 // GENERAL = false: every pattern is anchored and there is no reverse-complement retry -- the common
 // case, compiled without the search code, because every kilobyte of this kernel competes for the
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   // Warp roles, lowest warp ids first: back, scan, front, loader.
-  constexpr int NB = NM * kBackWarps;
+  constexpr int NB = NM * back_warps(PAIRED);
   const bool is_back = warp < NB;
   const bool is_scan = !is_back && warp < NB + kScanWarps;
   const bool is_front = !is_back && !is_scan && warp < NB + kScanWarps + NM * kFrontPairs;
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
   const int fw = warp - NB - kScanWarps;  // front warp index
   // Back warps per mate: four each, or five and three when only one mate's reads are rewritten (its
   // records cost more to assemble than the other mate's verbatim copies).
-  const uint32_t nb0 = !PAIRED ? kBackWarps
+  const uint32_t nb0 = !PAIRED ? back_warps(false)
                        : (P.prog[0].present && !P.prog[1].present) ? kBackWarps + 1
                        : (!P.prog[0].present && P.prog[1].present) ? kBackWarps - 1 : kBackWarps;
   const int m = is_back ? (warp < (int)nb0 ? 0 : 1) : is_front ? fw % NM : 0;  // mate = output stream
@@ -522,7 +526,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       if (tile == kEndTile2) break;
       if (tile != kEndTile) {
         EVT(tile, 8)
+#ifdef BK_EXP_NOLB  // experiment: what the kernel does without the look-back (output offsets wrong, timing only)
+        const ulonglong2 g = make_ulonglong2((unsigned long long)tile * R * 400ull, (unsigned long long)tile * R * 400ull);
+#else
         const ulonglong2 g = lookback<PAIRED>(P.desc[0], P.desc[1], tile, meta[0][s].total, PAIRED ? meta[NM - 1][s].total : 0u, lane);
+#endif
         if (lane == 0) {
           meta[0][s].gout = g.x;
           if (PAIRED) meta[NM - 1][s].gout = g.y;
@@ -583,7 +591,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
             const EmitProg ep = emit_prog(pg, ms >= 0 ? P.xtab[m][tile * R + lane] : make_uint4(0, 0, 0, 0));
             emit_part(ep, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
           }
-        } else if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
+        }
+#ifndef BK_EXP_NOEMIT  // experiment: the kernel without the assembly of rewritten records (timing only)
+        else if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
+#endif
         // warp per pass: maximal runs of consecutive unchanged records
         const unsigned um = __ballot_sync(0xffffffffu, unc);
         if (um) {

@@ -1164,6 +1164,10 @@ __device__ __forceinline__ void bulk16(const uint4 r, int lane, uint32_t t0, uin
 }
 
 constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is written by warp j
+#ifndef BK_SE_BACKS
+#define BK_SE_BACKS 4  // back warps of a single-end launch (bk_extract.cuh)
+#endif
+constexpr bool kSplitLines = BK_SE_BACKS >= 6;  // six or seven parts: the seq and the qual line are two parts each
 
 // Part `part` of `nparts` (3, 4 or 5) of one record's output at shared address d.  The record is
 //   '@' head { " NAME:" seq[cap] ":" qual[cap] }* "\n" seq[..s0) seq[e0..] "\n+\n" qual[..s0) qual[e0..] "\n"
@@ -1183,7 +1187,13 @@ __device__ __forceinline__ void emit_part(const PG& pg, const RecView& r, int ms
                                           uint32_t part, uint32_t nparts, uint32_t rot) {
   OutStream o;
   // jobs of this part, bit 0 = A ... bit 4 = E
-  const uint32_t jobs = nparts == 5 ? 1u << part : nparts == 4 ? (part == 0 ? 3u : 2u << part) : (part == 0 ? 5u : 4u << part);
+  // (six or seven parts: the seq and the qual line are two parts each, `half` = 1 / 2)
+  const uint32_t jobs = nparts == 7 ? (part < 3u ? 1u << part : part < 5u ? 8u : 16u)
+                        : nparts == 6 ? (part == 0 ? 3u : part == 1 ? 4u : part < 4u ? 8u : 16u)
+                        : nparts == 5 ? 1u << part : nparts == 4 ? (part == 0 ? 3u : 2u << part) : (part == 0 ? 5u : 4u << part);
+  // (compiled in only when the build asks for that many back warps, BK_SE_BACKS in bk_extract.cuh: the default build's
+  // hot code stays as it was)
+  const uint32_t half = !kSplitLines ? 0u : nparts == 7 ? (part >= 3u ? ((part - 3u) & 1u) + 1u : 0u) : nparts == 6 ? (part >= 2u ? (part & 1u) + 1u : 0u) : 0u;
   const uint32_t ncaps = ms >= 0 ? pg.ncaps : 0u;
   const uint32_t csplit = (ncaps + 1u) >> 1;
   const uint32_t H = r.head_len, L = r.seq_len;
@@ -1227,15 +1237,41 @@ __device__ __forceinline__ void emit_part(const PG& pg, const RecView& r, int ms
   const uint32_t sep = isD ? (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16) : (uint32_t)'\n';
   const uint32_t nsep = isD ? 3u : 1u;
   const uint32_t dpos = d + 2u + H + G + (isD ? 0u : L - (ce - cs) + 3u);
+  // the line end ("\n+\n" after seq, "\n" after qual) travels with the run behind the cut when the framing has it there
+  const uint32_t tl = ll - pe + (r.fast ? nsep : 0u);
+  if (half) {
+    // Two warps per line: the longer of the two runs (in front of the cut / behind it) is split near its middle, at a
+    // multiple of 16 bytes from its start; the halves meet at an arbitrary byte of the output, like any two parts.
+    const bool in_tail = tl >= ps;
+    const uint32_t n1 = ((in_tail ? tl : ps) >> 1) & ~15u;
+    if (half == 1u) {
+      os_begin(o, dpos);
+      o.rot = rot;
+      if (in_tail) {
+        if (ps) os_run(o, src, ps);
+        if (n1) os_run(o, src + pe, n1);
+      } else if (n1) {
+        os_run(o, src, n1);
+      }
+    } else {
+      os_begin(o, dpos + (in_tail ? ps + n1 : n1));
+      o.rot = rot;
+      if (in_tail) {
+        if (tl > n1) os_run(o, src + pe + n1, tl - n1);
+      } else {
+        os_run(o, src + n1, ps - n1);
+        if (tl) os_run(o, src + pe, tl);
+      }
+      if (!r.fast) os_put(o, sep, nsep);
+    }
+    os_end(o);
+    return;
+  }
   os_begin(o, dpos);
   o.rot = rot;
   if (ps) os_run(o, src, ps);
-  if (r.fast) {
-    os_run(o, src + pe, ll - pe + nsep);  // the line end ("\n+\n" after seq, "\n" after qual) travels with the run
-  } else {
-    if (ll > pe) os_run(o, src + pe, ll - pe);
-    os_put(o, sep, nsep);
-  }
+  if (tl) os_run(o, src + pe, tl);
+  if (!r.fast) os_put(o, sep, nsep);
   os_end(o);
 }
 
