@@ -589,11 +589,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         if (VAR && TABLE && bk_free_shape(pg)) {
           if (kept && !unc) {
             const EmitProg ep = emit_prog(pg, ms >= 0 ? P.xtab[m][tile * R + lane] : make_uint4(0, 0, 0, 0));
-            emit_part(ep, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
+            emit_part(ep, rv, ms, trim, dst, (uint32_t)bj, nparts, rot, kEmitCp && !PAIRED);
           }
         }
 #ifndef BK_EXP_NOEMIT  // experiment: the kernel without the assembly of rewritten records (timing only)
-        else if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot);
+        else if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot, kEmitCp && !PAIRED);
 #endif
         // warp per pass: maximal runs of consecutive unchanged records
         const unsigned um = __ballot_sync(0xffffffffu, unc);

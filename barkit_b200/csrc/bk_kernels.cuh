@@ -1163,6 +1163,95 @@ __device__ __forceinline__ void bulk16(const uint4 r, int lane, uint32_t t0, uin
   }
 }
 
+// ---- stand-alone run copy ------------------------------------------------------------------------------------------
+//
+// Every field of a rewritten record has a destination that is a closed form of the record's header length, read
+// length and the program's constants (emit_part), so a field does not have to travel through the stream writer: it
+// can be copied on its own.  cp_run copies [s, s + n) to [d, d + n), n >= 1, shared addresses at any alignment, and
+// writes exactly those bytes (the words at both ends may belong to other writers as well): up to three bytes bring the
+// destination to a word boundary, whole words follow -- 16 bytes per step, each word an aligned load and a funnel
+// shift by the source's misalignment -- and up to three bytes end the run.  Against os_run_f this leaves out the two
+// os_chunk passes (60-65 instructions each) at the ends of every run.  Reads up to 19 bytes past the run: inside the
+// staged tile or the buffer behind it, never used.
+// Used by the single-end launches (`cp` of emit_part).  Measured on one box, 10 M units, two builds each way
+// (BK_DEFINES="BK_EMIT_CP=0" is the stream writer everywhere): C1 1.657 / 1.647 -> 1.630 / 1.644 ms, C3 2.857 / 2.844 ->
+// 2.809 / 2.811 ms, C2 2.897 / 2.889 -> 2.898 / 2.872 ms.  In the paired kernels (C4 4.849 -> 4.886 ms) both writers would
+// be hot at once -- unchanged records' ragged ends go through the stream writer -- which costs more instruction-cache
+// misses than the shorter path saves, so those keep the stream writer alone.
+#ifndef BK_EMIT_CP
+#define BK_EMIT_CP 1
+#endif
+constexpr bool kEmitCp = BK_EMIT_CP != 0;
+// `rot` (0, or 1 + a step): the 16-byte steps of a long run are taken from that one on, wrapping round -- lanes whose
+// runs sit a multiple of 32 bytes apart then work on different banks (see os_run_f).
+__device__ __noinline__ void cp_run(uint32_t d, uint32_t s, uint32_t n, uint32_t rot = 0u) {
+  {
+    const uint32_t h0 = (0u - d) & 3u;
+    const uint32_t h = h0 < n ? h0 : n;
+    const uint32_t sp = s & ~3u;
+    const uint32_t v = __funnelshift_r(lds32(sp), lds32(sp + 4u), (s & 3u) * 8u);  // source bytes 0..3
+    if (h > 0u) sts8(d, v);
+    if (h > 1u) sts8(d + 1u, v >> 8);
+    if (h > 2u) sts8(d + 2u, v >> 16);
+    d += h;
+    s += h;
+    n -= h;
+  }
+  uint32_t sp = s & ~3u;
+  const uint32_t sh = (s & 3u) * 8u;
+  uint32_t prev = lds32(sp);
+  uint32_t nw = n >> 2;
+  if (rot != 0u && nw >= 8u) {  // each step reads the source word before it instead of carrying it over: any order will do
+    const uint32_t nsteps = nw >> 2;
+    uint32_t q = rot - 1u < nsteps ? rot - 1u : 0u;
+#pragma unroll 1
+    for (uint32_t it = 0; it < nsteps; ++it) {
+      const uint32_t x = sp + 16u * q, y = d + 16u * q;
+      const uint32_t wm = lds32(x), a = lds32(x + 4u), b = lds32(x + 8u), c = lds32(x + 12u), e = lds32(x + 16u);
+      sts32(y, __funnelshift_r(wm, a, sh));
+      sts32(y + 4u, __funnelshift_r(a, b, sh));
+      sts32(y + 8u, __funnelshift_r(b, c, sh));
+      sts32(y + 12u, __funnelshift_r(c, e, sh));
+      q = q + 1u == nsteps ? 0u : q + 1u;
+    }
+    sp += 16u * nsteps;
+    d += 16u * nsteps;
+    nw -= 4u * nsteps;
+    prev = lds32(sp);
+  }
+#pragma unroll 1
+  for (; nw >= 4u; nw -= 4u) {
+    const uint32_t a = lds32(sp + 4u), b = lds32(sp + 8u), c = lds32(sp + 12u), e = lds32(sp + 16u);
+    sts32(d, __funnelshift_r(prev, a, sh));
+    sts32(d + 4u, __funnelshift_r(a, b, sh));
+    sts32(d + 8u, __funnelshift_r(b, c, sh));
+    sts32(d + 12u, __funnelshift_r(c, e, sh));
+    prev = e;
+    sp += 16u;
+    d += 16u;
+  }
+  // the last 0..3 words and 0..3 bytes
+  const uint32_t a = lds32(sp + 4u), b = lds32(sp + 8u), c = lds32(sp + 12u), e = lds32(sp + 16u);
+  const uint32_t v0 = __funnelshift_r(prev, a, sh), v1 = __funnelshift_r(a, b, sh), v2 = __funnelshift_r(b, c, sh),
+                 v3 = __funnelshift_r(c, e, sh);
+  if (nw > 0u) sts32(d, v0);
+  if (nw > 1u) sts32(d + 4u, v1);
+  if (nw > 2u) sts32(d + 8u, v2);
+  const uint32_t t = nw == 0u ? v0 : nw == 1u ? v1 : nw == 2u ? v2 : v3;
+  d += 4u * nw;
+  const uint32_t r = n & 3u;
+  if (r > 0u) sts8(d, t);
+  if (r > 1u) sts8(d + 1u, t >> 8);
+  if (r > 2u) sts8(d + 2u, t >> 16);
+}
+// the n (1..4) low bytes of v at any address
+__device__ __forceinline__ void put_bytes(uint32_t d, uint32_t v, uint32_t n) {
+  sts8(d, v);
+  if (n > 1u) sts8(d + 1u, v >> 8);
+  if (n > 2u) sts8(d + 2u, v >> 16);
+  if (n > 3u) sts8(d + 3u, v >> 24);
+}
+
 constexpr int kEmitParts = 4;  // back warps per mate; part j of every record is written by warp j
 #ifndef BK_SE_BACKS
 #define BK_SE_BACKS 4  // back warps of a single-end launch (bk_extract.cuh)
@@ -1184,7 +1273,7 @@ constexpr bool kSplitLines = BK_SE_BACKS >= 6;  // six or seven parts: the seq a
 // (the front warp treats anything else as unmatched; bk_tokenize never produces it).
 template <class PG>
 __device__ __forceinline__ void emit_part(const PG& pg, const RecView& r, int ms, bool trim, uint32_t d,
-                                          uint32_t part, uint32_t nparts, uint32_t rot) {
+                                          uint32_t part, uint32_t nparts, uint32_t rot, bool cp = false) {
   OutStream o;
   // jobs of this part, bit 0 = A ... bit 4 = E
   // (six or seven parts: the seq and the qual line are two parts each, `half` = 1 / 2)
@@ -1204,6 +1293,29 @@ __device__ __forceinline__ void emit_part(const PG& pg, const RecView& r, int ms
     if (!(jobs & 3u)) {
 #pragma unroll 1
       for (uint32_t c = 0; c < c0; ++c) off += 3u + pg.caps[c].name_len + 2u * pg.caps[c].len;
+    }
+    if (cp) {  // every field copied on its own (cp_run)
+      uint32_t pos = d + ((jobs & 1u) ? 0u : off);
+      if (jobs & 1u) {
+        cp_run(pos, r.beg, 1u + H);  // '@' + head
+        pos += 1u + H;
+      }
+#pragma unroll 1
+      for (uint32_t c = c0; c < c1; ++c) {  // pattern order (parse.rs:101)
+        const bk_cap cap = pg.caps[c];
+        const uint32_t b3 = cap.name_len == 3 ? (uint32_t)(uint8_t)cap.name[2] : (uint32_t)':';
+        put_bytes(pos, (uint32_t)' ' | ((uint32_t)(uint8_t)cap.name[0] << 8) | ((uint32_t)(uint8_t)cap.name[1] << 16) | (b3 << 24), 4u);
+        if (cap.name_len == 3) sts8(pos + 4u, (uint32_t)':');  // " NAME:"  (parse.rs:166); names are 2 or 3 bytes
+        pos += 2u + cap.name_len;
+        if (cap.len) cp_run(pos, r.seq + ms + cap.off, cap.len);
+        pos += cap.len;
+        sts8(pos, (uint32_t)':');
+        pos += 1u;
+        if (cap.len) cp_run(pos, r.qual + ms + cap.off, cap.len);
+        pos += cap.len;
+      }
+      if (jobs & 4u) sts8(pos, (uint32_t)'\n');
+      return;
     }
     if (jobs & 1u) {
       os_begin(o, d);
@@ -1265,6 +1377,12 @@ __device__ __forceinline__ void emit_part(const PG& pg, const RecView& r, int ms
       if (!r.fast) os_put(o, sep, nsep);
     }
     os_end(o);
+    return;
+  }
+  if (cp) {
+    if (ps) cp_run(dpos, src, ps, rot);
+    if (tl) cp_run(dpos + ps, src + pe, tl, rot);
+    if (!r.fast) put_bytes(dpos + ps + tl, sep, nsep);
     return;
   }
   os_begin(o, dpos);

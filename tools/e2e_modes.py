@@ -1,5 +1,7 @@
 """End-to-end rate of bk_submit / bk_wait (offsets from the host) against bk_submit_text (raw text, device tokenizer), both
-mates over the bus, pinned host buffers, two slots in flight.   python tools/e2e_modes.py [pairs per step] [steps]"""
+mates over the bus, pinned host buffers, two slots in flight.   python tools/e2e_modes.py [pairs per step] [steps]
+BK_E2E_FLAGS=<int> replaces the context flags (0: the library's default, the pattern-less mate assembled on the host);
+BK_DEBUG=1 adds the library's per-batch timing lines."""
 import ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from barkit_b200 import _lib
@@ -8,7 +10,7 @@ Q = int(sys.argv[1]) if len(sys.argv) > 1 else 2000000
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 rl = 329; nb = Q * rl
 p1 = CONFIG_PATTERNS["C3"][0]
-ctx = _lib.Context(_lib.Program(p1, 1), None, paired=True, extra_flags=_lib.FLAG_DEVICE_BOTH_MATES | (_lib.FLAG_VERBOSE if os.environ.get("BK_DEBUG") else 0))
+ctx = _lib.Context(_lib.Program(p1, 1), None, paired=True, extra_flags=int(os.environ.get("BK_E2E_FLAGS", _lib.FLAG_DEVICE_BOTH_MATES)) | (_lib.FLAG_VERBOSE if os.environ.get("BK_DEBUG") else 0))
 h = {}
 for name, size in (("t1", nb + 64), ("t2", nb + 64), ("off", (Q + 1) * 4), ("o1a", ctx.out_bound(1, Q, nb)), ("o2a", ctx.out_bound(2, Q, nb)),
                    ("o1b", ctx.out_bound(1, Q, nb)), ("o2b", ctx.out_bound(2, Q, nb))):
