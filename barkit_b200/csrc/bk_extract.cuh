@@ -589,11 +589,11 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         if (VAR && TABLE && bk_free_shape(pg)) {
           if (kept && !unc) {
             const EmitProg ep = emit_prog(pg, ms >= 0 ? P.xtab[m][tile * R + lane] : make_uint4(0, 0, 0, 0));
-            emit_part(ep, rv, ms, trim, dst, (uint32_t)bj, nparts, rot, kEmitCp && !PAIRED);
+            emit_part(ep, rv, ms, trim, dst, (uint32_t)bj, nparts, rot, kEmitCp && (!PAIRED || BK_EMIT_CP > 1));
           }
         }
 #ifndef BK_EXP_NOEMIT  // experiment: the kernel without the assembly of rewritten records (timing only)
-        else if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot, kEmitCp && !PAIRED);
+        else if (kept && !unc) emit_part(pe, rv, ms, trim, dst, (uint32_t)bj, nparts, rot, kEmitCp && (!PAIRED || BK_EMIT_CP > 1));
 #endif
         // warp per pass: maximal runs of consecutive unchanged records
         const unsigned um = __ballot_sync(0xffffffffu, unc);
@@ -617,10 +617,14 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
             const uint32_t tlo = (int32_t)t0 > (int32_t)pad ? t0 : pad;
             const bool head = bj == 0 && first && pad, tail = bj == 1 && i1 == lane && tlo < run_n;
             if (head || tail) {
-              OutStream o;
-              os_begin(o, head ? run_d : run_d + tlo);
-              os_run(o, head ? run_s : run_s + tlo, head ? pad : run_n - tlo);
-              os_end(o);
+              if (kEmitCp) {
+                cp_run(head ? run_d : run_d + tlo, head ? run_s : run_s + tlo, head ? pad : run_n - tlo);
+              } else {
+                OutStream o;
+                os_begin(o, head ? run_d : run_d + tlo);
+                os_run(o, head ? run_s : run_s + tlo, head ? pad : run_n - tlo);
+                os_end(o);
+              }
             }
           }
           __syncwarp();

@@ -420,6 +420,10 @@ __device__ __forceinline__ uint32_t fetch(uint32_t tab, uint32_t seq, uint32_t L
 // pattern.rs:40-79), a class run looks its bytes up in `tab`.  A mismatching byte sits in a
 // wildcard slot of one of the alternatives, i.e. under the regex `.`, which must be ASCII here
 // ('\n' cannot occur inside a line).
+#ifndef BK_MATCH_UNROLL
+#define BK_MATCH_UNROLL 1
+#endif
+constexpr int kMatchUnroll = BK_MATCH_UNROLL;  // words of a compare run per turn of the matcher's loops
 template <bool EARLY_OUT>
 __device__ __forceinline__ bool match_at_fwd(uint32_t tab, uint32_t seq, uint32_t s) {
   bool ok = true;
@@ -434,7 +438,7 @@ __device__ __forceinline__ bool match_at_fwd(uint32_t tab, uint32_t seq, uint32_
     if (op.kind == BK_OP_LIT) {
       uint32_t mism = 0, bad = 0;
       const uint32_t lit = tab + kTabLit + op.idx;  // literals start on words (bk_pattern.cc)
-#pragma unroll 1
+#pragma unroll kMatchUnroll
       for (uint32_t i = 0; i < nw; ++i) {
         const uint32_t nxt = lds32(p + 4u * i + 4u);
         const uint32_t v = __funnelshift_r(prev, nxt, sh);
@@ -448,7 +452,7 @@ __device__ __forceinline__ bool match_at_fwd(uint32_t tab, uint32_t seq, uint32_
       ok = ok && (mism <= op.k) && !bad;
     } else {
       uint32_t acc = 0xFFu;
-#pragma unroll 1
+#pragma unroll kMatchUnroll
       for (uint32_t i = 0; i < nw; ++i) {
         const uint32_t nxt = lds32(p + 4u * i + 4u);
         uint32_t v = __funnelshift_r(prev, nxt, sh);
@@ -1173,13 +1177,14 @@ __device__ __forceinline__ void bulk16(const uint4 r, int lane, uint32_t t0, uin
 // shift by the source's misalignment -- and up to three bytes end the run.  Against os_run_f this leaves out the two
 // os_chunk passes (60-65 instructions each) at the ends of every run.  Reads up to 19 bytes past the run: inside the
 // staged tile or the buffer behind it, never used.
-// Used by the single-end launches (`cp` of emit_part).  Measured on one box, 10 M units, two builds each way
-// (BK_DEFINES="BK_EMIT_CP=0" is the stream writer everywhere): C1 1.657 / 1.647 -> 1.630 / 1.644 ms, C3 2.857 / 2.844 ->
-// 2.809 / 2.811 ms, C2 2.897 / 2.889 -> 2.898 / 2.872 ms.  In the paired kernels (C4 4.849 -> 4.886 ms) both writers would
-// be hot at once -- unchanged records' ragged ends go through the stream writer -- which costs more instruction-cache
-// misses than the shorter path saves, so those keep the stream writer alone.
+// Used by every launch, and for the ragged ends of the unchanged records' runs as well, so that the stream writer
+// (os_*) is not part of the default build's kernels at all: they are 4 KB smaller for it (the anchored single-end
+// kernel 41.2 -> 36.9 KB).  Measured on one box, 10 M units, BK_DEFINES="BK_EMIT_CP=0" (the stream writer) against the
+// default: C1 1.657 / 1.647 -> 1.624 / 1.646 ms, C3 2.857 / 2.844 -> 2.816 / 2.820 ms, C2 2.897 / 2.889 -> 2.897 / 2.893 ms,
+// C4 4.839 / 4.842 -> 4.786 / 4.794 ms.  (BK_EMIT_CP=1, cp_run in the single-end launches only: the paired kernels then
+// carry both writers, C4 4.814-4.886 ms.)
 #ifndef BK_EMIT_CP
-#define BK_EMIT_CP 1
+#define BK_EMIT_CP 2  // 0: the stream writer everywhere, 1: cp_run in the single-end launches only, 2: everywhere
 #endif
 constexpr bool kEmitCp = BK_EMIT_CP != 0;
 // `rot` (0, or 1 + a step): the 16-byte steps of a long run are taken from that one on, wrapping round -- lanes whose

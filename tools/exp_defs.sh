@@ -5,7 +5,7 @@ K='baseline_configs_small or ragged or runs_of_unchanged or derived or crlf or v
 for d in "$@"; do
   BK_DEFINES="$d" python -m barkit_b200.build --force >/dev/null 2>&1 || { echo "build failed: $d"; continue; }
   echo "== [$d]"
-  for c in C1 C3 C2 C4; do BK_ONLY=$c timeout -k 5 120 python tools/config_speed.py 10000000 2>&1 | tail -1; done
+  for c in ${BK_CFGS:-C1 C3 C2 C4}; do BK_ONLY=$c timeout -k 5 120 python tools/config_speed.py 10000000 2>&1 | tail -1; done
   [ -z "$BK_NOTEST" ] && timeout -k 5 300 python -m pytest tests/test_extract_gpu.py -m gpu -x -q -k "$K" 2>&1 | tail -3
 done
 python -m barkit_b200.build --force >/dev/null 2>&1
