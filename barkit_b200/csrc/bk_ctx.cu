@@ -176,6 +176,14 @@ size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_
   for (int m = 0; m < 2; ++m) in_cap[m] = out_cap[m] = 0;
   for (int m = 0; m < nm; ++m) {
     uint32_t growth = ctx->prog[m].present ? ctx->growth[m] + (uint32_t)par_growth(ctx->prog[m], maxrec[m]) : 0;
+    // A trimmed match takes its own bytes out of the seq and out of the qual line (parse.rs:138-148), so a record of a
+    // fixed-shape program grows by its header growth LESS twice the match length, if at all (C3: 67 - 70: the output
+    // tile needs no more room than the input records; every byte saved here is a byte for the input ring).
+    if (ctx->prog[m].present && !(ctx->flags & BK_FLAG_SKIP_TRIM) && !bk_free_shape(ctx->prog[m])) {
+      uint32_t net = 0;
+      for (const bk_devprog& v : ctx->var[m]) net = std::max(net, v.hdr_growth > 2 * v.total_len ? v.hdr_growth - 2 * v.total_len : 0u);
+      growth = net;
+    }
     in_cap[m] = (uint32_t)(((size_t)R * maxrec[m] + 32 + 15) & ~size_t(15));
     out_cap[m] = (uint32_t)(((size_t)R * ((size_t)maxrec[m] + growth + 2) + 32 + 15) & ~size_t(15));
     total += (size_t)stages * in_cap[m] + out_cap[m];

@@ -214,16 +214,18 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
   static_assert(ST % kScanWarps == 0 && ST % kFrontPairs == 0 && 4 + 2 * ST + (PAIRED ? 1 : 0) <= 16, "ring depth: a multiple of the scan / front warp counts, and 16 named barriers");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NM = PAIRED ? 2 : 1;
-  __shared__ __align__(8) uint64_t bar_full[2][ST], bar_empty[2][ST];
-  __shared__ __align__(16) uint8_t cls_tab[2][kTabBytes];  // per mate: class bits per byte, complement table, program
-  __shared__ int s_ms[kFrontPairs][2][2][32];  // [front pair][round parity][mate][lane]
+  __shared__ __align__(8) uint64_t bar_full[NM][ST], bar_empty[NM][ST];
+  // (static shared memory counts against the ring: a single-end launch carries one lookup block and no exchange buffer,
+  // 2.5 KB less per CTA, which is one more record per tile at four CTAs per SM)
+  __shared__ __align__(16) uint8_t cls_tab[NM][kTabBytes];  // per mate: class bits per byte, complement table, program
+  __shared__ int s_ms[PAIRED ? kFrontPairs : 1][2][PAIRED ? 2 : 1][PAIRED ? 32 : 1];  // [front pair][round parity][mate][lane]
   // search sharing (GENERAL, paired, exactly one mate unanchored): the searching mate's reads {seq, len, can}
   // for the other mate's front warp, and that warp's results for the upper half of the tile
   __shared__ uint32_t s_share[GENERAL && PAIRED ? kFrontPairs : 1][2][3][32];
   __shared__ int s_help[GENERAL && PAIRED ? kFrontPairs : 1][2][32];
   __shared__ int s_res[GENERAL && PAIRED ? kFrontPairs : 1][2][2][32];  // match_unanchored shared by two warps: [round parity][warp][lane]
   __shared__ TileMeta meta[NM][ST];
-  __shared__ uint4 run_desc[NM][32];  // copy descriptors of the tile's runs of unchanged records
+  __shared__ uint4 run_desc[NM][16];  // copy descriptors of the tile's runs of unchanged records (runs are at least one record apart: <= 16)
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
