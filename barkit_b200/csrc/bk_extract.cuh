@@ -175,8 +175,9 @@ constexpr uint32_t kEndTile = 0xFFFFFFFFu, kEndTile2 = 0xFFFFFFFEu;
 constexpr uint32_t kNotKept = 0xFFFFFFFFu;
 
 struct TileMeta {  // hand-over between the roles, one per (mate, stage); SoA so lanes do not conflict
-  uint32_t beg[32], end[32];  // record bounds, shared-memory addresses (loader)
-  uint32_t head_len[32], seq[32], seq_len[32], qual[32], qual_len_fast[32];  // (front)
+  // (every array here is shared memory the ring does not get: bounds as 33 starts, the two line lengths in one word)
+  uint32_t beg[33];  // record bounds, shared-memory addresses: record i is [beg[i], beg[i + 1]) (loader)
+  uint32_t head_len_fast[32], seq[32], lens[32], qual[32];  // head_len | fast << 31, seq_len | qual_len << 16 (front)
   int32_t ms[32];
   uint32_t ooff[32];  // record's offset inside the tile's output, kNotKept if dropped
   uint32_t tile;      // kEndTile terminates the consumers (loader)
@@ -320,8 +321,8 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         const uint32_t bytes = ((oem + 15u) & ~15u) - gbase;
         const bool too_big = bytes > P.in_cap[mm];  // host sized the ring from max_rec_bytes
         const uint32_t in_s = smem_base + (mm ? ST * P.in_cap[0] : 0) + s * P.in_cap[mm];
-        tm.beg[lane] = in_s + (om - gbase);
-        tm.end[lane] = in_s + (onext - gbase);
+        if (lane < (int)nrec) tm.beg[lane] = in_s + (om - gbase);
+        if (lane == (int)nrec - 1) tm.beg[nrec] = in_s + (onext - gbase);
         if (lane == 0) {
           tm.tile = tile;
           tm.nrec = nrec;
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       int ms = -1;
       if (!too_big) {
         // ---- parse + match (lane per record) ---------------------------------------------------
-        if (active) rv = parse_record(tm.beg[lane], tm.end[lane]);
+        if (active) rv = parse_record(tm.beg[lane], tm.beg[lane + 1]);
         __syncwarp();
         if (m == 0) { EVT(tile, 4) }
         const bool can = active && pg.present && rv.qual_len == rv.seq_len;  // unequal lengths never leave bk_tokenize
@@ -492,11 +493,10 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
       n_matched += active && ms >= 0;
 
       // ---- hand the slot to the scan and back warps ---------------------------------------------------
-      tm.head_len[lane] = rv.head_len;
+      tm.head_len_fast[lane] = rv.head_len | (rv.fast << 31);
       tm.seq[lane] = rv.seq;
-      tm.seq_len[lane] = rv.seq_len;
+      tm.lens[lane] = rv.seq_len | (rv.qual_len << 16);  // (a staged record is < 64 KiB: the ring holds four tiles in 200 KiB)
       tm.qual[lane] = rv.qual;
-      tm.qual_len_fast[lane] = (rv.qual_len << 1) | rv.fast;
       tm.ms[lane] = ms;
       tm.ooff[lane] = keep ? incl - olen : kNotKept;
       if (lane == 0) tm.total = total;
@@ -569,14 +569,14 @@ __global__ void __launch_bounds__(cta_warps(PAIRED) * 32, PAIRED ? 2 : 4) extrac
         const bool kept = ooff != kNotKept;
         RecView rv;
         rv.beg = tm.beg[lane];
-        rv.end = tm.end[lane];
-        rv.head_len = tm.head_len[lane];
+        rv.end = tm.beg[lane + 1];
+        const uint32_t hf = tm.head_len_fast[lane], ln = tm.lens[lane];
+        rv.head_len = hf & 0x7FFFFFFFu;
+        rv.fast = hf >> 31;
         rv.seq = tm.seq[lane];
-        rv.seq_len = tm.seq_len[lane];
+        rv.seq_len = ln & 0xFFFFu;
         rv.qual = tm.qual[lane];
-        const uint32_t qf = tm.qual_len_fast[lane];
-        rv.qual_len = qf >> 1;
-        rv.fast = qf & 1u;
+        rv.qual_len = ln >> 16;
         const int msv = tm.ms[lane];
         const int ms = (VAR && msv >= 0) ? (msv & 0xFFFFFF) : msv;
         const bk_devprog& pe = (VAR && msv >= 0 && P.nvar[m] > 1u) ? P.vprog[m][msv >> 24] : pg;
