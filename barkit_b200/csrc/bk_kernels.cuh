@@ -1183,6 +1183,9 @@ __device__ __forceinline__ void bulk16(const uint4 r, int lane, uint32_t t0, uin
 // default: C1 1.657 / 1.647 -> 1.624 / 1.646 ms, C3 2.857 / 2.844 -> 2.816 / 2.820 ms, C2 2.897 / 2.889 -> 2.897 / 2.893 ms,
 // C4 4.839 / 4.842 -> 4.786 / 4.794 ms.  (BK_EMIT_CP=1, cp_run in the single-end launches only: the paired kernels then
 // carry both writers, C4 4.814-4.886 ms.)
+#ifndef BK_CP_ROT
+#define BK_CP_ROT 0
+#endif
 #ifndef BK_EMIT_CP
 #define BK_EMIT_CP 2  // 0: the stream writer everywhere, 1: cp_run in the single-end launches only, 2: everywhere
 #endif
@@ -1206,6 +1209,19 @@ __device__ __noinline__ void cp_run(uint32_t d, uint32_t s, uint32_t n, uint32_t
   const uint32_t sh = (s & 3u) * 8u;
   uint32_t prev = lds32(sp);
   uint32_t nw = n >> 2;
+#if BK_CP_ROT
+  // Bank-aware start steps.  A lane's loads at step t hit banks 4 * (group + t) + class + j (mod 32), group = bits 4..6
+  // and class = bits 2..3 of its source address: lanes of different classes never meet, and the (up to eight) lanes of
+  // one class that are dealt the start steps 0..7 relative to their groups never meet either -- the loads of a long run
+  // become conflict-free whatever the records' lengths (lane-per-record copying otherwise runs 2-3 ways conflicted:
+  // record starts are as good as random modulo 128).
+  if (nw >= 16u) {
+    const unsigned act = __activemask();
+    const unsigned same = __match_any_sync(act, (sp >> 2) & 3u);
+    const uint32_t rank = __popc(same & ((1u << (threadIdx.x & 31)) - 1u));
+    rot = 1u + ((rank - (sp >> 4)) & 7u);
+  }
+#endif
   if (rot != 0u && nw >= 8u) {  // each step reads the source word before it instead of carrying it over: any order will do
     const uint32_t nsteps = nw >> 2;
     uint32_t q = rot - 1u < nsteps ? rot - 1u : 0u;

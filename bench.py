@@ -291,10 +291,11 @@ def kernel_name(paired, one_pattern, general):
         return ("bk::extract_kernel<PAIRED=false, GENERAL=%s> on the pattern's mate + bk::compact_kernel on the other"
                 % ("true" if general else "false"))
     if paired and general:
-        # two patterns, one of them needs a search: match_kernel on that mate, then one single-end extract launch per
-        # mate (the searched mate's takes its matches from the table); timed together
-        return ("bk::match_kernel on the searched mate + bk::extract_kernel<PAIRED=false, GENERAL=false> on the anchored "
-                "mate + bk::extract_kernel<PAIRED=false, TABLE=true> on the searched mate")
+        # two patterns, one of them needs a search: match_kernel on that mate, then ONE paired extract launch in table
+        # form (the searched mate's front warps read its matches from the table, the anchored mate matches for itself)
+        # and a one-thread merge of the matchers' error bits; timed together
+        return ("bk::match_kernel on the searched mate + bk::extract_kernel<PAIRED=true, GENERAL=false, TABLE=true> on both "
+                "mates (+ merge_error_kernel)")
     return "bk::extract_kernel<PAIRED=%s, GENERAL=%s>" % ("true" if paired else "false", "true" if general else "false")
 
 
