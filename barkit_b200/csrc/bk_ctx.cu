@@ -179,7 +179,7 @@ size_t smem_for(const bk_ctx* ctx, uint32_t R, const uint32_t maxrec[2], uint32_
     // A trimmed match takes its own bytes out of the seq and out of the qual line (parse.rs:138-148), so a record of a
     // fixed-shape program grows by its header growth LESS twice the match length, if at all (C3: 67 - 70: the output
     // tile needs no more room than the input records; every byte saved here is a byte for the input ring).
-    if (ctx->prog[m].present && !(ctx->flags & BK_FLAG_SKIP_TRIM) && !bk_free_shape(ctx->prog[m])) {
+    if (ctx->prog[m].present && !(ctx->flags & BK_FLAG_SKIP_TRIM) && !bk_free_shape(ctx->prog[m]) && !ctx->var[m].empty()) {
       uint32_t net = 0;
       for (const bk_devprog& v : ctx->var[m]) net = std::max(net, v.hdr_growth > 2 * v.total_len ? v.hdr_growth - 2 * v.total_len : 0u);
       growth = net;

@@ -642,6 +642,32 @@ def test_long_records_through_match_kernel():
         assert (o1, o2) == bo.extract_pe(fq1, fq2, p1, p2, 1)
 
 
+@pytest.mark.parametrize("skip", [False, True])
+def test_output_tile_holds_records_that_grow(skip):
+    """The shared-memory output tile is sized by what a record can grow to: header growth less twice the match length
+    when the match is trimmed out of the seq and qual lines (parse.rs:138-148), the whole header growth with -s.
+    Patterns whose captures make up the whole match grow every record (3 x (4 + 2 x 20) - 2 x 60 = +12 bytes trimmed,
+    +132 with -s); equal-length reads fill every tile to its bound, single-end and as either mate of a pair."""
+    p = "^(?P<UMI>[ATGCN]{20})(?P<CB>[ATGCN]{20})(?P<SB>[ATGCN]{20})"
+    rnd = random.Random(31)
+    n = 3000
+    recs1, recs2 = [], []
+    for i in range(n):
+        L = 61 if i % 97 else 59          # (a few reads too short to match: dropped / kept unchanged)
+        s1 = bytes(rnd.choice(b"ACGT") for _ in range(L))
+        s2 = bytes(rnd.choice(b"ACGTN") for _ in range(L))
+        h = b"r%06d" % i
+        recs1.append(b"@" + h + b"\n" + s1 + b"\n+\n" + _qual(L) + b"\n")
+        recs2.append(b"@" + h + b"\n" + s2 + b"\n+\n" + _qual(L, 40) + b"\n")
+    fq1, fq2 = b"".join(recs1), b"".join(recs2)
+    out, res = run_se(fq1, p, 0, skip=skip)
+    assert out == bo.extract_se(fq1, p, 0, skip_trimming=skip)
+    assert res.n_out == n - len(range(0, n, 97))
+    for p1, p2 in ((p, None), (None, p), (p, p)):
+        o1, o2, _ = run_pe(fq1, fq2, p1, p2, 0, skip=skip)
+        assert (o1, o2) == bo.extract_pe(fq1, fq2, p1, p2, 0, skip_trimming=skip)
+
+
 def test_output_capacity_error_is_reported():
     ctx = make_ctx("^(?P<UMI>[ATGCN]{12})")
     fq = bksyn.generate(bksyn.CONFIGS["C1"], 1, 0, 1000)
