@@ -14,7 +14,7 @@ for name, k in (("C1", 1), ("C2", 1), ("C3", 1), ("C4", 0), ("C4", 1), ("C4", 2)
     p1, p2, paired = CONFIG_PATTERNS[name]
     prog1 = _lib.Program(p1, k) if p1 else None
     prog2 = _lib.Program(p2, k) if p2 else None
-    ctx = _lib.Context(prog1, prog2, paired=paired)
+    ctx = _lib.Context(prog1, prog2, paired=paired, extra_flags=int(os.environ.get("BK_CTX_FLAGS", "0")))  # e.g. 256: BK_FLAG_SPLIT_TWO_PATTERNS
     cfg = lib_syn_config(name)
     ms = []
     for mate in ((1, 2) if paired else (1,)):
